@@ -1,0 +1,161 @@
+/* mbexwn.h -- C ABI of the B200-native MBExWN mel-inversion forward pass.
+ *
+ * Drop-in boundary for ONE path of roebel/MBExWN_Vocoder: MELInverter.synth_from_mel
+ * (MBExWN_NVoc/mel_inverter.py:151-154) -> PaNWaveNet.infer (vocoder/model/wavegen_1d.py:483-526)
+ * -> MBExWN.call (vocoder/model/custom_pulsed_generator.py:556-771).  The reference has no native layer
+ * (it is 100 % Python over TensorFlow), so each entry point names the Python interface it stands in for.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no framework types; every function returns 0 on success or a negative
+ *     mbexwn_status code, with a message available from mbexwn_last_error().
+ *   - the library never allocates device memory after mbexwn_create(): the caller (PyTorch on the Python
+ *     side) owns weights, inputs, outputs and one workspace buffer sized by mbexwn_workspace_bytes().
+ *   - a handle is bound to the CUDA device that is current in mbexwn_create(); calls on one handle are
+ *     serialised on the caller's stream.  One handle per GPU; no global state.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns MBEXWN_ERR_CUDA.
+ *
+ * Batch layout ("padded frame grid"): utterances are concatenated in time with `halo_frames` all-zero guard
+ * frames before the first, between neighbours and after the last one.  frame_utt[f] = utterance index of padded
+ * frame f or -1 for guard frames; utt_begin/utt_end = [begin, end) padded-frame range per utterance.  Every
+ * buffer at every rate uses this grid: row r at R rows per frame belongs to padded frame r / R.
+ */
+#ifndef MBEXWN_H_
+#define MBEXWN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBEXWN_ABI_VERSION 1
+#define MBEXWN_MAX_LAYERS 64
+#define MBEXWN_MAX_OPS 32
+
+typedef struct mbexwn_handle_s* mbexwn_handle_t;
+
+enum mbexwn_status {
+    MBEXWN_OK = 0,
+    MBEXWN_ERR_INVALID = -1,   /* bad argument / inconsistent config   (Python: RuntimeError / ValueError) */
+    MBEXWN_ERR_MISSING = -2,   /* a tensor was not registered           (Python: KeyError)                */
+    MBEXWN_ERR_CUDA = -3,      /* CUDA runtime / driver failure         (Python: RuntimeError)            */
+    MBEXWN_ERR_UNSUPPORTED = -4 /* configuration outside the built path (Python: NotImplementedError)     */
+};
+
+/* precision of the WaveNet contractions */
+enum mbexwn_precision {
+    MBEXWN_PREC_FP32_SIMT = 0,  /* fp32 FMA on CUDA cores: bit-for-bit the reference's arithmetic type          */
+    MBEXWN_PREC_BF16X3 = 1,     /* tcgen05 bf16 with hi/lo operand split (3 products), fp32 accumulate in TMEM */
+    MBEXWN_PREC_BF16 = 2        /* tcgen05 bf16 operands, fp32 accumulate                                      */
+};
+
+/* One step of a mel-rate conv sub-net (generate_subnet_from_specs, custom_pulsed_generator.py:38-148) with the
+ * TFPad1d layer folded into the conv and the activation fused behind the op. */
+typedef struct {
+    int32_t kind;        /* 0 = conv1d, 1 = linear interpolation */
+    int32_t k, cin, cout, dilation, pad_l, pad_r, pad_mode; /* conv; pad_mode 0 zero, 1 symmetric, 2 edge */
+    int32_t subpixel;    /* depth-to-time unfold factor of the conv output (conv_layers.py:250-255) */
+    int32_t up;          /* interpolation factor (kind 1) */
+    int32_t act;         /* 0 none, 1 PReLU, 2 LeakyReLU, 3 soft-sigmoid + F0 affine */
+    int32_t act_channels;
+    int32_t rate_in, rate_out, ch_out;
+    char name[96];       /* layer name: tensors <name>/W (k,cin,cout) and <name>/b */
+    char act_name[96];   /* PReLU tensor <act_name>/alpha */
+} mbexwn_op_t;
+
+/* Flat model description == the keyword arguments of MBExWN.__init__ that matter at inference
+ * (custom_pulsed_generator.py:155-230) after the rate algebra of :256-267 and :459-488. */
+typedef struct {
+    int32_t abi_version;
+    int32_t sample_rate, hop, mel_channels;
+    int32_t pulse_per_frame;    /* spect_to_pulse_upsampling_factor */
+    int32_t steps_per_frame;    /* WaveNet rows per mel frame */
+    int32_t pulse_channels, subbands;
+    float pulse_rate, f0_min, f0_max, f0_span /* float(f0_max - f0_min) */, noise_sigma, leaky_alpha;
+    int32_t n_pp_ops, n_ps_ops;
+    mbexwn_op_t pp_ops[MBEXWN_MAX_OPS];     /* F0 sub-net  ("PulsPar") */
+    mbexwn_op_t ps_ops[MBEXWN_MAX_OPS];     /* VTF sub-net ("PS")      */
+    /* WaveNetAE (custom_AE_layers.py:114-346) */
+    int32_t wn_c, wn_cin, wn_cout, wn_layers, wn_k, wn_gate;
+    int32_t wn_cond_k, wn_cond_conv_up, wn_cond_lin_up;
+    int32_t wn_dilations[MBEXWN_MAX_LAYERS];
+    char wn_name[96];           /* tensors <wn_name>/start/W, /cond_/W, /conv1D_<i>/W, /res_skip_<i>/W, /end/W (+ /b) */
+    char post_name[96];         /* wn_post_net 1x1 (custom_pulsed_generator.py:490-493) */
+    /* spectral envelope / STFT (custom_pulsed_generator.py:391-400, :793-836) */
+    int32_t n_ceps, stft_win, fft_size, n_lifters, n_smooth;
+    float filter_max_log_range; /* 0 => exp(L) without the tanh limiter */
+    /* wavetable (tf_wavetable.py:182-307) */
+    int32_t wt_n_period, wt_n_tables;
+    float wt_nominal_f0, wt_min_transposition, wt_max_transposition, wt_grid_norm;
+    int32_t cumsum_chunk;       /* 1000 (tf_wavetable.py:429) */
+    /* PQMF polyphase bank (tf_preprocess.py:120-161, :208-226) */
+    int32_t pqmf_q, pqmf_back;
+    int32_t halo_frames;        /* guard frames between utterances */
+} mbexwn_config_t;
+
+/* One batch on the padded frame grid; all pointers are DEVICE pointers. */
+typedef struct {
+    int32_t n_utt;
+    int32_t n_frames;               /* padded frames, guards included */
+    int32_t n_chunks;               /* total cumsum chunks = chunk_first[n_utt] */
+    const int32_t* frame_utt;       /* [n_frames] */
+    const int32_t* utt_begin;       /* [n_utt] */
+    const int32_t* utt_end;         /* [n_utt] */
+    const int32_t* chunk_first;     /* [n_utt + 1] exclusive scan of ceil(T_u * pulse_per_frame / cumsum_chunk) */
+    const float* mel;               /* (n_frames, mel_channels) scaled log-mel, guard frames zero */
+    const float* noise;             /* (n_frames * steps_per_frame) N(0,1) draws, or NULL => in-kernel Philox(seed) */
+    const float* f0_override;       /* (n_frames * pulse_per_frame) Hz, or NULL => F0 sub-net (infer_components, wavegen_1d.py:528-557) */
+    uint64_t seed;
+    float* out;                     /* (n_frames * hop) waveform on the grid */
+} mbexwn_batch_t;
+
+/* ---- life cycle: stands in for create_model + build_model + load_weights (mel_inverter.py:184-210) ---- */
+int mbexwn_abi_version(void);
+int mbexwn_create(const mbexwn_config_t* cfg, mbexwn_handle_t* out);
+void mbexwn_destroy(mbexwn_handle_t h);
+const char* mbexwn_last_error(mbexwn_handle_t h);
+
+/* Register a device tensor by name (folded weights, biases, PReLU slopes, DSP constants).  The pointer must stay
+ * valid for the life of the handle.  Names: see mbexwn_op_t / mbexwn_config_t, plus the constants "wavetable"
+ * (n_period+1, n_tables), "pqmf_poly" (Q, S, S), "window" (win), "inv_window" (win), "twiddle" (fft/2, 2),
+ * "lifters" (n_lifters, n_ceps), "lifter_grid" (n_lifters), "f0_smooth" (n_smooth), "end_post/W" (wn_c, subbands),
+ * "end_post/b" (subbands). */
+int mbexwn_set_tensor(mbexwn_handle_t h, const char* name, const void* dev_ptr, size_t n_bytes);
+
+/* ---- forward: stands in for MELInverter.synth_from_mel / PaNWaveNet.infer ---- */
+size_t mbexwn_workspace_bytes(mbexwn_handle_t h, int32_t n_frames, int32_t n_chunks, int32_t precision);
+int mbexwn_forward(mbexwn_handle_t h, const mbexwn_batch_t* batch, int32_t precision,
+                   void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Same call with HOST buffers (pinned for asynchronous copies): copies mel (and noise if given) host->device into
+ * the staging pointers of `batch`, runs the forward, copies the waveform device->host and synchronises the stream.
+ * mel_host: (n_frames, mel_channels); out_host: (n_frames * hop). */
+int mbexwn_forward_host(mbexwn_handle_t h, const mbexwn_batch_t* batch, int32_t precision,
+                        const float* mel_host, const float* noise_host, float* out_host,
+                        void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Per-stage taps (return_F0 / return_components of PaNWaveNet.infer, custom_pulsed_generator.py:756-771, plus the
+ * stage boundaries of SURVEY.md 8a): after mbexwn_forward the named intermediate lives in the workspace at
+ * [*offset_bytes, *offset_bytes + *n_bytes).  Names: "F0", "phase", "index", "pulse", "wn_in", "cond", "h", "skip",
+ * "subbands", "excitation", "ceps", "frames", "vtf", "lifter_index". */
+int mbexwn_tap(mbexwn_handle_t h, const char* name, int32_t n_frames, int32_t n_chunks, int32_t precision,
+               size_t* offset_bytes, size_t* n_bytes);
+
+/* Number of kernel launches issued by the last mbexwn_forward on this handle. */
+int mbexwn_last_launch_count(mbexwn_handle_t h);
+
+/* Options: "debug_taps" (default 1): keep the phase / index / pulse / vtf / lifter_index taps in the workspace. */
+int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value);
+
+/* ---- single kernels on caller-provided buffers (stage-level parity tests; same kernels the forward uses) ---- */
+int mbexwn_k_conv1d(mbexwn_handle_t h, const mbexwn_batch_t* grid, const mbexwn_op_t* op, int32_t rate,
+                    const float* x, const float* w, const float* bias, const float* alpha, float* out,
+                    void* cuda_stream);
+int mbexwn_k_lininterp(mbexwn_handle_t h, const mbexwn_batch_t* grid, const mbexwn_op_t* op,
+                       const float* x, const float* alpha, float* out, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBEXWN_H_ */

@@ -1,0 +1,440 @@
+// C ABI of the MBExWN forward pass (include/mbexwn.h): handle, tensor registry, workspace carving and the stage
+// orchestration of MBExWN.call (custom_pulsed_generator.py:556-771) on the padded frame grid.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mbexwn.h"
+#include "kernels.cuh"
+#include "wn_tc.cuh"
+
+struct mbexwn_handle_s {
+    mbexwn_config_t cfg;
+    int device = 0;
+    std::map<std::string, std::pair<const void*, size_t>> tensors;
+    std::string error;
+    int launches = 0;
+    int debug_taps = 1;
+    mbx::WnTcState tc;
+};
+
+namespace mbx {
+
+int set_error(mbexwn_handle_t h, const char* what, cudaError_t e) {
+    if (h) {
+        h->error = std::string(what) + ": " + cudaGetErrorString(e);
+    }
+    return MBEXWN_ERR_CUDA;
+}
+
+static int fail(mbexwn_handle_t h, int code, const std::string& msg) {
+    if (h) h->error = msg;
+    return code;
+}
+
+// ---- workspace ----------------------------------------------------------------------------------------
+struct Slot {
+    size_t off = 0, bytes = 0;
+};
+
+struct Workspace {
+    std::map<std::string, Slot> slots;
+    size_t total = 0;
+    void add(const std::string& name, size_t bytes) {
+        size_t aligned = (bytes + 1023) & ~size_t(1023);
+        slots[name] = Slot{total, bytes};
+        total += aligned;
+    }
+};
+
+static size_t subnet_scratch_elems(const mbexwn_op_t* ops, int n, int n_mel) {
+    size_t m = (size_t)n_mel;
+    for (int i = 0; i < n; ++i) {
+        size_t a = (size_t)ops[i].rate_out * ops[i].ch_out;
+        if (a > m) m = a;
+    }
+    return m;
+}
+
+static Workspace carve(const mbexwn_config_t& c, int64_t F, int64_t n_chunks, int precision, int debug_taps) {
+    Workspace w;
+    const size_t f4 = sizeof(float);
+    const int64_t rows = F * c.steps_per_frame;
+    size_t sn = subnet_scratch_elems(c.pp_ops, c.n_pp_ops, c.mel_channels);
+    size_t sn2 = subnet_scratch_elems(c.ps_ops, c.n_ps_ops, c.mel_channels);
+    if (sn2 > sn) sn = sn2;
+    w.add("sn_a", (size_t)F * sn * f4);
+    w.add("sn_b", (size_t)F * sn * f4);
+    w.add("F0", (size_t)F * c.pulse_per_frame * f4);
+    w.add("cum", (size_t)F * c.pulse_per_frame * f4);
+    w.add("chunk_off", (size_t)(n_chunks + 1) * f4);
+    if (debug_taps) {
+        w.add("phase", (size_t)F * c.pulse_per_frame * f4);
+        w.add("index", (size_t)F * c.pulse_per_frame * sizeof(int32_t));
+        w.add("pulse", (size_t)F * c.pulse_per_frame * f4);
+        w.add("vtf", (size_t)F * (c.fft_size / 2 + 1) * 2 * f4);
+        w.add("lifter_index", (size_t)F * sizeof(int32_t));
+    }
+    w.add("wn_in", (size_t)rows * c.wn_cin * f4);
+    w.add("cond", (size_t)F * c.wn_cond_conv_up * 2 * c.wn_c * f4);
+    w.add("skip", (size_t)rows * c.wn_c * f4);
+    if (precision == MBEXWN_PREC_FP32_SIMT) {
+        w.add("h", (size_t)rows * c.wn_c * f4);
+        w.add("z", (size_t)rows * 2 * c.wn_c * f4);
+        w.add("act", (size_t)rows * c.wn_c * f4);
+        w.add("rs", (size_t)rows * 2 * c.wn_c * f4);
+    } else {
+        wn_tc_carve(c, rows, precision, [&](const char* n, size_t b) { w.add(n, b); });
+    }
+    w.add("subbands", (size_t)rows * c.subbands * f4);
+    w.add("excitation", (size_t)F * c.hop * f4);
+    w.add("ceps", (size_t)F * c.n_ceps * f4);
+    w.add("frames", (size_t)F * c.stft_win * f4);
+    return w;
+}
+
+struct Ctx {
+    mbexwn_handle_t h;
+    const mbexwn_batch_t* b;
+    FrameGrid g;
+    Workspace ws;
+    char* base;
+    cudaStream_t s;
+    template <class T>
+    T* p(const char* name) {
+        auto it = ws.slots.find(name);
+        return it == ws.slots.end() ? nullptr : reinterpret_cast<T*>(base + it->second.off);
+    }
+};
+
+static const float* tensor(mbexwn_handle_t h, const std::string& name, size_t min_bytes, int* rc) {
+    auto it = h->tensors.find(name);
+    if (it == h->tensors.end()) {
+        *rc = fail(h, MBEXWN_ERR_MISSING, "tensor not registered: " + name);
+        return nullptr;
+    }
+    if (it->second.second < min_bytes) {
+        *rc = fail(h, MBEXWN_ERR_INVALID, "tensor too small: " + name);
+        return nullptr;
+    }
+    return reinterpret_cast<const float*>(it->second.first);
+}
+
+static ConvArgs conv_args(const mbexwn_config_t& c, const mbexwn_op_t& op, int rate, long long rows,
+                          const float* x, const float* w, const float* bias, const float* alpha, float* out) {
+    ConvArgs a{};
+    a.x = x; a.ld_x = op.cin; a.w = w; a.bias = bias; a.alpha = alpha; a.out = out; a.ld_out = op.cout;
+    a.rows = rows; a.rate = rate;
+    a.k = op.k; a.cin = op.cin; a.cout = op.cout; a.dilation = op.dilation > 0 ? op.dilation : 1;
+    a.pad_l = op.pad_l; a.pad_mode = op.pad_mode;
+    a.act = op.act; a.act_mod = op.act_channels > 0 ? op.act_channels : op.cout;
+    a.leaky = c.leaky_alpha; a.a0 = c.f0_span; a.a1 = c.f0_min;
+    return a;
+}
+
+// Run one mel-rate sub-net program; the last op writes into `final_out`.
+static int run_subnet(Ctx& cx, const mbexwn_op_t* ops, int n_ops, const float* input, float* final_out) {
+    mbexwn_handle_t h = cx.h;
+    const mbexwn_config_t& c = h->cfg;
+    float* bufs[2] = {cx.p<float>("sn_a"), cx.p<float>("sn_b")};
+    const float* cur = input;
+    int flip = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        const mbexwn_op_t& op = ops[i];
+        float* out = (i == n_ops - 1) ? final_out : bufs[flip];
+        int rc = 0;
+        const float* alpha = nullptr;
+        if (op.act == ACT_PRELU) {
+            alpha = tensor(h, std::string(op.act_name) + "/alpha", (size_t)op.act_channels * 4, &rc);
+            if (!alpha) return rc;
+        }
+        if (op.kind == 0) {
+            const float* w = tensor(h, std::string(op.name) + "/W", (size_t)op.k * op.cin * op.cout * 4, &rc);
+            if (!w) return rc;
+            const float* bias = tensor(h, std::string(op.name) + "/b", (size_t)op.cout * 4, &rc);
+            if (!bias) return rc;
+            ConvArgs a = conv_args(c, op, op.rate_in, (long long)cx.g.n_frames * op.rate_in, cur, w, bias, alpha, out);
+            MBX_CUDA_CHECK(launch_conv1d(a, cx.g, cx.s));
+        } else {
+            LinInterpArgs a{};
+            a.x = cur; a.out = out; a.rows_in = (long long)cx.g.n_frames * op.rate_in; a.rate_in = op.rate_in;
+            a.ch = op.ch_out; a.up = op.up; a.act = op.act; a.alpha = alpha; a.leaky = c.leaky_alpha;
+            a.a0 = c.f0_span; a.a1 = c.f0_min;
+            MBX_CUDA_CHECK(launch_lininterp(a, cx.g, cx.s));
+        }
+        h->launches++;
+        cur = out;
+        flip ^= 1;
+    }
+    return MBEXWN_OK;
+}
+
+static mbexwn_op_t simple_conv(int k, int cin, int cout, int dil, int pad_l) {
+    mbexwn_op_t op{};
+    op.kind = 0; op.k = k; op.cin = cin; op.cout = cout; op.dilation = dil; op.pad_l = pad_l; op.pad_r = pad_l;
+    op.pad_mode = PAD_ZERO; op.act = ACT_NONE; op.act_channels = cout; op.subpixel = 1;
+    return op;
+}
+
+static int wavenet_fp32(Ctx& cx) {
+    mbexwn_handle_t h = cx.h;
+    const mbexwn_config_t& c = h->cfg;
+    const long long rows = (long long)cx.g.n_frames * c.steps_per_frame;
+    const std::string n = c.wn_name;
+    int rc = 0;
+    float *hbuf = cx.p<float>("h"), *z = cx.p<float>("z"), *act = cx.p<float>("act"), *rs = cx.p<float>("rs");
+    float* skip = cx.p<float>("skip");
+    const float* cond = cx.p<float>("cond");
+    {   // start 1x1 (custom_AE_layers.py:280)
+        const float* w = tensor(h, n + "/start/W", (size_t)c.wn_cin * c.wn_c * 4, &rc); if (!w) return rc;
+        const float* b = tensor(h, n + "/start/b", (size_t)c.wn_c * 4, &rc); if (!b) return rc;
+        mbexwn_op_t op = simple_conv(1, c.wn_cin, c.wn_c, 1, 0);
+        MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op, c.steps_per_frame, rows, cx.p<float>("wn_in"), w, b, nullptr, hbuf), cx.g, cx.s));
+        h->launches++;
+    }
+    for (int i = 0; i < c.wn_layers; ++i) {
+        const int d = c.wn_dilations[i];
+        const int n_rs = (i < c.wn_layers - 1) ? 2 * c.wn_c : c.wn_c;
+        const std::string li = std::to_string(i);
+        const float* w = tensor(h, n + "/conv1D_" + li + "/W", (size_t)c.wn_k * c.wn_c * 2 * c.wn_c * 4, &rc); if (!w) return rc;
+        const float* b = tensor(h, n + "/conv1D_" + li + "/b", (size_t)2 * c.wn_c * 4, &rc); if (!b) return rc;
+        const float* rw = tensor(h, n + "/res_skip_" + li + "/W", (size_t)c.wn_c * n_rs * 4, &rc); if (!rw) return rc;
+        const float* rb = tensor(h, n + "/res_skip_" + li + "/b", (size_t)n_rs * 4, &rc); if (!rb) return rc;
+        mbexwn_op_t op = simple_conv(c.wn_k, c.wn_c, 2 * c.wn_c, d, (c.wn_k - 1) * d / 2);
+        MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op, c.steps_per_frame, rows, hbuf, w, b, nullptr, z), cx.g, cx.s));
+        GateArgs ga{z, cond, act, rows, c.steps_per_frame, c.wn_c, c.wn_cond_lin_up, c.wn_gate};
+        MBX_CUDA_CHECK(launch_gate(ga, cx.g, cx.s));
+        mbexwn_op_t op2 = simple_conv(1, c.wn_c, n_rs, 1, 0);
+        MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op2, c.steps_per_frame, rows, act, rw, rb, nullptr, rs), cx.g, cx.s));
+        ResSkipArgs ra{rs, hbuf, skip, rows, c.steps_per_frame, c.wn_c, n_rs, i == 0 ? 1 : 0};
+        MBX_CUDA_CHECK(launch_resskip(ra, cx.g, cx.s));
+        h->launches += 4;
+    }
+    return MBEXWN_OK;
+}
+
+static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precision, void* workspace,
+                        size_t workspace_bytes, cudaStream_t s) {
+    const mbexwn_config_t& c = h->cfg;
+    if (!b || b->n_frames <= 0 || b->n_utt <= 0) return fail(h, MBEXWN_ERR_INVALID, "empty batch");
+    if (!b->frame_utt || !b->utt_begin || !b->utt_end || !b->chunk_first || !b->mel || !b->out)
+        return fail(h, MBEXWN_ERR_INVALID, "batch has null pointers");
+    if (precision < MBEXWN_PREC_FP32_SIMT || precision > MBEXWN_PREC_BF16)
+        return fail(h, MBEXWN_ERR_INVALID, "unknown precision");
+    Ctx cx{h, b, FrameGrid{b->frame_utt, b->utt_begin, b->utt_end, b->n_frames, b->n_utt},
+           carve(c, b->n_frames, b->n_chunks, precision, h->debug_taps), reinterpret_cast<char*>(workspace), s};
+    if (!workspace || workspace_bytes < cx.ws.total) return fail(h, MBEXWN_ERR_INVALID, "workspace too small");
+    h->launches = 0;
+    int rc = 0;
+    const long long rows = (long long)b->n_frames * c.steps_per_frame;
+
+    // (1) F0 sub-net (generate_f0, custom_pulsed_generator.py:773-791)
+    const float* f0 = b->f0_override;
+    if (!f0) {
+        rc = run_subnet(cx, c.pp_ops, c.n_pp_ops, b->mel, cx.p<float>("F0"));
+        if (rc) return rc;
+        f0 = cx.p<float>("F0");
+    } else {
+        MBX_CUDA_CHECK(cudaMemcpyAsync(cx.p<float>("F0"), f0, (size_t)b->n_frames * c.pulse_per_frame * 4,
+                                       cudaMemcpyDeviceToDevice, s));
+    }
+
+    // (2) excitation generator head (generate_excitation, :886-906)
+    {
+        ExcitationArgs a{};
+        a.f0 = f0; a.noise = b->noise; a.seed = b->seed;
+        a.tables = tensor(h, "wavetable", (size_t)(c.wt_n_period + 1) * c.wt_n_tables * 4, &rc); if (!a.tables) return rc;
+        a.n_period = c.wt_n_period; a.n_tables = c.wt_n_tables; a.pulse_rate = c.pulse_rate;
+        a.nominal_f0 = c.wt_nominal_f0; a.min_tr = c.wt_min_transposition; a.max_tr = c.wt_max_transposition;
+        a.grid_norm = c.wt_grid_norm; a.sigma = c.noise_sigma;
+        a.pulse_per_frame = c.pulse_per_frame; a.steps_per_frame = c.steps_per_frame; a.pulse_channels = c.pulse_channels;
+        a.chunk = c.cumsum_chunk; a.cum = cx.p<float>("cum"); a.chunk_off = cx.p<float>("chunk_off");
+        a.chunk_first = b->chunk_first; a.wn_in = cx.p<float>("wn_in"); a.ld_wn_in = c.wn_cin;
+        a.phase_out = cx.p<float>("phase"); a.index_out = cx.p<int32_t>("index"); a.pulse_out = cx.p<float>("pulse");
+        MBX_CUDA_CHECK(launch_excitation(a, cx.g, b->n_chunks, s));
+        h->launches += 3;
+    }
+
+    // (3) conditioning conv at mel rate; the x10 linear interpolation is fused into the gate (custom_AE_layers.py:282-289)
+    {
+        const std::string n = std::string(c.wn_name) + "/cond_";
+        const int cout = 2 * c.wn_c * c.wn_cond_conv_up;
+        const float* w = tensor(h, n + "/W", (size_t)c.wn_cond_k * c.mel_channels * cout * 4, &rc); if (!w) return rc;
+        const float* bias = tensor(h, n + "/b", (size_t)cout * 4, &rc); if (!bias) return rc;
+        mbexwn_op_t op = simple_conv(c.wn_cond_k, c.mel_channels, cout, 1, (c.wn_cond_k - 1) / 2);
+        MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op, 1, b->n_frames, b->mel, w, bias, nullptr, cx.p<float>("cond")), cx.g, s));
+        h->launches++;
+    }
+
+    // (4) WaveNet (WaveNetAE.call, custom_AE_layers.py:273-346)
+    if (precision == MBEXWN_PREC_FP32_SIMT) {
+        rc = wavenet_fp32(cx);
+    } else {
+        rc = wn_tc_forward(h->tc, c, cx.g, precision, cx.p<float>("wn_in"), cx.p<float>("cond"), cx.p<float>("skip"),
+                           [&](const char* nm) { return (void*)cx.p<char>(nm); },
+                           [&](const std::string& nm, size_t bytes) { int r = 0; return (const void*)tensor(h, nm, bytes, &r); },
+                           s, &h->launches, &h->error);
+    }
+    if (rc) return rc;
+
+    // (5) end 1x1 and post 1x1 are both linear: one pre-multiplied C -> S matrix (custom_AE_layers.py:340,
+    //     custom_pulsed_generator.py:913-914), then PQMF synthesis (:920-921)
+    {
+        const float* w = tensor(h, "end_post/W", (size_t)c.wn_c * c.subbands * 4, &rc); if (!w) return rc;
+        const float* bias = tensor(h, "end_post/b", (size_t)c.subbands * 4, &rc); if (!bias) return rc;
+        mbexwn_op_t op = simple_conv(1, c.wn_c, c.subbands, 1, 0);
+        MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op, c.steps_per_frame, rows, cx.p<float>("skip"), w, bias, nullptr,
+                                               cx.p<float>("subbands")), cx.g, s));
+        PqmfArgs pa{};
+        pa.sub = cx.p<float>("subbands");
+        pa.poly = tensor(h, "pqmf_poly", (size_t)c.pqmf_q * c.subbands * c.subbands * 4, &rc); if (!pa.poly) return rc;
+        pa.out = cx.p<float>("excitation"); pa.rows = rows; pa.steps_per_frame = c.steps_per_frame;
+        pa.S = c.subbands; pa.Q = c.pqmf_q; pa.back = c.pqmf_back;
+        MBX_CUDA_CHECK(launch_pqmf(pa, cx.g, s));
+        h->launches += 2;
+    }
+
+    // (6) VTF sub-net -> cepstrum (generate_specenv, :793-799)
+    rc = run_subnet(cx, c.ps_ops, c.n_ps_ops, b->mel, cx.p<float>("ceps"));
+    if (rc) return rc;
+
+    // (7) STFT-domain filtering + overlap-add (:681-724, :801-836)
+    {
+        StftFilterArgs a{};
+        a.exc = cx.p<float>("excitation"); a.ceps = cx.p<float>("ceps"); a.f0 = f0;
+        if (c.n_lifters > 0) {
+            a.lifters = tensor(h, "lifters", (size_t)c.n_lifters * c.n_ceps * 4, &rc); if (!a.lifters) return rc;
+            a.lifter_grid = tensor(h, "lifter_grid", (size_t)c.n_lifters * 4, &rc); if (!a.lifter_grid) return rc;
+            a.f0_smooth = tensor(h, "f0_smooth", (size_t)c.n_smooth * 4, &rc); if (!a.f0_smooth) return rc;
+        }
+        a.n_lift = c.n_lifters; a.n_smooth = c.n_smooth; a.pulse_per_frame = c.pulse_per_frame;
+        a.window = tensor(h, "window", (size_t)c.stft_win * 4, &rc); if (!a.window) return rc;
+        a.inv_window = tensor(h, "inv_window", (size_t)c.stft_win * 4, &rc); if (!a.inv_window) return rc;
+        a.twiddle = reinterpret_cast<const float2*>(tensor(h, "twiddle", (size_t)c.fft_size * 4, &rc)); if (!a.twiddle) return rc;
+        a.frames_out = cx.p<float>("frames"); a.vtf_out = cx.p<float>("vtf"); a.lifter_index_out = cx.p<int32_t>("lifter_index");
+        a.n_frames = b->n_frames; a.hop = c.hop; a.win = c.stft_win; a.fft = c.fft_size; a.n_ceps = c.n_ceps;
+        a.max_log_range = c.filter_max_log_range;
+        MBX_CUDA_CHECK(launch_stft_filter(a, cx.g, s));
+        OlaArgs oa{cx.p<float>("frames"), b->out, b->n_frames, c.hop, c.stft_win};
+        MBX_CUDA_CHECK(launch_ola(oa, cx.g, s));
+        h->launches += 2;
+    }
+    return MBEXWN_OK;
+}
+
+}  // namespace mbx
+
+// ---- extern "C" ------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int mbexwn_abi_version(void) { return MBEXWN_ABI_VERSION; }
+
+int mbexwn_create(const mbexwn_config_t* cfg, mbexwn_handle_t* out) {
+    if (!cfg || !out) return MBEXWN_ERR_INVALID;
+    *out = nullptr;
+    if (cfg->abi_version != MBEXWN_ABI_VERSION) return MBEXWN_ERR_INVALID;
+    if (cfg->wn_layers < 1 || cfg->wn_layers > MBEXWN_MAX_LAYERS || cfg->n_pp_ops > MBEXWN_MAX_OPS ||
+        cfg->n_ps_ops > MBEXWN_MAX_OPS || cfg->n_pp_ops < 1 || cfg->n_ps_ops < 1)
+        return MBEXWN_ERR_INVALID;
+    if (cfg->steps_per_frame * cfg->subbands != cfg->hop) return MBEXWN_ERR_INVALID;
+    if (cfg->steps_per_frame * cfg->pulse_channels != cfg->pulse_per_frame) return MBEXWN_ERR_INVALID;
+    if (cfg->fft_size < cfg->stft_win || (cfg->fft_size & (cfg->fft_size - 1))) return MBEXWN_ERR_INVALID;
+    if (cfg->stft_win != 4 * cfg->hop) return MBEXWN_ERR_UNSUPPORTED;     // 4x overlap (wavegen_1d.py:592)
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return MBEXWN_ERR_CUDA;                          // no CPU fallback
+    mbexwn_handle_s* h = new mbexwn_handle_s();
+    h->cfg = *cfg;
+    h->device = dev;
+    *out = h;
+    return MBEXWN_OK;
+}
+
+void mbexwn_destroy(mbexwn_handle_t h) {
+    if (!h) return;
+    mbx::wn_tc_destroy(h->tc);
+    delete h;
+}
+
+const char* mbexwn_last_error(mbexwn_handle_t h) { return h ? h->error.c_str() : "null handle"; }
+
+int mbexwn_set_tensor(mbexwn_handle_t h, const char* name, const void* dev_ptr, size_t n_bytes) {
+    if (!h || !name || !dev_ptr) return MBEXWN_ERR_INVALID;
+    h->tensors[name] = std::make_pair(dev_ptr, n_bytes);
+    mbx::wn_tc_invalidate(h->tc);
+    return MBEXWN_OK;
+}
+
+size_t mbexwn_workspace_bytes(mbexwn_handle_t h, int32_t n_frames, int32_t n_chunks, int32_t precision) {
+    if (!h || n_frames <= 0) return 0;
+    return mbx::carve(h->cfg, n_frames, n_chunks, precision, h->debug_taps).total;
+}
+
+int mbexwn_forward(mbexwn_handle_t h, const mbexwn_batch_t* batch, int32_t precision, void* workspace,
+                   size_t workspace_bytes, void* cuda_stream) {
+    if (!h) return MBEXWN_ERR_INVALID;
+    return mbx::forward_impl(h, batch, precision, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int mbexwn_forward_host(mbexwn_handle_t h, const mbexwn_batch_t* batch, int32_t precision, const float* mel_host,
+                        const float* noise_host, float* out_host, void* workspace, size_t workspace_bytes,
+                        void* cuda_stream) {
+    if (!h || !batch || !mel_host || !out_host) return MBEXWN_ERR_INVALID;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const mbexwn_config_t& c = h->cfg;
+    MBX_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(batch->mel), mel_host,
+                                   (size_t)batch->n_frames * c.mel_channels * 4, cudaMemcpyHostToDevice, s));
+    if (noise_host && batch->noise)
+        MBX_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(batch->noise), noise_host,
+                                       (size_t)batch->n_frames * c.steps_per_frame * 4, cudaMemcpyHostToDevice, s));
+    int rc = mbx::forward_impl(h, batch, precision, workspace, workspace_bytes, s);
+    if (rc) return rc;
+    MBX_CUDA_CHECK(cudaMemcpyAsync(out_host, batch->out, (size_t)batch->n_frames * c.hop * 4, cudaMemcpyDeviceToHost, s));
+    MBX_CUDA_CHECK(cudaStreamSynchronize(s));
+    return MBEXWN_OK;
+}
+
+int mbexwn_tap(mbexwn_handle_t h, const char* name, int32_t n_frames, int32_t n_chunks, int32_t precision,
+               size_t* offset_bytes, size_t* n_bytes) {
+    if (!h || !name || !offset_bytes || !n_bytes) return MBEXWN_ERR_INVALID;
+    mbx::Workspace w = mbx::carve(h->cfg, n_frames, n_chunks, precision, h->debug_taps);
+    auto it = w.slots.find(name);
+    if (it == w.slots.end()) return mbx::fail(h, MBEXWN_ERR_MISSING, std::string("unknown tap: ") + name);
+    *offset_bytes = it->second.off;
+    *n_bytes = it->second.bytes;
+    return MBEXWN_OK;
+}
+
+int mbexwn_last_launch_count(mbexwn_handle_t h) { return h ? h->launches : 0; }
+
+int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value) {
+    if (!h || !name) return MBEXWN_ERR_INVALID;
+    if (!strcmp(name, "debug_taps")) { h->debug_taps = value ? 1 : 0; return MBEXWN_OK; }
+    return mbx::fail(h, MBEXWN_ERR_INVALID, std::string("unknown option: ") + name);
+}
+
+int mbexwn_k_conv1d(mbexwn_handle_t h, const mbexwn_batch_t* b, const mbexwn_op_t* op, int32_t rate, const float* x,
+                    const float* w, const float* bias, const float* alpha, float* out, void* cuda_stream) {
+    if (!h || !b || !op || !x || !w || !bias || !out) return MBEXWN_ERR_INVALID;
+    mbx::FrameGrid g{b->frame_utt, b->utt_begin, b->utt_end, b->n_frames, b->n_utt};
+    mbx::ConvArgs a = mbx::conv_args(h->cfg, *op, rate, (long long)b->n_frames * rate, x, w, bias, alpha, out);
+    MBX_CUDA_CHECK(mbx::launch_conv1d(a, g, reinterpret_cast<cudaStream_t>(cuda_stream)));
+    return MBEXWN_OK;
+}
+
+int mbexwn_k_lininterp(mbexwn_handle_t h, const mbexwn_batch_t* b, const mbexwn_op_t* op, const float* x,
+                       const float* alpha, float* out, void* cuda_stream) {
+    if (!h || !b || !op || !x || !out) return MBEXWN_ERR_INVALID;
+    mbx::FrameGrid g{b->frame_utt, b->utt_begin, b->utt_end, b->n_frames, b->n_utt};
+    mbx::LinInterpArgs a{};
+    a.x = x; a.out = out; a.rows_in = (long long)b->n_frames * op->rate_in; a.rate_in = op->rate_in; a.ch = op->ch_out;
+    a.up = op->up; a.act = op->act; a.alpha = alpha; a.leaky = h->cfg.leaky_alpha;
+    a.a0 = h->cfg.f0_span; a.a1 = h->cfg.f0_min;
+    MBX_CUDA_CHECK(mbx::launch_lininterp(a, g, reinterpret_cast<cudaStream_t>(cuda_stream)));
+    return MBEXWN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+// Glottal-pulse excitation generator: F0 -> phase velocity -> chunked cumulative phase -> wavetable lookup ->
+// F0-grid cross-fade -> (20T x 5) reshape + noise channel = WaveNet input.
+//
+// Reference: PulseWaveTable.call / stable_cumsum_and_wrap / _linear_lookup (tf_wavetable.py:429-492, :495-560,
+// :605-638) and the head of MBExWN.generate_excitation (custom_pulsed_generator.py:886-906).
+//
+// Bit-exactness contract (integer wavetable index): the reference accumulates float32 phase velocities
+// *sequentially* inside chunks of 1000 samples anchored at the utterance start, wraps the chunk totals with a
+// floor-mod 1, accumulates those (unwrapped) sequentially over chunks, wraps, adds, wraps.  The three kernels below
+// keep exactly that association order with __fadd_rn/__fmul_rn/__fdiv_rn (no FMA contraction, no tree scan):
+//   1. phase_chunk_kernel : one warp per chunk; lanes stage the chunk in shared memory (coalesced), one lane runs
+//                           the sequential sum, lanes write the running sums back (coalesced)
+//   2. chunk_offset_kernel: one warp per utterance; sequential (warp-uniform) scan over the chunk totals
+//   3. pulse_kernel       : fully parallel; wrap, 2-tap table lookup, 2-table cross-fade, reshape, noise
+// Parallelism comes from the B*T/10 independent chunks, not from splitting a chain.
+#include "kernels.cuh"
+
+namespace mbx {
+
+namespace {
+
+constexpr int CHUNK_WARPS = 4;
+constexpr int MAX_CHUNK = 1024;
+
+__device__ __forceinline__ float wrap1(float x) { return x - floorf(x); }   // floor-mod 1 for x >= 0 (exact)
+
+__device__ __forceinline__ int find_utt(const int32_t* chunk_first, int n_utt, int c) {
+    int lo = 0, hi = n_utt;            // chunk_first has n_utt + 1 entries, find u with first[u] <= c < first[u+1]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (chunk_first[mid] <= c) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(CHUNK_WARPS * 32)
+phase_chunk_kernel(ExcitationArgs a, FrameGrid g, int n_chunks_total) {
+    __shared__ float buf[CHUNK_WARPS][MAX_CHUNK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * CHUNK_WARPS + warp;
+    if (c >= n_chunks_total) return;
+    const int u = find_utt(a.chunk_first, g.n_utt, c);
+    const int j = c - a.chunk_first[u];
+    const long long base = (long long)g.utt_begin[u] * a.pulse_per_frame;
+    const long long n_u = (long long)(g.utt_end[u] - g.utt_begin[u]) * a.pulse_per_frame;
+    const long long s0 = (long long)j * a.chunk;
+    const int n = (int)min((long long)a.chunk, n_u - s0);
+    float* sb = buf[warp];
+    for (int i = lane; i < n; i += 32) sb[i] = __fdiv_rn(a.f0[base + s0 + i], a.pulse_rate);
+    __syncwarp();
+    if (lane == 0) {
+        float acc = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < n; ++i) {
+            acc = __fadd_rn(acc, sb[i]);
+            sb[i] = acc;
+        }
+        // zero padding up to the chunk size leaves the last running sum unchanged
+        a.chunk_off[c] = wrap1(acc);
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) a.cum[base + s0 + i] = sb[i];
+}
+
+__global__ void chunk_offset_kernel(ExcitationArgs a, FrameGrid g) {
+    // chunk_off[c] holds (chunk total mod 1) on entry and the offset to add to chunk c on exit
+    const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (u >= g.n_utt) return;
+    const int first = a.chunk_first[u], n = a.chunk_first[u + 1] - first;
+    float run = 0.f;            // unwrapped running sum of the wrapped totals (tf.cumsum(offsets, axis=1))
+    for (int b0 = 0; b0 < n; b0 += 32) {
+        int i = b0 + lane;
+        float tot = i < n ? a.chunk_off[first + i] : 0.f;
+        float mine = 0.f;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) {
+            // offset of chunk b0 + l = wrapped sum of the totals of chunks 0 .. b0 + l - 1 (0 for the first chunk);
+            // every lane carries the same `run`, lane l keeps its own chunk's value
+            float off_l = wrap1(run);
+            if (l == lane) mine = off_l;
+            run = __fadd_rn(run, __shfl_sync(0xffffffffu, tot, l));
+        }
+        if (i < n) a.chunk_off[first + i] = mine;
+    }
+}
+
+// Philox4x32-10 counter-based generator (Salmon et al. 2011) for the in-kernel noise channel.
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+    const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        unsigned hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        unsigned hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned utt, unsigned long long pos) {
+    uint4 r = philox4x32(make_uint4((unsigned)pos, (unsigned)(pos >> 32), utt, 0x4d425857u),
+                         make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    float u1 = ((float)(r.x >> 8) + 0.5f) * (1.f / 16777216.f);
+    float u2 = ((float)(r.y >> 8) + 0.5f) * (1.f / 16777216.f);
+    return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+}
+
+__global__ void pulse_kernel(ExcitationArgs a, FrameGrid g) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // pulse-rate sample on the grid
+    const long long total = (long long)g.n_frames * a.pulse_per_frame;
+    if (n >= total) return;
+    const long long step = n / a.pulse_channels;
+    const int ch = (int)(n - step * a.pulse_channels);
+    float* row = a.wn_in + step * a.ld_wn_in;
+    long long lo, hi;
+    if (!utt_bounds(g, a.pulse_per_frame, n, lo, hi)) {
+        row[ch] = 0.f;
+        if (ch == 0 && a.sigma != 0.f) row[a.pulse_channels] = 0.f;
+        if (a.phase_out) a.phase_out[n] = 0.f;
+        if (a.index_out) a.index_out[n] = 0;
+        if (a.pulse_out) a.pulse_out[n] = 0.f;
+        return;
+    }
+    const int f = (int)(n / a.pulse_per_frame);
+    const int u = g.frame_utt[f];
+    const long long local = n - lo;
+    const int c = a.chunk_first[u] + (int)(local / a.chunk);
+    // phase = ((cum + offset) mod 1)   (tf_wavetable.py:483-486)
+    const float phase = wrap1(__fadd_rn(a.cum[n], a.chunk_off[c]));
+    // _linear_lookup (tf_wavetable.py:621-638)
+    const float p = __fmul_rn(phase, (float)a.n_period);
+    const float pq = floorf(p);
+    const float frac = __fsub_rn(p, pq);
+    const int i0 = (int)pq;
+    const float one_m = __fsub_rn(1.f, frac);
+    // table cross-fade (tf_wavetable.py:539-548); only the two grid neighbours have non-zero weight
+    const float f0 = a.f0[n];
+    const float ratio = fmaxf(a.min_tr, fminf(a.max_tr, __fdiv_rn(f0, a.nominal_f0)));
+    const float x = __fmul_rn(logf(ratio), a.grid_norm);
+    int k0 = (int)floorf(x);
+    if (k0 < 0) k0 = 0;
+    if (k0 > a.n_tables - 1) k0 = a.n_tables - 1;
+    // memory safety only: phase < 1 and a power-of-two period keep i0 < n_period (the reference would raise otherwise)
+    const int i0c = min(max(i0, 0), a.n_period - 1);
+    const float* t0 = a.tables + (long long)i0c * a.n_tables;
+    const float* t1 = t0 + a.n_tables;
+    float acc = 0.f;
+#pragma unroll
+    for (int dk = 0; dk < 2; ++dk) {
+        int k = k0 + dk;
+        if (k < a.n_tables) {
+            float w = fmaxf(__fsub_rn(1.f, fabsf(__fsub_rn(x, (float)k))), 0.f);
+            float s = __fadd_rn(__fmul_rn(__ldg(t0 + k), one_m), __fmul_rn(__ldg(t1 + k), frac));
+            acc = __fadd_rn(acc, __fmul_rn(s, w));
+        }
+    }
+    row[ch] = acc;
+    if (ch == 0 && a.sigma != 0.f) {
+        const long long lstep = step - lo / a.pulse_channels;
+        float z = a.noise ? a.noise[step] : philox_normal(a.seed, (unsigned)u, (unsigned long long)lstep);
+        row[a.pulse_channels] = __fmul_rn(a.sigma, z);
+    }
+    if (a.phase_out) a.phase_out[n] = phase;
+    if (a.index_out) a.index_out[n] = i0;
+    if (a.pulse_out) a.pulse_out[n] = acc;
+}
+
+}  // namespace
+
+cudaError_t launch_excitation(const ExcitationArgs& a, const FrameGrid& g, int n_chunks_total, cudaStream_t s) {
+    if (a.chunk > MAX_CHUNK) return cudaErrorInvalidValue;
+    if (g.n_frames <= 0 || n_chunks_total <= 0) return cudaSuccess;
+    phase_chunk_kernel<<<(n_chunks_total + CHUNK_WARPS - 1) / CHUNK_WARPS, CHUNK_WARPS * 32, 0, s>>>(a, g, n_chunks_total);
+    chunk_offset_kernel<<<(g.n_utt * 32 + 127) / 128, 128, 0, s>>>(a, g);
+    long long total = (long long)g.n_frames * a.pulse_per_frame;
+    pulse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, g);
+    return cudaGetLastError();
+}
+
+}  // namespace mbx

@@ -1,0 +1,124 @@
+// Launcher declarations of the MBExWN forward kernels (definitions in k_*.cu).
+#pragma once
+#include "common.cuh"
+
+namespace mbx {
+
+// ---- k_conv.cu -----------------------------------------------------------------------------------
+struct ConvArgs {
+    const float* x;      // (rows, ld_x) input activations at `rate` rows per frame
+    int ld_x;
+    const float* w;      // (k, cin, cout) folded weight-norm kernel, row-major
+    const float* bias;   // (cout)
+    const float* alpha;  // PReLU slopes (act_mod) or nullptr
+    float* out;          // (rows, ld_out)
+    int ld_out;
+    long long rows;
+    int rate;
+    int k, cin, cout, dilation, pad_l, pad_mode;
+    int act;             // Act
+    int act_mod;         // alpha index = co % act_mod (sub-pixel convs share alpha across the unfold)
+    float leaky;         // LeakyReLU slope
+    float a0, a1;        // affine of ACT_SOFT_SIGMOID_AFFINE
+};
+cudaError_t launch_conv1d(const ConvArgs& a, const FrameGrid& g, cudaStream_t s);
+
+struct LinInterpArgs {
+    const float* x;      // (rows_in, ch)
+    float* out;          // (rows_in * up, ch)
+    long long rows_in;
+    int rate_in;
+    int ch;
+    int up;
+    int act;
+    const float* alpha;
+    float leaky;
+    float a0, a1;
+};
+cudaError_t launch_lininterp(const LinInterpArgs& a, const FrameGrid& g, cudaStream_t s);
+
+struct GateArgs {
+    const float* z;        // (rows, 2C) dilated conv output incl. bias
+    const float* cond;     // (rows / lin_up, 2C) conditioning at the low rate
+    float* act;            // (rows, C)
+    long long rows;
+    int rate;              // rows per frame
+    int c;
+    int lin_up;
+    int gate;
+};
+cudaError_t launch_gate(const GateArgs& a, const FrameGrid& g, cudaStream_t s);
+
+struct ResSkipArgs {
+    const float* rs;       // (rows, n_rs) 1x1 output incl. bias; n_rs = 2C (res | skip) or C (skip only)
+    float* h;              // (rows, C) residual stream, updated in place when n_rs == 2C
+    float* skip;           // (rows, C)
+    long long rows;
+    int rate;
+    int c;
+    int n_rs;
+    int first;             // 1: skip = ..., 0: skip += ...
+};
+cudaError_t launch_resskip(const ResSkipArgs& a, const FrameGrid& g, cudaStream_t s);
+
+// ---- k_excitation.cu -----------------------------------------------------------------------------
+struct ExcitationArgs {
+    const float* f0;        // (frames * pulse_per_frame) Hz at the pulse rate
+    const float* noise;     // (frames * steps_per_frame) standard normal, or nullptr => in-kernel Philox
+    unsigned long long seed;
+    const float* tables;    // (n_period + 1, n_tables)
+    int n_period, n_tables;
+    float pulse_rate;
+    float nominal_f0, min_tr, max_tr, grid_norm;
+    float sigma;
+    int pulse_per_frame, steps_per_frame, pulse_channels;
+    int chunk;              // cumsum chunk (1000, tf_wavetable.py:429)
+    float* cum;             // scratch (frames * pulse_per_frame): in-chunk running sums
+    float* chunk_off;       // scratch (n_chunks_total): per chunk offsets
+    const int32_t* chunk_first;  // [n_utt + 1] first chunk slot of each utterance (exclusive scan)
+    float* wn_in;           // (frames * steps_per_frame, ld_wn_in): pulse_channels pulse samples [+ noise]
+    int ld_wn_in;
+    float* phase_out;       // optional taps (frames * pulse_per_frame)
+    int32_t* index_out;
+    float* pulse_out;
+};
+cudaError_t launch_excitation(const ExcitationArgs& a, const FrameGrid& g, int n_chunks_total, cudaStream_t s);
+
+// ---- k_synth.cu ----------------------------------------------------------------------------------
+struct PqmfArgs {
+    const float* sub;       // (frames * steps, S)
+    const float* poly;      // (Q, S, S) polyphase bank
+    float* out;             // (frames * steps * S)
+    long long rows;         // frames * steps
+    int steps_per_frame;
+    int S, Q, back;
+};
+cudaError_t launch_pqmf(const PqmfArgs& a, const FrameGrid& g, cudaStream_t s);
+
+struct StftFilterArgs {
+    const float* exc;       // (frames * hop)
+    const float* ceps;      // (frames, n_ceps)
+    const float* f0;        // (frames * pulse_per_frame) for the lifter selection, or nullptr
+    const float* lifters;   // (n_lift, n_ceps) or nullptr
+    const float* lifter_grid;   // (n_lift) log10 f0
+    const float* f0_smooth; // (n_smooth) normalised Bartlett kernel
+    int n_lift, n_smooth, pulse_per_frame;
+    const float* window;    // (win)
+    const float* inv_window;// (win)
+    const float2* twiddle;  // (fft/2) exp(-2 pi i k / fft)
+    float* frames_out;      // (frames, win) windowed synthesis frames
+    float* vtf_out;         // optional tap (frames, fft/2+1) complex
+    int32_t* lifter_index_out;  // optional tap (frames)
+    int n_frames, hop, win, fft, n_ceps;
+    float max_log_range;    // 0 => plain exp
+};
+cudaError_t launch_stft_filter(const StftFilterArgs& a, const FrameGrid& g, cudaStream_t s);
+
+struct OlaArgs {
+    const float* frames;    // (frames, win)
+    float* out;             // (frames * hop)
+    int n_frames, hop, win;
+};
+cudaError_t launch_ola(const OlaArgs& a, const FrameGrid& g, cudaStream_t s);
+
+}  // namespace mbx

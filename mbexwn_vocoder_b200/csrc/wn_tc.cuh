@@ -1,0 +1,29 @@
+// tcgen05 / TMEM / TMA WaveNet layer path (definitions in k_wavenet_tc.cu).
+#pragma once
+#include <functional>
+#include <string>
+
+#include "../../include/mbexwn.h"
+#include "common.cuh"
+
+namespace mbx {
+
+struct WnTcState {
+    bool ready = false;
+    void* impl = nullptr;
+};
+
+// workspace slots the tensor-core path needs (called from the workspace carver)
+void wn_tc_carve(const mbexwn_config_t& c, long long rows, int precision,
+                 const std::function<void(const char*, size_t)>& add);
+
+// Runs start conv + all WaveNet layers; leaves the skip sum (rows, C) fp32 in `skip`.
+int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, int precision, const float* wn_in,
+                  const float* cond, float* skip, const std::function<void*(const char*)>& slot,
+                  const std::function<const void*(const std::string&, size_t)>& tensor, cudaStream_t s, int* launches,
+                  std::string* error);
+
+void wn_tc_invalidate(WnTcState& st);
+void wn_tc_destroy(WnTcState& st);
+
+}  // namespace mbx

@@ -1,0 +1,289 @@
+"""Device engine: owns the PyTorch-allocated buffers and drives libmbexwn_b200.so through the C-ABI.
+
+PyTorch is used for device memory, streams and pinned host memory only; every arithmetic op of the forward
+path runs in the hand-written CUDA kernels behind ``mbexwn_forward`` (include/mbexwn.h).  There is no CPU
+fallback: constructing an Engine without a CUDA device or without the built library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import weights as W
+from .plan import ACT_PRELU, ModelPlan, Op
+from .sched import FrameGridLayout, make_layout
+
+_TAP_DTYPES = {"index": torch.int32, "lifter_index": torch.int32}
+
+
+def _fill_op(dst: _cabi.Op, op: Op):
+    dst.kind = 0 if op.kind == "conv" else 1
+    if op.conv is not None:
+        cv = op.conv
+        dst.k, dst.cin, dst.cout, dst.dilation = cv.k, cv.cin, cv.cout, cv.dilation
+        dst.pad_l, dst.pad_r, dst.pad_mode, dst.subpixel = cv.pad_l, cv.pad_r, cv.pad_mode, cv.subpixel
+        dst.name = cv.name.encode()
+    dst.up = op.up
+    dst.act = op.act
+    dst.act_channels = op.act_channels
+    dst.rate_in, dst.rate_out, dst.ch_out = op.rate_in, op.rate_out, op.ch_out
+    dst.act_name = (op.act_name or "").encode()
+
+
+def make_config(plan: ModelPlan) -> _cabi.Config:
+    c = _cabi.Config()
+    c.abi_version = _cabi.ABI_VERSION
+    c.sample_rate, c.hop, c.mel_channels = plan.sample_rate, plan.hop, plan.mel_channels
+    c.pulse_per_frame, c.steps_per_frame = plan.pulse_per_frame, plan.steps_per_frame
+    c.pulse_channels, c.subbands = plan.pulse_channels, plan.subbands
+    c.pulse_rate, c.f0_min, c.f0_max = plan.pulse_rate, plan.f0_min, plan.f0_max
+    c.f0_span = plan.f0_max - plan.f0_min
+    c.noise_sigma, c.leaky_alpha = plan.noise_sigma, plan.alpha
+    if len(plan.pp_ops) > _cabi.MAX_OPS or len(plan.ps_ops) > _cabi.MAX_OPS:
+        raise NotImplementedError("sub-net too deep for the C-ABI op table")
+    c.n_pp_ops, c.n_ps_ops = len(plan.pp_ops), len(plan.ps_ops)
+    for i, op in enumerate(plan.pp_ops):
+        _fill_op(c.pp_ops[i], op)
+    for i, op in enumerate(plan.ps_ops):
+        _fill_op(c.ps_ops[i], op)
+    wn = plan.wavenet
+    if wn.n_layers > _cabi.MAX_LAYERS:
+        raise NotImplementedError("too many WaveNet layers for the C-ABI")
+    c.wn_c, c.wn_cin, c.wn_cout, c.wn_layers, c.wn_k, c.wn_gate = wn.c, wn.c_in, wn.c_out, wn.n_layers, wn.k, wn.gate
+    c.wn_cond_k, c.wn_cond_conv_up, c.wn_cond_lin_up = wn.cond_k, wn.cond_conv_up, wn.cond_lin_up
+    for i, d in enumerate(wn.dilations):
+        c.wn_dilations[i] = d
+    c.wn_name = (wn.name + "_WNBlock_WN").encode()
+    c.post_name = plan.post_name.encode()
+    c.n_ceps, c.stft_win, c.fft_size = plan.n_ceps, plan.stft_win, plan.fft_size
+    c.n_lifters = 0 if plan.lifters is None else int(plan.lifters.shape[0])
+    c.n_smooth = int(plan.f0_smooth.shape[0])
+    c.filter_max_log_range = float(plan.filter_max_log_range or 0.0)
+    wt = plan.wavetables
+    c.wt_n_period, c.wt_n_tables = wt.n_period, int(wt.tables.shape[1])
+    c.wt_nominal_f0 = float(np.float32(wt.nominal_f0))
+    c.wt_min_transposition, c.wt_max_transposition = float(wt.min_transposition), float(wt.max_transposition)
+    c.wt_grid_norm = float(wt.grid_norm)
+    c.cumsum_chunk = 1000
+    c.pqmf_q, c.pqmf_back = plan.pqmf_q, plan.pqmf_back
+    c.halo_frames = engine_halo(plan)
+    return c
+
+
+def engine_halo(plan: ModelPlan) -> int:
+    """Guard frames between utterances: covers the widest dilated tap and the PQMF polyphase reach."""
+    reach = max(plan.max_halo_frames * plan.steps_per_frame, plan.pqmf_back, plan.pqmf_q - 1 - plan.pqmf_back)
+    return max(1, -(-reach // plan.steps_per_frame))
+
+
+class Engine:
+    def __init__(self, plan: ModelPlan, weights: Dict[str, np.ndarray], device: Union[int, str, torch.device] = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mbexwn_vocoder_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _cabi.load()
+        self.plan = plan
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        W.check(plan, weights)
+        self.cfg = make_config(plan)
+        self.halo = self.cfg.halo_frames
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.mbexwn_create(C.byref(self.cfg), C.byref(self._handle))
+        if rc != _cabi.OK:
+            raise RuntimeError(f"mbexwn_create failed ({rc})")
+        self._tensors: Dict[str, torch.Tensor] = {}
+        self._workspace: Optional[torch.Tensor] = None
+        self._upload(weights)
+        self.last_layout: Optional[FrameGridLayout] = None
+        self._last = None
+
+    # ---- weights / constants ----------------------------------------------------------------------
+    def _register(self, name: str, array: np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(array)).to(self.device)
+        self._tensors[name] = t
+        _cabi.check(self.lib, self._handle,
+                    self.lib.mbexwn_set_tensor(self._handle, name.encode(), t.data_ptr(), t.numel() * t.element_size()),
+                    f"set_tensor({name})")
+
+    def _upload(self, weights: Dict[str, np.ndarray]):
+        plan = self.plan
+        for layer in plan.conv_layers():
+            w, b = W.folded(weights, layer.name)
+            self._register(f"{layer.name}/W", w)
+            self._register(f"{layer.name}/b", b)
+        for ops in (plan.pp_ops, plan.ps_ops):
+            for op in ops:
+                if op.act == ACT_PRELU and op.act_name:
+                    self._register(f"{op.act_name}/alpha", weights[f"{op.act_name}/alpha"].astype(np.float32))
+        # end (C -> c_out) and post (c_out -> S) are both linear 1x1 convs with nothing in between
+        # (custom_AE_layers.py:340, custom_pulsed_generator.py:913-914): pre-multiply once in float64
+        wn_name = plan.wavenet.name + "_WNBlock_WN"
+        we, be = W.folded(weights, f"{wn_name}/end")
+        wp, bp = W.folded(weights, plan.post_name)
+        we64, wp64 = we[0].astype(np.float64), wp[0].astype(np.float64)
+        self._register("end_post/W", (we64 @ wp64).astype(np.float32))
+        self._register("end_post/b", (be.astype(np.float64) @ wp64 + bp.astype(np.float64)).astype(np.float32))
+        self._register("wavetable", plan.wavetables.tables)
+        self._register("pqmf_poly", plan.pqmf_poly)
+        self._register("window", plan.window)
+        self._register("inv_window", plan.inv_window)
+        n = plan.fft_size
+        ang = -2.0 * np.pi * np.arange(n // 2) / n
+        self._register("twiddle", np.stack((np.cos(ang), np.sin(ang)), axis=1).astype(np.float32))
+        self._register("f0_smooth", plan.f0_smooth)
+        if plan.lifters is not None:
+            self._register("lifters", plan.lifters)
+            self._register("lifter_grid", plan.lifter_log10f0)
+
+    def set_option(self, name: str, value: int):
+        _cabi.check(self.lib, self._handle, self.lib.mbexwn_set_option(self._handle, name.encode(), value), "set_option")
+
+    # ---- forward ----------------------------------------------------------------------------------
+    def _ensure_workspace(self, nbytes: int) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = None
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def _grid_tensors(self, layout: FrameGridLayout):
+        dev = self.device
+        return (torch.from_numpy(layout.frame_utt).to(dev), torch.from_numpy(layout.utt_begin).to(dev),
+                torch.from_numpy(layout.utt_end).to(dev), torch.from_numpy(layout.chunk_first).to(dev))
+
+    def prepare(self, lengths: Sequence[int], precision: str = "fp32", with_noise: bool = True,
+                with_f0: bool = False) -> "PreparedBatch":
+        """Allocate everything one batch geometry needs (device grid, staging, pinned host buffers, workspace)."""
+        return PreparedBatch(self, lengths, precision, with_noise, with_f0)
+
+    def forward(self, mels: Sequence[np.ndarray], noise: Optional[Sequence[np.ndarray]] = None,
+                f0: Optional[Sequence[np.ndarray]] = None, precision: str = "fp32", seed: int = 0,
+                taps: Sequence[str] = ()):
+        """mels: list of (T_u, n_mel) float32.  Returns (list of (T_u*hop,) waveforms, {tap: list of arrays})."""
+        pb = self.prepare([m.shape[0] for m in mels], precision, noise is not None, f0 is not None)
+        pb.load(mels, noise, f0)
+        pb.run_host(seed)
+        out = [w.copy() for w in pb.waveforms()]
+        return out, {t: pb.tap(t) for t in taps}
+
+    def close(self):
+        if self._handle:
+            self.lib.mbexwn_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PreparedBatch:
+    """One batch geometry bound to its buffers; `run_host` is the reference-facing call (host in, host out)."""
+
+    def __init__(self, eng: Engine, lengths: Sequence[int], precision: str, with_noise: bool, with_f0: bool):
+        plan = eng.plan
+        self.eng = eng
+        self.prec = _cabi.PRECISIONS[precision]
+        self.layout = make_layout(lengths, eng.halo, plan.pulse_per_frame, eng.cfg.cumsum_chunk)
+        L = self.layout
+        dev = eng.device
+        self.frame_utt, self.utt_begin, self.utt_end, self.chunk_first = eng._grid_tensors(L)
+        F = L.n_frames
+        self.mel_host = torch.zeros(F, plan.mel_channels, dtype=torch.float32).pin_memory()
+        self.out_host = torch.zeros(F * plan.hop, dtype=torch.float32).pin_memory()
+        self.mel_dev = torch.zeros(F, plan.mel_channels, dtype=torch.float32, device=dev)
+        self.out_dev = torch.zeros(F * plan.hop, dtype=torch.float32, device=dev)
+        self.noise_host = self.noise_dev = self.f0_dev = None
+        if with_noise:
+            self.noise_host = torch.zeros(F * plan.steps_per_frame, dtype=torch.float32).pin_memory()
+            self.noise_dev = torch.zeros(F * plan.steps_per_frame, dtype=torch.float32, device=dev)
+        if with_f0:
+            self.f0_dev = torch.zeros(F * plan.pulse_per_frame, dtype=torch.float32, device=dev)
+        self.ws_bytes = int(eng.lib.mbexwn_workspace_bytes(eng._handle, F, L.n_chunks, self.prec))
+        self.workspace = eng._ensure_workspace(self.ws_bytes)
+        self.batch = _cabi.Batch()
+        b = self.batch
+        b.n_utt, b.n_frames, b.n_chunks = L.n_utt, F, L.n_chunks
+        b.frame_utt, b.utt_begin, b.utt_end = self.frame_utt.data_ptr(), self.utt_begin.data_ptr(), self.utt_end.data_ptr()
+        b.chunk_first = self.chunk_first.data_ptr()
+        b.mel = self.mel_dev.data_ptr()
+        b.noise = self.noise_dev.data_ptr() if with_noise else None
+        b.f0_override = self.f0_dev.data_ptr() if with_f0 else None
+        b.out = self.out_dev.data_ptr()
+
+    # bytes moved per run_host call
+    @property
+    def h2d_bytes(self) -> int:
+        n = self.mel_host.numel() * 4
+        return n + (self.noise_host.numel() * 4 if self.noise_host is not None else 0)
+
+    @property
+    def d2h_bytes(self) -> int:
+        return self.out_host.numel() * 4
+
+    def load(self, mels, noise=None, f0=None):
+        L, plan = self.layout, self.eng.plan
+        self.layout.scatter([np.asarray(m, dtype=np.float32) for m in mels], 1, self.mel_host.numpy())
+        if noise is not None:
+            L.scatter([np.asarray(z, dtype=np.float32).reshape(-1) for z in noise], plan.steps_per_frame,
+                      self.noise_host.numpy())
+        if f0 is not None:
+            buf = np.zeros(L.n_frames * plan.pulse_per_frame, dtype=np.float32)
+            L.scatter([np.asarray(x, dtype=np.float32).reshape(-1) for x in f0], plan.pulse_per_frame, buf)
+            self.f0_dev.copy_(torch.from_numpy(buf))
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.eng.device).cuda_stream
+
+    def run_host(self, seed: int = 0):
+        """Host mel in -> host waveform out through mbexwn_forward_host (copies inside the call)."""
+        eng = self.eng
+        self.batch.seed = seed
+        with torch.cuda.device(eng.device):
+            rc = eng.lib.mbexwn_forward_host(
+                eng._handle, C.byref(self.batch), self.prec, self.mel_host.data_ptr(),
+                self.noise_host.data_ptr() if self.noise_host is not None else None, self.out_host.data_ptr(),
+                self.workspace.data_ptr(), self.workspace.numel(), self._stream())
+        _cabi.check(eng.lib, eng._handle, rc, "mbexwn_forward_host")
+
+    def upload(self):
+        self.mel_dev.copy_(self.mel_host, non_blocking=True)
+        if self.noise_host is not None:
+            self.noise_dev.copy_(self.noise_host, non_blocking=True)
+
+    def run_device(self, seed: int = 0):
+        """Device-resident inputs -> device output (asynchronous on the current stream)."""
+        eng = self.eng
+        self.batch.seed = seed
+        with torch.cuda.device(eng.device):
+            rc = eng.lib.mbexwn_forward(eng._handle, C.byref(self.batch), self.prec, self.workspace.data_ptr(),
+                                        self.workspace.numel(), self._stream())
+        _cabi.check(eng.lib, eng._handle, rc, "mbexwn_forward")
+
+    def launches(self) -> int:
+        return int(self.eng.lib.mbexwn_last_launch_count(self.eng._handle))
+
+    def waveforms(self, from_device: bool = False) -> List[np.ndarray]:
+        buf = self.out_dev.cpu().numpy() if from_device else self.out_host.numpy()
+        return self.layout.gather(buf, self.eng.plan.hop)
+
+    def tap_grid(self, name: str) -> torch.Tensor:
+        eng = self.eng
+        off, nb = C.c_size_t(), C.c_size_t()
+        rc = eng.lib.mbexwn_tap(eng._handle, name.encode(), self.layout.n_frames, self.layout.n_chunks, self.prec,
+                                C.byref(off), C.byref(nb))
+        _cabi.check(eng.lib, eng._handle, rc, f"tap({name})")
+        raw = self.workspace[off.value:off.value + nb.value]
+        return raw.view(_TAP_DTYPES.get(name, torch.float32))
+
+    def tap(self, name: str) -> List[np.ndarray]:
+        """Per-utterance view of a stage tap: list of (T_u * rate, channels) arrays."""
+        flat = self.tap_grid(name).cpu().numpy()
+        F = self.layout.n_frames
+        per_frame = flat.size // F
+        grid = flat.reshape(F, per_frame)
+        return [grid[self.layout.utt_begin[u]:self.layout.utt_end[u]].reshape(-1) for u in range(self.layout.n_utt)]

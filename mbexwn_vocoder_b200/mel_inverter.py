@@ -1,0 +1,180 @@
+"""MELInverter: drop-in for MBExWN_NVoc.mel_inverter.MELInverter (mel_inverter.py:21-239) on one B200.
+
+Same constructor, same ``scale_mel`` / ``synth_from_mel`` / ``srate`` surface and the same exception classes;
+behind it the TensorFlow graph is replaced by the hand-written sm_100a kernels of libmbexwn_b200.so.  The
+noise channel of the generator (custom_pulsed_generator.py:906) is drawn in-kernel from a counter-based
+Philox stream seeded by ``seed`` (the reference uses TensorFlow's global generator).
+"""
+from __future__ import annotations
+
+import os
+import sys
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+from scipy.interpolate import interp1d
+
+from . import get_config_file, list_models  # noqa: F401  (re-exported like the reference module)
+from . import config as cutils
+from . import weights as W
+from .plan import build_plan
+
+log_to_db = 20 * np.log10(np.exp(1))            # vocoder/model/preprocess.py:78
+
+
+class MELInverter(object):
+    def __init__(self, model_id_or_path: Union[str, None] = None, verbose: bool = False,
+                 device: Union[int, str] = 0, precision: str = "fp32", seed: int = 42):
+        self.model = None
+        self.model_id_or_path = model_id_or_path
+        self.config_file = None
+        self.preprocess_config = None
+        self.mel_channels = None
+        self.hop_size = None
+        self.fft_size = None
+        self.fmin = None
+        self.fmax = None
+        self._srate = None
+        self.win_len = None
+
+        self.lin_amp_scale = 1
+        self.lin_amp_off = 1.e-5
+        self.mel_amp_scale = 1
+        self.use_max_limit = False
+
+        self.device = device
+        self.precision = precision
+        self.seed = seed                        # bin/resynth_mel.py:65-67 seeds everything with 42
+        self.plan = None
+        if model_id_or_path:
+            self.load_model(model_id_or_path=model_id_or_path, verbose=verbose)
+
+    @property
+    def srate(self):
+        return self._srate
+
+    # ------------------------------------------------------------------------------------------------
+    def scale_mel(self, mel_config: Dict, verbose=False):
+        """Bring an analysis dict (keys mell|mel, sr, hoplen, nfft, fmin, fmax, ...) to the model's log-mel scaling.
+
+        Restates mel_inverter.py:48-148 (NumPy, host side).  The reference's verbose-only branches that reference
+        undefined names are not reproduced.
+        """
+        hop_ratio = (mel_config['hoplen'] / mel_config['sr']) / (self.hop_size / self.srate)
+        if verbose and np.abs(hop_ratio - 1) > 0.001:
+            print(f"compensate change in analysis hop size. mel analysis has {mel_config['hoplen'] / mel_config['sr']}"
+                  f" while the model expects {self.hop_size / self.srate}.", file=sys.stderr)
+        if verbose and mel_config['sr'] != self.srate:
+            print(f"    WARNING::sample rate of mel analysis is  {mel_config['sr']} model expects {self.srate}.",
+                  file=sys.stderr)
+        if mel_config['fmin'] != self.fmin:
+            raise RuntimeError(f"mell fmin {mel_config['fmin']} does not match model fmin {self.fmin}")
+        if ((mel_config['fmax'] is None) and self.fmax != mel_config['sr'] / 2) or \
+                ((mel_config['fmax'] is not None) and mel_config['fmax'] != self.fmax):
+            raise RuntimeError(f"mell fmax {mel_config['fmax']} does not match model fmax {self.fmax}")
+
+        if "mell" in mel_config:
+            log_mel = np.array(mel_config['mell'].T[np.newaxis], dtype=np.float64 if
+                               mel_config['mell'].dtype == np.float64 else np.float32)
+            if "log_spec_offset" in mel_config and mel_config["log_spec_offset"] != 0:
+                log_mel -= mel_config["log_spec_offset"]
+            if "log_spec_scale" in mel_config and mel_config["log_spec_scale"] != 1:
+                log_mel /= mel_config["log_spec_scale"]
+            mel = np.exp(log_mel)
+        elif "mel" in mel_config:
+            mel = np.array(mel_config['mel'].T[np.newaxis])
+        else:
+            raise RuntimeError("error::no supported mel spectrum (keys:mell or mell) in mel_config")
+
+        n_fft = mel_config.get("nfft", None)
+        if n_fft is None:
+            n_fft = mel_config.get("n_fft", None)
+        if n_fft is None:
+            n_fft = mel_config.get("fft_size", None)
+        fft_scale = self.fft_size // n_fft
+        if fft_scale != 1:
+            mel *= fft_scale
+        if mel_config.get("lin_spec_offset") is not None and mel_config.get("lin_spec_offset", 0) != 0:
+            mel -= mel_config["lin_spec_offset"]
+        if "lin_spec_scale" in mel_config and mel_config["lin_spec_scale"] != 1:
+            mel /= mel_config["lin_spec_scale"]
+        if self.lin_amp_scale != 1:
+            mel *= self.lin_amp_scale
+        if self.use_max_limit:
+            mell = np.log(np.fmax(mel, self.lin_amp_off)).astype(np.float32)
+        else:
+            mell = np.log(mel + self.lin_amp_off).astype(np.float32)
+
+        if np.abs(hop_ratio - 1) > 0.001:
+            src_hop = mel_config['hoplen'] / mel_config['sr']
+            mell = interp1d(np.arange(mell.shape[1]) * src_hop, mell, axis=1, bounds_error=False,
+                            fill_value="extrapolate")(
+                np.arange(0, (mell.shape[1] - 1 + 0.1) * src_hop, self.hop_size / self.srate)).astype(np.float32)
+        return mell * self.mel_amp_scale
+
+    # ------------------------------------------------------------------------------------------------
+    def synth_from_mel(self, scaled_mell, noise=None, seed: Optional[int] = None):
+        """(B, T, n_mel) float32 log-mel -> flat float32 waveform of length B*T*hop (mel_inverter.py:151-154).
+
+        Like the reference the batch is flattened by ``ravel``.  ``noise`` optionally supplies
+        the (B, T*steps, 1) standard-normal draw of the generator's noise channel (parity runs).
+        """
+        scaled_mell = np.asarray(scaled_mell, dtype=np.float32)
+        if scaled_mell.ndim != 3 or scaled_mell.shape[2] != self.mel_channels:
+            raise RuntimeError(f"expected a (batch, frames, {self.mel_channels}) mel spectrogram, got {scaled_mell.shape}")
+        noise_list = None if noise is None else [np.asarray(z) for z in noise]
+        out, _ = self.model.forward(list(scaled_mell), noise=noise_list, precision=self.precision,
+                                    seed=self.seed if seed is None else seed)
+        return np.stack(out).ravel()
+
+    def synth_batch(self, mels: Sequence[np.ndarray], noise=None, f0=None, taps: Sequence[str] = (),
+                    seed: Optional[int] = None):
+        """Variable-length batch: list of (T_u, n_mel) -> list of (T_u*hop,) waveforms [+ stage taps]."""
+        out, tp = self.model.forward([np.asarray(m, dtype=np.float32) for m in mels], noise=noise, f0=f0,
+                                     precision=self.precision, seed=self.seed if seed is None else seed, taps=taps)
+        return (out, tp) if taps else out
+
+    def generate_mel_from_snd(self, snd, srate):
+        raise NotImplementedError("audio -> mel analysis is outside the B200 hot path (SURVEY.md 8f-2)")
+
+    # ------------------------------------------------------------------------------------------------
+    def load_model(self, model_id_or_path, verbose=False):
+        """Config lookup, plan, weights and engine construction (mel_inverter.py:184-239)."""
+        from .engine import Engine
+
+        config_file = get_config_file(model_id_or_path=model_id_or_path)
+        model_dir = os.path.dirname(config_file)
+        hparams = cutils.read_config(config_file=config_file)
+        self.config_file = config_file
+        self.preprocess_config = hparams["preprocess_config"]
+        self.plan = build_plan(hparams)
+
+        weights_path = os.path.join(model_dir, "weights.npz")
+        if os.path.exists(weights_path):
+            if verbose:
+                print(f"restore from {weights_path}", file=sys.stderr)
+            weights = W.load(weights_path)
+        elif os.path.exists(os.path.join(model_dir, "weights.tf.index")):
+            raise NotImplementedError("TensorFlow checkpoint import is not built yet (SURVEY.md 8f-1); "
+                                      "convert the checkpoint to weights.npz")
+        else:
+            seed = int(hparams.get("synthetic_weights", {}).get("seed", 0))
+            if verbose:
+                print(f"no weights beside {config_file}: random-initialised weights, seed {seed}", file=sys.stderr)
+            weights = W.init_synthetic(self.plan, seed=seed)
+        self.weights = weights
+        self.model = Engine(self.plan, weights, device=self.device)
+
+        pc = self.preprocess_config
+        self.mel_channels = pc["mel_channels"]
+        self.hop_size = pc["hop_size"]
+        self.fft_size = pc["fft_size"]
+        self.fmin = pc["fmin"]
+        self.fmax = pc["fmax"]
+        self._srate = pc['sample_rate']
+        self.win_len = pc['win_size'] if 'win_size' in pc else self.fft_size
+        self.lin_amp_scale = pc["lin_amp_scale"] if pc.get("lin_amp_scale", 1) != 1 else 1
+        self.lin_amp_off = pc["lin_amp_off"] if pc.get("lin_amp_off") is not None else 1.e-5
+        self.mel_amp_scale = pc["mel_amp_scale"] if pc.get("mel_amp_scale", 1) != 1 else 1
+        self.use_max_limit = bool(pc.get("use_max_limit", False))
+        return
