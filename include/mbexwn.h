@@ -29,6 +29,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define MBEXWN_API __attribute__((visibility("default")))
+#else
+#define MBEXWN_API
+#endif
+
 #define MBEXWN_ABI_VERSION 1
 #define MBEXWN_MAX_LAYERS 64
 #define MBEXWN_MAX_OPS 32
@@ -111,27 +117,27 @@ typedef struct {
 } mbexwn_batch_t;
 
 /* ---- life cycle: stands in for create_model + build_model + load_weights (mel_inverter.py:184-210) ---- */
-int mbexwn_abi_version(void);
-int mbexwn_create(const mbexwn_config_t* cfg, mbexwn_handle_t* out);
-void mbexwn_destroy(mbexwn_handle_t h);
-const char* mbexwn_last_error(mbexwn_handle_t h);
+MBEXWN_API int mbexwn_abi_version(void);
+MBEXWN_API int mbexwn_create(const mbexwn_config_t* cfg, mbexwn_handle_t* out);
+MBEXWN_API void mbexwn_destroy(mbexwn_handle_t h);
+MBEXWN_API const char* mbexwn_last_error(mbexwn_handle_t h);
 
 /* Register a device tensor by name (folded weights, biases, PReLU slopes, DSP constants).  The pointer must stay
  * valid for the life of the handle.  Names: see mbexwn_op_t / mbexwn_config_t, plus the constants "wavetable"
  * (n_period+1, n_tables), "pqmf_poly" (Q, S, S), "window" (win), "inv_window" (win), "twiddle" (fft/2, 2),
  * "lifters" (n_lifters, n_ceps), "lifter_grid" (n_lifters), "f0_smooth" (n_smooth), "end_post/W" (wn_c, subbands),
  * "end_post/b" (subbands). */
-int mbexwn_set_tensor(mbexwn_handle_t h, const char* name, const void* dev_ptr, size_t n_bytes);
+MBEXWN_API int mbexwn_set_tensor(mbexwn_handle_t h, const char* name, const void* dev_ptr, size_t n_bytes);
 
 /* ---- forward: stands in for MELInverter.synth_from_mel / PaNWaveNet.infer ---- */
-size_t mbexwn_workspace_bytes(mbexwn_handle_t h, int32_t n_frames, int32_t n_chunks, int32_t precision);
-int mbexwn_forward(mbexwn_handle_t h, const mbexwn_batch_t* batch, int32_t precision,
+MBEXWN_API size_t mbexwn_workspace_bytes(mbexwn_handle_t h, int32_t n_frames, int32_t n_chunks, int32_t precision);
+MBEXWN_API int mbexwn_forward(mbexwn_handle_t h, const mbexwn_batch_t* batch, int32_t precision,
                    void* workspace, size_t workspace_bytes, void* cuda_stream);
 
 /* Same call with HOST buffers (pinned for asynchronous copies): copies mel (and noise if given) host->device into
  * the staging pointers of `batch`, runs the forward, copies the waveform device->host and synchronises the stream.
  * mel_host: (n_frames, mel_channels); out_host: (n_frames * hop). */
-int mbexwn_forward_host(mbexwn_handle_t h, const mbexwn_batch_t* batch, int32_t precision,
+MBEXWN_API int mbexwn_forward_host(mbexwn_handle_t h, const mbexwn_batch_t* batch, int32_t precision,
                         const float* mel_host, const float* noise_host, float* out_host,
                         void* workspace, size_t workspace_bytes, void* cuda_stream);
 
@@ -139,20 +145,20 @@ int mbexwn_forward_host(mbexwn_handle_t h, const mbexwn_batch_t* batch, int32_t 
  * stage boundaries of SURVEY.md 8a): after mbexwn_forward the named intermediate lives in the workspace at
  * [*offset_bytes, *offset_bytes + *n_bytes).  Names: "F0", "phase", "index", "pulse", "wn_in", "cond", "h", "skip",
  * "subbands", "excitation", "ceps", "frames", "vtf", "lifter_index". */
-int mbexwn_tap(mbexwn_handle_t h, const char* name, int32_t n_frames, int32_t n_chunks, int32_t precision,
+MBEXWN_API int mbexwn_tap(mbexwn_handle_t h, const char* name, int32_t n_frames, int32_t n_chunks, int32_t precision,
                size_t* offset_bytes, size_t* n_bytes);
 
 /* Number of kernel launches issued by the last mbexwn_forward on this handle. */
-int mbexwn_last_launch_count(mbexwn_handle_t h);
+MBEXWN_API int mbexwn_last_launch_count(mbexwn_handle_t h);
 
 /* Options: "debug_taps" (default 1): keep the phase / index / pulse / vtf / lifter_index taps in the workspace. */
-int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value);
+MBEXWN_API int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value);
 
 /* ---- single kernels on caller-provided buffers (stage-level parity tests; same kernels the forward uses) ---- */
-int mbexwn_k_conv1d(mbexwn_handle_t h, const mbexwn_batch_t* grid, const mbexwn_op_t* op, int32_t rate,
+MBEXWN_API int mbexwn_k_conv1d(mbexwn_handle_t h, const mbexwn_batch_t* grid, const mbexwn_op_t* op, int32_t rate,
                     const float* x, const float* w, const float* bias, const float* alpha, float* out,
                     void* cuda_stream);
-int mbexwn_k_lininterp(mbexwn_handle_t h, const mbexwn_batch_t* grid, const mbexwn_op_t* op,
+MBEXWN_API int mbexwn_k_lininterp(mbexwn_handle_t h, const mbexwn_batch_t* grid, const mbexwn_op_t* op,
                        const float* x, const float* alpha, float* out, void* cuda_stream);
 
 #ifdef __cplusplus
