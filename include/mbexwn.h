@@ -126,7 +126,13 @@ MBEXWN_API const char* mbexwn_last_error(mbexwn_handle_t h);
  * valid for the life of the handle.  Names: see mbexwn_op_t / mbexwn_config_t, plus the constants "wavetable"
  * (n_period+1, n_tables), "pqmf_poly" (Q, S, S), "window" (win), "inv_window" (win), "twiddle" (fft/2, 2),
  * "lifters" (n_lifters, n_ceps), "lifter_grid" (n_lifters), "f0_smooth" (n_smooth), "end_post/W" (wn_c, subbands),
- * "end_post/b" (subbands). */
+ * "end_post/b" (subbands).
+ * Tensor-core path (precision != FP32_SIMT), per WaveNet layer i, C padded to cpad = ceil(C / 64) * 64:
+ *   "<wn_name>/tc/W1_<i>" bf16 (2*cpad, 2*k*cpad): rows = output channels permuted so that each block of 128 rows is
+ *        [64 tanh channels | the matching 64 sigmoid channels]; columns = [hi plane | lo plane], each (tap, cin)-major
+ *   "<wn_name>/tc/b1_<i>" fp32 (2*cpad) in the same row order
+ *   "<wn_name>/tc/R_<i>"  bf16 (2*cpad or cpad for the last layer, 2*cpad): rows = [res channels | skip channels]
+ *   "<wn_name>/tc/rb_<i>" fp32 in the same row order */
 MBEXWN_API int mbexwn_set_tensor(mbexwn_handle_t h, const char* name, const void* dev_ptr, size_t n_bytes);
 
 /* ---- forward: stands in for MELInverter.synth_from_mel / PaNWaveNet.infer ---- */
@@ -160,6 +166,13 @@ MBEXWN_API int mbexwn_k_conv1d(mbexwn_handle_t h, const mbexwn_batch_t* grid, co
                     void* cuda_stream);
 MBEXWN_API int mbexwn_k_lininterp(mbexwn_handle_t h, const mbexwn_batch_t* grid, const mbexwn_op_t* op,
                        const float* x, const float* alpha, float* out, void* cuda_stream);
+
+/* The tensor-core tap-GEMM on its own: out (rows, n) fp32 = sum over K blocks of
+ * A[rows + shift_b, a_col_b : a_col_b + 64] @ B[0:n, b_col_b : b_col_b + 64]^T with A (rows, a_cols) and B (n, b_cols)
+ * row-major bf16; kblocks = n_kb x {a_col, row_shift, b_col}.  Rows shifted outside [0, rows) read as zero. */
+MBEXWN_API int mbexwn_k_tc_gemm(mbexwn_handle_t h, const void* a_bf16, int64_t rows, int32_t a_cols, const void* b_bf16,
+                                int32_t n, int32_t b_cols, const int32_t* kblocks, int32_t n_kb, float* out,
+                                void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,8 @@ SYMBOLS = {
     "mbexwn_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
     "mbexwn_k_conv1d": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Op), C.c_int32, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mbexwn_k_tc_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mbexwn_k_lininterp": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Op), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
 }

@@ -437,4 +437,11 @@ int mbexwn_k_lininterp(mbexwn_handle_t h, const mbexwn_batch_t* b, const mbexwn_
     return MBEXWN_OK;
 }
 
+int mbexwn_k_tc_gemm(mbexwn_handle_t h, const void* a_bf16, int64_t rows, int32_t a_cols, const void* b_bf16, int32_t n,
+                     int32_t b_cols, const int32_t* kblocks, int32_t n_kb, float* out, void* cuda_stream) {
+    if (!h || !a_bf16 || !b_bf16 || !kblocks || !out) return MBEXWN_ERR_INVALID;
+    return mbx::wn_tc_gemm_test(h->tc, a_bf16, rows, a_cols, b_bf16, n, b_cols, kblocks, n_kb, out,
+                                reinterpret_cast<cudaStream_t>(cuda_stream), &h->error);
+}
+
 }  // extern "C"

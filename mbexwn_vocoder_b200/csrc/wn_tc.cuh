@@ -23,6 +23,11 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
                   const std::function<const void*(const std::string&, size_t)>& tensor, cudaStream_t s, int* launches,
                   std::string* error);
 
+// Stand-alone tap-GEMM (unit tests): out (rows, n) fp32 = sum over K blocks {a_col, a_row_shift, b_col} of
+// A[rows + shift, a_col : a_col + 64] @ B[:, b_col : b_col + 64]^T, A (rows, a_cols) bf16, B (n, b_cols) bf16.
+int wn_tc_gemm_test(WnTcState& st, const void* a_bf16, long long rows, int a_cols, const void* b_bf16, int n, int b_cols,
+                    const int* kblocks, int n_kb, float* out, cudaStream_t s, std::string* error);
+
 void wn_tc_invalidate(WnTcState& st);
 void wn_tc_destroy(WnTcState& st);
 

@@ -138,6 +138,30 @@ class Engine:
         if plan.lifters is not None:
             self._register("lifters", plan.lifters)
             self._register("lifter_grid", plan.lifter_log10f0)
+        self._upload_tc(weights)
+
+    def _register_torch(self, name: str, t: torch.Tensor):
+        t = t.contiguous().to(self.device)
+        self._tensors[name] = t
+        _cabi.check(self.lib, self._handle,
+                    self.lib.mbexwn_set_tensor(self._handle, name.encode(), t.data_ptr(), t.numel() * t.element_size()),
+                    f"set_tensor({name})")
+
+    def _upload_tc(self, weights: Dict[str, np.ndarray]):
+        from .tc_pack import pack_tc_weights
+        for name, t in pack_tc_weights(self.plan, weights).items():
+            self._register_torch(name, t)
+
+    def tc_gemm(self, a: torch.Tensor, b: torch.Tensor, kblocks: np.ndarray) -> torch.Tensor:
+        """Unit-test hook for the tap-GEMM kernel: a (rows, a_cols) bf16, b (n, b_cols) bf16 on the device."""
+        assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_cuda and b.is_cuda
+        kb = np.ascontiguousarray(kblocks, dtype=np.int32)
+        out = torch.empty(a.shape[0], b.shape[0], dtype=torch.float32, device=self.device)
+        rc = self.lib.mbexwn_k_tc_gemm(self._handle, a.data_ptr(), a.shape[0], a.shape[1], b.data_ptr(), b.shape[0],
+                                       b.shape[1], kb.ctypes.data, kb.shape[0], out.data_ptr(),
+                                       torch.cuda.current_stream(self.device).cuda_stream)
+        _cabi.check(self.lib, self._handle, rc, "mbexwn_k_tc_gemm")
+        return out
 
     def set_option(self, name: str, value: int):
         _cabi.check(self.lib, self._handle, self.lib.mbexwn_set_option(self._handle, name.encode(), value), "set_option")

@@ -1,0 +1,87 @@
+"""GPU tests of the tcgen05 tap-GEMM kernel and the tensor-core WaveNet path."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.forward import OracleMBExWN, synthetic_mel, synthetic_noise
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine(speech_setup):
+    from mbexwn_vocoder_b200.engine import Engine
+    hp, plan, w = speech_setup
+    eng = Engine(plan, w, device=0)
+    yield eng
+    eng.close()
+
+
+def _ref_gemm(a, b, kblocks):
+    rows = a.shape[0]
+    af, bf = a.float().cpu().numpy().astype(np.float64), b.float().cpu().numpy().astype(np.float64)
+    out = np.zeros((rows, b.shape[0]))
+    for a_col, shift, b_col in kblocks:
+        blk = np.zeros((rows, 64))
+        lo, hi = max(0, -shift), min(rows, rows - shift)
+        blk[lo:hi] = af[lo + shift:hi + shift, a_col:a_col + 64]
+        out += blk @ bf[:, b_col:b_col + 64].T
+    return out
+
+
+@pytest.mark.parametrize("rows,n,kblocks", [
+    (128, 128, [(0, 0, 0)]),
+    (256, 128, [(0, 0, 0), (64, 0, 64)]),
+    (300, 256, [(0, 0, 0), (64, 0, 64), (0, -3, 128), (64, 5, 192)]),
+    (1000, 320, [(64 * i, s, 64 * (3 * i + j)) for i in range(3) for j, s in enumerate((-8, 0, 8))]),
+])
+def test_tap_gemm_exact(engine, rows, n, kblocks):
+    g = torch.Generator(device="cpu").manual_seed(rows + n)
+    a_cols = max(k[0] for k in kblocks) + 64
+    b_cols = max(k[2] for k in kblocks) + 64
+    # small integers are exact in bf16 and in the fp32 accumulator: the result must match bit for bit
+    a = torch.randint(-4, 5, (rows, a_cols), generator=g).to(torch.bfloat16).cuda()
+    b = torch.randint(-4, 5, (n, b_cols), generator=g).to(torch.bfloat16).cuda()
+    out = engine.tc_gemm(a, b, np.array(kblocks)).cpu().numpy()
+    ref = _ref_gemm(a, b, kblocks)
+    assert np.array_equal(out, ref.astype(np.float32))
+
+
+def test_tap_gemm_random(engine):
+    g = torch.Generator(device="cpu").manual_seed(7)
+    rows, n = 777, 640
+    kblocks = [(64 * c, (t - 1) * 4, t * 320 + 64 * c) for t in range(3) for c in range(5)]
+    a = torch.randn(rows, 320, generator=g).to(torch.bfloat16).cuda()
+    b = (torch.randn(n, 960, generator=g) * 0.05).to(torch.bfloat16).cuda()
+    out = engine.tc_gemm(a, b, np.array(kblocks)).cpu().numpy()
+    ref = _ref_gemm(a, b, kblocks)
+    assert np.abs(out - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+def _snr_db(ref, test):
+    ref = np.asarray(ref, dtype=np.float64)
+    err = np.asarray(test, dtype=np.float64) - ref
+    return 10 * np.log10(np.sum(ref ** 2) / max(np.sum(err ** 2), 1e-300))
+
+
+@pytest.mark.parametrize("precision,tol,snr", [("bf16x3", 1e-4, 60.0), ("bf16", 5e-2, 35.0)])
+def test_wavenet_tc_parity(engine, speech_setup, precision, tol, snr):
+    hp, plan, w = speech_setup
+    oracle = OracleMBExWN(hp, w, torch.float32)
+    lengths = [23, 57, 10]
+    mels = [synthetic_mel(t, i) for i, t in enumerate(lengths)]
+    noise = [synthetic_noise(t * plan.steps_per_frame, i) for i, t in enumerate(lengths)]
+    f0 = [oracle.generate_f0(torch.as_tensor(m[None])).numpy()[0] for m in mels]
+    out, tp = engine.forward(mels, noise=noise, f0=f0, precision=precision, taps=["index", "skip", "subbands", "excitation"])
+    for u, t in enumerate(lengths):
+        ref = oracle.forward(mels[u][None], noise[u][None], f0_override=f0[u][None])
+        assert np.array_equal(tp["index"][u], ref["index"][0])
+        for st in ["skip", "subbands", "excitation"]:
+            r = np.asarray(ref[st][0]).reshape(-1)
+            e = np.abs(tp[st][u] - r).max() / np.abs(r).max()
+            print(f"{precision} utt {u} {st}: max|err|/peak {e:.3e}")
+            assert e <= tol, st
+        s = _snr_db(ref["waveform"][0], out[u])
+        e = np.abs(out[u] - ref["waveform"][0]).max() / np.abs(ref["waveform"][0]).max()
+        print(f"{precision} utt {u} waveform: max|err|/peak {e:.3e}  SNR {s:.1f} dB")
+        assert s >= snr and e <= tol
