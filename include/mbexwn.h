@@ -157,8 +157,14 @@ MBEXWN_API int mbexwn_tap(mbexwn_handle_t h, const char* name, int32_t n_frames,
 /* Number of kernel launches issued by the last mbexwn_forward on this handle. */
 MBEXWN_API int mbexwn_last_launch_count(mbexwn_handle_t h);
 
-/* Options: "debug_taps" (default 1): keep the phase / index / pulse / vtf / lifter_index taps in the workspace. */
+/* Options: "debug_taps" (default 1): keep the phase / index / pulse / vtf / lifter_index taps in the workspace;
+ * "stage_timing" (default 0): record CUDA events on the caller's stream at the stage boundaries of each forward. */
 MBEXWN_API int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value);
+
+/* Device time of each stage of the last forward (needs "stage_timing"); ms[MBEXWN_N_STAGES] in the order
+ * f0_net, excitation, cond_conv, wavenet, post_pqmf, vtf_net, stft_ola.  Synchronises on the last event. */
+#define MBEXWN_N_STAGES 7
+MBEXWN_API int mbexwn_stage_ms(mbexwn_handle_t h, float* ms);
 
 /* ---- single kernels on caller-provided buffers (stage-level parity tests; same kernels the forward uses) ---- */
 MBEXWN_API int mbexwn_k_conv1d(mbexwn_handle_t h, const mbexwn_batch_t* grid, const mbexwn_op_t* op, int32_t rate,

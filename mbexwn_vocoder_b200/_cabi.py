@@ -12,6 +12,8 @@ LIB_NAME = "libmbexwn_b200.so"
 ABI_VERSION = 1
 MAX_LAYERS = 64
 MAX_OPS = 32
+N_STAGES = 7
+STAGE_NAMES = ("f0_net", "excitation", "cond_conv", "wavenet", "post_pqmf", "vtf_net", "stft_ola")
 
 PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
@@ -74,6 +76,7 @@ SYMBOLS = {
                              C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mbexwn_last_launch_count": (C.c_int, [C.c_void_p]),
     "mbexwn_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
+    "mbexwn_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mbexwn_k_conv1d": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Op), C.c_int32, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mbexwn_k_tc_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,

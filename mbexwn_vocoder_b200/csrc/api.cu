@@ -17,6 +17,10 @@ struct mbexwn_handle_s {
     std::string error;
     int launches = 0;
     int debug_taps = 1;
+    int stage_timing = 0;
+    cudaEvent_t ev[MBEXWN_N_STAGES + 1] = {};
+    bool ev_ready = false;
+    bool ev_recorded = false;
     mbx::WnTcState tc;
 };
 
@@ -229,6 +233,14 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
     h->launches = 0;
     int rc = 0;
     const long long rows = (long long)b->n_frames * c.steps_per_frame;
+    int stage = 0;
+    h->ev_recorded = false;
+    if (h->stage_timing && !h->ev_ready) {
+        for (int i = 0; i <= MBEXWN_N_STAGES; ++i) MBX_CUDA_CHECK(cudaEventCreate(&h->ev[i]));
+        h->ev_ready = true;
+    }
+    auto mark = [&]() { if (h->stage_timing) cudaEventRecord(h->ev[stage++], s); };
+    mark();
 
     // (1) F0 sub-net (generate_f0, custom_pulsed_generator.py:773-791)
     const float* f0 = b->f0_override;
@@ -241,6 +253,7 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
                                        cudaMemcpyDeviceToDevice, s));
     }
 
+    mark();
     // (2) excitation generator head (generate_excitation, :886-906)
     {
         ExcitationArgs a{};
@@ -257,6 +270,7 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
         h->launches += 3;
     }
 
+    mark();
     // (3) conditioning conv at mel rate; the x10 linear interpolation is fused into the gate (custom_AE_layers.py:282-289)
     {
         const std::string n = std::string(c.wn_name) + "/cond_";
@@ -268,6 +282,7 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
         h->launches++;
     }
 
+    mark();
     // (4) WaveNet (WaveNetAE.call, custom_AE_layers.py:273-346)
     if (precision == MBEXWN_PREC_FP32_SIMT) {
         rc = wavenet_fp32(cx);
@@ -278,6 +293,7 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
                            s, &h->launches, &h->error);
     }
     if (rc) return rc;
+    mark();
 
     // (5) end 1x1 and post 1x1 are both linear: one pre-multiplied C -> S matrix (custom_AE_layers.py:340,
     //     custom_pulsed_generator.py:913-914), then PQMF synthesis (:920-921)
@@ -296,9 +312,11 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
         h->launches += 2;
     }
 
+    mark();
     // (6) VTF sub-net -> cepstrum (generate_specenv, :793-799)
     rc = run_subnet(cx, c.ps_ops, c.n_ps_ops, b->mel, cx.p<float>("ceps"));
     if (rc) return rc;
+    mark();
 
     // (7) STFT-domain filtering + overlap-add (:681-724, :801-836)
     {
@@ -321,6 +339,8 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
         MBX_CUDA_CHECK(launch_ola(oa, cx.g, s));
         h->launches += 2;
     }
+    mark();
+    h->ev_recorded = h->stage_timing != 0;
     return MBEXWN_OK;
 }
 
@@ -355,6 +375,7 @@ int mbexwn_create(const mbexwn_config_t* cfg, mbexwn_handle_t* out) {
 
 void mbexwn_destroy(mbexwn_handle_t h) {
     if (!h) return;
+    if (h->ev_ready) for (int i = 0; i <= MBEXWN_N_STAGES; ++i) cudaEventDestroy(h->ev[i]);
     mbx::wn_tc_destroy(h->tc);
     delete h;
 }
@@ -413,7 +434,16 @@ int mbexwn_last_launch_count(mbexwn_handle_t h) { return h ? h->launches : 0; }
 int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value) {
     if (!h || !name) return MBEXWN_ERR_INVALID;
     if (!strcmp(name, "debug_taps")) { h->debug_taps = value ? 1 : 0; return MBEXWN_OK; }
+    if (!strcmp(name, "stage_timing")) { h->stage_timing = value ? 1 : 0; return MBEXWN_OK; }
     return mbx::fail(h, MBEXWN_ERR_INVALID, std::string("unknown option: ") + name);
+}
+
+int mbexwn_stage_ms(mbexwn_handle_t h, float* ms) {
+    if (!h || !ms) return MBEXWN_ERR_INVALID;
+    if (!h->ev_recorded) return mbx::fail(h, MBEXWN_ERR_INVALID, "no stage timing recorded (set option stage_timing)");
+    MBX_CUDA_CHECK(cudaEventSynchronize(h->ev[MBEXWN_N_STAGES]));
+    for (int i = 0; i < MBEXWN_N_STAGES; ++i) MBX_CUDA_CHECK(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+    return MBEXWN_OK;
 }
 
 int mbexwn_k_conv1d(mbexwn_handle_t h, const mbexwn_batch_t* b, const mbexwn_op_t* op, int32_t rate, const float* x,

@@ -288,6 +288,12 @@ class PreparedBatch:
                                         self.workspace.numel(), self._stream())
         _cabi.check(eng.lib, eng._handle, rc, "mbexwn_forward")
 
+    def stage_ms(self) -> Dict[str, float]:
+        """Device milliseconds per stage of the last run (needs eng.set_option("stage_timing", 1))."""
+        buf = (C.c_float * _cabi.N_STAGES)()
+        _cabi.check(self.eng.lib, self.eng._handle, self.eng.lib.mbexwn_stage_ms(self.eng._handle, buf), "stage_ms")
+        return {n: float(buf[i]) for i, n in enumerate(_cabi.STAGE_NAMES)}
+
     def launches(self) -> int:
         return int(self.eng.lib.mbexwn_last_launch_count(self.eng._handle))
 
