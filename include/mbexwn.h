@@ -128,8 +128,9 @@ MBEXWN_API const char* mbexwn_last_error(mbexwn_handle_t h);
  * "lifters" (n_lifters, n_ceps), "lifter_grid" (n_lifters), "f0_smooth" (n_smooth), "end_post/W" (wn_c, subbands),
  * "end_post/b" (subbands).
  * Tensor-core path (precision != FP32_SIMT), per WaveNet layer i, C padded to cpad = ceil(C / 64) * 64:
- *   "<wn_name>/tc/W1_<i>" bf16 (2*cpad, 2*k*cpad): rows = output channels permuted so that each block of 128 rows is
- *        [64 tanh channels | the matching 64 sigmoid channels]; columns = [hi plane | lo plane], each (tap, cin)-major
+ *   "<wn_name>/tc/W1_<i>" bf16 (2*cpad, 2*k*cpad): rows = output channels permuted so that each tile of 256 rows
+ *        (the last tile may be narrower) is [tanh channels | the matching sigmoid channels]; columns = [hi plane |
+ *        lo plane], each (tap, cin)-major
  *   "<wn_name>/tc/b1_<i>" fp32 (2*cpad) in the same row order
  *   "<wn_name>/tc/R_<i>"  bf16 (2*cpad or cpad for the last layer, 2*cpad): rows = [res channels | skip channels]
  *   "<wn_name>/tc/rb_<i>" fp32 in the same row order */

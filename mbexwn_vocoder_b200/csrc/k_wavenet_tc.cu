@@ -12,17 +12,20 @@
 //
 // Implicit GEMM: the dilated taps are *row-shifted TMA loads* of the same activation tensor; guard rows between
 // utterances hold zeros and TMA zero-fills outside the tensor, which reproduces the reference's per-utterance SAME
-// zero padding without any im2col buffer.  Weight columns are permuted at load so that every 128-wide N tile holds 64
-// tanh channels next to the matching 64 sigmoid channels, so the gate needs no cross-tile exchange.
+// zero padding without any im2col buffer.  Weight columns are permuted at load so that every N tile (256 wide, the
+// last one narrower) holds its tanh channels in the first half and the matching sigmoid channels in the second half,
+// so the gate needs no cross-tile exchange.
 //
 // Precision: operands are bf16, accumulation is fp32 in TMEM.  Activations and weights are stored as bf16 (hi, lo)
 // pairs (x ~ hi + lo, 16 mantissa bits); MBEXWN_PREC_BF16X3 runs three products per K block (hi*hi + lo*hi + hi*lo)
 // simply by listing three times as many K blocks, MBEXWN_PREC_BF16 lists only hi*hi.  The K-block table
 // {A column, A row shift, B column} is the whole "program" of a launch.
 //
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue
-// (TMEM lanes 32*(warp%4)..+31).  smem ring of 6 x (A 128x64 + B 128x64 bf16, SWIZZLE_128B), TMEM double buffered
-// (2 x 128 fp32 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-11 = epilogue
+// (TMEM lanes 32*(warp%4)..+31, two warps per lane quarter taking alternate 32-column chunks).  smem ring of
+// 4 x (A 128x64 + B 256x64 bf16, SWIZZLE_128B), TMEM double buffered (2 x 256 fp32 columns = all 512) so the epilogue
+// of tile i overlaps the MMAs of tile i+1.  The MMA N of a tile is min(256, N - n0), so a narrow last tile costs
+// proportionally less tensor time.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -36,14 +39,15 @@ namespace mbx {
 
 namespace {
 
-constexpr int TILE_M = 128, TILE_N = 128, TILE_K = 64, UMMA_K = 16;
-constexpr int STAGES = 6;
+constexpr int TILE_M = 128, TILE_N = 256, TILE_K = 64, UMMA_K = 16;
+constexpr int STAGES = 4;
 constexpr int A_BYTES = TILE_M * TILE_K * 2, B_BYTES = TILE_N * TILE_K * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int ACC_STAGES = 2;
-constexpr int TMEM_COLS = ACC_STAGES * TILE_N;          // 256, power of two
+constexpr int TMEM_COLS = ACC_STAGES * TILE_N;          // 512 = all of TMEM
 constexpr int MAX_KB = 64;
-constexpr int TC_THREADS = 256;
+constexpr int EPI_WARPS = 8;                            // two warps per TMEM lane quarter, splitting the columns
+constexpr int TC_THREADS = 128 + 32 * EPI_WARPS;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256;
 
 enum Epi { EPI_PLAIN = 0, EPI_GATE = 1, EPI_RESSKIP = 2 };
@@ -165,9 +169,25 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
 
 // ---- epilogues: one thread = one accumulator row -----------------------------------------------------------------
 
-__device__ __forceinline__ void epi_plain(const GemmParams& p, uint32_t tacc, long long row, int n0) {
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// tanh / sigmoid from one ex2 + one rcp each (relative error ~1e-6, saturates cleanly at +-inf)
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - 2.f * rcp_approx(1.f + ex2_approx(x * 2.885390081777927f)); }
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.f + ex2_approx(x * -1.4426950408889634f)); }
+
+// `half` (0/1) selects which alternate 32-column chunks of the tile this warp handles; `width` = valid tile columns.
+
+__device__ __forceinline__ void epi_plain(const GemmParams& p, uint32_t tacc, long long row, int n0, int width, int half) {
     float v[32];
-    for (int q = 0; q < TILE_N / 32; ++q) {
+    for (int q = half; q < width / 32; q += 2) {
         tmem_ld32(tacc + q * 32, v);
         tmem_ld_wait();
         if (row < p.rows) {
@@ -180,9 +200,10 @@ __device__ __forceinline__ void epi_plain(const GemmParams& p, uint32_t tacc, lo
     }
 }
 
-__device__ __forceinline__ void epi_gate(const GemmParams& p, uint32_t tacc, long long row, int n_tile) {
-    // N tile j holds tanh channels [64j, 64j+64) in columns [0,64) and the matching sigmoid channels in [64,128)
-    const int ch0 = n_tile * 64;
+__device__ __forceinline__ void epi_gate(const GemmParams& p, uint32_t tacc, long long row, int n0, int width, int half) {
+    // tile columns [0, width/2) = tanh channels [n0/2, n0/2 + width/2), columns [width/2, width) = their sigmoid partners
+    const int hw = width >> 1;
+    const int ch_tile = n0 >> 1;
     bool valid = false;
     long long rc = 0, rn = 0;
     float w0 = 1.f, w1 = 0.f;
@@ -200,55 +221,72 @@ __device__ __forceinline__ void epi_gate(const GemmParams& p, uint32_t tacc, lon
     }
     const float* c0 = p.cond + rc * 2 * p.c;
     const float* c1 = p.cond + rn * 2 * p.c;
-    const float* bias = p.bias + n_tile * TILE_N;
+    const float* bias = p.bias + n0;
     float zt[32], zs[32];
 #pragma unroll 1
-    for (int q = 0; q < 2; ++q) {
+    for (int q = half; q < hw / 32; q += 2) {
         tmem_ld32(tacc + q * 32, zt);
-        tmem_ld32(tacc + 64 + q * 32, zs);
+        tmem_ld32(tacc + hw + q * 32, zs);
         tmem_ld_wait();
         if (row >= p.rows) continue;
-        uint32_t hi_w[16], lo_w[16];
+        const int ch0 = ch_tile + q * 32;
+        __nv_bfloat16* dst = p.act + row * p.ld_act + ch0;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-            float a[2];
+        for (int i = 0; i < 32; i += 8) {
+            float a[8];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                int ch = ch0 + q * 32 + i + e;
-                float r = 0.f;
-                if (valid && ch < p.c) {
-                    float ct = __fadd_rn(__fmul_rn(__ldg(c0 + ch), w0), __fmul_rn(__ldg(c1 + ch), w1));
-                    float cs = __fadd_rn(__fmul_rn(__ldg(c0 + p.c + ch), w0), __fmul_rn(__ldg(c1 + p.c + ch), w1));
-                    float t = zt[i + e] + __ldg(bias + q * 32 + i + e) + ct;
-                    float s = zs[i + e] + __ldg(bias + 64 + q * 32 + i + e) + cs;
-                    switch (p.gate) {
-                        case GATE_GTU: t = tanhf(t); break;
-                        case GATE_GFU: t = t / (1.f + fabsf(t)); break;
-                        case GATE_GSU: t = t / (1.f + sqrtf(fabsf(t))); break;
-                        default: break;
+            for (int v4 = 0; v4 < 2; ++v4) {
+                const int cb = ch0 + i + 4 * v4;
+                if (valid && cb < p.c) {                      // C is a multiple of 4 on this path
+                    float4 x0 = __ldg(reinterpret_cast<const float4*>(c0 + cb));
+                    float4 x1 = __ldg(reinterpret_cast<const float4*>(c1 + cb));
+                    float4 y0 = __ldg(reinterpret_cast<const float4*>(c0 + p.c + cb));
+                    float4 y1 = __ldg(reinterpret_cast<const float4*>(c1 + p.c + cb));
+                    float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + q * 32 + i) + v4);
+                    float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + hw + q * 32 + i) + v4);
+                    const float ct[4] = {__fadd_rn(__fmul_rn(x0.x, w0), __fmul_rn(x1.x, w1)),
+                                         __fadd_rn(__fmul_rn(x0.y, w0), __fmul_rn(x1.y, w1)),
+                                         __fadd_rn(__fmul_rn(x0.z, w0), __fmul_rn(x1.z, w1)),
+                                         __fadd_rn(__fmul_rn(x0.w, w0), __fmul_rn(x1.w, w1))};
+                    const float cs[4] = {__fadd_rn(__fmul_rn(y0.x, w0), __fmul_rn(y1.x, w1)),
+                                         __fadd_rn(__fmul_rn(y0.y, w0), __fmul_rn(y1.y, w1)),
+                                         __fadd_rn(__fmul_rn(y0.z, w0), __fmul_rn(y1.z, w1)),
+                                         __fadd_rn(__fmul_rn(y0.w, w0), __fmul_rn(y1.w, w1))};
+                    const float bt[4] = {b0.x, b0.y, b0.z, b0.w};
+                    const float bs[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float t = zt[i + 4 * v4 + e] + bt[e] + ct[e];
+                        float sg = zs[i + 4 * v4 + e] + bs[e] + cs[e];
+                        switch (p.gate) {
+                            case GATE_GTU: t = fast_tanh(t); break;
+                            case GATE_GFU: t = t * rcp_approx(1.f + fabsf(t)); break;
+                            case GATE_GSU: t = t * rcp_approx(1.f + sqrtf(fabsf(t))); break;
+                            default: break;
+                        }
+                        a[4 * v4 + e] = t * fast_sigmoid(sg);
                     }
-                    r = t * (1.f / (1.f + expf(-s)));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) a[4 * v4 + e] = 0.f;
                 }
-                a[e] = r;
             }
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(a[0], h0, l0);
-            split_bf16(a[1], h1, l1);
-            hi_w[i / 2] = pack2(h0, h1);
-            lo_w[i / 2] = pack2(l0, l1);
-        }
-        uint4* dst_hi = reinterpret_cast<uint4*>(p.act + row * p.ld_act + ch0 + q * 32);
+            uint32_t hw4[4], lw4[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dst_hi[i] = make_uint4(hi_w[4 * i], hi_w[4 * i + 1], hi_w[4 * i + 2], hi_w[4 * i + 3]);
-        if (p.write_lo) {
-            uint4* dst_lo = reinterpret_cast<uint4*>(p.act + row * p.ld_act + p.cpad + ch0 + q * 32);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst_lo[i] = make_uint4(lo_w[4 * i], lo_w[4 * i + 1], lo_w[4 * i + 2], lo_w[4 * i + 3]);
+            for (int e = 0; e < 8; e += 2) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(a[e], h0, l0);
+                split_bf16(a[e + 1], h1, l1);
+                hw4[e / 2] = pack2(h0, h1);
+                lw4[e / 2] = pack2(l0, l1);
+            }
+            *reinterpret_cast<uint4*>(dst + i) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
+            if (p.write_lo) *reinterpret_cast<uint4*>(dst + p.cpad + i) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
         }
     }
 }
 
-__device__ __forceinline__ void epi_resskip(const GemmParams& p, uint32_t tacc, long long row, int n0) {
+__device__ __forceinline__ void epi_resskip(const GemmParams& p, uint32_t tacc, long long row, int n0, int width, int half) {
     bool valid = false;
     if (row < p.rows) {
         long long lo, hi;
@@ -256,7 +294,7 @@ __device__ __forceinline__ void epi_resskip(const GemmParams& p, uint32_t tacc, 
     }
     float v[32];
 #pragma unroll 1
-    for (int q = 0; q < TILE_N / 32; ++q) {
+    for (int q = half; q < width / 32; q += 2) {
         tmem_ld32(tacc + q * 32, v);
         tmem_ld_wait();
         const int n = n0 + q * 32;
@@ -268,6 +306,9 @@ __device__ __forceinline__ void epi_resskip(const GemmParams& p, uint32_t tacc, 
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 uint4 hv = ph[i], lv = pl[i];
+                float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8 * i));
+                float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8 * i) + 1);
+                const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
                 uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
 #pragma unroll
                 for (int w = 0; w < 4; ++w) {
@@ -277,7 +318,7 @@ __device__ __forceinline__ void epi_resskip(const GemmParams& p, uint32_t tacc, 
                         int idx = i * 8 + w * 2 + e;
                         float old = __bfloat162float(__ushort_as_bfloat16((unsigned short)(hw[w] >> (16 * e)))) +
                                     __bfloat162float(__ushort_as_bfloat16((unsigned short)(lw[w] >> (16 * e))));
-                        o[e] = (n + idx < p.c) ? old + (v[idx] + __ldg(p.bias + n + idx)) : 0.f;
+                        o[e] = (n + idx < p.c) ? old + (v[idx] + bv[w * 2 + e]) : 0.f;
                     }
                     __nv_bfloat16 h0, l0, h1, l1;
                     split_bf16(o[0], h0, l0);
@@ -326,7 +367,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -358,9 +399,12 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(TILE_M, TILE_N);
             uint32_t it = 0, tile_it = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
+                const int n_blk = t % p.tiles_n;
+                int width = p.n_cols - n_blk * TILE_N;
+                width = width > TILE_N ? TILE_N : ((width + 15) & ~15);
+                const uint32_t idesc = make_idesc(TILE_M, width);
                 const uint32_t as = tile_it % ACC_STAGES, aph = (tile_it / ACC_STAGES) & 1;
                 mbar_wait(&tmem_empty[as], aph ^ 1);
                 tc_fence_after();
@@ -383,7 +427,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
     } else if (warp >= 4) {
         // ===== epilogue warps =====
-        const int q4 = warp & 3;
+        const int q4 = warp & 3, half = (warp - 4) >> 2;
         uint32_t tile_it = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
             const int m_blk = t / p.tiles_n, n_blk = t - m_blk * p.tiles_n;
@@ -392,9 +436,11 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
             tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(q4 * 32) << 16) + as * TILE_N;
             const long long row = (long long)m_blk * TILE_M + q4 * 32 + lane;
-            if (EPI == EPI_PLAIN) epi_plain(p, tacc, row, n_blk * TILE_N);
-            if (EPI == EPI_GATE) epi_gate(p, tacc, row, n_blk);
-            if (EPI == EPI_RESSKIP) epi_resskip(p, tacc, row, n_blk * TILE_N);
+            int width = p.n_cols - n_blk * TILE_N;
+            width = width > TILE_N ? TILE_N : ((width + 31) & ~31);
+            if (EPI == EPI_PLAIN) epi_plain(p, tacc, row, n_blk * TILE_N, width, half);
+            if (EPI == EPI_GATE) epi_gate(p, tacc, row, n_blk * TILE_N, width, half);
+            if (EPI == EPI_RESSKIP) epi_resskip(p, tacc, row, n_blk * TILE_N, width, half);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);

@@ -1,7 +1,7 @@
 """Host-side packing of the WaveNet weights for the tcgen05 tap-GEMM (layout: include/mbexwn.h).
 
 * channels are padded to cpad = ceil(C / 64) * 64 (zero weights, zero bias);
-* W1 rows (GEMM N) are permuted so that every block of 128 rows is [64 tanh channels | the matching 64 sigmoid
+* W1 rows (GEMM N) are permuted so that every 256-row tile (the last may be narrower) is [tanh channels | the matching sigmoid
   channels]: the tanh*sigmoid gate (custom_AE_layers.py:309-321) becomes local to one 128-column accumulator tile;
 * res_skip rows are [res channels (cpad) | skip channels (cpad)] (skip only for the last layer);
 * every matrix is stored K-major as bf16 [hi | lo] planes with hi + lo ~ the fp32 value, so the same kernel runs
@@ -18,7 +18,7 @@ from . import weights as W
 from .plan import ModelPlan
 
 TILE_K = 64
-GATE_TILE = 128
+GATE_TILE = 256
 
 
 def hilo(x: np.ndarray) -> torch.Tensor:
@@ -31,8 +31,11 @@ def hilo(x: np.ndarray) -> torch.Tensor:
 def gate_permutation(c: int, cpad: int):
     """For packed row n of W1: (source column in the reference's [tanh(C) | sigmoid(C)] order, valid mask)."""
     n = np.arange(2 * cpad)
-    ch = (GATE_TILE // 2) * (n // GATE_TILE) + (n % (GATE_TILE // 2))
-    is_sig = (n % GATE_TILE) >= GATE_TILE // 2
+    tile = n // GATE_TILE
+    width = np.minimum(GATE_TILE, 2 * cpad - tile * GATE_TILE)      # the last tile may be narrower
+    within = n - tile * GATE_TILE
+    is_sig = within >= width // 2
+    ch = (GATE_TILE // 2) * tile + np.where(is_sig, within - width // 2, within)
     return np.where(is_sig, c + ch, ch), ch < c
 
 

@@ -85,3 +85,40 @@ def test_wavenet_tc_parity(engine, speech_setup, precision, tol, snr):
         e = np.abs(out[u] - ref["waveform"][0]).max() / np.abs(ref["waveform"][0]).max()
         print(f"{precision} utt {u} waveform: max|err|/peak {e:.3e}  SNR {s:.1f} dB")
         assert s >= snr and e <= tol
+
+
+def test_wavenet_tc_parity_c340():
+    """MW-VO-FD geometry: C = 340 is padded to 384 channels inside the tensor-core path (zero weights)."""
+    from mbexwn_vocoder_b200 import get_config_file, weights as W
+    from mbexwn_vocoder_b200.config import read_config
+    from mbexwn_vocoder_b200.engine import Engine
+    from mbexwn_vocoder_b200.plan import build_plan
+    hp = read_config(get_config_file("VOICE"))
+    plan = build_plan(hp)
+    w = W.init_synthetic(plan, seed=13)
+    eng = Engine(plan, w, device=0)
+    oracle = OracleMBExWN(hp, w, torch.float32)
+    lengths = [31, 12]
+    mels = [synthetic_mel(t, 10 + i) for i, t in enumerate(lengths)]
+    noise = [synthetic_noise(t * plan.steps_per_frame, 10 + i) for i, t in enumerate(lengths)]
+    # wide synthetic F0 sweep (45..1400 Hz) with vibrato to exercise every wavetable of the grid
+    f0 = []
+    for i, t in enumerate(lengths):
+        n = t * plan.pulse_per_frame
+        x = np.linspace(0, 1, n)
+        f0.append((45.0 * (1400.0 / 45.0) ** x * (1 + 0.03 * np.sin(2 * np.pi * 5.5 * np.arange(n) / 8000.0))).astype(np.float32))
+    for precision, tol, snr in (("bf16x3", 1e-4, 60.0), ("fp32", 1e-4, 60.0)):
+        out, tp = eng.forward(mels, noise=noise, f0=f0, precision=precision, taps=["index", "phase", "pulse", "skip"])
+        for u in range(len(lengths)):
+            ref = oracle.forward(mels[u][None], noise[u][None], f0_override=f0[u][None])
+            assert np.array_equal(tp["index"][u], ref["index"][0])
+            assert np.array_equal(tp["phase"][u], ref["phase"][0])
+            for st in ("pulse", "skip"):
+                r = np.asarray(ref[st][0]).reshape(-1)
+                e = np.abs(tp[st][u] - r).max() / np.abs(r).max()
+                print(f"C340 {precision} utt {u} {st}: {e:.3e}")
+                assert e <= tol
+            s = _snr_db(ref["waveform"][0], out[u])
+            print(f"C340 {precision} utt {u} waveform SNR {s:.1f} dB")
+            assert s >= snr
+    eng.close()
