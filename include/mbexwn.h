@@ -112,6 +112,7 @@ typedef struct {
     const float* mel;               /* (n_frames, mel_channels) scaled log-mel, guard frames zero */
     const float* noise;             /* (n_frames * steps_per_frame) N(0,1) draws, or NULL => in-kernel Philox(seed) */
     const float* f0_override;       /* (n_frames * pulse_per_frame) Hz, or NULL => F0 sub-net (infer_components, wavegen_1d.py:528-557) */
+    const int32_t* utt_ids;         /* [n_utt] global utterance ids for the Philox stream, or NULL => batch index */
     uint64_t seed;
     float* out;                     /* (n_frames * hop) waveform on the grid */
 } mbexwn_batch_t;

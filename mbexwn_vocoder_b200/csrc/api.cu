@@ -257,7 +257,7 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
     // (2) excitation generator head (generate_excitation, :886-906)
     {
         ExcitationArgs a{};
-        a.f0 = f0; a.noise = b->noise; a.seed = b->seed;
+        a.f0 = f0; a.noise = b->noise; a.seed = b->seed; a.utt_ids = b->utt_ids;
         a.tables = tensor(h, "wavetable", (size_t)(c.wt_n_period + 1) * c.wt_n_tables * 4, &rc); if (!a.tables) return rc;
         a.n_period = c.wt_n_period; a.n_tables = c.wt_n_tables; a.pulse_rate = c.pulse_rate;
         a.nominal_f0 = c.wt_nominal_f0; a.min_tr = c.wt_min_transposition; a.max_tr = c.wt_max_transposition;

@@ -159,7 +159,7 @@ __global__ void pulse_kernel(ExcitationArgs a, FrameGrid g) {
     row[ch] = acc;
     if (ch == 0 && a.sigma != 0.f) {
         const long long lstep = step - lo / a.pulse_channels;
-        float z = a.noise ? a.noise[step] : philox_normal(a.seed, (unsigned)u, (unsigned long long)lstep);
+        float z = a.noise ? a.noise[step] : philox_normal(a.seed, (unsigned)(a.utt_ids ? a.utt_ids[u] : u), (unsigned long long)lstep);
         row[a.pulse_channels] = __fmul_rn(a.sigma, z);
     }
     if (a.phase_out) a.phase_out[n] = phase;

@@ -66,6 +66,7 @@ struct ExcitationArgs {
     const float* f0;        // (frames * pulse_per_frame) Hz at the pulse rate
     const float* noise;     // (frames * steps_per_frame) standard normal, or nullptr => in-kernel Philox
     unsigned long long seed;
+    const int32_t* utt_ids; // global utterance ids for the Philox counter, or nullptr => batch index
     const float* tables;    // (n_period + 1, n_tables)
     int n_period, n_tables;
     float pulse_rate;

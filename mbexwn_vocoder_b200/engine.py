@@ -185,10 +185,14 @@ class Engine:
 
     def forward(self, mels: Sequence[np.ndarray], noise: Optional[Sequence[np.ndarray]] = None,
                 f0: Optional[Sequence[np.ndarray]] = None, precision: str = "fp32", seed: int = 0,
-                taps: Sequence[str] = ()):
-        """mels: list of (T_u, n_mel) float32.  Returns (list of (T_u*hop,) waveforms, {tap: list of arrays})."""
+                taps: Sequence[str] = (), utt_ids: Optional[Sequence[int]] = None):
+        """mels: list of (T_u, n_mel) float32.  Returns (list of (T_u*hop,) waveforms, {tap: list of arrays}).
+
+        utt_ids: global utterance ids keying the in-kernel noise stream (default: position in this batch)."""
         pb = self.prepare([m.shape[0] for m in mels], precision, noise is not None, f0 is not None)
         pb.load(mels, noise, f0)
+        if utt_ids is not None:
+            pb.set_utt_ids(utt_ids)
         pb.run_host(seed)
         out = [w.copy() for w in pb.waveforms()]
         return out, {t: pb.tap(t) for t in taps}
@@ -238,6 +242,12 @@ class PreparedBatch:
         b.noise = self.noise_dev.data_ptr() if with_noise else None
         b.f0_override = self.f0_dev.data_ptr() if with_f0 else None
         b.out = self.out_dev.data_ptr()
+
+    def set_utt_ids(self, utt_ids: Sequence[int]):
+        ids = np.asarray(utt_ids, dtype=np.int32)
+        assert ids.shape == (self.layout.n_utt,)
+        self.utt_ids = torch.from_numpy(ids).to(self.eng.device)
+        self.batch.utt_ids = self.utt_ids.data_ptr()
 
     # bytes moved per run_host call
     @property

@@ -94,3 +94,66 @@ def test_index_bit_exact_and_downstream(engine, oracle, speech_setup, lengths):
             print(f"utt {u} T={t} stage {st}: max|err|/peak = {e:.3e}")
             assert e <= STAGE_TOL, st
         assert _snr_db(ref["waveform"], out[u]) >= 60.0
+
+
+def test_cuda_matches_committed_goldens(engine, speech_setup):
+    """CUDA path vs the fixture minted by tests/golden/make_oracle_goldens.py (no oracle run needed)."""
+    import os
+    hp, plan, w = speech_setup
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_speech_T16.npz"))
+    for precision in ("fp32", "bf16x3"):
+        out, tp = engine.forward([g["mel"]], noise=[g["noise"]], f0=[g["F0"]], precision=precision,
+                                 taps=["phase", "index", "pulse", "subbands", "excitation", "ceps"])
+        assert np.array_equal(tp["index"][0], g["index"]) and np.array_equal(tp["phase"][0], g["phase"])
+        for k in ("pulse", "subbands", "excitation", "ceps"):
+            assert _rel_err(tp[k][0], g[k].reshape(-1)) <= STAGE_TOL, (precision, k)
+        assert _rel_err(out[0], g["waveform"]) <= STAGE_TOL and _snr_db(g["waveform"], out[0]) >= 60.0
+
+
+def test_batch_composition_does_not_change_output(engine, speech_setup):
+    """Sharding invariance: an utterance gives bit-identical samples alone, inside a batch, or in a
+    differently ordered batch -- every kernel works per row with per-utterance boundaries and fixed summation order."""
+    hp, plan, w = speech_setup
+    lengths = [19, 44, 7, 30]
+    mels, noise = _case(lengths, plan)
+    full, _ = engine.forward(mels, noise=noise, precision="bf16x3")
+    order = [2, 0, 3, 1]
+    perm, _ = engine.forward([mels[i] for i in order], noise=[noise[i] for i in order], precision="bf16x3")
+    for k, i in enumerate(order):
+        assert np.array_equal(perm[k], full[i])
+    alone, _ = engine.forward([mels[1]], noise=[noise[1]], precision="bf16x3")
+    assert np.array_equal(alone[0], full[1])
+    halves = engine.forward(mels[:2], noise=noise[:2], precision="bf16x3")[0] + \
+        engine.forward(mels[2:], noise=noise[2:], precision="bf16x3")[0]
+    for a, b in zip(halves, full):
+        assert np.array_equal(a, b)
+
+
+def test_mel_inverter_api(speech_setup):
+    """Drop-in surface: MELInverter(model_id).synth_from_mel((B,T,80)) -> flat float32 of length B*T*hop."""
+    from mbexwn_vocoder_b200.mel_inverter import MELInverter
+    hp, plan, w = speech_setup
+    inv = MELInverter("SPEECH", precision="bf16x3")
+    assert inv.srate == 24000 and inv.hop_size == 300 and inv.mel_channels == 80
+    mel = np.stack([synthetic_mel(20, 7), synthetic_mel(20, 8)])
+    y = inv.synth_from_mel(mel)
+    assert y.dtype == np.float32 and y.shape == (2 * 20 * 300,) and np.isfinite(y).all()
+    y2 = inv.synth_from_mel(mel)
+    assert np.array_equal(y, y2)                       # Philox noise is a pure function of (seed, utterance, position)
+    y3 = inv.synth_from_mel(mel, seed=7)
+    assert not np.array_equal(y, y3)
+    # global utterance ids make the noise stream independent of the batch an utterance travels in
+    a, _ = inv.model.forward([mel[1]], precision="bf16x3", seed=42, utt_ids=[1])
+    assert np.array_equal(a[0], y[20 * 300:])
+    with pytest.raises(RuntimeError):
+        inv.synth_from_mel(np.zeros((1, 5, 64), np.float32))
+    with pytest.raises(NotImplementedError):
+        inv.generate_mel_from_snd(np.zeros(100), 24000)
+
+
+def test_in_kernel_noise_statistics(engine, speech_setup):
+    hp, plan, w = speech_setup
+    mels = [synthetic_mel(200, 3)]
+    _, tp = engine.forward(mels, precision="bf16x3", seed=11, taps=["wn_in"])
+    z = tp["wn_in"][0].reshape(-1, plan.wavenet.c_in)[:, -1] / plan.noise_sigma
+    assert abs(z.mean()) < 0.05 and abs(z.std() - 1.0) < 0.05 and abs((z ** 3).mean()) < 0.15

@@ -1,0 +1,155 @@
+"""The CPU oracle against closed forms of the TF ops it restates and its committed goldens."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import forward as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "oracle_speech_T16.npz")
+
+
+@pytest.fixture(scope="module")
+def oracle(speech_setup):
+    hp, plan, w = speech_setup
+    return O.OracleMBExWN(hp, w, torch.float32)
+
+
+def test_lin_interp_closed_form():
+    """out[tU+u] = x[t](U-u)/U + x[min(t+1,T-1)]u/U for num_pad_end=1, drop_last=True (support_layers.py:99-121)."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 7, 3))
+    for U in (2, 5, 10):
+        y = O.lin_interp(torch.as_tensor(x), U).numpy()
+        assert y.shape == (2, 7 * U, 3)
+        for t in range(7):
+            for u in range(U):
+                ref = x[:, t] * (U - u) / U + x[:, min(t + 1, 6)] * u / U
+                assert np.allclose(y[:, t * U + u], ref, atol=1e-12)
+
+
+def test_pad1d_modes():
+    x = torch.arange(5.0).reshape(1, 5, 1)
+    assert O.pad1d(x, 2, 1, "SYMMETRIC")[0, :, 0].tolist() == [1, 0, 0, 1, 2, 3, 4, 4]
+    assert O.pad1d(x, 2, 1, "EDGE")[0, :, 0].tolist() == [0, 0, 0, 1, 2, 3, 4, 4]
+    assert O.pad1d(x, 1, 2, "CONSTANT")[0, :, 0].tolist() == [0, 0, 1, 2, 3, 4, 0, 0]
+
+
+def test_conv1d_keras_same_is_cross_correlation():
+    x = torch.zeros(1, 9, 1, dtype=torch.float64)
+    x[0, 4, 0] = 1.0
+    kern = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64).reshape(3, 1, 1)
+    y = O.conv1d_keras(x, kern, torch.zeros(1, dtype=torch.float64), "SAME", dilation=2)[0, :, 0]
+    # cross-correlation: y[t] = sum_j k[j] x[t + (j-1)*2]  -> impulse at 4 shows k reversed around it
+    assert y.tolist() == [0, 0, 3, 0, 2, 0, 1, 0, 0]
+
+
+def test_weight_norm_is_g_times_unit_direction():
+    rng = np.random.default_rng(1)
+    v = torch.as_tensor(rng.standard_normal((3, 4, 5)))
+    g = torch.as_tensor(rng.uniform(0.5, 2.0, 5))
+    k = O.weight_norm_kernel(v, g)
+    assert np.allclose(torch.sqrt((k * k).sum(dim=(0, 1))).numpy(), g.numpy())
+
+
+def test_cumsum_chunk_semantics(oracle):
+    """Chunks of 1000 anchored at the start; equal to a float64 running phase mod 1 up to float32 rounding."""
+    rng = np.random.default_rng(2)
+    v = rng.uniform(0.005, 0.07, size=(2, 3456)).astype(np.float32)
+    ph = oracle.stable_cumsum_and_wrap(v)
+    assert ph.dtype == np.float32 and ph.shape == v.shape and ph.min() >= 0 and ph.max() < 1
+    ref = np.mod(np.cumsum(v.astype(np.float64), axis=1), 1.0)
+    d = np.abs(ph - ref)
+    assert np.minimum(d, 1 - d).max() < 2e-4
+    # explicit restatement of the reference's association order for one row
+    row = v[0]
+    pad = np.concatenate((row, np.zeros(4000 - row.size, np.float32))).reshape(4, 1000)
+    cum = np.cumsum(pad, axis=1, dtype=np.float32)
+    off = np.mod(cum[:, -1], np.float32(1))
+    off = np.mod(np.cumsum(np.concatenate(([np.float32(0)], off[:-1])), dtype=np.float32), np.float32(1))
+    manual = np.mod(cum + off[:, None], np.float32(1)).reshape(-1)[:row.size]
+    assert np.array_equal(ph[0], manual)
+
+
+def test_pulse_generator_index_range_and_mix(oracle):
+    n = 5000
+    f0 = np.linspace(oracle.fmin, oracle.fmax, n, dtype=np.float32)[None]
+    r = oracle.pulse_generator(f0)
+    assert r["index"].dtype == np.int32 and r["index"].min() >= 0 and r["index"].max() < oracle.wt.n_period
+    assert np.all((r["frac"] >= 0) & (r["frac"] < 1))
+    assert np.isfinite(r["pulse"]).all()
+
+
+def test_stft_identity_filter_edge_profile(oracle):
+    """Unit filter: STFT -> iSTFT is the identity except the documented edge fade."""
+    T = 12
+    exc = torch.ones(1, T * oracle.hop, dtype=torch.float32)
+    vtf = torch.ones(1, T, oracle.fft_size // 2 + 1, dtype=torch.complex64)
+    y = oracle.stft_filter(exc, vtf, T, T * oracle.pulse_per_frame)[0].numpy()
+    assert y.shape == (T * oracle.hop,)
+    # closed form: gain(t) = sum over the frames j in [0, T) that cover t of w^2[t + 600 - 300 j] / 1.5
+    w2 = (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(1200) / 1200)) ** 2
+    gain = np.zeros(T * 300)
+    for j in range(T):
+        lo, hi = max(0, 300 * j - 600), min(T * 300, 300 * j + 600)
+        gain[lo:hi] += w2[lo + 600 - 300 * j:hi + 600 - 300 * j] / 1.5
+    assert np.abs(y - gain).max() < 1e-5
+    # the numbers quoted in SURVEY.md A.3-Q1
+    assert abs(y[0] - 0.8333) < 1e-3 and abs(y[300] - 1.0) < 1e-3 and np.allclose(y[300:-600], 1.0, atol=1e-4)
+    assert abs(y[-600] - 1.0) < 1e-3 and abs(y[-300] - 0.8333) < 1e-3 and abs(y[-150] - 0.5) < 1e-2
+
+
+def test_vtf_limiter_bounds(oracle):
+    mel = torch.as_tensor(O.synthetic_mel(10, 3)[None])
+    f0 = oracle.generate_f0(mel)
+    vtf = oracle.generate_specenv(mel, f0).abs().numpy()
+    r = oracle.filter_max_log_range
+    assert vtf.max() <= np.exp(r) * (1 + 1e-5) and vtf.min() >= np.exp(-r) * (1 - 1e-5)
+
+
+def test_forward_shapes_and_f0_range(oracle, speech_setup):
+    hp, plan, w = speech_setup
+    T = 9
+    r = oracle.forward(O.synthetic_mel(T, 1)[None], O.synthetic_noise(T * plan.steps_per_frame, 1)[None])
+    assert r["waveform"].shape == (1, T * plan.hop)
+    assert r["F0"].shape == (1, T * plan.pulse_per_frame)
+    assert r["F0"].min() >= plan.f0_min and r["F0"].max() <= plan.f0_max
+    assert r["wn_in"].shape == (1, T * plan.steps_per_frame, plan.pulse_channels + 1)
+    assert r["subbands"].shape == (1, T * plan.steps_per_frame, plan.subbands)
+
+
+def test_batch_independence(oracle, speech_setup):
+    """Utterances of a dense batch are independent: batched == one at a time (per-utterance boundaries, A.3-Q5)."""
+    hp, plan, w = speech_setup
+    T = 8
+    mel = np.stack([O.synthetic_mel(T, i) for i in range(2)])
+    nz = np.stack([O.synthetic_noise(T * plan.steps_per_frame, i) for i in range(2)])
+    both = oracle.forward(mel, nz)["waveform"]
+    for i in range(2):
+        one = oracle.forward(mel[i:i + 1], nz[i:i + 1])["waveform"][0]
+        assert np.abs(one - both[i]).max() <= 2e-5 * np.abs(one).max()
+
+
+def test_oracle_matches_committed_goldens(oracle, speech_setup):
+    hp, plan, w = speech_setup
+    g = np.load(GOLD)
+    torch.set_num_threads(1)
+    r = oracle.forward(g["mel"][None], g["noise"][None])
+    assert np.array_equal(r["index"][0], g["index"])
+    assert np.array_equal(r["phase"][0], g["phase"])
+    for k in ("F0", "pulse", "subbands", "excitation", "ceps", "waveform"):
+        ref = g[k]
+        assert np.abs(np.asarray(r[k][0]) - ref).max() <= 1e-5 * np.abs(ref).max(), k
+
+
+def test_fp32_oracle_tracks_fp64_oracle(speech_setup):
+    """Noise floor of the oracle itself: with the fp32 F0/phase fed to both, later stages agree to ~1e-5."""
+    hp, plan, w = speech_setup
+    o32, o64 = O.OracleMBExWN(hp, w, torch.float32), O.OracleMBExWN(hp, w, torch.float64)
+    T = 10
+    mel, nz = O.synthetic_mel(T, 4)[None], O.synthetic_noise(T * plan.steps_per_frame, 4)[None]
+    r32 = o32.forward(mel, nz)
+    x64 = torch.as_tensor(r32["wn_in"], dtype=torch.float64)
+    y64 = o64.wavenet(x64, torch.as_tensor(mel, dtype=torch.float64))
+    assert np.abs(y64.numpy() - r32["wn_out"]).max() <= 2e-5 * np.abs(r32["wn_out"]).max()
