@@ -160,7 +160,8 @@ MBEXWN_API int mbexwn_tap(mbexwn_handle_t h, const char* name, int32_t n_frames,
 MBEXWN_API int mbexwn_last_launch_count(mbexwn_handle_t h);
 
 /* Options: "debug_taps" (default 1): keep the phase / index / pulse / vtf / lifter_index taps in the workspace;
- * "stage_timing" (default 0): record CUDA events on the caller's stream at the stage boundaries of each forward. */
+ * "stage_timing" (default 0): record CUDA events on the caller's stream at the stage boundaries of each forward;
+ * "tc_cta_group" (1 or 2): tensor-core tiles owned by one CTA or by a CTA pair (cluster of 2, tcgen05 cta_group::2). */
 MBEXWN_API int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value);
 
 /* Device time of each stage of the last forward (needs "stage_timing"); ms[MBEXWN_N_STAGES] in the order

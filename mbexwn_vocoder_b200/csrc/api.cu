@@ -435,6 +435,7 @@ int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value) {
     if (!h || !name) return MBEXWN_ERR_INVALID;
     if (!strcmp(name, "debug_taps")) { h->debug_taps = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "stage_timing")) { h->stage_timing = value ? 1 : 0; return MBEXWN_OK; }
+    if (!strcmp(name, "tc_cta_group")) { h->tc.cta_group = value == 2 ? 2 : 1; return MBEXWN_OK; }
     return mbx::fail(h, MBEXWN_ERR_INVALID, std::string("unknown option: ") + name);
 }
 

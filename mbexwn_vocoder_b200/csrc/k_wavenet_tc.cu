@@ -40,22 +40,22 @@ namespace mbx {
 namespace {
 
 constexpr int TILE_M = 128, TILE_N = 256, TILE_K = 64, UMMA_K = 16;
-constexpr int STAGES = 4;
-constexpr int A_BYTES = TILE_M * TILE_K * 2, B_BYTES = TILE_N * TILE_K * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int A_BYTES = TILE_M * TILE_K * 2;            // one A operand tile (128 rows x 64 bf16)
+constexpr int RING_BYTES = 192 * 1024;                  // A ring + B ring
 constexpr int ACC_STAGES = 2;
+constexpr int MAX_RING = 8;
 constexpr int TMEM_COLS = ACC_STAGES * TILE_N;          // 512 = all of TMEM
 constexpr int MAX_KB = 64;
 constexpr int EPI_WARPS = 8;                            // two warps per TMEM lane quarter, splitting the columns
 constexpr int TC_THREADS = 128 + 32 * EPI_WARPS;
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256;
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)RING_BYTES + 512;
 
 enum Epi { EPI_PLAIN = 0, EPI_GATE = 1, EPI_RESSKIP = 2 };
 
 struct KBlock {
-    int a_col;      // first A column (elements) of this K block
+    int a_col;      // first A column (elements) of the hi plane for this K block
     int a_shift;    // row shift of the A tile (dilated tap)
-    int b_col;      // first B column (elements)
+    int b_col;      // first B column (elements) of the hi plane
 };
 
 struct alignas(64) GemmParams {
@@ -63,6 +63,8 @@ struct alignas(64) GemmParams {
     CUtensorMap tm_b;
     KBlock kb[MAX_KB];
     int n_kb;
+    int n_terms;            // 1: hi*hi;  3: hi*hi + lo*hi + hi*lo, the lo planes sit a_lo_off / b_lo_off columns further
+    int a_lo_off, b_lo_off;
     long long rows;         // M
     int n_cols;             // N (multiple of 8; tiles are masked)
     int tiles_m, tiles_n;
@@ -97,7 +99,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t addr = smem_u32(bar), done = 0;
+    const long long t0 = clock64();
     while (!done) {
+        if (clock64() - t0 > 20000000000LL) __trap();      // ~10 s: a protocol bug must not hang the device
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -111,6 +115,41 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-CTA TMA load: data lands in this CTA's smem, the transaction bytes are reported to the pair leader's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* tm, uint32_t leader_bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -347,95 +386,179 @@ __device__ __forceinline__ void epi_resskip(const GemmParams& p, uint32_t tacc, 
     }
 }
 
-template <int EPI>
+// Operand-ring pipeline.  A tiles (128 rows x 64 K) and B tiles (the CTA's share of the N rows x 64 K) travel through
+// two independent smem rings, each slot with its own full/empty mbarrier pair, so an operand that several products
+// need is loaded once: per K block the split precision issues hi*hi, lo*hi, hi*lo from {A_hi, A_lo, B_hi, B_lo}
+// (4 loads for 3 products instead of 6).
+//
+// CG = 1: one CTA per 128 x 256 tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2) owns a 256 x 256 tile: each CTA
+// loads its own 128 rows of A and *half* of the B rows, the leader issues M = 256 MMAs that read both halves, each CTA
+// keeps the accumulators of its own rows in its own TMEM and runs its own epilogue.  Halves the per-SM ingest of B.
+template <int EPI, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wn_gemm_kernel(const __grid_constant__ GemmParams p) {
+    constexpr int B_BYTES = (TILE_N / CG) * TILE_K * 2;
+    constexpr int NA = CG == 1 ? 4 : 6;
+    constexpr int NB = CG == 1 ? 4 : 6;
+    static_assert(NA * A_BYTES + NB * B_BYTES <= RING_BYTES && NA <= MAX_RING && NB <= MAX_RING, "ring sizes");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full = empty_bar + STAGES;
+    uint8_t* ring_a = smem;
+    uint8_t* ring_b = smem + NA * A_BYTES;
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
+    uint64_t* empty_a = full_a + MAX_RING;
+    uint64_t* full_b = empty_a + MAX_RING;
+    uint64_t* empty_b = full_b + MAX_RING;
+    uint64_t* tmem_full = empty_b + MAX_RING;
     uint64_t* tmem_empty = tmem_full + ACC_STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = p.tiles_m * p.tiles_n;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+    const bool leader = rank == 0;
+    const int tiles_mg = (p.tiles_m + CG - 1) / CG;                 // M tiles per CTA group
+    const int n_tiles = tiles_mg * p.tiles_n;
+    const int group = blockIdx.x / CG, n_groups = gridDim.x / CG;
+    const int ops_a = p.n_terms == 3 ? 2 : 1;                       // A / B tiles per K block
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_b) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
+        for (int s = 0; s < NA; ++s) { mbar_init(&full_a[s], CG); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < NB; ++s) { mbar_init(&full_b[s], CG); mbar_init(&empty_b[s], 1); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], CG * EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();                                // peer barriers are initialised before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (one thread per CTA) =====
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int m_blk = t / p.tiles_n, n_blk = t - m_blk * p.tiles_n;
-                const int m0 = m_blk * TILE_M, n0 = n_blk * TILE_N;
-                for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
-                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                    tma_load_2d(&p.tm_a, &full_bar[s], sa, p.kb[kb].a_col, m0 + p.kb[kb].a_shift);
-                    tma_load_2d(&p.tm_b, &full_bar[s], sa + A_BYTES, p.kb[kb].b_col, n0);
+            uint32_t ia = 0, ib = 0;
+            for (int t = group; t < n_tiles; t += n_groups) {
+                const int m_grp = t / p.tiles_n, n_blk = t - m_grp * p.tiles_n;
+                const int m0 = (m_grp * CG + (int)rank) * TILE_M;
+                int width = p.n_cols - n_blk * TILE_N;
+                width = width > TILE_N ? TILE_N : ((width + 15) & ~15);
+                const int nb0 = n_blk * TILE_N + (int)rank * (width / CG);      // this CTA's share of the B rows
+                for (int kb = 0; kb < p.n_kb; ++kb) {
+                    for (int o = 0; o < ops_a; ++o) {
+                        {   // A tile (hi, then lo)
+                            const uint32_t s = ia % NA, ph = (ia / NA) & 1;
+                            ++ia;
+                            mbar_wait(&empty_a[s], ph ^ 1);
+                            const int col = p.kb[kb].a_col + (o ? p.a_lo_off : 0);
+                            if (CG == 1) {
+                                mbar_expect_tx(&full_a[s], A_BYTES);
+                                tma_load_2d(&p.tm_a, &full_a[s], ring_a + s * A_BYTES, col, m0 + p.kb[kb].a_shift);
+                            } else {
+                                const uint32_t lbar = map_to_cta(smem_u32(&full_a[s]), 0);
+                                if (leader) mbar_expect_tx(&full_a[s], CG * A_BYTES);
+                                tma_load_2d_2sm(&p.tm_a, lbar, ring_a + s * A_BYTES, col, m0 + p.kb[kb].a_shift);
+                                if (!leader) mbar_arrive_cluster(lbar);
+                            }
+                        }
+                        {   // B tile (hi, then lo)
+                            const uint32_t s = ib % NB, ph = (ib / NB) & 1;
+                            ++ib;
+                            mbar_wait(&empty_b[s], ph ^ 1);
+                            const int col = p.kb[kb].b_col + (o ? p.b_lo_off : 0);
+                            if (CG == 1) {
+                                mbar_expect_tx(&full_b[s], B_BYTES);
+                                tma_load_2d(&p.tm_b, &full_b[s], ring_b + s * B_BYTES, col, nb0);
+                            } else {
+                                const uint32_t lbar = map_to_cta(smem_u32(&full_b[s]), 0);
+                                if (leader) mbar_expect_tx(&full_b[s], CG * B_BYTES);
+                                tma_load_2d_2sm(&p.tm_b, lbar, ring_b + s * B_BYTES, col, nb0);
+                                if (!leader) mbar_arrive_cluster(lbar);
+                            }
+                        }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            uint32_t it = 0, tile_it = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
+        // ===== MMA issuer (one thread of the leader CTA) =====
+        if (lane == 0 && leader) {
+            uint32_t ia = 0, ib = 0, tile_it = 0;
+            auto mma4 = [&](uint32_t tacc, uint32_t sa, uint32_t sb, uint32_t idesc, bool first) {
+                const uint64_t da = make_smem_desc(smem_u32(ring_a + sa * A_BYTES));
+                const uint64_t db = make_smem_desc(smem_u32(ring_b + sb * B_BYTES));
+#pragma unroll
+                for (int k = 0; k < TILE_K / UMMA_K; ++k) {
+                    // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16-byte units
+                    if (CG == 1) tc_mma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                    else tc_mma_bf16_2sm(tacc, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                }
+            };
+            auto commit = [&](uint64_t* bar) { if (CG == 1) tc_commit(bar); else tc_commit_2sm(bar); };
+            for (int t = group; t < n_tiles; t += n_groups, ++tile_it) {
                 const int n_blk = t % p.tiles_n;
                 int width = p.n_cols - n_blk * TILE_N;
                 width = width > TILE_N ? TILE_N : ((width + 15) & ~15);
-                const uint32_t idesc = make_idesc(TILE_M, width);
+                const uint32_t idesc = make_idesc(TILE_M * CG, width);
                 const uint32_t as = tile_it % ACC_STAGES, aph = (tile_it / ACC_STAGES) & 1;
                 mbar_wait(&tmem_empty[as], aph ^ 1);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + as * TILE_N;
-                for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
-                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                    mbar_wait(&full_bar[s], ph);
+                for (int kb = 0; kb < p.n_kb; ++kb) {
+                    const uint32_t sa_hi = ia % NA, pa_hi = (ia / NA) & 1;
+                    const uint32_t sb_hi = ib % NB, pb_hi = (ib / NB) & 1;
+                    mbar_wait(&full_a[sa_hi], pa_hi);
+                    mbar_wait(&full_b[sb_hi], pb_hi);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
-#pragma unroll
-                    for (int k = 0; k < TILE_K / UMMA_K; ++k) {
-                        // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16-byte units
-                        tc_mma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    mma4(tacc, sa_hi, sb_hi, idesc, kb == 0);                      // hi * hi
+                    if (p.n_terms == 3) {
+                        const uint32_t sa_lo = (ia + 1) % NA, pa_lo = ((ia + 1) / NA) & 1;
+                        const uint32_t sb_lo = (ib + 1) % NB, pb_lo = ((ib + 1) / NB) & 1;
+                        mbar_wait(&full_a[sa_lo], pa_lo);
+                        tc_fence_after();
+                        mma4(tacc, sa_lo, sb_hi, idesc, false);                    // lo * hi
+                        commit(&empty_a[sa_lo]);
+                        commit(&empty_b[sb_hi]);
+                        mbar_wait(&full_b[sb_lo], pb_lo);
+                        tc_fence_after();
+                        mma4(tacc, sa_hi, sb_lo, idesc, false);                    // hi * lo
+                        commit(&empty_a[sa_hi]);
+                        commit(&empty_b[sb_lo]);
+                        ia += 2;
+                        ib += 2;
+                    } else {
+                        commit(&empty_a[sa_hi]);
+                        commit(&empty_b[sb_hi]);
+                        ia += 1;
+                        ib += 1;
                     }
-                    tc_commit(&empty_bar[s]);          // frees the smem stage once these MMAs retire
                 }
-                tc_commit(&tmem_full[as]);             // accumulator complete
+                commit(&tmem_full[as]);                // accumulator complete (both CTAs of a pair are told)
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue warps =====
+        // ===== epilogue warps: every CTA drains the accumulators of its own 128 rows =====
         const int q4 = warp & 3, half = (warp - 4) >> 2;
         uint32_t tile_it = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
-            const int m_blk = t / p.tiles_n, n_blk = t - m_blk * p.tiles_n;
+        for (int t = group; t < n_tiles; t += n_groups, ++tile_it) {
+            const int m_grp = t / p.tiles_n, n_blk = t - m_grp * p.tiles_n;
             const uint32_t as = tile_it % ACC_STAGES, aph = (tile_it / ACC_STAGES) & 1;
             mbar_wait(&tmem_full[as], aph);
             tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(q4 * 32) << 16) + as * TILE_N;
-            const long long row = (long long)m_blk * TILE_M + q4 * 32 + lane;
+            const long long row = (long long)(m_grp * CG + (int)rank) * TILE_M + q4 * 32 + lane;
             int width = p.n_cols - n_blk * TILE_N;
             width = width > TILE_N ? TILE_N : ((width + 31) & ~31);
             if (EPI == EPI_PLAIN) epi_plain(p, tacc, row, n_blk * TILE_N, width, half);
@@ -443,15 +566,20 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
             if (EPI == EPI_RESSKIP) epi_resskip(p, tacc, row, n_blk * TILE_N, width, half);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (lane == 0) {
+                if (CG == 1 || leader) mbar_arrive(&tmem_empty[as]);
+                else mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));
+            }
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();                                // nobody leaves while the pair still uses its smem / TMEM
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -477,10 +605,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct Impl {
     EncodeTiledFn encode = nullptr;
     int sm_count = 0;
-    bool attrs_set = false;
+    int cta_group = 1;          // 1: one CTA per tile;  2: CTA pairs (cluster of 2, tcgen05 cta_group::2)
 };
 
 int make_map(Impl* im, CUtensorMap* tm, const void* base, long long rows, long long cols, int box_rows, std::string* err) {
+    if (box_rows == TILE_N) box_rows = TILE_N / im->cta_group;      // a CTA of a pair loads half of the B rows
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
     cuuint32_t box[2] = {(cuuint32_t)TILE_K, (cuuint32_t)box_rows};
@@ -510,9 +639,12 @@ int ensure_impl(WnTcState& st, std::string* err) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&im->sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t a = cudaFuncSetAttribute(wn_gemm_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (a == cudaSuccess) a = cudaFuncSetAttribute(wn_gemm_kernel<EPI_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (a == cudaSuccess) a = cudaFuncSetAttribute(wn_gemm_kernel<EPI_RESSKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t a = cudaSuccess;
+    const void* fns[6] = {(const void*)wn_gemm_kernel<EPI_PLAIN, 1>, (const void*)wn_gemm_kernel<EPI_GATE, 1>,
+                          (const void*)wn_gemm_kernel<EPI_RESSKIP, 1>, (const void*)wn_gemm_kernel<EPI_PLAIN, 2>,
+                          (const void*)wn_gemm_kernel<EPI_GATE, 2>, (const void*)wn_gemm_kernel<EPI_RESSKIP, 2>};
+    for (int i = 0; i < 6 && a == cudaSuccess; ++i)
+        a = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (a != cudaSuccess) {
         if (err) *err = std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(a);
         delete im;
@@ -526,27 +658,39 @@ template <int EPI>
 cudaError_t launch_gemm(Impl* im, GemmParams& p, cudaStream_t s) {
     p.tiles_m = (int)((p.rows + TILE_M - 1) / TILE_M);
     p.tiles_n = (p.n_cols + TILE_N - 1) / TILE_N;
-    int n_tiles = p.tiles_m * p.tiles_n;
-    int grid = n_tiles < im->sm_count ? n_tiles : im->sm_count;
-    wn_gemm_kernel<EPI><<<grid, TC_THREADS, SMEM_BYTES, s>>>(p);
-    return cudaGetLastError();
+    const int cg = im->cta_group;
+    const int n_tiles = ((p.tiles_m + cg - 1) / cg) * p.tiles_n;
+    int groups = im->sm_count / cg;
+    if (n_tiles < groups) groups = n_tiles;
+    if (cg == 1) {
+        wn_gemm_kernel<EPI, 1><<<groups, TC_THREADS, SMEM_BYTES, s>>>(p);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(groups * 2);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, wn_gemm_kernel<EPI, 2>, p);
 }
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// K-block program: n_terms in {1, 3}: (A hi, B hi), (A lo, B hi), (A hi, B lo)
-int build_kblocks(KBlock* kb, int n_taps, const int* shifts, int cpad, int n_terms) {
+// K-block program of a launch: one entry per (tap, 64-channel block); the lo planes are addressed by fixed offsets.
+int build_kblocks(KBlock* kb, int n_taps, const int* shifts, int cpad) {
     int n = 0;
-    const int kw = n_taps * cpad;              // width of one weight plane (hi or lo)
-    for (int term = 0; term < n_terms; ++term) {
-        const int a_base = (term == 1) ? cpad : 0;
-        const int b_base = (term == 2) ? kw : 0;
-        for (int tap = 0; tap < n_taps; ++tap)
-            for (int cb = 0; cb < cpad / TILE_K; ++cb) {
-                if (n >= MAX_KB) return -1;
-                kb[n++] = KBlock{a_base + cb * TILE_K, shifts[tap], b_base + tap * cpad + cb * TILE_K};
-            }
-    }
+    for (int tap = 0; tap < n_taps; ++tap)
+        for (int cb = 0; cb < cpad / TILE_K; ++cb) {
+            if (n >= MAX_KB) return -1;
+            kb[n++] = KBlock{cb * TILE_K, shifts[tap], tap * cpad + cb * TILE_K};
+        }
     return n;
 }
 
@@ -572,7 +716,8 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
     const int n_terms = precision == MBEXWN_PREC_BF16X3 ? 3 : 1;
     const std::string n = c.wn_name;
     if (c.wn_c % 4) { if (error) *error = "tensor-core path needs n_channels % 4 == 0"; return MBEXWN_ERR_UNSUPPORTED; }
-    if (c.wn_k * (cpad / TILE_K) * n_terms > MAX_KB) { if (error) *error = "K-block table too small"; return MBEXWN_ERR_UNSUPPORTED; }
+    if (c.wn_k * (cpad / TILE_K) > MAX_KB) { if (error) *error = "K-block table too small"; return MBEXWN_ERR_UNSUPPORTED; }
+    im->cta_group = st.cta_group == 2 ? 2 : 1;
 
     float* h0f = reinterpret_cast<float*>(slot("h0f"));
     __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(slot("h2"));
@@ -618,7 +763,8 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         if ((rc = make_map(im, &p1.tm_b, w1, n1, k1, TILE_N, error))) return rc;
         int shifts[16];
         for (int t = 0; t < c.wn_k; ++t) shifts[t] = (t - (c.wn_k - 1) / 2) * d;
-        p1.n_kb = build_kblocks(p1.kb, c.wn_k, shifts, cpad, n_terms);
+        p1.n_kb = build_kblocks(p1.kb, c.wn_k, shifts, cpad);
+        p1.n_terms = n_terms; p1.a_lo_off = cpad; p1.b_lo_off = c.wn_k * cpad;
         p1.rows = rows; p1.n_cols = n1; p1.bias = b1; p1.cond = cond; p1.act = a2; p1.ld_act = 2 * cpad;
         p1.c = c.wn_c; p1.cpad = cpad; p1.lin_up = c.wn_cond_lin_up; p1.gate = c.wn_gate; p1.write_lo = n_terms == 3;
         p1.steps_per_frame = c.steps_per_frame; p1.grid = g;
@@ -629,7 +775,8 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         p2.tm_a = tm_a;
         if ((rc = make_map(im, &p2.tm_b, w2, n2, k2, TILE_N, error))) return rc;
         int zero = 0;
-        p2.n_kb = build_kblocks(p2.kb, 1, &zero, cpad, n_terms);
+        p2.n_kb = build_kblocks(p2.kb, 1, &zero, cpad);
+        p2.n_terms = n_terms; p2.a_lo_off = cpad; p2.b_lo_off = cpad;
         p2.rows = rows; p2.n_cols = n2; p2.bias = b2; p2.h = h2; p2.ld_h = 2 * cpad; p2.skip = skip;
         p2.c = c.wn_c; p2.cpad = cpad; p2.res_cols = last ? 0 : cpad; p2.first = i == 0;
         p2.steps_per_frame = c.steps_per_frame; p2.grid = g;
@@ -647,7 +794,9 @@ int wn_tc_gemm_test(WnTcState& st, const void* a_bf16, long long rows, int a_col
     if (rc) return rc;
     Impl* im = reinterpret_cast<Impl*>(st.impl);
     if (n_kb < 1 || n_kb > MAX_KB) return MBEXWN_ERR_INVALID;
+    im->cta_group = st.cta_group == 2 ? 2 : 1;
     GemmParams p{};
+    p.n_terms = 1;
     if ((rc = make_map(im, &p.tm_a, a_bf16, rows, a_cols, TILE_M, error))) return rc;
     if ((rc = make_map(im, &p.tm_b, b_bf16, n, b_cols, TILE_N, error))) return rc;
     for (int i = 0; i < n_kb; ++i) p.kb[i] = KBlock{kblocks[3 * i], kblocks[3 * i + 1], kblocks[3 * i + 2]};

@@ -10,6 +10,7 @@ namespace mbx {
 
 struct WnTcState {
     bool ready = false;
+    int cta_group = 1;          // option "tc_cta_group": 1 = one CTA per tile, 2 = CTA pairs (cta_group::2)
     void* impl = nullptr;
 };
 

@@ -29,13 +29,20 @@ def _ref_gemm(a, b, kblocks):
     return out
 
 
+@pytest.fixture(params=[1, 2], ids=["cta_group1", "cta_group2"])
+def cg(request, engine):
+    engine.set_option("tc_cta_group", request.param)
+    yield request.param
+    engine.set_option("tc_cta_group", 1)
+
+
 @pytest.mark.parametrize("rows,n,kblocks", [
     (128, 128, [(0, 0, 0)]),
     (256, 128, [(0, 0, 0), (64, 0, 64)]),
     (300, 256, [(0, 0, 0), (64, 0, 64), (0, -3, 128), (64, 5, 192)]),
     (1000, 320, [(64 * i, s, 64 * (3 * i + j)) for i in range(3) for j, s in enumerate((-8, 0, 8))]),
 ])
-def test_tap_gemm_exact(engine, rows, n, kblocks):
+def test_tap_gemm_exact(engine, cg, rows, n, kblocks):
     g = torch.Generator(device="cpu").manual_seed(rows + n)
     a_cols = max(k[0] for k in kblocks) + 64
     b_cols = max(k[2] for k in kblocks) + 64
@@ -47,7 +54,7 @@ def test_tap_gemm_exact(engine, rows, n, kblocks):
     assert np.array_equal(out, ref.astype(np.float32))
 
 
-def test_tap_gemm_random(engine):
+def test_tap_gemm_random(engine, cg):
     g = torch.Generator(device="cpu").manual_seed(7)
     rows, n = 777, 640
     kblocks = [(64 * c, (t - 1) * 4, t * 320 + 64 * c) for t in range(3) for c in range(5)]
@@ -65,7 +72,7 @@ def _snr_db(ref, test):
 
 
 @pytest.mark.parametrize("precision,tol,snr", [("bf16x3", 1e-4, 60.0), ("bf16", 5e-2, 35.0)])
-def test_wavenet_tc_parity(engine, speech_setup, precision, tol, snr):
+def test_wavenet_tc_parity(engine, cg, speech_setup, precision, tol, snr):
     hp, plan, w = speech_setup
     oracle = OracleMBExWN(hp, w, torch.float32)
     lengths = [23, 57, 10]
