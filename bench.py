@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cta-group", type=int, default=1, choices=[1, 2], help="tcgen05 tiles per CTA (1) or per CTA pair (2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -200,6 +201,7 @@ def main():
     eng, plan = inv.model, inv.plan
     eng.set_option("debug_taps", 0)
     eng.set_option("stage_timing", 1)
+    eng.set_option("tc_cta_group", args.cta_group)
     mels, noise = synthetic_batch(batch, frames, plan.steps_per_frame, seed0=rank * batch)
     pb = eng.prepare([frames] * batch, precision=args.precision, with_noise=True)
     pb.load(mels, noise)
@@ -292,7 +294,7 @@ def main():
                   "fp32": "f32"}[args.precision],
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "per_gpu_batch": batch, "frames": frames,
-                   "precision": args.precision, "parallelism": f"dp{world} (independent utterances, no collective)",
+                   "precision": args.precision, "tc_cta_group": args.cta_group, "parallelism": f"dp{world} (independent utterances, no collective)",
                    "l2": "per-step working set (activations) is >> 126 MB L2; no flush needed"},
         "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": pb.h2d_bytes, "d2h_bytes_per_step": pb.d2h_bytes,
                 "ms_per_step": 1e3 * e2e_s / args.steps},

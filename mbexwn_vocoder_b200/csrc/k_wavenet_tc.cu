@@ -325,64 +325,109 @@ __device__ __forceinline__ void epi_gate(const GemmParams& p, uint32_t tacc, lon
     }
 }
 
-__device__ __forceinline__ void epi_resskip(const GemmParams& p, uint32_t tacc, long long row, int n0, int width, int half) {
-    bool valid = false;
-    if (row < p.rows) {
-        long long lo, hi;
-        valid = utt_bounds(p.grid, p.steps_per_frame, row, lo, hi);
+// res/skip epilogue.  The old values of the residual stream / skip sum do not depend on the accumulators, so their
+// global loads are issued *before* the wait on the MMA (chunk 0) and one chunk ahead inside the loop: the read latency
+// hides behind the tensor work instead of serialising behind it, and every thread keeps 8 x 16 B loads in flight.
+struct ResSkipCtx {
+    bool valid;
+    long long row;
+    int n0, width, half;
+};
+
+__device__ __forceinline__ void resskip_load_old(const GemmParams& p, const ResSkipCtx& c, int q, uint4 (&old)[8]) {
+    const int n = c.n0 + q * 32;
+    if (!c.valid || q >= c.width / 32 || n >= p.n_cols) return;
+    if (n < p.res_cols) {
+        const uint4* ph = reinterpret_cast<const uint4*>(p.h + c.row * p.ld_h + n);
+        const uint4* pl = reinterpret_cast<const uint4*>(p.h + c.row * p.ld_h + p.cpad + n);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { old[i] = ph[i]; old[4 + i] = pl[i]; }
+    } else if (!p.first) {
+        const int sc = n - p.res_cols;
+        const uint4* ps = reinterpret_cast<const uint4*>(p.skip + c.row * p.c + sc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (sc + 4 * i < p.c) old[i] = ps[i];
     }
-    float v[32];
-#pragma unroll 1
-    for (int q = half; q < width / 32; q += 2) {
-        tmem_ld32(tacc + q * 32, v);
-        tmem_ld_wait();
-        const int n = n0 + q * 32;
-        if (!valid || n >= p.n_cols) continue;
-        if (n < p.res_cols) {
-            // residual stream: h <- h + rs, kept as a bf16 (hi, lo) pair (guard rows stay zero: never written)
-            uint4* ph = reinterpret_cast<uint4*>(p.h + row * p.ld_h + n);
-            uint4* pl = reinterpret_cast<uint4*>(p.h + row * p.ld_h + p.cpad + n);
+}
+
+__device__ __forceinline__ void resskip_store(const GemmParams& p, const ResSkipCtx& c, int q, const float (&v)[32], const uint4 (&old)[8]) {
+    const int n = c.n0 + q * 32;
+    if (!c.valid || n >= p.n_cols) return;
+    if (n < p.res_cols) {
+        // residual stream: h <- h + rs, kept as a bf16 (hi, lo) pair (guard rows stay zero: never written)
+        uint4* ph = reinterpret_cast<uint4*>(p.h + c.row * p.ld_h + n);
+        uint4* pl = reinterpret_cast<uint4*>(p.h + c.row * p.ld_h + p.cpad + n);
+        uint4 oh[4], ol[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                uint4 hv = ph[i], lv = pl[i];
-                float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8 * i));
-                float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8 * i) + 1);
-                const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-                uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+        for (int i = 0; i < 4; ++i) {
+            float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8 * i));
+            float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8 * i) + 1);
+            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+            uint32_t hw[4] = {old[i].x, old[i].y, old[i].z, old[i].w};
+            uint32_t lw[4] = {old[4 + i].x, old[4 + i].y, old[4 + i].z, old[4 + i].w};
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    float o[2];
+            for (int w = 0; w < 4; ++w) {
+                float o[2];
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        int idx = i * 8 + w * 2 + e;
-                        float old = __bfloat162float(__ushort_as_bfloat16((unsigned short)(hw[w] >> (16 * e)))) +
-                                    __bfloat162float(__ushort_as_bfloat16((unsigned short)(lw[w] >> (16 * e))));
-                        o[e] = (n + idx < p.c) ? old + (v[idx] + bv[w * 2 + e]) : 0.f;
-                    }
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    split_bf16(o[0], h0, l0);
-                    split_bf16(o[1], h1, l1);
-                    hw[w] = pack2(h0, h1);
-                    lw[w] = pack2(l0, l1);
+                for (int e = 0; e < 2; ++e) {
+                    int idx = i * 8 + w * 2 + e;
+                    float prev = __bfloat162float(__ushort_as_bfloat16((unsigned short)(hw[w] >> (16 * e)))) +
+                                 __bfloat162float(__ushort_as_bfloat16((unsigned short)(lw[w] >> (16 * e))));
+                    o[e] = (n + idx < p.c) ? prev + (v[idx] + bv[w * 2 + e]) : 0.f;
                 }
-                ph[i] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                pl[i] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(o[0], h0, l0);
+                split_bf16(o[1], h1, l1);
+                hw[w] = pack2(h0, h1);
+                lw[w] = pack2(l0, l1);
             }
-        } else {
-            const int sc = n - p.res_cols;
-            float4* ps = reinterpret_cast<float4*>(p.skip + row * p.c + sc);
+            oh[i] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            ol[i] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (sc + 4 * i >= p.c) break;                 // c is a multiple of 4
-                float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * i));
-                float4 nv = make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
-                if (!p.first) {
-                    float4 old = ps[i];
-                    nv.x += old.x; nv.y += old.y; nv.z += old.z; nv.w += old.w;
-                }
-                ps[i] = nv;
+        for (int i = 0; i < 4; ++i) { ph[i] = oh[i]; pl[i] = ol[i]; }
+    } else {
+        const int sc = n - p.res_cols;
+        float4* ps = reinterpret_cast<float4*>(p.skip + c.row * p.c + sc);
+        float4 nv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * i));
+            nv[i] = make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
+            if (!p.first) {
+                nv[i].x += __uint_as_float(old[i].x); nv[i].y += __uint_as_float(old[i].y);
+                nv[i].z += __uint_as_float(old[i].z); nv[i].w += __uint_as_float(old[i].w);
             }
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (sc + 4 * i < p.c) ps[i] = nv[i];                // c is a multiple of 4
+    }
+}
+
+__device__ __forceinline__ ResSkipCtx resskip_begin(const GemmParams& p, long long row, int n0, int width, int half, uint4 (&old)[8]) {
+    ResSkipCtx c;
+    c.row = row; c.n0 = n0; c.width = width; c.half = half; c.valid = false;
+    if (row < p.rows) {
+        long long lo, hi;
+        c.valid = utt_bounds(p.grid, p.steps_per_frame, row, lo, hi);
+    }
+    resskip_load_old(p, c, half, old);
+    return c;
+}
+
+__device__ __forceinline__ void epi_resskip(const GemmParams& p, const ResSkipCtx& c, uint32_t tacc, uint4 (&old)[8]) {
+    float v[32];
+    uint4 nxt[8];
+#pragma unroll 1
+    for (int q = c.half; q < c.width / 32; q += 2) {
+        tmem_ld32(tacc + q * 32, v);
+        resskip_load_old(p, c, q + 2, nxt);
+        tmem_ld_wait();
+        resskip_store(p, c, q, v, old);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) old[i] = nxt[i];
     }
 }
 
@@ -555,15 +600,18 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
         for (int t = group; t < n_tiles; t += n_groups, ++tile_it) {
             const int m_grp = t / p.tiles_n, n_blk = t - m_grp * p.tiles_n;
             const uint32_t as = tile_it % ACC_STAGES, aph = (tile_it / ACC_STAGES) & 1;
-            mbar_wait(&tmem_full[as], aph);
-            tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(q4 * 32) << 16) + as * TILE_N;
             const long long row = (long long)(m_grp * CG + (int)rank) * TILE_M + q4 * 32 + lane;
             int width = p.n_cols - n_blk * TILE_N;
             width = width > TILE_N ? TILE_N : ((width + 31) & ~31);
+            uint4 old[8];
+            ResSkipCtx rctx;
+            if (EPI == EPI_RESSKIP) rctx = resskip_begin(p, row, n_blk * TILE_N, width, half, old);   // loads fly during the MMAs
+            mbar_wait(&tmem_full[as], aph);
+            tc_fence_after();
             if (EPI == EPI_PLAIN) epi_plain(p, tacc, row, n_blk * TILE_N, width, half);
             if (EPI == EPI_GATE) epi_gate(p, tacc, row, n_blk * TILE_N, width, half);
-            if (EPI == EPI_RESSKIP) epi_resskip(p, tacc, row, n_blk * TILE_N, width, half);
+            if (EPI == EPI_RESSKIP) epi_resskip(p, rctx, tacc, old);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
