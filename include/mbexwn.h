@@ -126,15 +126,16 @@ MBEXWN_API const char* mbexwn_last_error(mbexwn_handle_t h);
 /* Register a device tensor by name (folded weights, biases, PReLU slopes, DSP constants).  The pointer must stay
  * valid for the life of the handle.  Names: see mbexwn_op_t / mbexwn_config_t, plus the constants "wavetable"
  * (n_period+1, n_tables), "pqmf_poly" (Q, S, S), "window" (win), "inv_window" (win), "twiddle" (fft/2, 2),
- * "lifters" (n_lifters, n_ceps), "lifter_grid" (n_lifters), "f0_smooth" (n_smooth), "end_post/W" (wn_c, subbands),
- * "end_post/b" (subbands).
+ * "lifters" (n_lifters, n_ceps), "lifter_grid" (n_lifters), "f0_smooth" (n_smooth).
  * Tensor-core path (precision != FP32_SIMT), per WaveNet layer i, C padded to cpad = ceil(C / 64) * 64:
  *   "<wn_name>/tc/W1_<i>" bf16 (2*cpad, 2*k*cpad): rows = output channels permuted so that each tile of 256 rows
  *        (the last tile may be narrower) is [tanh channels | the matching sigmoid channels]; columns = [hi plane |
  *        lo plane], each (tap, cin)-major
  *   "<wn_name>/tc/b1_<i>" fp32 (2*cpad) in the same row order
- *   "<wn_name>/tc/R_<i>"  bf16 (2*cpad or cpad for the last layer, 2*cpad): rows = [res channels | skip channels]
- *   "<wn_name>/tc/rb_<i>" fp32 in the same row order */
+ *   "<wn_name>/tc/R_<i>"  bf16 (cpad + opad, or opad for the last layer; 2*cpad columns), opad = wn_cout rounded up to
+ *        32: rows = [res channels | res_skip's skip half pre-multiplied by the linear `end` 1x1 (C x wn_cout)], so the
+ *        kernel accumulates end(skip sum) -- the WaveNet output -- directly (custom_AE_layers.py:324-340)
+ *   "<wn_name>/tc/rb_<i>" fp32 in the same row order (layer 0 carries all skip biases @ W_end + b_end) */
 MBEXWN_API int mbexwn_set_tensor(mbexwn_handle_t h, const char* name, const void* dev_ptr, size_t n_bytes);
 
 /* ---- forward: stands in for MELInverter.synth_from_mel / PaNWaveNet.infer ---- */
@@ -151,8 +152,8 @@ MBEXWN_API int mbexwn_forward_host(mbexwn_handle_t h, const mbexwn_batch_t* batc
 
 /* Per-stage taps (return_F0 / return_components of PaNWaveNet.infer, custom_pulsed_generator.py:756-771, plus the
  * stage boundaries of SURVEY.md 8a): after mbexwn_forward the named intermediate lives in the workspace at
- * [*offset_bytes, *offset_bytes + *n_bytes).  Names: "F0", "phase", "index", "pulse", "wn_in", "cond", "h", "skip",
- * "subbands", "excitation", "ceps", "frames", "vtf", "lifter_index". */
+ * [*offset_bytes, *offset_bytes + *n_bytes).  Names: "F0", "phase", "index", "pulse", "wn_in", "cond", "wn_out"
+ * (rows, wn_cout rounded up to 32), "skip" (fp32 variant only), "subbands", "excitation", "ceps", "frames", "vtf", "lifter_index". */
 MBEXWN_API int mbexwn_tap(mbexwn_handle_t h, const char* name, int32_t n_frames, int32_t n_chunks, int32_t precision,
                size_t* offset_bytes, size_t* n_bytes);
 
@@ -161,7 +162,8 @@ MBEXWN_API int mbexwn_last_launch_count(mbexwn_handle_t h);
 
 /* Options: "debug_taps" (default 1): keep the phase / index / pulse / vtf / lifter_index taps in the workspace;
  * "stage_timing" (default 0): record CUDA events on the caller's stream at the stage boundaries of each forward;
- * "tc_cta_group" (1 or 2): tensor-core tiles owned by one CTA or by a CTA pair (cluster of 2, tcgen05 cta_group::2). */
+ * "tc_cta_group" (1 or 2): tensor-core tiles owned by one CTA or by a CTA pair (cluster of 2, tcgen05 cta_group::2);
+ * "tc_cond_stage" (default 1): the gate epilogue reads its conditioning rows from a shared-memory stage (0: global). */
 MBEXWN_API int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value);
 
 /* Device time of each stage of the last forward (needs "stage_timing"); ms[MBEXWN_N_STAGES] in the order

@@ -83,8 +83,9 @@ static Workspace carve(const mbexwn_config_t& c, int64_t F, int64_t n_chunks, in
     }
     w.add("wn_in", (size_t)rows * c.wn_cin * f4);
     w.add("cond", (size_t)F * c.wn_cond_conv_up * 2 * c.wn_c * f4);
-    w.add("skip", (size_t)rows * c.wn_c * f4);
+    w.add("wn_out", (size_t)rows * wn_tc_out_pad(c) * f4);
     if (precision == MBEXWN_PREC_FP32_SIMT) {
+        w.add("skip", (size_t)rows * c.wn_c * f4);
         w.add("h", (size_t)rows * c.wn_c * f4);
         w.add("z", (size_t)rows * 2 * c.wn_c * f4);
         w.add("act", (size_t)rows * c.wn_c * f4);
@@ -287,7 +288,7 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
     if (precision == MBEXWN_PREC_FP32_SIMT) {
         rc = wavenet_fp32(cx);
     } else {
-        rc = wn_tc_forward(h->tc, c, cx.g, precision, cx.p<float>("wn_in"), cx.p<float>("cond"), cx.p<float>("skip"),
+        rc = wn_tc_forward(h->tc, c, cx.g, precision, cx.p<float>("wn_in"), cx.p<float>("cond"), cx.p<float>("wn_out"),
                            [&](const char* nm) { return (void*)cx.p<char>(nm); },
                            [&](const std::string& nm, size_t bytes) { int r = 0; return (const void*)tensor(h, nm, bytes, &r); },
                            s, &h->launches, &h->error);
@@ -295,14 +296,28 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
     if (rc) return rc;
     mark();
 
-    // (5) end 1x1 and post 1x1 are both linear: one pre-multiplied C -> S matrix (custom_AE_layers.py:340,
-    //     custom_pulsed_generator.py:913-914), then PQMF synthesis (:920-921)
+    // (5) post 1x1 over the WaveNet output (custom_pulsed_generator.py:913-914), then PQMF synthesis (:920-921).
+    //     Tensor-core path: `end` (custom_AE_layers.py:340) is already folded into the res_skip matrices; the fp32
+    //     variant applies it here to the skip sum.
     {
-        const float* w = tensor(h, "end_post/W", (size_t)c.wn_c * c.subbands * 4, &rc); if (!w) return rc;
-        const float* bias = tensor(h, "end_post/b", (size_t)c.subbands * 4, &rc); if (!bias) return rc;
-        mbexwn_op_t op = simple_conv(1, c.wn_c, c.subbands, 1, 0);
-        MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op, c.steps_per_frame, rows, cx.p<float>("skip"), w, bias, nullptr,
-                                               cx.p<float>("subbands")), cx.g, s));
+        const int out_pad = wn_tc_out_pad(c);
+        if (precision == MBEXWN_PREC_FP32_SIMT) {
+            const std::string n = std::string(c.wn_name) + "/end";
+            const float* w = tensor(h, n + "/W", (size_t)c.wn_c * c.wn_cout * 4, &rc); if (!w) return rc;
+            const float* bias = tensor(h, n + "/b", (size_t)c.wn_cout * 4, &rc); if (!bias) return rc;
+            mbexwn_op_t op = simple_conv(1, c.wn_c, c.wn_cout, 1, 0);
+            ConvArgs a = conv_args(c, op, c.steps_per_frame, rows, cx.p<float>("skip"), w, bias, nullptr, cx.p<float>("wn_out"));
+            a.ld_out = out_pad;
+            MBX_CUDA_CHECK(launch_conv1d(a, cx.g, s));
+            h->launches++;
+        }
+        const std::string pn = c.post_name;
+        const float* w = tensor(h, pn + "/W", (size_t)c.wn_cout * c.subbands * 4, &rc); if (!w) return rc;
+        const float* bias = tensor(h, pn + "/b", (size_t)c.subbands * 4, &rc); if (!bias) return rc;
+        mbexwn_op_t op = simple_conv(1, c.wn_cout, c.subbands, 1, 0);
+        ConvArgs a = conv_args(c, op, c.steps_per_frame, rows, cx.p<float>("wn_out"), w, bias, nullptr, cx.p<float>("subbands"));
+        a.ld_x = out_pad;
+        MBX_CUDA_CHECK(launch_conv1d(a, cx.g, s));
         PqmfArgs pa{};
         pa.sub = cx.p<float>("subbands");
         pa.poly = tensor(h, "pqmf_poly", (size_t)c.pqmf_q * c.subbands * c.subbands * 4, &rc); if (!pa.poly) return rc;
@@ -436,6 +451,7 @@ int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value) {
     if (!strcmp(name, "debug_taps")) { h->debug_taps = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "stage_timing")) { h->stage_timing = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "tc_cta_group")) { h->tc.cta_group = value == 2 ? 2 : 1; return MBEXWN_OK; }
+    if (!strcmp(name, "tc_cond_stage")) { h->tc.cond_stage = value ? 1 : 0; return MBEXWN_OK; }
     return mbx::fail(h, MBEXWN_ERR_INVALID, std::string("unknown option: ") + name);
 }
 

@@ -7,8 +7,11 @@
 //                       act[r,c] = tanh(z_t + b_t + cond_t) * sigmoid(z_s + b_s + cond_s)
 //                       cond is the x10 linear interpolation of the mel-rate conditioning, evaluated in the
 //                       epilogue from the two neighbouring low-rate rows (never materialised at 1.6 kHz).
-//   GEMM2 (EPI_RESSKIP) rs[r, :] = act[r, :] @ R                                     K = C,   N = 2C (C last layer)
-//                       h[r, :] += rs[:, :C] ; skip[r, :] (+)= rs[:, C:]
+//   GEMM2 (EPI_RESSKIP) rs[r, :] = act[r, :] @ [R_res | R_skip @ W_end]               K = C,   N = C + c_out
+//                       h[r, :] += rs[:, :C] ; wn_out[r, :] (+)= rs[:, C:]
+//                       The skip sum only ever feeds the linear `end` 1x1 (custom_AE_layers.py:337-340), so the skip
+//                       half of every res_skip matrix is pre-multiplied by W_end on the host: the kernel accumulates
+//                       the c_out (30, padded to 32) channels of the WaveNet output instead of C skip channels.
 //
 // Implicit GEMM: the dilated taps are *row-shifted TMA loads* of the same activation tensor; guard rows between
 // utterances hold zeros and TMA zero-fills outside the tensor, which reproduces the reference's per-utterance SAME
@@ -26,6 +29,12 @@
 // 4 x (A 128x64 + B 256x64 bf16, SWIZZLE_128B), TMEM double buffered (2 x 256 fp32 columns = all 512) so the epilogue
 // of tile i overlaps the MMAs of tile i+1.  The MMA N of a tile is min(256, N - n0), so a narrow last tile costs
 // proportionally less tensor time.
+//
+// The producer and MMA warps run warp-uniform control flow (role index broadcast with shfl, one lane elected per
+// issue): ptxas then keeps descriptors and barrier addresses in uniform registers instead of emitting an
+// ELECT / R2UR.BROADCAST waterfall per tcgen05.mma, which made the single issuing thread the bottleneck (ncu r01d).
+// The gate epilogue reads the conditioning rows of its tile (15 low-rate rows x 256 channels, bias folded in) from a
+// double-buffered smem stage that is loaded one tile ahead, so its global-load latency is off the critical path.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -48,7 +57,13 @@ constexpr int TMEM_COLS = ACC_STAGES * TILE_N;          // 512 = all of TMEM
 constexpr int MAX_KB = 64;
 constexpr int EPI_WARPS = 8;                            // two warps per TMEM lane quarter, splitting the columns
 constexpr int TC_THREADS = 128 + 32 * EPI_WARPS;
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)RING_BYTES + 512;
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
+constexpr int COND_ROWS = 16;                           // staged conditioning rows per tile (<= 15 used at lin_up = 10)
+constexpr int COND_LD = TILE_N + 4;                     // floats per staged row: consecutive rows shift by 4 banks
+constexpr int COND_BYTES = COND_ROWS * COND_LD * 4;
+constexpr int MAX_LIN_UP = 32;
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)RING_BYTES + 512 + 2 * COND_BYTES;
+static_assert(SMEM_BYTES <= 232448, "dynamic shared memory budget (227 KB)");
 
 enum Epi { EPI_PLAIN = 0, EPI_GATE = 1, EPI_RESSKIP = 2 };
 
@@ -76,10 +91,14 @@ struct alignas(64) GemmParams {
     __nv_bfloat16* act;     // (rows, ld_act): [hi (cpad) | lo (cpad)]
     int ld_act;
     int c, cpad, lin_up, gate, write_lo, steps_per_frame;
+    int cond_rows;          // conditioning rows one 128-row tile touches, or 0 => read them from global memory
+    long long cond_total;   // rows of `cond`
+    float lin_w0[MAX_LIN_UP], lin_w1[MAX_LIN_UP];   // (U - u) / U and u / U rounded from double (support_layers.py:19-27)
     // EPI_RESSKIP
     __nv_bfloat16* h;       // (rows, ld_h): [hi | lo]
     int ld_h;
-    float* skip;            // (rows, c)
+    float* skip;            // (rows, skip_ld): accumulated WaveNet output channels
+    int skip_ld, skip_c;
     int res_cols;           // cpad, or 0 for the last layer (skip only)
     int first;              // skip = instead of +=
     FrameGrid grid;
@@ -97,20 +116,36 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t addr = smem_u32(bar), done = 0;
-    const long long t0 = clock64();
-    while (!done) {
-        if (clock64() - t0 > 20000000000LL) __trap();      // ~10 s: a protocol bug must not hang the device
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    }
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return done;
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    if (mbar_try_wait(addr, parity)) return;
+    // slow path: try_wait suspends the thread for a hardware time slice per attempt; a protocol bug must trap, not
+    // hang the device (the counter is only touched when the barrier was not ready)
+    uint32_t spins = 0;
+    while (!mbar_try_wait(addr, parity))
+        if (++spins > (1u << 26)) __trap();
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -181,17 +216,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row groups of 128 B rows, 1024 B apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);            // start address  [0,14)
-    d |= (uint64_t)1 << 16;                            // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset [32,46)
-    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
-    return d;
-}
-
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M x N
 __device__ __forceinline__ constexpr uint32_t make_idesc(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -254,8 +278,8 @@ __device__ __forceinline__ void epi_gate(const GemmParams& p, uint32_t tacc, lon
             int u = (int)(row - rc * p.lin_up);
             long long hic = hi / p.lin_up;
             rn = rc + 1 < hic ? rc + 1 : hic - 1;
-            w0 = (float)((double)(p.lin_up - u) / (double)p.lin_up);
-            w1 = (float)((double)u / (double)p.lin_up);
+            w0 = p.lin_w0[u];
+            w1 = p.lin_w1[u];
         }
     }
     const float* c0 = p.cond + rc * 2 * p.c;
@@ -325,6 +349,125 @@ __device__ __forceinline__ void epi_gate(const GemmParams& p, uint32_t tacc, lon
     }
 }
 
+// ---- gate epilogue with the conditioning rows staged in shared memory ---------------------------------------------
+// Tile (m0, n0, width): accumulator columns [0, width/2) are tanh channels n0/2 + j, columns [width/2, width) their
+// sigmoid partners.  The 128 rows of the tile interpolate between cond rows rc0 .. rc0 + cond_rows - 1 (rc0 = m0 /
+// lin_up).  Stage layout: buf[r][j] = cond[rc0 + r][channel of column j] + bias[n0 + j], j in [0, width).
+// The 256 epilogue threads load the stage of the *next* tile into registers before they start on the current one
+// and park it in the other smem buffer when they are done, so no global-load latency sits between the MMA and the gate.
+struct GateStage {
+    float4 v[4];
+    float4 b[4];
+};
+
+__device__ __forceinline__ void gate_stage_load(const GemmParams& p, long long m0, int n0, int width, int et, GateStage& st) {
+    const int w4 = width >> 2, hw = width >> 1;
+    const long long rc0 = m0 / p.lin_up;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int f = et + EPI_THREADS * i;
+        const int r = f / w4, j = (f - r * w4) * 4;
+        const int ch = (n0 >> 1) + (j < hw ? j : j - hw);
+        const int src_col = (j < hw ? 0 : p.c) + ch;
+        st.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        st.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ch < p.c && r < p.cond_rows && rc0 + r < p.cond_total) {           // channel padding: C is a multiple of 4
+            st.b[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+            st.v[i] = __ldg(reinterpret_cast<const float4*>(p.cond + (rc0 + r) * 2 * p.c + src_col));
+        }
+    }
+}
+
+__device__ __forceinline__ void gate_stage_store(float* buf, int width, int et, const GateStage& st) {
+    const int w4 = width >> 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int f = et + EPI_THREADS * i;
+        const int r = f / w4, j = (f - r * w4) * 4;
+        if (r < COND_ROWS)
+            *reinterpret_cast<float4*>(buf + r * COND_LD + j) =
+                make_float4(st.v[i].x + st.b[i].x, st.v[i].y + st.b[i].y, st.v[i].z + st.b[i].z, st.v[i].w + st.b[i].w);
+    }
+}
+
+__device__ __forceinline__ void epi_gate_staged(const GemmParams& p, const float* buf, uint32_t tacc, long long row, long long m0,
+                                                int n0, int width, int half) {
+    const int hw = width >> 1;
+    const int ch_tile = n0 >> 1;
+    bool valid = false;
+    int rl0 = 0, rl1 = 0;
+    float w0 = 1.f, w1 = 0.f;
+    if (row < p.rows) {
+        long long lo, hi;
+        valid = utt_bounds(p.grid, p.steps_per_frame, row, lo, hi);
+        if (valid) {
+            const long long rc0 = m0 / p.lin_up;
+            const long long rc = row / p.lin_up;
+            const int u = (int)(row - rc * p.lin_up);
+            const long long hic = hi / p.lin_up;
+            const long long rn = rc + 1 < hic ? rc + 1 : hic - 1;
+            rl0 = (int)(rc - rc0);
+            rl1 = (int)(rn - rc0);
+            w0 = p.lin_w0[u];
+            w1 = p.lin_w1[u];
+        }
+    }
+    const float* s0 = buf + rl0 * COND_LD;
+    const float* s1 = buf + rl1 * COND_LD;
+    float zt[32], zs[32];
+#pragma unroll 1
+    for (int q = half; q < hw / 32; q += 2) {
+        tmem_ld32(tacc + q * 32, zt);
+        tmem_ld32(tacc + hw + q * 32, zs);
+        tmem_ld_wait();
+        if (row >= p.rows) continue;
+        __nv_bfloat16* dst = p.act + row * p.ld_act + ch_tile + q * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            float a[8];
+#pragma unroll
+            for (int v4 = 0; v4 < 2; ++v4) {
+                const int col = q * 32 + i + 4 * v4;
+                const float4 x0 = *reinterpret_cast<const float4*>(s0 + col);
+                const float4 x1 = *reinterpret_cast<const float4*>(s1 + col);
+                const float4 y0 = *reinterpret_cast<const float4*>(s0 + hw + col);
+                const float4 y1 = *reinterpret_cast<const float4*>(s1 + hw + col);
+                const float ct[4] = {__fadd_rn(__fmul_rn(x0.x, w0), __fmul_rn(x1.x, w1)),
+                                     __fadd_rn(__fmul_rn(x0.y, w0), __fmul_rn(x1.y, w1)),
+                                     __fadd_rn(__fmul_rn(x0.z, w0), __fmul_rn(x1.z, w1)),
+                                     __fadd_rn(__fmul_rn(x0.w, w0), __fmul_rn(x1.w, w1))};
+                const float cs[4] = {__fadd_rn(__fmul_rn(y0.x, w0), __fmul_rn(y1.x, w1)),
+                                     __fadd_rn(__fmul_rn(y0.y, w0), __fmul_rn(y1.y, w1)),
+                                     __fadd_rn(__fmul_rn(y0.z, w0), __fmul_rn(y1.z, w1)),
+                                     __fadd_rn(__fmul_rn(y0.w, w0), __fmul_rn(y1.w, w1))};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float t = zt[i + 4 * v4 + e] + ct[e];
+                    const float sg = zs[i + 4 * v4 + e] + cs[e];
+                    switch (p.gate) {
+                        case GATE_GTU: t = fast_tanh(t); break;
+                        case GATE_GFU: t = t * rcp_approx(1.f + fabsf(t)); break;
+                        case GATE_GSU: t = t * rcp_approx(1.f + sqrtf(fabsf(t))); break;
+                        default: break;
+                    }
+                    a[4 * v4 + e] = valid ? t * fast_sigmoid(sg) : 0.f;       // padded channels: z = 0 -> act = 0
+                }
+            }
+            uint32_t hw4[4], lw4[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(a[e], h0, l0);
+                split_bf16(a[e + 1], h1, l1);
+                hw4[e / 2] = pack2(h0, h1);
+                lw4[e / 2] = pack2(l0, l1);
+            }
+            *reinterpret_cast<uint4*>(dst + i) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
+            if (p.write_lo) *reinterpret_cast<uint4*>(dst + p.cpad + i) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
+        }
+    }
+}
+
 // res/skip epilogue.  The old values of the residual stream / skip sum do not depend on the accumulators, so their
 // global loads are issued *before* the wait on the MMA (chunk 0) and one chunk ahead inside the loop: the read latency
 // hides behind the tensor work instead of serialising behind it, and every thread keeps 8 x 16 B loads in flight.
@@ -344,10 +487,10 @@ __device__ __forceinline__ void resskip_load_old(const GemmParams& p, const ResS
         for (int i = 0; i < 4; ++i) { old[i] = ph[i]; old[4 + i] = pl[i]; }
     } else if (!p.first) {
         const int sc = n - p.res_cols;
-        const uint4* ps = reinterpret_cast<const uint4*>(p.skip + c.row * p.c + sc);
+        const uint4* ps = reinterpret_cast<const uint4*>(p.skip + c.row * p.skip_ld + sc);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            if (sc + 4 * i < p.c) old[i] = ps[i];
+            if (sc + 4 * i < p.skip_c) old[i] = ps[i];
     }
 }
 
@@ -389,7 +532,7 @@ __device__ __forceinline__ void resskip_store(const GemmParams& p, const ResSkip
         for (int i = 0; i < 4; ++i) { ph[i] = oh[i]; pl[i] = ol[i]; }
     } else {
         const int sc = n - p.res_cols;
-        float4* ps = reinterpret_cast<float4*>(p.skip + c.row * p.c + sc);
+        float4* ps = reinterpret_cast<float4*>(p.skip + c.row * p.skip_ld + sc);
         float4 nv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -402,7 +545,7 @@ __device__ __forceinline__ void resskip_store(const GemmParams& p, const ResSkip
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            if (sc + 4 * i < p.c) ps[i] = nv[i];                // c is a multiple of 4
+            if (sc + 4 * i < p.skip_c) ps[i] = nv[i];           // skip_c is a multiple of 4
     }
 }
 
@@ -446,6 +589,9 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     constexpr int NA = CG == 1 ? 4 : 6;
     constexpr int NB = CG == 1 ? 4 : 6;
     static_assert(NA * A_BYTES + NB * B_BYTES <= RING_BYTES && NA <= MAX_RING && NB <= MAX_RING, "ring sizes");
+    // K-major SWIZZLE_128B smem matrix descriptor without the address field: LBO = 1 (ignored), SBO = 1024 B between
+    // 8-row groups, descriptor version 1 (Blackwell), swizzle mode 2 (128 B)
+    constexpr uint64_t DESC_HI = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* ring_a = smem;
@@ -457,8 +603,10 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     uint64_t* tmem_full = empty_b + MAX_RING;
     uint64_t* tmem_empty = tmem_full + ACC_STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+    float* cond_stage = reinterpret_cast<float*>(smem + RING_BYTES + 512);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform role index
+    const int lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
     const bool leader = rank == 0;
     const int tiles_mg = (p.tiles_m + CG - 1) / CG;                 // M tiles per CTA group
@@ -466,13 +614,16 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     const int group = blockIdx.x / CG, n_groups = gridDim.x / CG;
     const int ops_a = p.n_terms == 3 ? 2 : 1;                       // A / B tiles per K block
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_b) : "memory");
     }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < NA; ++s) { mbar_init(&full_a[s], CG); mbar_init(&empty_a[s], 1); }
-        for (int s = 0; s < NB; ++s) { mbar_init(&full_b[s], CG); mbar_init(&empty_b[s], 1); }
+    if (warp == 1 && elect_one()) {
+        // full barriers: one arrival (the leader's expect_tx for the bytes of *all* CTAs of the group); a peer CTA's
+        // TMA only reports its bytes to the leader's barrier (no remote arrive: a release.cluster arrive per load costs a
+        // MEMBAR + ERRBAR round trip and serialised the peer's producer thread)
+        for (int s = 0; s < NA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], CG * EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -492,37 +643,40 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ===== TMA producer (one thread per CTA) =====
-        if (lane == 0) {
-            uint32_t ia = 0, ib = 0;
-            for (int t = group; t < n_tiles; t += n_groups) {
-                const int m_grp = t / p.tiles_n, n_blk = t - m_grp * p.tiles_n;
-                const int m0 = (m_grp * CG + (int)rank) * TILE_M;
-                int width = p.n_cols - n_blk * TILE_N;
-                width = width > TILE_N ? TILE_N : ((width + 15) & ~15);
-                const int nb0 = n_blk * TILE_N + (int)rank * (width / CG);      // this CTA's share of the B rows
-                for (int kb = 0; kb < p.n_kb; ++kb) {
-                    for (int o = 0; o < ops_a; ++o) {
-                        {   // A tile (hi, then lo)
-                            const uint32_t s = ia % NA, ph = (ia / NA) & 1;
-                            ++ia;
-                            mbar_wait(&empty_a[s], ph ^ 1);
-                            const int col = p.kb[kb].a_col + (o ? p.a_lo_off : 0);
+        // ===== TMA producer: the whole warp walks the schedule, one elected lane issues =====
+        uint32_t ia = 0, ib = 0;
+        for (int t = group; t < n_tiles; t += n_groups) {
+            const int m_grp = t / p.tiles_n, n_blk = t - m_grp * p.tiles_n;
+            const int m0 = (m_grp * CG + (int)rank) * TILE_M;
+            int width = p.n_cols - n_blk * TILE_N;
+            width = width > TILE_N ? TILE_N : ((width + 15) & ~15);
+            const int nb0 = n_blk * TILE_N + (int)rank * (width / CG);      // this CTA's share of the B rows
+            for (int kb = 0; kb < p.n_kb; ++kb) {
+                const int a_col = p.kb[kb].a_col, a_row = m0 + p.kb[kb].a_shift, b_col = p.kb[kb].b_col;
+                for (int o = 0; o < ops_a; ++o) {
+                    {   // A tile (hi, then lo)
+                        const uint32_t s = ia % NA, ph = (ia / NA) & 1;
+                        ++ia;
+                        mbar_wait(&empty_a[s], ph ^ 1);
+                        if (elect_one()) {
+                            const int col = a_col + (o ? p.a_lo_off : 0);
                             if (CG == 1) {
                                 mbar_expect_tx(&full_a[s], A_BYTES);
-                                tma_load_2d(&p.tm_a, &full_a[s], ring_a + s * A_BYTES, col, m0 + p.kb[kb].a_shift);
+                                tma_load_2d(&p.tm_a, &full_a[s], ring_a + s * A_BYTES, col, a_row);
                             } else {
                                 const uint32_t lbar = map_to_cta(smem_u32(&full_a[s]), 0);
                                 if (leader) mbar_expect_tx(&full_a[s], CG * A_BYTES);
-                                tma_load_2d_2sm(&p.tm_a, lbar, ring_a + s * A_BYTES, col, m0 + p.kb[kb].a_shift);
-                                if (!leader) mbar_arrive_cluster(lbar);
+                                tma_load_2d_2sm(&p.tm_a, lbar, ring_a + s * A_BYTES, col, a_row);
                             }
                         }
-                        {   // B tile (hi, then lo)
-                            const uint32_t s = ib % NB, ph = (ib / NB) & 1;
-                            ++ib;
-                            mbar_wait(&empty_b[s], ph ^ 1);
-                            const int col = p.kb[kb].b_col + (o ? p.b_lo_off : 0);
+                        __syncwarp();
+                    }
+                    {   // B tile (hi, then lo)
+                        const uint32_t s = ib % NB, ph = (ib / NB) & 1;
+                        ++ib;
+                        mbar_wait(&empty_b[s], ph ^ 1);
+                        if (elect_one()) {
+                            const int col = b_col + (o ? p.b_lo_off : 0);
                             if (CG == 1) {
                                 mbar_expect_tx(&full_b[s], B_BYTES);
                                 tma_load_2d(&p.tm_b, &full_b[s], ring_b + s * B_BYTES, col, nb0);
@@ -530,20 +684,21 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                                 const uint32_t lbar = map_to_cta(smem_u32(&full_b[s]), 0);
                                 if (leader) mbar_expect_tx(&full_b[s], CG * B_BYTES);
                                 tma_load_2d_2sm(&p.tm_b, lbar, ring_b + s * B_BYTES, col, nb0);
-                                if (!leader) mbar_arrive_cluster(lbar);
                             }
                         }
+                        __syncwarp();
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread of the leader CTA) =====
-        if (lane == 0 && leader) {
+        // ===== MMA issuer (leader CTA): warp-uniform loop, one elected lane issues the tcgen05 instructions =====
+        if (leader) {
             uint32_t ia = 0, ib = 0, tile_it = 0;
+            const uint32_t a_base = smem_u32(ring_a) >> 4, b_base = smem_u32(ring_b) >> 4;
             auto mma4 = [&](uint32_t tacc, uint32_t sa, uint32_t sb, uint32_t idesc, bool first) {
-                const uint64_t da = make_smem_desc(smem_u32(ring_a + sa * A_BYTES));
-                const uint64_t db = make_smem_desc(smem_u32(ring_b + sb * B_BYTES));
+                const uint64_t da = DESC_HI | (uint64_t)(a_base + sa * (A_BYTES >> 4));
+                const uint64_t db = DESC_HI | (uint64_t)(b_base + sb * (B_BYTES >> 4));
 #pragma unroll
                 for (int k = 0; k < TILE_K / UMMA_K; ++k) {
                     // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16-byte units
@@ -567,50 +722,88 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                     mbar_wait(&full_a[sa_hi], pa_hi);
                     mbar_wait(&full_b[sb_hi], pb_hi);
                     tc_fence_after();
-                    mma4(tacc, sa_hi, sb_hi, idesc, kb == 0);                      // hi * hi
                     if (p.n_terms == 3) {
                         const uint32_t sa_lo = (ia + 1) % NA, pa_lo = ((ia + 1) / NA) & 1;
                         const uint32_t sb_lo = (ib + 1) % NB, pb_lo = ((ib + 1) / NB) & 1;
+                        if (elect_one()) mma4(tacc, sa_hi, sb_hi, idesc, kb == 0);     // hi * hi
+                        __syncwarp();
                         mbar_wait(&full_a[sa_lo], pa_lo);
                         tc_fence_after();
-                        mma4(tacc, sa_lo, sb_hi, idesc, false);                    // lo * hi
-                        commit(&empty_a[sa_lo]);
-                        commit(&empty_b[sb_hi]);
+                        if (elect_one()) {
+                            mma4(tacc, sa_lo, sb_hi, idesc, false);                    // lo * hi
+                            commit(&empty_a[sa_lo]);
+                            commit(&empty_b[sb_hi]);
+                        }
+                        __syncwarp();
                         mbar_wait(&full_b[sb_lo], pb_lo);
                         tc_fence_after();
-                        mma4(tacc, sa_hi, sb_lo, idesc, false);                    // hi * lo
-                        commit(&empty_a[sa_hi]);
-                        commit(&empty_b[sb_lo]);
+                        if (elect_one()) {
+                            mma4(tacc, sa_hi, sb_lo, idesc, false);                    // hi * lo
+                            commit(&empty_a[sa_hi]);
+                            commit(&empty_b[sb_lo]);
+                            if (kb == p.n_kb - 1) commit(&tmem_full[as]);              // accumulator complete
+                        }
+                        __syncwarp();
                         ia += 2;
                         ib += 2;
                     } else {
-                        commit(&empty_a[sa_hi]);
-                        commit(&empty_b[sb_hi]);
+                        if (elect_one()) {
+                            mma4(tacc, sa_hi, sb_hi, idesc, kb == 0);
+                            commit(&empty_a[sa_hi]);
+                            commit(&empty_b[sb_hi]);
+                            if (kb == p.n_kb - 1) commit(&tmem_full[as]);              // both CTAs of a pair are told
+                        }
+                        __syncwarp();
                         ia += 1;
                         ib += 1;
                     }
                 }
-                commit(&tmem_full[as]);                // accumulator complete (both CTAs of a pair are told)
             }
         }
     } else if (warp >= 4) {
         // ===== epilogue warps: every CTA drains the accumulators of its own 128 rows =====
         const int q4 = warp & 3, half = (warp - 4) >> 2;
+        const int et = threadIdx.x - (TC_THREADS - EPI_THREADS);
+        const bool staged = EPI == EPI_GATE && p.cond_rows > 0;
         uint32_t tile_it = 0;
+        GateStage gst;
+        if (staged && group < n_tiles) {
+            // stage of the first tile
+            const int m_grp = group / p.tiles_n, n_blk = group - m_grp * p.tiles_n;
+            int width = p.n_cols - n_blk * TILE_N;
+            width = width > TILE_N ? TILE_N : ((width + 31) & ~31);
+            gate_stage_load(p, (long long)(m_grp * CG + (int)rank) * TILE_M, n_blk * TILE_N, width, et, gst);
+            gate_stage_store(cond_stage, width, et, gst);
+        }
         for (int t = group; t < n_tiles; t += n_groups, ++tile_it) {
             const int m_grp = t / p.tiles_n, n_blk = t - m_grp * p.tiles_n;
             const uint32_t as = tile_it % ACC_STAGES, aph = (tile_it / ACC_STAGES) & 1;
             const uint32_t tacc = tmem_base + ((uint32_t)(q4 * 32) << 16) + as * TILE_N;
-            const long long row = (long long)(m_grp * CG + (int)rank) * TILE_M + q4 * 32 + lane;
+            const long long m0 = (long long)(m_grp * CG + (int)rank) * TILE_M;
+            const long long row = m0 + q4 * 32 + lane;
             int width = p.n_cols - n_blk * TILE_N;
             width = width > TILE_N ? TILE_N : ((width + 31) & ~31);
             uint4 old[8];
             ResSkipCtx rctx;
             if (EPI == EPI_RESSKIP) rctx = resskip_begin(p, row, n_blk * TILE_N, width, half, old);   // loads fly during the MMAs
+            int nwidth = 0;
+            if (staged) {
+                const int tn = t + n_groups;
+                if (tn < n_tiles) {                                 // next tile's conditioning rows -> registers
+                    const int mg2 = tn / p.tiles_n, nb2 = tn - mg2 * p.tiles_n;
+                    nwidth = p.n_cols - nb2 * TILE_N;
+                    nwidth = nwidth > TILE_N ? TILE_N : ((nwidth + 31) & ~31);
+                    gate_stage_load(p, (long long)(mg2 * CG + (int)rank) * TILE_M, nb2 * TILE_N, nwidth, et, gst);
+                }
+                epi_bar_sync();                                     // this tile's stage is complete in smem
+            }
             mbar_wait(&tmem_full[as], aph);
             tc_fence_after();
             if (EPI == EPI_PLAIN) epi_plain(p, tacc, row, n_blk * TILE_N, width, half);
-            if (EPI == EPI_GATE) epi_gate(p, tacc, row, n_blk * TILE_N, width, half);
+            if (EPI == EPI_GATE) {
+                if (staged) epi_gate_staged(p, cond_stage + (tile_it & 1) * (COND_ROWS * COND_LD), tacc, row, m0, n_blk * TILE_N, width, half);
+                else epi_gate(p, tacc, row, n_blk * TILE_N, width, half);
+            }
             if (EPI == EPI_RESSKIP) epi_resskip(p, rctx, tacc, old);
             tc_fence_before();
             __syncwarp();
@@ -618,6 +811,8 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                 if (CG == 1 || leader) mbar_arrive(&tmem_empty[as]);
                 else mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));
             }
+            // park the next tile's stage in the other buffer (last read two tiles ago, before the barrier above)
+            if (staged && nwidth) gate_stage_store(cond_stage + ((tile_it + 1) & 1) * (COND_ROWS * COND_LD), nwidth, et, gst);
         }
     }
 
@@ -631,17 +826,41 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
 }
 
-// fp32 (rows, c) -> bf16 [hi | lo] (rows, 2*cpad), zero in the channel padding
-__global__ void pack_hilo_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int c, int cpad) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * cpad) return;
-    long long r = idx / cpad;
-    int ch = (int)(idx - r * cpad);
-    float v = ch < c ? x[r * c + ch] : 0.f;
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
-    out[r * 2 * cpad + ch] = hi;
-    out[r * 2 * cpad + cpad + ch] = lo;
+// start 1x1 (custom_AE_layers.py:280) fused with the split into the bf16 [hi | lo] residual stream: one thread = one
+// row x 8 channels; guard rows and the channel padding are written as zeros (the tap-GEMM relies on both).
+__global__ void start_pack_kernel(const float* __restrict__ x, int cin, const float* __restrict__ w, const float* __restrict__ b,
+                                  __nv_bfloat16* __restrict__ out, long long rows, int c, int cpad, int rate, FrameGrid g) {
+    const int groups = cpad >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * groups) return;
+    const long long r = idx / groups;
+    const int ch0 = (int)(idx - r * groups) * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    long long lo, hi;
+    if (utt_bounds(g, rate, r, lo, hi)) {
+        for (int ci = 0; ci < cin; ++ci) {
+            const float xv = __ldg(x + r * cin + ci);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (ch0 + j < c) v[j] = fmaf(xv, __ldg(w + ci * c + ch0 + j), v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (ch0 + j < c) v[j] += __ldg(b + ch0 + j);
+    }
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v[j], h0, l0);
+        split_bf16(v[j + 1], h1, l1);
+        hw[j / 2] = pack2(h0, h1);
+        lw[j / 2] = pack2(l0, l1);
+    }
+    *reinterpret_cast<uint4*>(out + r * 2 * cpad + ch0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(out + r * 2 * cpad + cpad + ch0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
@@ -747,13 +966,14 @@ int build_kblocks(KBlock* kb, int n_taps, const int* shifts, int cpad) {
 void wn_tc_carve(const mbexwn_config_t& c, long long rows, int precision, const std::function<void(const char*, size_t)>& add) {
     (void)precision;
     const int cpad = round_up(c.wn_c, TILE_K);
-    add("h0f", (size_t)rows * c.wn_c * sizeof(float));
     add("h2", (size_t)rows * 2 * cpad * sizeof(__nv_bfloat16));
     add("a2", (size_t)rows * 2 * cpad * sizeof(__nv_bfloat16));
 }
 
+int wn_tc_out_pad(const mbexwn_config_t& c) { return round_up(c.wn_cout, 32); }
+
 int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, int precision, const float* wn_in,
-                  const float* cond, float* skip, const std::function<void*(const char*)>& slot,
+                  const float* cond, float* wn_out, const std::function<void*(const char*)>& slot,
                   const std::function<const void*(const std::string&, size_t)>& tensor, cudaStream_t s, int* launches,
                   std::string* error) {
     int rc = ensure_impl(st, error);
@@ -767,28 +987,33 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
     if (c.wn_k * (cpad / TILE_K) > MAX_KB) { if (error) *error = "K-block table too small"; return MBEXWN_ERR_UNSUPPORTED; }
     im->cta_group = st.cta_group == 2 ? 2 : 1;
 
-    float* h0f = reinterpret_cast<float*>(slot("h0f"));
     __nv_bfloat16* h2 = reinterpret_cast<__nv_bfloat16*>(slot("h2"));
     __nv_bfloat16* a2 = reinterpret_cast<__nv_bfloat16*>(slot("a2"));
     auto fail = [&](const std::string& m, int code) { if (error) *error = m; return code; };
+    const int out_pad = wn_tc_out_pad(c);
 
-    // start 1x1 on CUDA cores (K = 6), then split into the bf16 (hi, lo) residual stream
+    // start 1x1 on CUDA cores (K = 6), written straight into the bf16 (hi, lo) residual stream
     {
         const float* w = (const float*)tensor(n + "/start/W", (size_t)c.wn_cin * c.wn_c * 4);
         const float* b = (const float*)tensor(n + "/start/b", (size_t)c.wn_c * 4);
         if (!w || !b) return fail("start conv weights missing", MBEXWN_ERR_MISSING);
-        ConvArgs a{};
-        a.x = wn_in; a.ld_x = c.wn_cin; a.w = w; a.bias = b; a.out = h0f; a.ld_out = c.wn_c; a.rows = rows;
-        a.rate = c.steps_per_frame; a.k = 1; a.cin = c.wn_cin; a.cout = c.wn_c; a.dilation = 1; a.pad_l = 0;
-        a.pad_mode = PAD_ZERO; a.act = ACT_NONE; a.act_mod = c.wn_c;
-        cudaError_t e = launch_conv1d(a, g, s);
+        const long long total = rows * (cpad / 8);
+        start_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad,
+                                                                          c.steps_per_frame, g);
+        cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(std::string("start conv: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
-        long long total = rows * cpad;
-        pack_hilo_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h0f, h2, rows, c.wn_c, cpad);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return fail(std::string("pack: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
-        *launches += 2;
+        *launches += 1;
     }
+
+    // x lin_up interpolation weights exactly as the reference initialises them (double, rounded to float)
+    float lw0[MAX_LIN_UP], lw1[MAX_LIN_UP];
+    if (c.wn_cond_lin_up < 1 || c.wn_cond_lin_up > MAX_LIN_UP) return fail("cond_lin_upsampling outside [1, 32]", MBEXWN_ERR_UNSUPPORTED);
+    for (int u = 0; u < c.wn_cond_lin_up; ++u) {
+        lw0[u] = (float)((double)(c.wn_cond_lin_up - u) / (double)c.wn_cond_lin_up);
+        lw1[u] = (float)((double)u / (double)c.wn_cond_lin_up);
+    }
+    int cond_rows = (TILE_M + c.wn_cond_lin_up - 2) / c.wn_cond_lin_up + 2;
+    if (cond_rows > COND_ROWS - 1 || st.cond_stage == 0) cond_rows = 0;      // does not fit the smem stage: read from global
 
     CUtensorMap tm_h, tm_a;
     if ((rc = make_map(im, &tm_h, h2, rows, 2 * cpad, TILE_M, error))) return rc;
@@ -799,7 +1024,7 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         const bool last = i == c.wn_layers - 1;
         const int d = c.wn_dilations[i];
         const int n1 = 2 * cpad, k1 = 2 * c.wn_k * cpad;                 // W1 packed: (n1, [hi | lo] x k x cpad)
-        const int n2 = last ? cpad : 2 * cpad, k2 = 2 * cpad;            // R packed: (n2, [hi | lo] x cpad)
+        const int n2 = (last ? 0 : cpad) + out_pad, k2 = 2 * cpad;       // R packed: (n2, [hi | lo] x cpad)
         const void* w1 = tensor(n + "/tc/W1_" + li, (size_t)n1 * k1 * 2);
         const float* b1 = (const float*)tensor(n + "/tc/b1_" + li, (size_t)n1 * 4);
         const void* w2 = tensor(n + "/tc/R_" + li, (size_t)n2 * k2 * 2);
@@ -816,6 +1041,8 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         p1.rows = rows; p1.n_cols = n1; p1.bias = b1; p1.cond = cond; p1.act = a2; p1.ld_act = 2 * cpad;
         p1.c = c.wn_c; p1.cpad = cpad; p1.lin_up = c.wn_cond_lin_up; p1.gate = c.wn_gate; p1.write_lo = n_terms == 3;
         p1.steps_per_frame = c.steps_per_frame; p1.grid = g;
+        p1.cond_rows = cond_rows; p1.cond_total = rows / c.wn_cond_lin_up;
+        for (int u = 0; u < c.wn_cond_lin_up; ++u) { p1.lin_w0[u] = lw0[u]; p1.lin_w1[u] = lw1[u]; }
         cudaError_t e = launch_gemm<EPI_GATE>(im, p1, s);
         if (e != cudaSuccess) return fail(std::string("gate GEMM: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
 
@@ -825,7 +1052,8 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         int zero = 0;
         p2.n_kb = build_kblocks(p2.kb, 1, &zero, cpad);
         p2.n_terms = n_terms; p2.a_lo_off = cpad; p2.b_lo_off = cpad;
-        p2.rows = rows; p2.n_cols = n2; p2.bias = b2; p2.h = h2; p2.ld_h = 2 * cpad; p2.skip = skip;
+        p2.rows = rows; p2.n_cols = n2; p2.bias = b2; p2.h = h2; p2.ld_h = 2 * cpad;
+        p2.skip = wn_out; p2.skip_ld = out_pad; p2.skip_c = out_pad;
         p2.c = c.wn_c; p2.cpad = cpad; p2.res_cols = last ? 0 : cpad; p2.first = i == 0;
         p2.steps_per_frame = c.steps_per_frame; p2.grid = g;
         e = launch_gemm<EPI_RESSKIP>(im, p2, s);

@@ -11,6 +11,7 @@ namespace mbx {
 struct WnTcState {
     bool ready = false;
     int cta_group = 1;          // option "tc_cta_group": 1 = one CTA per tile, 2 = CTA pairs (cta_group::2)
+    int cond_stage = 1;         // option "tc_cond_stage": gate epilogue reads its conditioning rows from a smem stage
     void* impl = nullptr;
 };
 
@@ -18,9 +19,13 @@ struct WnTcState {
 void wn_tc_carve(const mbexwn_config_t& c, long long rows, int precision,
                  const std::function<void(const char*, size_t)>& add);
 
-// Runs start conv + all WaveNet layers; leaves the skip sum (rows, C) fp32 in `skip`.
+// Channels of the WaveNet output buffer (c_out rounded up to 32; the padding columns are written as zeros).
+int wn_tc_out_pad(const mbexwn_config_t& c);
+
+// Runs start conv + all WaveNet layers; leaves end(skip sum) = the WaveNet output (rows, wn_tc_out_pad) fp32 in
+// `wn_out` (the linear `end` 1x1 is folded into the skip half of every res_skip matrix at pack time).
 int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, int precision, const float* wn_in,
-                  const float* cond, float* skip, const std::function<void*(const char*)>& slot,
+                  const float* cond, float* wn_out, const std::function<void*(const char*)>& slot,
                   const std::function<const void*(const std::string&, size_t)>& tensor, cudaStream_t s, int* launches,
                   std::string* error);
 

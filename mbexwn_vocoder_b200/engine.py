@@ -119,14 +119,6 @@ class Engine:
             for op in ops:
                 if op.act == ACT_PRELU and op.act_name:
                     self._register(f"{op.act_name}/alpha", weights[f"{op.act_name}/alpha"].astype(np.float32))
-        # end (C -> c_out) and post (c_out -> S) are both linear 1x1 convs with nothing in between
-        # (custom_AE_layers.py:340, custom_pulsed_generator.py:913-914): pre-multiply once in float64
-        wn_name = plan.wavenet.name + "_WNBlock_WN"
-        we, be = W.folded(weights, f"{wn_name}/end")
-        wp, bp = W.folded(weights, plan.post_name)
-        we64, wp64 = we[0].astype(np.float64), wp[0].astype(np.float64)
-        self._register("end_post/W", (we64 @ wp64).astype(np.float32))
-        self._register("end_post/b", (be.astype(np.float64) @ wp64 + bp.astype(np.float64)).astype(np.float32))
         self._register("wavetable", plan.wavetables.tables)
         self._register("pqmf_poly", plan.pqmf_poly)
         self._register("window", plan.window)
@@ -326,4 +318,7 @@ class PreparedBatch:
         F = self.layout.n_frames
         per_frame = flat.size // F
         grid = flat.reshape(F, per_frame)
+        if name == "wn_out":                                   # stored with the channels padded to a multiple of 32
+            c_out = self.eng.plan.wavenet.c_out
+            grid = grid.reshape(F, -1, -(-c_out // 32) * 32)[:, :, :c_out].reshape(F, -1)
         return [grid[self.layout.utt_begin[u]:self.layout.utt_end[u]].reshape(-1) for u in range(self.layout.n_utt)]

@@ -3,7 +3,10 @@
 * channels are padded to cpad = ceil(C / 64) * 64 (zero weights, zero bias);
 * W1 rows (GEMM N) are permuted so that every 256-row tile (the last may be narrower) is [tanh channels | the matching sigmoid
   channels]: the tanh*sigmoid gate (custom_AE_layers.py:309-321) becomes local to one 128-column accumulator tile;
-* res_skip rows are [res channels (cpad) | skip channels (cpad)] (skip only for the last layer);
+* res_skip rows are [res channels (cpad) | WaveNet output channels (c_out padded to 32)] (output only for the last layer):
+  the skip sum feeds nothing but the linear `end` 1x1 (custom_AE_layers.py:337-340), so the skip half of every res_skip
+  matrix is pre-multiplied by W_end in float64 (R_skip @ W_end, C x c_out) and the kernel accumulates end(skip) directly;
+  all skip biases and the `end` bias travel with layer 0;
 * every matrix is stored K-major as bf16 [hi | lo] planes with hi + lo ~ the fp32 value, so the same kernel runs
   plain bf16 (hi*hi) or the 3-product split (hi*hi + lo*hi + hi*lo) by listing more K blocks.
 """
@@ -19,6 +22,7 @@ from .plan import ModelPlan
 
 TILE_K = 64
 GATE_TILE = 256
+OUT_PAD = 32
 
 
 def hilo(x: np.ndarray) -> torch.Tensor:
@@ -46,6 +50,12 @@ def pack_tc_weights(plan: ModelPlan, weights: Dict[str, np.ndarray]) -> Dict[str
     name = wn.name + "_WNBlock_WN"
     col1, ok1 = gate_permutation(C, cpad)
     out: Dict[str, torch.Tensor] = {}
+    we, be = W.folded(weights, f"{name}/end")                         # (1, C, c_out), (c_out,)
+    we64 = we[0].astype(np.float64)
+    c_out = we64.shape[1]
+    out_pad = -(-c_out // OUT_PAD) * OUT_PAD
+    skip_bias = np.zeros(C, dtype=np.float64)
+    rbs = []
     for i in range(wn.n_layers):
         w, b = W.folded(weights, f"{name}/conv1D_{i}")                # (k, C, 2C), (2C,)
         w1 = np.zeros((2 * cpad, k, cpad), dtype=np.float32)
@@ -56,18 +66,22 @@ def pack_tc_weights(plan: ModelPlan, weights: Dict[str, np.ndarray]) -> Dict[str
         out[f"{name}/tc/b1_{i}"] = torch.from_numpy(b1)
         r, rb = W.folded(weights, f"{name}/res_skip_{i}")             # (1, C, 2C) or (1, C, C) for the last layer
         last = i == wn.n_layers - 1
-        n2 = cpad if last else 2 * cpad
-        m = np.arange(n2)
-        if last:
-            chan, col2 = m, m
-        else:
-            chan = np.where(m < cpad, m, m - cpad)
-            col2 = np.where(m < cpad, m, C + (m - cpad))
-        ok2 = chan < C
+        r64 = r[0].astype(np.float64)
+        r_skip = r64 if last else r64[:, C:]
+        n_res = 0 if last else cpad
+        n2 = n_res + out_pad
         r2 = np.zeros((n2, cpad), dtype=np.float32)
-        r2[ok2, :C] = r[0][:, col2[ok2]].T
         rb2 = np.zeros(n2, dtype=np.float32)
-        rb2[ok2] = rb[col2[ok2]]
+        if not last:
+            r2[:C, :C] = r[0][:, :C].T
+            rb2[:C] = rb[:C]
+        r2[n_res:n_res + c_out, :C] = (r_skip @ we64).T.astype(np.float32)
+        skip_bias += (rb if last else rb[C:]).astype(np.float64)
         out[f"{name}/tc/R_{i}"] = hilo(r2)
-        out[f"{name}/tc/rb_{i}"] = torch.from_numpy(rb2)
+        rbs.append((f"{name}/tc/rb_{i}", rb2, n_res))
+    # wn_out = sum_i act_i @ (Rskip_i @ We) + (sum_i bskip_i) @ We + be: the constant term rides on layer 0 (assign)
+    key0, rb0, n_res0 = rbs[0]
+    rb0[n_res0:n_res0 + c_out] = (skip_bias @ we64 + be.astype(np.float64)).astype(np.float32)
+    for key, rb2, _ in rbs:
+        out[key] = torch.from_numpy(rb2)
     return out

@@ -339,9 +339,11 @@ class OracleMBExWN:
             out = skip if out is None else out + skip
             if taps is not None:
                 taps[f"act_{i}"], taps[f"h_{i + 1}"] = act, h
+        wn_out = self._conv(out, f"{n}/end")
         if taps is not None:
             taps["skip"] = out
-        return self._conv(out, f"{n}/end")
+            taps["wn_out"] = wn_out
+        return wn_out
 
     def pqmf_synthesis(self, x: torch.Tensor) -> torch.Tensor:
         """TFPQMF.synthesis (tf_preprocess.py:208-226): zero-stuff x S with gain S, pad taps/2, correlate, sum bands."""

@@ -46,7 +46,7 @@ def _case(lengths, plan):
     return mels, noise
 
 
-STAGES = ["F0", "pulse", "wn_in", "cond", "skip", "subbands", "excitation", "ceps", "waveform"]
+STAGES = ["F0", "pulse", "wn_in", "cond", "skip", "wn_out", "subbands", "excitation", "ceps", "waveform"]
 
 
 def _oracle_taps(oracle, mel, noise, f0=None):
@@ -59,7 +59,7 @@ def _oracle_taps(oracle, mel, noise, f0=None):
 def test_stage_parity_fp32(engine, oracle, speech_setup, lengths):
     hp, plan, w = speech_setup
     mels, noise = _case(lengths, plan)
-    taps = ["F0", "phase", "index", "pulse", "wn_in", "cond", "skip", "subbands", "excitation", "ceps"]
+    taps = ["F0", "phase", "index", "pulse", "wn_in", "cond", "skip", "wn_out", "subbands", "excitation", "ceps"]
     out, tp = engine.forward(mels, noise=noise, precision="fp32", taps=taps)
     for u, t in enumerate(lengths):
         ref = _oracle_taps(oracle, mels[u], noise[u])
@@ -81,7 +81,7 @@ def test_index_bit_exact_and_downstream(engine, oracle, speech_setup, lengths):
     hp, plan, w = speech_setup
     mels, noise = _case(lengths, plan)
     f0 = [oracle.generate_f0(torch.as_tensor(m[None])).numpy()[0] for m in mels]
-    taps = ["F0", "phase", "index", "pulse", "wn_in", "cond", "skip", "subbands", "excitation", "ceps"]
+    taps = ["F0", "phase", "index", "pulse", "wn_in", "cond", "skip", "wn_out", "subbands", "excitation", "ceps"]
     out, tp = engine.forward(mels, noise=noise, f0=f0, precision="fp32", taps=taps)
     for u, t in enumerate(lengths):
         ref = _oracle_taps(oracle, mels[u], noise[u], f0[u])

@@ -79,11 +79,11 @@ def test_wavenet_tc_parity(engine, cg, speech_setup, precision, tol, snr):
     mels = [synthetic_mel(t, i) for i, t in enumerate(lengths)]
     noise = [synthetic_noise(t * plan.steps_per_frame, i) for i, t in enumerate(lengths)]
     f0 = [oracle.generate_f0(torch.as_tensor(m[None])).numpy()[0] for m in mels]
-    out, tp = engine.forward(mels, noise=noise, f0=f0, precision=precision, taps=["index", "skip", "subbands", "excitation"])
+    out, tp = engine.forward(mels, noise=noise, f0=f0, precision=precision, taps=["index", "wn_out", "subbands", "excitation"])
     for u, t in enumerate(lengths):
         ref = oracle.forward(mels[u][None], noise[u][None], f0_override=f0[u][None])
         assert np.array_equal(tp["index"][u], ref["index"][0])
-        for st in ["skip", "subbands", "excitation"]:
+        for st in ["wn_out", "subbands", "excitation"]:
             r = np.asarray(ref[st][0]).reshape(-1)
             e = np.abs(tp[st][u] - r).max() / np.abs(r).max()
             print(f"{precision} utt {u} {st}: max|err|/peak {e:.3e}")
@@ -115,12 +115,12 @@ def test_wavenet_tc_parity_c340():
         x = np.linspace(0, 1, n)
         f0.append((45.0 * (1400.0 / 45.0) ** x * (1 + 0.03 * np.sin(2 * np.pi * 5.5 * np.arange(n) / 8000.0))).astype(np.float32))
     for precision, tol, snr in (("bf16x3", 1e-4, 60.0), ("fp32", 1e-4, 60.0)):
-        out, tp = eng.forward(mels, noise=noise, f0=f0, precision=precision, taps=["index", "phase", "pulse", "skip"])
+        out, tp = eng.forward(mels, noise=noise, f0=f0, precision=precision, taps=["index", "phase", "pulse", "wn_out"])
         for u in range(len(lengths)):
             ref = oracle.forward(mels[u][None], noise[u][None], f0_override=f0[u][None])
             assert np.array_equal(tp["index"][u], ref["index"][0])
             assert np.array_equal(tp["phase"][u], ref["phase"][0])
-            for st in ("pulse", "skip"):
+            for st in ("pulse", "wn_out"):
                 r = np.asarray(ref[st][0]).reshape(-1)
                 e = np.abs(tp[st][u] - r).max() / np.abs(r).max()
                 print(f"C340 {precision} utt {u} {st}: {e:.3e}")
