@@ -468,56 +468,78 @@ __device__ __forceinline__ void epi_gate_staged(const GemmParams& p, const float
     }
 }
 
-// res/skip epilogue.  The old values of the residual stream / skip sum do not depend on the accumulators, so their
-// global loads are issued *before* the wait on the MMA (chunk 0) and one chunk ahead inside the loop: the read latency
-// hides behind the tensor work instead of serialising behind it, and every thread keeps 8 x 16 B loads in flight.
+// res/skip epilogue.  A TMEM lane is an accumulator row, so "one thread = one row" global accesses touch 32 different
+// 128 B lines per warp instruction and the L1 tag stage becomes the bottleneck (16 k cycles per tile, ncu r01e).  Each
+// warp therefore transposes its 32 x 32 fp32 chunk through a private, XOR-swizzled 4 KB smem scratch and does the
+// read-modify-write with 4 (bf16 planes) or 8 (fp32 output) lanes per row: every warp instruction covers whole 64 B /
+// 128 B row segments.  The old values do not depend on the accumulators, so their loads are issued one chunk ahead
+// (the first chunk's before the wait on the MMA) and their latency hides behind the tensor work.
 struct ResSkipCtx {
-    bool valid;
-    long long row;
+    unsigned vmask;          // bit r: row (row0 + r) of this warp is inside an utterance
+    long long row0;          // first row of this warp's lane quarter
     int n0, width, half;
 };
 
-__device__ __forceinline__ void resskip_load_old(const GemmParams& p, const ResSkipCtx& c, int q, uint4 (&old)[8]) {
+// scratch tile: float4 group g (0..7) of row r lives at r * 32 + ((g ^ (r & 7)) << 2): conflict-free row writes and
+// conflict-free 8-rows-x-64-B / 4-rows-x-128-B reads
+__device__ __forceinline__ float4 xp_read(const float* S, int r, int g) {
+    return *reinterpret_cast<const float4*>(S + r * 32 + ((g ^ (r & 7)) << 2));
+}
+
+__device__ __forceinline__ void resskip_load_old(const GemmParams& p, const ResSkipCtx& c, int q, int lane, uint4 (&old)[8]) {
     const int n = c.n0 + q * 32;
-    if (!c.valid || q >= c.width / 32 || n >= p.n_cols) return;
+    if (q >= c.width / 32 || n >= p.n_cols) return;
     if (n < p.res_cols) {
-        const uint4* ph = reinterpret_cast<const uint4*>(p.h + c.row * p.ld_h + n);
-        const uint4* pl = reinterpret_cast<const uint4*>(p.h + c.row * p.ld_h + p.cpad + n);
+        const int rr = lane >> 2, cg = lane & 3;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { old[i] = ph[i]; old[4 + i] = pl[i]; }
+        for (int ps = 0; ps < 4; ++ps) {
+            const int r = ps * 8 + rr;
+            if ((c.vmask >> r) & 1u) {
+                const __nv_bfloat16* ph = p.h + (c.row0 + r) * p.ld_h + n + cg * 8;
+                old[ps] = *reinterpret_cast<const uint4*>(ph);
+                old[4 + ps] = *reinterpret_cast<const uint4*>(ph + p.cpad);
+            }
+        }
     } else if (!p.first) {
-        const int sc = n - p.res_cols;
-        const uint4* ps = reinterpret_cast<const uint4*>(p.skip + c.row * p.skip_ld + sc);
+        const int rr = lane >> 3, cg = lane & 7;
+        const int sc = n - p.res_cols + cg * 4;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (sc + 4 * i < p.skip_c) old[i] = ps[i];
+        for (int ps = 0; ps < 8; ++ps) {
+            const int r = ps * 4 + rr;
+            if (((c.vmask >> r) & 1u) && sc < p.skip_c)
+                old[ps] = *reinterpret_cast<const uint4*>(p.skip + (c.row0 + r) * p.skip_ld + sc);
+        }
     }
 }
 
-__device__ __forceinline__ void resskip_store(const GemmParams& p, const ResSkipCtx& c, int q, const float (&v)[32], const uint4 (&old)[8]) {
+__device__ __forceinline__ void resskip_store(const GemmParams& p, const ResSkipCtx& c, int q, int lane, const float* S,
+                                              const uint4 (&old)[8]) {
     const int n = c.n0 + q * 32;
-    if (!c.valid || n >= p.n_cols) return;
+    if (n >= p.n_cols) return;
     if (n < p.res_cols) {
         // residual stream: h <- h + rs, kept as a bf16 (hi, lo) pair (guard rows stay zero: never written)
-        uint4* ph = reinterpret_cast<uint4*>(p.h + c.row * p.ld_h + n);
-        uint4* pl = reinterpret_cast<uint4*>(p.h + c.row * p.ld_h + p.cpad + n);
-        uint4 oh[4], ol[4];
+        const int rr = lane >> 2, cg = lane & 3;
+        const int ch0 = n + cg * 8;
+        const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + ch0));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + ch0) + 1);
+        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8 * i));
-            float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n + 8 * i) + 1);
-            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-            uint32_t hw[4] = {old[i].x, old[i].y, old[i].z, old[i].w};
-            uint32_t lw[4] = {old[4 + i].x, old[4 + i].y, old[4 + i].z, old[4 + i].w};
+        for (int ps = 0; ps < 4; ++ps) {
+            const int r = ps * 8 + rr;
+            if (!((c.vmask >> r) & 1u)) continue;
+            const float4 x0 = xp_read(S, r, 2 * cg), x1 = xp_read(S, r, 2 * cg + 1);
+            const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            uint32_t hw[4] = {old[ps].x, old[ps].y, old[ps].z, old[ps].w};
+            uint32_t lw[4] = {old[4 + ps].x, old[4 + ps].y, old[4 + ps].z, old[4 + ps].w};
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
                 float o[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    int idx = i * 8 + w * 2 + e;
-                    float prev = __bfloat162float(__ushort_as_bfloat16((unsigned short)(hw[w] >> (16 * e)))) +
-                                 __bfloat162float(__ushort_as_bfloat16((unsigned short)(lw[w] >> (16 * e))));
-                    o[e] = (n + idx < p.c) ? prev + (v[idx] + bv[w * 2 + e]) : 0.f;
+                    const int idx = w * 2 + e;
+                    const float prev = __bfloat162float(__ushort_as_bfloat16((unsigned short)(hw[w] >> (16 * e)))) +
+                                       __bfloat162float(__ushort_as_bfloat16((unsigned short)(lw[w] >> (16 * e))));
+                    o[e] = (ch0 + idx < p.c) ? prev + (xv[idx] + bv[idx]) : 0.f;
                 }
                 __nv_bfloat16 h0, l0, h1, l1;
                 split_bf16(o[0], h0, l0);
@@ -525,50 +547,58 @@ __device__ __forceinline__ void resskip_store(const GemmParams& p, const ResSkip
                 hw[w] = pack2(h0, h1);
                 lw[w] = pack2(l0, l1);
             }
-            oh[i] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            ol[i] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            __nv_bfloat16* ph = p.h + (c.row0 + r) * p.ld_h + ch0;
+            *reinterpret_cast<uint4*>(ph) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(ph + p.cpad) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { ph[i] = oh[i]; pl[i] = ol[i]; }
     } else {
-        const int sc = n - p.res_cols;
-        float4* ps = reinterpret_cast<float4*>(p.skip + c.row * p.skip_ld + sc);
-        float4 nv[8];
+        const int rr = lane >> 3, cg = lane & 7;
+        const int sc = n - p.res_cols + cg * 4;
+        if (sc >= p.skip_c) return;                               // skip_c is a multiple of 4
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + cg * 4));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * i));
-            nv[i] = make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
+        for (int ps = 0; ps < 8; ++ps) {
+            const int r = ps * 4 + rr;
+            if (!((c.vmask >> r) & 1u)) continue;
+            const float4 x = xp_read(S, r, cg);
+            float4 nv = make_float4(x.x + b4.x, x.y + b4.y, x.z + b4.z, x.w + b4.w);
             if (!p.first) {
-                nv[i].x += __uint_as_float(old[i].x); nv[i].y += __uint_as_float(old[i].y);
-                nv[i].z += __uint_as_float(old[i].z); nv[i].w += __uint_as_float(old[i].w);
+                nv.x += __uint_as_float(old[ps].x); nv.y += __uint_as_float(old[ps].y);
+                nv.z += __uint_as_float(old[ps].z); nv.w += __uint_as_float(old[ps].w);
             }
+            *reinterpret_cast<float4*>(p.skip + (c.row0 + r) * p.skip_ld + sc) = nv;
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (sc + 4 * i < p.skip_c) ps[i] = nv[i];           // skip_c is a multiple of 4
     }
 }
 
-__device__ __forceinline__ ResSkipCtx resskip_begin(const GemmParams& p, long long row, int n0, int width, int half, uint4 (&old)[8]) {
+__device__ __forceinline__ ResSkipCtx resskip_begin(const GemmParams& p, long long row, int n0, int width, int half, int lane,
+                                                    uint4 (&old)[8]) {
     ResSkipCtx c;
-    c.row = row; c.n0 = n0; c.width = width; c.half = half; c.valid = false;
+    c.row0 = row - lane; c.n0 = n0; c.width = width; c.half = half;
+    bool valid = false;
     if (row < p.rows) {
         long long lo, hi;
-        c.valid = utt_bounds(p.grid, p.steps_per_frame, row, lo, hi);
+        valid = utt_bounds(p.grid, p.steps_per_frame, row, lo, hi);
     }
-    resskip_load_old(p, c, half, old);
+    c.vmask = __ballot_sync(0xffffffffu, valid);
+    resskip_load_old(p, c, half, lane, old);
     return c;
 }
 
-__device__ __forceinline__ void epi_resskip(const GemmParams& p, const ResSkipCtx& c, uint32_t tacc, uint4 (&old)[8]) {
+__device__ __forceinline__ void epi_resskip(const GemmParams& p, const ResSkipCtx& c, uint32_t tacc, int lane, float* S, uint4 (&old)[8]) {
     float v[32];
     uint4 nxt[8];
 #pragma unroll 1
     for (int q = c.half; q < c.width / 32; q += 2) {
         tmem_ld32(tacc + q * 32, v);
-        resskip_load_old(p, c, q + 2, nxt);
+        resskip_load_old(p, c, q + 2, lane, nxt);
         tmem_ld_wait();
-        resskip_store(p, c, q, v, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(S + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        resskip_store(p, c, q, lane, S, old);
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) old[i] = nxt[i];
     }
@@ -785,7 +815,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
             width = width > TILE_N ? TILE_N : ((width + 31) & ~31);
             uint4 old[8];
             ResSkipCtx rctx;
-            if (EPI == EPI_RESSKIP) rctx = resskip_begin(p, row, n_blk * TILE_N, width, half, old);   // loads fly during the MMAs
+            if (EPI == EPI_RESSKIP) rctx = resskip_begin(p, row, n_blk * TILE_N, width, half, lane, old);   // loads fly during the MMAs
             int nwidth = 0;
             if (staged) {
                 const int tn = t + n_groups;
@@ -804,7 +834,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                 if (staged) epi_gate_staged(p, cond_stage + (tile_it & 1) * (COND_ROWS * COND_LD), tacc, row, m0, n_blk * TILE_N, width, half);
                 else epi_gate(p, tacc, row, n_blk * TILE_N, width, half);
             }
-            if (EPI == EPI_RESSKIP) epi_resskip(p, rctx, tacc, old);
+            if (EPI == EPI_RESSKIP) epi_resskip(p, rctx, tacc, lane, cond_stage + (warp - 4) * 1024, old);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -828,39 +858,62 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
 
 // start 1x1 (custom_AE_layers.py:280) fused with the split into the bf16 [hi | lo] residual stream: one thread = one
 // row x 8 channels; guard rows and the channel padding are written as zeros (the tap-GEMM relies on both).
+// Weights (cin x cpad, zero padded) and bias sit in shared memory; a block covers START_ROWS rows.
+constexpr int START_ROWS = 64;
+constexpr int START_MAX_CIN = 16;
 __global__ void start_pack_kernel(const float* __restrict__ x, int cin, const float* __restrict__ w, const float* __restrict__ b,
                                   __nv_bfloat16* __restrict__ out, long long rows, int c, int cpad, int rate, FrameGrid g) {
+    extern __shared__ float sw[];                       // [cin + 1][cpad]: weights, then bias
+    float* sx = sw + (cin + 1) * cpad;                  // [START_ROWS][cin] inputs, zero for guard rows
+    __shared__ int svalid[START_ROWS];
+    const long long r0 = (long long)blockIdx.x * START_ROWS;
+    for (int i = threadIdx.x; i < (cin + 1) * cpad; i += blockDim.x) {
+        const int ci = i / cpad, ch = i - ci * cpad;
+        sw[i] = ch < c ? (ci < cin ? w[ci * c + ch] : b[ch]) : 0.f;
+    }
+    for (int i = threadIdx.x; i < START_ROWS; i += blockDim.x) {
+        long long lo, hi;
+        svalid[i] = (r0 + i < rows) && utt_bounds(g, rate, r0 + i, lo, hi);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < START_ROWS * cin; i += blockDim.x) {
+        const int rl = i / cin;
+        sx[i] = svalid[rl] ? x[(r0 + rl) * cin + (i - rl * cin)] : 0.f;
+    }
+    __syncthreads();
     const int groups = cpad >> 3;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * groups) return;
-    const long long r = idx / groups;
-    const int ch0 = (int)(idx - r * groups) * 8;
-    float v[8];
+    for (int i = threadIdx.x; i < START_ROWS * groups; i += blockDim.x) {
+        const int rl = i / groups, ch0 = (i - rl * groups) * 8;
+        const long long r = r0 + rl;
+        if (r >= rows) break;
+        float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    long long lo, hi;
-    if (utt_bounds(g, rate, r, lo, hi)) {
-        for (int ci = 0; ci < cin; ++ci) {
-            const float xv = __ldg(x + r * cin + ci);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (ch0 + j < c) v[j] = fmaf(xv, __ldg(w + ci * c + ch0 + j), v[j]);
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        if (svalid[rl]) {
+            for (int ci = 0; ci < cin; ++ci) {
+                const float xv = sx[rl * cin + ci];
+                const float4 w0 = *reinterpret_cast<const float4*>(sw + ci * cpad + ch0);
+                const float4 w1 = *reinterpret_cast<const float4*>(sw + ci * cpad + ch0 + 4);
+                v[0] = fmaf(xv, w0.x, v[0]); v[1] = fmaf(xv, w0.y, v[1]); v[2] = fmaf(xv, w0.z, v[2]); v[3] = fmaf(xv, w0.w, v[3]);
+                v[4] = fmaf(xv, w1.x, v[4]); v[5] = fmaf(xv, w1.y, v[5]); v[6] = fmaf(xv, w1.z, v[6]); v[7] = fmaf(xv, w1.w, v[7]);
+            }
+            const float4 b0 = *reinterpret_cast<const float4*>(sw + cin * cpad + ch0);
+            const float4 b1 = *reinterpret_cast<const float4*>(sw + cin * cpad + ch0 + 4);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
         }
+        uint32_t hw[4], lw[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (ch0 + j < c) v[j] += __ldg(b + ch0 + j);
+        for (int j = 0; j < 8; j += 2) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v[j], h0, l0);
+            split_bf16(v[j + 1], h1, l1);
+            hw[j / 2] = pack2(h0, h1);
+            lw[j / 2] = pack2(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(out + r * 2 * cpad + ch0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(out + r * 2 * cpad + cpad + ch0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
     }
-    uint32_t hw[4], lw[4];
-#pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v[j], h0, l0);
-        split_bf16(v[j + 1], h1, l1);
-        hw[j / 2] = pack2(h0, h1);
-        lw[j / 2] = pack2(l0, l1);
-    }
-    *reinterpret_cast<uint4*>(out + r * 2 * cpad + ch0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(out + r * 2 * cpad + cpad + ch0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
@@ -997,9 +1050,10 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         const float* w = (const float*)tensor(n + "/start/W", (size_t)c.wn_cin * c.wn_c * 4);
         const float* b = (const float*)tensor(n + "/start/b", (size_t)c.wn_c * 4);
         if (!w || !b) return fail("start conv weights missing", MBEXWN_ERR_MISSING);
-        const long long total = rows * (cpad / 8);
-        start_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad,
-                                                                          c.steps_per_frame, g);
+        if (c.wn_cin > START_MAX_CIN) return fail("start conv: more than 16 input channels", MBEXWN_ERR_UNSUPPORTED);
+        const size_t smem = ((size_t)(c.wn_cin + 1) * cpad + (size_t)START_ROWS * c.wn_cin) * sizeof(float);
+        start_pack_kernel<<<(unsigned)((rows + START_ROWS - 1) / START_ROWS), 256, smem, s>>>(
+            wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(std::string("start conv: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
         *launches += 1;
