@@ -18,6 +18,7 @@ struct mbexwn_handle_s {
     int launches = 0;
     int debug_taps = 1;
     int stage_timing = 0;
+    int tc_subnets = 1;         // wide sub-net / conditioning convs on the tensor cores (TC precisions only)
     cudaEvent_t ev[MBEXWN_N_STAGES + 1] = {};
     bool ev_ready = false;
     bool ev_recorded = false;
@@ -62,6 +63,25 @@ static size_t subnet_scratch_elems(const mbexwn_op_t* ops, int n, int n_mel) {
     return m;
 }
 
+static int round64(int x) { return (x + 63) / 64 * 64; }
+
+// A conv op runs on the tensor cores when it is wide enough to fill MMA tiles and its epilogue is one the tap-GEMM has
+static bool tc_eligible(const mbexwn_op_t& op) {
+    if (op.kind != 0 || op.cin < 32 || op.cout < 16 || op.cout % 8 || op.act > ACT_LEAKY || op.k > 16) return false;
+    const int f = op.subpixel > 0 ? op.subpixel : 1;
+    return op.cout % f == 0 && (op.cout / f) % 8 == 0 && (op.dilation <= 1);
+}
+
+static size_t subnet_hilo_elems(const mbexwn_op_t* ops, int n) {
+    size_t m = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!tc_eligible(ops[i])) continue;
+        size_t a = (size_t)ops[i].rate_out * 2 * round64(ops[i].ch_out);
+        if (a > m) m = a;
+    }
+    return m;
+}
+
 static Workspace carve(const mbexwn_config_t& c, int64_t F, int64_t n_chunks, int precision, int debug_taps) {
     Workspace w;
     const size_t f4 = sizeof(float);
@@ -71,6 +91,14 @@ static Workspace carve(const mbexwn_config_t& c, int64_t F, int64_t n_chunks, in
     if (sn2 > sn) sn = sn2;
     w.add("sn_a", (size_t)F * sn * f4);
     w.add("sn_b", (size_t)F * sn * f4);
+    if (precision != MBEXWN_PREC_FP32_SIMT) {
+        // bf16 [hi | lo] activations of the tensor-core sub-net convs: packed mel + ping-pong layer outputs
+        size_t hl = subnet_hilo_elems(c.pp_ops, c.n_pp_ops), hl2 = subnet_hilo_elems(c.ps_ops, c.n_ps_ops);
+        if (hl2 > hl) hl = hl2;
+        w.add("mel_hl", (size_t)F * 2 * round64(c.mel_channels) * 2);
+        w.add("sn_h0", (size_t)F * hl * 2);
+        w.add("sn_h1", (size_t)F * hl * 2);
+    }
     w.add("F0", (size_t)F * c.pulse_per_frame * f4);
     w.add("cum", (size_t)F * c.pulse_per_frame * f4);
     w.add("chunk_off", (size_t)(n_chunks + 1) * f4);
@@ -176,6 +204,94 @@ static int run_subnet(Ctx& cx, const mbexwn_op_t* ops, int n_ops, const float* i
     return MBEXWN_OK;
 }
 
+// Tensor-core variant of run_subnet: wide convs run as 3-product bf16 tap-GEMMs whose epilogue writes the bf16
+// [hi | lo] planes the next conv reads (fp32 only where a CUDA-core op or the caller consumes the result).
+static int run_subnet_tc(Ctx& cx, const mbexwn_op_t* ops, int n_ops, const float* input, float* final_out) {
+    mbexwn_handle_t h = cx.h;
+    const mbexwn_config_t& c = h->cfg;
+    float* bufs[2] = {cx.p<float>("sn_a"), cx.p<float>("sn_b")};
+    char* hbufs[2] = {cx.p<char>("sn_h0"), cx.p<char>("sn_h1")};
+    const float* cur = input;        // fp32 view of the current activations (nullptr while they only exist as hi/lo)
+    const char* cur_hl = nullptr;    // bf16 [hi | lo] view
+    int cur_cpad = 0, flip = 0, hflip = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        const mbexwn_op_t& op = ops[i];
+        const bool last = i == n_ops - 1;
+        int rc = 0;
+        const float* alpha = nullptr;
+        if (op.act == ACT_PRELU) {
+            alpha = tensor(h, std::string(op.act_name) + "/alpha", (size_t)op.act_channels * 4, &rc);
+            if (!alpha) return rc;
+        }
+        if (tc_eligible(op) && (cur_hl || i == 0)) {
+            const int cin_pad = round64(op.cin);
+            if (op.pad_mode != PAD_ZERO && c.halo_frames * op.rate_in < op.pad_l + op.pad_r)
+                return fail(h, MBEXWN_ERR_INVALID, "halo_frames too small for the mirrored pad rows of the sub-net convs");
+            if (!cur_hl) {                                   // first layer: pack the fp32 input with its pad rows
+                MBX_RC(wn_tc_pack(cur, cx.p<char>("mel_hl"), (long long)cx.g.n_frames * op.rate_in, op.cin, cin_pad, op.rate_in,
+                                  op.pad_l, op.pad_r, op.pad_mode, cx.g, cx.s, &h->error));
+                cur_hl = cx.p<char>("mel_hl");
+                cur_cpad = cin_pad;
+                h->launches++;
+            }
+            if (cur_cpad != cin_pad) return fail(h, MBEXWN_ERR_INVALID, "sub-net channel mismatch");
+            const float* w = tensor(h, std::string(op.name) + "/tc/W", (size_t)op.cout * 2 * op.k * cin_pad * 2, &rc);
+            if (!w) return rc;
+            const float* bias = tensor(h, std::string(op.name) + "/b", (size_t)op.cout * 4, &rc);
+            if (!bias) return rc;
+            const int f = op.subpixel > 0 ? op.subpixel : 1;
+            // the next conv reads hi/lo planes only if they need no channel padding (cout / f a multiple of 64)
+            const bool next_tc = !last && tc_eligible(ops[i + 1]) && (op.cout / f) % 64 == 0;
+            TcConvArgs a{};
+            a.a_hilo = cur_hl; a.rows = (long long)cx.g.n_frames * op.rate_in; a.cin_pad = cin_pad;
+            a.w = w; a.cout = op.cout; a.k = op.k; a.dilation = 1; a.pad_l = op.pad_l;
+            a.bias = bias; a.act = op.act; a.alpha = alpha; a.act_mod = op.act_channels > 0 ? op.act_channels : op.cout;
+            a.leaky = c.leaky_alpha; a.rate = op.rate_in;
+            if (next_tc) {
+                a.out_hilo = hbufs[hflip]; a.out_cpad = round64(op.cout / f); a.subpixel = f;
+            } else {
+                a.out_f32 = last ? final_out : bufs[flip]; a.ld_out = op.cout;       // (T, cout) == (T f, cout / f)
+            }
+            MBX_RC(wn_tc_conv(h->tc, a, cx.g, cx.s, &h->error));
+            h->launches++;
+            if (next_tc) {
+                const mbexwn_op_t& nx = ops[i + 1];
+                if (nx.pad_mode != PAD_ZERO) {
+                    MBX_RC(wn_tc_mirror(hbufs[hflip], (long long)cx.g.n_frames * op.rate_out, a.out_cpad, op.rate_out, nx.pad_l,
+                                        nx.pad_r, nx.pad_mode, cx.g, cx.s, &h->error));
+                    h->launches++;
+                }
+                cur_hl = hbufs[hflip]; cur_cpad = a.out_cpad; cur = nullptr;
+                hflip ^= 1;
+            } else {
+                cur = last ? final_out : bufs[flip]; cur_hl = nullptr;
+                flip ^= 1;
+            }
+            continue;
+        }
+        if (!cur) return fail(h, MBEXWN_ERR_INVALID, "sub-net op needs fp32 activations");
+        float* out = last ? final_out : bufs[flip];
+        if (op.kind == 0) {
+            const float* w = tensor(h, std::string(op.name) + "/W", (size_t)op.k * op.cin * op.cout * 4, &rc);
+            if (!w) return rc;
+            const float* bias = tensor(h, std::string(op.name) + "/b", (size_t)op.cout * 4, &rc);
+            if (!bias) return rc;
+            ConvArgs a = conv_args(c, op, op.rate_in, (long long)cx.g.n_frames * op.rate_in, cur, w, bias, alpha, out);
+            MBX_CUDA_CHECK(launch_conv1d(a, cx.g, cx.s));
+        } else {
+            LinInterpArgs a{};
+            a.x = cur; a.out = out; a.rows_in = (long long)cx.g.n_frames * op.rate_in; a.rate_in = op.rate_in;
+            a.ch = op.ch_out; a.up = op.up; a.act = op.act; a.alpha = alpha; a.leaky = c.leaky_alpha;
+            a.a0 = c.f0_span; a.a1 = c.f0_min;
+            MBX_CUDA_CHECK(launch_lininterp(a, cx.g, cx.s));
+        }
+        h->launches++;
+        cur = out;
+        flip ^= 1;
+    }
+    return MBEXWN_OK;
+}
+
 static mbexwn_op_t simple_conv(int k, int cin, int cout, int dil, int pad_l) {
     mbexwn_op_t op{};
     op.kind = 0; op.k = k; op.cin = cin; op.cout = cout; op.dilation = dil; op.pad_l = pad_l; op.pad_r = pad_l;
@@ -246,7 +362,9 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
     // (1) F0 sub-net (generate_f0, custom_pulsed_generator.py:773-791)
     const float* f0 = b->f0_override;
     if (!f0) {
-        rc = run_subnet(cx, c.pp_ops, c.n_pp_ops, b->mel, cx.p<float>("F0"));
+        rc = (precision == MBEXWN_PREC_FP32_SIMT || !h->tc_subnets)
+                 ? run_subnet(cx, c.pp_ops, c.n_pp_ops, b->mel, cx.p<float>("F0"))
+                 : run_subnet_tc(cx, c.pp_ops, c.n_pp_ops, b->mel, cx.p<float>("F0"));
         if (rc) return rc;
         f0 = cx.p<float>("F0");
     } else {
@@ -279,8 +397,20 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
         const float* w = tensor(h, n + "/W", (size_t)c.wn_cond_k * c.mel_channels * cout * 4, &rc); if (!w) return rc;
         const float* bias = tensor(h, n + "/b", (size_t)cout * 4, &rc); if (!bias) return rc;
         mbexwn_op_t op = simple_conv(c.wn_cond_k, c.mel_channels, cout, 1, (c.wn_cond_k - 1) / 2);
-        MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op, 1, b->n_frames, b->mel, w, bias, nullptr, cx.p<float>("cond")), cx.g, s));
-        h->launches++;
+        if (precision != MBEXWN_PREC_FP32_SIMT && h->tc_subnets && tc_eligible(op)) {
+            const int cin_pad = round64(c.mel_channels);
+            const float* wt = tensor(h, n + "/tc/W", (size_t)cout * 2 * op.k * cin_pad * 2, &rc); if (!wt) return rc;
+            MBX_RC(wn_tc_pack(b->mel, cx.p<char>("mel_hl"), b->n_frames, c.mel_channels, cin_pad, 1, 0, 0, PAD_ZERO, cx.g, s, &h->error));
+            TcConvArgs a{};
+            a.a_hilo = cx.p<char>("mel_hl"); a.rows = b->n_frames; a.cin_pad = cin_pad; a.w = wt; a.cout = cout; a.k = op.k;
+            a.dilation = 1; a.pad_l = op.pad_l; a.bias = bias; a.act = ACT_NONE; a.rate = 1;
+            a.out_f32 = cx.p<float>("cond"); a.ld_out = cout;
+            MBX_RC(wn_tc_conv(h->tc, a, cx.g, s, &h->error));
+            h->launches += 2;
+        } else {
+            MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op, 1, b->n_frames, b->mel, w, bias, nullptr, cx.p<float>("cond")), cx.g, s));
+            h->launches++;
+        }
     }
 
     mark();
@@ -329,7 +459,9 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
 
     mark();
     // (6) VTF sub-net -> cepstrum (generate_specenv, :793-799)
-    rc = run_subnet(cx, c.ps_ops, c.n_ps_ops, b->mel, cx.p<float>("ceps"));
+    rc = (precision == MBEXWN_PREC_FP32_SIMT || !h->tc_subnets)
+             ? run_subnet(cx, c.ps_ops, c.n_ps_ops, b->mel, cx.p<float>("ceps"))
+             : run_subnet_tc(cx, c.ps_ops, c.n_ps_ops, b->mel, cx.p<float>("ceps"));
     if (rc) return rc;
     mark();
 
@@ -451,6 +583,7 @@ int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value) {
     if (!strcmp(name, "debug_taps")) { h->debug_taps = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "stage_timing")) { h->stage_timing = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "tc_cta_group")) { h->tc.cta_group = value == 2 ? 2 : 1; return MBEXWN_OK; }
+    if (!strcmp(name, "tc_subnets")) { h->tc_subnets = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "tc_cond_stage")) { h->tc.cond_stage = value ? 1 : 0; return MBEXWN_OK; }
     return mbx::fail(h, MBEXWN_ERR_INVALID, std::string("unknown option: ") + name);
 }

@@ -68,6 +68,12 @@ __device__ __forceinline__ float apply_act(float v, int act, float alpha, float 
 
 }  // namespace mbx
 
+#define MBX_RC(expr)                                                                           \
+    do {                                                                                       \
+        int _rc = (expr);                                                                      \
+        if (_rc) return _rc;                                                                   \
+    } while (0)
+
 #define MBX_CUDA_CHECK(expr)                                                                   \
     do {                                                                                       \
         cudaError_t _e = (expr);                                                               \

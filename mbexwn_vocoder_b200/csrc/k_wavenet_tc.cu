@@ -65,7 +65,7 @@ constexpr int MAX_LIN_UP = 32;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)RING_BYTES + 512 + 2 * COND_BYTES;
 static_assert(SMEM_BYTES <= 232448, "dynamic shared memory budget (227 KB)");
 
-enum Epi { EPI_PLAIN = 0, EPI_GATE = 1, EPI_RESSKIP = 2 };
+enum Epi { EPI_PLAIN = 0, EPI_GATE = 1, EPI_RESSKIP = 2, EPI_CONV = 3 };
 
 struct KBlock {
     int a_col;      // first A column (elements) of the hi plane for this K block
@@ -85,7 +85,14 @@ struct alignas(64) GemmParams {
     int tiles_m, tiles_n;
     // epilogue
     const float* bias;      // (N) in packed column order
-    float* out_f32;         // EPI_PLAIN: (rows, n_cols)
+    float* out_f32;         // EPI_PLAIN: (rows, n_cols); EPI_CONV: optional (rows, ld_out)
+    // EPI_CONV: bias + activation, fp32 and / or bf16 [hi | lo] output with the sub-pixel unfold
+    int ld_out;
+    __nv_bfloat16* out_hilo;    // optional (rows * subpixel, 2 * out_cpad)
+    int out_cpad, subpixel, cout_per;   // cout_per = n_cols / subpixel
+    int cv_act, cv_act_mod, rate;
+    const float* alpha;
+    float leaky;
     // EPI_GATE
     const float* cond;      // (rows / lin_up, 2C) fp32
     __nv_bfloat16* act;     // (rows, ld_act): [hi (cpad) | lo (cpad)]
@@ -258,6 +265,66 @@ __device__ __forceinline__ void epi_plain(const GemmParams& p, uint32_t tacc, lo
             for (int i = 0; i < 32; ++i) {
                 int n = n0 + q * 32 + i;
                 if (n < p.n_cols) p.out_f32[row * p.n_cols + n] = v[i] + (p.bias ? p.bias[n] : 0.f);
+            }
+        }
+    }
+}
+
+// Conv epilogue of the mel-rate sub-nets (conv_layers.py:149-165 + PReLU / LeakyReLU, custom_pulsed_generator.py:86-124):
+// bias, activation, then fp32 rows and / or the bf16 [hi | lo] planes the next tensor-core conv reads.  A sub-pixel conv
+// (conv_layers.py:250-255) unfolds channel c' of row t to row t * f + c' / (cout / f), channel c' % (cout / f).
+// Guard rows are written as zeros (the next conv's zero padding; mirrored pads are patched by mirror_guards_kernel).
+__device__ __forceinline__ void epi_conv(const GemmParams& p, uint32_t tacc, long long row, int n0, int width, int half) {
+    float v[32];
+    bool valid = false;
+    if (row < p.rows) {
+        long long lo, hi;
+        valid = utt_bounds(p.grid, p.rate, row, lo, hi);
+    }
+    for (int q = half; q < width / 32; q += 2) {
+        tmem_ld32(tacc + q * 32, v);
+        tmem_ld_wait();
+        if (row >= p.rows) continue;
+        const int nq = n0 + q * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int n = nq + i;
+            float x = 0.f;
+            if (valid && n < p.n_cols) {
+                x = v[i] + __ldg(p.bias + n);
+                if (p.cv_act == ACT_PRELU) x = x >= 0.f ? x : __fmul_rn(__ldg(p.alpha + n % p.cv_act_mod), x);
+                else if (p.cv_act == ACT_LEAKY) x = x >= 0.f ? x : __fmul_rn(p.leaky, x);
+            }
+            v[i] = x;
+        }
+        if (p.out_f32) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const int n = nq + i;
+                if (n + 3 < p.n_cols) *reinterpret_cast<float4*>(p.out_f32 + row * p.ld_out + n) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                else
+                    for (int e = 0; e < 4; ++e)
+                        if (n + e < p.n_cols) p.out_f32[row * p.ld_out + n + e] = v[i + e];
+            }
+        }
+        if (p.out_hilo) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                const int n = nq + i;
+                if (n >= p.n_cols) break;                       // n_cols and cout_per are multiples of 8
+                const int sub = n / p.cout_per, ch = n - sub * p.cout_per;
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(v[i + e], h0, l0);
+                    split_bf16(v[i + e + 1], h1, l1);
+                    hw[e / 2] = pack2(h0, h1);
+                    lw[e / 2] = pack2(l0, l1);
+                }
+                __nv_bfloat16* dst = p.out_hilo + (row * p.subpixel + sub) * 2 * p.out_cpad + ch;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(dst + p.out_cpad) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
         }
     }
@@ -830,6 +897,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
             mbar_wait(&tmem_full[as], aph);
             tc_fence_after();
             if (EPI == EPI_PLAIN) epi_plain(p, tacc, row, n_blk * TILE_N, width, half);
+            if (EPI == EPI_CONV) epi_conv(p, tacc, row, n_blk * TILE_N, width, half);
             if (EPI == EPI_GATE) {
                 if (staged) epi_gate_staged(p, cond_stage + (tile_it & 1) * (COND_ROWS * COND_LD), tacc, row, m0, n_blk * TILE_N, width, half);
                 else epi_gate(p, tacc, row, n_blk * TILE_N, width, half);
@@ -916,6 +984,53 @@ __global__ void start_pack_kernel(const float* __restrict__ x, int cin, const fl
     }
 }
 
+// fp32 (rows, c) -> bf16 [hi | lo] (rows, 2 * cpad) for the first tensor-core conv of a sub-net.  Guard rows within
+// pad_l / pad_r of an utterance take the value the reference's TFPad1d would put there (custom_layers.py:47-71), every
+// other guard row and the channel padding are zero.  One thread per output (row, 8-channel group): a pure gather.
+__global__ void pack_hilo_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int c, int cpad,
+                                     int rate, int pad_l, int pad_r, int pad_mode, FrameGrid g) {
+    const int groups = cpad >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * groups) return;
+    const long long r = idx / groups;
+    const int ch0 = (int)(idx - r * groups) * 8;
+    long long src = -1, lo, hi;
+    if (utt_bounds(g, rate, r, lo, hi)) src = r;
+    else if (pad_mode != PAD_ZERO) {
+        if (utt_bounds(g, rate, r + pad_l, lo, hi) && r < lo) src = pad_index(r, lo, hi, pad_mode);
+        else if (r - pad_r >= 0 && utt_bounds(g, rate, r - pad_r, lo, hi) && r >= hi) src = pad_index(r, lo, hi, pad_mode);
+    }
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        float v0 = (src >= 0 && ch0 + j < c) ? x[src * c + ch0 + j] : 0.f;
+        float v1 = (src >= 0 && ch0 + j + 1 < c) ? x[src * c + ch0 + j + 1] : 0.f;
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v0, h0, l0);
+        split_bf16(v1, h1, l1);
+        hw[j / 2] = pack2(h0, h1);
+        lw[j / 2] = pack2(l0, l1);
+    }
+    *reinterpret_cast<uint4*>(out + r * 2 * cpad + ch0) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(out + r * 2 * cpad + cpad + ch0) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+// Patch the guard rows next to every utterance of a bf16 [hi | lo] activation buffer with the mirrored / replicated edge
+// rows (TFPad1d SYMMETRIC / EDGE) so that the next conv's row-shifted TMA loads see the reference's padding.
+// grid = (n_utt, pad_l + pad_r); threads stride over the row's 16-byte groups.
+__global__ void mirror_guards_kernel(__nv_bfloat16* __restrict__ buf, int row_elems, int rate, int pad_l, int pad_r, int pad_mode,
+                                     FrameGrid g) {
+    const int u = blockIdx.x, j = blockIdx.y;
+    const long long lo = (long long)g.utt_begin[u] * rate, hi = (long long)g.utt_end[u] * rate;
+    const long long dst = j < pad_l ? lo - 1 - j : hi + (j - pad_l);
+    if (dst < 0 || dst >= (long long)g.n_frames * rate) return;
+    const long long src = pad_index(dst, lo, hi, pad_mode);
+    if (src < 0) return;
+    const uint4* s4 = reinterpret_cast<const uint4*>(buf + src * row_elems);
+    uint4* d4 = reinterpret_cast<uint4*>(buf + dst * row_elems);
+    for (int i = threadIdx.x; i < row_elems / 8; i += blockDim.x) d4[i] = s4[i];
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -960,10 +1075,11 @@ int ensure_impl(WnTcState& st, std::string* err) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&im->sm_count, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t a = cudaSuccess;
-    const void* fns[6] = {(const void*)wn_gemm_kernel<EPI_PLAIN, 1>, (const void*)wn_gemm_kernel<EPI_GATE, 1>,
+    const void* fns[8] = {(const void*)wn_gemm_kernel<EPI_CONV, 1>, (const void*)wn_gemm_kernel<EPI_CONV, 2>,
+                          (const void*)wn_gemm_kernel<EPI_PLAIN, 1>, (const void*)wn_gemm_kernel<EPI_GATE, 1>,
                           (const void*)wn_gemm_kernel<EPI_RESSKIP, 1>, (const void*)wn_gemm_kernel<EPI_PLAIN, 2>,
                           (const void*)wn_gemm_kernel<EPI_GATE, 2>, (const void*)wn_gemm_kernel<EPI_RESSKIP, 2>};
-    for (int i = 0; i < 6 && a == cudaSuccess; ++i)
+    for (int i = 0; i < 8 && a == cudaSuccess; ++i)
         a = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (a != cudaSuccess) {
         if (err) *err = std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(a);
@@ -1114,6 +1230,55 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         if (e != cudaSuccess) return fail(std::string("res/skip GEMM: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
         *launches += 2;
     }
+    return MBEXWN_OK;
+}
+
+int wn_tc_pack(const float* x, void* out_hilo, long long rows, int c, int cpad, int rate, int pad_l, int pad_r, int pad_mode,
+               const FrameGrid& g, cudaStream_t s, std::string* error) {
+    const long long total = rows * (cpad / 8);
+    pack_hilo_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, reinterpret_cast<__nv_bfloat16*>(out_hilo), rows, c, cpad,
+                                                                          rate, pad_l, pad_r, pad_mode, g);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { if (error) *error = std::string("pack: ") + cudaGetErrorString(e); return MBEXWN_ERR_CUDA; }
+    return MBEXWN_OK;
+}
+
+int wn_tc_mirror(void* hilo, long long rows, int cpad, int rate, int pad_l, int pad_r, int pad_mode, const FrameGrid& g,
+                 cudaStream_t s, std::string* error) {
+    (void)rows;
+    if (pad_mode == PAD_ZERO || pad_l + pad_r <= 0) return MBEXWN_OK;
+    dim3 grid((unsigned)g.n_utt, (unsigned)(pad_l + pad_r));
+    mirror_guards_kernel<<<grid, 64, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(hilo), 2 * cpad, rate, pad_l, pad_r, pad_mode, g);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { if (error) *error = std::string("mirror: ") + cudaGetErrorString(e); return MBEXWN_ERR_CUDA; }
+    return MBEXWN_OK;
+}
+
+int wn_tc_conv(WnTcState& st, const TcConvArgs& a, const FrameGrid& g, cudaStream_t s, std::string* error) {
+    int rc = ensure_impl(st, error);
+    if (rc) return rc;
+    Impl* im = reinterpret_cast<Impl*>(st.impl);
+    im->cta_group = st.cta_group == 2 ? 2 : 1;
+    auto fail = [&](const std::string& m, int code) { if (error) *error = m; return code; };
+    if (a.cin_pad % TILE_K || a.cout % 8 || a.k * (a.cin_pad / TILE_K) > MAX_KB || a.k > 16)
+        return fail("tensor-core conv: unsupported geometry", MBEXWN_ERR_UNSUPPORTED);
+    if (a.out_hilo && (a.subpixel < 1 || a.cout % a.subpixel || (a.cout / a.subpixel) % 8))
+        return fail("tensor-core conv: sub-pixel unfold needs cout / f to be a multiple of 8", MBEXWN_ERR_UNSUPPORTED);
+    GemmParams p{};
+    if ((rc = make_map(im, &p.tm_a, a.a_hilo, a.rows, 2 * a.cin_pad, TILE_M, error))) return rc;
+    if ((rc = make_map(im, &p.tm_b, a.w, a.cout, 2 * a.k * a.cin_pad, TILE_N, error))) return rc;
+    int shifts[16];
+    for (int t = 0; t < a.k; ++t) shifts[t] = t * a.dilation - a.pad_l;
+    p.n_kb = build_kblocks(p.kb, a.k, shifts, a.cin_pad);
+    p.n_terms = 3; p.a_lo_off = a.cin_pad; p.b_lo_off = a.k * a.cin_pad;
+    p.rows = a.rows; p.n_cols = a.cout; p.bias = a.bias;
+    p.out_f32 = a.out_f32; p.ld_out = a.ld_out;
+    p.out_hilo = reinterpret_cast<__nv_bfloat16*>(a.out_hilo); p.out_cpad = a.out_cpad;
+    p.subpixel = a.subpixel > 0 ? a.subpixel : 1; p.cout_per = a.cout / p.subpixel;
+    p.cv_act = a.act; p.cv_act_mod = a.act_mod > 0 ? a.act_mod : a.cout; p.alpha = a.alpha; p.leaky = a.leaky; p.rate = a.rate;
+    p.grid = g;
+    cudaError_t e = launch_gemm<EPI_CONV>(im, p, s);
+    if (e != cudaSuccess) return fail(std::string("tensor-core conv: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
     return MBEXWN_OK;
 }
 

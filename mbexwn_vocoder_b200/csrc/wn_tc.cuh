@@ -29,6 +29,34 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
                   const std::function<const void*(const std::string&, size_t)>& tensor, cudaStream_t s, int* launches,
                   std::string* error);
 
+// One conv of a mel-rate sub-net on the tensor cores (3-product bf16 split, fp32 accumulate): out[r, :] =
+// act(sum_t A[r + t * dilation - pad_l, :] @ W[t] + bias), rows outside an utterance read as zero (or as the mirrored
+// rows wn_tc_pack / wn_tc_mirror put into the guard rows of A).
+struct TcConvArgs {
+    const void* a_hilo;         // (rows, 2 * cin_pad) bf16 [hi | lo]
+    long long rows;
+    int cin_pad;                // multiple of 64
+    const void* w;              // (cout, 2 * k * cin_pad) bf16 [hi | lo], (tap, cin)-major
+    int cout, k, dilation, pad_l;
+    const float* bias;          // (cout)
+    int act;                    // Act: none / PReLU / LeakyReLU
+    const float* alpha;         // PReLU slopes, index n % act_mod
+    int act_mod;
+    float leaky;
+    int rate;                   // rows per frame of A
+    float* out_f32;             // optional (rows, ld_out)
+    int ld_out;
+    void* out_hilo;             // optional (rows * subpixel, 2 * out_cpad) bf16 [hi | lo]
+    int out_cpad, subpixel;
+};
+int wn_tc_conv(WnTcState& st, const TcConvArgs& a, const FrameGrid& g, cudaStream_t s, std::string* error);
+// fp32 (rows, c) -> bf16 [hi | lo] (rows, 2 * cpad) with the reference's pad values in the guard rows next to utterances
+int wn_tc_pack(const float* x, void* out_hilo, long long rows, int c, int cpad, int rate, int pad_l, int pad_r, int pad_mode,
+               const FrameGrid& g, cudaStream_t s, std::string* error);
+// copy mirrored / replicated edge rows into the guard rows of a [hi | lo] buffer (SYMMETRIC / EDGE padding of the next conv)
+int wn_tc_mirror(void* hilo, long long rows, int cpad, int rate, int pad_l, int pad_r, int pad_mode, const FrameGrid& g,
+                 cudaStream_t s, std::string* error);
+
 // Stand-alone tap-GEMM (unit tests): out (rows, n) fp32 = sum over K blocks {a_col, a_row_shift, b_col} of
 // A[rows + shift, a_col : a_col + 64] @ B[:, b_col : b_col + 64]^T, A (rows, a_cols) bf16, B (n, b_cols) bf16.
 int wn_tc_gemm_test(WnTcState& st, const void* a_bf16, long long rows, int a_cols, const void* b_bf16, int n, int b_cols,

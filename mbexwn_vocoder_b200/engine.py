@@ -77,7 +77,14 @@ def make_config(plan: ModelPlan) -> _cabi.Config:
 def engine_halo(plan: ModelPlan) -> int:
     """Guard frames between utterances: covers the widest dilated tap and the PQMF polyphase reach."""
     reach = max(plan.max_halo_frames * plan.steps_per_frame, plan.pqmf_back, plan.pqmf_q - 1 - plan.pqmf_back)
-    return max(1, -(-reach // plan.steps_per_frame))
+    halo = max(1, -(-reach // plan.steps_per_frame))
+    # the tensor-core sub-net convs read their SYMMETRIC / EDGE pad rows from the guard rows next to each utterance:
+    # the guard gap must hold the right pad of one utterance and the left pad of the next without overlap
+    for ops in (plan.pp_ops, plan.ps_ops):
+        for op in ops:
+            if op.kind == "conv" and op.conv.pad_mode != 0:
+                halo = max(halo, -(-(op.conv.pad_l + op.conv.pad_r) // op.rate_in))
+    return halo
 
 
 class Engine:
@@ -140,8 +147,10 @@ class Engine:
                     f"set_tensor({name})")
 
     def _upload_tc(self, weights: Dict[str, np.ndarray]):
-        from .tc_pack import pack_tc_weights
+        from .tc_pack import pack_subnet_weights, pack_tc_weights
         for name, t in pack_tc_weights(self.plan, weights).items():
+            self._register_torch(name, t)
+        for name, t in pack_subnet_weights(self.plan, weights).items():
             self._register_torch(name, t)
 
     def tc_gemm(self, a: torch.Tensor, b: torch.Tensor, kblocks: np.ndarray) -> torch.Tensor:

@@ -85,3 +85,25 @@ def pack_tc_weights(plan: ModelPlan, weights: Dict[str, np.ndarray]) -> Dict[str
     for key, rb2, _ in rbs:
         out[key] = torch.from_numpy(rb2)
     return out
+
+
+def pack_conv_tc(w: np.ndarray) -> torch.Tensor:
+    """(k, cin, cout) folded conv kernel -> (cout, [hi | lo] x k x cin_pad) bf16, K-major, cin padded to 64."""
+    k, cin, cout = w.shape
+    cin_pad = -(-cin // TILE_K) * TILE_K
+    b = np.zeros((cout, k, cin_pad), dtype=np.float32)
+    b[:, :, :cin] = np.transpose(w, (2, 0, 1))
+    return hilo(b.reshape(cout, k * cin_pad))
+
+
+def pack_subnet_weights(plan: ModelPlan, weights: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
+    """Tensor-core copies ("<layer>/tc/W") of the wide mel-rate convs: both sub-nets and the conditioning conv."""
+    wn = plan.wavenet
+    layers = [op.conv for ops in (plan.pp_ops, plan.ps_ops) for op in ops if op.kind == "conv"]
+    layers += [l for l in plan.conv_layers() if l.name == f"{wn.name}_WNBlock_WN/cond_"]
+    out: Dict[str, torch.Tensor] = {}
+    for layer in layers:
+        if layer.cin >= 32 and layer.cout >= 16 and layer.cout % 8 == 0 and layer.dilation == 1:
+            w, _ = W.folded(weights, layer.name)
+            out[f"{layer.name}/tc/W"] = pack_conv_tc(w)
+    return out

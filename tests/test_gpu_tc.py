@@ -40,6 +40,8 @@ def cg(request, engine):
     (128, 128, [(0, 0, 0)]),
     (256, 128, [(0, 0, 0), (64, 0, 64)]),
     (300, 256, [(0, 0, 0), (64, 0, 64), (0, -3, 128), (64, 5, 192)]),
+    (200, 32, [(0, 0, 0), (64, 1, 64)]),
+    (513, 240, [(0, -1, 0), (0, 0, 64), (0, 1, 128)]),
     (1000, 320, [(64 * i, s, 64 * (3 * i + j)) for i in range(3) for j, s in enumerate((-8, 0, 8))]),
 ])
 def test_tap_gemm_exact(engine, cg, rows, n, kblocks):
@@ -92,6 +94,26 @@ def test_wavenet_tc_parity(engine, cg, speech_setup, precision, tol, snr):
         e = np.abs(out[u] - ref["waveform"][0]).max() / np.abs(ref["waveform"][0]).max()
         print(f"{precision} utt {u} waveform: max|err|/peak {e:.3e}  SNR {s:.1f} dB")
         assert s >= snr and e <= tol
+
+
+@pytest.mark.parametrize("lengths", [[40], [23, 57, 10, 1, 2]])
+def test_subnets_tc_parity(engine, cg, speech_setup, lengths):
+    """F0 net, VTF net and conditioning conv as 3-product bf16 tap-GEMMs (mirrored pad rows, sub-pixel unfold, PReLU
+    epilogue) against the fp32 oracle: every stage within 1e-4 of its peak, also for 1- and 2-frame utterances."""
+    hp, plan, w = speech_setup
+    oracle = OracleMBExWN(hp, w, torch.float32)
+    mels = [synthetic_mel(t, 20 + i) for i, t in enumerate(lengths)]
+    noise = [synthetic_noise(t * plan.steps_per_frame, 20 + i) for i, t in enumerate(lengths)]
+    out, tp = engine.forward(mels, noise=noise, precision="bf16x3", taps=["F0", "cond", "ceps"])
+    assert engine.lib.mbexwn_last_launch_count(engine._handle) > 0
+    for u, t in enumerate(lengths):
+        ref = oracle.forward(mels[u][None], noise[u][None])
+        ref["cond"] = ref["cond_lo"]
+        for st in ("F0", "cond", "ceps"):
+            r = np.asarray(ref[st][0]).reshape(-1)
+            e = np.abs(tp[st][u].reshape(-1) - r).max() / np.abs(r).max()
+            print(f"subnets tc utt {u} T={t} {st}: max|err|/peak {e:.3e}")
+            assert e <= 1e-4, st
 
 
 def test_wavenet_tc_parity_c340():
