@@ -83,6 +83,7 @@ struct alignas(64) GemmParams {
     long long rows;         // M
     int n_cols;             // N (multiple of 8; tiles are masked)
     int tiles_m, tiles_n;
+    int sched_m_major;      // tile schedule: 1 = a CTA walks all N tiles of its M tiles, 0 = round-robin over (m, n)
     // epilogue
     const float* bias;      // (N) in packed column order
     float* out_f32;         // EPI_PLAIN: (rows, n_cols); EPI_CONV: optional (rows, ld_out)
@@ -707,8 +708,24 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
     const bool leader = rank == 0;
     const int tiles_mg = (p.tiles_m + CG - 1) / CG;                 // M tiles per CTA group
-    const int n_tiles = tiles_mg * p.tiles_n;
     const int group = blockIdx.x / CG, n_groups = gridDim.x / CG;
+    // Tile schedule: a CTA (pair) owns M tiles group, group + n_groups, ... and walks all N tiles of one M tile back to
+    // back.  Every CTA gets the same mix of wide and narrow N tiles (a round-robin over (m, n) pairs gave the even
+    // CTAs all the 256-wide res/skip tiles and the odd ones all the 96-wide ones), and the A operand of an M tile is
+    // re-read by the same SM while it is still in L2.
+    // Small problems (fewer M tiles than a few waves of CTAs) keep the round-robin over (m, n) pairs so that all SMs get work.
+    const int n_seq = p.sched_m_major ? (group < tiles_mg ? ((tiles_mg - group + n_groups - 1) / n_groups) * p.tiles_n : 0)
+                                      : (group < tiles_mg * p.tiles_n ? (tiles_mg * p.tiles_n - group + n_groups - 1) / n_groups : 0);
+    auto tile_of = [&](int j, int& m_grp, int& n_blk) {
+        if (p.sched_m_major) {
+            m_grp = group + n_groups * (j / p.tiles_n);
+            n_blk = j % p.tiles_n;
+        } else {
+            const int t = group + n_groups * j;
+            m_grp = t / p.tiles_n;
+            n_blk = t - m_grp * p.tiles_n;
+        }
+    };
     const int ops_a = p.n_terms == 3 ? 2 : 1;                       // A / B tiles per K block
 
     if (warp == 0 && elect_one()) {
@@ -742,8 +759,9 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     if (warp == 0) {
         // ===== TMA producer: the whole warp walks the schedule, one elected lane issues =====
         uint32_t ia = 0, ib = 0;
-        for (int t = group; t < n_tiles; t += n_groups) {
-            const int m_grp = t / p.tiles_n, n_blk = t - m_grp * p.tiles_n;
+        for (int j = 0; j < n_seq; ++j) {
+            int m_grp, n_blk;
+            tile_of(j, m_grp, n_blk);
             const int m0 = (m_grp * CG + (int)rank) * TILE_M;
             int width = p.n_cols - n_blk * TILE_N;
             width = width > TILE_N ? TILE_N : ((width + 15) & ~15);
@@ -804,8 +822,9 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                 }
             };
             auto commit = [&](uint64_t* bar) { if (CG == 1) tc_commit(bar); else tc_commit_2sm(bar); };
-            for (int t = group; t < n_tiles; t += n_groups, ++tile_it) {
-                const int n_blk = t % p.tiles_n;
+            for (int j = 0; j < n_seq; ++j, ++tile_it) {
+                int m_grp, n_blk;
+                tile_of(j, m_grp, n_blk);
                 int width = p.n_cols - n_blk * TILE_N;
                 width = width > TILE_N ? TILE_N : ((width + 15) & ~15);
                 const uint32_t idesc = make_idesc(TILE_M * CG, width);
@@ -864,16 +883,18 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
         const bool staged = EPI == EPI_GATE && p.cond_rows > 0;
         uint32_t tile_it = 0;
         GateStage gst;
-        if (staged && group < n_tiles) {
+        if (staged && n_seq > 0) {
             // stage of the first tile
-            const int m_grp = group / p.tiles_n, n_blk = group - m_grp * p.tiles_n;
+            int m_grp, n_blk;
+            tile_of(0, m_grp, n_blk);
             int width = p.n_cols - n_blk * TILE_N;
             width = width > TILE_N ? TILE_N : ((width + 31) & ~31);
             gate_stage_load(p, (long long)(m_grp * CG + (int)rank) * TILE_M, n_blk * TILE_N, width, et, gst);
             gate_stage_store(cond_stage, width, et, gst);
         }
-        for (int t = group; t < n_tiles; t += n_groups, ++tile_it) {
-            const int m_grp = t / p.tiles_n, n_blk = t - m_grp * p.tiles_n;
+        for (int j = 0; j < n_seq; ++j, ++tile_it) {
+            int m_grp, n_blk;
+            tile_of(j, m_grp, n_blk);
             const uint32_t as = tile_it % ACC_STAGES, aph = (tile_it / ACC_STAGES) & 1;
             const uint32_t tacc = tmem_base + ((uint32_t)(q4 * 32) << 16) + as * TILE_N;
             const long long m0 = (long long)(m_grp * CG + (int)rank) * TILE_M;
@@ -885,9 +906,9 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
             if (EPI == EPI_RESSKIP) rctx = resskip_begin(p, row, n_blk * TILE_N, width, half, lane, old);   // loads fly during the MMAs
             int nwidth = 0;
             if (staged) {
-                const int tn = t + n_groups;
-                if (tn < n_tiles) {                                 // next tile's conditioning rows -> registers
-                    const int mg2 = tn / p.tiles_n, nb2 = tn - mg2 * p.tiles_n;
+                if (j + 1 < n_seq) {                                // next tile's conditioning rows -> registers
+                    int mg2, nb2;
+                    tile_of(j + 1, mg2, nb2);
                     nwidth = p.n_cols - nb2 * TILE_N;
                     nwidth = nwidth > TILE_N ? TILE_N : ((nwidth + 31) & ~31);
                     gate_stage_load(p, (long long)(mg2 * CG + (int)rank) * TILE_M, nb2 * TILE_N, nwidth, et, gst);
@@ -1095,9 +1116,11 @@ cudaError_t launch_gemm(Impl* im, GemmParams& p, cudaStream_t s) {
     p.tiles_m = (int)((p.rows + TILE_M - 1) / TILE_M);
     p.tiles_n = (p.n_cols + TILE_N - 1) / TILE_N;
     const int cg = im->cta_group;
-    const int n_tiles = ((p.tiles_m + cg - 1) / cg) * p.tiles_n;
+    const int tiles_mg = (p.tiles_m + cg - 1) / cg;
+    const int n_tiles = tiles_mg * p.tiles_n;
     int groups = im->sm_count / cg;
     if (n_tiles < groups) groups = n_tiles;
+    p.sched_m_major = tiles_mg >= 8 * groups ? 1 : 0;
     if (cg == 1) {
         wn_gemm_kernel<EPI, 1><<<groups, TC_THREADS, SMEM_BYTES, s>>>(p);
         return cudaGetLastError();

@@ -10,7 +10,7 @@ namespace mbx {
 
 struct WnTcState {
     bool ready = false;
-    int cta_group = 1;          // option "tc_cta_group": 1 = one CTA per tile, 2 = CTA pairs (cta_group::2)
+    int cta_group = 2;          // option "tc_cta_group": 1 = one CTA per tile, 2 = CTA pairs (cta_group::2)
     int cond_stage = 1;         // option "tc_cond_stage": gate epilogue reads its conditioning rows from a smem stage
     void* impl = nullptr;
 };
