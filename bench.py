@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16x3", choices=["f16f8", "bf16x3", "bf16", "fp32"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cta-group", type=int, default=2, choices=[1, 2], help="tcgen05 tiles per CTA (1) or per CTA pair (2)")
@@ -265,7 +265,9 @@ def main():
     n_gemm = 2 * plan.wavenet.n_layers
     wn_ms = stage_acc["wavenet"]
     achieved = wn_flops / (wn_ms / 1e3) / 1e12
-    factor = 3 if args.precision == "bf16x3" else 1
+    # executed tensor work in bf16-rate product equivalents: bf16x3 = 3 products; f16f8 = 1 fp16 product + 2 e4m3 products
+    # that run at twice the rate
+    factor = {"bf16x3": 3, "f16f8": 2}.get(args.precision, 1)
     peak = pk["bf16_tflops_sustained"]
     roofline = {
         "bound": "tensor", "kernel": "wn_gemm_kernel (tcgen05 tap-GEMM, gate + res/skip epilogues)",
@@ -290,7 +292,8 @@ def main():
         "metric": "audio-sec generated/sec (24 kHz)", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16x3": "bf16x3 (bf16 hi/lo split, fp32 accumulate; fp32-accurate)", "bf16": "bf16",
+        "dtype": {"f16f8": "f16+2xe4m3 split (fp16 product + two e4m3 correction products, fp32 accumulate; fp32-accurate)",
+                  "bf16x3": "bf16x3 (bf16 hi/lo split, fp32 accumulate; fp32-accurate)", "bf16": "bf16",
                   "fp32": "f32"}[args.precision],
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "per_gpu_batch": batch, "frames": frames,

@@ -53,7 +53,9 @@ enum mbexwn_status {
 enum mbexwn_precision {
     MBEXWN_PREC_FP32_SIMT = 0,  /* fp32 FMA on CUDA cores: bit-for-bit the reference's arithmetic type          */
     MBEXWN_PREC_BF16X3 = 1,     /* tcgen05 bf16 with hi/lo operand split (3 products), fp32 accumulate in TMEM */
-    MBEXWN_PREC_BF16 = 2        /* tcgen05 bf16 operands, fp32 accumulate                                      */
+    MBEXWN_PREC_BF16 = 2,       /* tcgen05 bf16 operands, fp32 accumulate                                      */
+    MBEXWN_PREC_F16F8 = 3       /* tcgen05 fp16 main product + two e4m3 correction products (lo x hi, hi x lo) at the
+                                   fp8 rate, folded in with scale-input-d 2^-15; fp32 accumulate; fp32-accurate    */
 };
 
 /* One step of a mel-rate conv sub-net (generate_subnet_from_specs, custom_pulsed_generator.py:38-148) with the
@@ -184,6 +186,13 @@ MBEXWN_API int mbexwn_k_lininterp(mbexwn_handle_t h, const mbexwn_batch_t* grid,
 MBEXWN_API int mbexwn_k_tc_gemm(mbexwn_handle_t h, const void* a_bf16, int64_t rows, int32_t a_cols, const void* b_bf16,
                                 int32_t n, int32_t b_cols, const int32_t* kblocks, int32_t n_kb, float* out,
                                 void* cuda_stream);
+
+/* The split-precision tap-GEMM of MBEXWN_PREC_F16F8 on its own.  A (rows, 4 * a_cpad bytes per row) = [fp16 x (a_cpad) |
+ * e4m3 lo8 (a_cpad) | e4m3 hi8 (a_cpad)], B (n, 4 * b_k bytes per row) = [fp16 w (b_k) | e4m3 hi8 (b_k) | e4m3 lo8 (b_k)];
+ * out = sum_b A16 @ B16^T + 2^-15 * sum_b (A_lo8 @ B_hi8^T + A_hi8 @ B_lo8^T) over the same K-block list as above. */
+MBEXWN_API int mbexwn_k_tc_gemm_f16f8(mbexwn_handle_t h, const void* a, int64_t rows, int32_t a_cpad, const void* b,
+                                      int32_t n, int32_t b_k, const int32_t* kblocks, int32_t n_kb, float* out,
+                                      void* cuda_stream);
 
 #ifdef __cplusplus
 }

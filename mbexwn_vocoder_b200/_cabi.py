@@ -15,8 +15,9 @@ MAX_OPS = 32
 N_STAGES = 7
 STAGE_NAMES = ("f0_net", "excitation", "cond_conv", "wavenet", "post_pqmf", "vtf_net", "stft_ola")
 
-PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16, PREC_F16F8 = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16,
+              "f16f8": PREC_F16F8}
 
 OK, ERR_INVALID, ERR_MISSING, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 
@@ -81,6 +82,8 @@ SYMBOLS = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mbexwn_k_tc_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mbexwn_k_tc_gemm_f16f8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mbexwn_k_lininterp": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Op), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
 }

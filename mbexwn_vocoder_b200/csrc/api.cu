@@ -342,7 +342,7 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
     if (!b || b->n_frames <= 0 || b->n_utt <= 0) return fail(h, MBEXWN_ERR_INVALID, "empty batch");
     if (!b->frame_utt || !b->utt_begin || !b->utt_end || !b->chunk_first || !b->mel || !b->out)
         return fail(h, MBEXWN_ERR_INVALID, "batch has null pointers");
-    if (precision < MBEXWN_PREC_FP32_SIMT || precision > MBEXWN_PREC_BF16)
+    if (precision < MBEXWN_PREC_FP32_SIMT || precision > MBEXWN_PREC_F16F8)
         return fail(h, MBEXWN_ERR_INVALID, "unknown precision");
     Ctx cx{h, b, FrameGrid{b->frame_utt, b->utt_begin, b->utt_end, b->n_frames, b->n_utt},
            carve(c, b->n_frames, b->n_chunks, precision, h->debug_taps), reinterpret_cast<char*>(workspace), s};
@@ -585,6 +585,10 @@ int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value) {
     if (!strcmp(name, "tc_cta_group")) { h->tc.cta_group = value == 2 ? 2 : 1; return MBEXWN_OK; }
     if (!strcmp(name, "tc_subnets")) { h->tc_subnets = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "tc_cond_stage")) { h->tc.cond_stage = value ? 1 : 0; return MBEXWN_OK; }
+    if (!strcmp(name, "tc8_h_lo")) { h->tc.sh_h_lo = value; return MBEXWN_OK; }
+    if (!strcmp(name, "tc8_h_hi")) { h->tc.sh_h_hi = value; return MBEXWN_OK; }
+    if (!strcmp(name, "tc8_a_lo")) { h->tc.sh_a_lo = value; return MBEXWN_OK; }
+    if (!strcmp(name, "tc8_a_hi")) { h->tc.sh_a_hi = value; return MBEXWN_OK; }
     return mbx::fail(h, MBEXWN_ERR_INVALID, std::string("unknown option: ") + name);
 }
 
@@ -622,6 +626,13 @@ int mbexwn_k_tc_gemm(mbexwn_handle_t h, const void* a_bf16, int64_t rows, int32_
     if (!h || !a_bf16 || !b_bf16 || !kblocks || !out) return MBEXWN_ERR_INVALID;
     return mbx::wn_tc_gemm_test(h->tc, a_bf16, rows, a_cols, b_bf16, n, b_cols, kblocks, n_kb, out,
                                 reinterpret_cast<cudaStream_t>(cuda_stream), &h->error);
+}
+
+int mbexwn_k_tc_gemm_f16f8(mbexwn_handle_t h, const void* a, int64_t rows, int32_t a_cpad, const void* b, int32_t n,
+                           int32_t b_k, const int32_t* kblocks, int32_t n_kb, float* out, void* cuda_stream) {
+    if (!h || !a || !b || !kblocks || !out) return MBEXWN_ERR_INVALID;
+    return mbx::wn_tc_gemm_test_f16f8(h->tc, a, rows, a_cpad, b, n, b_k, kblocks, n_kb, out,
+                                      reinterpret_cast<cudaStream_t>(cuda_stream), &h->error);
 }
 
 }  // extern "C"

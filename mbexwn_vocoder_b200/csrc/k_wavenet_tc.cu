@@ -37,6 +37,8 @@
 // double-buffered smem stage that is loaded one tile ahead, so its global-load latency is off the critical path.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include <map>
 #include <vector>
@@ -76,10 +78,18 @@ struct KBlock {
 struct alignas(64) GemmParams {
     CUtensorMap tm_a;
     CUtensorMap tm_b;
+    CUtensorMap tm_a8;      // n_terms == 2: byte view of the A rows (e4m3 planes), 64-byte boxes, SWIZZLE_64B
+    CUtensorMap tm_b8;
     KBlock kb[MAX_KB];
     int n_kb;
-    int n_terms;            // 1: hi*hi;  3: hi*hi + lo*hi + hi*lo, the lo planes sit a_lo_off / b_lo_off columns further
+    int n_terms;            // 1: hi*hi;  3: hi*hi + lo*hi + hi*lo, the lo planes sit a_lo_off / b_lo_off columns further;
+                            // 2: fp16 hi*hi + 2^-15 (e4m3 lo8*hi8 + e4m3 hi8*lo8) (MBEXWN_PREC_F16F8)
     int a_lo_off, b_lo_off;
+    int f16;                // main product operands are fp16 (else bf16)
+    int a8_lo_off, a8_hi_off, b8_hi_off, b8_lo_off;     // byte columns of the e4m3 planes in the A / B rows
+    // scales of the e4m3 planes the epilogues write: x_lo8 = e4m3((x - fp16(x)) * lo_scale), x_hi8 = e4m3(x * hi_scale)
+    int out_f16f8;
+    float out_lo_scale, out_hi_scale, in_lo_inv;
     long long rows;         // M
     int n_cols;             // N (multiple of 8; tiles are masked)
     int tiles_m, tiles_n;
@@ -208,6 +218,42 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, ui
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// e4m3 x e4m3 -> fp32 (kind::f8f6f4, K = 32 per instruction: twice the MACs of a kind::f16 instruction in the same time)
+__device__ __forceinline__ void tc_mma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_f8_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// D = A * B + D * 2^-15 (scale-input-d): folds the 2^15 scale of the e4m3 correction products already sitting in the
+// accumulator into the first fp16 product of a tile
+constexpr int CORR_SHIFT = 15;
+__device__ __forceinline__ void tc_mma_f16_sd(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, %4;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(CORR_SHIFT)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_sd_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p, %4;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(CORR_SHIFT)
+        : "memory");
+}
 // 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -228,6 +274,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ constexpr uint32_t make_idesc(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// the same with format code 0 for A and B: fp16 under kind::f16, e4m3 under kind::f8f6f4
+__device__ __forceinline__ constexpr uint32_t make_idesc_fmt0(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
     hi = __float2bfloat16_rn(x);
@@ -236,6 +286,38 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// MBEXWN_PREC_F16F8 operand planes of 8 consecutive channels: fp16(x), e4m3((x - fp16(x)) * lo_scale), e4m3(x * hi_scale).
+// The scales are powers of two chosen so that the planes sit in e4m3's normal range and the two correction products of a
+// GEMM share the factor 2^15 that scale-input-d removes (see wn_tc_forward).
+__device__ __forceinline__ void split_f16f8(const float (&a)[8], float lo_scale, float hi_scale, uint4& h16, uint2& lo8, uint2& hi8) {
+    uint32_t hw[4], l[4], h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __half2 hh = __floats2half2_rn(a[2 * e], a[2 * e + 1]);
+        const float2 hf = __half22float2(hh);
+        hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[e] = __nv_cvt_float2_to_fp8x2(make_float2((a[2 * e] - hf.x) * lo_scale, (a[2 * e + 1] - hf.y) * lo_scale), __NV_SATFINITE, __NV_E4M3);
+        h[e] = __nv_cvt_float2_to_fp8x2(make_float2(a[2 * e] * hi_scale, a[2 * e + 1] * hi_scale), __NV_SATFINITE, __NV_E4M3);
+    }
+    h16 = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    lo8 = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+    hi8 = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+}
+
+// the value a (fp16, e4m3 lo8) pair stands for: 8 channels
+__device__ __forceinline__ void join_f16f8(const uint4& h16, const uint2& lo8, float lo_inv, float (&x)[8]) {
+    const uint32_t hw[4] = {h16.x, h16.y, h16.z, h16.w};
+    const uint32_t lw[2] = {lo8.x, lo8.y};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+        const __half2_raw lr = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(lw[e >> 1] >> (16 * (e & 1))), __NV_E4M3);
+        const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lr));
+        x[2 * e] = fmaf(lf.x, lo_inv, hf.x);
+        x[2 * e + 1] = fmaf(lf.y, lo_inv, hf.y);
+    }
 }
 
 // ---- epilogues: one thread = one accumulator row -----------------------------------------------------------------
@@ -362,6 +444,7 @@ __device__ __forceinline__ void epi_gate(const GemmParams& p, uint32_t tacc, lon
         if (row >= p.rows) continue;
         const int ch0 = ch_tile + q * 32;
         __nv_bfloat16* dst = p.act + row * p.ld_act + ch0;
+        uint8_t* dst8 = reinterpret_cast<uint8_t*>(p.act + row * p.ld_act) + 2 * p.cpad + ch0;      // e4m3 lo8 plane; hi8 is cpad further
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
             float a[8];
@@ -401,6 +484,16 @@ __device__ __forceinline__ void epi_gate(const GemmParams& p, uint32_t tacc, lon
 #pragma unroll
                     for (int e = 0; e < 4; ++e) a[4 * v4 + e] = 0.f;
                 }
+            }
+            if (p.out_f16f8) {
+                uint4 h16;
+                uint2 l8, h8;
+                split_f16f8(a, p.out_lo_scale, p.out_hi_scale, h16, l8, h8);
+                uint8_t* d8 = dst8 + i;
+                *reinterpret_cast<uint4*>(dst + i) = h16;
+                *reinterpret_cast<uint2*>(d8) = l8;
+                *reinterpret_cast<uint2*>(d8 + p.cpad) = h8;
+                continue;
             }
             uint32_t hw4[4], lw4[4];
 #pragma unroll
@@ -490,6 +583,7 @@ __device__ __forceinline__ void epi_gate_staged(const GemmParams& p, const float
         tmem_ld_wait();
         if (row >= p.rows) continue;
         __nv_bfloat16* dst = p.act + row * p.ld_act + ch_tile + q * 32;
+        uint8_t* dst8 = reinterpret_cast<uint8_t*>(p.act + row * p.ld_act) + 2 * p.cpad + ch_tile + q * 32;    // e4m3 lo8 plane; hi8 is cpad further
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
             float a[8];
@@ -520,6 +614,16 @@ __device__ __forceinline__ void epi_gate_staged(const GemmParams& p, const float
                     }
                     a[4 * v4 + e] = valid ? t * fast_sigmoid(sg) : 0.f;       // padded channels: z = 0 -> act = 0
                 }
+            }
+            if (p.out_f16f8) {
+                uint4 h16;
+                uint2 l8, h8;
+                split_f16f8(a, p.out_lo_scale, p.out_hi_scale, h16, l8, h8);
+                uint8_t* d8 = dst8 + i;
+                *reinterpret_cast<uint4*>(dst + i) = h16;
+                *reinterpret_cast<uint2*>(d8) = l8;
+                *reinterpret_cast<uint2*>(d8 + p.cpad) = h8;
+                continue;
             }
             uint32_t hw4[4], lw4[4];
 #pragma unroll
@@ -565,7 +669,12 @@ __device__ __forceinline__ void resskip_load_old(const GemmParams& p, const ResS
             if ((c.vmask >> r) & 1u) {
                 const __nv_bfloat16* ph = p.h + (c.row0 + r) * p.ld_h + n + cg * 8;
                 old[ps] = *reinterpret_cast<const uint4*>(ph);
-                old[4 + ps] = *reinterpret_cast<const uint4*>(ph + p.cpad);
+                if (p.out_f16f8) {
+                    const uint2 l8 = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(p.h + (c.row0 + r) * p.ld_h) + 2 * p.cpad + n + cg * 8);
+                    old[4 + ps] = make_uint4(l8.x, l8.y, 0u, 0u);
+                } else {
+                    old[4 + ps] = *reinterpret_cast<const uint4*>(ph + p.cpad);
+                }
             }
         }
     } else if (!p.first) {
@@ -597,6 +706,21 @@ __device__ __forceinline__ void resskip_store(const GemmParams& p, const ResSkip
             if (!((c.vmask >> r) & 1u)) continue;
             const float4 x0 = xp_read(S, r, 2 * cg), x1 = xp_read(S, r, 2 * cg + 1);
             const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            if (p.out_f16f8) {
+                float prev[8], o[8];
+                join_f16f8(old[ps], make_uint2(old[4 + ps].x, old[4 + ps].y), p.in_lo_inv, prev);
+#pragma unroll
+                for (int idx = 0; idx < 8; ++idx) o[idx] = (ch0 + idx < p.c) ? prev[idx] + (xv[idx] + bv[idx]) : 0.f;
+                uint4 h16;
+                uint2 l8, h8;
+                split_f16f8(o, p.out_lo_scale, p.out_hi_scale, h16, l8, h8);
+                __nv_bfloat16* prow = p.h + (c.row0 + r) * p.ld_h;
+                uint8_t* p8 = reinterpret_cast<uint8_t*>(prow) + 2 * p.cpad + ch0;
+                *reinterpret_cast<uint4*>(prow + ch0) = h16;
+                *reinterpret_cast<uint2*>(p8) = l8;
+                *reinterpret_cast<uint2*>(p8 + p.cpad) = h8;
+                continue;
+            }
             uint32_t hw[4] = {old[ps].x, old[ps].y, old[ps].z, old[ps].w};
             uint32_t lw[4] = {old[4 + ps].x, old[4 + ps].y, old[4 + ps].z, old[4 + ps].w};
 #pragma unroll
@@ -690,6 +814,8 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     // K-major SWIZZLE_128B smem matrix descriptor without the address field: LBO = 1 (ignored), SBO = 1024 B between
     // 8-row groups, descriptor version 1 (Blackwell), swizzle mode 2 (128 B)
     constexpr uint64_t DESC_HI = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    // the e4m3 tiles are 64 bytes wide: SWIZZLE_64B (layout type 4), 512 B between 8-row groups
+    constexpr uint64_t DESC8_HI = ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* ring_a = smem;
@@ -731,6 +857,10 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     if (warp == 0 && elect_one()) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_b) : "memory");
+        if (p.n_terms == 2) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_a8) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_b8) : "memory");
+        }
     }
     if (warp == 1 && elect_one()) {
         // full barriers: one arrival (the leader's expect_tx for the bytes of *all* CTAs of the group); a peer CTA's
@@ -766,6 +896,51 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
             int width = p.n_cols - n_blk * TILE_N;
             width = width > TILE_N ? TILE_N : ((width + 15) & ~15);
             const int nb0 = n_blk * TILE_N + (int)rank * (width / CG);      // this CTA's share of the B rows
+            if (p.n_terms == 2) {
+                // e4m3 correction planes first (their products are rescaled by the first fp16 MMA of the tile): one A slot
+                // holds the [lo8 | hi8] tiles of a K block (2 x 128 rows x 64 B), one B slot the [hi8 | lo8] weight tiles
+                for (int kb = 0; kb < p.n_kb; ++kb) {
+                    const int a_col = p.kb[kb].a_col, a_row = m0 + p.kb[kb].a_shift, b_col = p.kb[kb].b_col;
+                    {
+                        const uint32_t s = ia % NA, ph = (ia / NA) & 1;
+                        ++ia;
+                        mbar_wait(&empty_a[s], ph ^ 1);
+                        if (elect_one()) {
+                            uint8_t* dst = ring_a + s * A_BYTES;
+                            if (CG == 1) {
+                                mbar_expect_tx(&full_a[s], A_BYTES);
+                                tma_load_2d(&p.tm_a8, &full_a[s], dst, p.a8_lo_off + a_col, a_row);
+                                tma_load_2d(&p.tm_a8, &full_a[s], dst + A_BYTES / 2, p.a8_hi_off + a_col, a_row);
+                            } else {
+                                const uint32_t lbar = map_to_cta(smem_u32(&full_a[s]), 0);
+                                if (leader) mbar_expect_tx(&full_a[s], CG * A_BYTES);
+                                tma_load_2d_2sm(&p.tm_a8, lbar, dst, p.a8_lo_off + a_col, a_row);
+                                tma_load_2d_2sm(&p.tm_a8, lbar, dst + A_BYTES / 2, p.a8_hi_off + a_col, a_row);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    {
+                        const uint32_t s = ib % NB, ph = (ib / NB) & 1;
+                        ++ib;
+                        mbar_wait(&empty_b[s], ph ^ 1);
+                        if (elect_one()) {
+                            uint8_t* dst = ring_b + s * B_BYTES;
+                            if (CG == 1) {
+                                mbar_expect_tx(&full_b[s], B_BYTES);
+                                tma_load_2d(&p.tm_b8, &full_b[s], dst, p.b8_hi_off + b_col, nb0);
+                                tma_load_2d(&p.tm_b8, &full_b[s], dst + B_BYTES / 2, p.b8_lo_off + b_col, nb0);
+                            } else {
+                                const uint32_t lbar = map_to_cta(smem_u32(&full_b[s]), 0);
+                                if (leader) mbar_expect_tx(&full_b[s], CG * B_BYTES);
+                                tma_load_2d_2sm(&p.tm_b8, lbar, dst, p.b8_hi_off + b_col, nb0);
+                                tma_load_2d_2sm(&p.tm_b8, lbar, dst + B_BYTES / 2, p.b8_lo_off + b_col, nb0);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
             for (int kb = 0; kb < p.n_kb; ++kb) {
                 const int a_col = p.kb[kb].a_col, a_row = m0 + p.kb[kb].a_shift, b_col = p.kb[kb].b_col;
                 for (int o = 0; o < ops_a; ++o) {
@@ -811,14 +986,33 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
         if (leader) {
             uint32_t ia = 0, ib = 0, tile_it = 0;
             const uint32_t a_base = smem_u32(ring_a) >> 4, b_base = smem_u32(ring_b) >> 4;
-            auto mma4 = [&](uint32_t tacc, uint32_t sa, uint32_t sb, uint32_t idesc, bool first) {
+            // first: 0 = accumulate, 1 = the first MMA overwrites the accumulator, 2 = the first MMA rescales it by 2^-15
+            auto mma4 = [&](uint32_t tacc, uint32_t sa, uint32_t sb, uint32_t idesc, int first) {
                 const uint64_t da = DESC_HI | (uint64_t)(a_base + sa * (A_BYTES >> 4));
                 const uint64_t db = DESC_HI | (uint64_t)(b_base + sb * (B_BYTES >> 4));
 #pragma unroll
                 for (int k = 0; k < TILE_K / UMMA_K; ++k) {
                     // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16-byte units
-                    if (CG == 1) tc_mma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
-                    else tc_mma_bf16_2sm(tacc, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                    if (k == 0 && first == 2) {
+                        if (CG == 1) tc_mma_f16_sd(tacc, da, db, idesc);
+                        else tc_mma_f16_sd_2sm(tacc, da, db, idesc);
+                    } else if (CG == 1) tc_mma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, !(first == 1 && k == 0));
+                    else tc_mma_bf16_2sm(tacc, da + 2 * k, db + 2 * k, idesc, !(first == 1 && k == 0));
+                }
+            };
+            // e4m3 products of one K block: lo8 (A) x hi8 (B), then hi8 (A) x lo8 (B); 64 channels = 2 instructions of K = 32
+            // each (32 B along K inside the 64 B swizzle row: +2 in 16-byte units)
+            auto mma8 = [&](uint32_t tacc, uint32_t sa, uint32_t sb, uint32_t idesc, bool first) {
+                const uint64_t da = DESC8_HI | (uint64_t)(a_base + sa * (A_BYTES >> 4));
+                const uint64_t db = DESC8_HI | (uint64_t)(b_base + sb * (B_BYTES >> 4));
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const uint64_t xa = da + (t ? (A_BYTES >> 5) : 0), xb = db + (t ? (B_BYTES >> 5) : 0);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        if (CG == 1) tc_mma_f8(tacc, xa + 2 * k, xb + 2 * k, idesc, !(first && t == 0 && k == 0));
+                        else tc_mma_f8_2sm(tacc, xa + 2 * k, xb + 2 * k, idesc, !(first && t == 0 && k == 0));
+                    }
                 }
             };
             auto commit = [&](uint64_t* bar) { if (CG == 1) tc_commit(bar); else tc_commit_2sm(bar); };
@@ -827,11 +1021,28 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                 tile_of(j, m_grp, n_blk);
                 int width = p.n_cols - n_blk * TILE_N;
                 width = width > TILE_N ? TILE_N : ((width + 15) & ~15);
-                const uint32_t idesc = make_idesc(TILE_M * CG, width);
+                const uint32_t idesc = p.f16 ? make_idesc_fmt0(TILE_M * CG, width) : make_idesc(TILE_M * CG, width);
                 const uint32_t as = tile_it % ACC_STAGES, aph = (tile_it / ACC_STAGES) & 1;
                 mbar_wait(&tmem_empty[as], aph ^ 1);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + as * TILE_N;
+                if (p.n_terms == 2) {
+                    for (int kb = 0; kb < p.n_kb; ++kb) {
+                        const uint32_t sa = ia % NA, pa = (ia / NA) & 1;
+                        const uint32_t sb = ib % NB, pb = (ib / NB) & 1;
+                        mbar_wait(&full_a[sa], pa);
+                        mbar_wait(&full_b[sb], pb);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            mma8(tacc, sa, sb, idesc, kb == 0);
+                            commit(&empty_a[sa]);
+                            commit(&empty_b[sb]);
+                        }
+                        __syncwarp();
+                        ia += 1;
+                        ib += 1;
+                    }
+                }
                 for (int kb = 0; kb < p.n_kb; ++kb) {
                     const uint32_t sa_hi = ia % NA, pa_hi = (ia / NA) & 1;
                     const uint32_t sb_hi = ib % NB, pb_hi = (ib / NB) & 1;
@@ -841,12 +1052,12 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                     if (p.n_terms == 3) {
                         const uint32_t sa_lo = (ia + 1) % NA, pa_lo = ((ia + 1) / NA) & 1;
                         const uint32_t sb_lo = (ib + 1) % NB, pb_lo = ((ib + 1) / NB) & 1;
-                        if (elect_one()) mma4(tacc, sa_hi, sb_hi, idesc, kb == 0);     // hi * hi
+                        if (elect_one()) mma4(tacc, sa_hi, sb_hi, idesc, kb == 0 ? 1 : 0);     // hi * hi
                         __syncwarp();
                         mbar_wait(&full_a[sa_lo], pa_lo);
                         tc_fence_after();
                         if (elect_one()) {
-                            mma4(tacc, sa_lo, sb_hi, idesc, false);                    // lo * hi
+                            mma4(tacc, sa_lo, sb_hi, idesc, 0);                        // lo * hi
                             commit(&empty_a[sa_lo]);
                             commit(&empty_b[sb_hi]);
                         }
@@ -854,7 +1065,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                         mbar_wait(&full_b[sb_lo], pb_lo);
                         tc_fence_after();
                         if (elect_one()) {
-                            mma4(tacc, sa_hi, sb_lo, idesc, false);                    // hi * lo
+                            mma4(tacc, sa_hi, sb_lo, idesc, 0);                        // hi * lo
                             commit(&empty_a[sa_hi]);
                             commit(&empty_b[sb_lo]);
                             if (kb == p.n_kb - 1) commit(&tmem_full[as]);              // accumulator complete
@@ -864,7 +1075,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                         ib += 2;
                     } else {
                         if (elect_one()) {
-                            mma4(tacc, sa_hi, sb_hi, idesc, kb == 0);
+                            mma4(tacc, sa_hi, sb_hi, idesc, kb == 0 ? (p.n_terms == 2 ? 2 : 1) : 0);
                             commit(&empty_a[sa_hi]);
                             commit(&empty_b[sb_hi]);
                             if (kb == p.n_kb - 1) commit(&tmem_full[as]);              // both CTAs of a pair are told
@@ -951,7 +1162,8 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
 constexpr int START_ROWS = 64;
 constexpr int START_MAX_CIN = 16;
 __global__ void start_pack_kernel(const float* __restrict__ x, int cin, const float* __restrict__ w, const float* __restrict__ b,
-                                  __nv_bfloat16* __restrict__ out, long long rows, int c, int cpad, int rate, FrameGrid g) {
+                                  __nv_bfloat16* __restrict__ out, long long rows, int c, int cpad, int rate, FrameGrid g,
+                                  int f16f8, float lo_scale, float hi_scale) {
     extern __shared__ float sw[];                       // [cin + 1][cpad]: weights, then bias
     float* sx = sw + (cin + 1) * cpad;                  // [START_ROWS][cin] inputs, zero for guard rows
     __shared__ int svalid[START_ROWS];
@@ -990,6 +1202,16 @@ __global__ void start_pack_kernel(const float* __restrict__ x, int cin, const fl
             const float4 b1 = *reinterpret_cast<const float4*>(sw + cin * cpad + ch0 + 4);
             v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
             v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (f16f8) {
+            uint4 h16;
+            uint2 l8, h8;
+            split_f16f8(v, lo_scale, hi_scale, h16, l8, h8);
+            uint8_t* p8 = reinterpret_cast<uint8_t*>(out + r * 2 * cpad) + 2 * cpad + ch0;
+            *reinterpret_cast<uint4*>(out + r * 2 * cpad + ch0) = h16;
+            *reinterpret_cast<uint2*>(p8) = l8;
+            *reinterpret_cast<uint2*>(p8 + cpad) = h8;
+            continue;
         }
         uint32_t hw[4], lw[4];
 #pragma unroll
@@ -1075,6 +1297,23 @@ int make_map(Impl* im, CUtensorMap* tm, const void* base, long long rows, long l
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         if (err) *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
+        return MBEXWN_ERR_CUDA;
+    }
+    return MBEXWN_OK;
+}
+
+// byte view of a row-major matrix (rows, row_bytes) for the e4m3 planes: 64-byte x box_rows boxes, SWIZZLE_64B
+int make_map8(Impl* im, CUtensorMap* tm, const void* base, long long rows, long long row_bytes, int box_rows, std::string* err) {
+    if (box_rows == TILE_N) box_rows = TILE_N / im->cta_group;
+    cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)TILE_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = im->encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) *err = "cuTensorMapEncodeTiled (e4m3 planes) failed with code " + std::to_string((int)r);
         return MBEXWN_ERR_CUDA;
     }
     return MBEXWN_OK;
@@ -1173,7 +1412,11 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
     Impl* im = reinterpret_cast<Impl*>(st.impl);
     const long long rows = (long long)g.n_frames * c.steps_per_frame;
     const int cpad = round_up(c.wn_c, TILE_K);
-    const int n_terms = precision == MBEXWN_PREC_BF16X3 ? 3 : 1;
+    const bool f8 = precision == MBEXWN_PREC_F16F8;
+    const int n_terms = precision == MBEXWN_PREC_BF16X3 ? 3 : (f8 ? 2 : 1);
+    // power-of-two scales of the e4m3 planes (MBEXWN_PREC_F16F8): residual stream h and gated activations
+    const float h_lo = ldexpf(1.f, st.sh_h_lo), h_hi = ldexpf(1.f, st.sh_h_hi);
+    const float a_lo = ldexpf(1.f, st.sh_a_lo), a_hi = ldexpf(1.f, st.sh_a_hi);
     const std::string n = c.wn_name;
     if (c.wn_c % 4) { if (error) *error = "tensor-core path needs n_channels % 4 == 0"; return MBEXWN_ERR_UNSUPPORTED; }
     if (c.wn_k * (cpad / TILE_K) > MAX_KB) { if (error) *error = "K-block table too small"; return MBEXWN_ERR_UNSUPPORTED; }
@@ -1192,7 +1435,7 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         if (c.wn_cin > START_MAX_CIN) return fail("start conv: more than 16 input channels", MBEXWN_ERR_UNSUPPORTED);
         const size_t smem = ((size_t)(c.wn_cin + 1) * cpad + (size_t)START_ROWS * c.wn_cin) * sizeof(float);
         start_pack_kernel<<<(unsigned)((rows + START_ROWS - 1) / START_ROWS), 256, smem, s>>>(
-            wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g);
+            wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g, f8 ? 1 : 0, h_lo, h_hi);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(std::string("start conv: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
         *launches += 1;
@@ -1208,9 +1451,14 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
     int cond_rows = (TILE_M + c.wn_cond_lin_up - 2) / c.wn_cond_lin_up + 2;
     if (cond_rows > COND_ROWS - 1 || st.cond_stage == 0) cond_rows = 0;      // does not fit the smem stage: read from global
 
-    CUtensorMap tm_h, tm_a;
+    CUtensorMap tm_h, tm_a, tm_h8{}, tm_a8{};
     if ((rc = make_map(im, &tm_h, h2, rows, 2 * cpad, TILE_M, error))) return rc;
     if ((rc = make_map(im, &tm_a, a2, rows, 2 * cpad, TILE_M, error))) return rc;
+    if (f8) {
+        if ((rc = make_map8(im, &tm_h8, h2, rows, 4LL * cpad, TILE_M, error))) return rc;
+        if ((rc = make_map8(im, &tm_a8, a2, rows, 4LL * cpad, TILE_M, error))) return rc;
+    }
+    const std::string tc = f8 ? "/tc8/" : "/tc/";
 
     for (int i = 0; i < c.wn_layers; ++i) {
         const std::string li = std::to_string(i);
@@ -1218,9 +1466,9 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         const int d = c.wn_dilations[i];
         const int n1 = 2 * cpad, k1 = 2 * c.wn_k * cpad;                 // W1 packed: (n1, [hi | lo] x k x cpad)
         const int n2 = (last ? 0 : cpad) + out_pad, k2 = 2 * cpad;       // R packed: (n2, [hi | lo] x cpad)
-        const void* w1 = tensor(n + "/tc/W1_" + li, (size_t)n1 * k1 * 2);
+        const void* w1 = tensor(n + tc + "W1_" + li, (size_t)n1 * k1 * 2);
         const float* b1 = (const float*)tensor(n + "/tc/b1_" + li, (size_t)n1 * 4);
-        const void* w2 = tensor(n + "/tc/R_" + li, (size_t)n2 * k2 * 2);
+        const void* w2 = tensor(n + tc + "R_" + li, (size_t)n2 * k2 * 2);
         const float* b2 = (const float*)tensor(n + "/tc/rb_" + li, (size_t)n2 * 4);
         if (!w1 || !b1 || !w2 || !b2) return fail("packed tensor-core weights missing for layer " + li, MBEXWN_ERR_MISSING);
 
@@ -1231,6 +1479,12 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         for (int t = 0; t < c.wn_k; ++t) shifts[t] = (t - (c.wn_k - 1) / 2) * d;
         p1.n_kb = build_kblocks(p1.kb, c.wn_k, shifts, cpad);
         p1.n_terms = n_terms; p1.a_lo_off = cpad; p1.b_lo_off = c.wn_k * cpad;
+        if (f8) {
+            p1.tm_a8 = tm_h8;
+            if ((rc = make_map8(im, &p1.tm_b8, w1, n1, 2LL * k1, TILE_N, error))) return rc;
+            p1.f16 = 1; p1.a8_lo_off = 2 * cpad; p1.a8_hi_off = 3 * cpad; p1.b8_hi_off = k1; p1.b8_lo_off = k1 + k1 / 2;
+            p1.out_f16f8 = 1; p1.out_lo_scale = a_lo; p1.out_hi_scale = a_hi;
+        }
         p1.rows = rows; p1.n_cols = n1; p1.bias = b1; p1.cond = cond; p1.act = a2; p1.ld_act = 2 * cpad;
         p1.c = c.wn_c; p1.cpad = cpad; p1.lin_up = c.wn_cond_lin_up; p1.gate = c.wn_gate; p1.write_lo = n_terms == 3;
         p1.steps_per_frame = c.steps_per_frame; p1.grid = g;
@@ -1245,6 +1499,12 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         int zero = 0;
         p2.n_kb = build_kblocks(p2.kb, 1, &zero, cpad);
         p2.n_terms = n_terms; p2.a_lo_off = cpad; p2.b_lo_off = cpad;
+        if (f8) {
+            p2.tm_a8 = tm_a8;
+            if ((rc = make_map8(im, &p2.tm_b8, w2, n2, 2LL * k2, TILE_N, error))) return rc;
+            p2.f16 = 1; p2.a8_lo_off = 2 * cpad; p2.a8_hi_off = 3 * cpad; p2.b8_hi_off = k2; p2.b8_lo_off = k2 + k2 / 2;
+            p2.out_f16f8 = 1; p2.out_lo_scale = h_lo; p2.out_hi_scale = h_hi; p2.in_lo_inv = 1.f / h_lo;
+        }
         p2.rows = rows; p2.n_cols = n2; p2.bias = b2; p2.h = h2; p2.ld_h = 2 * cpad;
         p2.skip = wn_out; p2.skip_ld = out_pad; p2.skip_c = out_pad;
         p2.c = c.wn_c; p2.cpad = cpad; p2.res_cols = last ? 0 : cpad; p2.first = i == 0;
@@ -1317,6 +1577,30 @@ int wn_tc_gemm_test(WnTcState& st, const void* a_bf16, long long rows, int a_col
     p.n_terms = 1;
     if ((rc = make_map(im, &p.tm_a, a_bf16, rows, a_cols, TILE_M, error))) return rc;
     if ((rc = make_map(im, &p.tm_b, b_bf16, n, b_cols, TILE_N, error))) return rc;
+    for (int i = 0; i < n_kb; ++i) p.kb[i] = KBlock{kblocks[3 * i], kblocks[3 * i + 1], kblocks[3 * i + 2]};
+    p.n_kb = n_kb; p.rows = rows; p.n_cols = n; p.out_f32 = out; p.bias = nullptr;
+    cudaError_t e = launch_gemm<EPI_PLAIN>(im, p, s);
+    if (e != cudaSuccess) { if (error) *error = cudaGetErrorString(e); return MBEXWN_ERR_CUDA; }
+    return MBEXWN_OK;
+}
+
+// Stand-alone split-precision tap-GEMM (unit tests): A (rows, 4 * a_cpad bytes) = [fp16 (a_cpad) | e4m3 lo8 (a_cpad) | e4m3 hi8
+// (a_cpad)], B (n, 4 * b_k bytes) = [fp16 (b_k) | e4m3 hi8 (b_k) | e4m3 lo8 (b_k)];
+// out = sum_kb A16 @ B16^T + 2^-15 sum_kb (A_lo8 @ B_hi8^T + A_hi8 @ B_lo8^T)
+int wn_tc_gemm_test_f16f8(WnTcState& st, const void* a, long long rows, int a_cpad, const void* b, int n, int b_k,
+                          const int* kblocks, int n_kb, float* out, cudaStream_t s, std::string* error) {
+    int rc = ensure_impl(st, error);
+    if (rc) return rc;
+    Impl* im = reinterpret_cast<Impl*>(st.impl);
+    if (n_kb < 1 || n_kb > MAX_KB) return MBEXWN_ERR_INVALID;
+    im->cta_group = st.cta_group == 2 ? 2 : 1;
+    GemmParams p{};
+    p.n_terms = 2; p.f16 = 1;
+    if ((rc = make_map(im, &p.tm_a, a, rows, 2 * a_cpad, TILE_M, error))) return rc;
+    if ((rc = make_map(im, &p.tm_b, b, n, 2 * b_k, TILE_N, error))) return rc;
+    if ((rc = make_map8(im, &p.tm_a8, a, rows, 4LL * a_cpad, TILE_M, error))) return rc;
+    if ((rc = make_map8(im, &p.tm_b8, b, n, 4LL * b_k, TILE_N, error))) return rc;
+    p.a8_lo_off = 2 * a_cpad; p.a8_hi_off = 3 * a_cpad; p.b8_hi_off = 2 * b_k; p.b8_lo_off = 3 * b_k;
     for (int i = 0; i < n_kb; ++i) p.kb[i] = KBlock{kblocks[3 * i], kblocks[3 * i + 1], kblocks[3 * i + 2]};
     p.n_kb = n_kb; p.rows = rows; p.n_cols = n; p.out_f32 = out; p.bias = nullptr;
     cudaError_t e = launch_gemm<EPI_PLAIN>(im, p, s);

@@ -12,6 +12,9 @@ struct WnTcState {
     bool ready = false;
     int cta_group = 2;          // option "tc_cta_group": 1 = one CTA per tile, 2 = CTA pairs (cta_group::2)
     int cond_stage = 1;         // option "tc_cond_stage": gate epilogue reads its conditioning rows from a smem stage
+    // MBEXWN_PREC_F16F8: log2 scales of the e4m3 planes of the residual stream (h) and of the gated activations (a).
+    // The weight planes carry 2^(15 - sh_*): options "tc8_h_lo", "tc8_h_hi", "tc8_a_lo", "tc8_a_hi" (host packer must agree).
+    int sh_h_lo = 9, sh_h_hi = 2, sh_a_lo = 10, sh_a_hi = 4;
     void* impl = nullptr;
 };
 
@@ -61,6 +64,11 @@ int wn_tc_mirror(void* hilo, long long rows, int cpad, int rate, int pad_l, int 
 // A[rows + shift, a_col : a_col + 64] @ B[:, b_col : b_col + 64]^T, A (rows, a_cols) bf16, B (n, b_cols) bf16.
 int wn_tc_gemm_test(WnTcState& st, const void* a_bf16, long long rows, int a_cols, const void* b_bf16, int n, int b_cols,
                     const int* kblocks, int n_kb, float* out, cudaStream_t s, std::string* error);
+
+// Split-precision variant (MBEXWN_PREC_F16F8 operand format, see include/mbexwn.h): fp16 main product plus two e4m3
+// correction products scaled by 2^-15.
+int wn_tc_gemm_test_f16f8(WnTcState& st, const void* a, long long rows, int a_cpad, const void* b, int n, int b_k,
+                          const int* kblocks, int n_kb, float* out, cudaStream_t s, std::string* error);
 
 void wn_tc_invalidate(WnTcState& st);
 void wn_tc_destroy(WnTcState& st);

@@ -147,9 +147,15 @@ class Engine:
                     f"set_tensor({name})")
 
     def _upload_tc(self, weights: Dict[str, np.ndarray]):
-        from .tc_pack import pack_subnet_weights, pack_tc_weights
+        from .tc_pack import pack_subnet_weights, pack_tc8_weights, pack_tc_weights
         for name, t in pack_tc_weights(self.plan, weights).items():
             self._register_torch(name, t)
+        tc8, shifts = pack_tc8_weights(self.plan, weights)
+        for name, t in tc8.items():
+            self._register_torch(name, t)
+        for opt, v in shifts.items():
+            self.set_option(opt, v)
+        self.tc8_shifts = shifts
         for name, t in pack_subnet_weights(self.plan, weights).items():
             self._register_torch(name, t)
 
@@ -162,6 +168,18 @@ class Engine:
                                        b.shape[1], kb.ctypes.data, kb.shape[0], out.data_ptr(),
                                        torch.cuda.current_stream(self.device).cuda_stream)
         _cabi.check(self.lib, self._handle, rc, "mbexwn_k_tc_gemm")
+        return out
+
+    def tc_gemm_f16f8(self, a: torch.Tensor, b: torch.Tensor, kblocks: np.ndarray) -> torch.Tensor:
+        """Unit-test hook for the split-precision tap-GEMM: a (rows, 4 * a_cpad) uint8, b (n, 4 * b_k) uint8 rows in the
+        [fp16 | e4m3 | e4m3] plane layout of include/mbexwn.h."""
+        assert a.dtype == torch.uint8 and b.dtype == torch.uint8 and a.is_cuda and b.is_cuda
+        kb = np.ascontiguousarray(kblocks, dtype=np.int32)
+        out = torch.empty(a.shape[0], b.shape[0], dtype=torch.float32, device=self.device)
+        rc = self.lib.mbexwn_k_tc_gemm_f16f8(self._handle, a.data_ptr(), a.shape[0], a.shape[1] // 4, b.data_ptr(),
+                                             b.shape[0], b.shape[1] // 4, kb.ctypes.data, kb.shape[0], out.data_ptr(),
+                                             torch.cuda.current_stream(self.device).cuda_stream)
+        _cabi.check(self.lib, self._handle, rc, "mbexwn_k_tc_gemm_f16f8")
         return out
 
     def set_option(self, name: str, value: int):

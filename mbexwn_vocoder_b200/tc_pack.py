@@ -44,12 +44,21 @@ def gate_permutation(c: int, cpad: int):
 
 
 def pack_tc_weights(plan: ModelPlan, weights: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
+    """bf16 [hi | lo] planes of the packed matrices, fp32 biases."""
+    out: Dict[str, torch.Tensor] = {}
+    for key, m in _tc_matrices(plan, weights).items():
+        out[key] = hilo(m) if m.ndim == 2 else torch.from_numpy(m)
+    return out
+
+
+def _tc_matrices(plan: ModelPlan, weights: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """fp32 GEMM operands of the tensor-core path: W1_i (2 cpad, k cpad), R_i (n2, cpad) and the biases b1_i, rb_i."""
     wn = plan.wavenet
     C, k = wn.c, wn.k
     cpad = -(-C // TILE_K) * TILE_K
     name = wn.name + "_WNBlock_WN"
     col1, ok1 = gate_permutation(C, cpad)
-    out: Dict[str, torch.Tensor] = {}
+    out: Dict[str, np.ndarray] = {}
     we, be = W.folded(weights, f"{name}/end")                         # (1, C, c_out), (c_out,)
     we64 = we[0].astype(np.float64)
     c_out = we64.shape[1]
@@ -62,8 +71,8 @@ def pack_tc_weights(plan: ModelPlan, weights: Dict[str, np.ndarray]) -> Dict[str
         w1[ok1, :, :C] = np.transpose(w[:, :, col1[ok1]], (2, 0, 1))
         b1 = np.zeros(2 * cpad, dtype=np.float32)
         b1[ok1] = b[col1[ok1]]
-        out[f"{name}/tc/W1_{i}"] = hilo(w1.reshape(2 * cpad, k * cpad))
-        out[f"{name}/tc/b1_{i}"] = torch.from_numpy(b1)
+        out[f"{name}/tc/W1_{i}"] = w1.reshape(2 * cpad, k * cpad)
+        out[f"{name}/tc/b1_{i}"] = b1
         r, rb = W.folded(weights, f"{name}/res_skip_{i}")             # (1, C, 2C) or (1, C, C) for the last layer
         last = i == wn.n_layers - 1
         r64 = r[0].astype(np.float64)
@@ -77,14 +86,62 @@ def pack_tc_weights(plan: ModelPlan, weights: Dict[str, np.ndarray]) -> Dict[str
             rb2[:C] = rb[:C]
         r2[n_res:n_res + c_out, :C] = (r_skip @ we64).T.astype(np.float32)
         skip_bias += (rb if last else rb[C:]).astype(np.float64)
-        out[f"{name}/tc/R_{i}"] = hilo(r2)
+        out[f"{name}/tc/R_{i}"] = r2
         rbs.append((f"{name}/tc/rb_{i}", rb2, n_res))
     # wn_out = sum_i act_i @ (Rskip_i @ We) + (sum_i bskip_i) @ We + be: the constant term rides on layer 0 (assign)
     key0, rb0, n_res0 = rbs[0]
     rb0[n_res0:n_res0 + c_out] = (skip_bias @ we64 + be.astype(np.float64)).astype(np.float32)
     for key, rb2, _ in rbs:
-        out[key] = torch.from_numpy(rb2)
+        out[key] = rb2
     return out
+
+
+# ---- MBEXWN_PREC_F16F8: fp16 main product + two e4m3 correction products ---------------------------------------
+# x * w ~ f16(x) f16(w) + 2^-15 [ e4m3((x - f16 x) 2^sa) e4m3(w 2^(15 - sa)) + e4m3(x 2^sa') e4m3((w - f16 w) 2^(15 - sa')) ]
+# The tensor cores rescale the accumulated correction products by 2^-15 (scale-input-d of the first fp16 MMA of a tile), so
+# for every GEMM the plane scales of the two operands must multiply to 2^15.  Activation-side shifts (kernel options
+# tc8_h_lo / tc8_h_hi for the residual stream, tc8_a_lo / tc8_a_hi for the gated activations in (-1, 1)):
+CORR_SHIFT = 15
+TC8_DEFAULT_SHIFTS = {"tc8_h_lo": 9, "tc8_h_hi": 2, "tc8_a_lo": 10, "tc8_a_hi": 4}
+E4M3_MAX = 448.0
+
+
+def f16f8_planes(x: np.ndarray, hi_shift: int, lo_shift: int) -> torch.Tensor:
+    """(n, K) fp32 -> (n, 4 K) uint8 rows [fp16 (K) | e4m3(x 2^hi_shift) (K) | e4m3((x - f16 x) 2^lo_shift) (K)]."""
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    h16 = t.to(torch.float16)
+    lo = t - h16.to(torch.float32)
+    hi8 = torch.clamp(t * 2.0 ** hi_shift, -E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn)
+    lo8 = torch.clamp(lo * 2.0 ** lo_shift, -E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn)
+    return torch.cat((h16.view(torch.uint8), hi8.view(torch.uint8), lo8.view(torch.uint8)), dim=1).contiguous()
+
+
+def choose_tc8_shifts(w1_max: float, r_max: float) -> Dict[str, int]:
+    """Activation-plane shifts; the weight hi8 plane 2^(15 - *_lo) must not saturate e4m3 for the largest weight."""
+    out = dict(TC8_DEFAULT_SHIFTS)
+    for key, wmax in (("tc8_h_lo", w1_max), ("tc8_a_lo", r_max)):
+        room = int(np.floor(np.log2(E4M3_MAX / max(wmax, 1e-30))))          # largest weight-side shift without saturation
+        out[key] = max(out[key], CORR_SHIFT - room)
+    return out
+
+
+def pack_tc8_weights(plan: ModelPlan, weights: Dict[str, np.ndarray], packed: Dict[str, torch.Tensor] = None):
+    """The matrices of pack_tc_weights (same row order / folding, fp32 before the split) as [fp16 | e4m3 | e4m3] planes.
+
+    Returns ({name: uint8 tensor}, shifts)."""
+    wn = plan.wavenet
+    name = wn.name + "_WNBlock_WN"
+    mats = _tc_matrices(plan, weights)
+    w1_max = max(float(np.abs(m).max()) for k, m in mats.items() if "/W1_" in k)
+    r_max = max(float(np.abs(m).max()) for k, m in mats.items() if "/R_" in k)
+    sh = choose_tc8_shifts(w1_max, r_max)
+    out: Dict[str, torch.Tensor] = {}
+    for key, m in mats.items():
+        if "/W1_" in key:
+            out[key.replace("/tc/", "/tc8/")] = f16f8_planes(m, CORR_SHIFT - sh["tc8_h_lo"], CORR_SHIFT - sh["tc8_h_hi"])
+        elif "/R_" in key:
+            out[key.replace("/tc/", "/tc8/")] = f16f8_planes(m, CORR_SHIFT - sh["tc8_a_lo"], CORR_SHIFT - sh["tc8_a_hi"])
+    return out, sh
 
 
 def pack_conv_tc(w: np.ndarray) -> torch.Tensor:

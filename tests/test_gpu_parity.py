@@ -101,7 +101,7 @@ def test_cuda_matches_committed_goldens(engine, speech_setup):
     import os
     hp, plan, w = speech_setup
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_speech_T16.npz"))
-    for precision in ("fp32", "bf16x3"):
+    for precision in ("fp32", "bf16x3", "f16f8"):
         out, tp = engine.forward([g["mel"]], noise=[g["noise"]], f0=[g["F0"]], precision=precision,
                                  taps=["phase", "index", "pulse", "subbands", "excitation", "ceps"])
         assert np.array_equal(tp["index"][0], g["index"]) and np.array_equal(tp["phase"][0], g["phase"])

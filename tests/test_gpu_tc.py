@@ -67,13 +67,52 @@ def test_tap_gemm_random(engine, cg):
     assert np.abs(out - ref).max() <= 2e-5 * np.abs(ref).max()
 
 
+def _pack_f16f8(x16, lo8, hi8):
+    """rows of [fp16 | e4m3 | e4m3] planes as a uint8 matrix (the MBEXWN_PREC_F16F8 operand layout)."""
+    return torch.cat((x16.to(torch.float16).view(torch.uint8), lo8.to(torch.float8_e4m3fn).view(torch.uint8),
+                      hi8.to(torch.float8_e4m3fn).view(torch.uint8)), dim=1).contiguous()
+
+
+def _ref_gemm_planes(a, b, kblocks):
+    rows = a.shape[0]
+    out = np.zeros((rows, b.shape[0]))
+    a, b = a.double().numpy(), b.double().numpy()
+    for a_col, shift, b_col in kblocks:
+        blk = np.zeros((rows, 64))
+        lo, hi = max(0, -shift), min(rows, rows - shift)
+        blk[lo:hi] = a[lo + shift:hi + shift, a_col:a_col + 64]
+        out += blk @ b[:, b_col:b_col + 64].T
+    return out
+
+
+@pytest.mark.parametrize("rows,n,kblocks", [
+    (128, 128, [(0, 0, 0)]),
+    (300, 256, [(0, 0, 0), (64, 0, 64), (0, -3, 128), (64, 5, 192)]),
+    (200, 32, [(0, 0, 0), (64, 1, 64)]),
+    (513, 240, [(0, -1, 0), (0, 0, 64), (0, 1, 128)]),
+    (1000, 320, [(64 * i, s, 64 * (3 * i + j)) for i in range(3) for j, s in enumerate((-8, 0, 8))]),
+])
+def test_tap_gemm_f16f8_exact(engine, cg, rows, n, kblocks):
+    """fp16 main product + 2^-15 (lo8 x hi8 + hi8 x lo8) with small integers: every partial sum is exact in fp32."""
+    g = torch.Generator(device="cpu").manual_seed(rows * 3 + n)
+    a_cpad = max(k[0] for k in kblocks) + 64
+    b_k = max(k[2] for k in kblocks) + 64
+    amp = 4 if len(kblocks) <= 4 else 2          # keep every partial sum below 2^9 (15 fractional bits + 9 = fp32's 24)
+    ri = lambda *shape: torch.randint(-amp, amp + 1, shape, generator=g).float()
+    a16, alo, ahi = ri(rows, a_cpad), ri(rows, a_cpad), ri(rows, a_cpad)
+    b16, bhi, blo = ri(n, b_k), ri(n, b_k), ri(n, b_k)
+    out = engine.tc_gemm_f16f8(_pack_f16f8(a16, alo, ahi).cuda(), _pack_f16f8(b16, bhi, blo).cuda(), np.array(kblocks)).cpu().numpy()
+    ref = _ref_gemm_planes(a16, b16, kblocks) + 2.0 ** -15 * (_ref_gemm_planes(alo, bhi, kblocks) + _ref_gemm_planes(ahi, blo, kblocks))
+    assert np.array_equal(out, ref.astype(np.float32))
+
+
 def _snr_db(ref, test):
     ref = np.asarray(ref, dtype=np.float64)
     err = np.asarray(test, dtype=np.float64) - ref
     return 10 * np.log10(np.sum(ref ** 2) / max(np.sum(err ** 2), 1e-300))
 
 
-@pytest.mark.parametrize("precision,tol,snr", [("bf16x3", 1e-4, 60.0), ("bf16", 5e-2, 35.0)])
+@pytest.mark.parametrize("precision,tol,snr", [("bf16x3", 1e-4, 60.0), ("f16f8", 1e-4, 60.0), ("bf16", 5e-2, 35.0)])
 def test_wavenet_tc_parity(engine, cg, speech_setup, precision, tol, snr):
     hp, plan, w = speech_setup
     oracle = OracleMBExWN(hp, w, torch.float32)
@@ -136,7 +175,7 @@ def test_wavenet_tc_parity_c340():
         n = t * plan.pulse_per_frame
         x = np.linspace(0, 1, n)
         f0.append((45.0 * (1400.0 / 45.0) ** x * (1 + 0.03 * np.sin(2 * np.pi * 5.5 * np.arange(n) / 8000.0))).astype(np.float32))
-    for precision, tol, snr in (("bf16x3", 1e-4, 60.0), ("fp32", 1e-4, 60.0)):
+    for precision, tol, snr in (("bf16x3", 1e-4, 60.0), ("f16f8", 1e-4, 60.0), ("fp32", 1e-4, 60.0)):
         out, tp = eng.forward(mels, noise=noise, f0=f0, precision=precision, taps=["index", "phase", "pulse", "wn_out"])
         for u in range(len(lengths)):
             ref = oracle.forward(mels[u][None], noise[u][None], f0_override=f0[u][None])
