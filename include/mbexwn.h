@@ -188,7 +188,8 @@ MBEXWN_API int mbexwn_k_tc_gemm(mbexwn_handle_t h, const void* a_bf16, int64_t r
                                 void* cuda_stream);
 
 /* The split-precision tap-GEMM of MBEXWN_PREC_F16F8 on its own.  A (rows, 4 * a_cpad bytes per row) = [fp16 x (a_cpad) |
- * e4m3 lo8 (a_cpad) | e4m3 hi8 (a_cpad)], B (n, 4 * b_k bytes per row) = [fp16 w (b_k) | e4m3 hi8 (b_k) | e4m3 lo8 (b_k)];
+ * for every 64 channels: e4m3 lo8 (64 B), e4m3 hi8 (64 B)], B (n, 4 * b_k bytes per row) = [fp16 w (b_k) | for every 64 of K:
+ * e4m3 hi8 (64 B), e4m3 lo8 (64 B)] -- the two correction products of a K block are one 128-byte e4m3 block;
  * out = sum_b A16 @ B16^T + 2^-15 * sum_b (A_lo8 @ B_hi8^T + A_hi8 @ B_lo8^T) over the same K-block list as above. */
 MBEXWN_API int mbexwn_k_tc_gemm_f16f8(mbexwn_handle_t h, const void* a, int64_t rows, int32_t a_cpad, const void* b,
                                       int32_t n, int32_t b_k, const int32_t* kblocks, int32_t n_kb, float* out,

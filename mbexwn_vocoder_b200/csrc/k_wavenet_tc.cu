@@ -78,15 +78,14 @@ struct KBlock {
 struct alignas(64) GemmParams {
     CUtensorMap tm_a;
     CUtensorMap tm_b;
-    CUtensorMap tm_a8;      // n_terms == 2: byte view of the A rows (e4m3 planes), 64-byte boxes, SWIZZLE_64B
-    CUtensorMap tm_b8;
     KBlock kb[MAX_KB];
     int n_kb;
     int n_terms;            // 1: hi*hi;  3: hi*hi + lo*hi + hi*lo, the lo planes sit a_lo_off / b_lo_off columns further;
-                            // 2: fp16 hi*hi + 2^-15 (e4m3 lo8*hi8 + e4m3 hi8*lo8) (MBEXWN_PREC_F16F8)
+                            // 2: fp16 hi*hi + 2^-15 (e4m3 lo8*hi8 + e4m3 hi8*lo8) (MBEXWN_PREC_F16F8): the "lo plane" of a
+                            //    64-channel K block is 128 bytes of e4m3, A = [lo8 (64) | hi8 (64)], B = [hi8 (64) | lo8 (64)],
+                            //    so both correction products are one K = 128 e4m3 block
     int a_lo_off, b_lo_off;
     int f16;                // main product operands are fp16 (else bf16)
-    int a8_lo_off, a8_hi_off, b8_hi_off, b8_lo_off;     // byte columns of the e4m3 planes in the A / B rows
     // scales of the e4m3 planes the epilogues write: x_lo8 = e4m3((x - fp16(x)) * lo_scale), x_hi8 = e4m3(x * hi_scale)
     int out_f16f8;
     float out_lo_scale, out_hi_scale, in_lo_inv;
@@ -181,7 +180,9 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (.release at CTA scope): the accumulator reads were already ordered by tcgen05.wait::ld +
+    // tcgen05.fence::before_thread_sync; a .release.cluster arrive costs MEMBAR.ALL.GPU + ERRBAR per tile and warp
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -305,6 +306,9 @@ __device__ __forceinline__ void split_f16f8(const float (&a)[8], float lo_scale,
     lo8 = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
     hi8 = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
 }
+
+// byte offset of the e4m3 lo8 group of channel ch (a multiple of 8) inside a row of 4 * cpad bytes; hi8 sits 64 bytes further
+__device__ __forceinline__ int f8_off(int cpad, int ch) { return 2 * cpad + ((ch >> 6) << 7) + (ch & 63); }
 
 // the value a (fp16, e4m3 lo8) pair stands for: 8 channels
 __device__ __forceinline__ void join_f16f8(const uint4& h16, const uint2& lo8, float lo_inv, float (&x)[8]) {
@@ -444,7 +448,7 @@ __device__ __forceinline__ void epi_gate(const GemmParams& p, uint32_t tacc, lon
         if (row >= p.rows) continue;
         const int ch0 = ch_tile + q * 32;
         __nv_bfloat16* dst = p.act + row * p.ld_act + ch0;
-        uint8_t* dst8 = reinterpret_cast<uint8_t*>(p.act + row * p.ld_act) + 2 * p.cpad + ch0;      // e4m3 lo8 plane; hi8 is cpad further
+        uint8_t* row8 = reinterpret_cast<uint8_t*>(p.act + row * p.ld_act);
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
             float a[8];
@@ -489,10 +493,10 @@ __device__ __forceinline__ void epi_gate(const GemmParams& p, uint32_t tacc, lon
                 uint4 h16;
                 uint2 l8, h8;
                 split_f16f8(a, p.out_lo_scale, p.out_hi_scale, h16, l8, h8);
-                uint8_t* d8 = dst8 + i;
+                uint8_t* d8 = row8 + f8_off(p.cpad, ch0 + i);
                 *reinterpret_cast<uint4*>(dst + i) = h16;
                 *reinterpret_cast<uint2*>(d8) = l8;
-                *reinterpret_cast<uint2*>(d8 + p.cpad) = h8;
+                *reinterpret_cast<uint2*>(d8 + 64) = h8;
                 continue;
             }
             uint32_t hw4[4], lw4[4];
@@ -583,7 +587,8 @@ __device__ __forceinline__ void epi_gate_staged(const GemmParams& p, const float
         tmem_ld_wait();
         if (row >= p.rows) continue;
         __nv_bfloat16* dst = p.act + row * p.ld_act + ch_tile + q * 32;
-        uint8_t* dst8 = reinterpret_cast<uint8_t*>(p.act + row * p.ld_act) + 2 * p.cpad + ch_tile + q * 32;    // e4m3 lo8 plane; hi8 is cpad further
+        uint8_t* row8 = reinterpret_cast<uint8_t*>(p.act + row * p.ld_act);
+        const int ch0 = ch_tile + q * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
             float a[8];
@@ -619,10 +624,10 @@ __device__ __forceinline__ void epi_gate_staged(const GemmParams& p, const float
                 uint4 h16;
                 uint2 l8, h8;
                 split_f16f8(a, p.out_lo_scale, p.out_hi_scale, h16, l8, h8);
-                uint8_t* d8 = dst8 + i;
+                uint8_t* d8 = row8 + f8_off(p.cpad, ch0 + i);
                 *reinterpret_cast<uint4*>(dst + i) = h16;
                 *reinterpret_cast<uint2*>(d8) = l8;
-                *reinterpret_cast<uint2*>(d8 + p.cpad) = h8;
+                *reinterpret_cast<uint2*>(d8 + 64) = h8;
                 continue;
             }
             uint32_t hw4[4], lw4[4];
@@ -670,7 +675,7 @@ __device__ __forceinline__ void resskip_load_old(const GemmParams& p, const ResS
                 const __nv_bfloat16* ph = p.h + (c.row0 + r) * p.ld_h + n + cg * 8;
                 old[ps] = *reinterpret_cast<const uint4*>(ph);
                 if (p.out_f16f8) {
-                    const uint2 l8 = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(p.h + (c.row0 + r) * p.ld_h) + 2 * p.cpad + n + cg * 8);
+                    const uint2 l8 = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(p.h + (c.row0 + r) * p.ld_h) + f8_off(p.cpad, n + cg * 8));
                     old[4 + ps] = make_uint4(l8.x, l8.y, 0u, 0u);
                 } else {
                     old[4 + ps] = *reinterpret_cast<const uint4*>(ph + p.cpad);
@@ -715,10 +720,10 @@ __device__ __forceinline__ void resskip_store(const GemmParams& p, const ResSkip
                 uint2 l8, h8;
                 split_f16f8(o, p.out_lo_scale, p.out_hi_scale, h16, l8, h8);
                 __nv_bfloat16* prow = p.h + (c.row0 + r) * p.ld_h;
-                uint8_t* p8 = reinterpret_cast<uint8_t*>(prow) + 2 * p.cpad + ch0;
+                uint8_t* p8 = reinterpret_cast<uint8_t*>(prow) + f8_off(p.cpad, ch0);
                 *reinterpret_cast<uint4*>(prow + ch0) = h16;
                 *reinterpret_cast<uint2*>(p8) = l8;
-                *reinterpret_cast<uint2*>(p8 + p.cpad) = h8;
+                *reinterpret_cast<uint2*>(p8 + 64) = h8;
                 continue;
             }
             uint32_t hw[4] = {old[ps].x, old[ps].y, old[ps].z, old[ps].w};
@@ -814,10 +819,10 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     // K-major SWIZZLE_128B smem matrix descriptor without the address field: LBO = 1 (ignored), SBO = 1024 B between
     // 8-row groups, descriptor version 1 (Blackwell), swizzle mode 2 (128 B)
     constexpr uint64_t DESC_HI = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-    // the e4m3 tiles are 64 bytes wide: SWIZZLE_64B (layout type 4), 512 B between 8-row groups
-    constexpr uint64_t DESC8_HI = ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // align up inside the shared window with plain pointer arithmetic: a round trip through uintptr_t makes ptxas treat
+    // every later access as generic (LD.E / ST.E instead of LDS / STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* ring_a = smem;
     uint8_t* ring_b = smem + NA * A_BYTES;
     uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
@@ -857,10 +862,6 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     if (warp == 0 && elect_one()) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_b) : "memory");
-        if (p.n_terms == 2) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_a8) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_b8) : "memory");
-        }
     }
     if (warp == 1 && elect_one()) {
         // full barriers: one arrival (the leader's expect_tx for the bytes of *all* CTAs of the group); a peer CTA's
@@ -897,25 +898,21 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
             width = width > TILE_N ? TILE_N : ((width + 15) & ~15);
             const int nb0 = n_blk * TILE_N + (int)rank * (width / CG);      // this CTA's share of the B rows
             if (p.n_terms == 2) {
-                // e4m3 correction planes first (their products are rescaled by the first fp16 MMA of the tile): one A slot
-                // holds the [lo8 | hi8] tiles of a K block (2 x 128 rows x 64 B), one B slot the [hi8 | lo8] weight tiles
+                // e4m3 correction blocks first (their products are rescaled by the first fp16 MMA of the tile)
                 for (int kb = 0; kb < p.n_kb; ++kb) {
-                    const int a_col = p.kb[kb].a_col, a_row = m0 + p.kb[kb].a_shift, b_col = p.kb[kb].b_col;
+                    const int a_col = p.kb[kb].a_col + p.a_lo_off, a_row = m0 + p.kb[kb].a_shift, b_col = p.kb[kb].b_col + p.b_lo_off;
                     {
                         const uint32_t s = ia % NA, ph = (ia / NA) & 1;
                         ++ia;
                         mbar_wait(&empty_a[s], ph ^ 1);
                         if (elect_one()) {
-                            uint8_t* dst = ring_a + s * A_BYTES;
                             if (CG == 1) {
                                 mbar_expect_tx(&full_a[s], A_BYTES);
-                                tma_load_2d(&p.tm_a8, &full_a[s], dst, p.a8_lo_off + a_col, a_row);
-                                tma_load_2d(&p.tm_a8, &full_a[s], dst + A_BYTES / 2, p.a8_hi_off + a_col, a_row);
+                                tma_load_2d(&p.tm_a, &full_a[s], ring_a + s * A_BYTES, a_col, a_row);
                             } else {
                                 const uint32_t lbar = map_to_cta(smem_u32(&full_a[s]), 0);
                                 if (leader) mbar_expect_tx(&full_a[s], CG * A_BYTES);
-                                tma_load_2d_2sm(&p.tm_a8, lbar, dst, p.a8_lo_off + a_col, a_row);
-                                tma_load_2d_2sm(&p.tm_a8, lbar, dst + A_BYTES / 2, p.a8_hi_off + a_col, a_row);
+                                tma_load_2d_2sm(&p.tm_a, lbar, ring_a + s * A_BYTES, a_col, a_row);
                             }
                         }
                         __syncwarp();
@@ -925,16 +922,13 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                         ++ib;
                         mbar_wait(&empty_b[s], ph ^ 1);
                         if (elect_one()) {
-                            uint8_t* dst = ring_b + s * B_BYTES;
                             if (CG == 1) {
                                 mbar_expect_tx(&full_b[s], B_BYTES);
-                                tma_load_2d(&p.tm_b8, &full_b[s], dst, p.b8_hi_off + b_col, nb0);
-                                tma_load_2d(&p.tm_b8, &full_b[s], dst + B_BYTES / 2, p.b8_lo_off + b_col, nb0);
+                                tma_load_2d(&p.tm_b, &full_b[s], ring_b + s * B_BYTES, b_col, nb0);
                             } else {
                                 const uint32_t lbar = map_to_cta(smem_u32(&full_b[s]), 0);
                                 if (leader) mbar_expect_tx(&full_b[s], CG * B_BYTES);
-                                tma_load_2d_2sm(&p.tm_b8, lbar, dst, p.b8_hi_off + b_col, nb0);
-                                tma_load_2d_2sm(&p.tm_b8, lbar, dst + B_BYTES / 2, p.b8_lo_off + b_col, nb0);
+                                tma_load_2d_2sm(&p.tm_b, lbar, ring_b + s * B_BYTES, b_col, nb0);
                             }
                         }
                         __syncwarp();
@@ -1000,19 +994,14 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                     else tc_mma_bf16_2sm(tacc, da + 2 * k, db + 2 * k, idesc, !(first == 1 && k == 0));
                 }
             };
-            // e4m3 products of one K block: lo8 (A) x hi8 (B), then hi8 (A) x lo8 (B); 64 channels = 2 instructions of K = 32
-            // each (32 B along K inside the 64 B swizzle row: +2 in 16-byte units)
+            // e4m3 products of one K block: [lo8 | hi8] (A) x [hi8 | lo8] (B) = 128 bytes along K = 4 instructions of K = 32
             auto mma8 = [&](uint32_t tacc, uint32_t sa, uint32_t sb, uint32_t idesc, bool first) {
-                const uint64_t da = DESC8_HI | (uint64_t)(a_base + sa * (A_BYTES >> 4));
-                const uint64_t db = DESC8_HI | (uint64_t)(b_base + sb * (B_BYTES >> 4));
+                const uint64_t da = DESC_HI | (uint64_t)(a_base + sa * (A_BYTES >> 4));
+                const uint64_t db = DESC_HI | (uint64_t)(b_base + sb * (B_BYTES >> 4));
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const uint64_t xa = da + (t ? (A_BYTES >> 5) : 0), xb = db + (t ? (B_BYTES >> 5) : 0);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        if (CG == 1) tc_mma_f8(tacc, xa + 2 * k, xb + 2 * k, idesc, !(first && t == 0 && k == 0));
-                        else tc_mma_f8_2sm(tacc, xa + 2 * k, xb + 2 * k, idesc, !(first && t == 0 && k == 0));
-                    }
+                for (int k = 0; k < 4; ++k) {
+                    if (CG == 1) tc_mma_f8(tacc, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                    else tc_mma_f8_2sm(tacc, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
                 }
             };
             auto commit = [&](uint64_t* bar) { if (CG == 1) tc_commit(bar); else tc_commit_2sm(bar); };
@@ -1207,10 +1196,10 @@ __global__ void start_pack_kernel(const float* __restrict__ x, int cin, const fl
             uint4 h16;
             uint2 l8, h8;
             split_f16f8(v, lo_scale, hi_scale, h16, l8, h8);
-            uint8_t* p8 = reinterpret_cast<uint8_t*>(out + r * 2 * cpad) + 2 * cpad + ch0;
+            uint8_t* p8 = reinterpret_cast<uint8_t*>(out + r * 2 * cpad) + f8_off(cpad, ch0);
             *reinterpret_cast<uint4*>(out + r * 2 * cpad + ch0) = h16;
             *reinterpret_cast<uint2*>(p8) = l8;
-            *reinterpret_cast<uint2*>(p8 + cpad) = h8;
+            *reinterpret_cast<uint2*>(p8 + 64) = h8;
             continue;
         }
         uint32_t hw[4], lw[4];
@@ -1297,23 +1286,6 @@ int make_map(Impl* im, CUtensorMap* tm, const void* base, long long rows, long l
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         if (err) *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
-        return MBEXWN_ERR_CUDA;
-    }
-    return MBEXWN_OK;
-}
-
-// byte view of a row-major matrix (rows, row_bytes) for the e4m3 planes: 64-byte x box_rows boxes, SWIZZLE_64B
-int make_map8(Impl* im, CUtensorMap* tm, const void* base, long long rows, long long row_bytes, int box_rows, std::string* err) {
-    if (box_rows == TILE_N) box_rows = TILE_N / im->cta_group;
-    cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)TILE_K, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = im->encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        if (err) *err = "cuTensorMapEncodeTiled (e4m3 planes) failed with code " + std::to_string((int)r);
         return MBEXWN_ERR_CUDA;
     }
     return MBEXWN_OK;
@@ -1451,13 +1423,9 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
     int cond_rows = (TILE_M + c.wn_cond_lin_up - 2) / c.wn_cond_lin_up + 2;
     if (cond_rows > COND_ROWS - 1 || st.cond_stage == 0) cond_rows = 0;      // does not fit the smem stage: read from global
 
-    CUtensorMap tm_h, tm_a, tm_h8{}, tm_a8{};
+    CUtensorMap tm_h, tm_a;
     if ((rc = make_map(im, &tm_h, h2, rows, 2 * cpad, TILE_M, error))) return rc;
     if ((rc = make_map(im, &tm_a, a2, rows, 2 * cpad, TILE_M, error))) return rc;
-    if (f8) {
-        if ((rc = make_map8(im, &tm_h8, h2, rows, 4LL * cpad, TILE_M, error))) return rc;
-        if ((rc = make_map8(im, &tm_a8, a2, rows, 4LL * cpad, TILE_M, error))) return rc;
-    }
     const std::string tc = f8 ? "/tc8/" : "/tc/";
 
     for (int i = 0; i < c.wn_layers; ++i) {
@@ -1479,12 +1447,7 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         for (int t = 0; t < c.wn_k; ++t) shifts[t] = (t - (c.wn_k - 1) / 2) * d;
         p1.n_kb = build_kblocks(p1.kb, c.wn_k, shifts, cpad);
         p1.n_terms = n_terms; p1.a_lo_off = cpad; p1.b_lo_off = c.wn_k * cpad;
-        if (f8) {
-            p1.tm_a8 = tm_h8;
-            if ((rc = make_map8(im, &p1.tm_b8, w1, n1, 2LL * k1, TILE_N, error))) return rc;
-            p1.f16 = 1; p1.a8_lo_off = 2 * cpad; p1.a8_hi_off = 3 * cpad; p1.b8_hi_off = k1; p1.b8_lo_off = k1 + k1 / 2;
-            p1.out_f16f8 = 1; p1.out_lo_scale = a_lo; p1.out_hi_scale = a_hi;
-        }
+        if (f8) { p1.f16 = 1; p1.out_f16f8 = 1; p1.out_lo_scale = a_lo; p1.out_hi_scale = a_hi; }
         p1.rows = rows; p1.n_cols = n1; p1.bias = b1; p1.cond = cond; p1.act = a2; p1.ld_act = 2 * cpad;
         p1.c = c.wn_c; p1.cpad = cpad; p1.lin_up = c.wn_cond_lin_up; p1.gate = c.wn_gate; p1.write_lo = n_terms == 3;
         p1.steps_per_frame = c.steps_per_frame; p1.grid = g;
@@ -1499,12 +1462,7 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         int zero = 0;
         p2.n_kb = build_kblocks(p2.kb, 1, &zero, cpad);
         p2.n_terms = n_terms; p2.a_lo_off = cpad; p2.b_lo_off = cpad;
-        if (f8) {
-            p2.tm_a8 = tm_a8;
-            if ((rc = make_map8(im, &p2.tm_b8, w2, n2, 2LL * k2, TILE_N, error))) return rc;
-            p2.f16 = 1; p2.a8_lo_off = 2 * cpad; p2.a8_hi_off = 3 * cpad; p2.b8_hi_off = k2; p2.b8_lo_off = k2 + k2 / 2;
-            p2.out_f16f8 = 1; p2.out_lo_scale = h_lo; p2.out_hi_scale = h_hi; p2.in_lo_inv = 1.f / h_lo;
-        }
+        if (f8) { p2.f16 = 1; p2.out_f16f8 = 1; p2.out_lo_scale = h_lo; p2.out_hi_scale = h_hi; p2.in_lo_inv = 1.f / h_lo; }
         p2.rows = rows; p2.n_cols = n2; p2.bias = b2; p2.h = h2; p2.ld_h = 2 * cpad;
         p2.skip = wn_out; p2.skip_ld = out_pad; p2.skip_c = out_pad;
         p2.c = c.wn_c; p2.cpad = cpad; p2.res_cols = last ? 0 : cpad; p2.first = i == 0;
@@ -1584,8 +1542,8 @@ int wn_tc_gemm_test(WnTcState& st, const void* a_bf16, long long rows, int a_col
     return MBEXWN_OK;
 }
 
-// Stand-alone split-precision tap-GEMM (unit tests): A (rows, 4 * a_cpad bytes) = [fp16 (a_cpad) | e4m3 lo8 (a_cpad) | e4m3 hi8
-// (a_cpad)], B (n, 4 * b_k bytes) = [fp16 (b_k) | e4m3 hi8 (b_k) | e4m3 lo8 (b_k)];
+// Stand-alone split-precision tap-GEMM (unit tests): A (rows, 4 * a_cpad bytes) = [fp16 (a_cpad) | per 64 channels: e4m3 lo8
+// (64), e4m3 hi8 (64)], B (n, 4 * b_k bytes) = [fp16 (b_k) | per 64 of K: e4m3 hi8 (64), e4m3 lo8 (64)];
 // out = sum_kb A16 @ B16^T + 2^-15 sum_kb (A_lo8 @ B_hi8^T + A_hi8 @ B_lo8^T)
 int wn_tc_gemm_test_f16f8(WnTcState& st, const void* a, long long rows, int a_cpad, const void* b, int n, int b_k,
                           const int* kblocks, int n_kb, float* out, cudaStream_t s, std::string* error) {
@@ -1598,9 +1556,7 @@ int wn_tc_gemm_test_f16f8(WnTcState& st, const void* a, long long rows, int a_cp
     p.n_terms = 2; p.f16 = 1;
     if ((rc = make_map(im, &p.tm_a, a, rows, 2 * a_cpad, TILE_M, error))) return rc;
     if ((rc = make_map(im, &p.tm_b, b, n, 2 * b_k, TILE_N, error))) return rc;
-    if ((rc = make_map8(im, &p.tm_a8, a, rows, 4LL * a_cpad, TILE_M, error))) return rc;
-    if ((rc = make_map8(im, &p.tm_b8, b, n, 4LL * b_k, TILE_N, error))) return rc;
-    p.a8_lo_off = 2 * a_cpad; p.a8_hi_off = 3 * a_cpad; p.b8_hi_off = 2 * b_k; p.b8_lo_off = 3 * b_k;
+    p.a_lo_off = a_cpad; p.b_lo_off = b_k;
     for (int i = 0; i < n_kb; ++i) p.kb[i] = KBlock{kblocks[3 * i], kblocks[3 * i + 1], kblocks[3 * i + 2]};
     p.n_kb = n_kb; p.rows = rows; p.n_cols = n; p.out_f32 = out; p.bias = nullptr;
     cudaError_t e = launch_gemm<EPI_PLAIN>(im, p, s);

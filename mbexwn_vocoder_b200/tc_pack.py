@@ -107,13 +107,16 @@ E4M3_MAX = 448.0
 
 
 def f16f8_planes(x: np.ndarray, hi_shift: int, lo_shift: int) -> torch.Tensor:
-    """(n, K) fp32 -> (n, 4 K) uint8 rows [fp16 (K) | e4m3(x 2^hi_shift) (K) | e4m3((x - f16 x) 2^lo_shift) (K)]."""
+    """(n, K) fp32, K % 64 == 0 -> (n, 4 K) uint8 rows [fp16 (K) | per 64 of K: e4m3(x 2^hi_shift) (64), e4m3((x - f16 x)
+    2^lo_shift) (64)]: the weight side of the layout in include/mbexwn.h (activations store lo8 first)."""
     t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    n, k = t.shape
     h16 = t.to(torch.float16)
     lo = t - h16.to(torch.float32)
-    hi8 = torch.clamp(t * 2.0 ** hi_shift, -E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn)
-    lo8 = torch.clamp(lo * 2.0 ** lo_shift, -E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn)
-    return torch.cat((h16.view(torch.uint8), hi8.view(torch.uint8), lo8.view(torch.uint8)), dim=1).contiguous()
+    hi8 = torch.clamp(t * 2.0 ** hi_shift, -E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn).view(torch.uint8)
+    lo8 = torch.clamp(lo * 2.0 ** lo_shift, -E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn).view(torch.uint8)
+    f8 = torch.stack((hi8.reshape(n, k // TILE_K, TILE_K), lo8.reshape(n, k // TILE_K, TILE_K)), dim=2).reshape(n, 2 * k)
+    return torch.cat((h16.view(torch.uint8), f8), dim=1).contiguous()
 
 
 def choose_tc8_shifts(w1_max: float, r_max: float) -> Dict[str, int]:

@@ -67,10 +67,13 @@ def test_tap_gemm_random(engine, cg):
     assert np.abs(out - ref).max() <= 2e-5 * np.abs(ref).max()
 
 
-def _pack_f16f8(x16, lo8, hi8):
-    """rows of [fp16 | e4m3 | e4m3] planes as a uint8 matrix (the MBEXWN_PREC_F16F8 operand layout)."""
-    return torch.cat((x16.to(torch.float16).view(torch.uint8), lo8.to(torch.float8_e4m3fn).view(torch.uint8),
-                      hi8.to(torch.float8_e4m3fn).view(torch.uint8)), dim=1).contiguous()
+def _pack_f16f8(x16, first8, second8):
+    """rows of [fp16 | per 64 columns: e4m3 first8 (64), e4m3 second8 (64)] as a uint8 matrix (the MBEXWN_PREC_F16F8 operand
+    layout: activations store (lo8, hi8), weights (hi8, lo8))."""
+    n, k = x16.shape
+    a = first8.to(torch.float8_e4m3fn).view(torch.uint8).reshape(n, k // 64, 64)
+    b = second8.to(torch.float8_e4m3fn).view(torch.uint8).reshape(n, k // 64, 64)
+    return torch.cat((x16.to(torch.float16).view(torch.uint8), torch.stack((a, b), dim=2).reshape(n, 2 * k)), dim=1).contiguous()
 
 
 def _ref_gemm_planes(a, b, kblocks):
