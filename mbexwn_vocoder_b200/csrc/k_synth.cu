@@ -170,6 +170,249 @@ stft_filter_kernel(StftFilterArgs a, FrameGrid g) {
     for (int n = tid; n < a.win; n += blockDim.x) frame_out[n] = Bf[n].x * scale * a.inv_window[n];
 }
 
+// ---- register-resident 2048-point FFT -----------------------------------------------------------------------------
+// Stockham autosort, radices 16 x 16 x 8, 128 threads per frame: every thread holds 16 complex points in registers, the
+// three passes exchange data through one 17 KB shared buffer (pass 1 -> 2 with one pad element per 16 so that the
+// stride-16 writes are conflict free; the later layouts are linear).  Pass p with radix R and Ns = product of the earlier
+// radices: butterfly j reads x[j + t N/R], multiplies by exp(-2 pi i t (j mod Ns) / (Ns R)), does an R-point DFT and writes
+// y[(j - j mod Ns) R + j mod Ns + t Ns]; after the last pass the spectrum is in natural order.
+constexpr int FN = 2048, FT = 128;
+constexpr int F_S1 = FN + FN / 16;          // padded pass-1 -> pass-2 exchange
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+    const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), d = csub(a1, a3);
+    const float2 t3 = make_float2(d.y, -d.x);                  // -i (a1 - a3)
+    a0 = cadd(t0, t2); a1 = cadd(t1, t3); a2 = csub(t0, t2); a3 = csub(t1, t3);
+}
+
+// forward DFT of v[0..15] in place (natural order in, natural order out)
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+    // step 1: for every n2 a 4-point DFT over n1 of v[4 n1 + n2]; result u[n2][k1] stays in v[4 k1 + n2]
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+    // step 2: u[n2][k1] *= W16^(n2 k1)
+    const float2 w1 = make_float2(C1, -S1), w2 = make_float2(R2, -R2), w3 = make_float2(S1, -C1);
+    const float2 w6 = make_float2(-R2, -R2), w9 = make_float2(-C1, S1);
+    v[4 + 1] = cmul(v[4 + 1], w1); v[4 + 2] = cmul(v[4 + 2], w2); v[4 + 3] = cmul(v[4 + 3], w3);
+    v[8 + 1] = cmul(v[8 + 1], w2); v[8 + 2] = make_float2(v[8 + 2].y, -v[8 + 2].x); v[8 + 3] = cmul(v[8 + 3], w6);
+    v[12 + 1] = cmul(v[12 + 1], w3); v[12 + 2] = cmul(v[12 + 2], w6); v[12 + 3] = cmul(v[12 + 3], w9);
+    // step 3: for every k1 a 4-point DFT over n2 -> X[k1 + 4 k2] lands in v[4 k1 + k2]; then transpose to natural order
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b) {
+            const float2 t = v[4 * a + b];
+            v[4 * a + b] = v[4 * b + a];
+            v[4 * b + a] = t;
+        }
+}
+
+__device__ __forceinline__ void dft8(float2 (&v)[8]) {
+    constexpr float R2 = 0.70710678118654752f;
+    float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+    dft4(e0, e1, e2, e3);
+    dft4(o0, o1, o2, o3);
+    o1 = cmul(o1, make_float2(R2, -R2));
+    o2 = make_float2(o2.y, -o2.x);
+    o3 = cmul(o3, make_float2(-R2, -R2));
+    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+    v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+    v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+    v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+
+// v[t] *= w^t, t = 1 .. R-1, powers built by squaring / short products (depth <= 4 multiplications)
+template <int R>
+__device__ __forceinline__ void twiddle_powers(float2 (&v)[R], float2 w) {
+    float2 p[R];
+    p[1] = w;
+#pragma unroll
+    for (int t = 2; t < R; ++t) p[t] = (t & 1) ? cmul(p[t - 1], w) : cmul(p[t / 2], p[t / 2]);
+#pragma unroll
+    for (int t = 1; t < R; ++t) v[t] = cmul(v[t], p[t]);
+}
+
+// passes 2 and 3 of the forward transform; pass 1 has already put its butterflies into v.  S: F_S1 float2.
+// On return S[0 .. FN) holds the spectrum in natural order (after the trailing barrier).
+__device__ __forceinline__ void fft2048_tail(float2 (&v)[16], float2* S, const float2* __restrict__ tw, int j) {
+    dft16(v);
+    // pass-1 output y[16 j + t] into the padded exchange
+#pragma unroll
+    for (int t = 0; t < 16; ++t) S[17 * j + t] = v[t];
+    __syncthreads();
+    // pass 2: Ns = 16, R = 16
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const int i = j + FT * t;
+        v[t] = S[i + (i >> 4)];
+    }
+    const int k2 = j & 15;
+    twiddle_powers<16>(v, __ldg(tw + k2 * (FN / 256)));
+    dft16(v);
+    __syncthreads();                                         // every read of the padded layout is done
+    {
+        const int base = ((j - k2) << 4) + k2;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) S[base + 16 * t] = v[t];
+    }
+    __syncthreads();
+    // pass 3: Ns = 256, R = 8, two butterflies per thread (j and j + 128)
+    float2 a[8], b[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        a[t] = S[j + 256 * t];
+        b[t] = S[j + FT + 256 * t];
+    }
+    twiddle_powers<8>(a, __ldg(tw + j));
+    twiddle_powers<8>(b, __ldg(tw + j + FT));
+    dft8(a);
+    dft8(b);
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        S[j + 256 * t] = a[t];
+        S[j + FT + 256 * t] = b[t];
+    }
+    __syncthreads();
+}
+
+// STFT-domain filtering of one frame, N = 2048: same arithmetic as stft_filter_kernel, FFTs in registers.
+__global__ void __launch_bounds__(FT)
+stft_filter2048_kernel(StftFilterArgs a, FrameGrid g) {
+    __shared__ float2 S[F_S1];
+    __shared__ float red[FT / 32];
+    __shared__ int lifter_row;
+
+    const int f = blockIdx.x;
+    const int u = g.frame_utt[f];
+    const int j = threadIdx.x;
+    float* frame_out = a.frames_out + (long long)f * a.win;
+    if (u < 0) {                                             // guard frame: keep the frame buffer defined
+        for (int n = j; n < a.win; n += FT) frame_out[n] = 0.f;
+        if (a.lifter_index_out && j == 0) a.lifter_index_out[f] = 0;
+        return;
+    }
+    const long long s_lo = (long long)g.utt_begin[u] * a.hop, s_hi = (long long)g.utt_end[u] * a.hop;
+
+    // ---- cepstral lifter selection (custom_pulsed_generator.py:507-525) ----
+    if (a.lifters != nullptr) {
+        const long long p_lo = (long long)g.utt_begin[u] * a.pulse_per_frame;
+        const long long p_hi = (long long)g.utt_end[u] * a.pulse_per_frame;
+        const long long start = (long long)f * a.pulse_per_frame - a.n_smooth / 2;
+        float part = 0.f;
+        for (int i = j; i < a.n_smooth; i += FT) {
+            long long q = start + i;
+            q = q < p_lo ? p_lo : (q >= p_hi ? p_hi - 1 : q);
+            part = fmaf(a.f0_smooth[i], a.f0[q], part);
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) part += __shfl_xor_sync(0xffffffffu, part, sft);
+        if ((j & 31) == 0) red[j >> 5] = part;
+        __syncthreads();
+        if (j == 0) {
+            const float tot = (red[0] + red[1]) + (red[2] + red[3]);
+            float lo10 = a.lifter_grid[0], hi10 = a.lifter_grid[a.n_lift - 1];
+            float l10 = __fmul_rn(0.43429448190325176f, logf(tot));
+            l10 = fminf(fmaxf(l10, lo10), hi10);
+            float ratio = __fdiv_rn(__fsub_rn(l10, lo10), __fsub_rn(hi10, lo10));
+            int idx = (int)rintf(__fmul_rn(ratio, (float)(a.n_lift - 1)));   // round half to even like tf.round
+            lifter_row = idx;
+            if (a.lifter_index_out) a.lifter_index_out[f] = idx;
+        }
+        __syncthreads();
+    }
+
+    // ---- forward pass 1 straight from global memory: real = windowed excitation frame, imag = liftered cepstrum ----
+    const float* ceps = a.ceps + (long long)f * a.n_ceps;
+    const float* lift = a.lifters ? a.lifters + (long long)lifter_row * a.n_ceps : nullptr;
+    const long long x0 = (long long)f * a.hop - a.win / 2;      // first excitation sample of this frame
+    float2 v[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const int n = j + FT * t;
+        float re = 0.f, im = 0.f;
+        if (n < a.win) {
+            const long long sidx = x0 + n;
+            if (sidx >= s_lo && sidx < s_hi) re = __ldg(a.exc + sidx) * __ldg(a.window + n);
+        }
+        if (n >= 1 && n < a.n_ceps) im = lift ? __ldg(ceps + n) * __ldg(lift + n) : __ldg(ceps + n);
+        v[t] = make_float2(re, im);
+    }
+    fft2048_tail(v, S, a.twiddle, j);
+
+    // ---- separate the two spectra, apply the vocal-tract filter, build conj of the Hermitian product spectrum ----
+    float2* vtf_out = a.vtf_out ? reinterpret_cast<float2*>(a.vtf_out) + (long long)f * (FN / 2 + 1) : nullptr;
+    float2 Y[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int k = j + FT * t;                              // t = 8 only for k = 1024 (thread 0)
+        if (t == 8 && j != 0) break;
+        const float2 zk = S[k], zn = S[(FN - k) & (FN - 1)];
+        const float2 X = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));        // spectrum of the real part
+        const float2 L = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));        // spectrum of the imag part
+        const float mag = a.max_log_range > 0.f ? expf(a.max_log_range * tanhf(L.x)) : expf(L.x);
+        float sn, cs;
+        sincosf(L.y, &sn, &cs);
+        const float2 V = make_float2(mag * cs, mag * sn);
+        if (vtf_out) vtf_out[k] = V;
+        Y[t] = cmul(X, V);
+    }
+    __syncthreads();
+    // inverse transform as real(fft(conj(W))) with W Hermitian: W[k] = Y, W[N - k] = conj(Y)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int k = j + FT * t;
+        if (t == 8 && j != 0) break;
+        S[k] = make_float2(Y[t].x, -Y[t].y);
+        if (k > 0 && k < FN / 2) S[FN - k] = Y[t];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 16; ++t) v[t] = S[j + FT * t];
+    __syncthreads();                                         // pass-1 reads done before the padded layout is written
+    // ---- inverse passes; the last one goes straight to global memory (only the first `win` samples are kept) ----
+    dft16(v);
+#pragma unroll
+    for (int t = 0; t < 16; ++t) S[17 * j + t] = v[t];
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const int i = j + FT * t;
+        v[t] = S[i + (i >> 4)];
+    }
+    const int k2 = j & 15;
+    twiddle_powers<16>(v, __ldg(a.twiddle + k2 * (FN / 256)));
+    dft16(v);
+    __syncthreads();
+    {
+        const int base = ((j - k2) << 4) + k2;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) S[base + 16 * t] = v[t];
+    }
+    __syncthreads();
+    const float scale = 1.f / (float)FN;
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+        const int jj = j + FT * hb;
+        float2 c[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) c[t] = S[jj + 256 * t];
+        twiddle_powers<8>(c, __ldg(a.twiddle + jj));
+        dft8(c);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int n = jj + 256 * t;
+            if (n < a.win) frame_out[n] = c[t].x * scale * __ldg(a.inv_window + n);
+        }
+    }
+}
+
 __global__ void ola_kernel(OlaArgs a, FrameGrid g) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= (long long)a.n_frames * a.hop) return;
@@ -209,6 +452,10 @@ cudaError_t launch_pqmf(const PqmfArgs& a, const FrameGrid& g, cudaStream_t s) {
 cudaError_t launch_stft_filter(const StftFilterArgs& a, const FrameGrid& g, cudaStream_t s) {
     if (a.n_frames <= 0) return cudaSuccess;
     if (a.fft & (a.fft - 1)) return cudaErrorInvalidValue;
+    if (a.fft == FN && a.win <= FN && a.n_ceps <= FN / 2) {           // the scheme configuration: register-resident FFT
+        stft_filter2048_kernel<<<a.n_frames, FT, 0, s>>>(a, g);
+        return cudaGetLastError();
+    }
     size_t smem = (size_t)2 * a.fft * sizeof(float2);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(stft_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
