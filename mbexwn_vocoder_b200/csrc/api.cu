@@ -444,17 +444,27 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
         const std::string pn = c.post_name;
         const float* w = tensor(h, pn + "/W", (size_t)c.wn_cout * c.subbands * 4, &rc); if (!w) return rc;
         const float* bias = tensor(h, pn + "/b", (size_t)c.subbands * 4, &rc); if (!bias) return rc;
-        mbexwn_op_t op = simple_conv(1, c.wn_cout, c.subbands, 1, 0);
-        ConvArgs a = conv_args(c, op, c.steps_per_frame, rows, cx.p<float>("wn_out"), w, bias, nullptr, cx.p<float>("subbands"));
-        a.ld_x = out_pad;
-        MBX_CUDA_CHECK(launch_conv1d(a, cx.g, s));
-        PqmfArgs pa{};
-        pa.sub = cx.p<float>("subbands");
-        pa.poly = tensor(h, "pqmf_poly", (size_t)c.pqmf_q * c.subbands * c.subbands * 4, &rc); if (!pa.poly) return rc;
-        pa.out = cx.p<float>("excitation"); pa.rows = rows; pa.steps_per_frame = c.steps_per_frame;
-        pa.S = c.subbands; pa.Q = c.pqmf_q; pa.back = c.pqmf_back;
-        MBX_CUDA_CHECK(launch_pqmf(pa, cx.g, s));
-        h->launches += 2;
+        const float* poly = tensor(h, "pqmf_poly", (size_t)c.pqmf_q * c.subbands * c.subbands * 4, &rc); if (!poly) return rc;
+        PostPqmfArgs fa{};
+        fa.wn_out = cx.p<float>("wn_out"); fa.ld = out_pad; fa.cin = c.wn_cout; fa.post_w = w; fa.post_b = bias; fa.poly = poly;
+        fa.sub_out = h->debug_taps ? cx.p<float>("subbands") : nullptr; fa.out = cx.p<float>("excitation");
+        fa.rows = rows; fa.steps_per_frame = c.steps_per_frame; fa.S = c.subbands; fa.Q = c.pqmf_q; fa.back = c.pqmf_back;
+        if (post_pqmf_supported(fa)) {
+            MBX_CUDA_CHECK(launch_post_pqmf(fa, cx.g, s));
+            h->launches += 1;
+        } else {
+            mbexwn_op_t op = simple_conv(1, c.wn_cout, c.subbands, 1, 0);
+            ConvArgs a = conv_args(c, op, c.steps_per_frame, rows, cx.p<float>("wn_out"), w, bias, nullptr, cx.p<float>("subbands"));
+            a.ld_x = out_pad;
+            MBX_CUDA_CHECK(launch_conv1d(a, cx.g, s));
+            PqmfArgs pa{};
+            pa.sub = cx.p<float>("subbands");
+            pa.poly = poly;
+            pa.out = cx.p<float>("excitation"); pa.rows = rows; pa.steps_per_frame = c.steps_per_frame;
+            pa.S = c.subbands; pa.Q = c.pqmf_q; pa.back = c.pqmf_back;
+            MBX_CUDA_CHECK(launch_pqmf(pa, cx.g, s));
+            h->launches += 2;
+        }
     }
 
     mark();

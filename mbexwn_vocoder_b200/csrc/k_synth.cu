@@ -54,6 +54,128 @@ pqmf_kernel(PqmfArgs a, FrameGrid g) {
     }
 }
 
+// ---- fused post 1x1 + PQMF synthesis -------------------------------------------------------------------------------
+// One CTA = PP_ROWS sub-band rows (= PP_ROWS * S output samples).  The WaveNet output rows of the tile (with the Q - 1
+// halo rows the polyphase filter reaches) are staged coalesced in shared memory, the wn_post_net 1x1
+// (custom_pulsed_generator.py:913-914) turns them into the sub-band tile, then thread = row accumulates its S output
+// samples over the (Q, S) taps with the polyphase matrix read as warp-wide broadcasts (one LDS.128 feeds four FMAs).
+// Same summation order as conv1d_kernel + pqmf_kernel, so the results are bit-identical to the two-kernel path.
+constexpr int PP_ROWS = 128, PP_MAXS = 16, PP_MAXC = 32, PP_MAXQ = 24;
+
+__global__ void __launch_bounds__(PP_ROWS)
+post_pqmf_kernel(PostPqmfArgs a, FrameGrid g) {
+    extern __shared__ float sm[];
+    const int S = a.S, Q = a.Q, tile_rows = PP_ROWS + Q - 1;
+    float* G = sm;                                        // (Q * S, 16): polyphase taps, phase-padded to 16
+    float* Wp = G + Q * S * PP_MAXS;                      // (cin + 1, 16): post weights, then bias
+    float* Xw = Wp + (a.cin + 1) * PP_MAXS;               // (tile_rows, ld + 1) staged WaveNet output rows
+    float* X = Xw + tile_rows * (a.ld + 1);               // (tile_rows, S) sub-band tile; reused for the output samples
+    __shared__ int s_fu[PP_ROWS + PP_MAXQ];               // utterance of every tile row, -1 for guard / out-of-range rows
+    const int tid = threadIdx.x;
+    const long long m0 = (long long)blockIdx.x * PP_ROWS;
+    const long long r0 = m0 - a.back;                     // first staged row
+
+    for (int i = tid; i < Q * S * PP_MAXS; i += PP_ROWS) {
+        const int qk = i >> 4, p = i & 15;
+        G[i] = p < S ? a.poly[qk * S + p] : 0.f;
+    }
+    for (int i = tid; i < (a.cin + 1) * PP_MAXS; i += PP_ROWS) {
+        const int ci = i >> 4, p = i & 15;
+        Wp[i] = p < S ? (ci < a.cin ? a.post_w[ci * S + p] : a.post_b[p]) : 0.f;
+    }
+    for (int i = tid; i < tile_rows; i += PP_ROWS) {
+        const long long r = r0 + i;
+        s_fu[i] = (r >= 0 && r < a.rows) ? g.frame_utt[r / a.steps_per_frame] : -1;
+    }
+    {   // coalesced float4 copy of the contiguous (tile_rows, ld) block
+        const int n4 = tile_rows * a.ld / 4;
+        const float4* src = reinterpret_cast<const float4*>(a.wn_out + r0 * a.ld);
+        for (int i = tid; i < n4; i += PP_ROWS) {
+            const int e = i * 4, rl = e / a.ld, c = e - rl * a.ld;
+            const long long r = r0 + rl;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r >= 0 && r < a.rows) v = __ldg(src + i);
+            float* d = Xw + rl * (a.ld + 1) + c;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    }
+    __syncthreads();
+    // post 1x1: sub-bands of every staged row (guard rows are zero)
+    for (int rl = tid; rl < tile_rows; rl += PP_ROWS) {
+        float acc[PP_MAXS];
+#pragma unroll
+        for (int p = 0; p < PP_MAXS; ++p) acc[p] = 0.f;
+        const bool valid = s_fu[rl] >= 0;
+        if (valid) {
+            const float* xr = Xw + rl * (a.ld + 1);
+            for (int ci = 0; ci < a.cin; ++ci) {
+                const float x = xr[ci];
+                const float4* w4 = reinterpret_cast<const float4*>(Wp + ci * PP_MAXS);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float4 w = w4[v];
+                    acc[4 * v] = fmaf(x, w.x, acc[4 * v]); acc[4 * v + 1] = fmaf(x, w.y, acc[4 * v + 1]);
+                    acc[4 * v + 2] = fmaf(x, w.z, acc[4 * v + 2]); acc[4 * v + 3] = fmaf(x, w.w, acc[4 * v + 3]);
+                }
+            }
+            const float* b = Wp + a.cin * PP_MAXS;
+#pragma unroll
+            for (int p = 0; p < PP_MAXS; ++p) acc[p] += b[p];
+        }
+        const long long r = r0 + rl;
+#pragma unroll
+        for (int p = 0; p < PP_MAXS; ++p)
+            if (p < S) {
+                X[rl * S + p] = acc[p];
+                // the tile's own rows (not the halo) also go to the sub-band tap
+                if (a.sub_out && rl >= a.back && rl < a.back + PP_ROWS && r < a.rows) a.sub_out[r * S + p] = acc[p];
+            }
+    }
+    __syncthreads();
+    // polyphase synthesis: thread = row m0 + tid
+    float acc[PP_MAXS];
+#pragma unroll
+    for (int p = 0; p < PP_MAXS; ++p) acc[p] = 0.f;
+    const long long m = m0 + tid;
+    const int fu = s_fu[tid + a.back];
+    if (m < a.rows && fu >= 0) {
+        const long long lo = (long long)g.utt_begin[fu] * a.steps_per_frame;
+        const long long hi = (long long)g.utt_end[fu] * a.steps_per_frame;
+        for (int q = 0; q < Q; ++q) {
+            const long long r = m + q - a.back;
+            if (r < lo || r >= hi) continue;             // zero padding at the utterance's own ends
+            const float* xr = X + (tid + q) * S;
+            const float* gq = G + q * S * PP_MAXS;
+            for (int k = 0; k < S; ++k) {
+                const float x = xr[k];
+                const float4* g4 = reinterpret_cast<const float4*>(gq + k * PP_MAXS);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float4 w = g4[v];
+                    acc[4 * v] = fmaf(x, w.x, acc[4 * v]); acc[4 * v + 1] = fmaf(x, w.y, acc[4 * v + 1]);
+                    acc[4 * v + 2] = fmaf(x, w.z, acc[4 * v + 2]); acc[4 * v + 3] = fmaf(x, w.w, acc[4 * v + 3]);
+                }
+            }
+        }
+    }
+    __syncthreads();                                      // everyone is done reading X
+#pragma unroll
+    for (int p = 0; p < PP_MAXS; ++p)
+        if (p < S) X[tid * S + p] = acc[p];
+    __syncthreads();
+    // coalesced store of the PP_ROWS * S contiguous output samples
+    const long long o0 = m0 * S;
+    const long long total = a.rows * S;
+    for (int i = tid * 4; i < PP_ROWS * S; i += PP_ROWS * 4) {
+        if (o0 + i + 3 < total && ((o0 & 3) == 0)) {
+            *reinterpret_cast<float4*>(a.out + o0 + i) = make_float4(X[i], X[i + 1], X[i + 2], X[i + 3]);
+        } else {
+            for (int e = 0; e < 4; ++e)
+                if (i + e < PP_ROWS * S && o0 + i + e < total) a.out[o0 + i + e] = X[i + e];
+        }
+    }
+}
+
 // ---- shared-memory FFT ----------------------------------------------------------------------------
 
 __device__ __forceinline__ float2 cmul(float2 x, float2 y) {
@@ -446,6 +568,22 @@ cudaError_t launch_pqmf(const PqmfArgs& a, const FrameGrid& g, cudaStream_t s) {
         if (e != cudaSuccess) return e;
     }
     pqmf_kernel<<<(unsigned)((a.rows + PQ_ROWS - 1) / PQ_ROWS), PQ_THREADS, smem, s>>>(a, g);
+    return cudaGetLastError();
+}
+
+bool post_pqmf_supported(const PostPqmfArgs& a) {
+    return a.S <= PP_MAXS && a.cin <= PP_MAXC && a.ld <= PP_MAXC && a.ld % 4 == 0 && a.Q <= PP_MAXQ && (PP_ROWS * a.S) % 4 == 0;
+}
+
+cudaError_t launch_post_pqmf(const PostPqmfArgs& a, const FrameGrid& g, cudaStream_t s) {
+    if (a.rows <= 0) return cudaSuccess;
+    const int tile_rows = PP_ROWS + a.Q - 1;
+    const size_t smem = (size_t)(a.Q * a.S * PP_MAXS + (a.cin + 1) * PP_MAXS + tile_rows * (a.ld + 1) + tile_rows * a.S) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(post_pqmf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    post_pqmf_kernel<<<(unsigned)((a.rows + PP_ROWS - 1) / PP_ROWS), PP_ROWS, smem, s>>>(a, g);
     return cudaGetLastError();
 }
 

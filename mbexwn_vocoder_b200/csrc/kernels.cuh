@@ -96,6 +96,22 @@ struct PqmfArgs {
 };
 cudaError_t launch_pqmf(const PqmfArgs& a, const FrameGrid& g, cudaStream_t s);
 
+// wn_post_net 1x1 (custom_pulsed_generator.py:913-914) fused with the polyphase PQMF synthesis
+struct PostPqmfArgs {
+    const float* wn_out;    // (rows, ld) WaveNet output, channel padding beyond cin
+    int ld, cin;
+    const float* post_w;    // (cin, S)
+    const float* post_b;    // (S)
+    const float* poly;      // (Q, S, S) polyphase bank
+    float* sub_out;         // optional tap (rows, S)
+    float* out;             // (rows * S)
+    long long rows;
+    int steps_per_frame;
+    int S, Q, back;
+};
+bool post_pqmf_supported(const PostPqmfArgs& a);
+cudaError_t launch_post_pqmf(const PostPqmfArgs& a, const FrameGrid& g, cudaStream_t s);
+
 struct StftFilterArgs {
     const float* exc;       // (frames * hop)
     const float* ceps;      // (frames, n_ceps)
