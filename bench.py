@@ -1,18 +1,19 @@
 #!/usr/bin/env python
 """Headline benchmark: audio-seconds generated per wall-second (24 kHz) of the MBExWN mel-inversion forward pass.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16x3|bf16|fp32] [--workload config2|config3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision f16f8|bf16x3|bf16|fp32] [--workload config2|config3]
     python bench.py --impl reference ...        # the restated reference forward on the box's host cores
 
 One "step" = one pass of the hot path over one batch of synthetic mels (BASELINE.json configs[1]: MW-SP-FD,
-batch 64 x 5 s, fp32-accurate = bf16x3 tensor-core path).  N > 1 (torchrun): every rank runs its own batch of the
+batch 64 x 5 s, fp32-accurate = f16f8 split-precision tensor-core path: fp16 product + two e4m3 correction products).  N > 1 (torchrun): every rank runs its own batch of the
 same size (independent utterances, no data-path collective; weak scaling); time = max over ranks.
 
 JSON keys beyond the base contract:
   value     whole-job audio-s/s with inputs already resident in HBM (device events around K steps)
   e2e       the same metric through the host-buffer C-ABI call (H2D of mel+noise and D2H of audio inside the timing)
-  roofline  the dominant kernel (tcgen05 tap-GEMM, 2 launches per WaveNet layer): algorithmic TFLOP/s over the
-            WaveNet stage time measured with CUDA events recorded inside the library on the launch stream
+  roofline  the dominant kernel (wn_gemm_kernel<EPI_GATE>: dilated-conv tap-GEMM + gate epilogue, one launch per WaveNet
+            layer): its algorithmic TFLOP/s over its average launch duration, from CUDA events recorded inside the library
+            on the launch stream around every launch (a separate pass after the headline timing)
   stages    device ms per stage + achieved GB/s (algorithmic bytes) for the HBM-bound stages
   cpu_baseline  CPU oracle (restated reference forward, torch-CPU fp32) on a bounded sample of the workload
 """
@@ -28,6 +29,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one wn_gemm_kernel<EPI_GATE> launch from the `ncu --set full` capture
+# committed under profiles/ (bytes per launch; None where no capture exists for the configuration)
+NCU_TRAFFIC = {("config2", "f16f8"): 812.3e6 + 630.9e6}
 
 WORKLOADS = {
     # name: (model id, batch, frames, description)
@@ -173,12 +178,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["f16f8", "bf16x3", "bf16", "fp32"])
+    ap.add_argument("--precision", default=None, choices=["f16f8", "bf16x3", "bf16", "fp32"],
+                    help="default: f16f8 (fp32-accurate) for config1/2, bf16 for config3 (BASELINE.json configs)")
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tc-debug", type=int, default=0, help="kernel timing experiments (invalid results): see GemmParams::debug")
     ap.add_argument("--cta-group", type=int, default=2, choices=[1, 2], help="tcgen05 tiles per CTA (1) or per CTA pair (2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.precision is None:
+        args.precision = "bf16" if args.workload == "config3" else "f16f8"
     if args.impl == "reference":
         return run_reference(args)
 
@@ -200,8 +209,10 @@ def main():
     inv = MELInverter(model_id, device=local, precision=args.precision)
     eng, plan = inv.model, inv.plan
     eng.set_option("debug_taps", 0)
-    eng.set_option("stage_timing", 1)
+    eng.set_option("stage_timing", 0)
     eng.set_option("tc_cta_group", args.cta_group)
+    if args.tc_debug:
+        eng.set_option("tc_debug", args.tc_debug)
     mels, noise = synthetic_batch(batch, frames, plan.steps_per_frame, seed0=rank * batch)
     pb = eng.prepare([frames] * batch, precision=args.precision, with_noise=True)
     pb.load(mels, noise)
@@ -227,14 +238,21 @@ def main():
     ev1.record()
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
-    stage_last = pb.stage_ms()                      # stages of the last timed step (events recorded in-library)
     launches = pb.launches() * args.steps
-    # per-stage averages over a few more steps (outside the headline timing)
-    n_avg = 3
+    # per-stage / per-launch device times over a few more steps (outside the headline timing): CUDA events recorded
+    # inside the library on the launch stream at the stage boundaries and around every WaveNet tap-GEMM launch
+    eng.set_option("stage_timing", 1)
+    n_avg = 5
+    wn_launch = {"gate": 0.0, "resskip": 0.0, "layers": plan.wavenet.n_layers}
     for _ in range(n_avg):
         pb.run_device()
         for k, v in pb.stage_ms().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v / n_avg
+        if args.precision != "fp32":
+            t = pb.wavenet_launch_ms()
+            wn_launch["gate"] += t["gate"] / n_avg
+            wn_launch["resskip"] += t["resskip"] / n_avg
+    eng.set_option("stage_timing", 0)
     torch.cuda.synchronize()
 
     # ---- end to end through the host-buffer C-ABI call -------------------------------------------------
@@ -261,21 +279,35 @@ def main():
 
     pk = peaks()
     rows = batch * frames * plan.steps_per_frame
+    wn = plan.wavenet
+    L = wn.n_layers
     wn_flops = wavenet_flops_per_step(plan) * rows
-    n_gemm = 2 * plan.wavenet.n_layers
     wn_ms = stage_acc["wavenet"]
-    achieved = wn_flops / (wn_ms / 1e3) / 1e12
     # executed tensor work in bf16-rate product equivalents: bf16x3 = 3 products; f16f8 = 1 fp16 product + 2 e4m3 products
     # that run at twice the rate
     factor = {"bf16x3": 3, "f16f8": 2}.get(args.precision, 1)
     peak = pk["bf16_tflops_sustained"]
+    # dominant kernel: the gate tap-GEMM (dilated conv, K = k C, N = 2 C), one launch per layer
+    gate_flops = 2.0 * wn.k * wn.c * 2 * wn.c * rows                     # algorithmic, un-padded, per launch
+    if args.precision != "fp32" and wn_launch["gate"] > 0:
+        gate_ms = wn_launch["gate"] / L
+        achieved = gate_flops / (gate_ms / 1e3) / 1e12
+        kernel = "wn_gemm_kernel<EPI_GATE> (tcgen05 tap-GEMM of the dilated conv + tanh*sigmoid gate epilogue)"
+    else:
+        gate_ms = wn_ms / L
+        achieved = wn_flops / L / (gate_ms / 1e3) / 1e12
+        kernel = "fp32 SIMT WaveNet layer (conv1d + gate + res/skip kernels)"
+    ncu_traffic = NCU_TRAFFIC.get((args.workload, args.precision))
     roofline = {
-        "bound": "tensor", "kernel": "wn_gemm_kernel (tcgen05 tap-GEMM, gate + res/skip epilogues)",
+        "bound": "tensor", "kernel": kernel,
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "peak_source": f"{pk['source']} bf16 sustained (kernel timed inside a long step)",
+        "peak_source": f"{pk['source']} bf16 dense sustained (MEASURED_PEAKS.json; kernel timed inside a long step)",
         "executed_flop_factor": factor, "frac_executed": achieved * factor / peak,
-        "launches_per_step": n_gemm, "avg_launch_ms": wn_ms / n_gemm,
-        "algorithmic_flops_per_launch": wn_flops / n_gemm, "traffic": None,
+        "launches_per_step": L, "avg_launch_ms": gate_ms, "algorithmic_flops_per_launch": gate_flops,
+        "traffic": ncu_traffic,
+        "wavenet_stage": {"ms": wn_ms, "gate_ms": wn_launch["gate"], "resskip_ms": wn_launch["resskip"],
+                          "algorithmic_tflops": wn_flops / (wn_ms / 1e3) / 1e12,
+                          "frac_executed": wn_flops * factor / (wn_ms / 1e3) / 1e12 / peak},
     }
     # HBM-bound stages: algorithmic bytes per audio-second
     audio_s = audio_s_step

@@ -165,13 +165,19 @@ MBEXWN_API int mbexwn_last_launch_count(mbexwn_handle_t h);
 /* Options: "debug_taps" (default 1): keep the phase / index / pulse / vtf / lifter_index taps in the workspace;
  * "stage_timing" (default 0): record CUDA events on the caller's stream at the stage boundaries of each forward;
  * "tc_cta_group" (1 or 2): tensor-core tiles owned by one CTA or by a CTA pair (cluster of 2, tcgen05 cta_group::2);
- * "tc_cond_stage" (default 1): the gate epilogue reads its conditioning rows from a shared-memory stage (0: global). */
+ * "tc_cond_stage" (default 1): the gate epilogue reads its conditioning rows from a shared-memory stage (0: global);
+ * "tc8_h_lo" / "tc8_a_lo": log2 scale of the e4m3 lo8 planes of the residual stream / gated activations (F16F8). */
 MBEXWN_API int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value);
 
 /* Device time of each stage of the last forward (needs "stage_timing"); ms[MBEXWN_N_STAGES] in the order
  * f0_net, excitation, cond_conv, wavenet, post_pqmf, vtf_net, stft_ola.  Synchronises on the last event. */
 #define MBEXWN_N_STAGES 7
 MBEXWN_API int mbexwn_stage_ms(mbexwn_handle_t h, float* ms);
+
+/* Device time of the WaveNet tap-GEMM launches of the last forward (needs "stage_timing" and a tensor-core precision):
+ * sum over the layers of the gate launches (dilated conv + gate epilogue) and of the res/skip launches, from CUDA events
+ * recorded on the caller's stream around every launch.  Synchronises on the last event. */
+MBEXWN_API int mbexwn_wavenet_launch_ms(mbexwn_handle_t h, float* gate_ms, float* resskip_ms, int32_t* n_layers);
 
 /* ---- single kernels on caller-provided buffers (stage-level parity tests; same kernels the forward uses) ---- */
 MBEXWN_API int mbexwn_k_conv1d(mbexwn_handle_t h, const mbexwn_batch_t* grid, const mbexwn_op_t* op, int32_t rate,

@@ -591,14 +591,13 @@ int mbexwn_last_launch_count(mbexwn_handle_t h) { return h ? h->launches : 0; }
 int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value) {
     if (!h || !name) return MBEXWN_ERR_INVALID;
     if (!strcmp(name, "debug_taps")) { h->debug_taps = value ? 1 : 0; return MBEXWN_OK; }
-    if (!strcmp(name, "stage_timing")) { h->stage_timing = value ? 1 : 0; return MBEXWN_OK; }
+    if (!strcmp(name, "stage_timing")) { h->stage_timing = value ? 1 : 0; h->tc.time_launches = h->stage_timing; return MBEXWN_OK; }
     if (!strcmp(name, "tc_cta_group")) { h->tc.cta_group = value == 2 ? 2 : 1; return MBEXWN_OK; }
     if (!strcmp(name, "tc_subnets")) { h->tc_subnets = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "tc_cond_stage")) { h->tc.cond_stage = value ? 1 : 0; return MBEXWN_OK; }
+    if (!strcmp(name, "tc_debug")) { h->tc.debug = value; return MBEXWN_OK; }
     if (!strcmp(name, "tc8_h_lo")) { h->tc.sh_h_lo = value; return MBEXWN_OK; }
-    if (!strcmp(name, "tc8_h_hi")) { h->tc.sh_h_hi = value; return MBEXWN_OK; }
     if (!strcmp(name, "tc8_a_lo")) { h->tc.sh_a_lo = value; return MBEXWN_OK; }
-    if (!strcmp(name, "tc8_a_hi")) { h->tc.sh_a_hi = value; return MBEXWN_OK; }
     return mbx::fail(h, MBEXWN_ERR_INVALID, std::string("unknown option: ") + name);
 }
 
@@ -607,6 +606,15 @@ int mbexwn_stage_ms(mbexwn_handle_t h, float* ms) {
     if (!h->ev_recorded) return mbx::fail(h, MBEXWN_ERR_INVALID, "no stage timing recorded (set option stage_timing)");
     MBX_CUDA_CHECK(cudaEventSynchronize(h->ev[MBEXWN_N_STAGES]));
     for (int i = 0; i < MBEXWN_N_STAGES; ++i) MBX_CUDA_CHECK(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+    return MBEXWN_OK;
+}
+
+int mbexwn_wavenet_launch_ms(mbexwn_handle_t h, float* gate_ms, float* resskip_ms, int32_t* n_layers) {
+    if (!h || !gate_ms || !resskip_ms || !n_layers) return MBEXWN_ERR_INVALID;
+    int n = 0;
+    int rc = mbx::wn_tc_launch_ms(h->tc, gate_ms, resskip_ms, &n);
+    if (rc) return mbx::fail(h, rc, "no WaveNet launch timing recorded (set option stage_timing, tensor-core precision)");
+    *n_layers = n;
     return MBEXWN_OK;
 }
 

@@ -57,9 +57,11 @@ constexpr int ACC_STAGES = 2;
 constexpr int MAX_RING = 8;
 constexpr int TMEM_COLS = ACC_STAGES * TILE_N;          // 512 = all of TMEM
 constexpr int MAX_KB = 64;
-constexpr int EPI_WARPS = 8;                            // two warps per TMEM lane quarter, splitting the columns
-constexpr int TC_THREADS = 128 + 32 * EPI_WARPS;
-constexpr int EPI_THREADS = 32 * EPI_WARPS;
+// Epilogue warps: `parts` warps per TMEM lane quarter splitting the columns of a tile.  The gate epilogue is the long one
+// (54 -> ~25 instructions per output and latency bound), so it gets 16 warps (4 per scheduler) and the register budget
+// is moved from the producer / MMA warps to them with setmaxnreg; the other epilogues keep 8 warps.
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == 1 /* EPI_GATE */ ? 16 : 8; }
+__host__ __device__ constexpr int tc_threads(int epi) { return 128 + 32 * epi_warps(epi); }
 constexpr int COND_ROWS = 16;                           // staged conditioning rows per tile (<= 15 used at lin_up = 10)
 constexpr int COND_LD = TILE_N + 4;                     // floats per staged row: consecutive rows shift by 4 banks
 constexpr int COND_BYTES = COND_ROWS * COND_LD * 4;
@@ -88,7 +90,7 @@ struct alignas(64) GemmParams {
     int f16;                // main product operands are fp16 (else bf16)
     // scales of the e4m3 planes the epilogues write: x_lo8 = e4m3((x - fp16(x)) * lo_scale), x_hi8 = e4m3(x * hi_scale)
     int out_f16f8;
-    float out_lo_scale, out_hi_scale, in_lo_inv;
+    float out_lo_scale, in_lo_inv;
     long long rows;         // M
     int n_cols;             // N (multiple of 8; tiles are masked)
     int tiles_m, tiles_n;
@@ -119,6 +121,8 @@ struct alignas(64) GemmParams {
     int res_cols;           // cpad, or 0 for the last layer (skip only)
     int first;              // skip = instead of +=
     FrameGrid grid;
+    int debug;              // timing experiments only (option "tc_debug"): 1 = epilogues skip their math and stores,
+                            // 2 = every tile loads the operands of tile 0 (L2-resident feed), 4 = no MMAs are issued
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -137,11 +141,11 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
+        : "r"(addr), "r"(parity), "r"(0x989680u)      // suspend-time hint: sleep in hardware instead of spinning
+        : "memory");                                   // (a spinning warp costs issue slots and power the tensor pipe needs)
     return done;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -162,7 +166,8 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+template <int THREADS>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -269,6 +274,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "r"(taddr)
         : "memory");
 }
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M x N
@@ -289,10 +305,10 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-// MBEXWN_PREC_F16F8 operand planes of 8 consecutive channels: fp16(x), e4m3((x - fp16(x)) * lo_scale), e4m3(x * hi_scale).
+// MBEXWN_PREC_F16F8 operand planes of 8 consecutive channels: fp16(x), e4m3((x - fp16(x)) * lo_scale), e4m3(x).
 // The scales are powers of two chosen so that the planes sit in e4m3's normal range and the two correction products of a
 // GEMM share the factor 2^15 that scale-input-d removes (see wn_tc_forward).
-__device__ __forceinline__ void split_f16f8(const float (&a)[8], float lo_scale, float hi_scale, uint4& h16, uint2& lo8, uint2& hi8) {
+__device__ __forceinline__ void split_f16f8(const float (&a)[8], float lo_scale, uint4& h16, uint2& lo8, uint2& hi8) {
     uint32_t hw[4], l[4], h[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -300,7 +316,7 @@ __device__ __forceinline__ void split_f16f8(const float (&a)[8], float lo_scale,
         const float2 hf = __half22float2(hh);
         hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
         l[e] = __nv_cvt_float2_to_fp8x2(make_float2((a[2 * e] - hf.x) * lo_scale, (a[2 * e + 1] - hf.y) * lo_scale), __NV_SATFINITE, __NV_E4M3);
-        h[e] = __nv_cvt_float2_to_fp8x2(make_float2(a[2 * e] * hi_scale, a[2 * e + 1] * hi_scale), __NV_SATFINITE, __NV_E4M3);
+        h[e] = __nv_cvt_float2_to_fp8x2(make_float2(a[2 * e], a[2 * e + 1]), __NV_SATFINITE, __NV_E4M3);
     }
     h16 = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     lo8 = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
@@ -340,11 +356,12 @@ __device__ __forceinline__ float rcp_approx(float x) {
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - 2.f * rcp_approx(1.f + ex2_approx(x * 2.885390081777927f)); }
 __device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.f + ex2_approx(x * -1.4426950408889634f)); }
 
-// `half` (0/1) selects which alternate 32-column chunks of the tile this warp handles; `width` = valid tile columns.
+// `part` (0 .. nparts-1) selects which 32-column chunks of the tile this warp handles (part, part + nparts, ...);
+// `width` = valid tile columns.
 
-__device__ __forceinline__ void epi_plain(const GemmParams& p, uint32_t tacc, long long row, int n0, int width, int half) {
+__device__ __forceinline__ void epi_plain(const GemmParams& p, uint32_t tacc, long long row, int n0, int width, int part, int nparts) {
     float v[32];
-    for (int q = half; q < width / 32; q += 2) {
+    for (int q = part; q < width / 32; q += nparts) {
         tmem_ld32(tacc + q * 32, v);
         tmem_ld_wait();
         if (row < p.rows) {
@@ -361,14 +378,14 @@ __device__ __forceinline__ void epi_plain(const GemmParams& p, uint32_t tacc, lo
 // bias, activation, then fp32 rows and / or the bf16 [hi | lo] planes the next tensor-core conv reads.  A sub-pixel conv
 // (conv_layers.py:250-255) unfolds channel c' of row t to row t * f + c' / (cout / f), channel c' % (cout / f).
 // Guard rows are written as zeros (the next conv's zero padding; mirrored pads are patched by mirror_guards_kernel).
-__device__ __forceinline__ void epi_conv(const GemmParams& p, uint32_t tacc, long long row, int n0, int width, int half) {
+__device__ __forceinline__ void epi_conv(const GemmParams& p, uint32_t tacc, long long row, int n0, int width, int part, int nparts) {
     float v[32];
     bool valid = false;
     if (row < p.rows) {
         long long lo, hi;
         valid = utt_bounds(p.grid, p.rate, row, lo, hi);
     }
-    for (int q = half; q < width / 32; q += 2) {
+    for (int q = part; q < width / 32; q += nparts) {
         tmem_ld32(tacc + q * 32, v);
         tmem_ld_wait();
         if (row >= p.rows) continue;
@@ -417,65 +434,114 @@ __device__ __forceinline__ void epi_conv(const GemmParams& p, uint32_t tacc, lon
     }
 }
 
-__device__ __forceinline__ void epi_gate(const GemmParams& p, uint32_t tacc, long long row, int n0, int width, int half) {
-    // tile columns [0, width/2) = tanh channels [n0/2, n0/2 + width/2), columns [width/2, width) = their sigmoid partners
-    const int hw = width >> 1;
-    const int ch_tile = n0 >> 1;
-    bool valid = false;
-    long long rc = 0, rn = 0;
-    float w0 = 1.f, w1 = 0.f;
-    if (row < p.rows) {
-        long long lo, hi;
-        valid = utt_bounds(p.grid, p.steps_per_frame, row, lo, hi);
-        if (valid) {
-            rc = row / p.lin_up;
-            int u = (int)(row - rc * p.lin_up);
-            long long hic = hi / p.lin_up;
-            rn = rc + 1 < hic ? rc + 1 : hic - 1;
-            w0 = p.lin_w0[u];
-            w1 = p.lin_w1[u];
+// ---- gate epilogue with the conditioning rows staged in shared memory ---------------------------------------------
+// Tile (m0, n0, width): accumulator columns [0, width/2) are tanh channels n0/2 + j, columns [width/2, width) their
+// sigmoid partners.  The 128 rows of the tile interpolate between cond rows rc0 .. rc0 + cond_rows - 1 (rc0 = m0 /
+// lin_up).  Stage layout: buf[r][j] = cond[rc0 + r][channel of column j] + bias[n0 + j], j in [0, width).
+// The stage of tile j + 1 is filled by warp 3 while the epilogue warps work on tile j; one named barrier per tile (epilogue
+// warps + warp 3) hands a finished stage over and frees the buffer read two tiles ago.
+// Written by the otherwise idle warp 3, one tile ahead of the epilogue warps (double buffered): lane l copies float4 groups
+// l, l + 32, ... of the COND_ROWS x width stage, four row / bias pairs in flight at a time.
+__device__ __forceinline__ void gate_stage_fill(const GemmParams& p, float* buf, int m0, int n0, int width, int lane) {
+    const int w4 = width >> 2, hw = width >> 1;
+    const int rc0 = m0 / p.lin_up;
+    const int total = p.cond_rows * w4;
+    for (int f0 = lane; f0 < total; f0 += 32 * 4) {
+        float4 v[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int f = f0 + 32 * i;
+            const int r = f / w4, j = (f - r * w4) * 4;
+            const int ch = (n0 >> 1) + (j < hw ? j : j - hw);
+            const int src_col = (j < hw ? 0 : p.c) + ch;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (f < total && ch < p.c && rc0 + r < p.cond_total) {         // channel padding: C is a multiple of 4
+                b[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                v[i] = __ldg(reinterpret_cast<const float4*>(p.cond + (long long)(rc0 + r) * 2 * p.c + src_col));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int f = f0 + 32 * i;
+            const int r = f / w4, j = (f - r * w4) * 4;
+            if (f < total)
+                *reinterpret_cast<float4*>(buf + r * COND_LD + j) =
+                    make_float4(v[i].x + b[i].x, v[i].y + b[i].y, v[i].z + b[i].z, v[i].w + b[i].w);
         }
     }
-    const float* c0 = p.cond + rc * 2 * p.c;
-    const float* c1 = p.cond + rn * 2 * p.c;
-    const float* bias = p.bias + n0;
-    float zt[32], zs[32];
+}
+
+// One thread = one accumulator row, 16-column chunks (part, part + nparts, ...): the conditioning is interpolated with two
+// FMAs per value on top of the accumulator (z + c0 w0 + c1 w1; the reference rounds c0 w0 + c1 w1 first -- a difference of
+// one fp32 ulp of the conditioning, far inside the tolerance of the split-precision GEMM that produced z).
+// STAGED: conditioning rows (+ bias) come from the shared-memory stage `buf`; otherwise straight from global memory.
+template <bool STAGED>
+__device__ __forceinline__ void epi_gate(const GemmParams& p, const float* buf, uint32_t tacc, int row, int m0,
+                                         int n0, int width, int part, int nparts) {
+    const int hw = width >> 1;
+    const int ch_tile = n0 >> 1;
+    const bool in_range = row < (int)p.rows;                     // the TMEM loads are warp-collective: no early exit
+    bool valid = false;
+    int rl0 = 0, rl1 = 0;
+    float w0 = 1.f, w1 = 0.f;
+    if (in_range) {
+        const int f = row / p.steps_per_frame;
+        const int u = p.grid.frame_utt[f];
+        if (u >= 0) {
+            valid = true;
+            const int hic = p.grid.utt_end[u] * p.steps_per_frame / p.lin_up;
+            const int rc0 = m0 / p.lin_up, rc = row / p.lin_up;
+            const int un = row - rc * p.lin_up;
+            const int rn = rc + 1 < hic ? rc + 1 : hic - 1;
+            rl0 = STAGED ? rc - rc0 : rc;
+            rl1 = STAGED ? rn - rc0 : rn;
+            w0 = p.lin_w0[un];
+            w1 = p.lin_w1[un];
+        }
+    }
+    // STAGED: stage rows, column j of the tile (tanh half, then sigmoid half).  Global: cond rows [tanh (C) | sigmoid (C)].
+    const float* s0 = STAGED ? buf + rl0 * COND_LD : p.cond + (long long)rl0 * 2 * p.c + ch_tile;
+    const float* s1 = STAGED ? buf + rl1 * COND_LD : p.cond + (long long)rl1 * 2 * p.c + ch_tile;
+    const int sig_off = STAGED ? hw : p.c;
+    __nv_bfloat16* arow = p.act + (long long)row * p.ld_act;
+    uint8_t* row8 = reinterpret_cast<uint8_t*>(arow);
+    float zt[16], zs[16];
 #pragma unroll 1
-    for (int q = half; q < hw / 32; q += 2) {
-        tmem_ld32(tacc + q * 32, zt);
-        tmem_ld32(tacc + hw + q * 32, zs);
+    for (int q = part; q < hw / 16; q += nparts) {
+        tmem_ld16(tacc + q * 16, zt);
+        tmem_ld16(tacc + hw + q * 16, zs);
         tmem_ld_wait();
-        if (row >= p.rows) continue;
-        const int ch0 = ch_tile + q * 32;
-        __nv_bfloat16* dst = p.act + row * p.ld_act + ch0;
-        uint8_t* row8 = reinterpret_cast<uint8_t*>(p.act + row * p.ld_act);
+        if (!in_range) continue;
+        const int ch0 = ch_tile + q * 16;
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
+        for (int i = 0; i < 16; i += 8) {
             float a[8];
+            if (valid) {
 #pragma unroll
-            for (int v4 = 0; v4 < 2; ++v4) {
-                const int cb = ch0 + i + 4 * v4;
-                if (valid && cb < p.c) {                      // C is a multiple of 4 on this path
-                    float4 x0 = __ldg(reinterpret_cast<const float4*>(c0 + cb));
-                    float4 x1 = __ldg(reinterpret_cast<const float4*>(c1 + cb));
-                    float4 y0 = __ldg(reinterpret_cast<const float4*>(c0 + p.c + cb));
-                    float4 y1 = __ldg(reinterpret_cast<const float4*>(c1 + p.c + cb));
-                    float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + q * 32 + i) + v4);
-                    float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + hw + q * 32 + i) + v4);
-                    const float ct[4] = {__fadd_rn(__fmul_rn(x0.x, w0), __fmul_rn(x1.x, w1)),
-                                         __fadd_rn(__fmul_rn(x0.y, w0), __fmul_rn(x1.y, w1)),
-                                         __fadd_rn(__fmul_rn(x0.z, w0), __fmul_rn(x1.z, w1)),
-                                         __fadd_rn(__fmul_rn(x0.w, w0), __fmul_rn(x1.w, w1))};
-                    const float cs[4] = {__fadd_rn(__fmul_rn(y0.x, w0), __fmul_rn(y1.x, w1)),
-                                         __fadd_rn(__fmul_rn(y0.y, w0), __fmul_rn(y1.y, w1)),
-                                         __fadd_rn(__fmul_rn(y0.z, w0), __fmul_rn(y1.z, w1)),
-                                         __fadd_rn(__fmul_rn(y0.w, w0), __fmul_rn(y1.w, w1))};
-                    const float bt[4] = {b0.x, b0.y, b0.z, b0.w};
-                    const float bs[4] = {b1.x, b1.y, b1.z, b1.w};
+                for (int v4 = 0; v4 < 2; ++v4) {
+                    const int col = q * 16 + i + 4 * v4;
+                    if (!STAGED && ch_tile + col >= p.c) {             // channel padding (C is a multiple of 4): z = 0 -> act = 0
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) a[4 * v4 + e] = 0.f;
+                        continue;
+                    }
+                    const float4 x0 = *reinterpret_cast<const float4*>(s0 + col);
+                    const float4 x1 = *reinterpret_cast<const float4*>(s1 + col);
+                    const float4 y0 = *reinterpret_cast<const float4*>(s0 + sig_off + col);
+                    const float4 y1 = *reinterpret_cast<const float4*>(s1 + sig_off + col);
+                    const float xa[4] = {x0.x, x0.y, x0.z, x0.w}, xb[4] = {x1.x, x1.y, x1.z, x1.w};
+                    const float ya[4] = {y0.x, y0.y, y0.z, y0.w}, yb[4] = {y1.x, y1.y, y1.z, y1.w};
+                    if (!STAGED) {                                     // the stage has the bias folded in
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + hw + col));
+                        zt[i + 4 * v4] += b0.x; zt[i + 4 * v4 + 1] += b0.y; zt[i + 4 * v4 + 2] += b0.z; zt[i + 4 * v4 + 3] += b0.w;
+                        zs[i + 4 * v4] += b1.x; zs[i + 4 * v4 + 1] += b1.y; zs[i + 4 * v4 + 2] += b1.z; zs[i + 4 * v4 + 3] += b1.w;
+                    }
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        float t = zt[i + 4 * v4 + e] + bt[e] + ct[e];
-                        float sg = zs[i + 4 * v4 + e] + bs[e] + cs[e];
+                        float t = fmaf(xb[e], w1, fmaf(xa[e], w0, zt[i + 4 * v4 + e]));
+                        const float sg = fmaf(yb[e], w1, fmaf(ya[e], w0, zs[i + 4 * v4 + e]));
                         switch (p.gate) {
                             case GATE_GTU: t = fast_tanh(t); break;
                             case GATE_GFU: t = t * rcp_approx(1.f + fabsf(t)); break;
@@ -484,163 +550,33 @@ __device__ __forceinline__ void epi_gate(const GemmParams& p, uint32_t tacc, lon
                         }
                         a[4 * v4 + e] = t * fast_sigmoid(sg);
                     }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) a[4 * v4 + e] = 0.f;
                 }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] = 0.f;              // guard rows stay zero
             }
+            __nv_bfloat16* dst = arow + ch0 + i;
             if (p.out_f16f8) {
                 uint4 h16;
                 uint2 l8, h8;
-                split_f16f8(a, p.out_lo_scale, p.out_hi_scale, h16, l8, h8);
+                split_f16f8(a, p.out_lo_scale, h16, l8, h8);
                 uint8_t* d8 = row8 + f8_off(p.cpad, ch0 + i);
-                *reinterpret_cast<uint4*>(dst + i) = h16;
+                *reinterpret_cast<uint4*>(dst) = h16;
                 *reinterpret_cast<uint2*>(d8) = l8;
                 *reinterpret_cast<uint2*>(d8 + 64) = h8;
-                continue;
-            }
-            uint32_t hw4[4], lw4[4];
+            } else {
+                uint32_t hw4[4], lw4[4];
 #pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(a[e], h0, l0);
-                split_bf16(a[e + 1], h1, l1);
-                hw4[e / 2] = pack2(h0, h1);
-                lw4[e / 2] = pack2(l0, l1);
-            }
-            *reinterpret_cast<uint4*>(dst + i) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
-            if (p.write_lo) *reinterpret_cast<uint4*>(dst + p.cpad + i) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
-        }
-    }
-}
-
-// ---- gate epilogue with the conditioning rows staged in shared memory ---------------------------------------------
-// Tile (m0, n0, width): accumulator columns [0, width/2) are tanh channels n0/2 + j, columns [width/2, width) their
-// sigmoid partners.  The 128 rows of the tile interpolate between cond rows rc0 .. rc0 + cond_rows - 1 (rc0 = m0 /
-// lin_up).  Stage layout: buf[r][j] = cond[rc0 + r][channel of column j] + bias[n0 + j], j in [0, width).
-// The 256 epilogue threads load the stage of the *next* tile into registers before they start on the current one
-// and park it in the other smem buffer when they are done, so no global-load latency sits between the MMA and the gate.
-struct GateStage {
-    float4 v[4];
-    float4 b[4];
-};
-
-__device__ __forceinline__ void gate_stage_load(const GemmParams& p, long long m0, int n0, int width, int et, GateStage& st) {
-    const int w4 = width >> 2, hw = width >> 1;
-    const long long rc0 = m0 / p.lin_up;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int f = et + EPI_THREADS * i;
-        const int r = f / w4, j = (f - r * w4) * 4;
-        const int ch = (n0 >> 1) + (j < hw ? j : j - hw);
-        const int src_col = (j < hw ? 0 : p.c) + ch;
-        st.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        st.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ch < p.c && r < p.cond_rows && rc0 + r < p.cond_total) {           // channel padding: C is a multiple of 4
-            st.b[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-            st.v[i] = __ldg(reinterpret_cast<const float4*>(p.cond + (rc0 + r) * 2 * p.c + src_col));
-        }
-    }
-}
-
-__device__ __forceinline__ void gate_stage_store(float* buf, int width, int et, const GateStage& st) {
-    const int w4 = width >> 2;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int f = et + EPI_THREADS * i;
-        const int r = f / w4, j = (f - r * w4) * 4;
-        if (r < COND_ROWS)
-            *reinterpret_cast<float4*>(buf + r * COND_LD + j) =
-                make_float4(st.v[i].x + st.b[i].x, st.v[i].y + st.b[i].y, st.v[i].z + st.b[i].z, st.v[i].w + st.b[i].w);
-    }
-}
-
-__device__ __forceinline__ void epi_gate_staged(const GemmParams& p, const float* buf, uint32_t tacc, long long row, long long m0,
-                                                int n0, int width, int half) {
-    const int hw = width >> 1;
-    const int ch_tile = n0 >> 1;
-    bool valid = false;
-    int rl0 = 0, rl1 = 0;
-    float w0 = 1.f, w1 = 0.f;
-    if (row < p.rows) {
-        long long lo, hi;
-        valid = utt_bounds(p.grid, p.steps_per_frame, row, lo, hi);
-        if (valid) {
-            const long long rc0 = m0 / p.lin_up;
-            const long long rc = row / p.lin_up;
-            const int u = (int)(row - rc * p.lin_up);
-            const long long hic = hi / p.lin_up;
-            const long long rn = rc + 1 < hic ? rc + 1 : hic - 1;
-            rl0 = (int)(rc - rc0);
-            rl1 = (int)(rn - rc0);
-            w0 = p.lin_w0[u];
-            w1 = p.lin_w1[u];
-        }
-    }
-    const float* s0 = buf + rl0 * COND_LD;
-    const float* s1 = buf + rl1 * COND_LD;
-    float zt[32], zs[32];
-#pragma unroll 1
-    for (int q = half; q < hw / 32; q += 2) {
-        tmem_ld32(tacc + q * 32, zt);
-        tmem_ld32(tacc + hw + q * 32, zs);
-        tmem_ld_wait();
-        if (row >= p.rows) continue;
-        __nv_bfloat16* dst = p.act + row * p.ld_act + ch_tile + q * 32;
-        uint8_t* row8 = reinterpret_cast<uint8_t*>(p.act + row * p.ld_act);
-        const int ch0 = ch_tile + q * 32;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-            float a[8];
-#pragma unroll
-            for (int v4 = 0; v4 < 2; ++v4) {
-                const int col = q * 32 + i + 4 * v4;
-                const float4 x0 = *reinterpret_cast<const float4*>(s0 + col);
-                const float4 x1 = *reinterpret_cast<const float4*>(s1 + col);
-                const float4 y0 = *reinterpret_cast<const float4*>(s0 + hw + col);
-                const float4 y1 = *reinterpret_cast<const float4*>(s1 + hw + col);
-                const float ct[4] = {__fadd_rn(__fmul_rn(x0.x, w0), __fmul_rn(x1.x, w1)),
-                                     __fadd_rn(__fmul_rn(x0.y, w0), __fmul_rn(x1.y, w1)),
-                                     __fadd_rn(__fmul_rn(x0.z, w0), __fmul_rn(x1.z, w1)),
-                                     __fadd_rn(__fmul_rn(x0.w, w0), __fmul_rn(x1.w, w1))};
-                const float cs[4] = {__fadd_rn(__fmul_rn(y0.x, w0), __fmul_rn(y1.x, w1)),
-                                     __fadd_rn(__fmul_rn(y0.y, w0), __fmul_rn(y1.y, w1)),
-                                     __fadd_rn(__fmul_rn(y0.z, w0), __fmul_rn(y1.z, w1)),
-                                     __fadd_rn(__fmul_rn(y0.w, w0), __fmul_rn(y1.w, w1))};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float t = zt[i + 4 * v4 + e] + ct[e];
-                    const float sg = zs[i + 4 * v4 + e] + cs[e];
-                    switch (p.gate) {
-                        case GATE_GTU: t = fast_tanh(t); break;
-                        case GATE_GFU: t = t * rcp_approx(1.f + fabsf(t)); break;
-                        case GATE_GSU: t = t * rcp_approx(1.f + sqrtf(fabsf(t))); break;
-                        default: break;
-                    }
-                    a[4 * v4 + e] = valid ? t * fast_sigmoid(sg) : 0.f;       // padded channels: z = 0 -> act = 0
+                for (int e = 0; e < 8; e += 2) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(a[e], h0, l0);
+                    split_bf16(a[e + 1], h1, l1);
+                    hw4[e / 2] = pack2(h0, h1);
+                    lw4[e / 2] = pack2(l0, l1);
                 }
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
+                if (p.write_lo) *reinterpret_cast<uint4*>(dst + p.cpad) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
             }
-            if (p.out_f16f8) {
-                uint4 h16;
-                uint2 l8, h8;
-                split_f16f8(a, p.out_lo_scale, p.out_hi_scale, h16, l8, h8);
-                uint8_t* d8 = row8 + f8_off(p.cpad, ch0 + i);
-                *reinterpret_cast<uint4*>(dst + i) = h16;
-                *reinterpret_cast<uint2*>(d8) = l8;
-                *reinterpret_cast<uint2*>(d8 + 64) = h8;
-                continue;
-            }
-            uint32_t hw4[4], lw4[4];
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(a[e], h0, l0);
-                split_bf16(a[e + 1], h1, l1);
-                hw4[e / 2] = pack2(h0, h1);
-                lw4[e / 2] = pack2(l0, l1);
-            }
-            *reinterpret_cast<uint4*>(dst + i) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
-            if (p.write_lo) *reinterpret_cast<uint4*>(dst + p.cpad + i) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
         }
     }
 }
@@ -654,7 +590,7 @@ __device__ __forceinline__ void epi_gate_staged(const GemmParams& p, const float
 struct ResSkipCtx {
     unsigned vmask;          // bit r: row (row0 + r) of this warp is inside an utterance
     long long row0;          // first row of this warp's lane quarter
-    int n0, width, half;
+    int n0, width, part, nparts;
 };
 
 // scratch tile: float4 group g (0..7) of row r lives at r * 32 + ((g ^ (r & 7)) << 2): conflict-free row writes and
@@ -718,7 +654,7 @@ __device__ __forceinline__ void resskip_store(const GemmParams& p, const ResSkip
                 for (int idx = 0; idx < 8; ++idx) o[idx] = (ch0 + idx < p.c) ? prev[idx] + (xv[idx] + bv[idx]) : 0.f;
                 uint4 h16;
                 uint2 l8, h8;
-                split_f16f8(o, p.out_lo_scale, p.out_hi_scale, h16, l8, h8);
+                split_f16f8(o, p.out_lo_scale, h16, l8, h8);
                 __nv_bfloat16* prow = p.h + (c.row0 + r) * p.ld_h;
                 uint8_t* p8 = reinterpret_cast<uint8_t*>(prow) + f8_off(p.cpad, ch0);
                 *reinterpret_cast<uint4*>(prow + ch0) = h16;
@@ -768,17 +704,17 @@ __device__ __forceinline__ void resskip_store(const GemmParams& p, const ResSkip
     }
 }
 
-__device__ __forceinline__ ResSkipCtx resskip_begin(const GemmParams& p, long long row, int n0, int width, int half, int lane,
-                                                    uint4 (&old)[8]) {
+__device__ __forceinline__ ResSkipCtx resskip_begin(const GemmParams& p, long long row, int n0, int width, int part, int nparts,
+                                                    int lane, uint4 (&old)[8]) {
     ResSkipCtx c;
-    c.row0 = row - lane; c.n0 = n0; c.width = width; c.half = half;
+    c.row0 = row - lane; c.n0 = n0; c.width = width; c.part = part; c.nparts = nparts;
     bool valid = false;
     if (row < p.rows) {
         long long lo, hi;
         valid = utt_bounds(p.grid, p.steps_per_frame, row, lo, hi);
     }
     c.vmask = __ballot_sync(0xffffffffu, valid);
-    resskip_load_old(p, c, half, lane, old);
+    resskip_load_old(p, c, part, lane, old);
     return c;
 }
 
@@ -786,9 +722,9 @@ __device__ __forceinline__ void epi_resskip(const GemmParams& p, const ResSkipCt
     float v[32];
     uint4 nxt[8];
 #pragma unroll 1
-    for (int q = c.half; q < c.width / 32; q += 2) {
+    for (int q = c.part; q < c.width / 32; q += c.nparts) {
         tmem_ld32(tacc + q * 32, v);
-        resskip_load_old(p, c, q + 2, lane, nxt);
+        resskip_load_old(p, c, q + c.nparts, lane, nxt);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -810,8 +746,9 @@ __device__ __forceinline__ void epi_resskip(const GemmParams& p, const ResSkipCt
 // loads its own 128 rows of A and *half* of the B rows, the leader issues M = 256 MMAs that read both halves, each CTA
 // keeps the accumulators of its own rows in its own TMEM and runs its own epilogue.  Halves the per-SM ingest of B.
 template <int EPI, int CG>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads(EPI), 1)
 wn_gemm_kernel(const __grid_constant__ GemmParams p) {
+    constexpr int EW = epi_warps(EPI), ET = 32 * EW, NPARTS = EW / 4;
     constexpr int B_BYTES = (TILE_N / CG) * TILE_K * 2;
     constexpr int NA = CG == 1 ? 4 : 6;
     constexpr int NB = CG == 1 ? 4 : 6;
@@ -869,7 +806,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
         // MEMBAR + ERRBAR round trip and serialised the peer's producer thread)
         for (int s = 0; s < NA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
         for (int s = 0; s < NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], CG * EPI_WARPS); }
+        for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], CG * EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -887,13 +824,20 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
+    // EW == 16: 640 threads start with 96 registers each; the producer / MMA warpgroup hands most of its share to the 16
+    // epilogue warps (128 x 56 + 512 x 104 <= 64 K).  Every role branch starts with its own setmaxnreg so that ptxas
+    // allocates the branch under the new limit.
+#define MBX_REG_DEC() do { if (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;"); } while (0)
+#define MBX_REG_INC() do { if (EW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;"); } while (0)
+
     if (warp == 0) {
+        MBX_REG_DEC();
         // ===== TMA producer: the whole warp walks the schedule, one elected lane issues =====
         uint32_t ia = 0, ib = 0;
         for (int j = 0; j < n_seq; ++j) {
             int m_grp, n_blk;
             tile_of(j, m_grp, n_blk);
-            const int m0 = (m_grp * CG + (int)rank) * TILE_M;
+            const int m0 = (p.debug & 2) ? (int)rank * TILE_M : (m_grp * CG + (int)rank) * TILE_M;
             int width = p.n_cols - n_blk * TILE_N;
             width = width > TILE_N ? TILE_N : ((width + 15) & ~15);
             const int nb0 = n_blk * TILE_N + (int)rank * (width / CG);      // this CTA's share of the B rows
@@ -977,11 +921,13 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
     } else if (warp == 1) {
         // ===== MMA issuer (leader CTA): warp-uniform loop, one elected lane issues the tcgen05 instructions =====
+        MBX_REG_DEC();
         if (leader) {
             uint32_t ia = 0, ib = 0, tile_it = 0;
             const uint32_t a_base = smem_u32(ring_a) >> 4, b_base = smem_u32(ring_b) >> 4;
             // first: 0 = accumulate, 1 = the first MMA overwrites the accumulator, 2 = the first MMA rescales it by 2^-15
             auto mma4 = [&](uint32_t tacc, uint32_t sa, uint32_t sb, uint32_t idesc, int first) {
+                if (p.debug & 4) return;
                 const uint64_t da = DESC_HI | (uint64_t)(a_base + sa * (A_BYTES >> 4));
                 const uint64_t db = DESC_HI | (uint64_t)(b_base + sb * (B_BYTES >> 4));
 #pragma unroll
@@ -996,6 +942,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
             };
             // e4m3 products of one K block: [lo8 | hi8] (A) x [hi8 | lo8] (B) = 128 bytes along K = 4 instructions of K = 32
             auto mma8 = [&](uint32_t tacc, uint32_t sa, uint32_t sb, uint32_t idesc, bool first) {
+                if (p.debug & 4) return;
                 const uint64_t da = DESC_HI | (uint64_t)(a_base + sa * (A_BYTES >> 4));
                 const uint64_t db = DESC_HI | (uint64_t)(b_base + sb * (B_BYTES >> 4));
 #pragma unroll
@@ -1078,20 +1025,10 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
     } else if (warp >= 4) {
         // ===== epilogue warps: every CTA drains the accumulators of its own 128 rows =====
-        const int q4 = warp & 3, half = (warp - 4) >> 2;
-        const int et = threadIdx.x - (TC_THREADS - EPI_THREADS);
+        MBX_REG_INC();
+        const int q4 = warp & 3, part = (warp - 4) >> 2;
         const bool staged = EPI == EPI_GATE && p.cond_rows > 0;
         uint32_t tile_it = 0;
-        GateStage gst;
-        if (staged && n_seq > 0) {
-            // stage of the first tile
-            int m_grp, n_blk;
-            tile_of(0, m_grp, n_blk);
-            int width = p.n_cols - n_blk * TILE_N;
-            width = width > TILE_N ? TILE_N : ((width + 31) & ~31);
-            gate_stage_load(p, (long long)(m_grp * CG + (int)rank) * TILE_M, n_blk * TILE_N, width, et, gst);
-            gate_stage_store(cond_stage, width, et, gst);
-        }
         for (int j = 0; j < n_seq; ++j, ++tile_it) {
             int m_grp, n_blk;
             tile_of(j, m_grp, n_blk);
@@ -1103,25 +1040,24 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
             width = width > TILE_N ? TILE_N : ((width + 31) & ~31);
             uint4 old[8];
             ResSkipCtx rctx;
-            if (EPI == EPI_RESSKIP) rctx = resskip_begin(p, row, n_blk * TILE_N, width, half, lane, old);   // loads fly during the MMAs
-            int nwidth = 0;
-            if (staged) {
-                if (j + 1 < n_seq) {                                // next tile's conditioning rows -> registers
-                    int mg2, nb2;
-                    tile_of(j + 1, mg2, nb2);
-                    nwidth = p.n_cols - nb2 * TILE_N;
-                    nwidth = nwidth > TILE_N ? TILE_N : ((nwidth + 31) & ~31);
-                    gate_stage_load(p, (long long)(mg2 * CG + (int)rank) * TILE_M, nb2 * TILE_N, nwidth, et, gst);
-                }
-                epi_bar_sync();                                     // this tile's stage is complete in smem
-            }
+            if (EPI == EPI_RESSKIP) rctx = resskip_begin(p, row, n_blk * TILE_N, width, part, NPARTS, lane, old);   // loads fly during the MMAs
+            if (staged) epi_bar_sync<ET + 32>();                    // warp 3 has finished this tile's stage
             mbar_wait(&tmem_full[as], aph);
             tc_fence_after();
-            if (EPI == EPI_PLAIN) epi_plain(p, tacc, row, n_blk * TILE_N, width, half);
-            if (EPI == EPI_CONV) epi_conv(p, tacc, row, n_blk * TILE_N, width, half);
+            if (p.debug & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 1 || leader) mbar_arrive(&tmem_empty[as]);
+                    else mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));
+                }
+                continue;
+            }
+            if (EPI == EPI_PLAIN) epi_plain(p, tacc, row, n_blk * TILE_N, width, part, NPARTS);
+            if (EPI == EPI_CONV) epi_conv(p, tacc, row, n_blk * TILE_N, width, part, NPARTS);
             if (EPI == EPI_GATE) {
-                if (staged) epi_gate_staged(p, cond_stage + (tile_it & 1) * (COND_ROWS * COND_LD), tacc, row, m0, n_blk * TILE_N, width, half);
-                else epi_gate(p, tacc, row, n_blk * TILE_N, width, half);
+                if (staged) epi_gate<true>(p, cond_stage + (tile_it & 1) * (COND_ROWS * COND_LD), tacc, (int)row, (int)m0, n_blk * TILE_N, width, part, NPARTS);
+                else epi_gate<false>(p, nullptr, tacc, (int)row, (int)m0, n_blk * TILE_N, width, part, NPARTS);
             }
             if (EPI == EPI_RESSKIP) epi_resskip(p, rctx, tacc, lane, cond_stage + (warp - 4) * 1024, old);
             tc_fence_before();
@@ -1130,8 +1066,21 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                 if (CG == 1 || leader) mbar_arrive(&tmem_empty[as]);
                 else mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));
             }
-            // park the next tile's stage in the other buffer (last read two tiles ago, before the barrier above)
-            if (staged && nwidth) gate_stage_store(cond_stage + ((tile_it + 1) & 1) * (COND_ROWS * COND_LD), nwidth, et, gst);
+        }
+    } else if (warp == 2) {
+        MBX_REG_DEC();
+    } else if (warp == 3) {
+        // ===== conditioning stager of the gate epilogue =====
+        MBX_REG_DEC();
+        if (EPI == EPI_GATE && p.cond_rows > 0) {
+            for (int j = 0; j < n_seq; ++j) {
+                int m_grp, n_blk;
+                tile_of(j, m_grp, n_blk);
+                int width = p.n_cols - n_blk * TILE_N;
+                width = width > TILE_N ? TILE_N : ((width + 31) & ~31);
+                gate_stage_fill(p, cond_stage + (j & 1) * (COND_ROWS * COND_LD), (m_grp * CG + (int)rank) * TILE_M, n_blk * TILE_N, width, lane);
+                epi_bar_sync<ET + 32>();                            // stage j is ready; everyone is done with tile j - 1
+            }
         }
     }
 
@@ -1152,7 +1101,7 @@ constexpr int START_ROWS = 64;
 constexpr int START_MAX_CIN = 16;
 __global__ void start_pack_kernel(const float* __restrict__ x, int cin, const float* __restrict__ w, const float* __restrict__ b,
                                   __nv_bfloat16* __restrict__ out, long long rows, int c, int cpad, int rate, FrameGrid g,
-                                  int f16f8, float lo_scale, float hi_scale) {
+                                  int f16f8, float lo_scale) {
     extern __shared__ float sw[];                       // [cin + 1][cpad]: weights, then bias
     float* sx = sw + (cin + 1) * cpad;                  // [START_ROWS][cin] inputs, zero for guard rows
     __shared__ int svalid[START_ROWS];
@@ -1195,7 +1144,7 @@ __global__ void start_pack_kernel(const float* __restrict__ x, int cin, const fl
         if (f16f8) {
             uint4 h16;
             uint2 l8, h8;
-            split_f16f8(v, lo_scale, hi_scale, h16, l8, h8);
+            split_f16f8(v, lo_scale, h16, l8, h8);
             uint8_t* p8 = reinterpret_cast<uint8_t*>(out + r * 2 * cpad) + f8_off(cpad, ch0);
             *reinterpret_cast<uint4*>(out + r * 2 * cpad + ch0) = h16;
             *reinterpret_cast<uint2*>(p8) = l8;
@@ -1333,12 +1282,12 @@ cudaError_t launch_gemm(Impl* im, GemmParams& p, cudaStream_t s) {
     if (n_tiles < groups) groups = n_tiles;
     p.sched_m_major = tiles_mg >= 8 * groups ? 1 : 0;
     if (cg == 1) {
-        wn_gemm_kernel<EPI, 1><<<groups, TC_THREADS, SMEM_BYTES, s>>>(p);
+        wn_gemm_kernel<EPI, 1><<<groups, tc_threads(EPI), SMEM_BYTES, s>>>(p);
         return cudaGetLastError();
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(groups * 2);
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(tc_threads(EPI));
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -1387,8 +1336,7 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
     const bool f8 = precision == MBEXWN_PREC_F16F8;
     const int n_terms = precision == MBEXWN_PREC_BF16X3 ? 3 : (f8 ? 2 : 1);
     // power-of-two scales of the e4m3 planes (MBEXWN_PREC_F16F8): residual stream h and gated activations
-    const float h_lo = ldexpf(1.f, st.sh_h_lo), h_hi = ldexpf(1.f, st.sh_h_hi);
-    const float a_lo = ldexpf(1.f, st.sh_a_lo), a_hi = ldexpf(1.f, st.sh_a_hi);
+    const float h_lo = ldexpf(1.f, st.sh_h_lo), a_lo = ldexpf(1.f, st.sh_a_lo);
     const std::string n = c.wn_name;
     if (c.wn_c % 4) { if (error) *error = "tensor-core path needs n_channels % 4 == 0"; return MBEXWN_ERR_UNSUPPORTED; }
     if (c.wn_k * (cpad / TILE_K) > MAX_KB) { if (error) *error = "K-block table too small"; return MBEXWN_ERR_UNSUPPORTED; }
@@ -1407,7 +1355,7 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         if (c.wn_cin > START_MAX_CIN) return fail("start conv: more than 16 input channels", MBEXWN_ERR_UNSUPPORTED);
         const size_t smem = ((size_t)(c.wn_cin + 1) * cpad + (size_t)START_ROWS * c.wn_cin) * sizeof(float);
         start_pack_kernel<<<(unsigned)((rows + START_ROWS - 1) / START_ROWS), 256, smem, s>>>(
-            wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g, f8 ? 1 : 0, h_lo, h_hi);
+            wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g, f8 ? 1 : 0, h_lo);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(std::string("start conv: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
         *launches += 1;
@@ -1428,6 +1376,17 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
     if ((rc = make_map(im, &tm_a, a2, rows, 2 * cpad, TILE_M, error))) return rc;
     const std::string tc = f8 ? "/tc8/" : "/tc/";
 
+    cudaEvent_t* ev = nullptr;
+    st.n_timed = 0;
+    if (st.time_launches) {
+        if (!st.events) {
+            cudaEvent_t* e = new cudaEvent_t[2 * MBEXWN_MAX_LAYERS + 1];
+            for (int i = 0; i < 2 * MBEXWN_MAX_LAYERS + 1; ++i) cudaEventCreate(&e[i]);
+            st.events = e;
+        }
+        ev = reinterpret_cast<cudaEvent_t*>(st.events);
+        cudaEventRecord(ev[st.n_timed++], s);
+    }
     for (int i = 0; i < c.wn_layers; ++i) {
         const std::string li = std::to_string(i);
         const bool last = i == c.wn_layers - 1;
@@ -1447,14 +1406,15 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         for (int t = 0; t < c.wn_k; ++t) shifts[t] = (t - (c.wn_k - 1) / 2) * d;
         p1.n_kb = build_kblocks(p1.kb, c.wn_k, shifts, cpad);
         p1.n_terms = n_terms; p1.a_lo_off = cpad; p1.b_lo_off = c.wn_k * cpad;
-        if (f8) { p1.f16 = 1; p1.out_f16f8 = 1; p1.out_lo_scale = a_lo; p1.out_hi_scale = a_hi; }
+        if (f8) { p1.f16 = 1; p1.out_f16f8 = 1; p1.out_lo_scale = a_lo; }
         p1.rows = rows; p1.n_cols = n1; p1.bias = b1; p1.cond = cond; p1.act = a2; p1.ld_act = 2 * cpad;
         p1.c = c.wn_c; p1.cpad = cpad; p1.lin_up = c.wn_cond_lin_up; p1.gate = c.wn_gate; p1.write_lo = n_terms == 3;
-        p1.steps_per_frame = c.steps_per_frame; p1.grid = g;
+        p1.steps_per_frame = c.steps_per_frame; p1.grid = g; p1.debug = st.debug;
         p1.cond_rows = cond_rows; p1.cond_total = rows / c.wn_cond_lin_up;
         for (int u = 0; u < c.wn_cond_lin_up; ++u) { p1.lin_w0[u] = lw0[u]; p1.lin_w1[u] = lw1[u]; }
         cudaError_t e = launch_gemm<EPI_GATE>(im, p1, s);
         if (e != cudaSuccess) return fail(std::string("gate GEMM: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
+        if (ev) cudaEventRecord(ev[st.n_timed++], s);
 
         GemmParams p2{};
         p2.tm_a = tm_a;
@@ -1462,13 +1422,14 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         int zero = 0;
         p2.n_kb = build_kblocks(p2.kb, 1, &zero, cpad);
         p2.n_terms = n_terms; p2.a_lo_off = cpad; p2.b_lo_off = cpad;
-        if (f8) { p2.f16 = 1; p2.out_f16f8 = 1; p2.out_lo_scale = h_lo; p2.out_hi_scale = h_hi; p2.in_lo_inv = 1.f / h_lo; }
+        if (f8) { p2.f16 = 1; p2.out_f16f8 = 1; p2.out_lo_scale = h_lo; p2.in_lo_inv = 1.f / h_lo; }
         p2.rows = rows; p2.n_cols = n2; p2.bias = b2; p2.h = h2; p2.ld_h = 2 * cpad;
         p2.skip = wn_out; p2.skip_ld = out_pad; p2.skip_c = out_pad;
         p2.c = c.wn_c; p2.cpad = cpad; p2.res_cols = last ? 0 : cpad; p2.first = i == 0;
-        p2.steps_per_frame = c.steps_per_frame; p2.grid = g;
+        p2.steps_per_frame = c.steps_per_frame; p2.grid = g; p2.debug = st.debug;
         e = launch_gemm<EPI_RESSKIP>(im, p2, s);
         if (e != cudaSuccess) return fail(std::string("res/skip GEMM: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
+        if (ev) cudaEventRecord(ev[st.n_timed++], s);
         *launches += 2;
     }
     return MBEXWN_OK;
@@ -1564,9 +1525,29 @@ int wn_tc_gemm_test_f16f8(WnTcState& st, const void* a, long long rows, int a_cp
     return MBEXWN_OK;
 }
 
+int wn_tc_launch_ms(WnTcState& st, float* gate_ms, float* resskip_ms, int* n_layers) {
+    if (!st.events || st.n_timed < 3) return MBEXWN_ERR_INVALID;
+    cudaEvent_t* ev = reinterpret_cast<cudaEvent_t*>(st.events);
+    if (cudaEventSynchronize(ev[st.n_timed - 1]) != cudaSuccess) return MBEXWN_ERR_CUDA;
+    float g = 0.f, r = 0.f;
+    for (int i = 0; i + 1 < st.n_timed; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) != cudaSuccess) return MBEXWN_ERR_CUDA;
+        (i & 1 ? r : g) += ms;
+    }
+    *gate_ms = g; *resskip_ms = r; *n_layers = (st.n_timed - 1) / 2;
+    return MBEXWN_OK;
+}
+
 void wn_tc_invalidate(WnTcState&) {}
 
 void wn_tc_destroy(WnTcState& st) {
+    if (st.events) {
+        cudaEvent_t* e = reinterpret_cast<cudaEvent_t*>(st.events);
+        for (int i = 0; i < 2 * MBEXWN_MAX_LAYERS + 1; ++i) cudaEventDestroy(e[i]);
+        delete[] e;
+        st.events = nullptr;
+    }
     delete reinterpret_cast<Impl*>(st.impl);
     st.impl = nullptr;
 }

@@ -12,9 +12,15 @@ struct WnTcState {
     bool ready = false;
     int cta_group = 2;          // option "tc_cta_group": 1 = one CTA per tile, 2 = CTA pairs (cta_group::2)
     int cond_stage = 1;         // option "tc_cond_stage": gate epilogue reads its conditioning rows from a smem stage
-    // MBEXWN_PREC_F16F8: log2 scales of the e4m3 planes of the residual stream (h) and of the gated activations (a).
-    // The weight planes carry 2^(15 - sh_*): options "tc8_h_lo", "tc8_h_hi", "tc8_a_lo", "tc8_a_hi" (host packer must agree).
-    int sh_h_lo = 9, sh_h_hi = 2, sh_a_lo = 10, sh_a_hi = 4;
+    // MBEXWN_PREC_F16F8: log2 scales of the e4m3 lo8 planes ((x - fp16 x) * 2^sh) of the residual stream (h) and of the
+    // gated activations (a); the hi8 planes are e4m3(x) unscaled.  The weight hi8 planes carry 2^(15 - sh_*), the weight
+    // lo8 planes 2^15: options "tc8_h_lo", "tc8_a_lo" (the host packer must agree).
+    int sh_h_lo = 9, sh_a_lo = 10;
+    // option "stage_timing": CUDA events around every WaveNet GEMM launch of the last forward (gate / res-skip alternate)
+    int time_launches = 0;
+    int n_timed = 0;            // events recorded by the last forward (n launches + 1)
+    void* events = nullptr;     // cudaEvent_t[2 * MBEXWN_MAX_LAYERS + 1]
+    int debug = 0;              // option "tc_debug": timing experiments (results are wrong), see GemmParams::debug
     void* impl = nullptr;
 };
 
@@ -69,6 +75,9 @@ int wn_tc_gemm_test(WnTcState& st, const void* a_bf16, long long rows, int a_col
 // correction products scaled by 2^-15.
 int wn_tc_gemm_test_f16f8(WnTcState& st, const void* a, long long rows, int a_cpad, const void* b, int n, int b_k,
                           const int* kblocks, int n_kb, float* out, cudaStream_t s, std::string* error);
+
+// Device time of the gate and res/skip GEMM launches of the last forward (needs time_launches); synchronises.
+int wn_tc_launch_ms(WnTcState& st, float* gate_ms, float* resskip_ms, int* n_layers);
 
 void wn_tc_invalidate(WnTcState& st);
 void wn_tc_destroy(WnTcState& st);

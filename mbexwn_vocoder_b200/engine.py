@@ -323,6 +323,15 @@ class PreparedBatch:
         _cabi.check(self.eng.lib, self.eng._handle, self.eng.lib.mbexwn_stage_ms(self.eng._handle, buf), "stage_ms")
         return {n: float(buf[i]) for i, n in enumerate(_cabi.STAGE_NAMES)}
 
+    def wavenet_launch_ms(self) -> Dict[str, float]:
+        """Device ms of the gate / res-skip tap-GEMM launches of the last run, summed over the layers (needs
+        "stage_timing" and a tensor-core precision)."""
+        g, r, n = C.c_float(), C.c_float(), C.c_int32()
+        _cabi.check(self.eng.lib, self.eng._handle,
+                    self.eng.lib.mbexwn_wavenet_launch_ms(self.eng._handle, C.byref(g), C.byref(r), C.byref(n)),
+                    "wavenet_launch_ms")
+        return {"gate": float(g.value), "resskip": float(r.value), "layers": int(n.value)}
+
     def launches(self) -> int:
         return int(self.eng.lib.mbexwn_last_launch_count(self.eng._handle))
 

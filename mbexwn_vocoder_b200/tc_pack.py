@@ -99,10 +99,11 @@ def _tc_matrices(plan: ModelPlan, weights: Dict[str, np.ndarray]) -> Dict[str, n
 # ---- MBEXWN_PREC_F16F8: fp16 main product + two e4m3 correction products ---------------------------------------
 # x * w ~ f16(x) f16(w) + 2^-15 [ e4m3((x - f16 x) 2^sa) e4m3(w 2^(15 - sa)) + e4m3(x 2^sa') e4m3((w - f16 w) 2^(15 - sa')) ]
 # The tensor cores rescale the accumulated correction products by 2^-15 (scale-input-d of the first fp16 MMA of a tile), so
-# for every GEMM the plane scales of the two operands must multiply to 2^15.  Activation-side shifts (kernel options
-# tc8_h_lo / tc8_h_hi for the residual stream, tc8_a_lo / tc8_a_hi for the gated activations in (-1, 1)):
+# for every GEMM the plane scales of the two operands must multiply to 2^15.  The activation hi8 planes are unscaled
+# (e4m3(x): |x| up to 448, so the weight lo8 planes carry 2^15); the activation lo8 shifts are kernel options (tc8_h_lo for
+# the residual stream, tc8_a_lo for the gated activations in (-1, 1)):
 CORR_SHIFT = 15
-TC8_DEFAULT_SHIFTS = {"tc8_h_lo": 9, "tc8_h_hi": 2, "tc8_a_lo": 10, "tc8_a_hi": 4}
+TC8_DEFAULT_SHIFTS = {"tc8_h_lo": 9, "tc8_a_lo": 10}
 E4M3_MAX = 448.0
 
 
@@ -128,7 +129,7 @@ def choose_tc8_shifts(w1_max: float, r_max: float) -> Dict[str, int]:
     return out
 
 
-def pack_tc8_weights(plan: ModelPlan, weights: Dict[str, np.ndarray], packed: Dict[str, torch.Tensor] = None):
+def pack_tc8_weights(plan: ModelPlan, weights: Dict[str, np.ndarray]):
     """The matrices of pack_tc_weights (same row order / folding, fp32 before the split) as [fp16 | e4m3 | e4m3] planes.
 
     Returns ({name: uint8 tensor}, shifts)."""
@@ -141,9 +142,9 @@ def pack_tc8_weights(plan: ModelPlan, weights: Dict[str, np.ndarray], packed: Di
     out: Dict[str, torch.Tensor] = {}
     for key, m in mats.items():
         if "/W1_" in key:
-            out[key.replace("/tc/", "/tc8/")] = f16f8_planes(m, CORR_SHIFT - sh["tc8_h_lo"], CORR_SHIFT - sh["tc8_h_hi"])
+            out[key.replace("/tc/", "/tc8/")] = f16f8_planes(m, CORR_SHIFT - sh["tc8_h_lo"], CORR_SHIFT)
         elif "/R_" in key:
-            out[key.replace("/tc/", "/tc8/")] = f16f8_planes(m, CORR_SHIFT - sh["tc8_a_lo"], CORR_SHIFT - sh["tc8_a_hi"])
+            out[key.replace("/tc/", "/tc8/")] = f16f8_planes(m, CORR_SHIFT - sh["tc8_a_lo"], CORR_SHIFT)
     return out, sh
 
 

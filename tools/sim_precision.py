@@ -60,7 +60,7 @@ class Scheme:
             # scale-input-d variant: both correction products share the scale 2^15 (sa + sb = 15)
             ah, bh = rnd(a, torch.float16), rnd(b, torch.float16)
             al, bl = a - ah, b - bh
-            sa, sb, sa2, sb2 = (9, 6, 2, 13) if kind == "h" else (10, 5, 4, 11)
+            sa, sb, sa2, sb2 = (9, 6, 0, 15) if kind == "h" else (10, 5, 0, 15)
             t1 = e4m3(al * 2.0 ** sa) @ e4m3(bh * 2.0 ** sb)
             t2 = e4m3(ah * 2.0 ** sa2) @ e4m3(bl * 2.0 ** sb2)
             return ah @ bh + (t1 + t2) * 2.0 ** -15
