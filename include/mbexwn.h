@@ -117,6 +117,9 @@ typedef struct {
     const int32_t* utt_ids;         /* [n_utt] global utterance ids for the Philox stream, or NULL => batch index */
     uint64_t seed;
     float* out;                     /* (n_frames * hop) waveform on the grid */
+    const float* phase_carry;       /* [n_utt] or NULL: unwrapped running sum of the wrapped 1000-sample chunk totals that
+                                       precede the utterance (stable_cumsum_and_wrap, tf_wavetable.py:470-486) when the
+                                       "utterance" is a window of a longer signal that starts on a chunk boundary */
 } mbexwn_batch_t;
 
 /* ---- life cycle: stands in for create_model + build_model + load_weights (mel_inverter.py:184-210) ---- */
@@ -166,6 +169,7 @@ MBEXWN_API int mbexwn_last_launch_count(mbexwn_handle_t h);
  * "stage_timing" (default 0): record CUDA events on the caller's stream at the stage boundaries of each forward;
  * "tc_cta_group" (1 or 2): tensor-core tiles owned by one CTA or by a CTA pair (cluster of 2, tcgen05 cta_group::2);
  * "tc_cond_stage" (default 1): the gate epilogue reads its conditioning rows from a shared-memory stage (0: global);
+ * "stop_after_f0" (default 0): return after the F0 sub-net (tap "F0"), for the F0 pass of chunked long-form synthesis;
  * "tc8_h_lo" / "tc8_a_lo": log2 scale of the e4m3 lo8 planes of the residual stream / gated activations (F16F8). */
 MBEXWN_API int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value);
 

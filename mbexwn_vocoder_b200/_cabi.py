@@ -59,7 +59,8 @@ class Batch(C.Structure):
     _fields_ = [("n_utt", C.c_int32), ("n_frames", C.c_int32), ("n_chunks", C.c_int32),
                 ("frame_utt", C.c_void_p), ("utt_begin", C.c_void_p), ("utt_end", C.c_void_p),
                 ("chunk_first", C.c_void_p), ("mel", C.c_void_p), ("noise", C.c_void_p),
-                ("f0_override", C.c_void_p), ("utt_ids", C.c_void_p), ("seed", C.c_uint64), ("out", C.c_void_p)]
+                ("f0_override", C.c_void_p), ("utt_ids", C.c_void_p), ("seed", C.c_uint64), ("out", C.c_void_p),
+                ("phase_carry", C.c_void_p)]
 
 
 # every symbol include/mbexwn.h declares: name -> (restype, argtypes)

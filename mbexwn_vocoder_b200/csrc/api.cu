@@ -18,6 +18,7 @@ struct mbexwn_handle_s {
     int launches = 0;
     int debug_taps = 1;
     int stage_timing = 0;
+    int stop_after_f0 = 0;      // option: F0 pass of chunked long-form synthesis
     int tc_subnets = 1;         // wide sub-net / conditioning convs on the tensor cores (TC precisions only)
     cudaEvent_t ev[MBEXWN_N_STAGES + 1] = {};
     bool ev_ready = false;
@@ -372,6 +373,7 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
                                        cudaMemcpyDeviceToDevice, s));
     }
 
+    if (h->stop_after_f0) return MBEXWN_OK;
     mark();
     // (2) excitation generator head (generate_excitation, :886-906)
     {
@@ -383,7 +385,7 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
         a.grid_norm = c.wt_grid_norm; a.sigma = c.noise_sigma;
         a.pulse_per_frame = c.pulse_per_frame; a.steps_per_frame = c.steps_per_frame; a.pulse_channels = c.pulse_channels;
         a.chunk = c.cumsum_chunk; a.cum = cx.p<float>("cum"); a.chunk_off = cx.p<float>("chunk_off");
-        a.chunk_first = b->chunk_first; a.wn_in = cx.p<float>("wn_in"); a.ld_wn_in = c.wn_cin;
+        a.chunk_first = b->chunk_first; a.phase_carry = b->phase_carry; a.wn_in = cx.p<float>("wn_in"); a.ld_wn_in = c.wn_cin;
         a.phase_out = cx.p<float>("phase"); a.index_out = cx.p<int32_t>("index"); a.pulse_out = cx.p<float>("pulse");
         MBX_CUDA_CHECK(launch_excitation(a, cx.g, b->n_chunks, s));
         h->launches += 3;
@@ -595,6 +597,7 @@ int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value) {
     if (!strcmp(name, "tc_cta_group")) { h->tc.cta_group = value == 2 ? 2 : 1; return MBEXWN_OK; }
     if (!strcmp(name, "tc_subnets")) { h->tc_subnets = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "tc_cond_stage")) { h->tc.cond_stage = value ? 1 : 0; return MBEXWN_OK; }
+    if (!strcmp(name, "stop_after_f0")) { h->stop_after_f0 = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "tc_debug")) { h->tc.debug = value; return MBEXWN_OK; }
     if (!strcmp(name, "tc8_h_lo")) { h->tc.sh_h_lo = value; return MBEXWN_OK; }
     if (!strcmp(name, "tc8_a_lo")) { h->tc.sh_a_lo = value; return MBEXWN_OK; }

@@ -68,7 +68,9 @@ __global__ void chunk_offset_kernel(ExcitationArgs a, FrameGrid g) {
     const int lane = threadIdx.x & 31;
     if (u >= g.n_utt) return;
     const int first = a.chunk_first[u], n = a.chunk_first[u + 1] - first;
-    float run = 0.f;            // unwrapped running sum of the wrapped totals (tf.cumsum(offsets, axis=1))
+    // unwrapped running sum of the wrapped totals (tf.cumsum(offsets, axis=1)); a window of a longer signal continues
+    // the sum of the chunks before it
+    float run = a.phase_carry ? a.phase_carry[u] : 0.f;
     for (int b0 = 0; b0 < n; b0 += 32) {
         int i = b0 + lane;
         float tot = i < n ? a.chunk_off[first + i] : 0.f;

@@ -77,6 +77,7 @@ struct ExcitationArgs {
     float* cum;             // scratch (frames * pulse_per_frame): in-chunk running sums
     float* chunk_off;       // scratch (n_chunks_total): per chunk offsets
     const int32_t* chunk_first;  // [n_utt + 1] first chunk slot of each utterance (exclusive scan)
+    const float* phase_carry;    // [n_utt] or nullptr: running sum of the chunk totals before the utterance's first chunk
     float* wn_in;           // (frames * steps_per_frame, ld_wn_in): pulse_channels pulse samples [+ noise]
     int ld_wn_in;
     float* phase_out;       // optional taps (frames * pulse_per_frame)

@@ -198,9 +198,9 @@ class Engine:
                 torch.from_numpy(layout.utt_end).to(dev), torch.from_numpy(layout.chunk_first).to(dev))
 
     def prepare(self, lengths: Sequence[int], precision: str = "fp32", with_noise: bool = True,
-                with_f0: bool = False) -> "PreparedBatch":
+                with_f0: bool = False, with_carry: bool = False) -> "PreparedBatch":
         """Allocate everything one batch geometry needs (device grid, staging, pinned host buffers, workspace)."""
-        return PreparedBatch(self, lengths, precision, with_noise, with_f0)
+        return PreparedBatch(self, lengths, precision, with_noise, with_f0, with_carry)
 
     def forward(self, mels: Sequence[np.ndarray], noise: Optional[Sequence[np.ndarray]] = None,
                 f0: Optional[Sequence[np.ndarray]] = None, precision: str = "fp32", seed: int = 0,
@@ -231,7 +231,8 @@ class Engine:
 class PreparedBatch:
     """One batch geometry bound to its buffers; `run_host` is the reference-facing call (host in, host out)."""
 
-    def __init__(self, eng: Engine, lengths: Sequence[int], precision: str, with_noise: bool, with_f0: bool):
+    def __init__(self, eng: Engine, lengths: Sequence[int], precision: str, with_noise: bool, with_f0: bool,
+                 with_carry: bool = False):
         plan = eng.plan
         self.eng = eng
         self.prec = _cabi.PRECISIONS[precision]
@@ -261,6 +262,10 @@ class PreparedBatch:
         b.noise = self.noise_dev.data_ptr() if with_noise else None
         b.f0_override = self.f0_dev.data_ptr() if with_f0 else None
         b.out = self.out_dev.data_ptr()
+        self.carry_dev = None
+        if with_carry:                                        # windows of a longer signal (long_form.py)
+            self.carry_dev = torch.zeros(L.n_utt, dtype=torch.float32, device=dev)
+            b.phase_carry = self.carry_dev.data_ptr()
 
     def set_utt_ids(self, utt_ids: Sequence[int]):
         ids = np.asarray(utt_ids, dtype=np.int32)
@@ -278,7 +283,7 @@ class PreparedBatch:
     def d2h_bytes(self) -> int:
         return self.out_host.numel() * 4
 
-    def load(self, mels, noise=None, f0=None):
+    def load(self, mels, noise=None, f0=None, carry=None):
         L, plan = self.layout, self.eng.plan
         self.layout.scatter([np.asarray(m, dtype=np.float32) for m in mels], 1, self.mel_host.numpy())
         if noise is not None:
@@ -288,6 +293,8 @@ class PreparedBatch:
             buf = np.zeros(L.n_frames * plan.pulse_per_frame, dtype=np.float32)
             L.scatter([np.asarray(x, dtype=np.float32).reshape(-1) for x in f0], plan.pulse_per_frame, buf)
             self.f0_dev.copy_(torch.from_numpy(buf))
+        if carry is not None:
+            self.carry_dev.copy_(torch.from_numpy(np.asarray(carry, dtype=np.float32)))
 
     def _stream(self):
         return torch.cuda.current_stream(self.eng.device).cuda_stream

@@ -1,0 +1,174 @@
+"""Chunked long-form synthesis (BASELINE.json configs[4]: one 10-minute mel, chunked with receptive-field overlap).
+
+The forward pass of MBExWN (custom_pulsed_generator.py:556-771) has finite memory everywhere except in the pulse phase
+(tf_wavetable.py:429-492: a cumulative sum over the whole utterance).  A long mel is therefore cut into windows
+[core - context, core + context) that are processed as independent "utterances" of one batch; only the core of each
+window is kept.  With a context that covers the receptive field of every stage the cores are *bit-identical* to the
+un-chunked result, because every kernel works per row with a fixed summation order (tests/test_gpu_long_form.py).
+
+Three passes:
+  1. F0 pass  -- the F0 sub-net over windows with its own (small) context -> exact F0 track of the whole signal;
+  2. phase carry -- the unwrapped running sum of the wrapped 1000-sample chunk totals (host, float32, the reference's
+                    sequential association order), one value per cumsum chunk;
+  3. main pass -- windows whose start is a multiple of the cumsum chunk (10 frames) with f0_override = exact F0 slice and
+                  phase_carry = the running sum before the window's first chunk.
+Windows are batched up to `max_batch_frames` per call, so throughput comes from the same batched kernels as configs 2-4;
+the first window alone gives the first-chunk latency.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .plan import ModelPlan
+
+
+def subnet_reach_frames(ops) -> int:
+    """Mel frames a sub-net output frame can see on either side (conv pads and interpolation neighbours)."""
+    reach = 0.0
+    for op in ops:
+        if op.kind == "conv":
+            c = op.conv
+            reach += max(c.pad_l, c.pad_r, (c.k - 1) * c.dilation - min(c.pad_l, c.pad_r)) / op.rate_in
+        else:
+            reach += 1.0 / op.rate_in               # LinInterp reads the next low-rate row
+    return int(np.ceil(reach)) + 1
+
+
+def main_context_frames(plan: ModelPlan) -> int:
+    """Context (frames per side) after which a window's core no longer depends on where the window was cut, given the
+    exact F0: WaveNet receptive field + conditioning conv / interpolation + VTF sub-net + PQMF + STFT + lifter smoothing."""
+    wn = plan.wavenet
+    wn_rows = sum(d * (wn.k - 1) // 2 for d in wn.dilations) + max(plan.pqmf_back, plan.pqmf_q - 1 - plan.pqmf_back)
+    ctx = -(-wn_rows // wn.steps_per_frame)                                  # WaveNet + PQMF rows -> frames
+    ctx += (wn.cond_k - 1) // 2 + 1                                          # conditioning conv + its x10 interpolation
+    ctx += -(-(plan.stft_win // 2) // plan.hop)                              # STFT frames overlapping a sample
+    ctx = max(ctx, subnet_reach_frames(plan.ps_ops) + 2,                     # VTF sub-net (per frame, no recursion)
+              -(-(len(plan.f0_smooth) // 2) // plan.pulse_per_frame) + 2)    # F0 smoothing of the lifter selection
+    return ctx + 2
+
+
+def phase_run_before_chunks(f0: np.ndarray, pulse_rate: float, chunk: int = 1000) -> np.ndarray:
+    """Unwrapped float32 running sum of the wrapped chunk totals *before* every cumsum chunk of one utterance.
+
+    Restates the offset part of PulseWaveTable.stable_cumsum_and_wrap (tf_wavetable.py:470-486): velocities f0 / rate are
+    summed sequentially in float32 inside chunks of `chunk` samples, the totals are wrapped (floor-mod 1) and accumulated
+    sequentially over the chunks without wrapping.  Same association order as phase_chunk_kernel / chunk_offset_kernel.
+    """
+    v = np.asarray(f0, dtype=np.float32) / np.float32(pulse_rate)
+    n_chunks = -(-v.size // chunk)
+    pad = np.zeros(n_chunks * chunk, dtype=np.float32)
+    pad[:v.size] = v
+    totals = np.cumsum(pad.reshape(n_chunks, chunk), axis=1, dtype=np.float32)[:, -1]
+    wrapped = totals - np.floor(totals)
+    run = np.zeros(n_chunks, dtype=np.float32)
+    run[1:] = np.cumsum(wrapped, dtype=np.float32)[:-1]
+    return run
+
+
+@dataclass
+class Window:
+    start: int      # first frame of the window (multiple of `align`)
+    stop: int
+    core0: int      # first frame of the kept core
+    core1: int
+
+
+def plan_windows(n_frames: int, chunk_frames: int, context: int, align: int = 1) -> List[Window]:
+    """Cores tile [0, n_frames); every window is its core plus `context` frames per side, start rounded down to `align`."""
+    if chunk_frames <= 0:
+        raise ValueError("chunk_frames must be positive")
+    out = []
+    for c0 in range(0, n_frames, chunk_frames):
+        c1 = min(n_frames, c0 + chunk_frames)
+        s = max(0, c0 - context)
+        s -= s % align
+        out.append(Window(s, min(n_frames, c1 + context), c0, c1))
+    return out
+
+
+def _batches(windows: Sequence[Window], max_batch_frames: int) -> List[List[int]]:
+    groups, cur, frames = [], [], 0
+    for i, w in enumerate(windows):
+        n = w.stop - w.start
+        if cur and frames + n > max_batch_frames:
+            groups.append(cur)
+            cur, frames = [], 0
+        cur.append(i)
+        frames += n
+    if cur:
+        groups.append(cur)
+    return groups
+
+
+def synth_long(engine, mel: np.ndarray, noise: np.ndarray, chunk_frames: int = 400, precision: str = "f16f8",
+               max_batch_frames: int = 32768, first_alone: bool = True) -> Tuple[np.ndarray, Dict[str, float]]:
+    """mel (T, n_mel), noise (T * steps_per_frame,) standard normal -> waveform (T * hop,), timing info.
+
+    `first_alone`: the first window is synthesised in a call of its own (first-chunk latency of a streaming client)."""
+    plan: ModelPlan = engine.plan
+    mel = np.ascontiguousarray(mel, dtype=np.float32)
+    T = mel.shape[0]
+    ppf, spf, hop = plan.pulse_per_frame, plan.steps_per_frame, plan.hop
+    noise = np.asarray(noise, dtype=np.float32).reshape(-1)
+    if noise.size != T * spf:
+        raise RuntimeError(f"noise must hold {T * spf} draws, got {noise.size}")
+    chunk = int(engine.cfg.cumsum_chunk)
+    if chunk % ppf:
+        raise NotImplementedError("cumsum chunk is not a whole number of frames")
+    align = chunk // ppf
+    info: Dict[str, float] = {}
+    t0 = time.perf_counter()
+
+    # ---- pass 1: exact F0 of the whole signal ----------------------------------------------------------------
+    f0_ctx = subnet_reach_frames(plan.pp_ops)
+    f0_full = np.empty(T * ppf, dtype=np.float32)
+    wins = plan_windows(T, max(chunk_frames, 4 * f0_ctx), f0_ctx)
+    engine.set_option("stop_after_f0", 1)
+    try:
+        for grp in _batches(wins, max_batch_frames):
+            pb = engine.prepare([wins[i].stop - wins[i].start for i in grp], precision, with_noise=False)
+            pb.load([mel[wins[i].start:wins[i].stop] for i in grp])
+            pb.upload()
+            pb.run_device()
+            for i, x in zip(grp, pb.tap("F0")):
+                w = wins[i]
+                f0_full[w.core0 * ppf:w.core1 * ppf] = x[(w.core0 - w.start) * ppf:(w.core1 - w.start) * ppf]
+    finally:
+        engine.set_option("stop_after_f0", 0)
+    info["f0_pass_s"] = time.perf_counter() - t0
+
+    # ---- pass 2: phase carry per cumsum chunk ------------------------------------------------------------------
+    run = phase_run_before_chunks(f0_full, plan.pulse_rate, chunk)
+
+    # ---- pass 3: the windows ----------------------------------------------------------------------------------
+    ctx = main_context_frames(plan)
+    wins = plan_windows(T, chunk_frames, ctx, align)
+    out = np.empty(T * hop, dtype=np.float32)
+    groups = _batches(wins, max_batch_frames)
+    if first_alone and len(wins) > 1 and len(groups[0]) > 1:
+        groups = [[0]] + _batches(wins[1:], max_batch_frames)
+        groups = [groups[0]] + [[i + 1 for i in g] for g in groups[1:]]
+    t1 = time.perf_counter()
+    for gi, grp in enumerate(groups):
+        pb = engine.prepare([wins[i].stop - wins[i].start for i in grp], precision, with_noise=True, with_f0=True,
+                            with_carry=True)
+        pb.load([mel[wins[i].start:wins[i].stop] for i in grp],
+                noise=[noise[wins[i].start * spf:wins[i].stop * spf] for i in grp],
+                f0=[f0_full[wins[i].start * ppf:wins[i].stop * ppf] for i in grp],
+                carry=[run[wins[i].start // align] for i in grp])
+        pb.run_host()
+        for i, y in zip(grp, pb.waveforms()):
+            w = wins[i]
+            out[w.core0 * hop:w.core1 * hop] = y[(w.core0 - w.start) * hop:(w.core1 - w.start) * hop]
+        if gi == 0:
+            info["first_chunk_latency_s"] = time.perf_counter() - t0
+    info["main_pass_s"] = time.perf_counter() - t1
+    info["total_s"] = time.perf_counter() - t0
+    info["audio_s"] = T * hop / plan.sample_rate
+    info["n_windows"] = len(wins)
+    info["context_frames"] = ctx
+    return out, info

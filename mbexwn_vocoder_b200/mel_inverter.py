@@ -134,6 +134,25 @@ class MELInverter(object):
                                      precision=self.precision, seed=self.seed if seed is None else seed, taps=taps)
         return (out, tp) if taps else out
 
+    def synth_long_from_mel(self, scaled_mell, noise=None, chunk_frames: int = 400, max_batch_frames: int = 32768,
+                            seed: Optional[int] = None, return_info: bool = False):
+        """One long (T, n_mel) or (1, T, n_mel) mel -> flat waveform, synthesised in windows of `chunk_frames` frames with
+        receptive-field overlap and a carried pulse phase (long_form.py).  Equal to synth_from_mel on the same input, with
+        device memory bounded by `max_batch_frames` instead of T."""
+        from .long_form import synth_long
+        mel = np.asarray(scaled_mell, dtype=np.float32)
+        if mel.ndim == 3:
+            if mel.shape[0] != 1:
+                raise RuntimeError("synth_long_from_mel takes one utterance")
+            mel = mel[0]
+        if mel.ndim != 2 or mel.shape[1] != self.mel_channels:
+            raise RuntimeError(f"expected a (frames, {self.mel_channels}) mel spectrogram, got {mel.shape}")
+        if noise is None:
+            rng = np.random.default_rng(self.seed if seed is None else seed)
+            noise = rng.standard_normal(mel.shape[0] * self.plan.steps_per_frame, dtype=np.float32)
+        out, info = synth_long(self.model, mel, np.asarray(noise).reshape(-1), chunk_frames, self.precision, max_batch_frames)
+        return (out, info) if return_info else out
+
     def generate_mel_from_snd(self, snd, srate):
         raise NotImplementedError("audio -> mel analysis is outside the B200 hot path (SURVEY.md 8f-2)")
 

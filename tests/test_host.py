@@ -258,3 +258,55 @@ def test_two_rank_sharding_and_gather_gloo(tmp_path):
     outs = [p.communicate(timeout=120) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert outs[0][0].startswith("OK")
+
+
+# ---- chunked long-form synthesis: host logic (long_form.py) -----------------------------------------------------
+def test_long_form_windows_tile_the_signal():
+    from mbexwn_vocoder_b200.long_form import plan_windows
+    for T, chunk, ctx, align in [(173, 40, 17, 10), (48000, 400, 23, 10), (5, 400, 23, 10), (400, 400, 23, 10)]:
+        wins = plan_windows(T, chunk, ctx, align)
+        assert wins[0].core0 == 0 and wins[-1].core1 == T
+        for a, b in zip(wins, wins[1:]):
+            assert a.core1 == b.core0
+        for w in wins:
+            assert w.start % align == 0 and 0 <= w.start <= w.core0 < w.core1 <= w.stop <= T
+            assert w.core0 - w.start >= min(ctx, w.core0) and w.stop - w.core1 >= min(ctx, T - w.core1)
+
+
+def test_phase_carry_restates_the_reference_offsets(speech_setup):
+    """phase_run_before_chunks continues stable_cumsum_and_wrap (tf_wavetable.py:429-492) across a cut on a chunk boundary:
+    the oracle phase of a whole utterance equals the phase of its tail computed with the carried running sum."""
+    import torch
+    from mbexwn_vocoder_b200.long_form import phase_run_before_chunks
+    from oracle.forward import OracleMBExWN
+    hp, plan, w = speech_setup
+    orc = OracleMBExWN(hp, w, torch.float32)
+    n, cut = 7300, 3000
+    rng = np.random.default_rng(3)
+    f0 = (80.0 + 400.0 * rng.random(n)).astype(np.float32)
+    v = (f0 / np.float32(plan.pulse_rate))[None]
+    whole = orc.stable_cumsum_and_wrap(v)[0]
+    run = phase_run_before_chunks(f0, plan.pulse_rate, 1000)
+    assert run.shape == (8,) and run[0] == 0
+    # tail alone: in-chunk cumsum + (carry + running sum of its own wrapped totals), wrapped like the reference
+    tail = np.zeros(5000, dtype=np.float32)
+    tail[:n - cut] = v[0, cut:]
+    cum = np.cumsum(tail.reshape(5, 1000), axis=1, dtype=np.float32)
+    tot = np.mod(cum[:, -1], np.float32(1))
+    offs = np.empty(5, dtype=np.float32)
+    acc = run[cut // 1000]
+    for j in range(5):
+        offs[j] = acc
+        acc = np.float32(acc + tot[j])
+    phase = np.mod(cum + np.mod(offs, np.float32(1))[:, None], np.float32(1)).reshape(-1)[:n - cut]
+    assert np.array_equal(phase, whole[cut:])
+
+
+def test_long_form_context_covers_the_receptive_field(speech_setup):
+    from mbexwn_vocoder_b200.long_form import main_context_frames, subnet_reach_frames
+    hp, plan, w = speech_setup
+    wn = plan.wavenet
+    ctx = main_context_frames(plan)
+    assert ctx * wn.steps_per_frame >= sum(d * (wn.k - 1) // 2 for d in wn.dilations) + plan.pqmf_q
+    assert ctx >= subnet_reach_frames(plan.ps_ops) and ctx * plan.hop >= plan.stft_win
+    assert subnet_reach_frames(plan.pp_ops) >= 2
