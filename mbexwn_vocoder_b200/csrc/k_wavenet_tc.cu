@@ -68,6 +68,13 @@ constexpr int COND_BYTES = COND_ROWS * COND_LD * 4;
 constexpr int MAX_LIN_UP = 32;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)RING_BYTES + 512 + 2 * COND_BYTES;
 static_assert(SMEM_BYTES <= 232448, "dynamic shared memory budget (227 KB)");
+// Gate kernel with CTA pairs: the activations leave through TMA stores from two 32 KB staging buffers (64 channels x 128
+// rows: one 16 KB tile of the fp16 / bf16-hi plane + one 16 KB tile of the [lo8 | hi8] / bf16-lo plane, SWIZZLE_128B like the
+// operand tiles); the operand ring shrinks to 4 + 4 slots to make room.
+constexpr int RING_BYTES_TMA_OUT = 128 * 1024;
+constexpr int OUT_STAGE_BYTES = 2 * TILE_M * 128;
+static_assert(1024 + RING_BYTES_TMA_OUT + 512 + 2 * COND_BYTES + 2 * OUT_STAGE_BYTES <= 232448, "smem budget of the gate kernel");
+static_assert((RING_BYTES_TMA_OUT + 512 + 2 * COND_BYTES) % 1024 == 0, "staging tiles need 1024-byte alignment");
 
 enum Epi { EPI_PLAIN = 0, EPI_GATE = 1, EPI_RESSKIP = 2, EPI_CONV = 3 };
 
@@ -80,6 +87,7 @@ struct KBlock {
 struct alignas(64) GemmParams {
     CUtensorMap tm_a;
     CUtensorMap tm_b;
+    CUtensorMap tm_out;     // EPI_GATE with CTA pairs: the activation buffer (same geometry as tm_a of the res/skip GEMM)
     KBlock kb[MAX_KB];
     int n_kb;
     int n_terms;            // 1: hi*hi;  3: hi*hi + lo*hi + hi*lo, the lo planes sit a_lo_off / b_lo_off columns further;
@@ -122,7 +130,8 @@ struct alignas(64) GemmParams {
     int first;              // skip = instead of +=
     FrameGrid grid;
     int debug;              // timing experiments only (option "tc_debug"): 1 = epilogues skip their math and stores,
-                            // 2 = every tile loads the operands of tile 0 (L2-resident feed), 4 = no MMAs are issued
+                            // 2 = every tile loads the operands of tile 0 (L2-resident feed), 4 = no MMAs are issued,
+                            // 8 = epilogues skip their global stores, 16 = no gate math, 32 = res/skip does not read h
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -174,6 +183,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar
         ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"((uint64_t)tm), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -476,9 +493,12 @@ __device__ __forceinline__ void gate_stage_fill(const GemmParams& p, float* buf,
 // FMAs per value on top of the accumulator (z + c0 w0 + c1 w1; the reference rounds c0 w0 + c1 w1 first -- a difference of
 // one fp32 ulp of the conditioning, far inside the tolerance of the split-precision GEMM that produced z).
 // STAGED: conditioning rows (+ bias) come from the shared-memory stage `buf`; otherwise straight from global memory.
-template <bool STAGED>
+// TMA_OUT: the 16 epilogue warps fill a 64-channel x 128-row staging buffer per iteration (warp part p owns the 16-channel
+// chunk p of the block), meet at a named barrier, and one thread hands the two tiles to the TMA; `blk_it` counts the blocks of
+// this CTA so far (staging buffer = blk_it & 1).  Without it every thread stores its own row pieces straight to global memory.
+template <bool STAGED, bool TMA_OUT>
 __device__ __forceinline__ void epi_gate(const GemmParams& p, const float* buf, uint32_t tacc, int row, int m0,
-                                         int n0, int width, int part, int nparts) {
+                                         int n0, int width, int part, int nparts, uint8_t* out_stage, uint32_t& blk_it) {
     const int hw = width >> 1;
     const int ch_tile = n0 >> 1;
     const bool in_range = row < (int)p.rows;                     // the TMEM loads are warp-collective: no early exit
@@ -512,12 +532,15 @@ __device__ __forceinline__ void epi_gate(const GemmParams& p, const float* buf, 
         tmem_ld16(tacc + q * 16, zt);
         tmem_ld16(tacc + hw + q * 16, zs);
         tmem_ld_wait();
-        if (!in_range) continue;
         const int ch0 = ch_tile + q * 16;
 #pragma unroll
         for (int i = 0; i < 16; i += 8) {
+            if (!in_range) break;                                  // rows past the end: nothing to store (the TMA clips them)
             float a[8];
-            if (valid) {
+            if (p.debug & 16) {                                    // timing experiment: no gate math
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] = zt[i + e] + zs[i + e];
+            } else if (valid) {
 #pragma unroll
                 for (int v4 = 0; v4 < 2; ++v4) {
                     const int col = q * 16 + i + 4 * v4;
@@ -556,7 +579,34 @@ __device__ __forceinline__ void epi_gate(const GemmParams& p, const float* buf, 
                 for (int e = 0; e < 8; ++e) a[e] = 0.f;              // guard rows stay zero
             }
             __nv_bfloat16* dst = arow + ch0 + i;
-            if (p.out_f16f8) {
+            if (TMA_OUT) {
+                // staging tiles, SWIZZLE_128B: 16-byte chunk c of row r sits at r * 128 + ((c ^ (r & 7)) << 4)
+                const int r = row - m0, cq = q & 3, sw = r & 7;
+                uint8_t* t_hi = out_stage + (blk_it & 1) * OUT_STAGE_BYTES + r * 128;
+                uint8_t* t_lo = t_hi + TILE_M * 128;
+                if (p.out_f16f8) {
+                    uint4 h16;
+                    uint2 l8, h8;
+                    split_f16f8(a, p.out_lo_scale, h16, l8, h8);
+                    *reinterpret_cast<uint4*>(t_hi + (((2 * cq + (i >> 3)) ^ sw) << 4)) = h16;
+                    *reinterpret_cast<uint2*>(t_lo + ((cq ^ sw) << 4) + i) = l8;                 // lo8: bytes 0 .. 63 of the row
+                    *reinterpret_cast<uint2*>(t_lo + (((4 + cq) ^ sw) << 4) + i) = h8;           // hi8: bytes 64 .. 127
+                } else {
+                    uint32_t hw4[4], lw4[4];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        __nv_bfloat16 h0, l0, h1, l1;
+                        split_bf16(a[e], h0, l0);
+                        split_bf16(a[e + 1], h1, l1);
+                        hw4[e / 2] = pack2(h0, h1);
+                        lw4[e / 2] = pack2(l0, l1);
+                    }
+                    *reinterpret_cast<uint4*>(t_hi + (((2 * cq + (i >> 3)) ^ sw) << 4)) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
+                    *reinterpret_cast<uint4*>(t_lo + (((2 * cq + (i >> 3)) ^ sw) << 4)) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
+                }
+            } else if (p.debug & 8) {                              // timing experiment: no global stores
+                if (a[0] + a[1] + a[2] + a[3] + a[4] + a[5] + a[6] + a[7] == 123.456f) *reinterpret_cast<float*>(dst) = a[0];
+            } else if (p.out_f16f8) {
                 uint4 h16;
                 uint2 l8, h8;
                 split_f16f8(a, p.out_lo_scale, h16, l8, h8);
@@ -577,6 +627,22 @@ __device__ __forceinline__ void epi_gate(const GemmParams& p, const float* buf, 
                 *reinterpret_cast<uint4*>(dst) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
                 if (p.write_lo) *reinterpret_cast<uint4*>(dst + p.cpad) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
             }
+        }
+        if (TMA_OUT) {
+            // block (q / 4) of the tile is complete once all 16 warps have written their chunk.  The issuing thread first
+            // makes sure the stores it issued earlier have finished reading the *other* buffer (it is written next).
+            const bool issuer = threadIdx.x == 128;
+            if (issuer) tma_store_wait_read();
+            fence_proxy_async();
+            asm volatile("bar.sync 2, %0;" ::"n"(512) : "memory");
+            if (issuer && !(p.debug & 8)) {
+                const uint8_t* t_hi = out_stage + (blk_it & 1) * OUT_STAGE_BYTES;
+                const int col = ch_tile + (q >> 2) * 64;
+                tma_store_2d(&p.tm_out, t_hi, col, m0);
+                if (p.out_f16f8 || p.write_lo) tma_store_2d(&p.tm_out, t_hi + TILE_M * 128, p.cpad + col, m0);
+                tma_store_commit();
+            }
+            ++blk_it;
         }
     }
 }
@@ -601,6 +667,7 @@ __device__ __forceinline__ float4 xp_read(const float* S, int r, int g) {
 
 __device__ __forceinline__ void resskip_load_old(const GemmParams& p, const ResSkipCtx& c, int q, int lane, uint4 (&old)[8]) {
     const int n = c.n0 + q * 32;
+    if (p.debug & 32) return;                                      // timing experiment: no read of the old values
     if (q >= c.width / 32 || n >= p.n_cols) return;
     if (n < p.res_cols) {
         const int rr = lane >> 2, cg = lane & 3;
@@ -634,6 +701,7 @@ __device__ __forceinline__ void resskip_store(const GemmParams& p, const ResSkip
                                               const uint4 (&old)[8]) {
     const int n = c.n0 + q * 32;
     if (n >= p.n_cols) return;
+    if (p.debug & 8) return;                                       // timing experiment: no stores
     if (n < p.res_cols) {
         // residual stream: h <- h + rs, kept as a bf16 (hi, lo) pair (guard rows stay zero: never written)
         const int rr = lane >> 2, cg = lane & 3;
@@ -749,10 +817,12 @@ template <int EPI, int CG>
 __global__ void __launch_bounds__(tc_threads(EPI), 1)
 wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     constexpr int EW = epi_warps(EPI), ET = 32 * EW, NPARTS = EW / 4;
+    constexpr bool TMA_OUT = EPI == EPI_GATE && CG == 2;
+    constexpr int RB = TMA_OUT ? RING_BYTES_TMA_OUT : RING_BYTES;
     constexpr int B_BYTES = (TILE_N / CG) * TILE_K * 2;
-    constexpr int NA = CG == 1 ? 4 : 6;
-    constexpr int NB = CG == 1 ? 4 : 6;
-    static_assert(NA * A_BYTES + NB * B_BYTES <= RING_BYTES && NA <= MAX_RING && NB <= MAX_RING, "ring sizes");
+    constexpr int NA = CG == 1 ? 4 : (TMA_OUT ? 4 : 6);
+    constexpr int NB = CG == 1 ? 4 : (TMA_OUT ? 4 : 6);
+    static_assert(NA * A_BYTES + NB * B_BYTES <= RB && NA <= MAX_RING && NB <= MAX_RING, "ring sizes");
     // K-major SWIZZLE_128B smem matrix descriptor without the address field: LBO = 1 (ignored), SBO = 1024 B between
     // 8-row groups, descriptor version 1 (Blackwell), swizzle mode 2 (128 B)
     constexpr uint64_t DESC_HI = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -762,14 +832,15 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* ring_a = smem;
     uint8_t* ring_b = smem + NA * A_BYTES;
-    uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + RING_BYTES);
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + RB);
     uint64_t* empty_a = full_a + MAX_RING;
     uint64_t* full_b = empty_a + MAX_RING;
     uint64_t* empty_b = full_b + MAX_RING;
     uint64_t* tmem_full = empty_b + MAX_RING;
     uint64_t* tmem_empty = tmem_full + ACC_STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
-    float* cond_stage = reinterpret_cast<float*>(smem + RING_BYTES + 512);
+    float* cond_stage = reinterpret_cast<float*>(smem + RB + 512);
+    uint8_t* out_stage = smem + RB + 512 + 2 * COND_BYTES;          // TMA_OUT only
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform role index
     const int lane = threadIdx.x & 31;
@@ -799,6 +870,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     if (warp == 0 && elect_one()) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_b) : "memory");
+        if (TMA_OUT) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_out) : "memory");
     }
     if (warp == 1 && elect_one()) {
         // full barriers: one arrival (the leader's expect_tx for the bytes of *all* CTAs of the group); a peer CTA's
@@ -1028,7 +1100,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
         MBX_REG_INC();
         const int q4 = warp & 3, part = (warp - 4) >> 2;
         const bool staged = EPI == EPI_GATE && p.cond_rows > 0;
-        uint32_t tile_it = 0;
+        uint32_t tile_it = 0, blk_it = 0;
         for (int j = 0; j < n_seq; ++j, ++tile_it) {
             int m_grp, n_blk;
             tile_of(j, m_grp, n_blk);
@@ -1056,8 +1128,8 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
             if (EPI == EPI_PLAIN) epi_plain(p, tacc, row, n_blk * TILE_N, width, part, NPARTS);
             if (EPI == EPI_CONV) epi_conv(p, tacc, row, n_blk * TILE_N, width, part, NPARTS);
             if (EPI == EPI_GATE) {
-                if (staged) epi_gate<true>(p, cond_stage + (tile_it & 1) * (COND_ROWS * COND_LD), tacc, (int)row, (int)m0, n_blk * TILE_N, width, part, NPARTS);
-                else epi_gate<false>(p, nullptr, tacc, (int)row, (int)m0, n_blk * TILE_N, width, part, NPARTS);
+                if (staged) epi_gate<true, TMA_OUT>(p, cond_stage + (tile_it & 1) * (COND_ROWS * COND_LD), tacc, (int)row, (int)m0, n_blk * TILE_N, width, part, NPARTS, out_stage, blk_it);
+                else epi_gate<false, TMA_OUT>(p, nullptr, tacc, (int)row, (int)m0, n_blk * TILE_N, width, part, NPARTS, out_stage, blk_it);
             }
             if (EPI == EPI_RESSKIP) epi_resskip(p, rctx, tacc, lane, cond_stage + (warp - 4) * 1024, old);
             tc_fence_before();
@@ -1067,6 +1139,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                 else mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));
             }
         }
+        if (TMA_OUT && threadIdx.x == 128) tma_store_wait_all();     // the staging buffers and the writes outlive the loop
     } else if (warp == 2) {
         MBX_REG_DEC();
     } else if (warp == 3) {
@@ -1401,6 +1474,7 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
 
         GemmParams p1{};
         p1.tm_a = tm_h;
+        p1.tm_out = tm_a;
         if ((rc = make_map(im, &p1.tm_b, w1, n1, k1, TILE_N, error))) return rc;
         int shifts[16];
         for (int t = 0; t < c.wn_k; ++t) shifts[t] = (t - (c.wn_k - 1) / 2) * d;
