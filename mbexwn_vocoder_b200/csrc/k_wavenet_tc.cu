@@ -60,8 +60,10 @@ constexpr int MAX_KB = 64;
 // Epilogue warps: `parts` warps per TMEM lane quarter splitting the columns of a tile.  The gate epilogue is the long one
 // (54 -> ~25 instructions per output and latency bound), so it gets 16 warps (4 per scheduler) and the register budget
 // is moved from the producer / MMA warps to them with setmaxnreg; the other epilogues keep 8 warps.
-__host__ __device__ constexpr int epi_warps(int epi) { return epi == 1 /* EPI_GATE */ ? 16 : 8; }
-__host__ __device__ constexpr int tc_threads(int epi) { return 128 + 32 * epi_warps(epi); }
+__host__ __device__ constexpr int epi_warps(int epi, int cg) {
+    return epi == 1 /* EPI_GATE */ || (epi == 2 /* EPI_RESSKIP */ && cg == 2) ? 16 : 8;
+}
+__host__ __device__ constexpr int tc_threads(int epi, int cg) { return 128 + 32 * epi_warps(epi, cg); }
 constexpr int COND_ROWS = 16;                           // staged conditioning rows per tile (<= 15 used at lin_up = 10)
 constexpr int COND_LD = TILE_N + 4;                     // floats per staged row: consecutive rows shift by 4 banks
 constexpr int COND_BYTES = COND_ROWS * COND_LD * 4;
@@ -71,6 +73,11 @@ static_assert(SMEM_BYTES <= 232448, "dynamic shared memory budget (227 KB)");
 // Gate kernel with CTA pairs: the activations leave through TMA stores from two 32 KB staging buffers (64 channels x 128
 // rows: one 16 KB tile of the fp16 / bf16-hi plane + one 16 KB tile of the [lo8 | hi8] / bf16-lo plane, SWIZZLE_128B like the
 // operand tiles); the operand ring shrinks to 4 + 4 slots to make room.
+// Res/skip kernel with CTA pairs: the read-modify-write of the residual stream runs through three such staging buffers --
+// warp 3 TMA-loads the old 64-channel block, the 16 epilogue warps update it in place, one thread TMA-stores it.
+constexpr int RS_STAGES = 3;
+constexpr int RS_STAGE_OFF = 129 * 1024;                 // ring (128 KB) + barriers, rounded up to 1024
+static_assert(1024 + RS_STAGE_OFF + RS_STAGES * 2 * TILE_M * 128 <= 232448, "smem budget of the res/skip kernel");
 constexpr int RING_BYTES_TMA_OUT = 128 * 1024;
 constexpr int OUT_STAGE_BYTES = 2 * TILE_M * 128;
 static_assert(1024 + RING_BYTES_TMA_OUT + 512 + 2 * COND_BYTES + 2 * OUT_STAGE_BYTES <= 232448, "smem budget of the gate kernel");
@@ -805,6 +812,119 @@ __device__ __forceinline__ void epi_resskip(const GemmParams& p, const ResSkipCt
     }
 }
 
+// Res/skip epilogue of the CTA-pair kernel: 16 warps, 16-column chunks (warp part p owns chunk p of every 64-channel block).
+// Residual blocks are updated inside the staging buffer the TMA filled with the old values (SWIZZLE_128B: 16-byte chunk c
+// of row r sits at r * 128 + ((c ^ (r & 7)) << 4)), then stored back by the TMA; guard rows are left untouched (zeros).
+// The WaveNet-output columns (32 fp32 per row) are accumulated straight in global memory.
+struct RsPipe {
+    uint64_t* full_h;        // [RS_STAGES] TMA load of a block has landed
+    uint64_t* empty_h;       // [RS_STAGES] the store of a block has finished reading the buffer
+    uint8_t* stage;
+    uint32_t blk;            // blocks consumed by this CTA so far
+    int pending;             // issuer thread: buffer whose store may still be reading, or -1
+};
+
+__device__ __forceinline__ void epi_resskip_tma(const GemmParams& p, RsPipe& rp, uint32_t tacc, int row, int m0, int n0, int width,
+                                                int part, int nparts) {
+    const bool in_range = row < (int)p.rows;
+    bool valid = false;
+    if (in_range) valid = p.grid.frame_utt[row / p.steps_per_frame] >= 0;
+    const bool issuer = threadIdx.x == 128;
+    float v[16];
+#pragma unroll 1
+    for (int q = part; q < width / 16; q += nparts) {
+        const int n = n0 + q * 16;
+        tmem_ld16(tacc + q * 16, v);
+        if (n < p.res_cols) {
+            const uint32_t buf = rp.blk % RS_STAGES, ph = (rp.blk / RS_STAGES) & 1;
+            mbar_wait(&rp.full_h[buf], ph);
+            tmem_ld_wait();
+            if (valid && !(p.debug & 8)) {
+                const int r = row - m0, cq = q & 3, sw = r & 7;
+                uint8_t* t_hi = rp.stage + buf * OUT_STAGE_BYTES + r * 128;
+                uint8_t* t_lo = t_hi + TILE_M * 128;
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + 1);
+                const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + 2), b3 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + 3);
+                const float bv[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+#pragma unroll
+                for (int i = 0; i < 16; i += 8) {
+                    uint4* ph16 = reinterpret_cast<uint4*>(t_hi + (((2 * cq + (i >> 3)) ^ sw) << 4));
+                    float prev[8], o[8];
+                    if (p.out_f16f8) {
+                        uint2* pl8 = reinterpret_cast<uint2*>(t_lo + ((cq ^ sw) << 4) + i);
+                        join_f16f8(*ph16, *pl8, p.in_lo_inv, prev);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = (n + i + e < p.c) ? prev[e] + (v[i + e] + bv[i + e]) : 0.f;
+                        uint4 h16;
+                        uint2 l8, h8;
+                        split_f16f8(o, p.out_lo_scale, h16, l8, h8);
+                        *ph16 = h16;
+                        *pl8 = l8;
+                        *reinterpret_cast<uint2*>(t_lo + (((4 + cq) ^ sw) << 4) + i) = h8;
+                    } else {
+                        uint4* plo = reinterpret_cast<uint4*>(t_lo + (((2 * cq + (i >> 3)) ^ sw) << 4));
+                        const uint4 oh = *ph16, ol = *plo;
+                        const uint32_t hw[4] = {oh.x, oh.y, oh.z, oh.w}, lw[4] = {ol.x, ol.y, ol.z, ol.w};
+                        uint32_t nh[4], nl[4];
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            float x[2];
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int idx = 2 * w + e;
+                                const float pv = __bfloat162float(__ushort_as_bfloat16((unsigned short)(hw[w] >> (16 * e)))) +
+                                                 __bfloat162float(__ushort_as_bfloat16((unsigned short)(lw[w] >> (16 * e))));
+                                x[e] = (n + i + idx < p.c) ? pv + (v[i + idx] + bv[i + idx]) : 0.f;
+                            }
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            split_bf16(x[0], h0, l0);
+                            split_bf16(x[1], h1, l1);
+                            nh[w] = pack2(h0, h1);
+                            nl[w] = pack2(l0, l1);
+                        }
+                        *ph16 = make_uint4(nh[0], nh[1], nh[2], nh[3]);
+                        *plo = make_uint4(nl[0], nl[1], nl[2], nl[3]);
+                    }
+                }
+            }
+            // the block is complete once all 16 warps have updated their chunk.  Before the barrier the issuing thread retires
+            // the previous store (it has long finished reading) and hands that buffer back to the loader.
+            if (issuer && rp.pending >= 0) {
+                tma_store_wait_read();
+                mbar_arrive(&rp.empty_h[rp.pending]);
+                rp.pending = -1;
+            }
+            fence_proxy_async();
+            asm volatile("bar.sync 2, %0;" ::"n"(512) : "memory");
+            if (issuer) {
+                const uint8_t* t_hi = rp.stage + buf * OUT_STAGE_BYTES;
+                const int col = n0 + (q >> 2) * 64;
+                tma_store_2d(&p.tm_out, t_hi, col, m0);
+                tma_store_2d(&p.tm_out, t_hi + TILE_M * 128, p.cpad + col, m0);
+                tma_store_commit();
+                rp.pending = (int)buf;
+            }
+            ++rp.blk;
+        } else {
+            tmem_ld_wait();
+            const int sc = n - p.res_cols;                       // 16 consecutive WaveNet-output channels of this row
+            if (valid && sc < p.skip_c && !(p.debug & 8)) {
+                float* dst = p.skip + (long long)row * p.skip_ld + sc;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                    float4 nv = make_float4(v[i] + b4.x, v[i + 1] + b4.y, v[i + 2] + b4.z, v[i + 3] + b4.w);
+                    if (!p.first) {
+                        const float4 ov = *reinterpret_cast<const float4*>(dst + i);
+                        nv.x += ov.x; nv.y += ov.y; nv.z += ov.z; nv.w += ov.w;
+                    }
+                    *reinterpret_cast<float4*>(dst + i) = nv;
+                }
+            }
+        }
+    }
+}
+
 // Operand-ring pipeline.  A tiles (128 rows x 64 K) and B tiles (the CTA's share of the N rows x 64 K) travel through
 // two independent smem rings, each slot with its own full/empty mbarrier pair, so an operand that several products
 // need is loaded once: per K block the split precision issues hi*hi, lo*hi, hi*lo from {A_hi, A_lo, B_hi, B_lo}
@@ -814,14 +934,15 @@ __device__ __forceinline__ void epi_resskip(const GemmParams& p, const ResSkipCt
 // loads its own 128 rows of A and *half* of the B rows, the leader issues M = 256 MMAs that read both halves, each CTA
 // keeps the accumulators of its own rows in its own TMEM and runs its own epilogue.  Halves the per-SM ingest of B.
 template <int EPI, int CG>
-__global__ void __launch_bounds__(tc_threads(EPI), 1)
+__global__ void __launch_bounds__(tc_threads(EPI, CG), 1)
 wn_gemm_kernel(const __grid_constant__ GemmParams p) {
-    constexpr int EW = epi_warps(EPI), ET = 32 * EW, NPARTS = EW / 4;
+    constexpr int EW = epi_warps(EPI, CG), ET = 32 * EW, NPARTS = EW / 4;
     constexpr bool TMA_OUT = EPI == EPI_GATE && CG == 2;
-    constexpr int RB = TMA_OUT ? RING_BYTES_TMA_OUT : RING_BYTES;
+    constexpr bool TMA_RS = EPI == EPI_RESSKIP && CG == 2;
+    constexpr int RB = (TMA_OUT || TMA_RS) ? RING_BYTES_TMA_OUT : RING_BYTES;
     constexpr int B_BYTES = (TILE_N / CG) * TILE_K * 2;
-    constexpr int NA = CG == 1 ? 4 : (TMA_OUT ? 4 : 6);
-    constexpr int NB = CG == 1 ? 4 : (TMA_OUT ? 4 : 6);
+    constexpr int NA = CG == 1 ? 4 : ((TMA_OUT || TMA_RS) ? 4 : 6);
+    constexpr int NB = CG == 1 ? 4 : ((TMA_OUT || TMA_RS) ? 4 : 6);
     static_assert(NA * A_BYTES + NB * B_BYTES <= RB && NA <= MAX_RING && NB <= MAX_RING, "ring sizes");
     // K-major SWIZZLE_128B smem matrix descriptor without the address field: LBO = 1 (ignored), SBO = 1024 B between
     // 8-row groups, descriptor version 1 (Blackwell), swizzle mode 2 (128 B)
@@ -839,6 +960,8 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     uint64_t* tmem_full = empty_b + MAX_RING;
     uint64_t* tmem_empty = tmem_full + ACC_STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+    uint64_t* full_h = tmem_empty + ACC_STAGES + 1;                 // TMA_RS only
+    uint64_t* empty_h = full_h + RS_STAGES;
     float* cond_stage = reinterpret_cast<float*>(smem + RB + 512);
     uint8_t* out_stage = smem + RB + 512 + 2 * COND_BYTES;          // TMA_OUT only
 
@@ -870,7 +993,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
     if (warp == 0 && elect_one()) {
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_b) : "memory");
-        if (TMA_OUT) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_out) : "memory");
+        if (TMA_OUT || TMA_RS) asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_out) : "memory");
     }
     if (warp == 1 && elect_one()) {
         // full barriers: one arrival (the leader's expect_tx for the bytes of *all* CTAs of the group); a peer CTA's
@@ -879,6 +1002,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
         for (int s = 0; s < NA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
         for (int s = 0; s < NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], CG * EW); }
+        if (TMA_RS) for (int s = 0; s < RS_STAGES; ++s) { mbar_init(&full_h[s], 1); mbar_init(&empty_h[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -1101,6 +1225,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
         const int q4 = warp & 3, part = (warp - 4) >> 2;
         const bool staged = EPI == EPI_GATE && p.cond_rows > 0;
         uint32_t tile_it = 0, blk_it = 0;
+        RsPipe rpipe{full_h, empty_h, smem + RS_STAGE_OFF, 0u, -1};
         for (int j = 0; j < n_seq; ++j, ++tile_it) {
             int m_grp, n_blk;
             tile_of(j, m_grp, n_blk);
@@ -1110,9 +1235,10 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
             const long long row = m0 + q4 * 32 + lane;
             int width = p.n_cols - n_blk * TILE_N;
             width = width > TILE_N ? TILE_N : ((width + 31) & ~31);
-            uint4 old[8];
+            uint4 old[TMA_RS ? 1 : 8];
             ResSkipCtx rctx;
-            if (EPI == EPI_RESSKIP) rctx = resskip_begin(p, row, n_blk * TILE_N, width, part, NPARTS, lane, old);   // loads fly during the MMAs
+            if constexpr (EPI == EPI_RESSKIP && !TMA_RS)
+                rctx = resskip_begin(p, row, n_blk * TILE_N, width, part, NPARTS, lane, old);   // loads fly during the MMAs
             if (staged) epi_bar_sync<ET + 32>();                    // warp 3 has finished this tile's stage
             mbar_wait(&tmem_full[as], aph);
             tc_fence_after();
@@ -1131,7 +1257,8 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                 if (staged) epi_gate<true, TMA_OUT>(p, cond_stage + (tile_it & 1) * (COND_ROWS * COND_LD), tacc, (int)row, (int)m0, n_blk * TILE_N, width, part, NPARTS, out_stage, blk_it);
                 else epi_gate<false, TMA_OUT>(p, nullptr, tacc, (int)row, (int)m0, n_blk * TILE_N, width, part, NPARTS, out_stage, blk_it);
             }
-            if (EPI == EPI_RESSKIP) epi_resskip(p, rctx, tacc, lane, cond_stage + (warp - 4) * 1024, old);
+            if constexpr (TMA_RS) epi_resskip_tma(p, rpipe, tacc, (int)row, (int)m0, n_blk * TILE_N, width, part, NPARTS);
+            else if constexpr (EPI == EPI_RESSKIP) epi_resskip(p, rctx, tacc, lane, cond_stage + (warp - 4) * 1024, old);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -1139,12 +1266,32 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                 else mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));
             }
         }
-        if (TMA_OUT && threadIdx.x == 128) tma_store_wait_all();     // the staging buffers and the writes outlive the loop
+        if ((TMA_OUT || TMA_RS) && threadIdx.x == 128) tma_store_wait_all();     // the staging buffers and the writes outlive the loop
     } else if (warp == 2) {
         MBX_REG_DEC();
     } else if (warp == 3) {
         // ===== conditioning stager of the gate epilogue =====
         MBX_REG_DEC();
+        if (TMA_RS && !(p.debug & 1)) {
+            // ===== loader of the old residual blocks: same block order as the epilogue warps =====
+            uint32_t hb = 0;
+            uint8_t* stage = smem + RS_STAGE_OFF;
+            for (int j = 0; j < n_seq; ++j) {
+                int m_grp, n_blk;
+                tile_of(j, m_grp, n_blk);
+                const int m0 = (m_grp * CG + (int)rank) * TILE_M, n0 = n_blk * TILE_N;
+                for (int c0 = n0; c0 < p.res_cols && c0 < n0 + TILE_N; c0 += 64, ++hb) {
+                    const uint32_t buf = hb % RS_STAGES, ph = (hb / RS_STAGES) & 1;
+                    mbar_wait(&empty_h[buf], ph ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_h[buf], OUT_STAGE_BYTES);
+                        tma_load_2d(&p.tm_out, &full_h[buf], stage + buf * OUT_STAGE_BYTES, c0, m0);
+                        tma_load_2d(&p.tm_out, &full_h[buf], stage + buf * OUT_STAGE_BYTES + TILE_M * 128, p.cpad + c0, m0);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
         if (EPI == EPI_GATE && p.cond_rows > 0) {
             for (int j = 0; j < n_seq; ++j) {
                 int m_grp, n_blk;
@@ -1355,12 +1502,12 @@ cudaError_t launch_gemm(Impl* im, GemmParams& p, cudaStream_t s) {
     if (n_tiles < groups) groups = n_tiles;
     p.sched_m_major = tiles_mg >= 8 * groups ? 1 : 0;
     if (cg == 1) {
-        wn_gemm_kernel<EPI, 1><<<groups, tc_threads(EPI), SMEM_BYTES, s>>>(p);
+        wn_gemm_kernel<EPI, 1><<<groups, tc_threads(EPI, 1), SMEM_BYTES, s>>>(p);
         return cudaGetLastError();
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(groups * 2);
-    cfg.blockDim = dim3(tc_threads(EPI));
+    cfg.blockDim = dim3(tc_threads(EPI, 2));
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -1492,6 +1639,7 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
 
         GemmParams p2{};
         p2.tm_a = tm_a;
+        p2.tm_out = tm_h;
         if ((rc = make_map(im, &p2.tm_b, w2, n2, k2, TILE_N, error))) return rc;
         int zero = 0;
         p2.n_kb = build_kblocks(p2.kb, 1, &zero, cpad);
