@@ -22,6 +22,29 @@ from .plan import build_plan
 log_to_db = 20 * np.log10(np.exp(1))            # vocoder/model/preprocess.py:78
 
 
+def resolve_weights(model_dir: str, plan, hparams: Dict, verbose: bool = False) -> Dict[str, np.ndarray]:
+    """Weights of a model directory, in this order: ``weights.npz`` (this package's container), ``weights.tf``
+    (the reference's TensorFlow checkpoint, mel_inverter.py:203-208, read without TensorFlow by tf_checkpoint.py),
+    else Keras-like random initialisation from the seed in the config (no released weights ship offline)."""
+    npz = os.path.join(model_dir, "weights.npz")
+    tf_prefix = os.path.join(model_dir, "weights.tf")
+    if os.path.exists(npz):
+        if verbose:
+            print(f"restore from {npz}", file=sys.stderr)
+        weights = W.load(npz)
+        W.check(plan, weights)
+        return weights
+    if os.path.exists(tf_prefix + ".index"):
+        from .tf_checkpoint import import_weights
+        if verbose:
+            print(f"restore from {tf_prefix}", file=sys.stderr)
+        return import_weights(tf_prefix, plan)
+    seed = int(hparams.get("synthetic_weights", {}).get("seed", 0))
+    if verbose:
+        print(f"no weights in {model_dir}: random-initialised weights, seed {seed}", file=sys.stderr)
+    return W.init_synthetic(plan, seed=seed)
+
+
 class MELInverter(object):
     def __init__(self, model_id_or_path: Union[str, None] = None, verbose: bool = False,
                  device: Union[int, str] = 0, precision: str = "fp32", seed: int = 42):
@@ -168,19 +191,7 @@ class MELInverter(object):
         self.preprocess_config = hparams["preprocess_config"]
         self.plan = build_plan(hparams)
 
-        weights_path = os.path.join(model_dir, "weights.npz")
-        if os.path.exists(weights_path):
-            if verbose:
-                print(f"restore from {weights_path}", file=sys.stderr)
-            weights = W.load(weights_path)
-        elif os.path.exists(os.path.join(model_dir, "weights.tf.index")):
-            raise NotImplementedError("TensorFlow checkpoint import is not built yet (SURVEY.md 8f-1); "
-                                      "convert the checkpoint to weights.npz")
-        else:
-            seed = int(hparams.get("synthetic_weights", {}).get("seed", 0))
-            if verbose:
-                print(f"no weights beside {config_file}: random-initialised weights, seed {seed}", file=sys.stderr)
-            weights = W.init_synthetic(self.plan, seed=seed)
+        weights = resolve_weights(model_dir, self.plan, hparams, verbose=verbose)
         self.weights = weights
         self.model = Engine(self.plan, weights, device=self.device)
 

@@ -153,3 +153,20 @@ def test_fp32_oracle_tracks_fp64_oracle(speech_setup):
     x64 = torch.as_tensor(r32["wn_in"], dtype=torch.float64)
     y64 = o64.wavenet(x64, torch.as_tensor(mel, dtype=torch.float64))
     assert np.abs(y64.numpy() - r32["wn_out"]).max() <= 2e-5 * np.abs(r32["wn_out"]).max()
+
+
+TF_GOLD = os.path.join(os.path.dirname(__file__), "golden", "tf_reference_SPEECH.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(TF_GOLD), reason="tests/golden/make_tf_reference_goldens.py has not been run "
+                    "(needs TensorFlow; the forward oracle stays 'parity unpinned' until it has)")
+def test_oracle_against_tf_reference(oracle):
+    """The restated forward against tensors produced by the unmodified TensorFlow reference on the same weights."""
+    g = np.load(TF_GOLD)
+    r = oracle.forward(g["mel"], g["noise"])
+    f0 = g["F0"].reshape(r["F0"].shape)
+    assert np.abs(r["F0"] - f0).max() <= 1e-4 * np.abs(f0).max()
+    r = oracle.forward(g["mel"], g["noise"], f0_override=f0)
+    wav = g["waveform"].reshape(r["waveform"].shape)
+    err = r["waveform"].astype(np.float64) - wav
+    assert 10 * np.log10(np.sum(wav.astype(np.float64) ** 2) / np.sum(err ** 2)) >= 60.0
