@@ -205,6 +205,47 @@ MBEXWN_API int mbexwn_k_tc_gemm_f16f8(mbexwn_handle_t h, const void* a, int64_t 
                                       int32_t n, int32_t b_k, const int32_t* kblocks, int32_t n_kb, float* out,
                                       void* cuda_stream);
 
+/* ---- analysis side: audio -> log-mel; stands in for MELInverter.generate_mel_from_snd (mel_inverter.py:156-182) ->
+ * compute_mel_spectrogram_internal (vocoder/model/preprocess.py:417-560, band_limit=None) -> calc_stft
+ * (sig_proc/spec/stft.py:14-96), and for scale_mel_spectrogram (preprocess.py:80-108) when mode != 0.
+ * Stateless (no handle): every table is a caller-owned DEVICE buffer. ---- */
+typedef struct {
+    int32_t hop, win, fft_size, n_mel;   /* fft_size must be 2048 (the scheme configuration), win <= fft_size, n_mel <= 128 */
+    int32_t mode;                /* 0: log(max(mel, floor))                                  (do_post=False, preprocess.py:543)
+                                    1: log_scale * log(mel * lin_scale + lin_off)            (preprocess.py:107)
+                                    2: log_scale * log(max(mel * lin_scale, lin_off))        (use_max_limit, preprocess.py:102) */
+    float lin_scale, lin_off, log_scale, floor;
+    const float* window;         /* (win) symmetric Hann (sig_proc/Mwindows.py:65-67,192-196) */
+    const float* twiddle;        /* (fft_size / 2, 2) exp(-2 pi i k / fft_size) */
+    const int32_t* mel_lo;       /* (n_mel) first FFT bin of each triangular band */
+    const int32_t* mel_cnt;      /* (n_mel) number of bins of each band */
+    const int32_t* mel_off;      /* (n_mel) offset of the band's weights in mel_w */
+    const float* mel_w;          /* packed band weights (librosa.filters.mel, Slaney; preprocess.py:52-74) */
+} mbexwn_analysis_config_t;
+
+typedef struct {
+    int32_t n_utt;
+    int32_t n_pairs;             /* pair_first[n_utt]: one CTA per pair of consecutive frames */
+    int32_t n_frames;            /* frame_begin[n_utt] */
+    int64_t n_samples_total;     /* samples in `audio` */
+    const int64_t* sample_begin; /* [n_utt] first sample of each utterance in `audio` */
+    const int32_t* n_samples;    /* [n_utt] >= 1 */
+    const int32_t* frame_begin;  /* [n_utt + 1] exclusive scan of n_samples / hop + 1 (stft.py:56) */
+    const int32_t* pair_first;   /* [n_utt + 1] exclusive scan of ceil(frames / 2) */
+    const float* audio;          /* utterances back to back */
+    float* mel;                  /* (n_frames, n_mel) */
+    float* mag_tap;              /* optional (n_frames, fft_size / 2 + 1) |STFT|, or NULL */
+} mbexwn_analysis_batch_t;
+
+MBEXWN_API int mbexwn_mel_analysis(const mbexwn_analysis_config_t* cfg, const mbexwn_analysis_batch_t* batch,
+                                   void* cuda_stream);
+/* Same call with HOST audio / mel buffers (pinned for asynchronous copies): H2D of the samples into batch->audio, the
+ * kernel, D2H of batch->mel, stream synchronised. */
+MBEXWN_API int mbexwn_mel_analysis_host(const mbexwn_analysis_config_t* cfg, const mbexwn_analysis_batch_t* batch,
+                                        const float* audio_host, float* mel_host, void* cuda_stream);
+/* Message of the last failed handle-less call on this thread (the analysis entry points). */
+MBEXWN_API const char* mbexwn_global_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,19 @@ class Batch(C.Structure):
                 ("phase_carry", C.c_void_p)]
 
 
+class AnalysisConfig(C.Structure):
+    _fields_ = [("hop", C.c_int32), ("win", C.c_int32), ("fft_size", C.c_int32), ("n_mel", C.c_int32),
+                ("mode", C.c_int32), ("lin_scale", C.c_float), ("lin_off", C.c_float), ("log_scale", C.c_float),
+                ("floor", C.c_float), ("window", C.c_void_p), ("twiddle", C.c_void_p), ("mel_lo", C.c_void_p),
+                ("mel_cnt", C.c_void_p), ("mel_off", C.c_void_p), ("mel_w", C.c_void_p)]
+
+
+class AnalysisBatch(C.Structure):
+    _fields_ = [("n_utt", C.c_int32), ("n_pairs", C.c_int32), ("n_frames", C.c_int32), ("n_samples_total", C.c_int64),
+                ("sample_begin", C.c_void_p), ("n_samples", C.c_void_p), ("frame_begin", C.c_void_p),
+                ("pair_first", C.c_void_p), ("audio", C.c_void_p), ("mel", C.c_void_p), ("mag_tap", C.c_void_p)]
+
+
 # every symbol include/mbexwn.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "mbexwn_abi_version": (C.c_int, []),
@@ -86,6 +99,10 @@ SYMBOLS = {
                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mbexwn_k_tc_gemm_f16f8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mbexwn_mel_analysis": (C.c_int, [C.POINTER(AnalysisConfig), C.POINTER(AnalysisBatch), C.c_void_p]),
+    "mbexwn_mel_analysis_host": (C.c_int, [C.POINTER(AnalysisConfig), C.POINTER(AnalysisBatch), C.c_void_p, C.c_void_p,
+                                           C.c_void_p]),
+    "mbexwn_global_error": (C.c_char_p, []),
     "mbexwn_k_lininterp": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Op), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
 }
@@ -121,5 +138,5 @@ _EXC = {ERR_INVALID: RuntimeError, ERR_MISSING: KeyError, ERR_CUDA: RuntimeError
 def check(lib, handle, rc: int, what: str):
     if rc == OK:
         return
-    msg = lib.mbexwn_last_error(handle).decode() if handle else ""
+    msg = lib.mbexwn_last_error(handle).decode() if handle else lib.mbexwn_global_error().decode()
     raise _EXC.get(rc, RuntimeError)(f"{what} failed ({rc}): {msg}")

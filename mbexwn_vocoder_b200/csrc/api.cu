@@ -656,4 +656,52 @@ int mbexwn_k_tc_gemm_f16f8(mbexwn_handle_t h, const void* a, int64_t rows, int32
                                       reinterpret_cast<cudaStream_t>(cuda_stream), &h->error);
 }
 
+static thread_local std::string g_error;
+
+const char* mbexwn_global_error(void) { return g_error.c_str(); }
+
+static int analysis_fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+
+int mbexwn_mel_analysis(const mbexwn_analysis_config_t* c, const mbexwn_analysis_batch_t* b, void* cuda_stream) {
+    if (!c || !b) return analysis_fail(MBEXWN_ERR_INVALID, "null config / batch");
+    if (!c->window || !c->twiddle || !c->mel_lo || !c->mel_cnt || !c->mel_off || !c->mel_w)
+        return analysis_fail(MBEXWN_ERR_INVALID, "analysis config: a table pointer is null");
+    if (b->n_utt < 0 || b->n_pairs < 0) return analysis_fail(MBEXWN_ERR_INVALID, "negative batch size");
+    if (b->n_utt == 0 || b->n_pairs == 0) return MBEXWN_OK;
+    if (!b->sample_begin || !b->n_samples || !b->frame_begin || !b->pair_first || !b->audio || !b->mel)
+        return analysis_fail(MBEXWN_ERR_INVALID, "analysis batch: a buffer pointer is null");
+    mbx::MelAnalysisArgs a{};
+    a.audio = b->audio; a.sample_begin = reinterpret_cast<const long long*>(b->sample_begin); a.n_samples = b->n_samples;
+    a.frame_begin = b->frame_begin; a.pair_first = b->pair_first; a.n_utt = b->n_utt; a.n_pairs = b->n_pairs;
+    a.window = c->window; a.twiddle = reinterpret_cast<const float2*>(c->twiddle);
+    a.mel_lo = c->mel_lo; a.mel_cnt = c->mel_cnt; a.mel_off = c->mel_off; a.mel_w = c->mel_w;
+    a.hop = c->hop; a.win = c->win; a.fft = c->fft_size; a.n_mel = c->n_mel;
+    a.mode = c->mode; a.lin_scale = c->lin_scale; a.lin_off = c->lin_off; a.log_scale = c->log_scale; a.floor = c->floor;
+    a.mel_out = b->mel; a.mag_out = b->mag_tap;
+    if (c->mode < 0 || c->mode > 2) return analysis_fail(MBEXWN_ERR_INVALID, "analysis config: mode must be 0, 1 or 2");
+    if (!mbx::mel_analysis_supported(a))
+        return analysis_fail(MBEXWN_ERR_UNSUPPORTED, "mel analysis is built for fft_size 2048, win <= 2048, n_mel <= 128");
+    cudaError_t e = mbx::launch_mel_analysis(a, reinterpret_cast<cudaStream_t>(cuda_stream));
+    if (e != cudaSuccess) return analysis_fail(MBEXWN_ERR_CUDA, std::string("mel_analysis2048_kernel: ") + cudaGetErrorString(e));
+    return MBEXWN_OK;
+}
+
+int mbexwn_mel_analysis_host(const mbexwn_analysis_config_t* c, const mbexwn_analysis_batch_t* b, const float* audio_host,
+                             float* mel_host, void* cuda_stream) {
+    if (!c || !b || !audio_host || !mel_host) return analysis_fail(MBEXWN_ERR_INVALID, "null argument");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    cudaError_t e = cudaMemcpyAsync(const_cast<float*>(b->audio), audio_host, (size_t)b->n_samples_total * 4,
+                                    cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return analysis_fail(MBEXWN_ERR_CUDA, std::string("H2D audio: ") + cudaGetErrorString(e));
+    int rc = mbexwn_mel_analysis(c, b, cuda_stream);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(mel_host, b->mel, (size_t)b->n_frames * c->n_mel * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return analysis_fail(MBEXWN_ERR_CUDA, std::string("D2H mel: ") + cudaGetErrorString(e));
+    return MBEXWN_OK;
+}
+
 }  // extern "C"

@@ -535,6 +535,105 @@ stft_filter2048_kernel(StftFilterArgs a, FrameGrid g) {
     }
 }
 
+// ---- analysis side: audio -> log-mel ---------------------------------------------------------------
+// compute_mel_spectrogram_internal (vocoder/model/preprocess.py:479-560) over calc_stft (sig_proc/spec/stft.py:54-94):
+// reflect-pad by (win/2, win), len/hop + 1 frames of `win` samples, symmetric Hann, zero-pad to 2048, |rfft|, mel basis,
+// log.  One CTA = two consecutive frames of one utterance carried by ONE complex FFT (frame 2p in the real part, frame
+// 2p+1 in the imaginary part, spectra separated by symmetry); the 2 x 1025 magnitudes stay in shared memory and the
+// band-compressed triangular mel basis is applied by warp-wide dot products, so HBM sees the samples once (neighbouring
+// frames overlap in L2) and 80 floats per frame on the way out.
+constexpr int MA_MAXMEL = 128;
+
+__device__ __forceinline__ int reflect_index(int s, int L) {
+    // numpy.pad(mode="reflect") of any width: periodic extension of period 2 (L - 1) without repeating the edge sample
+    if ((unsigned)s < (unsigned)L) return s;
+    if (L == 1) return 0;
+    const int period = 2 * (L - 1);
+    int r = s % period;
+    if (r < 0) r += period;
+    return r >= L ? period - r : r;
+}
+
+__global__ void __launch_bounds__(FT)
+mel_analysis2048_kernel(MelAnalysisArgs a) {
+    __shared__ float2 S[F_S1];
+    __shared__ float M[2][FN / 2 + 1];
+    __shared__ float O[2][MA_MAXMEL];
+
+    const int p = blockIdx.x, j = threadIdx.x;
+    int lo = 0, hi = a.n_utt;                              // utterance u with pair_first[u] <= p < pair_first[u + 1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(a.pair_first + mid) <= p) lo = mid; else hi = mid;
+    }
+    const int u = lo;
+    const int L = a.n_samples[u];
+    const int fbeg = a.frame_begin[u];
+    const int nfr = a.frame_begin[u + 1] - fbeg;
+    const int fr0 = 2 * (p - a.pair_first[u]);
+    const bool has2 = fr0 + 1 < nfr;
+    const float* x = a.audio + a.sample_begin[u];
+
+    float2 v[16];
+    const int s0 = fr0 * a.hop - a.win / 2;           // utterance-local sample index (an utterance holds < 2^31 samples)
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const int n = j + FT * t;
+        float re = 0.f, im = 0.f;
+        if (n < a.win) {
+            const float w = __ldg(a.window + n);
+            re = __ldg(x + reflect_index(s0 + n, L)) * w;
+            if (has2) im = __ldg(x + reflect_index(s0 + a.hop + n, L)) * w;
+        }
+        v[t] = make_float2(re, im);
+    }
+    fft2048_tail(v, S, a.twiddle, j);
+
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int k = j + FT * t;                              // t = 8 only for k = 1024 (thread 0)
+        if (t == 8 && j != 0) break;
+        const float2 zk = S[k], zn = S[(FN - k) & (FN - 1)];
+        const float2 X0 = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));        // spectrum of the real part
+        const float2 X1 = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));        // spectrum of the imag part
+        M[0][k] = sqrtf(X0.x * X0.x + X0.y * X0.y);
+        M[1][k] = sqrtf(X1.x * X1.x + X1.y * X1.y);
+    }
+    __syncthreads();
+    if (a.mag_out) {
+        for (int fr = 0; fr < (has2 ? 2 : 1); ++fr) {
+            float* dst = a.mag_out + (long long)(fbeg + fr0 + fr) * (FN / 2 + 1);
+            for (int k = j; k <= FN / 2; k += FT) dst[k] = M[fr][k];
+        }
+    }
+    // thread = band, both frames at once (one weight load feeds two FMAs); the bands are served widest first so that the
+    // 48 threads left over by n_mel = 80 sit in the warp of the narrow bands
+    for (int b = a.n_mel - 1 - j; b >= 0; b -= FT) {
+        const int blo = __ldg(a.mel_lo + b), cnt = __ldg(a.mel_cnt + b);
+        const float* w = a.mel_w + __ldg(a.mel_off + b);
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int i = 0; i < cnt; ++i) {
+            const float wi = __ldg(w + i);
+            acc0 = fmaf(M[0][blo + i], wi, acc0);
+            acc1 = fmaf(M[1][blo + i], wi, acc1);
+        }
+#pragma unroll
+        for (int fr = 0; fr < 2; ++fr) {
+            const float acc = fr ? acc1 : acc0;
+            float r;
+            if (a.mode == 0) r = logf(fmaxf(acc, a.floor));                                   // do_post=False (preprocess.py:543)
+            else if (a.mode == 1) r = a.log_scale * logf(fmaf(acc, a.lin_scale, a.lin_off));  // preprocess.py:107
+            else r = a.log_scale * logf(fmaxf(acc * a.lin_scale, a.lin_off));                 // use_max_limit, :102
+            O[fr][b] = r;
+        }
+    }
+    __syncthreads();
+    for (int i = j; i < (has2 ? 2 : 1) * a.n_mel; i += FT) {
+        const int fr = i >= a.n_mel ? 1 : 0, b = i - fr * a.n_mel;
+        a.mel_out[(long long)(fbeg + fr0 + fr) * a.n_mel + b] = O[fr][b];
+    }
+}
+
 __global__ void ola_kernel(OlaArgs a, FrameGrid g) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= (long long)a.n_frames * a.hop) return;
@@ -607,6 +706,17 @@ cudaError_t launch_ola(const OlaArgs& a, const FrameGrid& g, cudaStream_t s) {
     long long total = (long long)a.n_frames * a.hop;
     if (total <= 0) return cudaSuccess;
     ola_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, g);
+    return cudaGetLastError();
+}
+
+bool mel_analysis_supported(const MelAnalysisArgs& a) {
+    return a.fft == FN && a.win <= FN && a.win > 0 && a.hop > 0 && a.n_mel > 0 && a.n_mel <= MA_MAXMEL;
+}
+
+cudaError_t launch_mel_analysis(const MelAnalysisArgs& a, cudaStream_t s) {
+    if (a.n_pairs <= 0) return cudaSuccess;
+    if (!mel_analysis_supported(a)) return cudaErrorInvalidValue;
+    mel_analysis2048_kernel<<<a.n_pairs, FT, 0, s>>>(a);
     return cudaGetLastError();
 }
 

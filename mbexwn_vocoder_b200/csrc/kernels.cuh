@@ -139,4 +139,27 @@ struct OlaArgs {
 };
 cudaError_t launch_ola(const OlaArgs& a, const FrameGrid& g, cudaStream_t s);
 
+// audio -> log-mel (analysis side); all pointers are device pointers
+struct MelAnalysisArgs {
+    const float* audio;             // utterances back to back
+    const long long* sample_begin;  // [n_utt] first sample of each utterance in `audio`
+    const int32_t* n_samples;       // [n_utt]
+    const int32_t* frame_begin;     // [n_utt + 1] exclusive scan of n_samples / hop + 1
+    const int32_t* pair_first;      // [n_utt + 1] exclusive scan of ceil(frames / 2): one CTA per frame pair
+    int n_utt, n_pairs;
+    const float* window;            // (win) symmetric Hann of the reference's window generator
+    const float2* twiddle;          // (fft/2) exp(-2 pi i k / fft)
+    const int32_t* mel_lo;          // (n_mel) first bin of each band
+    const int32_t* mel_cnt;         // (n_mel) bins per band
+    const int32_t* mel_off;         // (n_mel) offset of the band's weights in mel_w
+    const float* mel_w;             // packed band weights
+    int hop, win, fft, n_mel;
+    int mode;                       // 0 log(max(mel, floor)); 1 log_scale log(mel lin_scale + lin_off); 2 log_scale log(max(mel lin_scale, lin_off))
+    float lin_scale, lin_off, log_scale, floor;
+    float* mel_out;                 // (frames, n_mel)
+    float* mag_out;                 // optional tap (frames, fft/2 + 1)
+};
+bool mel_analysis_supported(const MelAnalysisArgs& a);
+cudaError_t launch_mel_analysis(const MelAnalysisArgs& a, cudaStream_t s);
+
 }  // namespace mbx

@@ -388,3 +388,109 @@ def cepstral_lifters(scale: float, sample_rate: int, fmin: float, fmax: float, n
             rows.append(np.concatenate((half, np.zeros(n_ceps - 1 - (win_len // 2)))))
         grid.append(np.log10(f0))
     return np.asarray(grid, dtype=np.float32), np.asarray(rows, dtype=np.float32)
+
+
+# ---- analysis side: audio -> mel ------------------------------------------------------------------
+def cosine_window(win_type: str, winlen: int) -> np.ndarray:
+    """Symmetric 'hann' / 'hamming' window of the reference's window generator (sig_proc/Mwindows.py:61-67, 192-196):
+    the first half is a1 + a2 cos(2 pi n / (N - 1)), n <= (N - 1) // 2, mirrored onto the second half."""
+    coefs = {"hann": (0.5, -0.5), "hanning": (0.5, -0.5), "hamming": (0.54, -0.46)}
+    if win_type.lower() not in coefs:
+        raise RuntimeError("window::unsupported window type {0}".format(win_type))
+    a1, a2 = coefs[win_type.lower()]
+    win = np.zeros((winlen,))
+    mid = (winlen - 1) // 2
+    x = np.arange(mid + 1)
+    half = a1 + a2 * np.cos(2. * np.pi * x / (winlen - 1)) + 0.0 * np.cos(4. * np.pi * x / (winlen - 1)) \
+        + 0.0 * np.cos(6. * np.pi * x / (winlen - 1))
+    win[:mid + 1] = half
+    win[winlen - 1:winlen - 2 - mid:-1] = half
+    return win
+
+
+def _hz_to_mel_slaney(f):
+    """Slaney (Auditory Toolbox) mel scale = librosa hz_to_mel(htk=False): linear below 1 kHz, log above."""
+    f = np.asanyarray(f, dtype=np.float64)
+    f_sp = 200.0 / 3
+    mels = f / f_sp
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-300) / min_log_hz) / logstep, mels)
+
+
+def _mel_to_hz_slaney(m):
+    m = np.asanyarray(m, dtype=np.float64)
+    f_sp = 200.0 / 3
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def mel_filter_bank(sr: float, n_fft: int, n_mels: int, fmin: float, fmax: Optional[float],
+                    norm: bool = True, dtype=np.float32) -> np.ndarray:
+    """(n_mels, n_fft // 2 + 1) triangular mel basis as the reference builds it with ``librosa.filters.mel(sr, n_fft,
+    n_mels, fmin, fmax, htk=False, norm='slaney')`` (vocoder/model/preprocess.py:52-74, centered=False).
+
+    librosa (>= 0.8.0, requirements.txt:5) is a third-party dependency that is absent here; this is its published
+    algorithm: n_mels + 2 band edges equally spaced on the Slaney mel scale, weights
+    max(0, min((f - f_lo) / (f_c - f_lo), (f_hi - f) / (f_hi - f_c))) on the FFT bin frequencies, each triangle scaled by
+    2 / (f_hi - f_lo) (Slaney area normalisation)."""
+    if fmax is None:
+        fmax = float(sr) / 2
+    fftfreqs = np.linspace(0, float(sr) / 2, int(1 + n_fft // 2), endpoint=True)
+    mel_f = _mel_to_hz_slaney(np.linspace(_hz_to_mel_slaney(fmin), _hz_to_mel_slaney(fmax), n_mels + 2))
+    fdiff = np.diff(mel_f)
+    ramps = np.subtract.outer(mel_f, fftfreqs)
+    weights = np.zeros((n_mels, int(1 + n_fft // 2)), dtype=dtype)
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        weights[i] = np.maximum(0, np.minimum(lower, upper))
+    if norm:
+        enorm = 2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels])
+        weights *= enorm[:, np.newaxis].astype(dtype)
+    return weights
+
+
+def mel_filter_csr(basis: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+    """Band-compressed form of the mel basis for the analysis kernel: per band the first non-zero bin, the number of bins
+    up to the last non-zero one, the offset of its weights in the packed array, and the packed weights."""
+    lo, cnt, off, packed = [], [], [], []
+    for row in basis:
+        nz = np.flatnonzero(row)
+        if nz.size == 0:
+            lo.append(0), cnt.append(0), off.append(len(packed))
+            continue
+        lo.append(int(nz[0])), cnt.append(int(nz[-1] - nz[0] + 1)), off.append(len(packed))
+        packed.extend(row[nz[0]:nz[-1] + 1].tolist())
+    return (np.asarray(lo, np.int32), np.asarray(cnt, np.int32), np.asarray(off, np.int32),
+            np.asarray(packed, np.float32))
+
+
+def resample_filter(in_sr: int, out_sr: int, stop_att: float = 70, trans_width_normed: float = 0.1,
+                    dtype=np.float64) -> Tuple[np.ndarray, int, int]:
+    """Kaiser anti-aliasing FIR and the up / down factors of the reference's resampler (sig_proc/resample.py:31-63)."""
+    import math
+    from scipy import signal as ss
+    in_sr, out_sr = int(in_sr), int(out_sr)
+    gcd = math.gcd(in_sr, out_sr)
+    up, down = out_sr // gcd, in_sr // gcd
+    if stop_att >= 50:
+        beta = 0.1102 * (stop_att - 8.7)
+    elif stop_att >= 21:
+        beta = 0.5842 * pow(stop_att - 21., 0.4) + 0.07886 * (stop_att - 21.)
+    else:
+        beta = 0.
+    trans_width = 2 * np.pi * np.fmin(1., out_sr / in_sr) * trans_width_normed
+    while True:
+        radius = int(np.ceil((stop_att - 8.) / 2.285 / trans_width / 2))
+        if (2 * radius > 8000) and stop_att > 10:
+            stop_att -= 6
+        else:
+            break
+    winlen = radius * 2 + 1
+    fir = ss.firwin(winlen * up, cutoff=(1 - trans_width_normed) / max(up, down), window=("kaiser", beta))
+    return fir.astype(dtype, copy=False), up, down

@@ -69,6 +69,7 @@ class MELInverter(object):
         self.precision = precision
         self.seed = seed                        # bin/resynth_mel.py:65-67 seeds everything with 42
         self.plan = None
+        self._analyzer = None
         if model_id_or_path:
             self.load_model(model_id_or_path=model_id_or_path, verbose=verbose)
 
@@ -177,7 +178,25 @@ class MELInverter(object):
         return (out, info) if return_info else out
 
     def generate_mel_from_snd(self, snd, srate):
-        raise NotImplementedError("audio -> mel analysis is outside the B200 hot path (SURVEY.md 8f-2)")
+        """Audio -> analysis dict with the log-mel under ``mell`` (mel_inverter.py:156-182); feed it to ``scale_mel``.
+
+        The STFT / mel projection / log run on the GPU (analysis.MelAnalyzer); resampling to the model rate, when
+        needed, stays on the host like in the reference (sig_proc/resample.py)."""
+        from .analysis import MelAnalyzer, resample
+        data_dict = {'nfft': self.fft_size, 'hoplen': self.hop_size, 'winlen': self.win_len, 'nmels': self.mel_channels,
+                     'sr': self.srate, 'fmin': self.fmin, 'fmax': self.fmax, 'lin_spec_offset': self.lin_amp_off,
+                     'lin_spec_scale': self.lin_amp_scale, 'log_spec_offset': 0., 'log_spec_scale': self.mel_amp_scale,
+                     "time_axis": 1}
+        snd = np.asarray(snd)
+        if srate != self.srate:
+            snd = resample(snd, srate, self.srate, axis=-1)
+        if len(snd.shape) == 1:
+            snd = np.array(snd)[np.newaxis]
+        if self._analyzer is None:
+            self._analyzer = MelAnalyzer(self.preprocess_config, device=self.device)
+        mel_ref = self._analyzer([snd[0]], do_post=False)[0]
+        data_dict['mell'] = mel_ref.T
+        return data_dict
 
     # ------------------------------------------------------------------------------------------------
     def load_model(self, model_id_or_path, verbose=False):

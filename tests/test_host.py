@@ -169,14 +169,16 @@ def test_shared_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header_sizes():
     """sizeof() of the ctypes mirrors must equal what the C compiler sees for include/mbexwn.h."""
-    src = ('#include <stdio.h>\n#include "mbexwn.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(mbexwn_op_t), '
-           'sizeof(mbexwn_config_t), sizeof(mbexwn_batch_t));return 0;}\n')
+    src = ('#include <stdio.h>\n#include "mbexwn.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(mbexwn_op_t), '
+           'sizeof(mbexwn_config_t), sizeof(mbexwn_batch_t), sizeof(mbexwn_analysis_config_t), '
+           'sizeof(mbexwn_analysis_batch_t));return 0;}\n')
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "s.c"), "w").write(src)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")], check=True)
         out = subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout.split()
-    assert [int(x) for x in out] == [ctypes.sizeof(_cabi.Op), ctypes.sizeof(_cabi.Config), ctypes.sizeof(_cabi.Batch)]
+    assert [int(x) for x in out] == [ctypes.sizeof(_cabi.Op), ctypes.sizeof(_cabi.Config), ctypes.sizeof(_cabi.Batch),
+                                     ctypes.sizeof(_cabi.AnalysisConfig), ctypes.sizeof(_cabi.AnalysisBatch)]
 
 
 def test_no_cpu_fallback_without_gpu(speech_setup):
