@@ -65,15 +65,37 @@ def synthetic_batch(batch, frames, steps_per_frame, seed0=0):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe): NVML every 10 ms when the
+    binding is importable, else `nvidia-smi --query-gpu` every 200 ms."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.rows = []                          # [sm_mhz, sm_max_mhz, {reasons}]
         self.stop_flag = threading.Event()
+        self.source = "nvidia-smi"
 
-    def run(self):
+    def _nvml_loop(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        self.source = "nvml"
+        while not self.stop_flag.is_set():
+            sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            try:
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            self.rows.append([sm, mx, {k for k, b in bits.items() if r & b}])
+            self.stop_flag.wait(0.01)
+
+    def _smi_loop(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -81,21 +103,27 @@ class ClockSampler(threading.Thread):
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                c = [x.strip() for x in out.split(",")]
+                if len(c) >= 7 and c[0].replace(".", "").isdigit():
+                    self.rows.append([float(c[0]), float(c[1]),
+                                      {self.NAMES[i] for i in range(4) if c[3 + i].lower().startswith("active")}])
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
 
+    def run(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            self._smi_loop()
+
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 7 and r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        sm = [r[0] for r in self.rows]
+        busy = [v for v in sm if v > 0.5 * max(sm)] or sm          # idle-clock samples before / after the loop do not count
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(r[1] for r in self.rows),
+                "reasons": sorted(set().union(*[r[2] for r in self.rows])), "samples": len(self.rows), "source": self.source}
 
 
 def wavenet_flops_per_step(plan):
@@ -175,7 +203,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=None, choices=["f16f8", "bf16x3", "bf16", "fp32"],
