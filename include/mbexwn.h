@@ -35,7 +35,7 @@ extern "C" {
 #define MBEXWN_API
 #endif
 
-#define MBEXWN_ABI_VERSION 1
+#define MBEXWN_ABI_VERSION 2
 #define MBEXWN_MAX_LAYERS 64
 #define MBEXWN_MAX_OPS 32
 
@@ -100,6 +100,15 @@ typedef struct {
     /* PQMF polyphase bank (tf_preprocess.py:120-161, :208-226) */
     int32_t pqmf_q, pqmf_back;
     int32_t halo_frames;        /* guard frames between utterances */
+    /* NormMelComponents (wavegen_1d.py:578-769, model key normalize_rms_from_mell); norm_enable 0 = off.  Tensors:
+     * "norm/proj" (mel_channels) inv_enorm, or (mel_channels, norm_proj_cols) pinv(mel basis)^T when norm_proj_cols > 0;
+     * "norm/smooth_win" (norm_smooth_win); "norm/gwin" (norm_win) */
+    int32_t norm_enable, norm_iters, norm_win, norm_smooth_win, norm_proj_cols, norm_use_max_limit;
+    float norm_fact;            /* fft_size * win_size / 2 (:598) */
+    float norm_floor;           /* 1 / max_norm_fact, 0 = none (:691-692) */
+    float norm_compress_exp;    /* normalize_compressor_exp, 0 = none (:693-694) */
+    float norm_proj_scale;      /* 1 / win_norm of the pinv variant (:603, :687) */
+    float norm_lin_scale, norm_lin_off, norm_mel_scale;   /* re-scaling of the normalised mel (:725-730) */
 } mbexwn_config_t;
 
 /* One batch on the padded frame grid; all pointers are DEVICE pointers. */
@@ -158,7 +167,8 @@ MBEXWN_API int mbexwn_forward_host(mbexwn_handle_t h, const mbexwn_batch_t* batc
 /* Per-stage taps (return_F0 / return_components of PaNWaveNet.infer, custom_pulsed_generator.py:756-771, plus the
  * stage boundaries of SURVEY.md 8a): after mbexwn_forward the named intermediate lives in the workspace at
  * [*offset_bytes, *offset_bytes + *n_bytes).  Names: "F0", "phase", "index", "pulse", "wn_in", "cond", "wn_out"
- * (rows, wn_cout rounded up to 32), "skip" (fp32 variant only), "subbands", "excitation", "ceps", "frames", "vtf", "lifter_index". */
+ * (rows, wn_cout rounded up to 32), "skip" (fp32 variant only), "subbands", "excitation", "ceps", "frames", "vtf", "lifter_index";
+ * with norm_enable also "mel_norm" (frames, mel_channels), "norm_rms_a" / "norm_rms_b" (frames), "norm_gain" (frames * hop). */
 MBEXWN_API int mbexwn_tap(mbexwn_handle_t h, const char* name, int32_t n_frames, int32_t n_chunks, int32_t precision,
                size_t* offset_bytes, size_t* n_bytes);
 

@@ -9,7 +9,7 @@ import os
 
 _LIB = None
 LIB_NAME = "libmbexwn_b200.so"
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LAYERS = 64
 MAX_OPS = 32
 N_STAGES = 7
@@ -52,7 +52,12 @@ class Config(C.Structure):
                 ("wt_max_transposition", C.c_float), ("wt_grid_norm", C.c_float),
                 ("cumsum_chunk", C.c_int32),
                 ("pqmf_q", C.c_int32), ("pqmf_back", C.c_int32),
-                ("halo_frames", C.c_int32)]
+                ("halo_frames", C.c_int32),
+                ("norm_enable", C.c_int32), ("norm_iters", C.c_int32), ("norm_win", C.c_int32),
+                ("norm_smooth_win", C.c_int32), ("norm_proj_cols", C.c_int32), ("norm_use_max_limit", C.c_int32),
+                ("norm_fact", C.c_float), ("norm_floor", C.c_float), ("norm_compress_exp", C.c_float),
+                ("norm_proj_scale", C.c_float), ("norm_lin_scale", C.c_float), ("norm_lin_off", C.c_float),
+                ("norm_mel_scale", C.c_float)]
 
 
 class Batch(C.Structure):

@@ -126,6 +126,12 @@ static Workspace carve(const mbexwn_config_t& c, int64_t F, int64_t n_chunks, in
     w.add("excitation", (size_t)F * c.hop * f4);
     w.add("ceps", (size_t)F * c.n_ceps * f4);
     w.add("frames", (size_t)F * c.stft_win * f4);
+    if (c.norm_enable) {
+        w.add("mel_norm", (size_t)F * c.mel_channels * f4);
+        w.add("norm_rms_a", (size_t)F * f4);
+        w.add("norm_rms_b", (size_t)F * f4);
+        if (debug_taps) w.add("norm_gain", (size_t)F * c.hop * f4);
+    }
     return w;
 }
 
@@ -360,12 +366,29 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
     auto mark = [&]() { if (h->stage_timing) cudaEventRecord(h->ev[stage++], s); };
     mark();
 
+    // (0) optional mel-derived RMS normaliser (NormMelComponents.normalize_inputs_by_rms, wavegen_1d.py:493-497, :638-769)
+    const float* mel = b->mel;
+    NormArgs na{};
+    const float* norm_rms_prev = nullptr;
+    if (c.norm_enable) {
+        na.proj = tensor(h, "norm/proj", (size_t)c.mel_channels * (c.norm_proj_cols > 0 ? c.norm_proj_cols : 1) * 4, &rc); if (!na.proj) return rc;
+        na.smooth_win = tensor(h, "norm/smooth_win", (size_t)c.norm_smooth_win * 4, &rc); if (!na.smooth_win) return rc;
+        na.gwin = tensor(h, "norm/gwin", (size_t)c.norm_win * 4, &rc); if (!na.gwin) return rc;
+        na.n_mel = c.mel_channels; na.proj_cols = c.norm_proj_cols; na.hop = c.hop; na.win = c.norm_win; na.ws = c.norm_smooth_win;
+        na.off = c.norm_smooth_win / 2 + 2 * c.hop - c.norm_win / 2; na.iters = c.norm_iters; na.use_max_limit = c.norm_use_max_limit;
+        na.proj_scale = c.norm_proj_scale; na.norm_fact = c.norm_fact; na.floor = c.norm_floor; na.compress_exp = c.norm_compress_exp;
+        na.lin_scale = c.norm_lin_scale; na.lin_off = c.norm_lin_off; na.mel_scale = c.norm_mel_scale;
+        MBX_CUDA_CHECK(launch_norm_mel(na, cx.g, b->mel, cx.p<float>("norm_rms_a"), cx.p<float>("norm_rms_b"),
+                                       cx.p<float>("mel_norm"), &norm_rms_prev, &h->launches, s));
+        mel = cx.p<float>("mel_norm");
+    }
+
     // (1) F0 sub-net (generate_f0, custom_pulsed_generator.py:773-791)
     const float* f0 = b->f0_override;
     if (!f0) {
         rc = (precision == MBEXWN_PREC_FP32_SIMT || !h->tc_subnets)
-                 ? run_subnet(cx, c.pp_ops, c.n_pp_ops, b->mel, cx.p<float>("F0"))
-                 : run_subnet_tc(cx, c.pp_ops, c.n_pp_ops, b->mel, cx.p<float>("F0"));
+                 ? run_subnet(cx, c.pp_ops, c.n_pp_ops, mel, cx.p<float>("F0"))
+                 : run_subnet_tc(cx, c.pp_ops, c.n_pp_ops, mel, cx.p<float>("F0"));
         if (rc) return rc;
         f0 = cx.p<float>("F0");
     } else {
@@ -402,7 +425,7 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
         if (precision != MBEXWN_PREC_FP32_SIMT && h->tc_subnets && tc_eligible(op)) {
             const int cin_pad = round64(c.mel_channels);
             const float* wt = tensor(h, n + "/tc/W", (size_t)cout * 2 * op.k * cin_pad * 2, &rc); if (!wt) return rc;
-            MBX_RC(wn_tc_pack(b->mel, cx.p<char>("mel_hl"), b->n_frames, c.mel_channels, cin_pad, 1, 0, 0, PAD_ZERO, cx.g, s, &h->error));
+            MBX_RC(wn_tc_pack(mel, cx.p<char>("mel_hl"), b->n_frames, c.mel_channels, cin_pad, 1, 0, 0, PAD_ZERO, cx.g, s, &h->error));
             TcConvArgs a{};
             a.a_hilo = cx.p<char>("mel_hl"); a.rows = b->n_frames; a.cin_pad = cin_pad; a.w = wt; a.cout = cout; a.k = op.k;
             a.dilation = 1; a.pad_l = op.pad_l; a.bias = bias; a.act = ACT_NONE; a.rate = 1;
@@ -410,7 +433,7 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
             MBX_RC(wn_tc_conv(h->tc, a, cx.g, s, &h->error));
             h->launches += 2;
         } else {
-            MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op, 1, b->n_frames, b->mel, w, bias, nullptr, cx.p<float>("cond")), cx.g, s));
+            MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op, 1, b->n_frames, mel, w, bias, nullptr, cx.p<float>("cond")), cx.g, s));
             h->launches++;
         }
     }
@@ -472,8 +495,8 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
     mark();
     // (6) VTF sub-net -> cepstrum (generate_specenv, :793-799)
     rc = (precision == MBEXWN_PREC_FP32_SIMT || !h->tc_subnets)
-             ? run_subnet(cx, c.ps_ops, c.n_ps_ops, b->mel, cx.p<float>("ceps"))
-             : run_subnet_tc(cx, c.ps_ops, c.n_ps_ops, b->mel, cx.p<float>("ceps"));
+             ? run_subnet(cx, c.ps_ops, c.n_ps_ops, mel, cx.p<float>("ceps"))
+             : run_subnet_tc(cx, c.ps_ops, c.n_ps_ops, mel, cx.p<float>("ceps"));
     if (rc) return rc;
     mark();
 
@@ -497,6 +520,11 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
         OlaArgs oa{cx.p<float>("frames"), b->out, b->n_frames, c.hop, c.stft_win};
         MBX_CUDA_CHECK(launch_ola(oa, cx.g, s));
         h->launches += 2;
+        if (c.norm_enable) {                                  // signal * upsampled_rms (wavegen_1d.py:504-507)
+            float* tap = cx.ws.slots.count("norm_gain") ? cx.p<float>("norm_gain") : nullptr;
+            MBX_CUDA_CHECK(launch_norm_apply(na, cx.g, norm_rms_prev, b->out, tap, c.hop, s));
+            h->launches += 1;
+        }
     }
     mark();
     h->ev_recorded = h->stage_timing != 0;
@@ -522,6 +550,9 @@ int mbexwn_create(const mbexwn_config_t* cfg, mbexwn_handle_t* out) {
     if (cfg->steps_per_frame * cfg->pulse_channels != cfg->pulse_per_frame) return MBEXWN_ERR_INVALID;
     if (cfg->fft_size < cfg->stft_win || (cfg->fft_size & (cfg->fft_size - 1))) return MBEXWN_ERR_INVALID;
     if (cfg->stft_win != 4 * cfg->hop) return MBEXWN_ERR_UNSUPPORTED;     // 4x overlap (wavegen_1d.py:592)
+    if (cfg->norm_enable && (cfg->norm_iters < 1 || cfg->norm_win != 4 * cfg->hop || cfg->norm_smooth_win < 1 ||
+                             cfg->mel_channels > 256 || cfg->norm_fact <= 0.f))
+        return MBEXWN_ERR_UNSUPPORTED;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return MBEXWN_ERR_CUDA;                          // no CPU fallback

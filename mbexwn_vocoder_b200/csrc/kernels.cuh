@@ -139,6 +139,21 @@ struct OlaArgs {
 };
 cudaError_t launch_ola(const OlaArgs& a, const FrameGrid& g, cudaStream_t s);
 
+// ---- k_norm.cu: NormMelComponents (wavegen_1d.py:578-769) --------------------------------------------------------
+struct NormArgs {
+    const float* proj;        // (n_mel) inv_enorm when proj_cols == 0, else (n_mel, proj_cols) pinv(mel basis)^T
+    const float* smooth_win;  // (ws) Hann [squared] smoothing window
+    const float* gwin;        // (win) Hann / sum
+    int n_mel, proj_cols, hop, win, ws, off, iters, use_max_limit;
+    float proj_scale, norm_fact, floor, compress_exp, lin_scale, lin_off, mel_scale;
+};
+// mell (frames, n_mel) -> mel_out normalised; rms_a / rms_b (frames) scratch; *rms_prev_out = the frame RMS the last
+// smoothing iteration started from (its gain is what the output is multiplied with)
+cudaError_t launch_norm_mel(const NormArgs& a, const FrameGrid& g, const float* mell, float* rms_a, float* rms_b,
+                            float* mel_out, const float** rms_prev_out, int* launches, cudaStream_t s);
+cudaError_t launch_norm_apply(const NormArgs& a, const FrameGrid& g, const float* rms_prev, float* out, float* gain_tap,
+                              int out_hop, cudaStream_t s);
+
 // audio -> log-mel (analysis side); all pointers are device pointers
 struct MelAnalysisArgs {
     const float* audio;             // utterances back to back

@@ -429,6 +429,11 @@ def _mel_to_hz_slaney(m):
     return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
 
 
+def mel_frequencies(n_mels: int, fmin: float, fmax: float) -> np.ndarray:
+    """librosa.mel_frequencies(htk=False): n_mels frequencies equally spaced on the Slaney mel scale."""
+    return _mel_to_hz_slaney(np.linspace(_hz_to_mel_slaney(fmin), _hz_to_mel_slaney(fmax), n_mels))
+
+
 def mel_filter_bank(sr: float, n_fft: int, n_mels: int, fmin: float, fmax: Optional[float],
                     norm: bool = True, dtype=np.float32) -> np.ndarray:
     """(n_mels, n_fft // 2 + 1) triangular mel basis as the reference builds it with ``librosa.filters.mel(sr, n_fft,

@@ -71,6 +71,12 @@ def make_config(plan: ModelPlan) -> _cabi.Config:
     c.cumsum_chunk = 1000
     c.pqmf_q, c.pqmf_back = plan.pqmf_q, plan.pqmf_back
     c.halo_frames = engine_halo(plan)
+    if plan.norm is not None:
+        nm = plan.norm
+        c.norm_enable, c.norm_iters, c.norm_win, c.norm_smooth_win = 1, nm.iters, nm.win, nm.smooth_win
+        c.norm_proj_cols, c.norm_use_max_limit = nm.proj_cols, int(nm.use_max_limit)
+        c.norm_fact, c.norm_floor, c.norm_compress_exp, c.norm_proj_scale = nm.norm_fact, nm.floor, nm.compress_exp, nm.proj_scale
+        c.norm_lin_scale, c.norm_lin_off, c.norm_mel_scale = nm.lin_scale, nm.lin_off, nm.mel_scale
     return c
 
 
@@ -137,6 +143,10 @@ class Engine:
         if plan.lifters is not None:
             self._register("lifters", plan.lifters)
             self._register("lifter_grid", plan.lifter_log10f0)
+        if plan.norm is not None:
+            self._register("norm/proj", plan.norm.proj)
+            self._register("norm/smooth_win", plan.norm.smooth_window)
+            self._register("norm/gwin", plan.norm.gwin)
         self._upload_tc(weights)
 
     def _register_torch(self, name: str, t: torch.Tensor):

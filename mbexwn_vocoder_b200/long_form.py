@@ -110,6 +110,9 @@ def synth_long(engine, mel: np.ndarray, noise: np.ndarray, chunk_frames: int = 4
 
     `first_alone`: the first window is synthesised in a call of its own (first-chunk latency of a streaming client)."""
     plan: ModelPlan = engine.plan
+    if plan.norm is not None:
+        raise NotImplementedError("chunked synthesis with normalize_rms_from_mell is not built (the smoothed RMS spans "
+                                  "window borders)")
     mel = np.ascontiguousarray(mel, dtype=np.float32)
     T = mel.shape[0]
     ppf, spf, hop = plan.pulse_per_frame, plan.steps_per_frame, plan.hop

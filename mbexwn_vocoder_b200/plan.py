@@ -71,6 +71,34 @@ class WaveNetSpec:
 
 
 @dataclass
+class NormMelSpec:
+    """NormMelComponents constructor arguments that matter at inference (wavegen_1d.py:580-632)."""
+    iters: int
+    win: int
+    smooth_win: int
+    squared_win: bool
+    use_pinv: bool
+    norm_fact: float
+    floor: float                # 1 / max_norm_fact, 0 = none
+    compress_exp: float         # 0 = none
+    lin_scale: float
+    lin_off: float
+    mel_scale: float
+    use_max_limit: bool
+    sample_rate: int
+    fft_size: int
+    n_mel: int
+    fmin: float
+    fmax: float
+    # constants (finalize_plan)
+    proj: Optional[np.ndarray] = None
+    proj_cols: int = 0
+    proj_scale: float = 1.0
+    smooth_window: Optional[np.ndarray] = None
+    gwin: Optional[np.ndarray] = None
+
+
+@dataclass
 class ModelPlan:
     sample_rate: int
     hop: int
@@ -98,6 +126,7 @@ class ModelPlan:
     env_order_scale: Optional[float]
     wavetable_cfg: Dict
     max_halo_frames: int = 1
+    norm: Optional["NormMelSpec"] = None     # NormMelComponents (normalize_rms_from_mell), None = off
     # init-time constants (filled by finalize())
     wavetables: Optional[dsp_init.WaveTables] = None
     pqmf_syn: Optional[np.ndarray] = None
@@ -232,10 +261,34 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
                                   "are not supported")                                   # custom_pulsed_generator.py:272
     mc = copy.deepcopy(hparams["mbexwn_config"])
     pc = hparams["preprocess_config"]
+    norm = None
+    if mc.get("normalize_rms_from_mell", False):                                        # wavegen_1d.py:333-335
+        win = int(pc.get("win_size", pc["fft_size"]))
+        if 4 * int(pc["hop_size"]) != win:                                                # wavegen_1d.py:592-594
+            raise RuntimeError(f"NormMelComponents:error: this module currently supports only the case where win_size "
+                               f"{win} = 4 * hop_size {pc['hop_size']}")
+        iters = int(mc.get("normalize_rms_num_smooth_iters", 0))
+        if iters <= 0:
+            raise NotImplementedError("normalize_rms_num_smooth_iters = 0 (per-channel time average, wavegen_1d.py:722) "
+                                      "is not built")
+        if int(mc.get("n_group", 1)) != 1:
+            raise NotImplementedError("n_group != 1 is not built")
+        cexp = mc.get("normalize_compressor_exp")
+        norm = NormMelSpec(
+            iters=iters, win=win, smooth_win=int(win * mc.get("normalize_smooth_win_scale", 1)),
+            squared_win=bool(mc.get("normalize_smooth_with_squared_win", True)),
+            use_pinv=bool(mc.get("normalize_use_pinv", False)), norm_fact=float(pc["fft_size"] * win * 0.5),
+            floor=float(1. / mc["max_norm_fact"]) if mc.get("max_norm_fact") else 0.0,
+            compress_exp=float(cexp) if cexp is not None else 0.0,
+            lin_scale=float(mc.get("lin_amp_scale", 1.)), lin_off=float(mc.get("lin_amp_off", 1.e-5)),
+            mel_scale=float(mc.get("mel_amp_scale", 1.)), use_max_limit=bool(mc.get("use_max_limit", False)),
+            sample_rate=int(pc["sample_rate"]), fft_size=int(pc["fft_size"]), n_mel=int(pc["mel_channels"]),
+            fmin=pc["fmin"], fmax=pc["fmax"])
+        if cexp is not None and float(cexp) == 0.0:
+            raise NotImplementedError("normalize_compressor_exp = 0 is not built")
     for key in ("normalize_rms_from_mell", "normalize_rms_num_smooth_iters", "normalize_compressor_exp",
                 "normalize_smooth_win_scale", "normalize_smooth_with_squared_win", "normalize_use_pinv"):
-        if mc.pop(key, None) and key == "normalize_rms_from_mell":
-            raise NotImplementedError("normalize_rms_from_mell (NormMelComponents) is not built yet (SURVEY 8f-4)")
+        mc.pop(key, None)                                                               # wavegen_1d.py:416-422
     if "ps_max_db_range" in mc:                                                         # wavegen_1d.py:424-430
         mc["filter_max_db_range"] = mc.pop("ps_max_db_range")
         mc.pop("ns_max_db_range", None)
@@ -329,7 +382,7 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
         pp_ops=pp_ops, ps_ops=ps_ops, n_ceps=n_ceps, wavenet=wn, post_name="MBExWNGen_PaNMPulseWaveNet_Post",
         pqmf_cfg=mb, stft_win=win, fft_size=fft,
         filter_max_log_range=(fdb / (20 * np.log10(np.exp(1)))) if fdb is not None else None,
-        env_order_scale=mc.get("ps_env_order_scale"), wavetable_cfg=copy.deepcopy(mc["wavetable_config"]))
+        env_order_scale=mc.get("ps_env_order_scale"), wavetable_cfg=copy.deepcopy(mc["wavetable_config"]), norm=norm)
     half_span = max(d * (k - 1) // 2 for d in dil)
     plan.max_halo_frames = max(1, -(-half_span // steps_per_frame))
     if finalize:
@@ -352,4 +405,19 @@ def finalize_plan(plan: ModelPlan) -> ModelPlan:
     if plan.env_order_scale:
         plan.lifter_log10f0, plan.lifters = dsp_init.cepstral_lifters(
             plan.env_order_scale, plan.sample_rate, plan.f0_min, plan.f0_max, plan.n_ceps)
+    if plan.norm is not None:
+        nm = plan.norm
+        hann = dsp_init.cosine_window("hann", nm.win).astype(np.float32)
+        if nm.use_pinv:                                                                 # wavegen_1d.py:602-608
+            basis = dsp_init.mel_filter_bank(nm.sample_rate, nm.fft_size, nm.n_mel, nm.fmin, nm.fmax)
+            nm.proj = np.ascontiguousarray(np.linalg.pinv(basis).T.astype(np.float32))
+            nm.proj_cols = int(nm.proj.shape[1])
+            nm.proj_scale = float(1.0 / np.sqrt(np.sum(hann ** 2)))
+        else:                                                                           # wavegen_1d.py:609-612
+            mel_f = dsp_init.mel_frequencies(nm.n_mel + 2, nm.fmin, nm.fmax)
+            nm.proj = ((mel_f[2:nm.n_mel + 2] - mel_f[:nm.n_mel]) / 2.).astype(np.float32)
+            nm.proj_cols, nm.proj_scale = 0, 1.0
+        sw = dsp_init.cosine_window("hann", nm.smooth_win).astype(np.float32)
+        nm.smooth_window = sw ** 2 if nm.squared_win else sw
+        nm.gwin = hann / np.sum(hann)
     return plan

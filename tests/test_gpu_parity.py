@@ -147,8 +147,8 @@ def test_mel_inverter_api(speech_setup):
     assert np.array_equal(a[0], y[20 * 300:])
     with pytest.raises(RuntimeError):
         inv.synth_from_mel(np.zeros((1, 5, 64), np.float32))
-    with pytest.raises(NotImplementedError):
-        inv.generate_mel_from_snd(np.zeros(100), 24000)
+    dd = inv.generate_mel_from_snd(np.zeros(100), 24000)           # analysis side (tests/test_gpu_analysis.py)
+    assert dd["mell"].shape == (80, 1) and np.allclose(dd["mell"], np.log(np.finfo(np.float32).eps))
 
 
 def test_in_kernel_noise_statistics(engine, speech_setup):
