@@ -164,6 +164,16 @@ MBEXWN_API int mbexwn_forward_host(mbexwn_handle_t h, const mbexwn_batch_t* batc
                         const float* mel_host, const float* noise_host, float* out_host,
                         void* workspace, size_t workspace_bytes, void* cuda_stream);
 
+/* Pipelined form of mbexwn_forward_host for a stream of batches (throughput serving): `slot` 0 / 1 alternates between two
+ * sets of caller-owned device input / output buffers (two mbexwn_batch_t with their own mel / noise / out pointers; the
+ * workspace is shared).  _begin enqueues H2D (copy stream) -> forward (caller's stream) -> D2H (second copy stream) with
+ * event dependencies and returns at once, so the copies of neighbouring calls run under the kernels of this one;
+ * _wait blocks until the waveform of the slot's last _begin is in out_host.  Host buffers must be pinned. */
+MBEXWN_API int mbexwn_forward_host_begin(mbexwn_handle_t h, int32_t slot, const mbexwn_batch_t* batch, int32_t precision,
+                                         const float* mel_host, const float* noise_host, float* out_host,
+                                         void* workspace, size_t workspace_bytes, void* cuda_stream);
+MBEXWN_API int mbexwn_forward_host_wait(mbexwn_handle_t h, int32_t slot);
+
 /* Per-stage taps (return_F0 / return_components of PaNWaveNet.infer, custom_pulsed_generator.py:756-771, plus the
  * stage boundaries of SURVEY.md 8a): after mbexwn_forward the named intermediate lives in the workspace at
  * [*offset_bytes, *offset_bytes + *n_bytes).  Names: "F0", "phase", "index", "pulse", "wn_in", "cond", "wn_out"

@@ -92,6 +92,9 @@ SYMBOLS = {
     "mbexwn_forward": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mbexwn_forward_host": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mbexwn_forward_host_begin": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(Batch), C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mbexwn_forward_host_wait": (C.c_int, [C.c_void_p, C.c_int32]),
     "mbexwn_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32,
                              C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mbexwn_last_launch_count": (C.c_int, [C.c_void_p]),

@@ -24,6 +24,11 @@ struct mbexwn_handle_s {
     bool ev_ready = false;
     bool ev_recorded = false;
     mbx::WnTcState tc;
+    // pipelined host-buffer forward (mbexwn_forward_host_begin / _wait): two copy streams and per-slot events
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_h2d[2] = {}, ev_done[2] = {}, ev_d2h[2] = {};
+    bool pipe_ready = false;
+    bool slot_busy[2] = {false, false};
 };
 
 namespace mbx {
@@ -566,6 +571,11 @@ int mbexwn_create(const mbexwn_config_t* cfg, mbexwn_handle_t* out) {
 void mbexwn_destroy(mbexwn_handle_t h) {
     if (!h) return;
     if (h->ev_ready) for (int i = 0; i <= MBEXWN_N_STAGES; ++i) cudaEventDestroy(h->ev[i]);
+    if (h->pipe_ready) {
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev_h2d[i]); cudaEventDestroy(h->ev_done[i]); cudaEventDestroy(h->ev_d2h[i]); }
+        cudaStreamDestroy(h->copy_in);
+        cudaStreamDestroy(h->copy_out);
+    }
     mbx::wn_tc_destroy(h->tc);
     delete h;
 }
@@ -605,6 +615,51 @@ int mbexwn_forward_host(mbexwn_handle_t h, const mbexwn_batch_t* batch, int32_t 
     if (rc) return rc;
     MBX_CUDA_CHECK(cudaMemcpyAsync(out_host, batch->out, (size_t)batch->n_frames * c.hop * 4, cudaMemcpyDeviceToHost, s));
     MBX_CUDA_CHECK(cudaStreamSynchronize(s));
+    return MBEXWN_OK;
+}
+
+int mbexwn_forward_host_begin(mbexwn_handle_t h, int32_t slot, const mbexwn_batch_t* batch, int32_t precision,
+                              const float* mel_host, const float* noise_host, float* out_host, void* workspace,
+                              size_t workspace_bytes, void* cuda_stream) {
+    if (!h || !batch || !mel_host || !out_host || slot < 0 || slot > 1) return MBEXWN_ERR_INVALID;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const mbexwn_config_t& c = h->cfg;
+    if (!h->pipe_ready) {
+        MBX_CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+        MBX_CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            MBX_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+            MBX_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+            MBX_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
+        }
+        h->pipe_ready = true;
+    }
+    // H2D of this call's inputs: the slot's device input buffers were last read by the forward two calls ago
+    if (h->slot_busy[slot]) MBX_CUDA_CHECK(cudaStreamWaitEvent(h->copy_in, h->ev_done[slot], 0));
+    MBX_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(batch->mel), mel_host, (size_t)batch->n_frames * c.mel_channels * 4,
+                                   cudaMemcpyHostToDevice, h->copy_in));
+    if (noise_host && batch->noise)
+        MBX_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(batch->noise), noise_host,
+                                       (size_t)batch->n_frames * c.steps_per_frame * 4, cudaMemcpyHostToDevice, h->copy_in));
+    MBX_CUDA_CHECK(cudaEventRecord(h->ev_h2d[slot], h->copy_in));
+    // forward on the caller's stream: needs the inputs, and the slot's output buffer drained by the D2H two calls ago
+    MBX_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_h2d[slot], 0));
+    if (h->slot_busy[slot]) MBX_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_d2h[slot], 0));
+    int rc = mbx::forward_impl(h, batch, precision, workspace, workspace_bytes, s);
+    if (rc) return rc;
+    MBX_CUDA_CHECK(cudaEventRecord(h->ev_done[slot], s));
+    // D2H of the waveform under the next call's kernels
+    MBX_CUDA_CHECK(cudaStreamWaitEvent(h->copy_out, h->ev_done[slot], 0));
+    MBX_CUDA_CHECK(cudaMemcpyAsync(out_host, batch->out, (size_t)batch->n_frames * c.hop * 4, cudaMemcpyDeviceToHost, h->copy_out));
+    MBX_CUDA_CHECK(cudaEventRecord(h->ev_d2h[slot], h->copy_out));
+    h->slot_busy[slot] = true;
+    return MBEXWN_OK;
+}
+
+int mbexwn_forward_host_wait(mbexwn_handle_t h, int32_t slot) {
+    if (!h || slot < 0 || slot > 1) return MBEXWN_ERR_INVALID;
+    if (!h->pipe_ready || !h->slot_busy[slot]) return MBEXWN_OK;
+    MBX_CUDA_CHECK(cudaEventSynchronize(h->ev_d2h[slot]));
     return MBEXWN_OK;
 }
 

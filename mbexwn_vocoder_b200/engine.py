@@ -320,6 +320,22 @@ class PreparedBatch:
                 self.workspace.data_ptr(), self.workspace.numel(), self._stream())
         _cabi.check(eng.lib, eng._handle, rc, "mbexwn_forward_host")
 
+    def begin_host(self, slot: int, seed: int = 0):
+        """Pipelined host forward (mbexwn_forward_host_begin): returns once everything is enqueued.  Use two PreparedBatch
+        objects of one engine alternately as slot 0 / 1 and call wait_host(slot) before touching out_host / mel_host."""
+        eng = self.eng
+        self.batch.seed = seed
+        with torch.cuda.device(eng.device):
+            rc = eng.lib.mbexwn_forward_host_begin(
+                eng._handle, slot, C.byref(self.batch), self.prec, self.mel_host.data_ptr(),
+                self.noise_host.data_ptr() if self.noise_host is not None else None, self.out_host.data_ptr(),
+                self.workspace.data_ptr(), self.workspace.numel(), self._stream())
+        _cabi.check(eng.lib, eng._handle, rc, "mbexwn_forward_host_begin")
+
+    def wait_host(self, slot: int):
+        _cabi.check(self.eng.lib, self.eng._handle, self.eng.lib.mbexwn_forward_host_wait(self.eng._handle, slot),
+                    "mbexwn_forward_host_wait")
+
     def upload(self):
         self.mel_dev.copy_(self.mel_host, non_blocking=True)
         if self.noise_host is not None:

@@ -158,6 +158,31 @@ class MELInverter(object):
                                      precision=self.precision, seed=self.seed if seed is None else seed, taps=taps)
         return (out, tp) if taps else out
 
+    def synth_stream(self, batches, noise=None, seed: Optional[int] = None):
+        """Throughput serving: iterate over batches (each a list of (T_u, n_mel) mels) and yield, per batch, the list of
+        waveforms.  Consecutive batches alternate between two device buffer sets, so the host->device copy of the next
+        batch and the device->host copy of the previous one run under the kernels of the current one
+        (mbexwn_forward_host_begin / _wait).  ``noise``: optional iterable of per-batch noise lists (parity runs)."""
+        eng = self.model
+        seed = self.seed if seed is None else seed
+        pending = []                                         # (slot, PreparedBatch)
+        noise_it = iter(noise) if noise is not None else None
+        for i, mels in enumerate(batches):
+            slot = i & 1
+            if len(pending) == 2:                            # the slot about to be reused must be drained first
+                s0, pb0 = pending.pop(0)
+                pb0.wait_host(s0)
+                yield [w.copy() for w in pb0.waveforms()]
+            nz = next(noise_it) if noise_it is not None else None
+            mels = [np.asarray(m, dtype=np.float32) for m in mels]
+            pb = eng.prepare([m.shape[0] for m in mels], self.precision, nz is not None)
+            pb.load(mels, nz)
+            pb.begin_host(slot, seed)
+            pending.append((slot, pb))
+        for s0, pb0 in pending:
+            pb0.wait_host(s0)
+            yield [w.copy() for w in pb0.waveforms()]
+
     def synth_long_from_mel(self, scaled_mell, noise=None, chunk_frames: int = 400, max_batch_frames: int = 32768,
                             seed: Optional[int] = None, return_info: bool = False):
         """One long (T, n_mel) or (1, T, n_mel) mel -> flat waveform, synthesised in windows of `chunk_frames` frames with
