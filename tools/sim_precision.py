@@ -31,6 +31,39 @@ def e4m3(x):
     return x.clamp(-448, 448).to(torch.float32).to(torch.float8_e4m3fn).to(torch.float64)
 
 
+_E2M1 = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0], dtype=torch.float64)
+
+
+def fp4_block(x, axis, block, scale_kind):
+    """Block-scaled e2m1 emulation along `axis`: nvf4 = e4m3 scale per 16 values, mxf4 = power-of-two scale per 32."""
+    x = x.movedim(axis, -1)
+    shp = x.shape
+    K = shp[-1]
+    pad = (-K) % block
+    if pad:
+        x = torch.cat([x, torch.zeros(*shp[:-1], pad, dtype=x.dtype)], dim=-1)
+    xb = x.reshape(*shp[:-1], -1, block)
+    amax = xb.abs().amax(dim=-1, keepdim=True).clamp_min(1e-300)
+    if scale_kind == "nvf4":
+        sc = e4m3_pos(amax / 6.0)
+    else:
+        sc = 2.0 ** torch.ceil(torch.log2(amax / 6.0))
+    q = xb / sc
+    mag = q.abs().clamp(max=6.0)
+    idx = (mag.unsqueeze(-1) - _E2M1).abs().argmin(dim=-1)
+    deq = torch.sign(q) * _E2M1[idx] * sc
+    out = deq.reshape(*shp[:-1], -1)[..., :K]
+    return out.movedim(-1, axis)
+
+
+def e4m3_pos(x):
+    """Positive scale rounded up-ish to e4m3 (with a global 2^k pre-scale the kernel would fold into scale-input-d)."""
+    k = torch.floor(torch.log2(x.clamp_min(1e-300)))
+    m = x / 2.0 ** k                                   # [1, 2)
+    m = torch.ceil(m * 8.0) / 8.0
+    return m * 2.0 ** k
+
+
 def pow2_scale(x, target):
     m = float(x.abs().max())
     return 2.0 ** np.floor(np.log2(target / max(m, 1e-30)))
@@ -64,6 +97,15 @@ class Scheme:
             t1 = e4m3(al * 2.0 ** sa) @ e4m3(bh * 2.0 ** sb)
             t2 = e4m3(ah * 2.0 ** sa2) @ e4m3(bl * 2.0 ** sb2)
             return ah @ bh + (t1 + t2) * 2.0 ** -15
+        if n.startswith("f16f4"):
+            # fp16 main product + the two correction products in block-scaled e2m1 (4x rate): 1.5 units
+            kind4 = "nvf4" if "nv" in n else "mxf4"
+            blk = 16 if kind4 == "nvf4" else 32
+            ah, bh = rnd(a, torch.float16), rnd(b, torch.float16)
+            al, bl = a - ah, b - bh
+            t1 = fp4_block(al, 1, blk, kind4) @ fp4_block(bh, 0, blk, kind4)
+            t2 = fp4_block(ah, 1, blk, kind4) @ fp4_block(bl, 0, blk, kind4)
+            return ah @ bh + t1 + t2
         if n.startswith("f16f8"):
             ah, bh = rnd(a, torch.float16), rnd(b, torch.float16)
             al, bl = a - ah, b - bh
@@ -132,7 +174,7 @@ def main():
     cond = cond[0]
     ref, href = wavenet(orc, Scheme("fp64"), x, cond)
     print(f"model {model}: rows {x.shape[0]}, C {orc.C}, |wn_out| peak {float(ref.abs().max()):.3f}, |h| peak {float(href.abs().max()):.2f}")
-    for name in ("bf16x3", "f16f8", "s15", "s15_hm"):
+    for name in ("bf16x3", "f16", "f16f8", "s15", "s15_hm", "f16f4nv", "f16f4mx"):
         out, h = wavenet(orc, Scheme(name), x, cond)
         err = (out - ref)
         snr = 10 * np.log10(float((ref ** 2).sum() / (err ** 2).sum()))
