@@ -109,6 +109,12 @@ typedef struct {
     float norm_compress_exp;    /* normalize_compressor_exp, 0 = none (:693-694) */
     float norm_proj_scale;      /* 1 / win_norm of the pinv variant (:603, :687) */
     float norm_lin_scale, norm_lin_off, norm_mel_scale;   /* re-scaling of the normalised mel (:725-730) */
+    /* spectral shaping of the excitation (custom_pulsed_generator.py:666-724): 0 = STFT-domain vocal-tract filter,
+     * 1 = ps_use_stft False: the PS sub-net ends in `subbands` log gains per frame; exp, linear interpolation x hop
+     *     (ps_gain_interpolator :453) and product with the sub-band rows before the PQMF (:857-884, :916-917),
+     * 2 = ps_off: the PQMF output is the signal (n_ps_ops may be 0) */
+    int32_t ps_mode;
+    int32_t ps_preserve_energy; /* ps_mode 1: subtract the mean log gain over the bands (:867-876) */
 } mbexwn_config_t;
 
 /* One batch on the padded frame grid; all pointers are DEVICE pointers. */
@@ -177,7 +183,7 @@ MBEXWN_API int mbexwn_forward_host_wait(mbexwn_handle_t h, int32_t slot);
 /* Per-stage taps (return_F0 / return_components of PaNWaveNet.infer, custom_pulsed_generator.py:756-771, plus the
  * stage boundaries of SURVEY.md 8a): after mbexwn_forward the named intermediate lives in the workspace at
  * [*offset_bytes, *offset_bytes + *n_bytes).  Names: "F0", "phase", "index", "pulse", "wn_in", "cond", "wn_out"
- * (rows, wn_cout rounded up to 32), "skip" (fp32 variant only), "subbands", "excitation", "ceps", "frames", "vtf", "lifter_index";
+ * (rows, wn_cout rounded up to 32), "skip" (fp32 variant only), "subbands", "excitation", "ceps" (ps_mode 1: the (frames, subbands) log gains), "frames", "vtf", "lifter_index";
  * with norm_enable also "mel_norm" (frames, mel_channels), "norm_rms_a" / "norm_rms_b" (frames), "norm_gain" (frames * hop). */
 MBEXWN_API int mbexwn_tap(mbexwn_handle_t h, const char* name, int32_t n_frames, int32_t n_chunks, int32_t precision,
                size_t* offset_bytes, size_t* n_bytes);

@@ -479,6 +479,19 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
         fa.wn_out = cx.p<float>("wn_out"); fa.ld = out_pad; fa.cin = c.wn_cout; fa.post_w = w; fa.post_b = bias; fa.poly = poly;
         fa.sub_out = h->debug_taps ? cx.p<float>("subbands") : nullptr; fa.out = cx.p<float>("excitation");
         fa.rows = rows; fa.steps_per_frame = c.steps_per_frame; fa.S = c.subbands; fa.Q = c.pqmf_q; fa.back = c.pqmf_back;
+        if (c.ps_mode != 0) {
+            // no STFT-domain filter: the PQMF output is the signal (custom_pulsed_generator.py:666-674)
+            fa.out = b->out;
+            if (!post_pqmf_supported(fa)) return fail(h, MBEXWN_ERR_UNSUPPORTED, "ps_use_stft = False / ps_off need the fused post + PQMF kernel");
+            if (c.ps_mode == 1) {
+                // per-band log gains from the PS sub-net (generate_multiband_gain, :857-884), applied inside the fused kernel
+                rc = (precision == MBEXWN_PREC_FP32_SIMT || !h->tc_subnets)
+                         ? run_subnet(cx, c.ps_ops, c.n_ps_ops, mel, cx.p<float>("ceps"))
+                         : run_subnet_tc(cx, c.ps_ops, c.n_ps_ops, mel, cx.p<float>("ceps"));
+                if (rc) return rc;
+                fa.log_gain = cx.p<float>("ceps"); fa.gain_up = c.hop; fa.gain_center = c.ps_preserve_energy;
+            }
+        }
         if (post_pqmf_supported(fa)) {
             MBX_CUDA_CHECK(launch_post_pqmf(fa, cx.g, s));
             h->launches += 1;
@@ -498,6 +511,17 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
     }
 
     mark();
+    if (c.ps_mode != 0) {
+        mark();
+        if (c.norm_enable) {
+            float* tap = cx.ws.slots.count("norm_gain") ? cx.p<float>("norm_gain") : nullptr;
+            MBX_CUDA_CHECK(launch_norm_apply(na, cx.g, norm_rms_prev, b->out, tap, c.hop, s));
+            h->launches += 1;
+        }
+        mark();
+        h->ev_recorded = h->stage_timing != 0;
+        return MBEXWN_OK;
+    }
     // (6) VTF sub-net -> cepstrum (generate_specenv, :793-799)
     rc = (precision == MBEXWN_PREC_FP32_SIMT || !h->tc_subnets)
              ? run_subnet(cx, c.ps_ops, c.n_ps_ops, mel, cx.p<float>("ceps"))
@@ -549,8 +573,10 @@ int mbexwn_create(const mbexwn_config_t* cfg, mbexwn_handle_t* out) {
     *out = nullptr;
     if (cfg->abi_version != MBEXWN_ABI_VERSION) return MBEXWN_ERR_INVALID;
     if (cfg->wn_layers < 1 || cfg->wn_layers > MBEXWN_MAX_LAYERS || cfg->n_pp_ops > MBEXWN_MAX_OPS ||
-        cfg->n_ps_ops > MBEXWN_MAX_OPS || cfg->n_pp_ops < 1 || cfg->n_ps_ops < 1)
+        cfg->n_ps_ops > MBEXWN_MAX_OPS || cfg->n_pp_ops < 1 || (cfg->n_ps_ops < 1 && cfg->ps_mode != 2) ||
+        cfg->ps_mode < 0 || cfg->ps_mode > 2)
         return MBEXWN_ERR_INVALID;
+    if (cfg->ps_mode == 1 && cfg->ps_ops[cfg->n_ps_ops - 1].ch_out != cfg->subbands) return MBEXWN_ERR_INVALID;
     if (cfg->steps_per_frame * cfg->subbands != cfg->hop) return MBEXWN_ERR_INVALID;
     if (cfg->steps_per_frame * cfg->pulse_channels != cfg->pulse_per_frame) return MBEXWN_ERR_INVALID;
     if (cfg->fft_size < cfg->stft_win || (cfg->fft_size & (cfg->fft_size - 1))) return MBEXWN_ERR_INVALID;

@@ -121,6 +121,25 @@ post_pqmf_kernel(PostPqmfArgs a, FrameGrid g) {
             const float* b = Wp + a.cin * PP_MAXS;
 #pragma unroll
             for (int p = 0; p < PP_MAXS; ++p) acc[p] += b[p];
+            if (a.log_gain) {
+                // multi-band gain: value (r - first row of the utterance) of the x gain_up interpolation of exp(log gain)
+                const int fu = s_fu[rl];
+                const int fb = g.utt_begin[fu], T = g.utt_end[fu] - fb;
+                const long long rloc = (r0 + rl) - (long long)fb * a.steps_per_frame;
+                const int t = (int)(rloc / a.gain_up), u = (int)(rloc - (long long)t * a.gain_up);
+                const int t1 = t + 1 < T ? t + 1 : T - 1;
+                const float* l0 = a.log_gain + (long long)(fb + t) * S;
+                const float* l1 = a.log_gain + (long long)(fb + t1) * S;
+                float m0g = 0.f, m1g = 0.f;
+                if (a.gain_center) {
+                    for (int p = 0; p < S; ++p) { m0g += l0[p]; m1g += l1[p]; }
+                    m0g /= (float)S; m1g /= (float)S;
+                }
+                const float w0 = (float)((double)(a.gain_up - u) / a.gain_up), w1 = (float)((double)u / a.gain_up);
+#pragma unroll
+                for (int p = 0; p < PP_MAXS; ++p)
+                    if (p < S) acc[p] *= __fadd_rn(__fmul_rn(expf(l0[p] - m0g), w0), __fmul_rn(expf(l1[p] - m1g), w1));
+            }
         }
         const long long r = r0 + rl;
 #pragma unroll

@@ -109,6 +109,12 @@ struct PostPqmfArgs {
     long long rows;
     int steps_per_frame;
     int S, Q, back;
+    // ps_use_stft = False: per-band log gains of the PS sub-net at frame rate (frames, S), or nullptr.  The reference
+    // interpolates exp(gain) linearly by `gain_up` (= hop) and multiplies sub-band row r of an utterance with value r of
+    // that sequence (custom_pulsed_generator.py:453, :669-670, :916-917)
+    const float* log_gain;
+    int gain_up;
+    int gain_center;        // spect_filters_preserve_energy: subtract the mean over the bands first (:867-876)
 };
 bool post_pqmf_supported(const PostPqmfArgs& a);
 cudaError_t launch_post_pqmf(const PostPqmfArgs& a, const FrameGrid& g, cudaStream_t s);

@@ -18,6 +18,7 @@ import numpy as np
 from . import dsp_init
 
 PAD_ZERO, PAD_SYMMETRIC, PAD_EDGE = 0, 1, 2
+PS_STFT, PS_BAND_GAIN, PS_OFF = 0, 1, 2
 ACT_NONE, ACT_PRELU, ACT_LEAKY, ACT_SOFT_SIGMOID_AFFINE, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4, 5
 GATE_GTU, GATE_GLU, GATE_GFU, GATE_GSU = 0, 1, 2, 3
 _GATES = {"gtu": GATE_GTU, "glu": GATE_GLU, "gfu": GATE_GFU, "gsu": GATE_GSU}
@@ -126,6 +127,8 @@ class ModelPlan:
     env_order_scale: Optional[float]
     wavetable_cfg: Dict
     max_halo_frames: int = 1
+    ps_mode: int = PS_STFT      # PS_STFT | PS_BAND_GAIN | PS_OFF
+    ps_preserve_energy: bool = False
     norm: Optional["NormMelSpec"] = None     # NormMelComponents (normalize_rms_from_mell), None = off
     # init-time constants (filled by finalize())
     wavetables: Optional[dsp_init.WaveTables] = None
@@ -309,14 +312,17 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
                            f"{pulse_rate / pch * np.prod(ups_factors) * S} != {sr}")
     if len(ups_factors) != 1 or ups_factors[0] != 1:
         raise NotImplementedError("multi-block / up-sampling WaveNet stacks are not built yet (SURVEY 8f-4)")
-    for key, why in (("force_causal", "causal convolutions"), ("ps_off", "ps_off"),
+    for key, why in (("force_causal", "causal convolutions"),
                      ("pulse_channels_use_pqmf", "PQMF analysis of the pulse train"),
-                     ("spect_filters_preserve_energy", "energy preserving VTF"),
                      ("pp_subnet_training_only", "pp_subnet_training_only")):
         if mc.get(key):
             raise NotImplementedError(f"{why} is not built yet (SURVEY 8f-4)")
-    if not mc.get("ps_use_stft", True):
-        raise NotImplementedError("ps_use_stft=False (multi-band gain branch) is not built yet (SURVEY 8f-4)")
+    # spectral shaping of the excitation (custom_pulsed_generator.py:666-724): STFT-domain vocal-tract filter (default),
+    # per-band gain from the PS sub-net (ps_use_stft = False, :857-884), or none (ps_off)
+    ps_mode = PS_OFF if mc.get("ps_off") else (PS_STFT if mc.get("ps_use_stft", True) else PS_BAND_GAIN)
+    preserve_energy = bool(mc.get("spect_filters_preserve_energy", False))
+    if preserve_energy and ps_mode == PS_STFT:
+        raise NotImplementedError("spect_filters_preserve_energy with the STFT filter is not built yet (SURVEY 8f-4)")
     if not mc.get("pp_mod_subnet_use_pqmf", True):
         raise NotImplementedError("pp_mod_subnet_use_pqmf=False is not built yet")
 
@@ -333,11 +339,13 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
                                bool(mc.get("remove_inactive_pad_layers", False)))
     if not pp_ops:
         raise NotImplementedError("models without pp_subnet (constant F0) are not built yet")
-    ps_ops, _ = subnet_program(mc["ps_subnet"], "PS", n_mel, n_ceps, 1, ACT_NONE, 0.01, None, use_prelu,
-                               bool(mc.get("ps_subnet_use_valid_padding", False)),
-                               bool(mc.get("remove_inactive_pad_layers", False)))
-    if ps_ops[-1].rate_out != 1:
-        raise NotImplementedError("VTF sub-net must stay at mel-frame rate")
+    ps_ops: List[Op] = []
+    if ps_mode != PS_OFF:
+        ps_ops, _ = subnet_program(mc["ps_subnet"], "PS", n_mel, n_ceps if ps_mode == PS_STFT else S, 1, ACT_NONE, 0.01,
+                                   None, use_prelu, bool(mc.get("ps_subnet_use_valid_padding", False)),
+                                   bool(mc.get("remove_inactive_pad_layers", False)))   # final width: :422
+        if not ps_ops or ps_ops[-1].rate_out != 1:
+            raise NotImplementedError("VTF sub-net must stay at mel-frame rate")
 
     wn_cfg = copy.deepcopy(mc["pp_mod_subnet"])
     c = int(wn_cfg.pop("n_channels") * chan_factors[0])
@@ -382,7 +390,8 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
         pp_ops=pp_ops, ps_ops=ps_ops, n_ceps=n_ceps, wavenet=wn, post_name="MBExWNGen_PaNMPulseWaveNet_Post",
         pqmf_cfg=mb, stft_win=win, fft_size=fft,
         filter_max_log_range=(fdb / (20 * np.log10(np.exp(1)))) if fdb is not None else None,
-        env_order_scale=mc.get("ps_env_order_scale"), wavetable_cfg=copy.deepcopy(mc["wavetable_config"]), norm=norm)
+        env_order_scale=mc.get("ps_env_order_scale"), wavetable_cfg=copy.deepcopy(mc["wavetable_config"]), norm=norm,
+        ps_mode=ps_mode, ps_preserve_energy=preserve_energy)
     half_span = max(d * (k - 1) // 2 for d in dil)
     plan.max_halo_frames = max(1, -(-half_span // steps_per_frame))
     if finalize:

@@ -587,7 +587,8 @@ def import_weights(prefix: str, plan, verify: bool = True) -> Dict[str, np.ndarr
     block = g.child(0, "block") if g.has(0, "block") else g.find("pp_waveNetBlocks")
     out: Dict[str, np.ndarray] = {}
     _subnet_weights(g, g.child(block, "pp_subnet_layers"), plan.pp_ops, out)
-    _subnet_weights(g, g.child(block, "ps_subnet_layers"), plan.ps_ops, out)
+    if plan.ps_ops:                                        # ps_off models hold no PS sub-net
+        _subnet_weights(g, g.child(block, "ps_subnet_layers"), plan.ps_ops, out)
     blocks = g.list_items(g.child(block, "pp_waveNetBlocks"))
     if len(blocks) != 1:
         raise NotImplementedError("multi-block WaveNet checkpoints are not supported (SURVEY 8f-4)")
@@ -695,7 +696,8 @@ def export_weights(prefix: str, hparams: Dict, weights: Dict[str, np.ndarray]) -
     for attr, specs, base, final_act, target, valid in (
             ("pp_subnet_layers", mc["pp_subnet"], "PulsPar", True, plan.pulse_per_frame,
              bool(mc.get("pp_subnet_use_valid_padding", False))),
-            ("ps_subnet_layers", mc["ps_subnet"], "PS", False, None, bool(mc.get("ps_subnet_use_valid_padding", False)))):
+            ("ps_subnet_layers", mc["ps_subnet"] if plan.ps_ops else [], "PS", False, None,
+             bool(mc.get("ps_subnet_use_valid_padding", False)))):
         lst = b.add(block, attr)
         for i, (kind, name) in enumerate(reference_subnet_layout(specs, base, 1, final_act, target, valid, rip)):
             path = f"block/{attr}/{i}"

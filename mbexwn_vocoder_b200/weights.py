@@ -64,6 +64,8 @@ def init_synthetic(plan: ModelPlan, seed: int = 0, lively: bool = True) -> Dict[
         # sub-net trunks: N(0, 0.02) init leaves activations tiny; scale gains so features are O(1)
         for ops, head_gain in ((plan.pp_ops, 25.0), (plan.ps_ops, 1.5)):
             convs = [op.conv for op in ops if op.kind == "conv"]
+            if not convs:                                      # ps_off: no PS sub-net
+                continue
             for layer in convs[:-1]:
                 out[f"{layer.name}/g"] = (out[f"{layer.name}/g"] * 3.0).astype(np.float32)
             out[f"{convs[-1].name}/g"] = (out[f"{convs[-1].name}/g"] * head_gain).astype(np.float32)

@@ -221,7 +221,12 @@ class OracleMBExWN:
                          target_ups=self.pulse_per_frame, pad_to_valid=mc.get("pp_subnet_use_valid_padding", False),
                          remove_inactive_pad_layers=mc.get("remove_inactive_pad_layers", False),
                          use_prelu=use_prelu, alpha=alpha)
-        self.ps = SubNet(mc["ps_subnet"], "PS", weights, dtype, self.n_ceps, 1, None,
+        self.ps_use_stft = bool(mc.get("ps_use_stft", True))
+        self.ps_off = bool(mc.get("ps_off", False))
+        self.preserve_energy = bool(mc.get("spect_filters_preserve_energy", False))
+        # final width of the PS sub-net: cepstrum, or one log gain per sub-band (custom_pulsed_generator.py:422)
+        ps_final = self.n_ceps if self.ps_use_stft else self.mb_factor
+        self.ps = None if self.ps_off else SubNet(mc["ps_subnet"], "PS", weights, dtype, ps_final, 1, None,
                          pad_to_valid=mc.get("ps_subnet_use_valid_padding", False),
                          remove_inactive_pad_layers=mc.get("remove_inactive_pad_layers", False),
                          use_prelu=use_prelu, alpha=alpha)
@@ -354,8 +359,15 @@ class OracleMBExWN:
         kern = torch.as_tensor(self.h_syn, dtype=x.dtype)[None]                 # (1, S, taps+1)
         return F.conv1d(up, kern)[:, 0]
 
+    def generate_multiband_gain(self, mel: torch.Tensor) -> torch.Tensor:
+        """custom_pulsed_generator.py:857-884 (ps_use_stft = False): exp of the PS sub-net's per-band log gain."""
+        x = self.ps(mel)
+        if self.preserve_energy:
+            x = x - torch.mean(x, dim=-1, keepdim=True)
+        return torch.exp(x)
+
     def generate_excitation(self, mel: torch.Tensor, f0: torch.Tensor, noise: torch.Tensor,
-                            taps: Optional[Dict] = None) -> torch.Tensor:
+                            taps: Optional[Dict] = None, mb_gain: Optional[torch.Tensor] = None) -> torch.Tensor:
         """custom_pulsed_generator.py:886-925.  `noise` is the N(0,1) draw of :906, shape (B, 20T, 1)."""
         pg = self.pulse_generator(f0.detach().cpu().numpy())
         pulse = torch.as_tensor(pg["pulse"], dtype=self.dtype)
@@ -366,6 +378,8 @@ class OracleMBExWN:
             taps.update({"phase": pg["phase"], "index": pg["index"], "frac": pg["frac"], "pulse": pulse, "wn_in": x})
         y = self.wavenet(x, mel, taps)
         sub = self._conv(y, self.post_name)
+        if mb_gain is not None:                                               # :916-917
+            sub = sub * mb_gain[:, :sub.shape[1]]
         exc = self.pqmf_synthesis(sub)
         if taps is not None:
             taps.update({"wn_out": y, "subbands": sub, "excitation": exc})
@@ -429,6 +443,18 @@ class OracleMBExWN:
         synth_length = mel_t.shape[1] * self.hop                               # mel_inverter.py:152
         f0 = self.generate_f0(mel_t) if f0_override is None else torch.as_tensor(f0_override, dtype=self.dtype)
         taps["F0"] = f0
+        if (not self.ps_use_stft) or self.ps_off:                              # custom_pulsed_generator.py:666-674
+            gain = None
+            if not self.ps_off:
+                # ps_gain_interpolator: LinInterp x hop, num_pad_end=1, drop_last=False (:453); the gain is produced at
+                # the sample rate but applied to the sub-band rows, which read its first T * steps values (:917)
+                gain = lin_interp(self.generate_multiband_gain(mel_t), self.hop, num_pad_end=1, drop_last=False)
+                taps["mb_gain"] = gain[:, :mel_t.shape[1] * self.sub_per_frame]
+            sig = self.generate_excitation(mel_t, f0, torch.as_tensor(noise), taps, mb_gain=gain)
+            taps["waveform"] = sig[:, :synth_length]
+            if not return_taps:
+                return {"waveform": taps["waveform"].numpy()}
+            return {k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in taps.items()}
         exc = self.generate_excitation(mel_t, f0, torch.as_tensor(noise), taps)
         vtf = self.generate_specenv(mel_t, f0, taps)
         sig = self.stft_filter(exc, vtf, mel_t.shape[1], f0.shape[1])

@@ -1,0 +1,104 @@
+"""Variants of the spectral-shaping stage (custom_pulsed_generator.py:666-674): ps_use_stft = False
+(per-band gain from the PS sub-net, :857-884) and ps_off, on the CPU (plan / oracle) and against the oracle on the GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from mbexwn_vocoder_b200 import get_config_file, tf_checkpoint as T, weights as W
+from mbexwn_vocoder_b200.config import read_config
+from mbexwn_vocoder_b200.plan import PS_BAND_GAIN, PS_OFF, PS_STFT, build_plan
+from oracle.forward import OracleMBExWN, lin_interp, synthetic_mel, synthetic_noise
+
+VARIANTS = {"band_gain": {"ps_use_stft": False}, "band_gain_centered": {"ps_use_stft": False, "spect_filters_preserve_energy": True},
+            "ps_off": {"ps_off": True}}
+
+
+def _hp(extra):
+    hp = read_config(get_config_file("SPEECH"))
+    hp["mbexwn_config"].update(extra)
+    return hp
+
+
+def test_plan_modes_and_subnet_width():
+    assert build_plan(_hp({}), finalize=False).ps_mode == PS_STFT
+    p = build_plan(_hp(VARIANTS["band_gain"]), finalize=False)
+    assert p.ps_mode == PS_BAND_GAIN and p.ps_ops[-1].conv.cout == p.subbands == 15
+    assert build_plan(_hp(VARIANTS["band_gain_centered"]), finalize=False).ps_preserve_energy
+    q = build_plan(_hp(VARIANTS["ps_off"]), finalize=False)
+    assert q.ps_mode == PS_OFF and q.ps_ops == [] and not any(l.name.startswith("PS_") for l in q.conv_layers())
+    with pytest.raises(NotImplementedError):
+        build_plan(_hp({"spect_filters_preserve_energy": True}), finalize=False)
+
+
+def test_checkpoint_round_trip_of_the_variants(tmp_path):
+    for name, extra in VARIANTS.items():
+        hp = _hp(extra)
+        plan = build_plan(hp, finalize=False)
+        w = W.init_synthetic(plan, seed=2)
+        prefix = str(tmp_path / name / "weights.tf")
+        T.export_weights(prefix, hp, w)
+        got = T.import_weights(prefix, plan)
+        assert sorted(got) == sorted(w) and all(np.array_equal(got[k], w[k]) for k in w)
+
+
+def test_oracle_band_gain_semantics():
+    """The gain sequence is interpolated to the sample rate (x hop) but multiplies the sub-band rows: row r of an utterance
+    reads value r of that sequence (custom_pulsed_generator.py:453, :917); ps_off = the bare PQMF output."""
+    hp = _hp(VARIANTS["band_gain"])
+    plan = build_plan(hp)
+    w = W.init_synthetic(plan, seed=12)
+    orc = OracleMBExWN(hp, w, torch.float32)
+    mel = synthetic_mel(12, 0)[None]
+    nz = synthetic_noise(12 * plan.steps_per_frame, 0)[None]
+    r = orc.forward(mel, nz)
+    assert r["waveform"].shape == (1, 12 * 300) and "vtf" not in r
+    g = orc.generate_multiband_gain(torch.as_tensor(mel))
+    full = lin_interp(g, 300, num_pad_end=1, drop_last=False)
+    assert full.shape == (1, 12 * 300 + 1, 15)
+    assert np.allclose(r["mb_gain"], full[:, :12 * 20].numpy())
+    assert np.allclose(r["mb_gain"][0, 0], g[0, 0].numpy()) and np.all(r["mb_gain"] > 0)
+    # frame 0 -> frame 1 is reached only after 300 rows, i.e. never within a 12-frame (240-row) utterance
+    assert np.allclose(r["mb_gain"][0, 150], 0.5 * (g[0, 0] + g[0, 1]).numpy(), rtol=1e-5)
+    hp_off = _hp(VARIANTS["ps_off"])
+    plan_off = build_plan(hp_off)
+    orc_off = OracleMBExWN(hp_off, W.init_synthetic(plan_off, seed=12), torch.float32)
+    r_off = orc_off.forward(mel, nz)
+    assert np.array_equal(r_off["waveform"], r_off["excitation"][:, :12 * 300])
+
+
+def _model_dir(tmp_path, name):
+    cfg = yaml.safe_load(open(get_config_file("SPEECH")))
+    cfg["mbexwn_config"].update(VARIANTS[name])
+    d = tmp_path / name
+    os.makedirs(d, exist_ok=True)
+    yaml.safe_dump(cfg, open(d / "config.yaml", "w"))
+    return str(d)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_gpu_variants_against_oracle(tmp_path, name):
+    from mbexwn_vocoder_b200.mel_inverter import MELInverter
+    inv = MELInverter(_model_dir(tmp_path, name), device=0, precision="fp32")
+    plan = inv.plan
+    oracle = OracleMBExWN(read_config(inv.config_file), inv.weights, torch.float32)
+    lengths = [33, 9, 1]
+    mels = [synthetic_mel(t, i) for i, t in enumerate(lengths)]
+    noise = [synthetic_noise(t * plan.steps_per_frame, i) for i, t in enumerate(lengths)]
+    f0 = [oracle.generate_f0(torch.as_tensor(m[None])).numpy()[0] for m in mels]
+    refs = [oracle.forward(m[None], z[None], f0_override=f[None]) for m, z, f in zip(mels, noise, f0)]
+    for precision in ("fp32", "f16f8"):
+        inv.precision = precision
+        out, taps = inv.synth_batch(mels, noise=noise, f0=f0, taps=["subbands", "index"])
+        for u in range(len(lengths)):
+            ref = refs[u]
+            assert np.array_equal(taps["index"][u], ref["index"][0].reshape(-1))
+            sub = ref["subbands"][0]                           # after the band gain, i.e. what enters the PQMF
+            assert np.abs(taps["subbands"][u].reshape(sub.shape) - sub).max() <= 1e-4 * np.abs(sub).max(), (precision, u)
+            wav = ref["waveform"][0].astype(np.float64)
+            err = out[u].astype(np.float64) - wav
+            snr = 10 * np.log10(np.sum(wav ** 2) / max(np.sum(err ** 2), 1e-300))
+            assert snr >= 60.0, (precision, u, snr)
