@@ -115,6 +115,8 @@ typedef struct {
      * 2 = ps_off: the PQMF output is the signal (n_ps_ops may be 0) */
     int32_t ps_mode;
     int32_t ps_preserve_energy; /* ps_mode 1: subtract the mean log gain over the bands (:867-876) */
+    int32_t wt_subharm;         /* wavetable_config.add_subharm_chans: sin(2 pi phase / ii), ii = 2 .. n + 1, beside every pulse
+                                   sample (tf_wavetable.py:554-559); wn_cin = pulse_channels * (1 + n) [+ 1 noise] */
 } mbexwn_config_t;
 
 /* One batch on the padded frame grid; all pointers are DEVICE pointers. */

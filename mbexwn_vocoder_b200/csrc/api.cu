@@ -412,6 +412,7 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
         a.nominal_f0 = c.wt_nominal_f0; a.min_tr = c.wt_min_transposition; a.max_tr = c.wt_max_transposition;
         a.grid_norm = c.wt_grid_norm; a.sigma = c.noise_sigma;
         a.pulse_per_frame = c.pulse_per_frame; a.steps_per_frame = c.steps_per_frame; a.pulse_channels = c.pulse_channels;
+        a.subharm = c.wt_subharm;
         a.chunk = c.cumsum_chunk; a.cum = cx.p<float>("cum"); a.chunk_off = cx.p<float>("chunk_off");
         a.chunk_first = b->chunk_first; a.phase_carry = b->phase_carry; a.wn_in = cx.p<float>("wn_in"); a.ld_wn_in = c.wn_cin;
         a.phase_out = cx.p<float>("phase"); a.index_out = cx.p<int32_t>("index"); a.pulse_out = cx.p<float>("pulse");
@@ -579,6 +580,8 @@ int mbexwn_create(const mbexwn_config_t* cfg, mbexwn_handle_t* out) {
     if (cfg->ps_mode == 1 && cfg->ps_ops[cfg->n_ps_ops - 1].ch_out != cfg->subbands) return MBEXWN_ERR_INVALID;
     if (cfg->steps_per_frame * cfg->subbands != cfg->hop) return MBEXWN_ERR_INVALID;
     if (cfg->steps_per_frame * cfg->pulse_channels != cfg->pulse_per_frame) return MBEXWN_ERR_INVALID;
+    if (cfg->wt_subharm < 0 || cfg->wn_cin != cfg->pulse_channels * (1 + cfg->wt_subharm) + (cfg->noise_sigma != 0.f ? 1 : 0))
+        return MBEXWN_ERR_INVALID;
     if (cfg->fft_size < cfg->stft_win || (cfg->fft_size & (cfg->fft_size - 1))) return MBEXWN_ERR_INVALID;
     if (cfg->stft_win != 4 * cfg->hop) return MBEXWN_ERR_UNSUPPORTED;     // 4x overlap (wavegen_1d.py:592)
     if (cfg->norm_enable && (cfg->norm_iters < 1 || cfg->norm_win != 4 * cfg->hop || cfg->norm_smooth_win < 1 ||

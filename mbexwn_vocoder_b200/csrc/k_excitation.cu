@@ -116,10 +116,11 @@ __global__ void pulse_kernel(ExcitationArgs a, FrameGrid g) {
     const long long step = n / a.pulse_channels;
     const int ch = (int)(n - step * a.pulse_channels);
     float* row = a.wn_in + step * a.ld_wn_in;
+    const int per = 1 + a.subharm;                     // values per pulse sample: pulse [+ sub-harmonic sinusoids]
     long long lo, hi;
     if (!utt_bounds(g, a.pulse_per_frame, n, lo, hi)) {
-        row[ch] = 0.f;
-        if (ch == 0 && a.sigma != 0.f) row[a.pulse_channels] = 0.f;
+        for (int j = 0; j < per; ++j) row[ch * per + j] = 0.f;
+        if (ch == 0 && a.sigma != 0.f) row[a.pulse_channels * per] = 0.f;
         if (a.phase_out) a.phase_out[n] = 0.f;
         if (a.index_out) a.index_out[n] = 0;
         if (a.pulse_out) a.pulse_out[n] = 0.f;
@@ -158,11 +159,17 @@ __global__ void pulse_kernel(ExcitationArgs a, FrameGrid g) {
             acc = __fadd_rn(acc, __fmul_rn(s, w));
         }
     }
-    row[ch] = acc;
+    row[ch * per] = acc;
+    if (a.subharm > 0) {
+        // add_subharm_chans (tf_wavetable.py:520-521, :554-559): sin(2 pi phase / ii), ii = 2 .. subharm + 1, folded into
+        // the WaveNet row together with the pulse sample (custom_pulsed_generator.py:893)
+        const float w2pi = __fmul_rn(__fmul_rn(phase, 2.f), 3.14159274101257324f);
+        for (int j = 1; j < per; ++j) row[ch * per + j] = sinf(__fdiv_rn(w2pi, (float)(j + 1)));
+    }
     if (ch == 0 && a.sigma != 0.f) {
         const long long lstep = step - lo / a.pulse_channels;
         float z = a.noise ? a.noise[step] : philox_normal(a.seed, (unsigned)(a.utt_ids ? a.utt_ids[u] : u), (unsigned long long)lstep);
-        row[a.pulse_channels] = __fmul_rn(a.sigma, z);
+        row[a.pulse_channels * per] = __fmul_rn(a.sigma, z);
     }
     if (a.phase_out) a.phase_out[n] = phase;
     if (a.index_out) a.index_out[n] = i0;

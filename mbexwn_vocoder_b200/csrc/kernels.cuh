@@ -73,12 +73,13 @@ struct ExcitationArgs {
     float nominal_f0, min_tr, max_tr, grid_norm;
     float sigma;
     int pulse_per_frame, steps_per_frame, pulse_channels;
+    int subharm;            // add_subharm_chans: extra sin(2 pi phase / ii) values per pulse sample (tf_wavetable.py:554-559)
     int chunk;              // cumsum chunk (1000, tf_wavetable.py:429)
     float* cum;             // scratch (frames * pulse_per_frame): in-chunk running sums
     float* chunk_off;       // scratch (n_chunks_total): per chunk offsets
     const int32_t* chunk_first;  // [n_utt + 1] first chunk slot of each utterance (exclusive scan)
     const float* phase_carry;    // [n_utt] or nullptr: running sum of the chunk totals before the utterance's first chunk
-    float* wn_in;           // (frames * steps_per_frame, ld_wn_in): pulse_channels pulse samples [+ noise]
+    float* wn_in;           // (frames * steps_per_frame, ld_wn_in): pulse_channels x (1 + subharm) values [+ noise]
     int ld_wn_in;
     float* phase_out;       // optional taps (frames * pulse_per_frame)
     int32_t* index_out;

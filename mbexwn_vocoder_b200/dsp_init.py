@@ -247,10 +247,11 @@ def build_wavetables(sample_rate: float, nominalF0: float, maxF0: Optional[float
                      nominalBandWidth: Optional[float] = None, **unsupported) -> WaveTables:
     """Wavetable bank of PulseWaveTable.__init__ (tf_wavetable.py:182-307).
 
-    Options that change the run-time path (sinusoid tables, sub-harmonic channels, pulse-synchronous
-    gains, trainable tables) are not part of the MBExWN inference path and are rejected.
+    Options that change the run-time path (sinusoid tables, pulse-synchronous gains, trainable tables) are not part
+    of the MBExWN inference path and are rejected; ``add_subharm_chans`` does not touch the tables (it adds sinusoid
+    channels at run time, tf_wavetable.py:554-559) and is handled by the plan / pulse kernel.
     """
-    for key in ("use_sinusoid", "use_sinusoid_as_fun", "use_white_pulse", "add_subharm_chans",
+    for key in ("use_sinusoid", "use_sinusoid_as_fun", "use_white_pulse",
                 "pulse_sync_gain_avg", "no_interp", "trainable"):
         if unsupported.get(key):
             raise NotImplementedError(f"wavetable_config.{key} is not supported on the B200 path")

@@ -72,6 +72,7 @@ def make_config(plan: ModelPlan) -> _cabi.Config:
     c.pqmf_q, c.pqmf_back = plan.pqmf_q, plan.pqmf_back
     c.halo_frames = engine_halo(plan)
     c.ps_mode, c.ps_preserve_energy = plan.ps_mode, int(plan.ps_preserve_energy)
+    c.wt_subharm = plan.subharm
     if plan.norm is not None:
         nm = plan.norm
         c.norm_enable, c.norm_iters, c.norm_win, c.norm_smooth_win = 1, nm.iters, nm.win, nm.smooth_win

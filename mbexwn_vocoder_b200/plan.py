@@ -127,6 +127,7 @@ class ModelPlan:
     env_order_scale: Optional[float]
     wavetable_cfg: Dict
     max_halo_frames: int = 1
+    subharm: int = 0            # wavetable_config.add_subharm_chans
     ps_mode: int = PS_STFT      # PS_STFT | PS_BAND_GAIN | PS_OFF
     ps_preserve_energy: bool = False
     norm: Optional["NormMelSpec"] = None     # NormMelComponents (normalize_rms_from_mell), None = off
@@ -374,7 +375,8 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
     dil = [2 ** ((i // step) % max_log2) if max_log2 is not None else 2 ** (i // step) for i in range(n_layers)]
     sigma = mc.get("pp_mod_subnet_noise_channel_sigma", 0.5)
     steps_per_frame = int(round(wn_rate / spect_rate))
-    wn = WaveNetSpec(name="PP_waveNetBlock_ups1_0", c=c, c_in=pch + (1 if sigma else 0),
+    subharm = int(mc["wavetable_config"].get("add_subharm_chans", 0) or 0)             # tf_wavetable.py:212, :554-559
+    wn = WaveNetSpec(name="PP_waveNetBlock_ups1_0", c=c, c_in=pch * (1 + subharm) + (1 if sigma else 0),
                      c_out=int(wn_cfg["n_out_channels"]), n_layers=n_layers, k=k, dilations=dil,
                      gate=_GATES[gate], cond_k=cond_k,
                      cond_conv_up=int(wn_rate // (spect_rate * cond_lin)), cond_lin_up=cond_lin,
@@ -391,7 +393,7 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
         pqmf_cfg=mb, stft_win=win, fft_size=fft,
         filter_max_log_range=(fdb / (20 * np.log10(np.exp(1)))) if fdb is not None else None,
         env_order_scale=mc.get("ps_env_order_scale"), wavetable_cfg=copy.deepcopy(mc["wavetable_config"]), norm=norm,
-        ps_mode=ps_mode, ps_preserve_energy=preserve_energy)
+        ps_mode=ps_mode, ps_preserve_energy=preserve_energy, subharm=subharm)
     half_span = max(d * (k - 1) // 2 for d in dil)
     plan.max_halo_frames = max(1, -(-half_span // steps_per_frame))
     if finalize:

@@ -250,6 +250,7 @@ class OracleMBExWN:
         self.win_size, self.fft_size = dsp_init.stft_sizes(self.sample_rate, self.hop, mc.get("internal_win_size_s"),
                                                            int(mc.get("internal_fft_over", 0)))
         self.wt = dsp_init.build_wavetables(sample_rate=self.pulse_rate, **mc["wavetable_config"])
+        self.subharm = int(mc["wavetable_config"].get("add_subharm_chans", 0) or 0)
         self.taps = mb["taps"]
         _, self.h_syn = dsp_init.pqmf_filters(mb["subbands"], mb["taps"], mb["cutoff_ratio"], mb["beta"])
         self.window = dsp_init.hann_periodic(self.win_size)
@@ -371,7 +372,14 @@ class OracleMBExWN:
         """custom_pulsed_generator.py:886-925.  `noise` is the N(0,1) draw of :906, shape (B, 20T, 1)."""
         pg = self.pulse_generator(f0.detach().cpu().numpy())
         pulse = torch.as_tensor(pg["pulse"], dtype=self.dtype)
-        x = pulse.reshape(pulse.shape[0], -1, self.pulse_channels)
+        if self.subharm:                                                       # tf_wavetable.py:520-521, :554-559
+            dt = self.np_dtype
+            w2pi = pg["phase"].astype(dt) * dt(2) * dt(np.float32(np.pi))
+            chans = [pg["pulse"].astype(dt)] + [np.sin(w2pi / dt(ii)) for ii in range(2, self.subharm + 2)]
+            pulse_all = torch.as_tensor(np.stack(chans, axis=-1), dtype=self.dtype)
+            x = pulse_all.reshape(pulse.shape[0], -1, self.pulse_channels * (1 + self.subharm))   # custom_pulsed_generator.py:893
+        else:
+            x = pulse.reshape(pulse.shape[0], -1, self.pulse_channels)
         if self.sigma:
             x = torch.cat((x, self.sigma * noise.to(self.dtype)), dim=-1)
         if taps is not None:

@@ -12,7 +12,8 @@ from mbexwn_vocoder_b200.config import read_config
 from mbexwn_vocoder_b200.plan import PS_BAND_GAIN, PS_OFF, PS_STFT, build_plan
 from oracle.forward import OracleMBExWN, lin_interp, synthetic_mel, synthetic_noise
 
-VARIANTS = {"band_gain": {"ps_use_stft": False}, "band_gain_centered": {"ps_use_stft": False, "spect_filters_preserve_energy": True},
+VARIANTS = {"subharm": {"wavetable_config": {"nominalF0": 60, "maxF0": 550, "add_subharm_chans": 2}},
+            "band_gain": {"ps_use_stft": False}, "band_gain_centered": {"ps_use_stft": False, "spect_filters_preserve_energy": True},
             "ps_off": {"ps_off": True}}
 
 
@@ -31,6 +32,24 @@ def test_plan_modes_and_subnet_width():
     assert q.ps_mode == PS_OFF and q.ps_ops == [] and not any(l.name.startswith("PS_") for l in q.conv_layers())
     with pytest.raises(NotImplementedError):
         build_plan(_hp({"spect_filters_preserve_energy": True}), finalize=False)
+
+
+def test_subharmonic_channels_widen_the_wavenet_input():
+    """wavetable_config.add_subharm_chans = n: every pulse sample brings sin(2 pi phase / ii), ii = 2 .. n + 1, along
+    (tf_wavetable.py:554-559); rows are [p0 s0,2 s0,3 p1 s1,2 ... | noise] (custom_pulsed_generator.py:893)."""
+    hp = _hp(VARIANTS["subharm"])
+    plan = build_plan(hp)
+    assert plan.subharm == 2 and plan.wavenet.c_in == 5 * 3 + 1
+    assert [l for l in plan.conv_layers() if l.name.endswith("/start")][0].cin == 16
+    orc = OracleMBExWN(hp, W.init_synthetic(plan, seed=12), torch.float32)
+    mel = synthetic_mel(6, 0)[None]
+    r = orc.forward(mel, synthetic_noise(6 * plan.steps_per_frame, 0)[None])
+    x = r["wn_in"][0]
+    assert x.shape == (6 * 20, 16)
+    ph = r["phase"][0].reshape(-1, 5)
+    assert np.allclose(x[:, 0::3][:, :5], r["pulse"][0].reshape(-1, 5))
+    assert np.allclose(x[:, 1::3][:, :5], np.sin(2 * np.pi * ph / 2), atol=1e-6)
+    assert np.allclose(x[:, 2::3][:, :5], np.sin(2 * np.pi * ph / 3), atol=1e-6)
 
 
 def test_checkpoint_round_trip_of_the_variants(tmp_path):
@@ -96,6 +115,10 @@ def test_gpu_variants_against_oracle(tmp_path, name):
         for u in range(len(lengths)):
             ref = refs[u]
             assert np.array_equal(taps["index"][u], ref["index"][0].reshape(-1))
+            if name == "subharm":
+                x = ref["wn_in"][0]
+                got = inv.synth_batch(mels, noise=noise, f0=f0, taps=["wn_in"])[1]["wn_in"][u].reshape(x.shape)
+                assert np.abs(got - x).max() <= 1e-5 * np.abs(x).max()
             sub = ref["subbands"][0]                           # after the band gain, i.e. what enters the PQMF
             assert np.abs(taps["subbands"][u].reshape(sub.shape) - sub).max() <= 1e-4 * np.abs(sub).max(), (precision, u)
             wav = ref["waveform"][0].astype(np.float64)
