@@ -35,7 +35,10 @@ __device__ __forceinline__ int find_utt(const int32_t* chunk_first, int n_utt, i
 
 __global__ void __launch_bounds__(CHUNK_WARPS * 32)
 phase_chunk_kernel(ExcitationArgs a, FrameGrid g, int n_chunks_total) {
-    __shared__ float buf[CHUNK_WARPS][MAX_CHUNK];
+    // separate input / output stages: the sequential lane streams float4s in and out without load-after-store hazards,
+    // so the 1000-long chain runs at the latency of its dependent adds
+    __shared__ __align__(16) float buf_in[CHUNK_WARPS][MAX_CHUNK];
+    __shared__ __align__(16) float buf_out[CHUNK_WARPS][MAX_CHUNK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x * CHUNK_WARPS + warp;
     if (c >= n_chunks_total) return;
@@ -45,21 +48,34 @@ phase_chunk_kernel(ExcitationArgs a, FrameGrid g, int n_chunks_total) {
     const long long n_u = (long long)(g.utt_end[u] - g.utt_begin[u]) * a.pulse_per_frame;
     const long long s0 = (long long)j * a.chunk;
     const int n = (int)min((long long)a.chunk, n_u - s0);
-    float* sb = buf[warp];
-    for (int i = lane; i < n; i += 32) sb[i] = __fdiv_rn(a.f0[base + s0 + i], a.pulse_rate);
+    const int n8 = (n + 7) & ~7;
+    float* __restrict__ si = buf_in[warp];
+    float* __restrict__ so = buf_out[warp];
+    // zero padding up to a multiple of 8 leaves the running sum unchanged (x + 0 is exact)
+    for (int i = lane; i < n8; i += 32) si[i] = i < n ? __fdiv_rn(__ldg(a.f0 + base + s0 + i), a.pulse_rate) : 0.f;
     __syncwarp();
     if (lane == 0) {
         float acc = 0.f;
-#pragma unroll 8
-        for (int i = 0; i < n; ++i) {
-            acc = __fadd_rn(acc, sb[i]);
-            sb[i] = acc;
+#pragma unroll 4
+        for (int i = 0; i < n8; i += 8) {
+            const float4 x0 = *reinterpret_cast<const float4*>(si + i), x1 = *reinterpret_cast<const float4*>(si + i + 4);
+            float4 y0, y1;
+            acc = __fadd_rn(acc, x0.x); y0.x = acc;
+            acc = __fadd_rn(acc, x0.y); y0.y = acc;
+            acc = __fadd_rn(acc, x0.z); y0.z = acc;
+            acc = __fadd_rn(acc, x0.w); y0.w = acc;
+            acc = __fadd_rn(acc, x1.x); y1.x = acc;
+            acc = __fadd_rn(acc, x1.y); y1.y = acc;
+            acc = __fadd_rn(acc, x1.z); y1.z = acc;
+            acc = __fadd_rn(acc, x1.w); y1.w = acc;
+            *reinterpret_cast<float4*>(so + i) = y0;
+            *reinterpret_cast<float4*>(so + i + 4) = y1;
         }
         // zero padding up to the chunk size leaves the last running sum unchanged
         a.chunk_off[c] = wrap1(acc);
     }
     __syncwarp();
-    for (int i = lane; i < n; i += 32) a.cum[base + s0 + i] = sb[i];
+    for (int i = lane; i < n; i += 32) a.cum[base + s0 + i] = so[i];
 }
 
 __global__ void chunk_offset_kernel(ExcitationArgs a, FrameGrid g) {
@@ -109,16 +125,19 @@ __device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned
     return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
 }
 
+// IDX = unsigned when the grid holds fewer than 2^31 pulse samples (32-bit divisions), long long otherwise
+template <class IDX>
 __global__ void pulse_kernel(ExcitationArgs a, FrameGrid g) {
-    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // pulse-rate sample on the grid
-    const long long total = (long long)g.n_frames * a.pulse_per_frame;
+    const IDX n = (IDX)blockIdx.x * (IDX)blockDim.x + (IDX)threadIdx.x;        // pulse-rate sample on the grid
+    const IDX total = (IDX)g.n_frames * (IDX)a.pulse_per_frame;
     if (n >= total) return;
-    const long long step = n / a.pulse_channels;
-    const int ch = (int)(n - step * a.pulse_channels);
-    float* row = a.wn_in + step * a.ld_wn_in;
+    const IDX step = n / (IDX)a.pulse_channels;
+    const int ch = (int)(n - step * (IDX)a.pulse_channels);
+    float* row = a.wn_in + (long long)step * a.ld_wn_in;
     const int per = 1 + a.subharm;                     // values per pulse sample: pulse [+ sub-harmonic sinusoids]
-    long long lo, hi;
-    if (!utt_bounds(g, a.pulse_per_frame, n, lo, hi)) {
+    const int f = (int)(n / (IDX)a.pulse_per_frame);
+    const int u = g.frame_utt[f];
+    if (u < 0) {
         for (int j = 0; j < per; ++j) row[ch * per + j] = 0.f;
         if (ch == 0 && a.sigma != 0.f) row[a.pulse_channels * per] = 0.f;
         if (a.phase_out) a.phase_out[n] = 0.f;
@@ -126,10 +145,9 @@ __global__ void pulse_kernel(ExcitationArgs a, FrameGrid g) {
         if (a.pulse_out) a.pulse_out[n] = 0.f;
         return;
     }
-    const int f = (int)(n / a.pulse_per_frame);
-    const int u = g.frame_utt[f];
-    const long long local = n - lo;
-    const int c = a.chunk_first[u] + (int)(local / a.chunk);
+    const IDX lo = (IDX)g.utt_begin[u] * (IDX)a.pulse_per_frame;
+    const IDX local = n - lo;
+    const int c = a.chunk_first[u] + (int)(local / (IDX)a.chunk);
     // phase = ((cum + offset) mod 1)   (tf_wavetable.py:483-486)
     const float phase = wrap1(__fadd_rn(a.cum[n], a.chunk_off[c]));
     // _linear_lookup (tf_wavetable.py:621-638)
@@ -167,7 +185,7 @@ __global__ void pulse_kernel(ExcitationArgs a, FrameGrid g) {
         for (int j = 1; j < per; ++j) row[ch * per + j] = sinf(__fdiv_rn(w2pi, (float)(j + 1)));
     }
     if (ch == 0 && a.sigma != 0.f) {
-        const long long lstep = step - lo / a.pulse_channels;
+        const IDX lstep = step - lo / (IDX)a.pulse_channels;
         float z = a.noise ? a.noise[step] : philox_normal(a.seed, (unsigned)(a.utt_ids ? a.utt_ids[u] : u), (unsigned long long)lstep);
         row[a.pulse_channels * per] = __fmul_rn(a.sigma, z);
     }
@@ -184,7 +202,8 @@ cudaError_t launch_excitation(const ExcitationArgs& a, const FrameGrid& g, int n
     phase_chunk_kernel<<<(n_chunks_total + CHUNK_WARPS - 1) / CHUNK_WARPS, CHUNK_WARPS * 32, 0, s>>>(a, g, n_chunks_total);
     chunk_offset_kernel<<<(g.n_utt * 32 + 127) / 128, 128, 0, s>>>(a, g);
     long long total = (long long)g.n_frames * a.pulse_per_frame;
-    pulse_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, g);
+    if (total < (1ll << 31) - 256) pulse_kernel<unsigned><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, g);
+    else pulse_kernel<long long><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, g);
     return cudaGetLastError();
 }
 
