@@ -160,6 +160,10 @@ MBEXWN_API const char* mbexwn_last_error(mbexwn_handle_t h);
  *   "<wn_name>/tc/rb_<i>" fp32 in the same row order (layer 0 carries all skip biases @ W_end + b_end) */
 MBEXWN_API int mbexwn_set_tensor(mbexwn_handle_t h, const char* name, const void* dev_ptr, size_t n_bytes);
 
+/* Host-side copy of a one-element tensor (e.g. the bias "<name>/b" of a conv with one output channel) so that fused kernels
+ * can take it as a launch argument; optional -- without it the un-fused kernels run. */
+MBEXWN_API int mbexwn_set_scalar(mbexwn_handle_t h, const char* name, float value);
+
 /* ---- forward: stands in for MELInverter.synth_from_mel / PaNWaveNet.infer ---- */
 MBEXWN_API size_t mbexwn_workspace_bytes(mbexwn_handle_t h, int32_t n_frames, int32_t n_chunks, int32_t precision);
 MBEXWN_API int mbexwn_forward(mbexwn_handle_t h, const mbexwn_batch_t* batch, int32_t precision,
@@ -197,6 +201,7 @@ MBEXWN_API int mbexwn_last_launch_count(mbexwn_handle_t h);
  * "stage_timing" (default 0): record CUDA events on the caller's stream at the stage boundaries of each forward;
  * "tc_cta_group" (1 or 2): tensor-core tiles owned by one CTA or by a CTA pair (cluster of 2, tcgen05 cta_group::2);
  * "tc_cond_stage" (default 1): the gate epilogue reads its conditioning rows from a shared-memory stage (0: global);
+ * "fuse_tail" (default 1): the LinInterp -> 1x1 -> LinInterp end of the F0 sub-net runs as one kernel;
  * "stop_after_f0" (default 0): return after the F0 sub-net (tap "F0"), for the F0 pass of chunked long-form synthesis;
  * "tc8_h_lo" / "tc8_a_lo": log2 scale of the e4m3 lo8 planes of the residual stream / gated activations (F16F8). */
 MBEXWN_API int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value);

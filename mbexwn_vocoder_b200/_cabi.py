@@ -89,6 +89,7 @@ SYMBOLS = {
     "mbexwn_destroy": (None, [C.c_void_p]),
     "mbexwn_last_error": (C.c_char_p, [C.c_void_p]),
     "mbexwn_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),
+    "mbexwn_set_scalar": (C.c_int, [C.c_void_p, C.c_char_p, C.c_float]),
     "mbexwn_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "mbexwn_forward": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mbexwn_forward_host": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -20,6 +20,8 @@ struct mbexwn_handle_s {
     int stage_timing = 0;
     int stop_after_f0 = 0;      // option: F0 pass of chunked long-form synthesis
     int tc_subnets = 1;         // wide sub-net / conditioning convs on the tensor cores (TC precisions only)
+    int fuse_tail = 1;          // LinInterp -> 1x1 -> LinInterp tail of a sub-net as one launch
+    std::map<std::string, float> host_scalars;   // one-element tensors whose value the host knows (mbexwn_set_scalar)
     cudaEvent_t ev[MBEXWN_N_STAGES + 1] = {};
     bool ev_ready = false;
     bool ev_recorded = false;
@@ -179,6 +181,36 @@ static ConvArgs conv_args(const mbexwn_config_t& c, const mbexwn_op_t& op, int r
     return a;
 }
 
+// ops[i .. i + 2] = LinInterp + act, 1x1 conv to one channel, LinInterp + act ending the program: one fused launch.
+// Returns 1 if it ran, 0 if the pattern does not apply, < 0 on error.
+static int try_subnet_tail(Ctx& cx, const mbexwn_op_t* ops, int n_ops, int i, const float* cur, float* final_out) {
+    mbexwn_handle_t h = cx.h;
+    const mbexwn_config_t& c = h->cfg;
+    if (!h->fuse_tail || i + 2 != n_ops - 1) return 0;
+    const mbexwn_op_t &l1 = ops[i], &cv = ops[i + 1], &l2 = ops[i + 2];
+    if (l1.kind != 1 || cv.kind != 0 || l2.kind != 1 || cv.k != 1 || cv.cout != 1 || cv.act != ACT_NONE ||
+        cv.cin != l1.ch_out || cv.subpixel > 1 || cv.rate_in != l1.rate_out || l2.rate_in != cv.rate_out)
+        return 0;
+    int rc = 0;
+    SubnetTailArgs a{};
+    a.x = cur; a.out = final_out; a.rows_in = (long long)cx.g.n_frames * l1.rate_in; a.rate_in = l1.rate_in;
+    a.ch = l1.ch_out; a.up1 = l1.up; a.up2 = l2.up; a.act1 = l1.act; a.act2 = l2.act;
+    a.leaky = c.leaky_alpha; a.a0 = c.f0_span; a.a1 = c.f0_min;
+    if (!subnet_tail_supported(a)) return 0;
+    if (l1.act == ACT_PRELU) {
+        a.alpha1 = tensor(h, std::string(l1.act_name) + "/alpha", (size_t)l1.act_channels * 4, &rc);
+        if (!a.alpha1) return rc;
+    }
+    a.w = tensor(h, std::string(cv.name) + "/W", (size_t)cv.cin * 4, &rc);
+    if (!a.w) return rc;
+    auto it = h->host_scalars.find(std::string(cv.name) + "/b");
+    if (it == h->host_scalars.end()) return 0;               // bias value not known on the host: keep the three launches
+    a.bias = it->second;
+    MBX_CUDA_CHECK(launch_subnet_tail(a, cx.g, cx.s));
+    h->launches++;
+    return 1;
+}
+
 // Run one mel-rate sub-net program; the last op writes into `final_out`.
 static int run_subnet(Ctx& cx, const mbexwn_op_t* ops, int n_ops, const float* input, float* final_out) {
     mbexwn_handle_t h = cx.h;
@@ -190,6 +222,12 @@ static int run_subnet(Ctx& cx, const mbexwn_op_t* ops, int n_ops, const float* i
         const mbexwn_op_t& op = ops[i];
         float* out = (i == n_ops - 1) ? final_out : bufs[flip];
         int rc = 0;
+        if (op.kind == 1) {
+            rc = try_subnet_tail(cx, ops, n_ops, i, cur, final_out);
+            if (rc < 0) return rc;
+            if (rc == 1) return MBEXWN_OK;
+            rc = 0;
+        }
         const float* alpha = nullptr;
         if (op.act == ACT_PRELU) {
             alpha = tensor(h, std::string(op.act_name) + "/alpha", (size_t)op.act_channels * 4, &rc);
@@ -282,6 +320,12 @@ static int run_subnet_tc(Ctx& cx, const mbexwn_op_t* ops, int n_ops, const float
             continue;
         }
         if (!cur) return fail(h, MBEXWN_ERR_INVALID, "sub-net op needs fp32 activations");
+        if (op.kind == 1) {
+            rc = try_subnet_tail(cx, ops, n_ops, i, cur, final_out);
+            if (rc < 0) return rc;
+            if (rc == 1) return MBEXWN_OK;
+            rc = 0;
+        }
         float* out = last ? final_out : bufs[flip];
         if (op.kind == 0) {
             const float* w = tensor(h, std::string(op.name) + "/W", (size_t)op.k * op.cin * op.cout * 4, &rc);
@@ -618,6 +662,12 @@ int mbexwn_set_tensor(mbexwn_handle_t h, const char* name, const void* dev_ptr, 
     return MBEXWN_OK;
 }
 
+int mbexwn_set_scalar(mbexwn_handle_t h, const char* name, float value) {
+    if (!h || !name) return MBEXWN_ERR_INVALID;
+    h->host_scalars[name] = value;
+    return MBEXWN_OK;
+}
+
 size_t mbexwn_workspace_bytes(mbexwn_handle_t h, int32_t n_frames, int32_t n_chunks, int32_t precision) {
     if (!h || n_frames <= 0) return 0;
     return mbx::carve(h->cfg, n_frames, n_chunks, precision, h->debug_taps).total;
@@ -711,6 +761,7 @@ int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value) {
     if (!strcmp(name, "stage_timing")) { h->stage_timing = value ? 1 : 0; h->tc.time_launches = h->stage_timing; return MBEXWN_OK; }
     if (!strcmp(name, "tc_cta_group")) { h->tc.cta_group = value == 2 ? 2 : 1; return MBEXWN_OK; }
     if (!strcmp(name, "tc_subnets")) { h->tc_subnets = value ? 1 : 0; return MBEXWN_OK; }
+    if (!strcmp(name, "fuse_tail")) { h->fuse_tail = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "tc_cond_stage")) { h->tc.cond_stage = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "stop_after_f0")) { h->stop_after_f0 = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "tc_debug")) { h->tc.debug = value; return MBEXWN_OK; }

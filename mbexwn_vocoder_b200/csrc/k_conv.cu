@@ -104,27 +104,119 @@ conv1d_kernel(ConvArgs a, FrameGrid g) {
     }
 }
 
+constexpr int LIN_MAX_UP = 512;
+
 __global__ void lininterp_kernel(LinInterpArgs a, FrameGrid g) {
     // one thread per output element; w0 = (U-u)/U, w1 = u/U evaluated in double and rounded to float like the
-    // reference's float64 -> float32 kernel initialiser (support_layers.py:19-27)
+    // reference's float64 -> float32 kernel initialiser (support_layers.py:19-27), once per block
+    __shared__ float sw0[LIN_MAX_UP], sw1[LIN_MAX_UP];
+    const bool tab = a.up <= LIN_MAX_UP;
+    if (tab) {
+        for (int u = threadIdx.x; u < a.up; u += blockDim.x) {
+            sw0[u] = (float)((double)(a.up - u) / (double)a.up);
+            sw1[u] = (float)((double)u / (double)a.up);
+        }
+        __syncthreads();
+    }
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = a.rows_in * a.up * a.ch;
     if (idx >= total) return;
-    int c = (int)(idx % a.ch);
-    long long ro = idx / a.ch;
-    long long ri = ro / a.up;
-    int u = (int)(ro - ri * a.up);
+    int c;
+    long long ro, ri;
+    int u;
+    if (total < (1ll << 31)) {                            // 32-bit divisions on the common path
+        const unsigned i32 = (unsigned)idx;
+        const unsigned ro32 = i32 / (unsigned)a.ch, ri32 = ro32 / (unsigned)a.up;
+        c = (int)(i32 - ro32 * (unsigned)a.ch);
+        u = (int)(ro32 - ri32 * (unsigned)a.up);
+        ro = ro32; ri = ri32;
+    } else {
+        c = (int)(idx % a.ch);
+        ro = idx / a.ch;
+        ri = ro / a.up;
+        u = (int)(ro - ri * a.up);
+    }
     long long lo, hi;
     float v = 0.f;
     if (utt_bounds(g, a.rate_in, ri, lo, hi)) {
         long long rn = ri + 1 < hi ? ri + 1 : hi - 1;
-        float w0 = (float)((double)(a.up - u) / (double)a.up);
-        float w1 = (float)((double)u / (double)a.up);
+        const float w0 = tab ? sw0[u] : (float)((double)(a.up - u) / (double)a.up);
+        const float w1 = tab ? sw1[u] : (float)((double)u / (double)a.up);
         v = __fadd_rn(__fmul_rn(a.x[ri * a.ch + c], w0), __fmul_rn(a.x[rn * a.ch + c], w1));
         float al = a.act == ACT_PRELU ? a.alpha[c] : a.leaky;
         v = apply_act(v, a.act, al, a.a0, a.a1);
     }
     a.out[idx] = v;
+}
+
+// Fused tail of a sub-net: LinInterp(up1) + activation -> 1x1 conv to ONE channel -> LinInterp(up2) + activation, the shape of
+// the F0 sub-net's end (custom_pulsed_generator.py:86-90, :134-146: "[k, C, 'L5']" layer, PulsPar_Layer_final, the missing
+// up-sampling factor, soft-sigmoid).  One block = TAIL_Z rows at the intermediate rate (+ 1 look-ahead row): thread = row computes
+// the interpolated, activated C-vector on the fly and its dot product with the 1x1 kernel; the block then writes the
+// TAIL_Z * up2 outputs.  Same per-element arithmetic as lininterp_kernel / conv1d_kernel / lininterp_kernel in sequence.
+constexpr int TAIL_Z = 128, TAIL_MAX_C = 128;
+
+__global__ void __launch_bounds__(TAIL_Z)
+subnet_tail_kernel(SubnetTailArgs a, FrameGrid g) {
+    __shared__ float z[TAIL_Z + 1];
+    __shared__ float w[TAIL_MAX_C], al[TAIL_MAX_C];
+    __shared__ float w0a[LIN_MAX_UP], w1a[LIN_MAX_UP], w0b[LIN_MAX_UP], w1b[LIN_MAX_UP];
+    __shared__ long long jhi[TAIL_Z + 1];                 // utterance end at the intermediate rate, -1 for guard rows
+    const int t = threadIdx.x;
+    for (int c = t; c < a.ch; c += TAIL_Z) {
+        w[c] = a.w[c];
+        al[c] = a.act1 == ACT_PRELU ? a.alpha1[c] : a.leaky;
+    }
+    for (int u = t; u < a.up1; u += TAIL_Z) {
+        w0a[u] = (float)((double)(a.up1 - u) / (double)a.up1);
+        w1a[u] = (float)((double)u / (double)a.up1);
+    }
+    for (int u = t; u < a.up2; u += TAIL_Z) {
+        w0b[u] = (float)((double)(a.up2 - u) / (double)a.up2);
+        w1b[u] = (float)((double)u / (double)a.up2);
+    }
+    __syncthreads();
+    const long long rows_mid = a.rows_in * a.up1;
+    const long long j0 = (long long)blockIdx.x * TAIL_Z;
+    for (int i = t; i < TAIL_Z + 1; i += TAIL_Z) {
+        const long long j = j0 + i;
+        float acc = 0.f;
+        long long end = -1;
+        if (j < rows_mid) {
+            const long long ri = j / a.up1;
+            const int u = (int)(j - ri * a.up1);
+            long long lo, hi;
+            if (utt_bounds(g, a.rate_in, ri, lo, hi)) {
+                const long long rn = ri + 1 < hi ? ri + 1 : hi - 1;
+                const float* x0 = a.x + ri * a.ch;
+                const float* x1 = a.x + rn * a.ch;
+                const float f0 = w0a[u], f1 = w1a[u];
+                for (int c = 0; c < a.ch; ++c) {
+                    float v = __fadd_rn(__fmul_rn(__ldg(x0 + c), f0), __fmul_rn(__ldg(x1 + c), f1));
+                    v = apply_act(v, a.act1, al[c], 0.f, 0.f);
+                    acc = fmaf(v, w[c], acc);
+                }
+                acc += a.bias;
+                end = hi * a.up1;
+            }
+        }
+        z[i] = acc;
+        jhi[i] = end;
+    }
+    __syncthreads();
+    const long long total = rows_mid * a.up2;
+    const long long o0 = j0 * a.up2;
+    for (int o = t; o < TAIL_Z * a.up2; o += TAIL_Z) {
+        if (o0 + o >= total) break;
+        const int jl = o / a.up2, v = o - jl * a.up2;
+        float r = 0.f;
+        if (jhi[jl] >= 0) {
+            const int jn = (j0 + jl + 1 < jhi[jl]) ? jl + 1 : jl;
+            r = __fadd_rn(__fmul_rn(z[jl], w0b[v]), __fmul_rn(z[jn], w1b[v]));
+            r = apply_act(r, a.act2, a.leaky, a.a0, a.a1);
+        }
+        a.out[o0 + o] = r;
+    }
 }
 
 __global__ void gate_kernel(GateArgs a, FrameGrid g) {
@@ -186,6 +278,19 @@ cudaError_t launch_conv1d(const ConvArgs& a, const FrameGrid& g, cudaStream_t s)
     if (a.rows <= 0) return cudaSuccess;
     dim3 grid((unsigned)((a.rows + BM - 1) / BM), (unsigned)((a.cout + BN - 1) / BN));
     conv1d_kernel<<<grid, CONV_THREADS, 0, s>>>(a, g);
+    return cudaGetLastError();
+}
+
+bool subnet_tail_supported(const SubnetTailArgs& a) {
+    return a.ch >= 1 && a.ch <= TAIL_MAX_C && a.up1 >= 1 && a.up1 <= LIN_MAX_UP && a.up2 >= 1 && a.up2 <= LIN_MAX_UP &&
+           a.act2 != ACT_PRELU;
+}
+
+cudaError_t launch_subnet_tail(const SubnetTailArgs& a, const FrameGrid& g, cudaStream_t s) {
+    const long long rows_mid = a.rows_in * a.up1;
+    if (rows_mid <= 0) return cudaSuccess;
+    if (!subnet_tail_supported(a)) return cudaErrorInvalidValue;
+    subnet_tail_kernel<<<(unsigned)((rows_mid + TAIL_Z - 1) / TAIL_Z), TAIL_Z, 0, s>>>(a, g);
     return cudaGetLastError();
 }
 

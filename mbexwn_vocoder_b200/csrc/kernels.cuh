@@ -37,6 +37,22 @@ struct LinInterpArgs {
 };
 cudaError_t launch_lininterp(const LinInterpArgs& a, const FrameGrid& g, cudaStream_t s);
 
+// LinInterp(up1) + act1 -> 1x1 conv to one channel (+ bias) -> LinInterp(up2) + act2, fused (tail of the F0 sub-net)
+struct SubnetTailArgs {
+    const float* x;        // (rows_in, ch) at rate_in rows per frame
+    float* out;            // (rows_in * up1 * up2)
+    long long rows_in;
+    int rate_in, ch, up1, up2;
+    int act1;              // activation after the first interpolation (PReLU / LeakyReLU / none)
+    const float* alpha1;   // PReLU slopes (ch)
+    const float* w;        // (ch) 1x1 kernel
+    float bias;
+    int act2;              // activation after the second interpolation
+    float leaky, a0, a1;
+};
+bool subnet_tail_supported(const SubnetTailArgs& a);
+cudaError_t launch_subnet_tail(const SubnetTailArgs& a, const FrameGrid& g, cudaStream_t s);
+
 struct GateArgs {
     const float* z;        // (rows, 2C) dilated conv output incl. bias
     const float* cond;     // (rows / lin_up, 2C) conditioning at the low rate

@@ -130,6 +130,9 @@ class Engine:
             w, b = W.folded(weights, layer.name)
             self._register(f"{layer.name}/W", w)
             self._register(f"{layer.name}/b", b)
+            if b.size == 1:                                  # lets the fused sub-net tail take the bias as an argument
+                _cabi.check(self.lib, self._handle,
+                            self.lib.mbexwn_set_scalar(self._handle, f"{layer.name}/b".encode(), float(b[0])), "set_scalar")
         for ops in (plan.pp_ops, plan.ps_ops):
             for op in ops:
                 if op.act == ACT_PRELU and op.act_name:
