@@ -402,32 +402,60 @@ __device__ __forceinline__ void epi_plain(const GemmParams& p, uint32_t tacc, lo
 // bias, activation, then fp32 rows and / or the bf16 [hi | lo] planes the next tensor-core conv reads.  A sub-pixel conv
 // (conv_layers.py:250-255) unfolds channel c' of row t to row t * f + c' / (cout / f), channel c' % (cout / f).
 // Guard rows are written as zeros (the next conv's zero padding; mirrored pads are patched by mirror_guards_kernel).
+// 16-column chunks; the bias (and PReLU slope) vectors of a chunk are fetched as float4s before the accumulator wait so that
+// their latency hides behind the MMAs instead of sitting in front of every add (ncu r01k: the per-element __ldg made this
+// epilogue long-scoreboard bound).
 __device__ __forceinline__ void epi_conv(const GemmParams& p, uint32_t tacc, long long row, int n0, int width, int part, int nparts) {
-    float v[32];
+    float v[16], bz[16], al[16];
     bool valid = false;
     if (row < p.rows) {
         long long lo, hi;
         valid = utt_bounds(p.grid, p.rate, row, lo, hi);
     }
-    for (int q = part; q < width / 32; q += nparts) {
-        tmem_ld32(tacc + q * 32, v);
+    for (int q = part; q < width / 16; q += nparts) {
+        const int nq = n0 + q * 16;
+        const bool full = nq + 15 < p.n_cols;
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nq + i));
+                bz[i] = b4.x; bz[i + 1] = b4.y; bz[i + 2] = b4.z; bz[i + 3] = b4.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bz[i] = nq + i < p.n_cols ? __ldg(p.bias + nq + i) : 0.f;
+        }
+        if (p.cv_act == ACT_PRELU) {
+            const int a0 = nq % p.cv_act_mod;
+            if (full && a0 + 16 <= p.cv_act_mod && (a0 & 3) == 0) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.alpha + a0 + i));
+                    al[i] = a4.x; al[i + 1] = a4.y; al[i + 2] = a4.z; al[i + 3] = a4.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) al[i] = nq + i < p.n_cols ? __ldg(p.alpha + (nq + i) % p.cv_act_mod) : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) al[i] = p.leaky;
+        }
+        tmem_ld16(tacc + q * 16, v);
         tmem_ld_wait();
         if (row >= p.rows) continue;
-        const int nq = n0 + q * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int n = nq + i;
+        for (int i = 0; i < 16; ++i) {
             float x = 0.f;
-            if (valid && n < p.n_cols) {
-                x = v[i] + __ldg(p.bias + n);
-                if (p.cv_act == ACT_PRELU) x = x >= 0.f ? x : __fmul_rn(__ldg(p.alpha + n % p.cv_act_mod), x);
-                else if (p.cv_act == ACT_LEAKY) x = x >= 0.f ? x : __fmul_rn(p.leaky, x);
+            if (valid && nq + i < p.n_cols) {
+                x = v[i] + bz[i];
+                if (p.cv_act == ACT_PRELU || p.cv_act == ACT_LEAKY) x = x >= 0.f ? x : __fmul_rn(al[i], x);
             }
             v[i] = x;
         }
         if (p.out_f32) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
+            for (int i = 0; i < 16; i += 4) {
                 const int n = nq + i;
                 if (n + 3 < p.n_cols) *reinterpret_cast<float4*>(p.out_f32 + row * p.ld_out + n) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                 else
@@ -437,7 +465,7 @@ __device__ __forceinline__ void epi_conv(const GemmParams& p, uint32_t tacc, lon
         }
         if (p.out_hilo) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
+            for (int i = 0; i < 16; i += 8) {
                 const int n = nq + i;
                 if (n >= p.n_cols) break;                       // n_cols and cout_per are multiples of 8
                 const int sub = n / p.cout_per, ch = n - sub * p.cout_per;
