@@ -61,7 +61,7 @@ constexpr int MAX_KB = 64;
 // (54 -> ~25 instructions per output and latency bound), so it gets 16 warps (4 per scheduler) and the register budget
 // is moved from the producer / MMA warps to them with setmaxnreg; the other epilogues keep 8 warps.
 __host__ __device__ constexpr int epi_warps(int epi, int cg) {
-    return epi == 1 /* EPI_GATE */ || (epi == 2 /* EPI_RESSKIP */ && cg == 2) ? 16 : 8;
+    return epi == 1 /* EPI_GATE */ || epi == 3 /* EPI_CONV */ || (epi == 2 /* EPI_RESSKIP */ && cg == 2) ? 16 : 8;
 }
 __host__ __device__ constexpr int tc_threads(int epi, int cg) { return 128 + 32 * epi_warps(epi, cg); }
 constexpr int COND_ROWS = 16;                           // staged conditioning rows per tile (<= 15 used at lin_up = 10)
