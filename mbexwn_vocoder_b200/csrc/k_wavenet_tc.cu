@@ -1345,19 +1345,31 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
 // start 1x1 (custom_AE_layers.py:280) fused with the split into the bf16 [hi | lo] residual stream: one thread = one
 // row x 8 channels; guard rows and the channel padding are written as zeros (the tap-GEMM relies on both).
 // Weights (cin x cpad, zero padded) and bias sit in shared memory; a block covers START_ROWS rows.
-constexpr int START_ROWS = 64;
+// Thread = (row lane, 8-channel group): its 8 x cin weights and 8 biases live in registers for the whole block, so the
+// inner loop reads only the cin inputs of a row from shared memory (the earlier version re-read the weights from shared
+// memory for every row and was bound by that traffic: 0.32 ms for 0.66 GB of output).
+constexpr int START_ROWS = 256;
 constexpr int START_MAX_CIN = 16;
-__global__ void start_pack_kernel(const float* __restrict__ x, int cin, const float* __restrict__ w, const float* __restrict__ b,
-                                  __nv_bfloat16* __restrict__ out, long long rows, int c, int cpad, int rate, FrameGrid g,
-                                  int f16f8, float lo_scale) {
-    extern __shared__ float sw[];                       // [cin + 1][cpad]: weights, then bias
-    float* sx = sw + (cin + 1) * cpad;                  // [START_ROWS][cin] inputs, zero for guard rows
+constexpr int START_LANES = 8;                          // rows in flight per block pass
+template <int CIN_MAX>
+__global__ void __launch_bounds__(START_LANES * 48, CIN_MAX <= 8 ? 2 : 1)
+start_pack_kernel(const float* __restrict__ x, int cin, const float* __restrict__ w, const float* __restrict__ b,
+                  __nv_bfloat16* __restrict__ out, long long rows, int c, int cpad, int rate, FrameGrid g,
+                  int f16f8, float lo_scale) {
+    extern __shared__ float sx[];                       // [START_ROWS][cin] inputs, zero for guard rows
     __shared__ int svalid[START_ROWS];
+    const int groups = cpad >> 3;                       // <= 48 (cpad <= 384)
     const long long r0 = (long long)blockIdx.x * START_ROWS;
-    for (int i = threadIdx.x; i < (cin + 1) * cpad; i += blockDim.x) {
-        const int ci = i / cpad, ch = i - ci * cpad;
-        sw[i] = ch < c ? (ci < cin ? w[ci * c + ch] : b[ch]) : 0.f;
-    }
+    const int grp = threadIdx.x % groups, lane = threadIdx.x / groups;
+    const int ch0 = grp * 8;
+    const bool active = lane < START_LANES;
+    float wr[CIN_MAX][8], br[8];
+#pragma unroll
+    for (int ci = 0; ci < CIN_MAX; ++ci)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wr[ci][j] = (ci < cin && ch0 + j < c) ? __ldg(w + ci * c + ch0 + j) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) br[j] = ch0 + j < c ? __ldg(b + ch0 + j) : 0.f;
     for (int i = threadIdx.x; i < START_ROWS; i += blockDim.x) {
         long long lo, hi;
         svalid[i] = (r0 + i < rows) && utt_bounds(g, rate, r0 + i, lo, hi);
@@ -1368,26 +1380,24 @@ __global__ void start_pack_kernel(const float* __restrict__ x, int cin, const fl
         sx[i] = svalid[rl] ? x[(r0 + rl) * cin + (i - rl * cin)] : 0.f;
     }
     __syncthreads();
-    const int groups = cpad >> 3;
-    for (int i = threadIdx.x; i < START_ROWS * groups; i += blockDim.x) {
-        const int rl = i / groups, ch0 = (i - rl * groups) * 8;
+    if (!active) return;
+    for (int rl = lane; rl < START_ROWS; rl += START_LANES) {
         const long long r = r0 + rl;
         if (r >= rows) break;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = 0.f;
         if (svalid[rl]) {
-            for (int ci = 0; ci < cin; ++ci) {
-                const float xv = sx[rl * cin + ci];
-                const float4 w0 = *reinterpret_cast<const float4*>(sw + ci * cpad + ch0);
-                const float4 w1 = *reinterpret_cast<const float4*>(sw + ci * cpad + ch0 + 4);
-                v[0] = fmaf(xv, w0.x, v[0]); v[1] = fmaf(xv, w0.y, v[1]); v[2] = fmaf(xv, w0.z, v[2]); v[3] = fmaf(xv, w0.w, v[3]);
-                v[4] = fmaf(xv, w1.x, v[4]); v[5] = fmaf(xv, w1.y, v[5]); v[6] = fmaf(xv, w1.z, v[6]); v[7] = fmaf(xv, w1.w, v[7]);
+#pragma unroll
+            for (int ci = 0; ci < CIN_MAX; ++ci) {
+                if (ci < cin) {
+                    const float xv = sx[rl * cin + ci];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaf(xv, wr[ci][j], v[j]);
+                }
             }
-            const float4 b0 = *reinterpret_cast<const float4*>(sw + cin * cpad + ch0);
-            const float4 b1 = *reinterpret_cast<const float4*>(sw + cin * cpad + ch0 + 4);
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += br[j];
         }
         if (f16f8) {
             uint4 h16;
@@ -1601,9 +1611,15 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         const float* b = (const float*)tensor(n + "/start/b", (size_t)c.wn_c * 4);
         if (!w || !b) return fail("start conv weights missing", MBEXWN_ERR_MISSING);
         if (c.wn_cin > START_MAX_CIN) return fail("start conv: more than 16 input channels", MBEXWN_ERR_UNSUPPORTED);
-        const size_t smem = ((size_t)(c.wn_cin + 1) * cpad + (size_t)START_ROWS * c.wn_cin) * sizeof(float);
-        start_pack_kernel<<<(unsigned)((rows + START_ROWS - 1) / START_ROWS), 256, smem, s>>>(
-            wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g, f8 ? 1 : 0, h_lo);
+        if (cpad > 384) return fail("start conv: more than 384 residual channels", MBEXWN_ERR_UNSUPPORTED);
+        const size_t smem = (size_t)START_ROWS * c.wn_cin * sizeof(float);
+        const unsigned nblk = (unsigned)((rows + START_ROWS - 1) / START_ROWS), nthr = (unsigned)(START_LANES * (cpad >> 3));
+        if (c.wn_cin <= 8)
+            start_pack_kernel<8><<<nblk, nthr, smem, s>>>(wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g,
+                                                          f8 ? 1 : 0, h_lo);
+        else
+            start_pack_kernel<16><<<nblk, nthr, smem, s>>>(wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g,
+                                                           f8 ? 1 : 0, h_lo);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(std::string("start conv: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
         *launches += 1;
