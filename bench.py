@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one wn_gemm_kernel<EPI_GATE> launch from the `ncu --set full` capture
 # committed under profiles/ (bytes per launch; None where no capture exists for the configuration)
-NCU_TRAFFIC = {("config2", "f16f8"): 800.4e6 + 624.9e6}     # profiles/r01h_wn_gemm_full_raw.csv
+NCU_TRAFFIC = {("config2", "f16f8"): 805.3e6 + 626.1e6}     # profiles/r01k_wn_gemm_full_raw.csv
 
 WORKLOADS = {
     # name: (model id, batch, frames, description)
