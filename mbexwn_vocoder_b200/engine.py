@@ -7,6 +7,7 @@ fallback: constructing an Engine without a CUDA device or without the built libr
 from __future__ import annotations
 
 import ctypes as C
+from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Union
 
 import numpy as np
@@ -96,6 +97,8 @@ def engine_halo(plan: ModelPlan) -> int:
 
 
 class Engine:
+    PB_CACHE_SIZE = 6
+
     def __init__(self, plan: ModelPlan, weights: Dict[str, np.ndarray], device: Union[int, str, torch.device] = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("mbexwn_vocoder_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -112,6 +115,7 @@ class Engine:
             raise RuntimeError(f"mbexwn_create failed ({rc})")
         self._tensors: Dict[str, torch.Tensor] = {}
         self._workspace: Optional[torch.Tensor] = None
+        self._pb_cache: "OrderedDict" = OrderedDict()
         self._upload(weights)
         self.last_layout: Optional[FrameGridLayout] = None
         self._last = None
@@ -217,13 +221,32 @@ class Engine:
         """Allocate everything one batch geometry needs (device grid, staging, pinned host buffers, workspace)."""
         return PreparedBatch(self, lengths, precision, with_noise, with_f0, with_carry)
 
+    def prepare_cached(self, lengths: Sequence[int], precision: str = "fp32", with_noise: bool = True,
+                       with_f0: bool = False, slot: int = 0) -> "PreparedBatch":
+        """`prepare` with a small LRU of batch geometries: repeated calls of one shape (a client sending utterance after
+        utterance, the windows of long-form synthesis) skip the pinned-memory and device allocations, which cost far more
+        than a short forward.  `slot` separates buffer sets that are in flight at the same time (synth_stream)."""
+        key = (tuple(int(t) for t in lengths), precision, bool(with_noise), bool(with_f0), int(slot))
+        pb = self._pb_cache.pop(key, None)
+        if pb is None or pb.workspace.data_ptr() != (self._workspace.data_ptr() if self._workspace is not None else 0):
+            pb = PreparedBatch(self, lengths, precision, with_noise, with_f0, False)
+            # a larger workspace may have replaced the one cached batches point to: drop those
+            live = self._workspace.data_ptr()
+            for k in [k for k, v in self._pb_cache.items() if v.workspace.data_ptr() != live]:
+                del self._pb_cache[k]
+        self._pb_cache[key] = pb
+        while len(self._pb_cache) > self.PB_CACHE_SIZE:
+            self._pb_cache.pop(next(iter(self._pb_cache)))
+        pb.batch.utt_ids = None
+        return pb
+
     def forward(self, mels: Sequence[np.ndarray], noise: Optional[Sequence[np.ndarray]] = None,
                 f0: Optional[Sequence[np.ndarray]] = None, precision: str = "fp32", seed: int = 0,
                 taps: Sequence[str] = (), utt_ids: Optional[Sequence[int]] = None):
         """mels: list of (T_u, n_mel) float32.  Returns (list of (T_u*hop,) waveforms, {tap: list of arrays}).
 
         utt_ids: global utterance ids keying the in-kernel noise stream (default: position in this batch)."""
-        pb = self.prepare([m.shape[0] for m in mels], precision, noise is not None, f0 is not None)
+        pb = self.prepare_cached([m.shape[0] for m in mels], precision, noise is not None, f0 is not None)
         pb.load(mels, noise, f0)
         if utt_ids is not None:
             pb.set_utt_ids(utt_ids)

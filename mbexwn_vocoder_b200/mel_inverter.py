@@ -175,7 +175,7 @@ class MELInverter(object):
                 yield [w.copy() for w in pb0.waveforms()]
             nz = next(noise_it) if noise_it is not None else None
             mels = [np.asarray(m, dtype=np.float32) for m in mels]
-            pb = eng.prepare([m.shape[0] for m in mels], self.precision, nz is not None)
+            pb = eng.prepare_cached([m.shape[0] for m in mels], self.precision, nz is not None, slot=slot)
             pb.load(mels, nz)
             pb.begin_host(slot, seed)
             pending.append((slot, pb))
