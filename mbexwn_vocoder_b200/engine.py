@@ -217,9 +217,11 @@ class Engine:
                 torch.from_numpy(layout.utt_end).to(dev), torch.from_numpy(layout.chunk_first).to(dev))
 
     def prepare(self, lengths: Sequence[int], precision: str = "fp32", with_noise: bool = True,
-                with_f0: bool = False, with_carry: bool = False) -> "PreparedBatch":
-        """Allocate everything one batch geometry needs (device grid, staging, pinned host buffers, workspace)."""
-        return PreparedBatch(self, lengths, precision, with_noise, with_f0, with_carry)
+                with_f0: bool = False, with_carry: bool = False, capacity_frames: int = 0,
+                capacity_utts: int = 0) -> "PreparedBatch":
+        """Allocate everything one batch geometry needs (device grid, staging, pinned host buffers, workspace); with a
+        capacity, `PreparedBatch.rebind` later switches geometry without allocating."""
+        return PreparedBatch(self, lengths, precision, with_noise, with_f0, with_carry, capacity_frames, capacity_utts)
 
     def prepare_cached(self, lengths: Sequence[int], precision: str = "fp32", with_noise: bool = True,
                        with_f0: bool = False, slot: int = 0) -> "PreparedBatch":
@@ -270,15 +272,24 @@ class PreparedBatch:
     """One batch geometry bound to its buffers; `run_host` is the reference-facing call (host in, host out)."""
 
     def __init__(self, eng: Engine, lengths: Sequence[int], precision: str, with_noise: bool, with_f0: bool,
-                 with_carry: bool = False):
+                 with_carry: bool = False, capacity_frames: int = 0, capacity_utts: int = 0):
+        """`capacity_frames` / `capacity_utts` > 0: allocate for that many padded frames / utterances so that `rebind` can
+        switch to any other geometry within the capacity without allocating (ragged serving, config 4)."""
         plan = eng.plan
         self.eng = eng
         self.prec = _cabi.PRECISIONS[precision]
         self.layout = make_layout(lengths, eng.halo, plan.pulse_per_frame, eng.cfg.cumsum_chunk)
         L = self.layout
         dev = eng.device
-        self.frame_utt, self.utt_begin, self.utt_end, self.chunk_first = eng._grid_tensors(L)
-        F = L.n_frames
+        F = max(L.n_frames, int(capacity_frames))
+        U = max(L.n_utt, int(capacity_utts))
+        self.cap_frames, self.cap_utts = F, U
+        # worst case of ceil(T_u * pulse_per_frame / chunk) summed over the utterances
+        self.cap_chunks = max(L.n_chunks, -(-F * plan.pulse_per_frame // eng.cfg.cumsum_chunk) + U)
+        self.frame_utt = torch.full((F,), -1, dtype=torch.int32, device=dev)
+        self.utt_begin = torch.zeros(U, dtype=torch.int32, device=dev)
+        self.utt_end = torch.zeros(U, dtype=torch.int32, device=dev)
+        self.chunk_first = torch.zeros(U + 1, dtype=torch.int32, device=dev)
         self.mel_host = torch.zeros(F, plan.mel_channels, dtype=torch.float32).pin_memory()
         self.out_host = torch.zeros(F * plan.hop, dtype=torch.float32).pin_memory()
         self.mel_dev = torch.zeros(F, plan.mel_channels, dtype=torch.float32, device=dev)
@@ -289,11 +300,11 @@ class PreparedBatch:
             self.noise_dev = torch.zeros(F * plan.steps_per_frame, dtype=torch.float32, device=dev)
         if with_f0:
             self.f0_dev = torch.zeros(F * plan.pulse_per_frame, dtype=torch.float32, device=dev)
-        self.ws_bytes = int(eng.lib.mbexwn_workspace_bytes(eng._handle, F, L.n_chunks, self.prec))
+        self.ws_bytes = int(eng.lib.mbexwn_workspace_bytes(eng._handle, F, self.cap_chunks, self.prec))
         self.workspace = eng._ensure_workspace(self.ws_bytes)
+        self.utt_ids = None
         self.batch = _cabi.Batch()
         b = self.batch
-        b.n_utt, b.n_frames, b.n_chunks = L.n_utt, F, L.n_chunks
         b.frame_utt, b.utt_begin, b.utt_end = self.frame_utt.data_ptr(), self.utt_begin.data_ptr(), self.utt_end.data_ptr()
         b.chunk_first = self.chunk_first.data_ptr()
         b.mel = self.mel_dev.data_ptr()
@@ -302,24 +313,51 @@ class PreparedBatch:
         b.out = self.out_dev.data_ptr()
         self.carry_dev = None
         if with_carry:                                        # windows of a longer signal (long_form.py)
-            self.carry_dev = torch.zeros(L.n_utt, dtype=torch.float32, device=dev)
+            self.carry_dev = torch.zeros(U, dtype=torch.float32, device=dev)
             b.phase_carry = self.carry_dev.data_ptr()
+        self._bind(L)
+
+    def _bind(self, L: FrameGridLayout):
+        self.layout = L
+        self.frame_utt[:L.n_frames].copy_(torch.from_numpy(L.frame_utt))
+        self.utt_begin[:L.n_utt].copy_(torch.from_numpy(L.utt_begin))
+        self.utt_end[:L.n_utt].copy_(torch.from_numpy(L.utt_end))
+        self.chunk_first[:L.n_utt + 1].copy_(torch.from_numpy(L.chunk_first))
+        b = self.batch
+        b.n_utt, b.n_frames, b.n_chunks = L.n_utt, L.n_frames, L.n_chunks
+
+    def rebind(self, lengths: Sequence[int]):
+        """Switch to another batch geometry inside the allocated capacity.  The caller must have drained the previous use
+        (run_host returned / wait_host).  Guard rows of the host staging buffers are cleared."""
+        plan = self.eng.plan
+        L = make_layout(lengths, self.eng.halo, plan.pulse_per_frame, self.eng.cfg.cumsum_chunk)
+        if L.n_frames > self.cap_frames or L.n_utt > self.cap_utts or L.n_chunks > self.cap_chunks:
+            raise RuntimeError(f"batch of {L.n_frames} padded frames / {L.n_utt} utterances exceeds the prepared capacity "
+                               f"({self.cap_frames} / {self.cap_utts})")
+        self.mel_host[:L.n_frames].zero_()
+        if self.noise_host is not None:
+            self.noise_host[:L.n_frames * plan.steps_per_frame].zero_()
+        self._bind(L)
+        self.batch.utt_ids = None
+        return self
 
     def set_utt_ids(self, utt_ids: Sequence[int]):
         ids = np.asarray(utt_ids, dtype=np.int32)
         assert ids.shape == (self.layout.n_utt,)
-        self.utt_ids = torch.from_numpy(ids).to(self.eng.device)
+        if self.utt_ids is None or self.utt_ids.numel() < self.cap_utts:
+            self.utt_ids = torch.zeros(self.cap_utts, dtype=torch.int32, device=self.eng.device)
+        self.utt_ids[:ids.size].copy_(torch.from_numpy(ids))
         self.batch.utt_ids = self.utt_ids.data_ptr()
 
     # bytes moved per run_host call
     @property
     def h2d_bytes(self) -> int:
-        n = self.mel_host.numel() * 4
-        return n + (self.noise_host.numel() * 4 if self.noise_host is not None else 0)
+        plan, F = self.eng.plan, self.layout.n_frames
+        return F * plan.mel_channels * 4 + (F * plan.steps_per_frame * 4 if self.noise_host is not None else 0)
 
     @property
     def d2h_bytes(self) -> int:
-        return self.out_host.numel() * 4
+        return self.layout.n_frames * self.eng.plan.hop * 4
 
     def load(self, mels, noise=None, f0=None, carry=None):
         L, plan = self.layout, self.eng.plan
@@ -330,9 +368,10 @@ class PreparedBatch:
         if f0 is not None:
             buf = np.zeros(L.n_frames * plan.pulse_per_frame, dtype=np.float32)
             L.scatter([np.asarray(x, dtype=np.float32).reshape(-1) for x in f0], plan.pulse_per_frame, buf)
-            self.f0_dev.copy_(torch.from_numpy(buf))
+            self.f0_dev[:buf.size].copy_(torch.from_numpy(buf))
         if carry is not None:
-            self.carry_dev.copy_(torch.from_numpy(np.asarray(carry, dtype=np.float32)))
+            carry = np.asarray(carry, dtype=np.float32)
+            self.carry_dev[:carry.size].copy_(torch.from_numpy(carry))
 
     def _stream(self):
         return torch.cuda.current_stream(self.eng.device).cuda_stream
@@ -365,9 +404,10 @@ class PreparedBatch:
                     "mbexwn_forward_host_wait")
 
     def upload(self):
-        self.mel_dev.copy_(self.mel_host, non_blocking=True)
+        F, spf = self.layout.n_frames, self.eng.plan.steps_per_frame
+        self.mel_dev[:F].copy_(self.mel_host[:F], non_blocking=True)
         if self.noise_host is not None:
-            self.noise_dev.copy_(self.noise_host, non_blocking=True)
+            self.noise_dev[:F * spf].copy_(self.noise_host[:F * spf], non_blocking=True)
 
     def run_device(self, seed: int = 0):
         """Device-resident inputs -> device output (asynchronous on the current stream)."""
@@ -397,7 +437,8 @@ class PreparedBatch:
         return int(self.eng.lib.mbexwn_last_launch_count(self.eng._handle))
 
     def waveforms(self, from_device: bool = False) -> List[np.ndarray]:
-        buf = self.out_dev.cpu().numpy() if from_device else self.out_host.numpy()
+        n = self.layout.n_frames * self.eng.plan.hop
+        buf = self.out_dev[:n].cpu().numpy() if from_device else self.out_host.numpy()[:n]
         return self.layout.gather(buf, self.eng.plan.hop)
 
     def tap_grid(self, name: str) -> torch.Tensor:

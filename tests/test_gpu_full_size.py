@@ -88,3 +88,42 @@ def test_empty_and_degenerate_inputs():
         inv.synth_from_mel(np.zeros((1, 0, 80), np.float32))
     one = inv.synth_from_mel(synthetic_mel(1, 0)[None])
     assert one.shape == (300,) and np.isfinite(one).all()
+
+
+def test_rebound_capacity_batches_equal_fresh_ones():
+    """PreparedBatch with a capacity, re-bound to changing ragged geometries and driven through the pipelined host forward
+    (tools/run_configs.py config4), gives bit for bit what freshly allocated batches give."""
+    from mbexwn_vocoder_b200.mel_inverter import MELInverter
+    inv = MELInverter("SING", device=0, precision="f16f8")
+    eng = inv.model
+    rng = np.random.default_rng(3)
+    groups = [list(rng.integers(1, 90, size=int(n))) for n in (5, 2, 7, 1, 4)]
+    slots = [eng.prepare([1], precision="f16f8", with_noise=False, capacity_frames=700, capacity_utts=8) for _ in range(2)]
+    got, pending = [], [None, None]
+    uid = 0
+    ids = []
+    for i, lens in enumerate(groups):
+        s = i & 1
+        if pending[s] is not None:
+            slots[s].wait_host(s)
+            got.append([w.copy() for w in slots[s].waveforms()])
+        pb = slots[s].rebind(lens)
+        ids.append(list(range(uid, uid + len(lens))))
+        pb.set_utt_ids(ids[-1])
+        pb.load([synthetic_mel(int(t), 200 + ids[-1][j]) for j, t in enumerate(lens)])
+        pb.begin_host(s, seed=9)
+        pending[s] = i
+        uid += len(lens)
+    order = sorted((p, s) for s, p in enumerate(pending) if p is not None)
+    for _, s in order:
+        slots[s].wait_host(s)
+        got.append([w.copy() for w in slots[s].waveforms()])
+    assert len(got) == len(groups)
+    for lens, idl, out in zip(groups, ids, got):
+        ref = eng.forward([synthetic_mel(int(t), 200 + idl[j]) for j, t in enumerate(lens)], precision="f16f8", seed=9,
+                          utt_ids=idl)[0]
+        assert len(ref) == len(out)
+        for a, b in zip(ref, out):
+            assert np.array_equal(a, b)
+    with pytest.raises(RuntimeError, match="capacity"):
+        slots[0].rebind([800])

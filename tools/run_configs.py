@@ -95,16 +95,39 @@ def main():
         if cur:
             groups.append(cur)
         base = synthetic_mel(2400, 0)
+        base2 = np.concatenate([base, base])                  # utterance u = a window of the periodically extended base
+        off = lambda u: (-int(u)) % 2400                      # same values as np.roll(base, u)[:len], without the copy
+
+        # two buffer sets of full capacity, re-bound to every group's geometry (no allocation inside the timed loop);
+        # the host prepares group i + 1 and drains group i - 1 while the GPU works on group i
+        cap_utts = max(len(g) for g in groups)
+        slots = [eng.prepare([1], precision=prec, with_noise=False, capacity_frames=args.max_batch_frames + eng.halo,
+                             capacity_utts=cap_utts) for _ in range(2)]
+        in_flight = [None, None]
         barrier()
         t0 = time.perf_counter()
         total_frames, checksum = 0, 0.0
-        for grp in groups:
-            pb = eng.prepare([int(lengths[u]) for u in grp], precision=prec, with_noise=False)
+
+        def drain(s):
+            nonlocal checksum
+            if in_flight[s] is None:
+                return
+            slots[s].wait_host(s)
+            n = slots[s].layout.n_frames * plan.hop
+            checksum += float(np.abs(slots[s].out_host.numpy()[:n:997]).sum())
+            in_flight[s] = None
+
+        for i, grp in enumerate(groups):
+            s = i & 1
+            drain(s)
+            pb = slots[s].rebind([int(lengths[u]) for u in grp])
             pb.set_utt_ids(grp)
-            pb.load([np.roll(base, int(u), axis=0)[:lengths[u]] for u in grp])
-            pb.run_host(seed=7)
+            pb.load([base2[off(u):off(u) + int(lengths[u])] for u in grp])
+            pb.begin_host(s, seed=7)
+            in_flight[s] = grp
             total_frames += int(sum(lengths[u] for u in grp))
-            checksum += float(np.abs(pb.out_host.numpy()[::997]).sum())
+        drain(0)
+        drain(1)
         barrier()
         dt = time.perf_counter() - t0
         tot = torch.tensor([float(total_frames), checksum, dt], dtype=torch.float64, device="cuda")
