@@ -224,14 +224,14 @@ class Engine:
         return PreparedBatch(self, lengths, precision, with_noise, with_f0, with_carry, capacity_frames, capacity_utts)
 
     def prepare_cached(self, lengths: Sequence[int], precision: str = "fp32", with_noise: bool = True,
-                       with_f0: bool = False, slot: int = 0) -> "PreparedBatch":
+                       with_f0: bool = False, slot: int = 0, with_carry: bool = False) -> "PreparedBatch":
         """`prepare` with a small LRU of batch geometries: repeated calls of one shape (a client sending utterance after
         utterance, the windows of long-form synthesis) skip the pinned-memory and device allocations, which cost far more
         than a short forward.  `slot` separates buffer sets that are in flight at the same time (synth_stream)."""
-        key = (tuple(int(t) for t in lengths), precision, bool(with_noise), bool(with_f0), int(slot))
+        key = (tuple(int(t) for t in lengths), precision, bool(with_noise), bool(with_f0), int(slot), bool(with_carry))
         pb = self._pb_cache.pop(key, None)
         if pb is None or pb.workspace.data_ptr() != (self._workspace.data_ptr() if self._workspace is not None else 0):
-            pb = PreparedBatch(self, lengths, precision, with_noise, with_f0, False)
+            pb = PreparedBatch(self, lengths, precision, with_noise, with_f0, with_carry)
             # a larger workspace may have replaced the one cached batches point to: drop those
             live = self._workspace.data_ptr()
             for k in [k for k, v in self._pb_cache.items() if v.workspace.data_ptr() != live]:

@@ -126,52 +126,76 @@ def synth_long(engine, mel: np.ndarray, noise: np.ndarray, chunk_frames: int = 4
     info: Dict[str, float] = {}
     t0 = time.perf_counter()
 
-    # ---- pass 1: exact F0 of the whole signal ----------------------------------------------------------------
+    ctx = main_context_frames(plan)
+    main_wins = plan_windows(T, chunk_frames, ctx, align)
+    out = np.empty(T * hop, dtype=np.float32)
     f0_ctx = subnet_reach_frames(plan.pp_ops)
+
+    def f0_pass(lo: int, hi: int, dst: np.ndarray, cached: bool = False):
+        """Exact F0 of frames [lo, hi) (receptive-field context taken from the neighbouring frames) into dst[lo*ppf:hi*ppf]."""
+        a, b = max(0, lo - f0_ctx), min(T, hi + f0_ctx)
+        wins = plan_windows(b - a, max(chunk_frames, 4 * f0_ctx), f0_ctx)
+        engine.set_option("stop_after_f0", 1)
+        try:
+            for grp in _batches(wins, max_batch_frames):
+                # only the small first-window geometry is kept in the engine's buffer cache: holding the large batches
+                # there would keep their pinned staging memory from being recycled
+                prep = engine.prepare_cached if cached else engine.prepare
+                pb = prep([wins[i].stop - wins[i].start for i in grp], precision, with_noise=False)
+                pb.load([mel[a + wins[i].start:a + wins[i].stop] for i in grp])
+                pb.upload()
+                pb.run_device()
+                for i, x in zip(grp, pb.tap("F0")):
+                    w = wins[i]
+                    c0, c1 = max(w.core0 + a, lo), min(w.core1 + a, hi)
+                    if c1 > c0:
+                        dst[c0 * ppf:c1 * ppf] = x[(c0 - a - w.start) * ppf:(c1 - a - w.start) * ppf]
+        finally:
+            engine.set_option("stop_after_f0", 0)
+
+    def run_windows(grp, f0_src: np.ndarray, carries, cached: bool = False):
+        prep = engine.prepare_cached if cached else engine.prepare
+        pb = prep([main_wins[i].stop - main_wins[i].start for i in grp], precision, with_noise=True, with_f0=True,
+                  with_carry=True)
+        pb.load([mel[main_wins[i].start:main_wins[i].stop] for i in grp],
+                noise=[noise[main_wins[i].start * spf:main_wins[i].stop * spf] for i in grp],
+                f0=[f0_src[main_wins[i].start * ppf:main_wins[i].stop * ppf] for i in grp],
+                carry=carries)
+        pb.run_host()
+        for i, y in zip(grp, pb.waveforms()):
+            w = main_wins[i]
+            out[w.core0 * hop:w.core1 * hop] = y[(w.core0 - w.start) * hop:(w.core1 - w.start) * hop]
+
+    # ---- first window on its own: it needs the F0 of its own frames only and starts with a zero phase carry, so a
+    # streaming client hears it before the rest of the utterance has been looked at -------------------------------
     f0_full = np.empty(T * ppf, dtype=np.float32)
-    wins = plan_windows(T, max(chunk_frames, 4 * f0_ctx), f0_ctx)
-    engine.set_option("stop_after_f0", 1)
-    try:
-        for grp in _batches(wins, max_batch_frames):
-            pb = engine.prepare([wins[i].stop - wins[i].start for i in grp], precision, with_noise=False)
-            pb.load([mel[wins[i].start:wins[i].stop] for i in grp])
-            pb.upload()
-            pb.run_device()
-            for i, x in zip(grp, pb.tap("F0")):
-                w = wins[i]
-                f0_full[w.core0 * ppf:w.core1 * ppf] = x[(w.core0 - w.start) * ppf:(w.core1 - w.start) * ppf]
-    finally:
-        engine.set_option("stop_after_f0", 0)
-    info["f0_pass_s"] = time.perf_counter() - t0
+    first_done = False
+    if first_alone and len(main_wins) > 1:
+        w0 = main_wins[0]
+        f0_pass(w0.start, w0.stop, f0_full, cached=True)
+        run_windows([0], f0_full, [0.0], cached=True)
+        info["first_chunk_latency_s"] = time.perf_counter() - t0
+        first_done = True
+
+    # ---- pass 1: exact F0 of the whole signal ----------------------------------------------------------------
+    t_f0 = time.perf_counter()
+    f0_pass(0, T, f0_full)
+    info["f0_pass_s"] = time.perf_counter() - t_f0
 
     # ---- pass 2: phase carry per cumsum chunk ------------------------------------------------------------------
     run = phase_run_before_chunks(f0_full, plan.pulse_rate, chunk)
 
-    # ---- pass 3: the windows ----------------------------------------------------------------------------------
-    ctx = main_context_frames(plan)
-    wins = plan_windows(T, chunk_frames, ctx, align)
-    out = np.empty(T * hop, dtype=np.float32)
-    groups = _batches(wins, max_batch_frames)
-    if first_alone and len(wins) > 1 and len(groups[0]) > 1:
-        groups = [[0]] + _batches(wins[1:], max_batch_frames)
-        groups = [groups[0]] + [[i + 1 for i in g] for g in groups[1:]]
+    # ---- pass 3: the remaining windows, batched ---------------------------------------------------------------
+    rest = list(range(1 if first_done else 0, len(main_wins)))
+    groups = [[rest[j] for j in g] for g in _batches([main_wins[i] for i in rest], max_batch_frames)] if rest else []
     t1 = time.perf_counter()
     for gi, grp in enumerate(groups):
-        pb = engine.prepare([wins[i].stop - wins[i].start for i in grp], precision, with_noise=True, with_f0=True,
-                            with_carry=True)
-        pb.load([mel[wins[i].start:wins[i].stop] for i in grp],
-                noise=[noise[wins[i].start * spf:wins[i].stop * spf] for i in grp],
-                f0=[f0_full[wins[i].start * ppf:wins[i].stop * ppf] for i in grp],
-                carry=[run[wins[i].start // align] for i in grp])
-        pb.run_host()
-        for i, y in zip(grp, pb.waveforms()):
-            w = wins[i]
-            out[w.core0 * hop:w.core1 * hop] = y[(w.core0 - w.start) * hop:(w.core1 - w.start) * hop]
-        if gi == 0:
+        run_windows(grp, f0_full, [run[main_wins[i].start // align] for i in grp])
+        if gi == 0 and not first_done:
             info["first_chunk_latency_s"] = time.perf_counter() - t0
     info["main_pass_s"] = time.perf_counter() - t1
     info["total_s"] = time.perf_counter() - t0
     info["audio_s"] = T * hop / plan.sample_rate
-    info["n_windows"] = len(wins)
+    info["n_windows"] = len(main_wins)
     info["context_frames"] = ctx
     return out, info
