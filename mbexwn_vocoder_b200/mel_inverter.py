@@ -147,15 +147,26 @@ class MELInverter(object):
         if scaled_mell.ndim != 3 or scaled_mell.shape[2] != self.mel_channels:
             raise RuntimeError(f"expected a (batch, frames, {self.mel_channels}) mel spectrogram, got {scaled_mell.shape}")
         noise_list = None if noise is None else [np.asarray(z) for z in noise]
-        out, _ = self.model.forward(list(scaled_mell), noise=noise_list, precision=self.precision,
-                                    seed=self.seed if seed is None else seed)
+        out, _ = self._forward(list(scaled_mell), noise=noise_list, seed=self.seed if seed is None else seed)
         return np.stack(out).ravel()
+
+    def _forward(self, mels, noise=None, f0=None, seed=0, taps=()):
+        """Engine.forward with a range guard for the f16f8 path: its main operand plane is fp16, so a model whose residual
+        stream leaves the fp16 range (|x| > 65504; never seen with the synthetic weights) would produce non-finite samples.
+        A strided probe of the output detects that and the batch is re-run on the equally accurate bf16x3 path (bf16 planes
+        have the fp32 exponent range), with a note on stderr -- never a silent change of accuracy class."""
+        out, tp = self.model.forward(mels, noise=noise, f0=f0, precision=self.precision, seed=seed, taps=taps)
+        if self.precision == "f16f8" and not all(np.isfinite(w[::1021]).all() for w in out):
+            print("MELInverter::warning::non-finite samples on the f16f8 path (fp16 operand range exceeded); "
+                  "re-running this batch with precision bf16x3", file=sys.stderr)
+            out, tp = self.model.forward(mels, noise=noise, f0=f0, precision="bf16x3", seed=seed, taps=taps)
+        return out, tp
 
     def synth_batch(self, mels: Sequence[np.ndarray], noise=None, f0=None, taps: Sequence[str] = (),
                     seed: Optional[int] = None):
         """Variable-length batch: list of (T_u, n_mel) -> list of (T_u*hop,) waveforms [+ stage taps]."""
-        out, tp = self.model.forward([np.asarray(m, dtype=np.float32) for m in mels], noise=noise, f0=f0,
-                                     precision=self.precision, seed=self.seed if seed is None else seed, taps=taps)
+        out, tp = self._forward([np.asarray(m, dtype=np.float32) for m in mels], noise=noise, f0=f0,
+                                seed=self.seed if seed is None else seed, taps=taps)
         return (out, tp) if taps else out
 
     def synth_stream(self, batches, noise=None, seed: Optional[int] = None):

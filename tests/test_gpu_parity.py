@@ -183,3 +183,30 @@ def test_pipelined_host_forward_equals_the_blocking_call():
         ref = inv.synth_batch(m)
         for x, y in zip(ref, got):
             assert np.array_equal(x, y)
+
+
+def test_f16f8_range_guard_falls_back_to_bf16x3(tmp_path, capsys):
+    """A model whose residual stream leaves the fp16 range: the f16f8 path would return non-finite samples; the inverter
+    detects it and re-runs the batch on the bf16x3 path (same accuracy class), saying so on stderr."""
+    from mbexwn_vocoder_b200 import get_config_file, weights as W
+    from mbexwn_vocoder_b200.config import read_config
+    from mbexwn_vocoder_b200.mel_inverter import MELInverter
+    from mbexwn_vocoder_b200.plan import build_plan
+    import shutil
+    cfg = get_config_file("SPEECH")
+    hp = read_config(cfg)
+    plan = build_plan(hp, finalize=False)
+    w = W.init_synthetic(plan, seed=12)
+    name = "PP_waveNetBlock_ups1_0_WNBlock_WN/start"
+    w[f"{name}/g"] = w[f"{name}/g"] * 3e5                          # residual stream ~1e5 > 65504
+    shutil.copy(cfg, tmp_path / "config.yaml")
+    W.save(str(tmp_path / "weights.npz"), w)
+    inv = MELInverter(str(tmp_path), device=0, precision="f16f8")
+    mel = synthetic_mel(12, 0)[None]
+    raw, _ = inv.model.forward(list(mel), precision="f16f8", seed=1)
+    assert not np.isfinite(raw[0]).all()                           # the unguarded engine call shows the overflow
+    y = inv.synth_from_mel(mel, seed=1)
+    assert np.isfinite(y).all()
+    assert "bf16x3" in capsys.readouterr().err
+    ref, _ = inv.model.forward(list(mel), precision="bf16x3", seed=1)
+    assert np.array_equal(y, ref[0])
