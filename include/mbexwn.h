@@ -117,6 +117,9 @@ typedef struct {
     int32_t ps_preserve_energy; /* ps_mode 1: subtract the mean log gain over the bands (:867-876) */
     int32_t wt_subharm;         /* wavetable_config.add_subharm_chans: sin(2 pi phase / ii), ii = 2 .. n + 1, beside every pulse
                                    sample (tf_wavetable.py:554-559); wn_cin = pulse_channels * (1 + n) [+ 1 noise] */
+    int32_t pulse_pqmf_taps;    /* pulse_channels_use_pqmf: the pulse train enters the WaveNet as the pulse_channels bands of a PQMF
+                                   analysis bank (tensor "pulse_pqmf" (pulse_channels, taps + 1); TFPQMF.analysis,
+                                   tf_preprocess.py:192-202, custom_pulsed_generator.py:895) instead of being folded; 0 = off */
 } mbexwn_config_t;
 
 /* One batch on the padded frame grid; all pointers are DEVICE pointers. */

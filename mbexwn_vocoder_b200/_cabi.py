@@ -58,7 +58,8 @@ class Config(C.Structure):
                 ("norm_fact", C.c_float), ("norm_floor", C.c_float), ("norm_compress_exp", C.c_float),
                 ("norm_proj_scale", C.c_float), ("norm_lin_scale", C.c_float), ("norm_lin_off", C.c_float),
                 ("norm_mel_scale", C.c_float),
-                ("ps_mode", C.c_int32), ("ps_preserve_energy", C.c_int32), ("wt_subharm", C.c_int32)]
+                ("ps_mode", C.c_int32), ("ps_preserve_energy", C.c_int32), ("wt_subharm", C.c_int32),
+                ("pulse_pqmf_taps", C.c_int32)]
 
 
 class Batch(C.Structure):

@@ -110,10 +110,10 @@ static Workspace carve(const mbexwn_config_t& c, int64_t F, int64_t n_chunks, in
     w.add("F0", (size_t)F * c.pulse_per_frame * f4);
     w.add("cum", (size_t)F * c.pulse_per_frame * f4);
     w.add("chunk_off", (size_t)(n_chunks + 1) * f4);
+    if (debug_taps || c.pulse_pqmf_taps > 0) w.add("pulse", (size_t)F * c.pulse_per_frame * f4);   // input of the pulse PQMF analysis
     if (debug_taps) {
         w.add("phase", (size_t)F * c.pulse_per_frame * f4);
         w.add("index", (size_t)F * c.pulse_per_frame * sizeof(int32_t));
-        w.add("pulse", (size_t)F * c.pulse_per_frame * f4);
         w.add("vtf", (size_t)F * (c.fft_size / 2 + 1) * 2 * f4);
         w.add("lifter_index", (size_t)F * sizeof(int32_t));
     }
@@ -457,11 +457,15 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
         a.grid_norm = c.wt_grid_norm; a.sigma = c.noise_sigma;
         a.pulse_per_frame = c.pulse_per_frame; a.steps_per_frame = c.steps_per_frame; a.pulse_channels = c.pulse_channels;
         a.subharm = c.wt_subharm;
+        a.pqmf_taps = c.pulse_pqmf_taps;
+        if (c.pulse_pqmf_taps > 0) {
+            a.pqmf_ana = tensor(h, "pulse_pqmf", (size_t)c.pulse_channels * (c.pulse_pqmf_taps + 1) * 4, &rc); if (!a.pqmf_ana) return rc;
+        }
         a.chunk = c.cumsum_chunk; a.cum = cx.p<float>("cum"); a.chunk_off = cx.p<float>("chunk_off");
         a.chunk_first = b->chunk_first; a.phase_carry = b->phase_carry; a.wn_in = cx.p<float>("wn_in"); a.ld_wn_in = c.wn_cin;
         a.phase_out = cx.p<float>("phase"); a.index_out = cx.p<int32_t>("index"); a.pulse_out = cx.p<float>("pulse");
         MBX_CUDA_CHECK(launch_excitation(a, cx.g, b->n_chunks, s));
-        h->launches += 3;
+        h->launches += 3 + (c.pulse_pqmf_taps > 0 ? 1 : 0);
     }
 
     mark();
@@ -626,6 +630,7 @@ int mbexwn_create(const mbexwn_config_t* cfg, mbexwn_handle_t* out) {
     if (cfg->steps_per_frame * cfg->pulse_channels != cfg->pulse_per_frame) return MBEXWN_ERR_INVALID;
     if (cfg->wt_subharm < 0 || cfg->wn_cin != cfg->pulse_channels * (1 + cfg->wt_subharm) + (cfg->noise_sigma != 0.f ? 1 : 0))
         return MBEXWN_ERR_INVALID;
+    if (cfg->pulse_pqmf_taps < 0 || (cfg->pulse_pqmf_taps & 1)) return MBEXWN_ERR_INVALID;
     if (cfg->fft_size < cfg->stft_win || (cfg->fft_size & (cfg->fft_size - 1))) return MBEXWN_ERR_INVALID;
     if (cfg->stft_win != 4 * cfg->hop) return MBEXWN_ERR_UNSUPPORTED;     // 4x overlap (wavegen_1d.py:592)
     if (cfg->norm_enable && (cfg->norm_iters < 1 || cfg->norm_win != 4 * cfg->hop || cfg->norm_smooth_win < 1 ||

@@ -125,6 +125,58 @@ __device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned
     return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
 }
 
+// wavetable pulse sample at wrapped phase `phase` for fundamental f0: _linear_lookup + F0-grid cross-fade
+// (tf_wavetable.py:621-638, :539-548); same operation order as the in-line code of pulse_kernel
+__device__ __forceinline__ float pulse_value(const ExcitationArgs& a, float phase, float f0, int& i0) {
+    const float p = __fmul_rn(phase, (float)a.n_period);
+    const float pq = floorf(p);
+    const float frac = __fsub_rn(p, pq);
+    i0 = (int)pq;
+    const float one_m = __fsub_rn(1.f, frac);
+    const float ratio = fmaxf(a.min_tr, fminf(a.max_tr, __fdiv_rn(f0, a.nominal_f0)));
+    const float x = __fmul_rn(logf(ratio), a.grid_norm);
+    int k0 = (int)floorf(x);
+    if (k0 < 0) k0 = 0;
+    if (k0 > a.n_tables - 1) k0 = a.n_tables - 1;
+    const int i0c = min(max(i0, 0), a.n_period - 1);
+    const float* t0 = a.tables + (long long)i0c * a.n_tables;
+    const float* t1 = t0 + a.n_tables;
+    float acc = 0.f;
+#pragma unroll
+    for (int dk = 0; dk < 2; ++dk) {
+        int k = k0 + dk;
+        if (k < a.n_tables) {
+            float w = fmaxf(__fsub_rn(1.f, fabsf(__fsub_rn(x, (float)k))), 0.f);
+            float s = __fadd_rn(__fmul_rn(__ldg(t0 + k), one_m), __fmul_rn(__ldg(t1 + k), frac));
+            acc = __fadd_rn(acc, __fmul_rn(s, w));
+        }
+    }
+    return acc;
+}
+
+// PQMF analysis of the pulse train (pulse_channels_use_pqmf; TFPQMF.analysis, tf_preprocess.py:192-202): band k of WaveNet
+// row m = sum_j pulse[m S + j - taps / 2] h_k[j] with zeros outside the utterance; one thread per (row, band).
+__global__ void pulse_pqmf_kernel(ExcitationArgs a, FrameGrid g) {
+    const int S = a.pulse_channels;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long rows = (long long)g.n_frames * a.steps_per_frame;
+    if (idx >= rows * S) return;
+    const long long m = idx / S;
+    const int k = (int)(idx - m * S);
+    float* row = a.wn_in + m * a.ld_wn_in;
+    long long lo, hi;
+    float acc = 0.f;
+    if (utt_bounds(g, a.pulse_per_frame, m * S, lo, hi)) {
+        const float* hk = a.pqmf_ana + (long long)k * (a.pqmf_taps + 1);
+        const long long base = m * S - a.pqmf_taps / 2;
+        for (int j = 0; j <= a.pqmf_taps; ++j) {
+            const long long n = base + j;
+            if (n >= lo && n < hi) acc = fmaf(a.pulse_out[n], __ldg(hk + j), acc);
+        }
+    }
+    row[k] = acc;
+}
+
 // IDX = unsigned when the grid holds fewer than 2^31 pulse samples (32-bit divisions), long long otherwise
 template <class IDX>
 __global__ void pulse_kernel(ExcitationArgs a, FrameGrid g) {
@@ -135,6 +187,38 @@ __global__ void pulse_kernel(ExcitationArgs a, FrameGrid g) {
     const int ch = (int)(n - step * (IDX)a.pulse_channels);
     float* row = a.wn_in + (long long)step * a.ld_wn_in;
     const int per = 1 + a.subharm;                     // values per pulse sample: pulse [+ sub-harmonic sinusoids]
+    if (a.pqmf_taps > 0) {
+        // pulse_channels_use_pqmf: the row is [pulse_channels analysis bands (pulse_pqmf_kernel) | sub-harmonic values of the
+        // pulse_channels samples | noise] (custom_pulsed_generator.py:895-900); the pulse itself only goes to pulse_out
+        const int nsub = a.subharm;
+        const int fq = (int)(n / (IDX)a.pulse_per_frame);
+        const int uq = g.frame_utt[fq];
+        float phase_q = 0.f, acc_q = 0.f;
+        int i0q = 0;
+        if (uq >= 0) {
+            const IDX loq = (IDX)g.utt_begin[uq] * (IDX)a.pulse_per_frame;
+            const IDX localq = n - loq;
+            const int cq = a.chunk_first[uq] + (int)(localq / (IDX)a.chunk);
+            phase_q = wrap1(__fadd_rn(a.cum[n], a.chunk_off[cq]));
+            acc_q = pulse_value(a, phase_q, a.f0[n], i0q);
+            if (nsub > 0) {
+                const float w2pi = __fmul_rn(__fmul_rn(phase_q, 2.f), 3.14159274101257324f);
+                for (int j = 1; j <= nsub; ++j) row[a.pulse_channels + ch * nsub + (j - 1)] = sinf(__fdiv_rn(w2pi, (float)(j + 1)));
+            }
+            if (ch == 0 && a.sigma != 0.f) {
+                const IDX lstep = step - loq / (IDX)a.pulse_channels;
+                float z = a.noise ? a.noise[step] : philox_normal(a.seed, (unsigned)(a.utt_ids ? a.utt_ids[uq] : uq), (unsigned long long)lstep);
+                row[a.pulse_channels * per] = __fmul_rn(a.sigma, z);
+            }
+        } else {
+            for (int j = 1; j <= nsub; ++j) row[a.pulse_channels + ch * nsub + (j - 1)] = 0.f;
+            if (ch == 0 && a.sigma != 0.f) row[a.pulse_channels * per] = 0.f;
+        }
+        if (a.phase_out) a.phase_out[n] = phase_q;
+        if (a.index_out) a.index_out[n] = i0q;
+        a.pulse_out[n] = acc_q;
+        return;
+    }
     const int f = (int)(n / (IDX)a.pulse_per_frame);
     const int u = g.frame_utt[f];
     if (u < 0) {
@@ -202,8 +286,13 @@ cudaError_t launch_excitation(const ExcitationArgs& a, const FrameGrid& g, int n
     phase_chunk_kernel<<<(n_chunks_total + CHUNK_WARPS - 1) / CHUNK_WARPS, CHUNK_WARPS * 32, 0, s>>>(a, g, n_chunks_total);
     chunk_offset_kernel<<<(g.n_utt * 32 + 127) / 128, 128, 0, s>>>(a, g);
     long long total = (long long)g.n_frames * a.pulse_per_frame;
+    if (a.pqmf_taps > 0 && (!a.pulse_out || !a.pqmf_ana)) return cudaErrorInvalidValue;
     if (total < (1ll << 31) - 256) pulse_kernel<unsigned><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, g);
     else pulse_kernel<long long><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, g);
+    if (a.pqmf_taps > 0) {
+        const long long work = (long long)g.n_frames * a.steps_per_frame * a.pulse_channels;
+        pulse_pqmf_kernel<<<(unsigned)((work + 255) / 256), 256, 0, s>>>(a, g);
+    }
     return cudaGetLastError();
 }
 

@@ -90,6 +90,8 @@ struct ExcitationArgs {
     float sigma;
     int pulse_per_frame, steps_per_frame, pulse_channels;
     int subharm;            // add_subharm_chans: extra sin(2 pi phase / ii) values per pulse sample (tf_wavetable.py:554-559)
+    int pqmf_taps;          // pulse_channels_use_pqmf: taps of the pulse analysis bank (0 = off; needs pulse_out)
+    const float* pqmf_ana;  // (pulse_channels, pqmf_taps + 1) analysis filters
     int chunk;              // cumsum chunk (1000, tf_wavetable.py:429)
     float* cum;             // scratch (frames * pulse_per_frame): in-chunk running sums
     float* chunk_off;       // scratch (n_chunks_total): per chunk offsets

@@ -74,6 +74,7 @@ def make_config(plan: ModelPlan) -> _cabi.Config:
     c.halo_frames = engine_halo(plan)
     c.ps_mode, c.ps_preserve_energy = plan.ps_mode, int(plan.ps_preserve_energy)
     c.wt_subharm = plan.subharm
+    c.pulse_pqmf_taps = int(plan.pulse_pqmf_cfg["taps"]) if plan.pulse_pqmf_cfg is not None else 0
     if plan.norm is not None:
         nm = plan.norm
         c.norm_enable, c.norm_iters, c.norm_win, c.norm_smooth_win = 1, nm.iters, nm.win, nm.smooth_win
@@ -152,6 +153,8 @@ class Engine:
         if plan.lifters is not None:
             self._register("lifters", plan.lifters)
             self._register("lifter_grid", plan.lifter_log10f0)
+        if plan.pulse_pqmf_ana is not None:
+            self._register("pulse_pqmf", plan.pulse_pqmf_ana)
         if plan.norm is not None:
             self._register("norm/proj", plan.norm.proj)
             self._register("norm/smooth_win", plan.norm.smooth_window)

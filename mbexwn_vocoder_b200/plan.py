@@ -128,6 +128,8 @@ class ModelPlan:
     wavetable_cfg: Dict
     max_halo_frames: int = 1
     subharm: int = 0            # wavetable_config.add_subharm_chans
+    pulse_pqmf_cfg: Optional[Dict] = None    # pulse_channels_multi_band_config when pulse_channels_use_pqmf
+    pulse_pqmf_ana: Optional[np.ndarray] = None   # (pulse_channels, taps + 1) analysis bank (finalize)
     ps_mode: int = PS_STFT      # PS_STFT | PS_BAND_GAIN | PS_OFF
     ps_preserve_energy: bool = False
     norm: Optional["NormMelSpec"] = None     # NormMelComponents (normalize_rms_from_mell), None = off
@@ -314,7 +316,6 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
     if len(ups_factors) != 1 or ups_factors[0] != 1:
         raise NotImplementedError("multi-block / up-sampling WaveNet stacks are not built yet (SURVEY 8f-4)")
     for key, why in (("force_causal", "causal convolutions"),
-                     ("pulse_channels_use_pqmf", "PQMF analysis of the pulse train"),
                      ("pp_subnet_training_only", "pp_subnet_training_only")):
         if mc.get(key):
             raise NotImplementedError(f"{why} is not built yet (SURVEY 8f-4)")
@@ -376,6 +377,14 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
     sigma = mc.get("pp_mod_subnet_noise_channel_sigma", 0.5)
     steps_per_frame = int(round(wn_rate / spect_rate))
     subharm = int(mc["wavetable_config"].get("add_subharm_chans", 0) or 0)             # tf_wavetable.py:212, :554-559
+    pulse_pqmf_cfg = None
+    if mc.get("pulse_channels_use_pqmf"):                                               # custom_pulsed_generator.py:499-501, :895
+        pulse_pqmf_cfg = copy.deepcopy(mc.get("pulse_channels_multi_band_config") or {})
+        if int(pulse_pqmf_cfg.get("subbands", 0)) != pch:
+            raise RuntimeError(f"MBExWN::config_error::pulse_channels_multi_band_config.subbands "
+                               f"{pulse_pqmf_cfg.get('subbands')} != pulse_channels {pch}")
+        if int(pulse_pqmf_cfg["taps"]) % 2:
+            raise AssertionError("The number of taps mush be even number.")             # tf_preprocess.py:44
     wn = WaveNetSpec(name="PP_waveNetBlock_ups1_0", c=c, c_in=pch * (1 + subharm) + (1 if sigma else 0),
                      c_out=int(wn_cfg["n_out_channels"]), n_layers=n_layers, k=k, dilations=dil,
                      gate=_GATES[gate], cond_k=cond_k,
@@ -393,7 +402,7 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
         pqmf_cfg=mb, stft_win=win, fft_size=fft,
         filter_max_log_range=(fdb / (20 * np.log10(np.exp(1)))) if fdb is not None else None,
         env_order_scale=mc.get("ps_env_order_scale"), wavetable_cfg=copy.deepcopy(mc["wavetable_config"]), norm=norm,
-        ps_mode=ps_mode, ps_preserve_energy=preserve_energy, subharm=subharm)
+        ps_mode=ps_mode, ps_preserve_energy=preserve_energy, subharm=subharm, pulse_pqmf_cfg=pulse_pqmf_cfg)
     half_span = max(d * (k - 1) // 2 for d in dil)
     plan.max_halo_frames = max(1, -(-half_span // steps_per_frame))
     if finalize:
@@ -416,6 +425,9 @@ def finalize_plan(plan: ModelPlan) -> ModelPlan:
     if plan.env_order_scale:
         plan.lifter_log10f0, plan.lifters = dsp_init.cepstral_lifters(
             plan.env_order_scale, plan.sample_rate, plan.f0_min, plan.f0_max, plan.n_ceps)
+    if plan.pulse_pqmf_cfg is not None:
+        pq = plan.pulse_pqmf_cfg
+        plan.pulse_pqmf_ana, _ = dsp_init.pqmf_filters(pq["subbands"], pq["taps"], pq["cutoff_ratio"], pq["beta"])
     if plan.norm is not None:
         nm = plan.norm
         hann = dsp_init.cosine_window("hann", nm.win).astype(np.float32)

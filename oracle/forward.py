@@ -251,6 +251,10 @@ class OracleMBExWN:
                                                            int(mc.get("internal_fft_over", 0)))
         self.wt = dsp_init.build_wavetables(sample_rate=self.pulse_rate, **mc["wavetable_config"])
         self.subharm = int(mc["wavetable_config"].get("add_subharm_chans", 0) or 0)
+        self.pulse_pqmf = None
+        if mc.get("pulse_channels_use_pqmf"):                                  # custom_pulsed_generator.py:499-501
+            pq = mc["pulse_channels_multi_band_config"]
+            self.pulse_pqmf = (dsp_init.pqmf_filters(pq["subbands"], pq["taps"], pq["cutoff_ratio"], pq["beta"])[0], int(pq["taps"]))
         self.taps = mb["taps"]
         _, self.h_syn = dsp_init.pqmf_filters(mb["subbands"], mb["taps"], mb["cutoff_ratio"], mb["beta"])
         self.window = dsp_init.hann_periodic(self.win_size)
@@ -372,7 +376,21 @@ class OracleMBExWN:
         """custom_pulsed_generator.py:886-925.  `noise` is the N(0,1) draw of :906, shape (B, 20T, 1)."""
         pg = self.pulse_generator(f0.detach().cpu().numpy())
         pulse = torch.as_tensor(pg["pulse"], dtype=self.dtype)
-        if self.subharm:                                                       # tf_wavetable.py:520-521, :554-559
+        if self.pulse_pqmf is not None:
+            # TFPQMF.analysis (tf_preprocess.py:192-202): zero pad taps/2, cross-correlate with the analysis bank, keep every
+            # S-th sample; sub-harmonic channels are appended folded (custom_pulsed_generator.py:895-900)
+            ana, taps_p = self.pulse_pqmf
+            S = ana.shape[0]
+            xp = F.pad(pulse[:, None, :], (taps_p // 2, taps_p // 2))
+            y = F.conv1d(xp, torch.as_tensor(ana, dtype=self.dtype)[:, None, :], stride=1)      # (B, S, N)
+            x = y[:, :, ::S].transpose(1, 2)                                                   # (B, N / S, S)
+            if self.subharm:
+                dt = self.np_dtype
+                w2pi = pg["phase"].astype(dt) * dt(2) * dt(np.float32(np.pi))
+                sub = np.stack([np.sin(w2pi / dt(ii)) for ii in range(2, self.subharm + 2)], axis=-1)
+                x = torch.cat((x, torch.as_tensor(sub, dtype=self.dtype).reshape(pulse.shape[0], -1,
+                                                                                self.pulse_channels * self.subharm)), dim=-1)
+        elif self.subharm:                                                     # tf_wavetable.py:520-521, :554-559
             dt = self.np_dtype
             w2pi = pg["phase"].astype(dt) * dt(2) * dt(np.float32(np.pi))
             chans = [pg["pulse"].astype(dt)] + [np.sin(w2pi / dt(ii)) for ii in range(2, self.subharm + 2)]

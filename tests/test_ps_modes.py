@@ -12,7 +12,11 @@ from mbexwn_vocoder_b200.config import read_config
 from mbexwn_vocoder_b200.plan import PS_BAND_GAIN, PS_OFF, PS_STFT, build_plan
 from oracle.forward import OracleMBExWN, lin_interp, synthetic_mel, synthetic_noise
 
-VARIANTS = {"subharm": {"wavetable_config": {"nominalF0": 60, "maxF0": 550, "add_subharm_chans": 2}},
+_PULSE_PQMF = {"pulse_channels_use_pqmf": True,
+               "pulse_channels_multi_band_config": {"subbands": 5, "taps": 40, "cutoff_ratio": 0.11, "beta": 8.0}}
+VARIANTS = {"pulse_pqmf": dict(_PULSE_PQMF),
+            "pulse_pqmf_subharm": dict(_PULSE_PQMF, wavetable_config={"nominalF0": 60, "maxF0": 550, "add_subharm_chans": 1}),
+            "subharm": {"wavetable_config": {"nominalF0": 60, "maxF0": 550, "add_subharm_chans": 2}},
             "band_gain": {"ps_use_stft": False}, "band_gain_centered": {"ps_use_stft": False, "spect_filters_preserve_energy": True},
             "ps_off": {"ps_off": True}}
 
@@ -50,6 +54,26 @@ def test_subharmonic_channels_widen_the_wavenet_input():
     assert np.allclose(x[:, 0::3][:, :5], r["pulse"][0].reshape(-1, 5))
     assert np.allclose(x[:, 1::3][:, :5], np.sin(2 * np.pi * ph / 2), atol=1e-6)
     assert np.allclose(x[:, 2::3][:, :5], np.sin(2 * np.pi * ph / 3), atol=1e-6)
+
+
+def test_pulse_pqmf_analysis_input():
+    """pulse_channels_use_pqmf: the 5 WaveNet pulse channels are the bands of a PQMF analysis of the pulse train (decimated by
+    5) instead of 5 consecutive samples; an analysis -> synthesis round trip of the bank reconstructs the pulse."""
+    hp = _hp(VARIANTS["pulse_pqmf"])
+    plan = build_plan(hp)
+    assert plan.pulse_pqmf_ana.shape == (5, 41) and plan.wavenet.c_in == 6
+    with pytest.raises(RuntimeError, match="pulse_channels"):
+        build_plan(_hp(dict(_PULSE_PQMF, pulse_channels_multi_band_config={"subbands": 4, "taps": 40, "cutoff_ratio": 0.11, "beta": 8.0})))
+    orc = OracleMBExWN(hp, W.init_synthetic(plan, seed=12), torch.float32)
+    mel = synthetic_mel(8, 0)[None]
+    r = orc.forward(mel, synthetic_noise(8 * plan.steps_per_frame, 0)[None])
+    x, pulse = r["wn_in"][0], r["pulse"][0]
+    assert x.shape == (8 * 20, 6)
+    ana = plan.pulse_pqmf_ana
+    m, k = 37, 3                                              # one value by hand: sum_j pulse[5 m + j - 20] h_k[j]
+    idx = 5 * m + np.arange(41) - 20
+    ok = (idx >= 0) & (idx < pulse.size)
+    assert np.isclose(x[m, k], np.sum(pulse[idx[ok]] * ana[k][ok]), atol=1e-5)
 
 
 def test_checkpoint_round_trip_of_the_variants(tmp_path):
@@ -115,7 +139,7 @@ def test_gpu_variants_against_oracle(tmp_path, name):
         for u in range(len(lengths)):
             ref = refs[u]
             assert np.array_equal(taps["index"][u], ref["index"][0].reshape(-1))
-            if name == "subharm":
+            if name in ("subharm", "pulse_pqmf", "pulse_pqmf_subharm"):
                 x = ref["wn_in"][0]
                 got = inv.synth_batch(mels, noise=noise, f0=f0, taps=["wn_in"])[1]["wn_in"][u].reshape(x.shape)
                 assert np.abs(got - x).max() <= 1e-5 * np.abs(x).max()
