@@ -120,6 +120,9 @@ typedef struct {
     int32_t pulse_pqmf_taps;    /* pulse_channels_use_pqmf: the pulse train enters the WaveNet as the pulse_channels bands of a PQMF
                                    analysis bank (tensor "pulse_pqmf" (pulse_channels, taps + 1); TFPQMF.analysis,
                                    tf_preprocess.py:192-202, custom_pulsed_generator.py:895) instead of being folded; 0 = off */
+    int32_t wn_causal;          /* force_causal: the dilated WaveNet convs and the conditioning conv pad (k - 1) d zeros on the left
+                                   only (Keras padding "causal", custom_pulsed_generator.py:474-475); the sub-net ops carry their
+                                   own pad_l / pad_r */
 } mbexwn_config_t;
 
 /* One batch on the padded frame grid; all pointers are DEVICE pointers. */

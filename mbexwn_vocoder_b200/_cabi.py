@@ -59,7 +59,7 @@ class Config(C.Structure):
                 ("norm_proj_scale", C.c_float), ("norm_lin_scale", C.c_float), ("norm_lin_off", C.c_float),
                 ("norm_mel_scale", C.c_float),
                 ("ps_mode", C.c_int32), ("ps_preserve_energy", C.c_int32), ("wt_subharm", C.c_int32),
-                ("pulse_pqmf_taps", C.c_int32)]
+                ("pulse_pqmf_taps", C.c_int32), ("wn_causal", C.c_int32)]
 
 
 class Batch(C.Structure):

@@ -379,7 +379,7 @@ static int wavenet_fp32(Ctx& cx) {
         const float* b = tensor(h, n + "/conv1D_" + li + "/b", (size_t)2 * c.wn_c * 4, &rc); if (!b) return rc;
         const float* rw = tensor(h, n + "/res_skip_" + li + "/W", (size_t)c.wn_c * n_rs * 4, &rc); if (!rw) return rc;
         const float* rb = tensor(h, n + "/res_skip_" + li + "/b", (size_t)n_rs * 4, &rc); if (!rb) return rc;
-        mbexwn_op_t op = simple_conv(c.wn_k, c.wn_c, 2 * c.wn_c, d, (c.wn_k - 1) * d / 2);
+        mbexwn_op_t op = simple_conv(c.wn_k, c.wn_c, 2 * c.wn_c, d, (c.wn_causal ? (c.wn_k - 1) * d : (c.wn_k - 1) * d / 2));
         MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op, c.steps_per_frame, rows, hbuf, w, b, nullptr, z), cx.g, cx.s));
         GateArgs ga{z, cond, act, rows, c.steps_per_frame, c.wn_c, c.wn_cond_lin_up, c.wn_gate};
         MBX_CUDA_CHECK(launch_gate(ga, cx.g, cx.s));
@@ -475,7 +475,7 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
         const int cout = 2 * c.wn_c * c.wn_cond_conv_up;
         const float* w = tensor(h, n + "/W", (size_t)c.wn_cond_k * c.mel_channels * cout * 4, &rc); if (!w) return rc;
         const float* bias = tensor(h, n + "/b", (size_t)cout * 4, &rc); if (!bias) return rc;
-        mbexwn_op_t op = simple_conv(c.wn_cond_k, c.mel_channels, cout, 1, (c.wn_cond_k - 1) / 2);
+        mbexwn_op_t op = simple_conv(c.wn_cond_k, c.mel_channels, cout, 1, (c.wn_causal ? c.wn_cond_k - 1 : (c.wn_cond_k - 1) / 2));
         if (precision != MBEXWN_PREC_FP32_SIMT && h->tc_subnets && tc_eligible(op)) {
             const int cin_pad = round64(c.mel_channels);
             const float* wt = tensor(h, n + "/tc/W", (size_t)cout * 2 * op.k * cin_pad * 2, &rc); if (!wt) return rc;

@@ -1668,7 +1668,7 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         p1.tm_out = tm_a;
         if ((rc = make_map(im, &p1.tm_b, w1, n1, k1, TILE_N, error))) return rc;
         int shifts[16];
-        for (int t = 0; t < c.wn_k; ++t) shifts[t] = (t - (c.wn_k - 1) / 2) * d;
+        for (int t = 0; t < c.wn_k; ++t) shifts[t] = (t - (c.wn_causal ? c.wn_k - 1 : (c.wn_k - 1) / 2)) * d;
         p1.n_kb = build_kblocks(p1.kb, c.wn_k, shifts, cpad);
         p1.n_terms = n_terms; p1.a_lo_off = cpad; p1.b_lo_off = c.wn_k * cpad;
         if (f8) { p1.f16 = 1; p1.out_f16f8 = 1; p1.out_lo_scale = a_lo; }

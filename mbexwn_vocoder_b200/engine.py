@@ -74,6 +74,7 @@ def make_config(plan: ModelPlan) -> _cabi.Config:
     c.halo_frames = engine_halo(plan)
     c.ps_mode, c.ps_preserve_energy = plan.ps_mode, int(plan.ps_preserve_energy)
     c.wt_subharm = plan.subharm
+    c.wn_causal = int(wn.causal)
     c.pulse_pqmf_taps = int(plan.pulse_pqmf_cfg["taps"]) if plan.pulse_pqmf_cfg is not None else 0
     if plan.norm is not None:
         nm = plan.norm
@@ -94,6 +95,10 @@ def engine_halo(plan: ModelPlan) -> int:
         for op in ops:
             if op.kind == "conv" and op.conv.pad_mode != 0:
                 halo = max(halo, -(-(op.conv.pad_l + op.conv.pad_r) // op.rate_in))
+            elif op.kind == "conv":                          # zero padding is read from the guard rows
+                halo = max(halo, -(-max(op.conv.pad_l, op.conv.pad_r) // op.rate_in))
+    wn = plan.wavenet
+    halo = max(halo, wn.cond_k - 1 if wn.causal else (wn.cond_k - 1) // 2)     # conditioning conv at mel rate
     return halo
 
 

@@ -42,9 +42,10 @@ def main_context_frames(plan: ModelPlan) -> int:
     """Context (frames per side) after which a window's core no longer depends on where the window was cut, given the
     exact F0: WaveNet receptive field + conditioning conv / interpolation + VTF sub-net + PQMF + STFT + lifter smoothing."""
     wn = plan.wavenet
-    wn_rows = sum(d * (wn.k - 1) // 2 for d in wn.dilations) + max(plan.pqmf_back, plan.pqmf_q - 1 - plan.pqmf_back)
+    span = (wn.k - 1) if wn.causal else (wn.k - 1) // 2                      # causal convs look (k - 1) d rows back
+    wn_rows = sum(d * span for d in wn.dilations) + max(plan.pqmf_back, plan.pqmf_q - 1 - plan.pqmf_back)
     ctx = -(-wn_rows // wn.steps_per_frame)                                  # WaveNet + PQMF rows -> frames
-    ctx += (wn.cond_k - 1) // 2 + 1                                          # conditioning conv + its x10 interpolation
+    ctx += ((wn.cond_k - 1) if wn.causal else (wn.cond_k - 1) // 2) + 1      # conditioning conv + its x10 interpolation
     ctx += -(-(plan.stft_win // 2) // plan.hop)                              # STFT frames overlapping a sample
     ctx = max(ctx, subnet_reach_frames(plan.ps_ops) + 2,                     # VTF sub-net (per frame, no recursion)
               -(-(len(plan.f0_smooth) // 2) // plan.pulse_per_frame) + 2)    # F0 smoothing of the lifter selection

@@ -69,6 +69,7 @@ class WaveNetSpec:
     cond_lin_up: int            # linear interpolation factor after it
     steps_per_frame: int        # WaveNet rows per mel frame
     cond_cin: int = 80          # mel channels feeding the conditioning conv
+    causal: bool = False        # force_causal: padding "CAUSAL" for the dilated and the conditioning convs
 
 
 @dataclass
@@ -171,9 +172,12 @@ def subnet_program(specs, base_name: str, cin: int, final_n_channels: int, final
 
     Padding layers are folded into the conv that follows them; sub-pixel unfolds are free re-views.
     """
-    if force_causal:
-        raise NotImplementedError("force_causal sub-nets are not supported on the B200 path")
     act = ACT_PRELU if use_prelu else ACT_LEAKY
+    if force_causal:                                    # every pad on the left (custom_pulsed_generator.py:53, :76-81)
+        _pads = lambda ks: (ks - 1, 0)
+        _same = lambda ks: (ks - 1, 0)
+    else:
+        _pads, _same = _pad_sizes, _same_pad
     pad_kind = PAD_EDGE if pad_to_valid else PAD_SYMMETRIC
     ops: List[Op] = []
     rate, ch, total_ups = 1, cin, 1
@@ -193,7 +197,7 @@ def subnet_program(specs, base_name: str, cin: int, final_n_channels: int, final
                 up = int(spec[2][1:])
             else:
                 up = int(spec[2])
-        pl, pr = _pad_sizes(ks)
+        pl, pr = _pads(ks)
         name, act_name = f"{base_name}_Layer_{ii}", f"{base_name}_ActLayer_{ii}"
         if linear_up:
             conv = ConvLayer(name, ks, ch, nf, pad_l=pl, pad_r=pr, pad_mode=pad_kind, init_std=init_std)
@@ -205,7 +209,7 @@ def subnet_program(specs, base_name: str, cin: int, final_n_channels: int, final
                 conv = ConvLayer(name, ks, ch, nf * up, pad_l=pl, pad_r=pr, pad_mode=PAD_EDGE, subpixel=up,
                                  init_std=init_std, cb_free=up)
             else:
-                sl, sr = _same_pad(ks)
+                sl, sr = _same(ks)
                 conv = ConvLayer(name, ks, ch, nf * up, pad_l=sl, pad_r=sr, pad_mode=PAD_ZERO, subpixel=up,
                                  init_std=init_std, cb_free=up)
             ops.append(Op("conv", conv=conv, act=act, act_name=act_name, act_channels=nf,
@@ -219,11 +223,11 @@ def subnet_program(specs, base_name: str, cin: int, final_n_channels: int, final
         ch = nf
     if final_nks is not None:
         if pad_to_valid:
-            pl, pr = _pad_sizes(final_nks)
+            pl, pr = _pads(final_nks)
             conv = ConvLayer(f"{base_name}_Layer_final", final_nks, ch, final_n_channels, pad_l=pl, pad_r=pr,
                              pad_mode=PAD_EDGE, init_std=init_std)
         else:
-            sl, sr = _same_pad(final_nks)
+            sl, sr = _same(final_nks)
             conv = ConvLayer(f"{base_name}_Layer_final", final_nks, ch, final_n_channels, pad_l=sl, pad_r=sr,
                              pad_mode=PAD_ZERO, init_std=init_std)
         ch = final_n_channels
@@ -245,13 +249,13 @@ def subnet_program(specs, base_name: str, cin: int, final_n_channels: int, final
 def wavenet_layers(wn: WaveNetSpec) -> List[ConvLayer]:
     """Weight-carrying layers of one WaveNetAE in construction order (custom_AE_layers.py:177-259)."""
     n = wn.name + "_WNBlock_WN"
-    cl, cr = _same_pad(wn.cond_k)
+    cl, cr = ((wn.cond_k - 1), 0) if wn.causal else _same_pad(wn.cond_k)
     layers = [ConvLayer(f"{n}/start", 1, wn.c_in, wn.c),
               ConvLayer(f"{n}/end", 1, wn.c, wn.c_out),
               ConvLayer(f"{n}/cond_", wn.cond_k, wn.cond_cin, 2 * wn.c * wn.cond_conv_up, pad_l=cl, pad_r=cr,
                         subpixel=wn.cond_conv_up, cb_free=wn.cond_conv_up)]
     for i, d in enumerate(wn.dilations):
-        pl, pr = _same_pad(wn.k, d)
+        pl, pr = ((wn.k - 1) * d, 0) if wn.causal else _same_pad(wn.k, d)
         layers.append(ConvLayer(f"{n}/conv1D_{i}", wn.k, wn.c, 2 * wn.c, dilation=d, pad_l=pl, pad_r=pr))
         layers.append(ConvLayer(f"{n}/res_skip_{i}", 1, wn.c, 2 * wn.c if i < wn.n_layers - 1 else wn.c))
     return layers
@@ -315,8 +319,7 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
                            f"{pulse_rate / pch * np.prod(ups_factors) * S} != {sr}")
     if len(ups_factors) != 1 or ups_factors[0] != 1:
         raise NotImplementedError("multi-block / up-sampling WaveNet stacks are not built yet (SURVEY 8f-4)")
-    for key, why in (("force_causal", "causal convolutions"),
-                     ("pp_subnet_training_only", "pp_subnet_training_only")):
+    for key, why in (("pp_subnet_training_only", "pp_subnet_training_only"),):
         if mc.get(key):
             raise NotImplementedError(f"{why} is not built yet (SURVEY 8f-4)")
     # spectral shaping of the excitation (custom_pulsed_generator.py:666-724): STFT-domain vocal-tract filter (default),
@@ -338,14 +341,15 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
 
     pp_ops, _ = subnet_program(mc["pp_subnet"], "PulsPar", n_mel, 1, 1, ACT_SOFT_SIGMOID_AFFINE, 0.02,
                                pulse_per_frame, use_prelu, bool(mc.get("pp_subnet_use_valid_padding", False)),
-                               bool(mc.get("remove_inactive_pad_layers", False)))
+                               bool(mc.get("remove_inactive_pad_layers", False)), bool(mc.get("force_causal", False)))
     if not pp_ops:
         raise NotImplementedError("models without pp_subnet (constant F0) are not built yet")
     ps_ops: List[Op] = []
     if ps_mode != PS_OFF:
         ps_ops, _ = subnet_program(mc["ps_subnet"], "PS", n_mel, n_ceps if ps_mode == PS_STFT else S, 1, ACT_NONE, 0.01,
                                    None, use_prelu, bool(mc.get("ps_subnet_use_valid_padding", False)),
-                                   bool(mc.get("remove_inactive_pad_layers", False)))   # final width: :422
+                                   bool(mc.get("remove_inactive_pad_layers", False)),
+                                   bool(mc.get("force_causal", False)))                # final width: :422
         if not ps_ops or ps_ops[-1].rate_out != 1:
             raise NotImplementedError("VTF sub-net must stay at mel-frame rate")
 
@@ -389,7 +393,7 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
                      c_out=int(wn_cfg["n_out_channels"]), n_layers=n_layers, k=k, dilations=dil,
                      gate=_GATES[gate], cond_k=cond_k,
                      cond_conv_up=int(wn_rate // (spect_rate * cond_lin)), cond_lin_up=cond_lin,
-                     steps_per_frame=steps_per_frame, cond_cin=n_mel)
+                     steps_per_frame=steps_per_frame, cond_cin=n_mel, causal=bool(mc.get("force_causal", False)))
 
     win, fft = dsp_init.stft_sizes(sr, hop, mc.get("internal_win_size_s"), int(mc.get("internal_fft_over", 0)))
     fdb = mc.get("filter_max_db_range")
@@ -403,7 +407,7 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
         filter_max_log_range=(fdb / (20 * np.log10(np.exp(1)))) if fdb is not None else None,
         env_order_scale=mc.get("ps_env_order_scale"), wavetable_cfg=copy.deepcopy(mc["wavetable_config"]), norm=norm,
         ps_mode=ps_mode, ps_preserve_energy=preserve_energy, subharm=subharm, pulse_pqmf_cfg=pulse_pqmf_cfg)
-    half_span = max(d * (k - 1) // 2 for d in dil)
+    half_span = max(d * (k - 1) // (1 if wn.causal else 2) for d in dil)
     plan.max_halo_frames = max(1, -(-half_span // steps_per_frame))
     if finalize:
         finalize_plan(plan)

@@ -54,6 +54,8 @@ def conv1d_keras(x: torch.Tensor, kernel: torch.Tensor, bias: torch.Tensor, padd
     if padding == "SAME":
         total = (k - 1) * dilation
         xt = F.pad(xt, (total // 2, total - total // 2))
+    elif padding == "CAUSAL":                                 # Keras padding="causal": all (k - 1) d zeros on the left
+        xt = F.pad(xt, ((k - 1) * dilation, 0))
     elif padding != "VALID":
         raise NotImplementedError(padding)
     y = F.conv1d(xt, kernel.permute(2, 1, 0).contiguous(), bias, dilation=dilation)
@@ -100,8 +102,15 @@ class SubNet:
     """Layer list of generate_subnet_from_specs (custom_pulsed_generator.py:38-148), inference only."""
 
     def __init__(self, specs, base_name, weights, dtype, final_n_channels, final_nks, final_activation,
-                 target_ups=None, pad_to_valid=False, remove_inactive_pad_layers=False, use_prelu=True, alpha=0.2):
+                 target_ups=None, pad_to_valid=False, remove_inactive_pad_layers=False, use_prelu=True, alpha=0.2,
+                 force_causal=False):
         self.layers: List[Tuple] = []
+        default_padding = "CAUSAL" if force_causal else "SAME"            # custom_pulsed_generator.py:53
+
+        def pads(ks):
+            """TFPad1d sizes; force_causal moves all of them to the left (custom_pulsed_generator.py:76-81)."""
+            pl, pr = (ks - 1) // 2 + ((ks - 1) % 2), (ks - 1) // 2
+            return (pl + pr, 0, pl) if force_causal else (pl, pr, pl)
         self.w = weights
         self.dtype = dtype
         total_ups = 1
@@ -121,28 +130,28 @@ class SubNet:
                     up = int(spec[2][1:])
                 else:
                     up = spec[2]
-            pl, pr = (ks - 1) // 2 + ((ks - 1) % 2), (ks - 1) // 2
+            pl, pr, active = pads(ks)
             name = f"{base_name}_Layer_{ii}"
             if linear_up:
-                if (not remove_inactive_pad_layers) or pl > 0:
+                if (not remove_inactive_pad_layers) or active > 0:
                     self.layers.append(("pad", pl, pr, "EDGE" if pad_to_valid else "SYMMETRIC"))
                 self.layers.append(("conv", name, "VALID", 1))
                 self.layers.append(("lin", up))
             elif up > 1:
-                if pad_to_valid and pl > 0:
+                if pad_to_valid and active > 0:
                     self.layers.append(("pad", pl, pr, "EDGE"))
-                self.layers.append(("conv", name, "VALID" if pad_to_valid else "SAME", up))
+                self.layers.append(("conv", name, "VALID" if pad_to_valid else default_padding, up))
             else:
-                if (not remove_inactive_pad_layers) or pl > 0:
+                if (not remove_inactive_pad_layers) or active > 0:
                     self.layers.append(("pad", pl, pr, "EDGE" if pad_to_valid else "SYMMETRIC"))
                 self.layers.append(("conv", name, "VALID", 1))
             self.layers.append(("prelu", f"{base_name}_ActLayer_{ii}") if use_prelu else ("leaky", alpha))
             total_ups *= up
         if final_nks is not None:
-            pl, pr = (final_nks - 1) // 2 + ((final_nks - 1) % 2), (final_nks - 1) // 2
-            if pad_to_valid and pl > 0:
+            pl, pr, active = pads(final_nks)
+            if pad_to_valid and active > 0:
                 self.layers.append(("pad", pl, pr, "EDGE"))
-            self.layers.append(("conv", f"{base_name}_Layer_final", "VALID" if pad_to_valid else "SAME", 1))
+            self.layers.append(("conv", f"{base_name}_Layer_final", "VALID" if pad_to_valid else default_padding, 1))
             if target_ups is not None and total_ups != target_ups:
                 up = target_ups // total_ups
                 if total_ups * up != target_ups:
@@ -220,7 +229,8 @@ class OracleMBExWN:
         self.pp = SubNet(mc["pp_subnet"], "PulsPar", weights, dtype, 1, 1, mc.get("pp_activation", "soft_sigmoid"),
                          target_ups=self.pulse_per_frame, pad_to_valid=mc.get("pp_subnet_use_valid_padding", False),
                          remove_inactive_pad_layers=mc.get("remove_inactive_pad_layers", False),
-                         use_prelu=use_prelu, alpha=alpha)
+                         use_prelu=use_prelu, alpha=alpha, force_causal=bool(mc.get("force_causal", False)))
+        self.wn_padding = "CAUSAL" if mc.get("force_causal") else "SAME"       # custom_pulsed_generator.py:474-475
         self.ps_use_stft = bool(mc.get("ps_use_stft", True))
         self.ps_off = bool(mc.get("ps_off", False))
         self.preserve_energy = bool(mc.get("spect_filters_preserve_energy", False))
@@ -229,7 +239,7 @@ class OracleMBExWN:
         self.ps = None if self.ps_off else SubNet(mc["ps_subnet"], "PS", weights, dtype, ps_final, 1, None,
                          pad_to_valid=mc.get("ps_subnet_use_valid_padding", False),
                          remove_inactive_pad_layers=mc.get("remove_inactive_pad_layers", False),
-                         use_prelu=use_prelu, alpha=alpha)
+                         use_prelu=use_prelu, alpha=alpha, force_causal=bool(mc.get("force_causal", False)))
 
         wn = copy.deepcopy(mc["pp_mod_subnet"])
         self.C = int(wn.pop("n_channels") * mc["pp_mod_subnet_channel_factors"][0])
@@ -318,7 +328,7 @@ class OracleMBExWN:
     # ---- stage 3/4: conditioning + WaveNet ---------------------------------------------------------
     def conditioning(self, mel: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """cond_ sub-pixel conv + LinInterp (custom_AE_layers.py:215-227, :287-289)."""
-        c = self._conv(mel, f"{self.wn_name}/cond_", "SAME")
+        c = self._conv(mel, f"{self.wn_name}/cond_", self.wn_padding)
         c = c.reshape(c.shape[0], c.shape[1] * self.cond_conv_up, -1)
         return c, lin_interp(c, self.cond_lin)
 
@@ -331,7 +341,7 @@ class OracleMBExWN:
             taps["cond_lo"], taps["h0"] = cond_lo, h
         out = None
         for i, d in enumerate(self.dilations):
-            z = self._conv(h, f"{n}/conv1D_{i}", "SAME", d) + cond
+            z = self._conv(h, f"{n}/conv1D_{i}", self.wn_padding, d) + cond
             a, b = torch.split(z, z.shape[-1] // 2, dim=-1)
             if self.gate == "gtu":
                 a = torch.tanh(a)

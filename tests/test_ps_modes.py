@@ -14,7 +14,8 @@ from oracle.forward import OracleMBExWN, lin_interp, synthetic_mel, synthetic_no
 
 _PULSE_PQMF = {"pulse_channels_use_pqmf": True,
                "pulse_channels_multi_band_config": {"subbands": 5, "taps": 40, "cutoff_ratio": 0.11, "beta": 8.0}}
-VARIANTS = {"pulse_pqmf": dict(_PULSE_PQMF),
+VARIANTS = {"causal": {"force_causal": True},
+            "pulse_pqmf": dict(_PULSE_PQMF),
             "pulse_pqmf_subharm": dict(_PULSE_PQMF, wavetable_config={"nominalF0": 60, "maxF0": 550, "add_subharm_chans": 1}),
             "subharm": {"wavetable_config": {"nominalF0": 60, "maxF0": 550, "add_subharm_chans": 2}},
             "band_gain": {"ps_use_stft": False}, "band_gain_centered": {"ps_use_stft": False, "spect_filters_preserve_energy": True},
@@ -54,6 +55,31 @@ def test_subharmonic_channels_widen_the_wavenet_input():
     assert np.allclose(x[:, 0::3][:, :5], r["pulse"][0].reshape(-1, 5))
     assert np.allclose(x[:, 1::3][:, :5], np.sin(2 * np.pi * ph / 2), atol=1e-6)
     assert np.allclose(x[:, 2::3][:, :5], np.sin(2 * np.pi * ph / 3), atol=1e-6)
+
+
+def test_force_causal_moves_every_pad_to_the_left():
+    """force_causal (custom_pulsed_generator.py:53, :76-81, :474-475): no output sample depends on a later mel frame, up to
+    the look-ahead of the stages that are not convolutions (LinInterp's next row, PQMF, STFT)."""
+    hp = _hp(VARIANTS["causal"])
+    plan = build_plan(hp)
+    for layer in plan.conv_layers():
+        assert layer.pad_r == 0 and layer.pad_l == (layer.k - 1) * layer.dilation, layer.name
+    assert plan.wavenet.causal
+    orc = OracleMBExWN(hp, W.init_synthetic(plan, seed=12), torch.float32)
+    T = 30
+    mel = synthetic_mel(T, 0)[None]
+    mel2 = mel.copy()
+    mel2[:, 20:] = synthetic_mel(T, 5)[None][:, 20:]            # change the future of frame 20
+    nz = synthetic_noise(T * plan.steps_per_frame, 0)[None]
+    a, b = orc.forward(mel, nz), orc.forward(mel2, nz)
+    # WaveNet rows strictly before frame 19 (one frame of LinInterp look-ahead in the conditioning) are unchanged
+    assert np.array_equal(a["wn_out"][0, :18 * 20], b["wn_out"][0, :18 * 20])
+    assert not np.array_equal(a["wn_out"][0, 21 * 20:], b["wn_out"][0, 21 * 20:])
+    # the non-causal model looks ahead: the same experiment changes earlier rows
+    hp0 = _hp({})
+    orc0 = OracleMBExWN(hp0, W.init_synthetic(build_plan(hp0), seed=12), torch.float32)
+    a0, b0 = orc0.forward(mel, nz), orc0.forward(mel2, nz)
+    assert not np.array_equal(a0["wn_out"][0, :18 * 20], b0["wn_out"][0, :18 * 20])
 
 
 def test_pulse_pqmf_analysis_input():
@@ -128,7 +154,8 @@ def test_gpu_variants_against_oracle(tmp_path, name):
     inv = MELInverter(_model_dir(tmp_path, name), device=0, precision="fp32")
     plan = inv.plan
     oracle = OracleMBExWN(read_config(inv.config_file), inv.weights, torch.float32)
-    lengths = [33, 9, 1]
+    # (tf.pad SYMMETRIC cannot mirror 2 rows out of a 1-frame utterance: the causal reference needs >= 2 frames)
+    lengths = [33, 9, 2] if name == "causal" else [33, 9, 1]
     mels = [synthetic_mel(t, i) for i, t in enumerate(lengths)]
     noise = [synthetic_noise(t * plan.steps_per_frame, i) for i, t in enumerate(lengths)]
     f0 = [oracle.generate_f0(torch.as_tensor(m[None])).numpy()[0] for m in mels]
@@ -149,3 +176,12 @@ def test_gpu_variants_against_oracle(tmp_path, name):
             err = out[u].astype(np.float64) - wav
             snr = 10 * np.log10(np.sum(wav ** 2) / max(np.sum(err ** 2), 1e-300))
             assert snr >= 60.0, (precision, u, snr)
+    if name == "causal":
+        # chunked long-form synthesis stays bit-identical with the one-sided receptive field
+        inv.precision = "f16f8"
+        T = 131
+        mel = synthetic_mel(T, 9)
+        nz = synthetic_noise(T * plan.steps_per_frame, 9).reshape(-1)
+        whole = inv.synth_from_mel(mel[None], noise=[nz])
+        chunked = inv.synth_long_from_mel(mel, noise=nz, chunk_frames=40)
+        assert np.array_equal(whole, chunked)
