@@ -97,6 +97,18 @@ class Scheme:
             t1 = e4m3(al * 2.0 ** sa) @ e4m3(bh * 2.0 ** sb)
             t2 = e4m3(ah * 2.0 ** sa2) @ e4m3(bl * 2.0 ** sb2)
             return ah @ bh + (t1 + t2) * 2.0 ** -15
+        if n == "f16f8a":      # activation-side correction only (K = 64 e4m3 block): 1.5 units
+            ah, bh = rnd(a, torch.float16), rnd(b, torch.float16)
+            al = a - ah
+            sb = pow2_scale(b, 256.0)
+            sa_lo = 2.0 ** 8 if kind == "h" else 2.0 ** 12
+            return ah @ bh + e4m3(al * sa_lo) @ e4m3(bh * sb) / (sa_lo * sb)
+        if n == "f16f8w":      # weight-side correction only
+            ah, bh = rnd(a, torch.float16), rnd(b, torch.float16)
+            bl = b - bh
+            sbl = pow2_scale(bl, 256.0)
+            sa_hi = 2.0 ** -3 if kind == "h" else 2.0 ** 4
+            return ah @ bh + e4m3(ah * sa_hi) @ e4m3(bl * sbl) / (sa_hi * sbl)
         if n.startswith("f16f4"):
             # fp16 main product + the two correction products in block-scaled e2m1 (4x rate): 1.5 units
             kind4 = "nvf4" if "nv" in n else "mxf4"
@@ -174,7 +186,7 @@ def main():
     cond = cond[0]
     ref, href = wavenet(orc, Scheme("fp64"), x, cond)
     print(f"model {model}: rows {x.shape[0]}, C {orc.C}, |wn_out| peak {float(ref.abs().max()):.3f}, |h| peak {float(href.abs().max()):.2f}")
-    for name in ("bf16x3", "f16", "f16f8", "s15", "s15_hm", "f16f4nv", "f16f4mx"):
+    for name in ("bf16x3", "f16", "f16f8", "f16f8a", "f16f8w", "s15", "s15_hm", "f16f4nv", "f16f4mx"):
         out, h = wavenet(orc, Scheme(name), x, cond)
         err = (out - ref)
         snr = 10 * np.log10(float((ref ** 2).sum() / (err ** 2).sum()))
