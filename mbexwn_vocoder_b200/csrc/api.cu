@@ -517,6 +517,8 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
             mbexwn_op_t op = simple_conv(1, c.wn_c, c.wn_cout, 1, 0);
             ConvArgs a = conv_args(c, op, c.steps_per_frame, rows, cx.p<float>("skip"), w, bias, nullptr, cx.p<float>("wn_out"));
             a.ld_out = out_pad;
+            // the row pitch is padded to 32 channels and read back as float4s: define the padding columns
+            if (out_pad != c.wn_cout) MBX_CUDA_CHECK(cudaMemsetAsync(cx.p<float>("wn_out"), 0, (size_t)rows * out_pad * 4, s));
             MBX_CUDA_CHECK(launch_conv1d(a, cx.g, s));
             h->launches++;
         }

@@ -94,7 +94,8 @@ post_pqmf_kernel(PostPqmfArgs a, FrameGrid g) {
             const int e = i * 4, rl = e / a.ld, c = e - rl * a.ld;
             const long long r = r0 + rl;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r >= 0 && r < a.rows) v = __ldg(src + i);
+            // guard rows of the WaveNet output are never written by the res/skip epilogue: do not read them
+            if (r >= 0 && r < a.rows && __ldg(g.frame_utt + r / a.steps_per_frame) >= 0) v = __ldg(src + i);
             float* d = Xw + rl * (a.ld + 1) + c;
             d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         }
