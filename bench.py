@@ -396,9 +396,16 @@ def main():
         threads = os.cpu_count() or 1
         sample = 4 if frames <= 400 else 2
         v, med = cpu_oracle_throughput(model_id, frames, sample, 2, threads)
+        # also at 1 thread (the README's "single laptop core" claim) and 2 threads (the reference CLI default,
+        # bin/resynth_mel.py:120), one utterance each
+        sweep = {str(threads): v}
+        for n in (1, 2):
+            if n < threads:
+                sweep[str(n)] = cpu_oracle_throughput(model_id, frames, 1, 1, n)[0]
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
                                 "sample": f"{sample} of {batch} utterances x {frames} frames, median of 2 runs "
-                                          f"({med:.1f} s each), restated reference forward (torch-CPU fp32)"}
+                                          f"({med:.1f} s each), restated reference forward (torch-CPU fp32)",
+                                "by_threads": sweep}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
