@@ -498,9 +498,18 @@ stft_filter2048_kernel(StftFilterArgs a, FrameGrid g) {
         const float2 zk = S[k], zn = S[(FN - k) & (FN - 1)];
         const float2 X = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));        // spectrum of the real part
         const float2 L = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));        // spectrum of the imag part
-        const float mag = a.max_log_range > 0.f ? expf(a.max_log_range * tanhf(L.x)) : expf(L.x);
+        // exp(r tanh(x)) with tanh from one fast exponential: 1 - 2 / (1 + e^(2x)) (abs. error ~1e-7, x clamped where tanh
+        // has saturated); sin / cos of the phase through the fast path for |phase| <= 64, the accurate one beyond
+        float mag;
+        if (a.max_log_range > 0.f) {
+            const float e2 = __expf(2.f * fminf(fmaxf(L.x, -15.f), 15.f));
+            mag = __expf(a.max_log_range * (1.f - __fdividef(2.f, 1.f + e2)));
+        } else {
+            mag = expf(L.x);
+        }
         float sn, cs;
-        sincosf(L.y, &sn, &cs);
+        if (fabsf(L.y) <= 64.f) __sincosf(L.y, &sn, &cs);
+        else sincosf(L.y, &sn, &cs);
         const float2 V = make_float2(mag * cs, mag * sn);
         if (vtf_out) vtf_out[k] = V;
         Y[t] = cmul(X, V);
