@@ -87,15 +87,15 @@ post_pqmf_kernel(PostPqmfArgs a, FrameGrid g) {
         const long long r = r0 + i;
         s_fu[i] = (r >= 0 && r < a.rows) ? g.frame_utt[r / a.steps_per_frame] : -1;
     }
+    __syncthreads();                                      // the copy below skips guard rows by s_fu
     {   // coalesced float4 copy of the contiguous (tile_rows, ld) block
         const int n4 = tile_rows * a.ld / 4;
         const float4* src = reinterpret_cast<const float4*>(a.wn_out + r0 * a.ld);
         for (int i = tid; i < n4; i += PP_ROWS) {
             const int e = i * 4, rl = e / a.ld, c = e - rl * a.ld;
-            const long long r = r0 + rl;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             // guard rows of the WaveNet output are never written by the res/skip epilogue: do not read them
-            if (r >= 0 && r < a.rows && __ldg(g.frame_utt + r / a.steps_per_frame) >= 0) v = __ldg(src + i);
+            if (s_fu[rl] >= 0) v = __ldg(src + i);
             float* d = Xw + rl * (a.ld + 1) + c;
             d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         }
