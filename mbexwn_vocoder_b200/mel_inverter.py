@@ -156,7 +156,8 @@ class MELInverter(object):
         A strided probe of the output detects that and the batch is re-run on the equally accurate bf16x3 path (bf16 planes
         have the fp32 exponent range), with a note on stderr -- never a silent change of accuracy class."""
         out, tp = self.model.forward(mels, noise=noise, f0=f0, precision=self.precision, seed=seed, taps=taps)
-        if self.precision == "f16f8" and not all(np.isfinite(w[::1021]).all() for w in out):
+        # one hop in four is probed (every frame overlaps four hops, so a non-finite frame cannot hide), at least 64 probes
+        if self.precision == "f16f8" and not all(np.isfinite(w[::max(1, min(self.hop_size * 4 - 1, w.size // 64))]).all() for w in out):
             print("MELInverter::warning::non-finite samples on the f16f8 path (fp16 operand range exceeded); "
                   "re-running this batch with precision bf16x3", file=sys.stderr)
             out, tp = self.model.forward(mels, noise=noise, f0=f0, precision="bf16x3", seed=seed, taps=taps)

@@ -8,6 +8,7 @@ import bench
 from mbexwn_vocoder_b200.mel_inverter import MELInverter
 
 opt = sys.argv[1]
+VALUES = tuple(int(x) for x in sys.argv[3].split(",")) if len(sys.argv) > 3 else (0, 1)
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 inv = MELInverter("SPEECH", device=0, precision="f16f8")
 eng, plan = inv.model, inv.plan
@@ -32,7 +33,7 @@ def run(n):
 
 
 for rep in range(reps):
-    for v in (0, 1):
+    for v in VALUES:
         eng.set_option(opt, v)
         ms = run(20)
         eng.set_option("stage_timing", 1)
