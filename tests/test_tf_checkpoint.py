@@ -237,3 +237,36 @@ def test_resolve_weights_order(tmp_path):
     w_npz = W.init_synthetic(plan, seed=12)
     W.save(os.path.join(d, "weights.npz"), w_npz)
     assert np.array_equal(resolve_weights(d, plan, hp)["PS_Layer_0/v"], w_npz["PS_Layer_0/v"])
+
+
+def test_install_models_from_a_zip_like_the_reference_download(tmp_path):
+    """tools/install_models.py: a zip laid out like the reference's model archive (./MBExWN_NVoc/models/<name>/config.yaml +
+    weights.tf.*) is unpacked into a models directory, its checkpoint parsed and checked, optionally converted to npz."""
+    import importlib.util
+    import shutil
+    import zipfile
+    spec = importlib.util.spec_from_file_location("install_models", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "tools", "install_models.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cfg = get_config_file("SPEECH")
+    hp = read_config(cfg)
+    plan = build_plan(hp, finalize=False)
+    w = W.init_synthetic(plan, seed=21)
+    name = os.path.basename(os.path.dirname(cfg))
+    src = tmp_path / "pack" / "MBExWN_NVoc" / "models" / name
+    os.makedirs(src)
+    shutil.copy(cfg, src / "config.yaml")
+    T.export_weights(str(src / "weights.tf"), hp, w)
+    zpath = tmp_path / "models.zip"
+    with zipfile.ZipFile(zpath, "w") as z:
+        for f in os.listdir(src):
+            z.write(src / f, f"./MBExWN_NVoc/models/{name}/{f}")
+    dest = tmp_path / "installed"
+    assert mod.main([str(zpath), "--dest", str(dest), "--convert"]) == 0
+    files = sorted(os.listdir(dest / name))
+    assert files == ["config.yaml", "weights.npz", "weights.tf.data-00000-of-00001", "weights.tf.index"]
+    got = resolve_weights(str(dest / name), plan, hp)
+    assert all(np.array_equal(got[k], w[k]) for k in w)
+    with pytest.raises(FileNotFoundError):
+        mod.install(str(tmp_path / "installed" / name / "nothing"), str(dest))
