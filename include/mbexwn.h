@@ -35,9 +35,10 @@ extern "C" {
 #define MBEXWN_API
 #endif
 
-#define MBEXWN_ABI_VERSION 2
+#define MBEXWN_ABI_VERSION 3
 #define MBEXWN_MAX_LAYERS 64
 #define MBEXWN_MAX_OPS 32
+#define MBEXWN_MAX_BLOCKS 4
 
 typedef struct mbexwn_handle_s* mbexwn_handle_t;
 
@@ -71,6 +72,17 @@ typedef struct {
     char name[96];       /* layer name: tensors <name>/W (k,cin,cout) and <name>/b */
     char act_name[96];   /* PReLU tensor <act_name>/alpha */
 } mbexwn_op_t;
+
+/* One WaveNetAEBlock of pp_waveNetBlocks (custom_AE_layers.py:457-575, custom_pulsed_generator.py:459-488): a WaveNetAE and,
+ * when up > 1, the sub-pixel up-sampling conv TF2C_Conv1DUpDownSample(n_out_channels, kernel_size 3) behind it. */
+typedef struct {
+    int32_t c;              /* residual channels = n_channels x the block's channel factor */
+    int32_t cond_conv_up;   /* sub-pixel factor of the block's conditioning conv: block rate / (frame rate x cond_lin_upsampling) */
+    int32_t up;             /* up_down_factor; 1 = no up-sampling conv */
+    int32_t reserved;
+    char name[96];          /* tensor prefix of the block's WaveNetAE, used like wn_name */
+    char up_name[96];       /* up-sampling conv: <up_name>/W (3, wn_cout, wn_cout * up) and <up_name>/b */
+} mbexwn_wn_block_t;
 
 /* Flat model description == the keyword arguments of MBExWN.__init__ that matter at inference
  * (custom_pulsed_generator.py:155-230) after the rate algebra of :256-267 and :459-488. */
@@ -123,6 +135,14 @@ typedef struct {
     int32_t wn_causal;          /* force_causal: the dilated WaveNet convs and the conditioning conv pad (k - 1) d zeros on the left
                                    only (Keras padding "causal", custom_pulsed_generator.py:474-475); the sub-net ops carry their
                                    own pad_l / pad_r */
+    /* pp_waveNetBlocks with more than one block or with up-sampling (pp_mod_subnet_upsampling_factors / _channel_factors,
+     * custom_pulsed_generator.py:465-488).  0 = the single WaveNetAE of the wn_* fields, no up-sampling.  n >= 1: the blocks run
+     * in sequence and share wn_layers / wn_k / wn_dilations / wn_gate / wn_cond_k / wn_cond_lin_up / wn_cout (one pp_mod_subnet
+     * dict builds them all); wn_c, wn_cond_conv_up and wn_name are ignored.  Block 0 reads wn_cin channels at steps_per_frame
+     * rows per frame, block i + 1 reads the wn_cout channels block i (and its up-sampling conv) left at up_i times that rate;
+     * steps_per_frame x prod(up_i) = hop / subbands is the rate of the post net and the PQMF bank. */
+    int32_t wn_n_blocks;
+    mbexwn_wn_block_t wn_blocks[MBEXWN_MAX_BLOCKS];
 } mbexwn_config_t;
 
 /* One batch on the padded frame grid; all pointers are DEVICE pointers. */

@@ -9,9 +9,10 @@ import os
 
 _LIB = None
 LIB_NAME = "libmbexwn_b200.so"
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LAYERS = 64
 MAX_OPS = 32
+MAX_BLOCKS = 4
 N_STAGES = 7
 STAGE_NAMES = ("f0_net", "excitation", "cond_conv", "wavenet", "post_pqmf", "vtf_net", "stft_ola")
 
@@ -28,6 +29,11 @@ class Op(C.Structure):
                 ("subpixel", C.c_int32), ("up", C.c_int32), ("act", C.c_int32), ("act_channels", C.c_int32),
                 ("rate_in", C.c_int32), ("rate_out", C.c_int32), ("ch_out", C.c_int32),
                 ("name", C.c_char * 96), ("act_name", C.c_char * 96)]
+
+
+class WnBlock(C.Structure):
+    _fields_ = [("c", C.c_int32), ("cond_conv_up", C.c_int32), ("up", C.c_int32), ("reserved", C.c_int32),
+                ("name", C.c_char * 96), ("up_name", C.c_char * 96)]
 
 
 class Config(C.Structure):
@@ -59,7 +65,8 @@ class Config(C.Structure):
                 ("norm_proj_scale", C.c_float), ("norm_lin_scale", C.c_float), ("norm_lin_off", C.c_float),
                 ("norm_mel_scale", C.c_float),
                 ("ps_mode", C.c_int32), ("ps_preserve_energy", C.c_int32), ("wt_subharm", C.c_int32),
-                ("pulse_pqmf_taps", C.c_int32), ("wn_causal", C.c_int32)]
+                ("pulse_pqmf_taps", C.c_int32), ("wn_causal", C.c_int32),
+                ("wn_n_blocks", C.c_int32), ("wn_blocks", WnBlock * MAX_BLOCKS)]
 
 
 class Batch(C.Structure):

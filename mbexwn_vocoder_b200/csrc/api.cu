@@ -10,8 +10,18 @@
 #include "kernels.cuh"
 #include "wn_tc.cuh"
 
+// One WaveNetAEBlock as the engine runs it: the model config with the block's own WaveNet geometry substituted
+// (wn_c, wn_cin, wn_cond_conv_up, wn_name, steps_per_frame), so every WaveNet routine takes a block like a single-block model.
+struct WnBlock {
+    mbexwn_config_t cfg;
+    int up = 1;                 // sub-pixel up-sampling conv after the block (custom_AE_layers.py:519-526), 1 = none
+    std::string up_name;
+};
+
 struct mbexwn_handle_s {
     mbexwn_config_t cfg;
+    std::vector<WnBlock> blocks;    // >= 1 entry
+    int out_steps = 0;              // rows per frame behind the last block = hop / subbands
     int device = 0;
     std::map<std::string, std::pair<const void*, size_t>> tensors;
     std::string error;
@@ -90,10 +100,12 @@ static size_t subnet_hilo_elems(const mbexwn_op_t* ops, int n) {
     return m;
 }
 
-static Workspace carve(const mbexwn_config_t& c, int64_t F, int64_t n_chunks, int precision, int debug_taps) {
+static Workspace carve(const mbexwn_handle_s& hd, int64_t F, int64_t n_chunks, int precision, int debug_taps) {
+    const mbexwn_config_t& c = hd.cfg;
     Workspace w;
     const size_t f4 = sizeof(float);
-    const int64_t rows = F * c.steps_per_frame;
+    const int64_t rows = F * c.steps_per_frame;             // rate of the WaveNet input (block 0)
+    const int64_t out_rows = F * hd.out_steps;              // rate of the sub-band signals
     size_t sn = subnet_scratch_elems(c.pp_ops, c.n_pp_ops, c.mel_channels);
     size_t sn2 = subnet_scratch_elems(c.ps_ops, c.n_ps_ops, c.mel_channels);
     if (sn2 > sn) sn = sn2;
@@ -118,18 +130,39 @@ static Workspace carve(const mbexwn_config_t& c, int64_t F, int64_t n_chunks, in
         w.add("lifter_index", (size_t)F * sizeof(int32_t));
     }
     w.add("wn_in", (size_t)rows * c.wn_cin * f4);
-    w.add("cond", (size_t)F * c.wn_cond_conv_up * 2 * c.wn_c * f4);
-    w.add("wn_out", (size_t)rows * wn_tc_out_pad(c) * f4);
-    if (precision == MBEXWN_PREC_FP32_SIMT) {
-        w.add("skip", (size_t)rows * c.wn_c * f4);
-        w.add("h", (size_t)rows * c.wn_c * f4);
-        w.add("z", (size_t)rows * 2 * c.wn_c * f4);
-        w.add("act", (size_t)rows * c.wn_c * f4);
-        w.add("rs", (size_t)rows * 2 * c.wn_c * f4);
-    } else {
-        wn_tc_carve(c, rows, precision, [&](const char* n, size_t b) { w.add(n, b); });
+    {
+        // the blocks run one after the other and share their buffers: every slot takes its largest user
+        std::vector<std::pair<std::string, size_t>> wn;
+        auto need = [&](const std::string& name, size_t bytes) {
+            for (auto& e : wn)
+                if (e.first == name) { if (bytes > e.second) e.second = bytes; return; }
+            wn.emplace_back(name, bytes);
+        };
+        const int out_pad = wn_tc_out_pad(c);
+        for (size_t ib = 0; ib < hd.blocks.size(); ++ib) {
+            const mbexwn_config_t& bc = hd.blocks[ib].cfg;
+            const int64_t brows = F * bc.steps_per_frame;
+            need("cond", (size_t)F * bc.wn_cond_conv_up * 2 * bc.wn_c * f4);
+            need("wn_out", (size_t)brows * out_pad * f4);
+            if (precision == MBEXWN_PREC_FP32_SIMT) {
+                need("skip", (size_t)brows * bc.wn_c * f4);
+                need("h", (size_t)brows * bc.wn_c * f4);
+                need("z", (size_t)brows * 2 * bc.wn_c * f4);
+                need("act", (size_t)brows * bc.wn_c * f4);
+                need("rs", (size_t)brows * 2 * bc.wn_c * f4);
+            } else {
+                wn_tc_carve(bc, brows, precision, [&](const char* n, size_t b) { need(n, b); });
+            }
+            // up-sampling conv output: the next block's input (rows x wn_cout) or, behind the last block, the post net's
+            // input with the row pitch of wn_out
+            if (hd.blocks[ib].up > 1)
+                need("blk_in", (size_t)brows * hd.blocks[ib].up * (ib + 1 < hd.blocks.size() ? c.wn_cout : out_pad) * f4);
+            else if (ib + 1 < hd.blocks.size())
+                need("blk_in", (size_t)brows * c.wn_cout * f4);
+        }
+        for (auto& e : wn) w.add(e.first, e.second);
     }
-    w.add("subbands", (size_t)rows * c.subbands * f4);
+    w.add("subbands", (size_t)out_rows * c.subbands * f4);
     w.add("excitation", (size_t)F * c.hop * f4);
     w.add("ceps", (size_t)F * c.n_ceps * f4);
     w.add("frames", (size_t)F * c.stft_win * f4);
@@ -355,9 +388,8 @@ static mbexwn_op_t simple_conv(int k, int cin, int cout, int dil, int pad_l) {
     return op;
 }
 
-static int wavenet_fp32(Ctx& cx) {
+static int wavenet_fp32(Ctx& cx, const mbexwn_config_t& c, const float* wn_in) {
     mbexwn_handle_t h = cx.h;
-    const mbexwn_config_t& c = h->cfg;
     const long long rows = (long long)cx.g.n_frames * c.steps_per_frame;
     const std::string n = c.wn_name;
     int rc = 0;
@@ -368,7 +400,7 @@ static int wavenet_fp32(Ctx& cx) {
         const float* w = tensor(h, n + "/start/W", (size_t)c.wn_cin * c.wn_c * 4, &rc); if (!w) return rc;
         const float* b = tensor(h, n + "/start/b", (size_t)c.wn_c * 4, &rc); if (!b) return rc;
         mbexwn_op_t op = simple_conv(1, c.wn_cin, c.wn_c, 1, 0);
-        MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op, c.steps_per_frame, rows, cx.p<float>("wn_in"), w, b, nullptr, hbuf), cx.g, cx.s));
+        MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op, c.steps_per_frame, rows, wn_in, w, b, nullptr, hbuf), cx.g, cx.s));
         h->launches++;
     }
     for (int i = 0; i < c.wn_layers; ++i) {
@@ -401,11 +433,11 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
     if (precision < MBEXWN_PREC_FP32_SIMT || precision > MBEXWN_PREC_F16F8)
         return fail(h, MBEXWN_ERR_INVALID, "unknown precision");
     Ctx cx{h, b, FrameGrid{b->frame_utt, b->utt_begin, b->utt_end, b->n_frames, b->n_utt},
-           carve(c, b->n_frames, b->n_chunks, precision, h->debug_taps), reinterpret_cast<char*>(workspace), s};
+           carve(*h, b->n_frames, b->n_chunks, precision, h->debug_taps), reinterpret_cast<char*>(workspace), s};
     if (!workspace || workspace_bytes < cx.ws.total) return fail(h, MBEXWN_ERR_INVALID, "workspace too small");
     h->launches = 0;
     int rc = 0;
-    const long long rows = (long long)b->n_frames * c.steps_per_frame;
+    const long long rows = (long long)b->n_frames * h->out_steps;      // rows of the sub-band signals (post net, PQMF)
     int stage = 0;
     h->ev_recorded = false;
     if (h->stage_timing && !h->ev_ready) {
@@ -470,16 +502,16 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
 
     mark();
     // (3) conditioning conv at mel rate; the x10 linear interpolation is fused into the gate (custom_AE_layers.py:282-289)
-    {
-        const std::string n = std::string(c.wn_name) + "/cond_";
-        const int cout = 2 * c.wn_c * c.wn_cond_conv_up;
-        const float* w = tensor(h, n + "/W", (size_t)c.wn_cond_k * c.mel_channels * cout * 4, &rc); if (!w) return rc;
+    auto run_cond = [&](const mbexwn_config_t& bc) -> int {
+        const std::string n = std::string(bc.wn_name) + "/cond_";
+        const int cout = 2 * bc.wn_c * bc.wn_cond_conv_up;
+        const float* w = tensor(h, n + "/W", (size_t)bc.wn_cond_k * bc.mel_channels * cout * 4, &rc); if (!w) return rc;
         const float* bias = tensor(h, n + "/b", (size_t)cout * 4, &rc); if (!bias) return rc;
-        mbexwn_op_t op = simple_conv(c.wn_cond_k, c.mel_channels, cout, 1, (c.wn_causal ? c.wn_cond_k - 1 : (c.wn_cond_k - 1) / 2));
+        mbexwn_op_t op = simple_conv(bc.wn_cond_k, bc.mel_channels, cout, 1, (bc.wn_causal ? bc.wn_cond_k - 1 : (bc.wn_cond_k - 1) / 2));
         if (precision != MBEXWN_PREC_FP32_SIMT && h->tc_subnets && tc_eligible(op)) {
-            const int cin_pad = round64(c.mel_channels);
+            const int cin_pad = round64(bc.mel_channels);
             const float* wt = tensor(h, n + "/tc/W", (size_t)cout * 2 * op.k * cin_pad * 2, &rc); if (!wt) return rc;
-            MBX_RC(wn_tc_pack(mel, cx.p<char>("mel_hl"), b->n_frames, c.mel_channels, cin_pad, 1, 0, 0, PAD_ZERO, cx.g, s, &h->error));
+            MBX_RC(wn_tc_pack(mel, cx.p<char>("mel_hl"), b->n_frames, bc.mel_channels, cin_pad, 1, 0, 0, PAD_ZERO, cx.g, s, &h->error));
             TcConvArgs a{};
             a.a_hilo = cx.p<char>("mel_hl"); a.rows = b->n_frames; a.cin_pad = cin_pad; a.w = wt; a.cout = cout; a.k = op.k;
             a.dilation = 1; a.pad_l = op.pad_l; a.bias = bias; a.act = ACT_NONE; a.rate = 1;
@@ -487,49 +519,82 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
             MBX_RC(wn_tc_conv(h->tc, a, cx.g, s, &h->error));
             h->launches += 2;
         } else {
-            MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op, 1, b->n_frames, mel, w, bias, nullptr, cx.p<float>("cond")), cx.g, s));
+            MBX_CUDA_CHECK(launch_conv1d(conv_args(bc, op, 1, b->n_frames, mel, w, bias, nullptr, cx.p<float>("cond")), cx.g, s));
             h->launches++;
         }
-    }
+        return MBEXWN_OK;
+    };
+    if ((rc = run_cond(h->blocks[0].cfg))) return rc;
 
     mark();
-    // (4) WaveNet (WaveNetAE.call, custom_AE_layers.py:273-346)
-    if (precision == MBEXWN_PREC_FP32_SIMT) {
-        rc = wavenet_fp32(cx);
-    } else {
-        rc = wn_tc_forward(h->tc, c, cx.g, precision, cx.p<float>("wn_in"), cx.p<float>("cond"), cx.p<float>("wn_out"),
-                           [&](const char* nm) { return (void*)cx.p<char>(nm); },
-                           [&](const std::string& nm, size_t bytes) { int r = 0; return (const void*)tensor(h, nm, bytes, &r); },
-                           s, &h->launches, &h->error);
+    // (4) WaveNet blocks (custom_pulsed_generator.py:908-910): WaveNetAE.call (custom_AE_layers.py:273-346), then the block's
+    //     sub-pixel up-sampling conv (:519-526, :571-573) when its factor is > 1.  The released models are one block without it.
+    const int out_pad = wn_tc_out_pad(c);
+    const float* post_in = cx.p<float>("wn_out");
+    for (size_t ib = 0; ib < h->blocks.size(); ++ib) {
+        const WnBlock& blk = h->blocks[ib];
+        const mbexwn_config_t& bc = blk.cfg;
+        const bool last_block = ib + 1 == h->blocks.size();
+        const long long brows = (long long)b->n_frames * bc.steps_per_frame;
+        const float* wn_in = ib == 0 ? cx.p<float>("wn_in") : cx.p<float>("blk_in");
+        if (ib > 0 && (rc = run_cond(bc))) return rc;         // every block has its own conditioning conv
+        if (precision == MBEXWN_PREC_FP32_SIMT) {
+            rc = wavenet_fp32(cx, bc, wn_in);
+            if (rc) return rc;
+            // `end` 1x1 over the skip sum (custom_AE_layers.py:340); the tensor-core path folds it into the res_skip matrices
+            const std::string n = std::string(bc.wn_name) + "/end";
+            const float* w = tensor(h, n + "/W", (size_t)bc.wn_c * bc.wn_cout * 4, &rc); if (!w) return rc;
+            const float* bias = tensor(h, n + "/b", (size_t)bc.wn_cout * 4, &rc); if (!bias) return rc;
+            mbexwn_op_t op = simple_conv(1, bc.wn_c, bc.wn_cout, 1, 0);
+            ConvArgs a = conv_args(bc, op, bc.steps_per_frame, brows, cx.p<float>("skip"), w, bias, nullptr, cx.p<float>("wn_out"));
+            a.ld_out = out_pad;
+            // the row pitch is padded to 32 channels and read back as float4s: define the padding columns
+            if (out_pad != bc.wn_cout) MBX_CUDA_CHECK(cudaMemsetAsync(cx.p<float>("wn_out"), 0, (size_t)brows * out_pad * 4, s));
+            MBX_CUDA_CHECK(launch_conv1d(a, cx.g, s));
+            h->launches++;
+        } else {
+            rc = wn_tc_forward(h->tc, bc, cx.g, precision, wn_in, cx.p<float>("cond"), cx.p<float>("wn_out"),
+                               [&](const char* nm) { return (void*)cx.p<char>(nm); },
+                               [&](const std::string& nm, size_t bytes) { int r = 0; return (const void*)tensor(h, nm, bytes, &r); },
+                               s, &h->launches, &h->error);
+            if (rc) return rc;
+        }
+        if (blk.up > 1) {
+            // TF2C_Conv1DUpDownSample (conv_layers.py:250-255): k = 3 conv to wn_cout x up channels, channel c' of row t becomes
+            // row t x up + c' / wn_cout, channel c' % wn_cout
+            const int cout = bc.wn_cout * blk.up;
+            const float* w = tensor(h, blk.up_name + "/W", (size_t)3 * bc.wn_cout * cout * 4, &rc); if (!w) return rc;
+            const float* bias = tensor(h, blk.up_name + "/b", (size_t)cout * 4, &rc); if (!bias) return rc;
+            mbexwn_op_t op = simple_conv(3, bc.wn_cout, cout, 1, bc.wn_causal ? 2 : 1);
+            ConvArgs a = conv_args(bc, op, bc.steps_per_frame, brows, cx.p<float>("wn_out"), w, bias, nullptr, cx.p<float>("blk_in"));
+            a.ld_x = out_pad;
+            a.sub_ch = bc.wn_cout;
+            a.ld_out = last_block ? out_pad : bc.wn_cout;
+            if (last_block && out_pad != bc.wn_cout)
+                MBX_CUDA_CHECK(cudaMemsetAsync(cx.p<float>("blk_in"), 0, (size_t)brows * blk.up * out_pad * 4, s));
+            MBX_CUDA_CHECK(launch_conv1d(a, cx.g, s));
+            h->launches++;
+            if (last_block) post_in = cx.p<float>("blk_in");
+        } else if (!last_block) {
+            // the next block reads rows of wn_cout contiguous channels
+            MBX_CUDA_CHECK(cudaMemcpy2DAsync(cx.p<float>("blk_in"), (size_t)bc.wn_cout * 4, cx.p<float>("wn_out"), (size_t)out_pad * 4,
+                                             (size_t)bc.wn_cout * 4, (size_t)brows, cudaMemcpyDeviceToDevice, s));
+        }
     }
-    if (rc) return rc;
     mark();
 
     // (5) post 1x1 over the WaveNet output (custom_pulsed_generator.py:913-914), then PQMF synthesis (:920-921).
     //     Tensor-core path: `end` (custom_AE_layers.py:340) is already folded into the res_skip matrices; the fp32
     //     variant applies it here to the skip sum.
     {
-        const int out_pad = wn_tc_out_pad(c);
-        if (precision == MBEXWN_PREC_FP32_SIMT) {
-            const std::string n = std::string(c.wn_name) + "/end";
-            const float* w = tensor(h, n + "/W", (size_t)c.wn_c * c.wn_cout * 4, &rc); if (!w) return rc;
-            const float* bias = tensor(h, n + "/b", (size_t)c.wn_cout * 4, &rc); if (!bias) return rc;
-            mbexwn_op_t op = simple_conv(1, c.wn_c, c.wn_cout, 1, 0);
-            ConvArgs a = conv_args(c, op, c.steps_per_frame, rows, cx.p<float>("skip"), w, bias, nullptr, cx.p<float>("wn_out"));
-            a.ld_out = out_pad;
-            // the row pitch is padded to 32 channels and read back as float4s: define the padding columns
-            if (out_pad != c.wn_cout) MBX_CUDA_CHECK(cudaMemsetAsync(cx.p<float>("wn_out"), 0, (size_t)rows * out_pad * 4, s));
-            MBX_CUDA_CHECK(launch_conv1d(a, cx.g, s));
-            h->launches++;
-        }
         const std::string pn = c.post_name;
         const float* w = tensor(h, pn + "/W", (size_t)c.wn_cout * c.subbands * 4, &rc); if (!w) return rc;
         const float* bias = tensor(h, pn + "/b", (size_t)c.subbands * 4, &rc); if (!bias) return rc;
         const float* poly = tensor(h, "pqmf_poly", (size_t)c.pqmf_q * c.subbands * c.subbands * 4, &rc); if (!poly) return rc;
         PostPqmfArgs fa{};
-        fa.wn_out = cx.p<float>("wn_out"); fa.ld = out_pad; fa.cin = c.wn_cout; fa.post_w = w; fa.post_b = bias; fa.poly = poly;
+        fa.wn_out = post_in; fa.ld = out_pad; fa.cin = c.wn_cout; fa.post_w = w; fa.post_b = bias; fa.poly = poly;
         fa.sub_out = h->debug_taps ? cx.p<float>("subbands") : nullptr; fa.out = cx.p<float>("excitation");
-        fa.rows = rows; fa.steps_per_frame = c.steps_per_frame; fa.S = c.subbands; fa.Q = c.pqmf_q; fa.back = c.pqmf_back;
+        fa.rows = rows; fa.steps_per_frame = h->out_steps; fa.S = c.subbands; fa.Q = c.pqmf_q; fa.back = c.pqmf_back;
         if (c.ps_mode != 0) {
             // no STFT-domain filter: the PQMF output is the signal (custom_pulsed_generator.py:666-674)
             fa.out = b->out;
@@ -548,13 +613,13 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
             h->launches += 1;
         } else {
             mbexwn_op_t op = simple_conv(1, c.wn_cout, c.subbands, 1, 0);
-            ConvArgs a = conv_args(c, op, c.steps_per_frame, rows, cx.p<float>("wn_out"), w, bias, nullptr, cx.p<float>("subbands"));
+            ConvArgs a = conv_args(c, op, h->out_steps, rows, post_in, w, bias, nullptr, cx.p<float>("subbands"));
             a.ld_x = out_pad;
             MBX_CUDA_CHECK(launch_conv1d(a, cx.g, s));
             PqmfArgs pa{};
             pa.sub = cx.p<float>("subbands");
             pa.poly = poly;
-            pa.out = cx.p<float>("excitation"); pa.rows = rows; pa.steps_per_frame = c.steps_per_frame;
+            pa.out = cx.p<float>("excitation"); pa.rows = rows; pa.steps_per_frame = h->out_steps;
             pa.S = c.subbands; pa.Q = c.pqmf_q; pa.back = c.pqmf_back;
             MBX_CUDA_CHECK(launch_pqmf(pa, cx.g, s));
             h->launches += 2;
@@ -628,7 +693,15 @@ int mbexwn_create(const mbexwn_config_t* cfg, mbexwn_handle_t* out) {
         cfg->ps_mode < 0 || cfg->ps_mode > 2)
         return MBEXWN_ERR_INVALID;
     if (cfg->ps_mode == 1 && cfg->ps_ops[cfg->n_ps_ops - 1].ch_out != cfg->subbands) return MBEXWN_ERR_INVALID;
-    if (cfg->steps_per_frame * cfg->subbands != cfg->hop) return MBEXWN_ERR_INVALID;
+    if (cfg->wn_n_blocks < 0 || cfg->wn_n_blocks > MBEXWN_MAX_BLOCKS) return MBEXWN_ERR_INVALID;
+    int out_steps = cfg->steps_per_frame;
+    for (int i = 0; i < cfg->wn_n_blocks; ++i) {
+        const mbexwn_wn_block_t& bl = cfg->wn_blocks[i];
+        if (bl.c < 2 || bl.cond_conv_up < 1 || bl.up < 1 || !bl.name[0] || (bl.up > 1 && !bl.up_name[0])) return MBEXWN_ERR_INVALID;
+        if (out_steps != bl.cond_conv_up * cfg->wn_cond_lin_up) return MBEXWN_ERR_INVALID;   // custom_pulsed_generator.py:469
+        out_steps *= bl.up;
+    }
+    if (out_steps * cfg->subbands != cfg->hop) return MBEXWN_ERR_INVALID;
     if (cfg->steps_per_frame * cfg->pulse_channels != cfg->pulse_per_frame) return MBEXWN_ERR_INVALID;
     if (cfg->wt_subharm < 0 || cfg->wn_cin != cfg->pulse_channels * (1 + cfg->wt_subharm) + (cfg->noise_sigma != 0.f ? 1 : 0))
         return MBEXWN_ERR_INVALID;
@@ -644,6 +717,23 @@ int mbexwn_create(const mbexwn_config_t* cfg, mbexwn_handle_t* out) {
     mbexwn_handle_s* h = new mbexwn_handle_s();
     h->cfg = *cfg;
     h->device = dev;
+    h->out_steps = out_steps;
+    if (cfg->wn_n_blocks == 0) {
+        h->blocks.push_back(WnBlock{*cfg, 1, std::string()});
+    } else {
+        int rate = cfg->steps_per_frame;
+        for (int i = 0; i < cfg->wn_n_blocks; ++i) {
+            const mbexwn_wn_block_t& bl = cfg->wn_blocks[i];
+            WnBlock wb{*cfg, bl.up, std::string(bl.up_name)};
+            wb.cfg.wn_c = bl.c;
+            wb.cfg.wn_cond_conv_up = bl.cond_conv_up;
+            wb.cfg.steps_per_frame = rate;
+            if (i > 0) wb.cfg.wn_cin = cfg->wn_cout;
+            std::memcpy(wb.cfg.wn_name, bl.name, sizeof(wb.cfg.wn_name));
+            h->blocks.push_back(wb);
+            rate *= bl.up;
+        }
+    }
     *out = h;
     return MBEXWN_OK;
 }
@@ -677,7 +767,7 @@ int mbexwn_set_scalar(mbexwn_handle_t h, const char* name, float value) {
 
 size_t mbexwn_workspace_bytes(mbexwn_handle_t h, int32_t n_frames, int32_t n_chunks, int32_t precision) {
     if (!h || n_frames <= 0) return 0;
-    return mbx::carve(h->cfg, n_frames, n_chunks, precision, h->debug_taps).total;
+    return mbx::carve(*h, n_frames, n_chunks, precision, h->debug_taps).total;
 }
 
 int mbexwn_forward(mbexwn_handle_t h, const mbexwn_batch_t* batch, int32_t precision, void* workspace,
@@ -752,7 +842,7 @@ int mbexwn_forward_host_wait(mbexwn_handle_t h, int32_t slot) {
 int mbexwn_tap(mbexwn_handle_t h, const char* name, int32_t n_frames, int32_t n_chunks, int32_t precision,
                size_t* offset_bytes, size_t* n_bytes) {
     if (!h || !name || !offset_bytes || !n_bytes) return MBEXWN_ERR_INVALID;
-    mbx::Workspace w = mbx::carve(h->cfg, n_frames, n_chunks, precision, h->debug_taps);
+    mbx::Workspace w = mbx::carve(*h, n_frames, n_chunks, precision, h->debug_taps);
     auto it = w.slots.find(name);
     if (it == w.slots.end()) return mbx::fail(h, MBEXWN_ERR_MISSING, std::string("unknown tap: ") + name);
     *offset_bytes = it->second.off;

@@ -99,7 +99,12 @@ conv1d_kernel(ConvArgs a, FrameGrid g) {
                 float al = a.act == ACT_PRELU ? a.alpha[co % a.act_mod] : a.leaky;
                 v = apply_act(v, a.act, al, a.a0, a.a1);
             }
-            a.out[r * a.ld_out + co] = v;
+            if (a.sub_ch > 0) {
+                const int sub = co / a.sub_ch;
+                a.out[(r * (a.cout / a.sub_ch) + sub) * a.ld_out + (co - sub * a.sub_ch)] = v;
+            } else {
+                a.out[r * a.ld_out + co] = v;
+            }
         }
     }
 }

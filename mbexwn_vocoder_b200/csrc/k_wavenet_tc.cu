@@ -1349,10 +1349,11 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
 // inner loop reads only the cin inputs of a row from shared memory (the earlier version re-read the weights from shared
 // memory for every row and was bound by that traffic: 0.32 ms for 0.66 GB of output).
 constexpr int START_ROWS = 256;
-constexpr int START_MAX_CIN = 16;
+constexpr int START_MAX_CIN = 16;                      // register-resident weights up to here
+constexpr int START_WIDE_CIN = 40;                     // START_ROWS x cin floats of staging within the default 48 KB
 constexpr int START_LANES = 8;                          // rows in flight per block pass
 template <int CIN_MAX>
-__global__ void __launch_bounds__(START_LANES * 48, CIN_MAX <= 8 ? 2 : 1)
+__global__ void __launch_bounds__(START_LANES * 48, (CIN_MAX > 0 && CIN_MAX <= 8) ? 2 : 1)
 start_pack_kernel(const float* __restrict__ x, int cin, const float* __restrict__ w, const float* __restrict__ b,
                   __nv_bfloat16* __restrict__ out, long long rows, int c, int cpad, int rate, FrameGrid g,
                   int f16f8, float lo_scale) {
@@ -1363,7 +1364,9 @@ start_pack_kernel(const float* __restrict__ x, int cin, const float* __restrict_
     const int grp = threadIdx.x % groups, lane = threadIdx.x / groups;
     const int ch0 = grp * 8;
     const bool active = lane < START_LANES;
-    float wr[CIN_MAX][8], br[8];
+    // CIN_MAX = 0: wide inputs (the blocks behind the first of a multi-block stack read n_out_channels); the weights of a row pass
+    // come from global memory / L1 instead of registers
+    float wr[CIN_MAX > 0 ? CIN_MAX : 1][8], br[8];
 #pragma unroll
     for (int ci = 0; ci < CIN_MAX; ++ci)
 #pragma unroll
@@ -1394,6 +1397,13 @@ start_pack_kernel(const float* __restrict__ x, int cin, const float* __restrict_
                     const float xv = sx[rl * cin + ci];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = fmaf(xv, wr[ci][j], v[j]);
+                }
+            }
+            if (CIN_MAX == 0) {
+                for (int ci = 0; ci < cin; ++ci) {
+                    const float xv = sx[rl * cin + ci];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaf(xv, ch0 + j < c ? __ldg(w + ci * c + ch0 + j) : 0.f, v[j]);
                 }
             }
 #pragma unroll
@@ -1610,16 +1620,19 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         const float* w = (const float*)tensor(n + "/start/W", (size_t)c.wn_cin * c.wn_c * 4);
         const float* b = (const float*)tensor(n + "/start/b", (size_t)c.wn_c * 4);
         if (!w || !b) return fail("start conv weights missing", MBEXWN_ERR_MISSING);
-        if (c.wn_cin > START_MAX_CIN) return fail("start conv: more than 16 input channels", MBEXWN_ERR_UNSUPPORTED);
+        if (c.wn_cin > START_WIDE_CIN) return fail("start conv: more than 40 input channels", MBEXWN_ERR_UNSUPPORTED);
         if (cpad > 384) return fail("start conv: more than 384 residual channels", MBEXWN_ERR_UNSUPPORTED);
         const size_t smem = (size_t)START_ROWS * c.wn_cin * sizeof(float);
         const unsigned nblk = (unsigned)((rows + START_ROWS - 1) / START_ROWS), nthr = (unsigned)(START_LANES * (cpad >> 3));
         if (c.wn_cin <= 8)
             start_pack_kernel<8><<<nblk, nthr, smem, s>>>(wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g,
                                                           f8 ? 1 : 0, h_lo);
-        else
+        else if (c.wn_cin <= START_MAX_CIN)
             start_pack_kernel<16><<<nblk, nthr, smem, s>>>(wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g,
                                                            f8 ? 1 : 0, h_lo);
+        else
+            start_pack_kernel<0><<<nblk, nthr, smem, s>>>(wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g,
+                                                          f8 ? 1 : 0, h_lo);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(std::string("start conv: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
         *launches += 1;

@@ -20,6 +20,8 @@ struct ConvArgs {
     int act_mod;         // alpha index = co % act_mod (sub-pixel convs share alpha across the unfold)
     float leaky;         // LeakyReLU slope
     float a0, a1;        // affine of ACT_SOFT_SIGMOID_AFFINE
+    int sub_ch;          // > 0: sub-pixel unfold with its own row pitch -- channel co of row r goes to row r * (cout / sub_ch) +
+                         // co / sub_ch, column co % sub_ch of (rows * cout / sub_ch, ld_out); 0: out[r * ld_out + co]
 };
 cudaError_t launch_conv1d(const ConvArgs& a, const FrameGrid& g, cudaStream_t s);
 

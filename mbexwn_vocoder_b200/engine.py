@@ -59,6 +59,16 @@ def make_config(plan: ModelPlan) -> _cabi.Config:
     for i, d in enumerate(wn.dilations):
         c.wn_dilations[i] = d
     c.wn_name = (wn.name + "_WNBlock_WN").encode()
+    blocks = plan.blocks
+    if len(blocks) > 1 or blocks[0].up > 1:                # pp_waveNetBlocks beyond the single WaveNetAE of the released models
+        if len(blocks) > _cabi.MAX_BLOCKS:
+            raise NotImplementedError("too many WaveNet blocks for the C-ABI")
+        c.wn_n_blocks = len(blocks)
+        for i, b in enumerate(blocks):
+            dst = c.wn_blocks[i]
+            dst.c, dst.cond_conv_up, dst.up = b.c, b.cond_conv_up, b.up
+            dst.name = (b.name + "_WNBlock_WN").encode()
+            dst.up_name = b.up_name.encode() if b.up > 1 else b""
     c.post_name = plan.post_name.encode()
     c.n_ceps, c.stft_win, c.fft_size = plan.n_ceps, plan.stft_win, plan.fft_size
     c.n_lifters = 0 if plan.lifters is None else int(plan.lifters.shape[0])
@@ -87,8 +97,8 @@ def make_config(plan: ModelPlan) -> _cabi.Config:
 
 def engine_halo(plan: ModelPlan) -> int:
     """Guard frames between utterances: covers the widest dilated tap and the PQMF polyphase reach."""
-    reach = max(plan.max_halo_frames * plan.steps_per_frame, plan.pqmf_back, plan.pqmf_q - 1 - plan.pqmf_back)
-    halo = max(1, -(-reach // plan.steps_per_frame))
+    sub = plan.sub_per_frame or plan.steps_per_frame        # rows per frame of the sub-band signals
+    halo = max(1, plan.max_halo_frames, -(-max(plan.pqmf_back, plan.pqmf_q - 1 - plan.pqmf_back) // sub))
     # the tensor-core sub-net convs read their SYMMETRIC / EDGE pad rows from the guard rows next to each utterance:
     # the guard gap must hold the right pad of one utterance and the left pad of the next without overlap
     for ops in (plan.pp_ops, plan.ps_ops):

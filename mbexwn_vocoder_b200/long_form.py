@@ -43,8 +43,11 @@ def main_context_frames(plan: ModelPlan) -> int:
     exact F0: WaveNet receptive field + conditioning conv / interpolation + VTF sub-net + PQMF + STFT + lifter smoothing."""
     wn = plan.wavenet
     span = (wn.k - 1) if wn.causal else (wn.k - 1) // 2                      # causal convs look (k - 1) d rows back
-    wn_rows = sum(d * span for d in wn.dilations) + max(plan.pqmf_back, plan.pqmf_q - 1 - plan.pqmf_back)
-    ctx = -(-wn_rows // wn.steps_per_frame)                                  # WaveNet + PQMF rows -> frames
+    sub = plan.sub_per_frame or wn.steps_per_frame
+    ctx = -(-max(plan.pqmf_back, plan.pqmf_q - 1 - plan.pqmf_back) // sub)   # PQMF rows -> frames
+    for blk in plan.blocks:                                                  # receptive fields of the blocks add up
+        rows = sum(d * span for d in blk.dilations) + (2 if blk.up > 1 else 0)   # + the k = 3 up-sampling conv
+        ctx += -(-rows // blk.steps_per_frame)
     ctx += ((wn.cond_k - 1) if wn.causal else (wn.cond_k - 1) // 2) + 1      # conditioning conv + its x10 interpolation
     ctx += -(-(plan.stft_win // 2) // plan.hop)                              # STFT frames overlapping a sample
     ctx = max(ctx, subnet_reach_frames(plan.ps_ops) + 2,                     # VTF sub-net (per frame, no recursion)

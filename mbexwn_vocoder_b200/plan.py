@@ -70,6 +70,12 @@ class WaveNetSpec:
     steps_per_frame: int        # WaveNet rows per mel frame
     cond_cin: int = 80          # mel channels feeding the conditioning conv
     causal: bool = False        # force_causal: padding "CAUSAL" for the dilated and the conditioning convs
+    up: int = 1                 # WaveNetAEBlock.up_down_factor: sub-pixel up-sampling conv after the block (1 = none)
+
+    @property
+    def up_name(self) -> str:
+        """Layer name of the block's TF2C_Conv1DUpDownSample (custom_AE_layers.py:523-526)."""
+        return f"{self.name}_WNBlock_UP_{self.up}"
 
 
 @dataclass
@@ -134,6 +140,10 @@ class ModelPlan:
     ps_mode: int = PS_STFT      # PS_STFT | PS_BAND_GAIN | PS_OFF
     ps_preserve_energy: bool = False
     norm: Optional["NormMelSpec"] = None     # NormMelComponents (normalize_rms_from_mell), None = off
+    # pp_waveNetBlocks (custom_pulsed_generator.py:459-488): `wavenet` is block 0 (its rate = steps_per_frame, the rate of the
+    # pulse / noise input); later blocks run `up` times faster each; the last one ends at sub_per_frame = hop / subbands
+    wavenet_blocks: List["WaveNetSpec"] = field(default_factory=list)
+    sub_per_frame: int = 0
     # init-time constants (filled by finalize())
     wavetables: Optional[dsp_init.WaveTables] = None
     pqmf_syn: Optional[np.ndarray] = None
@@ -150,9 +160,14 @@ class ModelPlan:
         """Every weight-carrying conv in reference construction order."""
         out = [op.conv for op in self.pp_ops if op.kind == "conv"]
         out += [op.conv for op in self.ps_ops if op.kind == "conv"]
-        out += wavenet_layers(self.wavenet)
+        for wn in self.blocks:
+            out += wavenet_layers(wn)
         out.append(ConvLayer(self.post_name, 1, self.wavenet.c_out, self.subbands))
         return out
+
+    @property
+    def blocks(self) -> List["WaveNetSpec"]:
+        return self.wavenet_blocks or [self.wavenet]
 
 
 def _pad_sizes(ks: int) -> Tuple[int, int]:
@@ -258,6 +273,9 @@ def wavenet_layers(wn: WaveNetSpec) -> List[ConvLayer]:
         pl, pr = ((wn.k - 1) * d, 0) if wn.causal else _same_pad(wn.k, d)
         layers.append(ConvLayer(f"{n}/conv1D_{i}", wn.k, wn.c, 2 * wn.c, dilation=d, pad_l=pl, pad_r=pr))
         layers.append(ConvLayer(f"{n}/res_skip_{i}", 1, wn.c, 2 * wn.c if i < wn.n_layers - 1 else wn.c))
+    if wn.up > 1:                                       # WaveNetAEBlock.up_down_sample (custom_AE_layers.py:519-526): k = 3
+        ul, ur = (2, 0) if wn.causal else _same_pad(3)
+        layers.append(ConvLayer(wn.up_name, 3, wn.c_out, wn.c_out * wn.up, pad_l=ul, pad_r=ur, subpixel=wn.up))
     return layers
 
 
@@ -317,8 +335,14 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
     if pulse_rate / pch * np.prod(ups_factors) * S != sr:                               # :344
         raise RuntimeError(f"MBExWN::config_error::the generated sample rate "
                            f"{pulse_rate / pch * np.prod(ups_factors) * S} != {sr}")
-    if len(ups_factors) != 1 or ups_factors[0] != 1:
-        raise NotImplementedError("multi-block / up-sampling WaveNet stacks are not built yet (SURVEY 8f-4)")
+    # blocks = zip(upsampling factors, channel factors) (:465): the shorter list decides
+    n_blocks = min(len(ups_factors), len(chan_factors))
+    if n_blocks < 1 or any(int(u) != u or u < 1 for u in ups_factors):
+        raise RuntimeError(f"MBExWN::config_error::pp_mod_subnet_upsampling_factors {ups_factors} / "
+                           f"pp_mod_subnet_channel_factors {chan_factors}")
+    if int(np.prod(ups_factors[:n_blocks])) != int(np.prod(ups_factors)):
+        raise RuntimeError("MBExWN::config_error::up-sampling factors without a channel factor")
+    ups_factors, chan_factors = [int(u) for u in ups_factors[:n_blocks]], list(chan_factors[:n_blocks])
     for key, why in (("pp_subnet_training_only", "pp_subnet_training_only"),):
         if mc.get(key):
             raise NotImplementedError(f"{why} is not built yet (SURVEY 8f-4)")
@@ -354,19 +378,24 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
             raise NotImplementedError("VTF sub-net must stay at mel-frame rate")
 
     wn_cfg = copy.deepcopy(mc["pp_mod_subnet"])
-    c = int(wn_cfg.pop("n_channels") * chan_factors[0])
+    n_channels = wn_cfg.pop("n_channels")
     cond_lin = int(wn_cfg.pop("cond_lin_upsampling", 16))
     cond_k = int(wn_cfg.pop("cond_kernel_size", 3))
     wn_rate = pulse_rate / pch
     spect_rate = sr / hop
-    if wn_rate != (wn_rate // (spect_rate * cond_lin)) * spect_rate * cond_lin:         # :469
-        raise RuntimeError(f"MBExWN::config_error:: cannot achieve conditioning rate {wn_rate} by means of integer "
-                           f"usampling of spectrum rate {spect_rate} with linear up {cond_lin}")
+    block_rates = []
+    for u in ups_factors:                                                               # :465-488
+        if wn_rate != (wn_rate // (spect_rate * cond_lin)) * spect_rate * cond_lin:     # :469
+            raise RuntimeError(f"MBExWN::config_error:: cannot achieve conditioning rate {wn_rate} by means of integer "
+                               f"usampling of spectrum rate {spect_rate} with linear up {cond_lin}")
+        block_rates.append(wn_rate)
+        wn_rate *= u
+    wn_rate = block_rates[0]
     n_layers = int(wn_cfg.get("n_layers", 12))
     k = int(wn_cfg.get("kernel_size", 3))
     step = int(wn_cfg.get("dilation_rate_step", 1))
     max_log2 = wn_cfg.get("max_log2_dilation_rate", None)
-    if k % 2 != 1 or c % 2 != 0:
+    if k % 2 != 1 or any(int(n_channels * cf) % 2 for cf in chan_factors):
         raise AssertionError("WaveNetAE needs odd kernel_size and even n_channels")
     gate = wn_cfg.get("activation", "gtu")
     if gate not in _GATES:
@@ -389,11 +418,15 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
                                f"{pulse_pqmf_cfg.get('subbands')} != pulse_channels {pch}")
         if int(pulse_pqmf_cfg["taps"]) % 2:
             raise AssertionError("The number of taps mush be even number.")             # tf_preprocess.py:44
-    wn = WaveNetSpec(name="PP_waveNetBlock_ups1_0", c=c, c_in=pch * (1 + subharm) + (1 if sigma else 0),
-                     c_out=int(wn_cfg["n_out_channels"]), n_layers=n_layers, k=k, dilations=dil,
-                     gate=_GATES[gate], cond_k=cond_k,
-                     cond_conv_up=int(wn_rate // (spect_rate * cond_lin)), cond_lin_up=cond_lin,
-                     steps_per_frame=steps_per_frame, cond_cin=n_mel, causal=bool(mc.get("force_causal", False)))
+    blocks = []
+    for iwn, (u, cf, rate) in enumerate(zip(ups_factors, chan_factors, block_rates)):
+        blocks.append(WaveNetSpec(
+            name=f"PP_waveNetBlock_ups{mc['pp_mod_subnet_upsampling_factors'][iwn]}_{iwn}", c=int(n_channels * cf),
+            c_in=(pch * (1 + subharm) + (1 if sigma else 0)) if iwn == 0 else int(wn_cfg["n_out_channels"]),
+            c_out=int(wn_cfg["n_out_channels"]), n_layers=n_layers, k=k, dilations=list(dil), gate=_GATES[gate], cond_k=cond_k,
+            cond_conv_up=int(rate // (spect_rate * cond_lin)), cond_lin_up=cond_lin,
+            steps_per_frame=int(round(rate / spect_rate)), cond_cin=n_mel, causal=bool(mc.get("force_causal", False)), up=u))
+    wn = blocks[0]
 
     win, fft = dsp_init.stft_sizes(sr, hop, mc.get("internal_win_size_s"), int(mc.get("internal_fft_over", 0)))
     fdb = mc.get("filter_max_db_range")
@@ -406,9 +439,12 @@ def build_plan(hparams: Dict, finalize: bool = True) -> ModelPlan:
         pqmf_cfg=mb, stft_win=win, fft_size=fft,
         filter_max_log_range=(fdb / (20 * np.log10(np.exp(1)))) if fdb is not None else None,
         env_order_scale=mc.get("ps_env_order_scale"), wavetable_cfg=copy.deepcopy(mc["wavetable_config"]), norm=norm,
-        ps_mode=ps_mode, ps_preserve_energy=preserve_energy, subharm=subharm, pulse_pqmf_cfg=pulse_pqmf_cfg)
+        ps_mode=ps_mode, ps_preserve_energy=preserve_energy, subharm=subharm, pulse_pqmf_cfg=pulse_pqmf_cfg,
+        wavenet_blocks=blocks, sub_per_frame=sub_per_frame)
+    # guard frames: the widest single tap of any block (guard rows are re-zeroed by every layer, so reaches do not add up);
+    # the up-sampling conv between blocks reaches k - 1 = 2 rows at most
     half_span = max(d * (k - 1) // (1 if wn.causal else 2) for d in dil)
-    plan.max_halo_frames = max(1, -(-half_span // steps_per_frame))
+    plan.max_halo_frames = max(1, max(-(-max(half_span, 2 if b.up > 1 else 0) // b.steps_per_frame) for b in blocks))
     if finalize:
         finalize_plan(plan)
     return plan

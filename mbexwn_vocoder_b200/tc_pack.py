@@ -52,8 +52,15 @@ def pack_tc_weights(plan: ModelPlan, weights: Dict[str, np.ndarray]) -> Dict[str
 
 
 def _tc_matrices(plan: ModelPlan, weights: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
-    """fp32 GEMM operands of the tensor-core path: W1_i (2 cpad, k cpad), R_i (n2, cpad) and the biases b1_i, rb_i."""
-    wn = plan.wavenet
+    """fp32 GEMM operands of the tensor-core path for every WaveNet block (one for the released models)."""
+    out: Dict[str, np.ndarray] = {}
+    for wn in plan.blocks:
+        out.update(_tc_block_matrices(wn, weights))
+    return out
+
+
+def _tc_block_matrices(wn, weights: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """One WaveNetAE: W1_i (2 cpad, k cpad), R_i (n2, cpad) and the biases b1_i, rb_i."""
     C, k = wn.c, wn.k
     cpad = -(-C // TILE_K) * TILE_K
     name = wn.name + "_WNBlock_WN"
@@ -133,8 +140,6 @@ def pack_tc8_weights(plan: ModelPlan, weights: Dict[str, np.ndarray]):
     """The matrices of pack_tc_weights (same row order / folding, fp32 before the split) as [fp16 | e4m3 | e4m3] planes.
 
     Returns ({name: uint8 tensor}, shifts)."""
-    wn = plan.wavenet
-    name = wn.name + "_WNBlock_WN"
     mats = _tc_matrices(plan, weights)
     w1_max = max(float(np.abs(m).max()) for k, m in mats.items() if "/W1_" in k)
     r_max = max(float(np.abs(m).max()) for k, m in mats.items() if "/R_" in k)
@@ -159,9 +164,9 @@ def pack_conv_tc(w: np.ndarray) -> torch.Tensor:
 
 def pack_subnet_weights(plan: ModelPlan, weights: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
     """Tensor-core copies ("<layer>/tc/W") of the wide mel-rate convs: both sub-nets and the conditioning conv."""
-    wn = plan.wavenet
     layers = [op.conv for ops in (plan.pp_ops, plan.ps_ops) for op in ops if op.kind == "conv"]
-    layers += [l for l in plan.conv_layers() if l.name == f"{wn.name}_WNBlock_WN/cond_"]
+    cond_names = {f"{wn.name}_WNBlock_WN/cond_" for wn in plan.blocks}
+    layers += [l for l in plan.conv_layers() if l.name in cond_names]
     out: Dict[str, torch.Tensor] = {}
     for layer in layers:
         if layer.cin >= 32 and layer.cout >= 16 and layer.cout % 8 == 0 and layer.dilation == 1:

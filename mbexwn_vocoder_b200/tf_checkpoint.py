@@ -590,20 +590,23 @@ def import_weights(prefix: str, plan, verify: bool = True) -> Dict[str, np.ndarr
     if plan.ps_ops:                                        # ps_off models hold no PS sub-net
         _subnet_weights(g, g.child(block, "ps_subnet_layers"), plan.ps_ops, out)
     blocks = g.list_items(g.child(block, "pp_waveNetBlocks"))
-    if len(blocks) != 1:
-        raise NotImplementedError("multi-block WaveNet checkpoints are not supported (SURVEY 8f-4)")
-    wn = g.child(blocks[0], "wavenet")
-    base = plan.wavenet.name + "_WNBlock_WN"
-    _conv_weights(g, g.child(wn, "start"), f"{base}/start", out)
-    _conv_weights(g, g.child(wn, "end"), f"{base}/end", out)
-    _conv_weights(g, g.child(wn, "cond_layer"), f"{base}/cond_", out)
-    conv_nodes = g.list_items(g.child(wn, "conv_layers"))
-    rs_nodes = g.list_items(g.child(wn, "res_skip_layers"))
-    if len(conv_nodes) != plan.wavenet.n_layers or len(rs_nodes) != plan.wavenet.n_layers:
-        raise ValueError(f"checkpoint WaveNet has {len(conv_nodes)} layers, the config describes {plan.wavenet.n_layers}")
-    for i, (cn, rn) in enumerate(zip(conv_nodes, rs_nodes)):
-        _conv_weights(g, cn, f"{base}/conv1D_{i}", out)
-        _conv_weights(g, rn, f"{base}/res_skip_{i}", out)
+    if len(blocks) != len(plan.blocks):
+        raise ValueError(f"checkpoint holds {len(blocks)} WaveNet blocks, the config describes {len(plan.blocks)}")
+    for node, spec in zip(blocks, plan.blocks):
+        wn = g.child(node, "wavenet")
+        base = spec.name + "_WNBlock_WN"
+        _conv_weights(g, g.child(wn, "start"), f"{base}/start", out)
+        _conv_weights(g, g.child(wn, "end"), f"{base}/end", out)
+        _conv_weights(g, g.child(wn, "cond_layer"), f"{base}/cond_", out)
+        conv_nodes = g.list_items(g.child(wn, "conv_layers"))
+        rs_nodes = g.list_items(g.child(wn, "res_skip_layers"))
+        if len(conv_nodes) != spec.n_layers or len(rs_nodes) != spec.n_layers:
+            raise ValueError(f"checkpoint WaveNet has {len(conv_nodes)} layers, the config describes {spec.n_layers}")
+        for i, (cn, rn) in enumerate(zip(conv_nodes, rs_nodes)):
+            _conv_weights(g, cn, f"{base}/conv1D_{i}", out)
+            _conv_weights(g, rn, f"{base}/res_skip_{i}", out)
+        if spec.up > 1:                                    # WaveNetAEBlock.up_down_sample (custom_AE_layers.py:519-526)
+            _conv_weights(g, g.child(node, "up_down_sample"), spec.up_name, out)
     post = g.list_items(g.child(block, "wn_post_net"))
     if len(post) != 1:
         raise ValueError("checkpoint wn_post_net does not hold exactly one layer")
@@ -709,16 +712,19 @@ def export_weights(prefix: str, hparams: Dict, weights: Dict[str, np.ndarray]) -
             else:
                 b.add(lst, str(i))
     blocks = b.add(block, "pp_waveNetBlocks")
-    wnb = b.add(blocks, "0")
-    wn = b.add(wnb, "wavenet")
-    base, path = plan.wavenet.name + "_WNBlock_WN", "block/pp_waveNetBlocks/0/wavenet"
-    b.conv(wn, "start", f"{path}/start", "start", weights, f"{base}/start")
-    b.conv(wn, "end", f"{path}/end", "end", weights, f"{base}/end")
-    b.conv(wn, "cond_layer", f"{path}/cond_layer", "cond_", weights, f"{base}/cond_")
-    convs, rss = b.add(wn, "conv_layers"), b.add(wn, "res_skip_layers")
-    for i in range(plan.wavenet.n_layers):
-        b.conv(convs, str(i), f"{path}/conv_layers/{i}", f"conv1D_{i}", weights, f"{base}/conv1D_{i}")
-        b.conv(rss, str(i), f"{path}/res_skip_layers/{i}", f"res_skip_{i}", weights, f"{base}/res_skip_{i}")
+    for ib, spec in enumerate(plan.blocks):
+        wnb = b.add(blocks, str(ib))
+        wn = b.add(wnb, "wavenet")
+        base, path = spec.name + "_WNBlock_WN", f"block/pp_waveNetBlocks/{ib}/wavenet"
+        b.conv(wn, "start", f"{path}/start", "start", weights, f"{base}/start")
+        b.conv(wn, "end", f"{path}/end", "end", weights, f"{base}/end")
+        b.conv(wn, "cond_layer", f"{path}/cond_layer", "cond_", weights, f"{base}/cond_")
+        convs, rss = b.add(wn, "conv_layers"), b.add(wn, "res_skip_layers")
+        for i in range(spec.n_layers):
+            b.conv(convs, str(i), f"{path}/conv_layers/{i}", f"conv1D_{i}", weights, f"{base}/conv1D_{i}")
+            b.conv(rss, str(i), f"{path}/res_skip_layers/{i}", f"res_skip_{i}", weights, f"{base}/res_skip_{i}")
+        if spec.up > 1:
+            b.conv(wnb, "up_down_sample", f"block/pp_waveNetBlocks/{ib}/up_down_sample", spec.up_name, weights, spec.up_name)
     post = b.add(block, "wn_post_net")
     b.conv(post, "0", "block/wn_post_net/0", plan.post_name, weights, plan.post_name)
     tensors = dict(b.tensors)

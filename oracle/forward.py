@@ -212,8 +212,7 @@ class OracleMBExWN:
         self.pulse_rate_factor = mc.get("pulse_rate_factor", 2)
         self.pulse_rate = self.sample_rate / self.pulse_rate_factor
         self.pulse_channels = mc.get("pulse_channels", 8)
-        ups = mc["pp_mod_subnet_upsampling_factors"]
-        assert list(ups) == [1], "oracle covers the single-block scheme configuration"
+        ups = list(mc["pp_mod_subnet_upsampling_factors"])
         self.sub_per_frame = self.hop // self.mb_factor
         self.pulse_per_frame = (self.sub_per_frame * self.pulse_channels) // int(np.prod(ups))
         self.f0_down = int(self.sample_rate // self.pulse_rate)
@@ -242,19 +241,29 @@ class OracleMBExWN:
                          use_prelu=use_prelu, alpha=alpha, force_causal=bool(mc.get("force_causal", False)))
 
         wn = copy.deepcopy(mc["pp_mod_subnet"])
-        self.C = int(wn.pop("n_channels") * mc["pp_mod_subnet_channel_factors"][0])
+        n_channels = wn.pop("n_channels")
         self.cond_lin = wn.pop("cond_lin_upsampling", 16)
         self.cond_k = wn.pop("cond_kernel_size", 3)
         wn_rate = self.pulse_rate / self.pulse_channels
         spect_rate = self.sample_rate / self.hop
-        self.cond_conv_up = int(wn_rate // (spect_rate * self.cond_lin))
+        # pp_waveNetBlocks (custom_pulsed_generator.py:459-488): one WaveNetAEBlock per (up-sampling factor, channel factor);
+        # a block's conditioning conv up-samples to its own rate / cond_lin, its output rate is `up` times its input rate
+        self.blocks = []
+        rate = wn_rate
+        for iwn, (u, cf) in enumerate(zip(ups, mc["pp_mod_subnet_channel_factors"])):
+            self.blocks.append({"name": f"PP_waveNetBlock_ups{u}_{iwn}_WNBlock_WN", "C": int(n_channels * cf), "up": int(u),
+                                "up_name": f"PP_waveNetBlock_ups{u}_{iwn}_WNBlock_UP_{u}",
+                                "cond_conv_up": int(rate // (spect_rate * self.cond_lin))})
+            rate *= u
+        self.C = self.blocks[0]["C"]
+        self.cond_conv_up = self.blocks[0]["cond_conv_up"]
         self.n_layers = wn.get("n_layers", 12)
         self.k = wn.get("kernel_size", 3)
         step, max_log2 = wn.get("dilation_rate_step", 1), wn.get("max_log2_dilation_rate", None)
         self.dilations = [2 ** (int(i // step) % max_log2) if max_log2 is not None else 2 ** int(i // step)
                           for i in range(self.n_layers)]            # custom_AE_layers.py:229-233
         self.gate = wn.get("activation", "gtu")
-        self.wn_name = "PP_waveNetBlock_ups1_0_WNBlock_WN"
+        self.wn_name = self.blocks[0]["name"]
         self.post_name = "MBExWNGen_PaNMPulseWaveNet_Post"
 
         self.win_size, self.fft_size = dsp_init.stft_sizes(self.sample_rate, self.hop, mc.get("internal_win_size_s"),
@@ -326,17 +335,30 @@ class OracleMBExWN:
         return {"phase": phase, "index": i0, "frac": frac, "pulse": pulse}
 
     # ---- stage 3/4: conditioning + WaveNet ---------------------------------------------------------
-    def conditioning(self, mel: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    def conditioning(self, mel: torch.Tensor, block: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
         """cond_ sub-pixel conv + LinInterp (custom_AE_layers.py:215-227, :287-289)."""
-        c = self._conv(mel, f"{self.wn_name}/cond_", self.wn_padding)
-        c = c.reshape(c.shape[0], c.shape[1] * self.cond_conv_up, -1)
+        blk = self.blocks[block]
+        c = self._conv(mel, f"{blk['name']}/cond_", self.wn_padding)
+        c = c.reshape(c.shape[0], c.shape[1] * blk["cond_conv_up"], -1)
         return c, lin_interp(c, self.cond_lin)
 
     def wavenet(self, x: torch.Tensor, mel: torch.Tensor, taps: Optional[Dict] = None) -> torch.Tensor:
+        """The pp_waveNetBlocks loop (custom_pulsed_generator.py:908-910): WaveNetAEBlock.call (custom_AE_layers.py:564-575) =
+        WaveNetAE, then the sub-pixel up-sampling conv (k = 3, conv_layers.py:250-255) when the block's factor is > 1."""
+        for ib, blk in enumerate(self.blocks):
+            x = self.wavenet_block(x, mel, ib, taps if ib == len(self.blocks) - 1 else None)
+            if blk["up"] > 1:
+                y = self._conv(x, blk["up_name"], self.wn_padding)
+                x = y.reshape(y.shape[0], y.shape[1] * blk["up"], -1)
+            if taps is not None:
+                taps[f"block_out_{ib}"] = x
+        return x
+
+    def wavenet_block(self, x: torch.Tensor, mel: torch.Tensor, block: int = 0, taps: Optional[Dict] = None) -> torch.Tensor:
         """WaveNetAE.call (custom_AE_layers.py:273-346), n_ch_groups = 1, shared up-sampled conditioning."""
-        n = self.wn_name
+        n = self.blocks[block]["name"]
         h = self._conv(x, f"{n}/start")
-        cond_lo, cond = self.conditioning(mel)
+        cond_lo, cond = self.conditioning(mel, block)
         if taps is not None:
             taps["cond_lo"], taps["h0"] = cond_lo, h
         out = None
@@ -418,7 +440,7 @@ class OracleMBExWN:
             sub = sub * mb_gain[:, :sub.shape[1]]
         exc = self.pqmf_synthesis(sub)
         if taps is not None:
-            taps.update({"wn_out": y, "subbands": sub, "excitation": exc})
+            taps.update({"subbands": sub, "excitation": exc})      # "wn_out" = the last block's WaveNetAE output
         return exc
 
     # ---- stage 5: vocal-tract filter ---------------------------------------------------------------

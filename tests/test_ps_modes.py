@@ -1,5 +1,7 @@
-"""Variants of the spectral-shaping stage (custom_pulsed_generator.py:666-674): ps_use_stft = False
-(per-band gain from the PS sub-net, :857-884) and ps_off, on the CPU (plan / oracle) and against the oracle on the GPU."""
+"""Variants of the path the scheme configuration does not use: the spectral-shaping stage without the STFT
+filter (custom_pulsed_generator.py:666-674: ps_use_stft = False with the per-band gain of :857-884, ps_off), sub-harmonic
+channels, PQMF analysis of the pulse train, force_causal and multi-block / up-sampling WaveNet stacks (:459-488,
+custom_AE_layers.py:457-575) -- on the CPU (plan / oracle) and against the oracle on the GPU."""
 import os
 
 import numpy as np
@@ -19,7 +21,13 @@ VARIANTS = {"causal": {"force_causal": True},
             "pulse_pqmf_subharm": dict(_PULSE_PQMF, wavetable_config={"nominalF0": 60, "maxF0": 550, "add_subharm_chans": 1}),
             "subharm": {"wavetable_config": {"nominalF0": 60, "maxF0": 550, "add_subharm_chans": 2}},
             "band_gain": {"ps_use_stft": False}, "band_gain_centered": {"ps_use_stft": False, "spect_filters_preserve_energy": True},
-            "ps_off": {"ps_off": True}}
+            "ps_off": {"ps_off": True},
+            # pp_waveNetBlocks: a block at 800 Hz with a x2 sub-pixel up-sampling conv, then a block at 1600 Hz ...
+            "blocks_2x1": {"pulse_channels": 10, "pp_mod_subnet_upsampling_factors": [2, 1],
+                           "pp_mod_subnet_channel_factors": [0.5, 0.25]},
+            # ... two blocks at 800 Hz, the up-sampling conv behind the last one feeds the post net
+            "blocks_1x2": {"pulse_channels": 10, "pp_mod_subnet_upsampling_factors": [1, 2],
+                           "pp_mod_subnet_channel_factors": [0.25, 0.5]}}
 
 
 def _hp(extra):
@@ -102,6 +110,61 @@ def test_pulse_pqmf_analysis_input():
     assert np.isclose(x[m, k], np.sum(pulse[idx[ok]] * ana[k][ok]), atol=1e-5)
 
 
+def test_multi_block_wavenet_plan_and_oracle():
+    """pp_mod_subnet_upsampling_factors / _channel_factors build one WaveNetAEBlock each (custom_pulsed_generator.py:465-488):
+    rates multiply by the up-sampling factors, every block has its own conditioning conv (sub-pixel factor = block rate /
+    (frame rate x cond_lin_upsampling)), blocks behind the first read n_out_channels, and a block with factor > 1 ends in a
+    k = 3 sub-pixel conv named <block>_WNBlock_UP_<factor> (custom_AE_layers.py:519-526)."""
+    hp = _hp(VARIANTS["blocks_2x1"])
+    plan = build_plan(hp)
+    b0, b1 = plan.blocks
+    assert plan.wavenet is b0 and (plan.steps_per_frame, plan.sub_per_frame, plan.pulse_per_frame) == (10, 20, 100)
+    assert (b0.name, b0.c, b0.c_in, b0.steps_per_frame, b0.cond_conv_up, b0.up) == ("PP_waveNetBlock_ups2_0", 160, 11, 10, 1, 2)
+    assert (b1.name, b1.c, b1.c_in, b1.steps_per_frame, b1.cond_conv_up, b1.up) == ("PP_waveNetBlock_ups1_1", 80, 30, 20, 2, 1)
+    ups = [l for l in plan.conv_layers() if "_WNBlock_UP_" in l.name]
+    assert [(l.name, l.k, l.cin, l.cout, l.subpixel) for l in ups] == [("PP_waveNetBlock_ups2_0_WNBlock_UP_2", 3, 30, 60, 2)]
+    single = build_plan(_hp({}), finalize=False)
+    assert len(single.blocks) == 1 and single.blocks[0].up == 1 and single.sub_per_frame == single.steps_per_frame == 20
+    with pytest.raises(RuntimeError, match="generated sample rate"):                 # custom_pulsed_generator.py:344
+        build_plan(_hp({"pp_mod_subnet_upsampling_factors": [2, 1], "pp_mod_subnet_channel_factors": [1, 1]}), finalize=False)
+    with pytest.raises(RuntimeError, match="cannot achieve conditioning rate"):      # :469: 400 Hz is not 80 Hz x 10 x n
+        build_plan(_hp({"pulse_channels": 20, "pp_mod_subnet_upsampling_factors": [4], "pp_mod_subnet_channel_factors": [1]}),
+                   finalize=False)
+    w = W.init_synthetic(plan, seed=12)
+    orc = OracleMBExWN(hp, w, torch.float32)
+    T_ = 7
+    mel = synthetic_mel(T_, 0)[None]
+    nz = synthetic_noise(T_ * plan.steps_per_frame, 0)[None]
+    r = orc.forward(mel, nz)
+    assert r["wn_in"].shape == (1, T_ * 10, 11) and r["block_out_0"].shape == (1, T_ * 20, 30)
+    assert r["wn_out"].shape == (1, T_ * 20, 30) and r["subbands"].shape == (1, T_ * 20, 15) and r["waveform"].shape == (1, T_ * 300)
+    # the up-sampling conv by hand: row 2 t + s of its output = channels [30 s, 30 s + 30) of the k = 3 SAME conv at row t
+    x0 = orc.wavenet_block(torch.as_tensor(r["wn_in"]), torch.as_tensor(mel), 0)
+    kern, bias = W.folded(w, b0.up_name)
+    t = 4
+    row = sum(x0[0, t - 1 + j].numpy() @ kern[j] for j in range(3)) + bias
+    assert np.allclose(r["block_out_0"][0, 2 * t], row[:30], atol=1e-5) and np.allclose(r["block_out_0"][0, 2 * t + 1], row[30:], atol=1e-5)
+    # the up-sampling conv behind the last block feeds the post net
+    hp2 = _hp(VARIANTS["blocks_1x2"])
+    plan2 = build_plan(hp2)
+    assert [(b.steps_per_frame, b.cond_conv_up, b.up) for b in plan2.blocks] == [(10, 1, 1), (10, 1, 2)] and plan2.sub_per_frame == 20
+    r2 = OracleMBExWN(hp2, W.init_synthetic(plan2, seed=12), torch.float32).forward(mel, nz)
+    assert r2["wn_out"].shape == (1, T_ * 10, 30) and r2["block_out_1"].shape == (1, T_ * 20, 30) and r2["subbands"].shape == (1, T_ * 20, 15)
+
+
+def test_multi_block_cabi_config_and_context():
+    from mbexwn_vocoder_b200.engine import make_config
+    from mbexwn_vocoder_b200.long_form import main_context_frames
+    plan = build_plan(_hp(VARIANTS["blocks_2x1"]))
+    c = make_config(plan)
+    assert c.wn_n_blocks == 2 and c.steps_per_frame == 10 and c.wn_cin == 11 and c.wn_cout == 30
+    assert [(b.c, b.cond_conv_up, b.up) for b in c.wn_blocks[:2]] == [(160, 1, 2), (80, 2, 1)]
+    assert c.wn_blocks[0].up_name == b"PP_waveNetBlock_ups2_0_WNBlock_UP_2" and c.wn_blocks[1].name == b"PP_waveNetBlock_ups1_1_WNBlock_WN"
+    assert make_config(build_plan(_hp({}))).wn_n_blocks == 0
+    # receptive fields of the blocks add up: 30 rows at 10 per frame + 2 (up conv) and 30 rows at 20 per frame
+    assert main_context_frames(plan) >= 4 + 2 + main_context_frames(build_plan(_hp({}))) - 2 - 1
+
+
 def test_checkpoint_round_trip_of_the_variants(tmp_path):
     for name, extra in VARIANTS.items():
         hp = _hp(extra)
@@ -176,8 +239,8 @@ def test_gpu_variants_against_oracle(tmp_path, name):
             err = out[u].astype(np.float64) - wav
             snr = 10 * np.log10(np.sum(wav ** 2) / max(np.sum(err ** 2), 1e-300))
             assert snr >= 60.0, (precision, u, snr)
-    if name == "causal":
-        # chunked long-form synthesis stays bit-identical with the one-sided receptive field
+    if name in ("causal", "blocks_2x1"):
+        # chunked long-form synthesis stays bit-identical with the one-sided receptive field / the blocks' summed context
         inv.precision = "f16f8"
         T = 131
         mel = synthetic_mel(T, 9)
