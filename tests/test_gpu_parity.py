@@ -96,6 +96,48 @@ def test_index_bit_exact_and_downstream(engine, oracle, speech_setup, lengths):
         assert _snr_db(ref["waveform"], out[u]) >= 60.0
 
 
+def test_cuda_pulse_generator_matches_the_reference_source(engine, speech_setup):
+    """CUDA excitation head vs tests/golden/reference_pulse.npz -- the output of the reference's own PulseWaveTable.call /
+    stable_cumsum_and_wrap / _linear_lookup source (tests/golden/make_reference_pulse_goldens.py), no oracle in between:
+    wrapped phase and integer table index bit for bit, pulse samples to 1e-5 of the peak.  Constant, swept (45 - 700 Hz) and
+    random-walk F0 over 23, 10 and 7 frames (2.3, 1 and 0.7 cumsum chunks)."""
+    import os
+    hp, plan, w = speech_setup
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_pulse.npz"))
+    mels, noise, f0, keys = [], [], [], []
+    for n in (2300, 1000, 700):
+        for row in range(3):
+            t = n // plan.pulse_per_frame
+            mels.append(synthetic_mel(t, len(mels)))
+            noise.append(synthetic_noise(t * plan.steps_per_frame, len(noise)))
+            f0.append(gold[f"sp_s0_{n}_f0"][row])
+            keys.append((f"sp_s0_{n}", row))
+    _, tp = engine.forward(mels, noise=noise, f0=f0, precision="fp32", taps=["phase", "index", "pulse"])
+    for u, (key, row) in enumerate(keys):
+        assert np.array_equal(tp["index"][u], gold[key + "_index"][row]), (key, row)
+        assert np.array_equal(tp["phase"][u], gold[key + "_phase"][row]), (key, row)
+        ref = gold[key + "_audio"][row, :, 0]
+        assert np.abs(tp["pulse"][u] - ref).max() <= 1e-5 * np.abs(ref).max(), (key, row)
+
+
+def test_cuda_pulse_generator_wide_range_matches_the_reference_source():
+    """Same check on the 60 - 1400 Hz wavetable bank (MW-SI-FD): the 45 - 1400 Hz sweep selects every table of the bank."""
+    import os
+    from mbexwn_vocoder_b200.mel_inverter import MELInverter
+    inv = MELInverter("SING", device=0, precision="fp32")
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_pulse.npz"))
+    key, t = "vo_s0_2300", 23
+    mels = [synthetic_mel(t, i) for i in range(3)]
+    noise = [synthetic_noise(t * inv.plan.steps_per_frame, i) for i in range(3)]
+    _, tp = inv.synth_batch(mels, noise=noise, f0=list(gold[key + "_f0"]), taps=["phase", "index", "pulse"])
+    for row in range(3):
+        assert np.array_equal(tp["index"][row], gold[key + "_index"][row]), row
+        assert np.array_equal(tp["phase"][row], gold[key + "_phase"][row]), row
+        ref = gold[key + "_audio"][row, :, 0]
+        assert np.abs(tp["pulse"][row] - ref).max() <= 1e-5 * np.abs(ref).max(), row
+    inv.model.close()
+
+
 def test_cuda_matches_committed_goldens(engine, speech_setup):
     """CUDA path vs the fixture minted by tests/golden/make_oracle_goldens.py (no oracle run needed)."""
     import os

@@ -1,0 +1,68 @@
+"""The pulse generator of the oracle against goldens produced by the REAL reference source: tests/golden/reference_pulse.npz holds
+what ``PulseWaveTable.call`` / ``stable_cumsum_and_wrap`` / ``_linear_lookup`` (tf_wavetable.py:429-638), executed unmodified from
+/root/reference over NumPy stand-ins for the TensorFlow primitives (tests/golden/make_reference_pulse_goldens.py), return for
+constant, swept and random-walk F0 contours.  Wrapped phase and table index must match bit for bit, the float outputs to 1e-6."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mbexwn_vocoder_b200 import get_config_file, weights as W
+from mbexwn_vocoder_b200.config import read_config
+from mbexwn_vocoder_b200.plan import build_plan
+from oracle.forward import OracleMBExWN, synthetic_mel, synthetic_noise
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_pulse.npz"))
+MODEL = {"sp": "SPEECH", "vo": "SING"}                  # wavetable_config (nominalF0 60, maxF0 550 / 1400), pulse rate 8 kHz
+
+
+def _oracle(tag, subharm):
+    hp = read_config(get_config_file(MODEL[tag]))
+    if subharm:
+        hp["mbexwn_config"]["wavetable_config"] = dict(hp["mbexwn_config"]["wavetable_config"], add_subharm_chans=subharm)
+    plan = build_plan(hp)
+    return plan, OracleMBExWN(hp, W.init_synthetic(plan, seed=0), torch.float32)
+
+
+@pytest.mark.parametrize("tag", ["sp", "vo"])
+def test_oracle_pulse_generator_matches_the_reference_source(tag):
+    plan, orc = _oracle(tag, 0)
+    assert np.array_equal(orc.wt.tables, np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_init_dsp.npz"))[f"wt_{tag}_tables"])
+    for n in (2300, 1000, 700):
+        key = f"{tag}_s0_{n}"
+        f0 = GOLD[key + "_f0"]
+        got = orc.pulse_generator(f0)
+        assert got["phase"].dtype == np.float32
+        assert np.array_equal(got["phase"], GOLD[key + "_phase"]), key           # stable_cumsum_and_wrap, bit for bit
+        assert np.array_equal(got["index"], GOLD[key + "_index"]), key           # floor(phase * n_period) as int32
+        ref = GOLD[key + "_audio"][:, :, 0]
+        assert np.abs(got["pulse"] - ref).max() <= 1e-6 * np.abs(ref).max(), key
+
+
+def test_oracle_subharmonic_channels_match_the_reference_source():
+    """add_subharm_chans = 2 (tf_wavetable.py:554-559) through generate_excitation: WaveNet input rows are the reference's
+    (B, T, 3) output folded by pulse_channels (custom_pulsed_generator.py:893)."""
+    plan, orc = _oracle("sp", 2)
+    key = "sp_s2_700"
+    f0 = GOLD[key + "_f0"]
+    T = 700 // plan.pulse_per_frame
+    mel = torch.as_tensor(np.stack([synthetic_mel(T, i) for i in range(3)]))
+    nz = torch.as_tensor(np.stack([synthetic_noise(T * plan.steps_per_frame, i) for i in range(3)])).reshape(3, -1, 1)
+    taps = {}
+    orc.generate_excitation(mel, torch.as_tensor(f0), nz, taps)
+    x = taps["wn_in"].numpy()[:, :, :-1].reshape(3, 700, 3)
+    ref = GOLD[key + "_audio"]
+    assert np.array_equal(taps["index"], GOLD[key + "_index"])
+    assert np.abs(x - ref).max() <= 2e-6
+
+
+def test_goldens_cover_chunk_boundaries_and_the_table_range():
+    """The vectors exercise what they are meant to pin: more than one cumsum chunk, a ragged last chunk, phase wraps, every
+    table of the bank selected by the sweep, and indices up to the last table row."""
+    idx = GOLD["vo_s0_2300_index"]
+    ph = GOLD["vo_s0_2300_phase"]
+    assert idx.min() == 0 and idx.max() == 511 and ph.min() >= 0 and ph.max() < 1
+    assert (np.diff(ph[1]) < 0).sum() > 100                                      # the sweep wraps many times
+    f0 = GOLD["vo_s0_2300_f0"][1]
+    assert f0.min() < 50 and f0.max() > 1350
