@@ -138,6 +138,29 @@ def test_cuda_pulse_generator_wide_range_matches_the_reference_source():
     inv.model.close()
 
 
+@pytest.mark.parametrize("tag", ["speech", "blocks_2x1"])
+def test_cuda_excitation_branch_matches_the_reference_source(tag):
+    """CUDA path vs tests/golden/reference_excitation.npz -- MBExWN.generate_excitation and the layer `call` methods under it,
+    executed unmodified from the reference's source over NumPy stand-ins for the TensorFlow primitives
+    (tests/golden/make_reference_excitation_goldens.py), no oracle in between: table index exact, WaveNet output, sub-band
+    signals and excitation within 1e-4 of their peak, for the fp32 and both fp32-accurate tensor-core paths."""
+    from mbexwn_vocoder_b200.engine import Engine
+    from test_reference_pulse import EXC, excitation_case
+    hp, plan, w = excitation_case(tag)
+    eng = Engine(plan, w, device=0)
+    mels, noise, f0 = list(EXC[f"{tag}_mel"]), list(EXC[f"{tag}_noise"]), list(EXC[f"{tag}_f0"])
+    for precision in ("fp32", "f16f8", "bf16x3"):
+        _, tp = eng.forward(mels, noise=noise, f0=f0, precision=precision, taps=["index", "wn_out", "subbands", "excitation"])
+        for u in range(2):
+            assert np.array_equal(tp["index"][u], EXC[f"{tag}_index"][u])
+            for name in ("wn_out", "subbands", "excitation"):
+                ref = EXC[f"{tag}_{name}"][u].reshape(-1)
+                e = _rel_err(tp[name][u].reshape(-1)[:ref.size], ref)
+                print(f"{tag} {precision} utt {u} {name}: max|err|/peak = {e:.3e}")
+                assert e <= STAGE_TOL, (precision, name, e)
+    eng.close()
+
+
 def test_cuda_matches_committed_goldens(engine, speech_setup):
     """CUDA path vs the fixture minted by tests/golden/make_oracle_goldens.py (no oracle run needed)."""
     import os

@@ -66,3 +66,38 @@ def test_goldens_cover_chunk_boundaries_and_the_table_range():
     assert (np.diff(ph[1]) < 0).sum() > 100                                      # the sweep wraps many times
     f0 = GOLD["vo_s0_2300_f0"][1]
     assert f0.min() < 50 and f0.max() > 1350
+
+
+# ---- the whole excitation branch (pulse -> WaveNet blocks -> post net -> PQMF synthesis) --------------------------------------
+EXC = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_excitation.npz"))
+EXC_CASES = {"speech": {}, "blocks_2x1": {"pulse_channels": 10, "pp_mod_subnet_upsampling_factors": [2, 1],
+                                          "pp_mod_subnet_channel_factors": [0.5, 0.25]}}
+
+
+def excitation_case(tag):
+    """(hparams, plan, weights) of a case of tests/golden/make_reference_excitation_goldens.py."""
+    hp = read_config(get_config_file("SPEECH"))
+    hp["mbexwn_config"].update(EXC_CASES[tag])
+    plan = build_plan(hp)
+    return hp, plan, W.init_synthetic(plan, seed=int(EXC[f"{tag}_seed"]))
+
+
+@pytest.mark.parametrize("tag", sorted(EXC_CASES))
+def test_oracle_excitation_branch_matches_the_reference_source(tag):
+    """tests/golden/reference_excitation.npz = MBExWN.generate_excitation, WaveNetAE(.Block).call, the weight-norm / sub-pixel conv
+    and LinInterp call methods, TFPQMF (constructor + synthesis) and the pulse generator, executed unmodified from /root/reference
+    over NumPy stand-ins for the TensorFlow primitives (single-block scheme model and a two-block stack with a x2 up-sampling conv).
+    The oracle must agree on the table index exactly and on the WaveNet output, the sub-band signals and the excitation to float32
+    rounding (different summation order inside the convolutions)."""
+    hp, plan, w = excitation_case(tag)
+    orc = OracleMBExWN(hp, w, torch.float32)
+    taps = {}
+    exc = orc.generate_excitation(torch.as_tensor(EXC[f"{tag}_mel"]), torch.as_tensor(EXC[f"{tag}_f0"]),
+                                  torch.as_tensor(EXC[f"{tag}_noise"]).reshape(2, -1, 1), taps).numpy()
+    assert np.array_equal(taps["index"], EXC[f"{tag}_index"])
+    for name, got in (("wn_out", taps["block_out_%d" % (len(plan.blocks) - 1)].numpy()), ("subbands", taps["subbands"].numpy()),
+                      ("excitation", exc[:, :EXC[f"{tag}_excitation"].shape[1]])):
+        ref = EXC[f"{tag}_{name}"]
+        assert got.shape == ref.shape, (name, got.shape, ref.shape)
+        err = np.abs(got - ref).max() / np.abs(ref).max()
+        assert err <= 1e-5, (tag, name, err)
