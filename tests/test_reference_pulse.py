@@ -101,3 +101,41 @@ def test_oracle_excitation_branch_matches_the_reference_source(tag):
         assert got.shape == ref.shape, (name, got.shape, ref.shape)
         err = np.abs(got - ref).max() / np.abs(ref).max()
         assert err <= 1e-5, (tag, name, err)
+
+
+# ---- the whole inference branch: mel in, waveform out ------------------------------------------------------------------------
+FWD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_forward.npz"))
+FWD_CASES = {"speech": {}, "speech_lifter": {"ps_env_order_scale": 2.0}}
+
+
+def forward_case(tag):
+    """(hparams, plan, weights) of a case of tests/golden/make_reference_forward_goldens.py."""
+    hp = read_config(get_config_file("SPEECH"))
+    hp["mbexwn_config"].update(FWD_CASES[tag])
+    plan = build_plan(hp)
+    return hp, plan, W.init_synthetic(plan, seed=int(FWD[f"{tag}_seed"]))
+
+
+@pytest.mark.parametrize("tag", sorted(FWD_CASES))
+def test_oracle_forward_matches_the_reference_source(tag):
+    """tests/golden/reference_forward.npz = MBExWN.call (inference branch) with generate_subnet_from_specs, generate_f0,
+    generate_excitation, generate_specenv, _get_cepstral_windows and every layer `call` under them executed unmodified from
+    /root/reference over NumPy stand-ins for the TensorFlow primitives (incl. tf.signal.stft / inverse_stft from their
+    documentation).  F0, table index, lifter index, excitation, |VTF| and the waveform of the oracle must agree."""
+    hp, plan, w = forward_case(tag)
+    orc = OracleMBExWN(hp, w, torch.float32)
+    r = orc.forward(FWD[f"{tag}_mel"], FWD[f"{tag}_noise"])
+    f0 = FWD[f"{tag}_F0"]
+    assert np.abs(r["F0"] - f0).max() <= 2e-5 * np.abs(f0).max()
+    # the index is a discontinuous function of F0: compare it on the reference's own F0
+    r = orc.forward(FWD[f"{tag}_mel"], FWD[f"{tag}_noise"], f0_override=f0)
+    assert np.array_equal(r["index"], FWD[f"{tag}_index"])
+    if FWD_CASES[tag].get("ps_env_order_scale"):
+        assert np.array_equal(r["lifter_index"], FWD[f"{tag}_lifter_index"])
+        assert len(np.unique(FWD[f"{tag}_lifter_index"])) > 3                   # the F0 contour selects several lifters
+    for name, key, tol in (("excitation", "excitation", 1e-5), ("vtf_mag", "vtf", 1e-4), ("waveform", "waveform", 2e-5)):
+        ref = FWD[f"{tag}_{name}"]
+        got = np.abs(r[key]) if name == "vtf_mag" else r[key]
+        got = got[:, :ref.shape[1]]
+        err = np.abs(got - ref).max() / np.abs(ref).max()
+        assert err <= tol, (tag, name, err)
