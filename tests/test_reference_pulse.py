@@ -139,3 +139,30 @@ def test_oracle_forward_matches_the_reference_source(tag):
         got = got[:, :ref.shape[1]]
         err = np.abs(got - ref).max() / np.abs(ref).max()
         assert err <= tol, (tag, name, err)
+
+
+# ---- NormMelComponents (row a3) ---------------------------------------------------------------------------------------------
+NORM = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_norm.npz"))
+NORM_CASES = {"default": {"normalize_rms_num_smooth_iters": 2},
+              "one_iter_wide": {"normalize_rms_num_smooth_iters": 1, "normalize_smooth_win_scale": 2,
+                                "normalize_smooth_with_squared_win": False, "max_norm_fact": 50.0, "normalize_compressor_exp": 0.8,
+                                "use_max_limit": True},
+              "pinv": {"normalize_rms_num_smooth_iters": 3, "normalize_use_pinv": True}}
+
+
+@pytest.mark.parametrize("tag", sorted(NORM_CASES))
+def test_oracle_norm_mel_matches_the_reference_source(tag):
+    """tests/golden/reference_norm.npz = the reference's NormMelComponents (real constructor + normalize_inputs_by_rms,
+    wavegen_1d.py:578-769) executed unmodified over NumPy stand-ins (tests/golden/make_reference_norm_goldens.py): the normalised
+    log-mel and the sample-rate gain of oracle/norm_mel.py must agree, also when synth_length exceeds the smoothed gain (:762-766)."""
+    from oracle.norm_mel import OracleNormMel
+    pc = read_config(get_config_file("SPEECH"))["preprocess_config"]
+    orc = OracleNormMel(pc, NORM_CASES[tag])
+    hop = pc["hop_size"]
+    T = NORM["mell"].shape[1]
+    for length, suffix in ((T * hop, ""), (T * hop + 170, "_long")):
+        mell, rms, _ = orc.normalize_inputs_by_rms(NORM["mell"], length)
+        ref_m, ref_r = NORM[f"{tag}{suffix}_mell"], NORM[f"{tag}{suffix}_rms"]
+        assert mell.shape == ref_m.shape and rms.shape == ref_r.shape
+        assert np.abs(mell - ref_m).max() <= 2e-5, (tag, suffix)                       # log domain: absolute
+        assert np.abs(rms - ref_r).max() <= 2e-6 * np.abs(ref_r).max(), (tag, suffix)
