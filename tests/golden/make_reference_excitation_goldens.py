@@ -259,7 +259,10 @@ def build_generator(ns, tf, plan, weights, tables_grid):
     pg.maxTranspositionFactorInGrid = tf.constant(np.max(grid) / nominal, tf.float32)
     pg.grid_f0_diff_norm_factor = 1. / tf.math.log(1.25)
 
-    gen = types.SimpleNamespace(pulse_generator=pg, pulse_pqmf=None, pulse_channels=plan.pulse_channels,
+    pulse_pqmf = None
+    if plan.pulse_pqmf_cfg is not None:                                                    # custom_pulsed_generator.py:499-501
+        pulse_pqmf = ns["TFPQMF"](**plan.pulse_pqmf_cfg, do_synthesis=False, name="PC_PQMFilterBank")
+    gen = types.SimpleNamespace(pulse_generator=pg, pulse_pqmf=pulse_pqmf, pulse_channels=plan.pulse_channels,
                                 pp_mod_subnet_noise_channel_sigma=plan.noise_sigma, pp_waveNetBlocks=blocks,
                                 wn_post_net=[conv(CW, plan.post_name)],
                                 pqmf=ns["TFPQMF"](**plan.pqmf_cfg, do_synthesis=True, name="PQMFilterBank"))   # real constructor

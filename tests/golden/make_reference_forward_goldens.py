@@ -98,6 +98,7 @@ def extend_tf(tf, weights):
     tf.round = lambda x: np.round(x)                           # half to even, like tf.round
     tf.assert_equal = lambda a, b, msg=None: None if np.all(a == b) else (_ for _ in ()).throw(AssertionError(msg))
     tf.stop_gradient = lambda x: x
+    tf.reduce_mean = lambda x, axis=None, keepdims=False: np.mean(x, axis=axis, keepdims=keepdims, dtype=F32)
     tf.ones = lambda shape, dtype=F32: np.ones(shape, dtype=dtype)
     tf.math.tanh = lambda x: np.tanh(x).astype(F32)
     tf.math.real = lambda x: np.real(x).astype(F32)
@@ -161,8 +162,8 @@ def load_forward(state, weights):
 
     ns["TF2C_Conv1DWeightNorm"], ns["TF2C_Conv1DUpDownSample"] = named(ns["TF2C_Conv1DWeightNorm"]), named(ns["TF2C_Conv1DUpDownSample"])
     methods = X._segments(os.path.join(model, "custom_pulsed_generator.py"),
-                          {"call", "generate_f0", "generate_specenv", "_get_cepstral_windows"}, "MBExWN")
-    assert len(methods) == 4
+                          {"call", "generate_f0", "generate_specenv", "_get_cepstral_windows", "generate_multiband_gain"}, "MBExWN")
+    assert len(methods) == 5
     for name, code in methods.items():
         local = dict(ns)
         exec(compile(code, f"custom_pulsed_generator.py:MBExWN.{name}", "exec"), local)
@@ -182,24 +183,28 @@ def build_model(ns, tf, hp, plan, weights, gen):
         mc["pp_subnet"], base_name="PulsPar", final_nks=1, final_n_channels=1,
         final_activation=mc.get("pp_activation", "soft_sigmoid"), target_ups=plan.pulse_per_frame,
         pad_to_valid=bool(mc.get("pp_subnet_use_valid_padding", False)), **common)
+    ps_use_stft = bool(mc.get("ps_use_stft", True))
     m.ps_subnet_layers, _ = ns["generate_subnet_from_specs"](                              # :412-426
-        mc["ps_subnet"], base_name="PS", final_nks=1, final_n_channels=plan.n_ceps, final_activation=None,
+        mc["ps_subnet"], base_name="PS", final_nks=1, final_n_channels=plan.n_ceps if ps_use_stft else plan.subbands,
+        final_activation=None,
         pad_to_valid=bool(mc.get("ps_subnet_use_valid_padding", False)), weight_init_scale=0.01, **common)
     m.pp_max_frequency, m.pp_min_frequency = plan.f0_max, plan.f0_min
     m.spect_to_pulse_upsampling_factor, m.spect_hop_size = plan.pulse_per_frame, plan.hop
     m.sample_rate, m.pulse_rate = plan.sample_rate, plan.pulse_rate
-    m.ps_use_stft, m.ps_off, m.dump_controls = True, False, False
+    m.ps_use_stft, m.ps_off, m.dump_controls = ps_use_stft, False, False
+    if not ps_use_stft:                                                                    # :452-453
+        m.ps_gain_interpolator = ns["LinInterpLayer"](upsampling_factor=plan.hop, num_pad_end=1)
     m.stft_win_size, m.fft_size, m.stft_win = plan.stft_win, plan.fft_size, tf.signal.hann_window
     m.ps_env_order_scale, m.psns_use_cepstral_loss_constraint = plan.env_order_scale, False
     if plan.env_order_scale:
         m.ps_cepstral_windows_log10f0, m.ps_cepstral_windows = np.asarray(plan.lifter_log10f0, F32), np.asarray(plan.lifters, F32)
     m.frequency_smoothing_kernel = np.asarray(plan.f0_smooth, F32)[:, None, None]          # :404-406
     m.log_to_log10 = 1 / np.log(10)                                                        # :503
-    m.spect_filters_preserve_energy, m.psns_gain_loss_weight = False, 0
+    m.spect_filters_preserve_energy, m.psns_gain_loss_weight = bool(mc.get("spect_filters_preserve_energy", False)), 0
     m.filter_max_log_range = plan.filter_max_log_range
     m.pulse_noise_floor_mag, m.stft_coh_loss_weight = None, 0
     m.pp_subnet_training_only, m.pp_teacher_forcing_schedule, m.pulse_rate_factor = False, None, plan.pulse_rate_factor
-    for name in ("generate_f0", "generate_specenv", "_get_cepstral_windows", "generate_excitation"):
+    for name in ("generate_f0", "generate_specenv", "_get_cepstral_windows", "generate_excitation", "generate_multiband_gain"):
         fn = ns.get("MBExWN_" + name) or ns[name]
         setattr(m, name, types.MethodType(fn, m))
     return m
@@ -217,7 +222,15 @@ def main():
     gold = np.load(os.path.join(HERE, "reference_init_dsp.npz"))
     out = {}
     # the scheme model, and the same with the F0-dependent cepstral lifter switched on (ps_env_order_scale, :434-450, :800-812)
-    for tag, model_id, seed, T, extra in (("speech", "SPEECH", 0, 21, {}), ("speech_lifter", "SPEECH", 1, 17, {"ps_env_order_scale": 2.0})):
+    pulse_pqmf = {"pulse_channels_use_pqmf": True,
+                  "pulse_channels_multi_band_config": {"subbands": 5, "taps": 40, "cutoff_ratio": 0.11, "beta": 8.0}}
+    cases = (("speech", "SPEECH", 0, 21, {}), ("speech_lifter", "SPEECH", 1, 17, {"ps_env_order_scale": 2.0}),
+             # variants of the path, short utterances
+             ("band_gain_centered", "SPEECH", 2, 9, {"ps_use_stft": False, "spect_filters_preserve_energy": True}),
+             ("causal", "SPEECH", 3, 9, {"force_causal": True}),
+             ("pulse_pqmf_subharm", "SPEECH", 4, 9,
+              dict(pulse_pqmf, wavetable_config={"nominalF0": 60, "maxF0": 550, "add_subharm_chans": 1})))
+    for tag, model_id, seed, T, extra in cases:
         hp = read_config(get_config_file(model_id))
         hp["mbexwn_config"].update(extra)
         plan = build_plan(hp)
@@ -235,7 +248,10 @@ def main():
         assert signal.shape == (2, T * plan.hop) and signal.dtype == np.float32, (signal.shape, signal.dtype)
         out[f"{tag}_seed"], out[f"{tag}_mel"], out[f"{tag}_noise"] = np.array(seed), mel, noise
         out[f"{tag}_F0"], out[f"{tag}_waveform"] = f0, signal
-        out[f"{tag}_excitation"], out[f"{tag}_vtf_mag"] = pp["PSig"], pp["PS"].astype(F32)
+        if "PSig" in pp:
+            out[f"{tag}_excitation"] = pp["PSig"]
+        if T > 10:                                             # the |VTF| tap only for the two main cases (size)
+            out[f"{tag}_vtf_mag"] = pp["PS"].astype(F32)
         out[f"{tag}_index"] = state["gather"][0][:, :, 0].astype(np.int32)
         if plan.env_order_scale:
             out[f"{tag}_lifter_index"] = state["gather"][1].astype(np.int32)
