@@ -111,6 +111,9 @@ def extend_tf(tf, weights):
     return tf
 
 
+SCOPE = [None]          # name of the WaveNetAE under construction (Keras name scope of its "start", "conv1D_<i>" ... sub-layers)
+
+
 def load_forward(state, weights):
     tf, ns = X.load_reference(state)
     extend_tf(tf, weights)
@@ -119,12 +122,16 @@ def load_forward(state, weights):
     class Layer(X.Layer):
         def __init__(self, *a, trainable=True, name=None, **k):
             self.trainable, self.name, self._built = trainable, name, False
+            if type(self).__name__ == "WaveNetAE":
+                SCOPE[0] = name
 
         def add_weight(self, name=None, shape=None, initializer=None, dtype=None, trainable=False):
             return initializer(shape, dtype or F32)
 
         def __call__(self, x, *a, **k):
-            if not getattr(self, "_built", True) and hasattr(self, "build_or_compute_output_shape"):
+            # leaf layers build on their first call, as in Keras; composite models (MBExWN, WaveNetAE ...) only pass the call on
+            if (not getattr(self, "_built", True) and hasattr(self, "build_or_compute_output_shape")
+                    and type(self).__name__ in ("TF2C_LinInterpLayer", "TFPad1d", "ActivationLayer")):
                 self.build_or_compute_output_shape(tuple(x.shape), do_build=True)
                 self._built = True
             return self.call(x, *a, **k)
@@ -151,9 +158,11 @@ def load_forward(state, weights):
                 assert use_weight_norm
                 self.use_equalized_lr, self.use_weight_norm, self.kernel_norm_axes = False, True, [0, 1]
                 self.pretrain_activations, self.activation = False, None
+                if f"{name}/v" not in weights:                 # a sub-layer of a WaveNetAE built by the reference's constructor
+                    name = f"{SCOPE[0]}/{name}"
                 self.v, self.g = np.asarray(weights[f"{name}/v"], F32), np.asarray(weights[f"{name}/g"], F32)
                 assert self.v.shape[0] == kernel_size and self.v.shape[2] == filters * (factor if up_sample else 1), name
-                self.conv1d_layer = X.KerasConv1D(weights[f"{name}/bias"], padding, 1)
+                self.conv1d_layer = X.KerasConv1D(weights[f"{name}/bias"], padding, kw.get("dilation_rate", 1))
                 self.up_sample, self.down_sample, self.factor = up_sample, False, factor
 
             def __call__(self, x):

@@ -196,6 +196,34 @@ def test_cuda_forward_matches_the_reference_source(tag):
     eng.close()
 
 
+@pytest.mark.parametrize("tag", ["speech", "blocks_2x1", "lifter_causal"])
+def test_cuda_matches_the_reference_model_object(tag):
+    """CUDA path vs tests/golden/reference_model.npz: the reference's MBExWN class, built by its own constructors from this
+    package's config.yaml and run through PaNWaveNet.infer over NumPy stand-ins for the TensorFlow primitives
+    (tests/golden/make_reference_model_goldens.py)."""
+    from mbexwn_vocoder_b200 import get_config_file, weights as W
+    from mbexwn_vocoder_b200.config import read_config
+    from mbexwn_vocoder_b200.engine import Engine
+    from mbexwn_vocoder_b200.plan import build_plan
+    from test_reference_pulse import MODEL_CASES, MODEL_GOLD
+    hp = read_config(get_config_file("SPEECH"))
+    hp["mbexwn_config"].update(MODEL_CASES[tag])
+    plan = build_plan(hp)
+    eng = Engine(plan, W.init_synthetic(plan, seed=int(MODEL_GOLD[f"{tag}_seed"])), device=0)
+    mels, noise, f0 = list(MODEL_GOLD[f"{tag}_mel"]), list(MODEL_GOLD[f"{tag}_noise"]), list(MODEL_GOLD[f"{tag}_F0"])
+    for precision in ("fp32", "f16f8"):
+        _, tp = eng.forward(mels, noise=noise, precision=precision, taps=["F0"])
+        out, tp2 = eng.forward(mels, noise=noise, f0=f0, precision=precision, taps=["index"])
+        for u in range(2):
+            assert _rel_err(tp["F0"][u], f0[u]) <= STAGE_TOL
+            assert np.array_equal(tp2["index"][u], MODEL_GOLD[f"{tag}_index"][u])
+            wav = MODEL_GOLD[f"{tag}_waveform"][u]
+            e, snr = _rel_err(out[u], wav), _snr_db(wav, out[u])
+            print(f"{tag} {precision} utt {u}: waveform max|err|/peak = {e:.3e}, SNR {snr:.1f} dB")
+            assert e <= STAGE_TOL and snr >= 60.0, (precision, e, snr)
+    eng.close()
+
+
 def test_cuda_matches_committed_goldens(engine, speech_setup):
     """CUDA path vs the fixture minted by tests/golden/make_oracle_goldens.py (no oracle run needed)."""
     import os

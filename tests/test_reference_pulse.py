@@ -172,3 +172,33 @@ def test_oracle_norm_mel_matches_the_reference_source(tag):
         assert mell.shape == ref_m.shape and rms.shape == ref_r.shape
         assert np.abs(mell - ref_m).max() <= 2e-5, (tag, suffix)                       # log domain: absolute
         assert np.abs(rms - ref_r).max() <= 2e-6 * np.abs(ref_r).max(), (tag, suffix)
+
+
+# ---- the reference's model object, built by its own constructors -------------------------------------------------------------
+MODEL_GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_model.npz"))
+MODEL_CASES = {"speech": {}, "blocks_2x1": EXC_CASES["blocks_2x1"], "lifter_causal": {"ps_env_order_scale": 1.5, "force_causal": True}}
+
+
+@pytest.mark.parametrize("tag", sorted(MODEL_CASES))
+def test_oracle_matches_the_reference_model_object(tag):
+    """tests/golden/reference_model.npz: `MBExWN(preprocess_config=..., **mbexwn_config)` -- the reference's class with its own
+    constructor (and those of WaveNetAEBlock / WaveNetAE / PulseWaveTable / TFPQMF), created from this package's config.yaml and
+    run through PaNWaveNet.infer, all compiled unmodified from /root/reference over NumPy stand-ins
+    (tests/golden/make_reference_model_goldens.py).  Pins what the other reference-source goldens leave to plan.py / dsp_init.py:
+    rate algebra, dilation schedule, conditioning factors, lifter bank, F0 smoothing kernel."""
+    hp = read_config(get_config_file("SPEECH"))
+    hp["mbexwn_config"].update(MODEL_CASES[tag])
+    plan = build_plan(hp)
+    w = W.init_synthetic(plan, seed=int(MODEL_GOLD[f"{tag}_seed"]))
+    orc = OracleMBExWN(hp, w, torch.float32)
+    mel, nz, f0 = MODEL_GOLD[f"{tag}_mel"], MODEL_GOLD[f"{tag}_noise"], MODEL_GOLD[f"{tag}_F0"]
+    r = orc.forward(mel, nz)
+    assert np.abs(r["F0"] - f0).max() <= 2e-5 * np.abs(f0).max()
+    r = orc.forward(mel, nz, f0_override=f0)
+    assert np.array_equal(r["index"], MODEL_GOLD[f"{tag}_index"])
+    wav = MODEL_GOLD[f"{tag}_waveform"]
+    assert r["waveform"].shape == wav.shape
+    assert np.abs(r["waveform"] - wav).max() <= 2e-5 * np.abs(wav).max(), tag
+    if plan.env_order_scale:                                                    # the lifter bank of the reference's constructor
+        assert np.array_equal(plan.lifters, MODEL_GOLD[f"{tag}_lifters"])
+        assert np.array_equal(plan.lifter_log10f0, MODEL_GOLD[f"{tag}_lifter_grid"])
