@@ -20,7 +20,7 @@ What *is* pinned against real reference code executed in the build container:
 * init-time DSP (tests/golden/make_reference_goldens.py -> reference_init_dsp.npz): the LF glottal-pulse
   model, the wavetable bank and the PQMF prototype, bit for bit.  Those constants come from
   ``mbexwn_vocoder_b200.dsp_init`` (the oracle imports the product for them, never the other way round).
-* the forward's *algorithm as the reference wrote it*: tests/golden/make_reference_{pulse,excitation,forward}_goldens.py compile
+* the forward's *algorithm as the reference wrote it*: tests/golden/make_reference_{pulse,excitation,forward,model,norm}_goldens.py compile
   the reference's own source unmodified -- ``MBExWN.call`` (inference branch), ``generate_subnet_from_specs``, ``generate_f0``,
   ``generate_excitation``, ``generate_specenv``, ``_get_cepstral_windows``, ``PulseWaveTable.call`` / ``stable_cumsum_and_wrap`` /
   ``_linear_lookup``, ``WaveNetAE(.Block).call``, the ``call`` methods of the weight-norm / sub-pixel conv, LinInterp, pad and
@@ -28,8 +28,9 @@ What *is* pinned against real reference code executed in the build container:
   gather, pad, rfft, tf.signal.stft / inverse_stft from their documentation ...).  tests/test_reference_pulse.py holds this
   oracle to those vectors: wrapped phase, table index and lifter index bit for bit; F0, WaveNet output, sub-bands, excitation,
   |VTF| and waveform to 1e-5 .. 1e-4 of peak.  What remains assumed is TensorFlow's arithmetic *inside* a primitive (summation
-  order of a convolution, sequential float32 cumsum, SAME-padding split) -- SURVEY.md A.1 -- plus ``NormMelComponents`` and the
-  constructor logic of the Keras layers, which stay anchored on closed-form properties (tests/test_oracle.py, tests/test_norm_mel.py).
+  order of a convolution, sequential float32 cumsum, SAME-padding split) -- SURVEY.md A.1.  ``make_reference_model_goldens.py``
+  goes furthest: the reference's ``MBExWN`` object is created by its own constructors from this package's config.yaml and run
+  through ``PaNWaveNet.infer``.
 """
 from __future__ import annotations
 
