@@ -25,7 +25,7 @@ What *is* pinned against real reference code executed in the build container:
   ``generate_excitation``, ``generate_specenv``, ``_get_cepstral_windows``, ``PulseWaveTable.call`` / ``stable_cumsum_and_wrap`` /
   ``_linear_lookup``, ``WaveNetAE(.Block).call``, the ``call`` methods of the weight-norm / sub-pixel conv, LinInterp, pad and
   activation layers, ``TFPQMF`` -- and execute it over NumPy float32 stand-ins for the TensorFlow *primitives* (conv1d, cumsum,
-  gather, pad, rfft, tf.signal.stft / inverse_stft from their documentation ...).  tests/test_reference_pulse.py holds this
+  gather, pad, rfft, tf.signal.stft / inverse_stft from their documentation ...).  tests/test_reference_source.py holds this
   oracle to those vectors: wrapped phase, table index and lifter index bit for bit; F0, WaveNet output, sub-bands, excitation,
   |VTF| and waveform to 1e-5 .. 1e-4 of peak.  What remains assumed is TensorFlow's arithmetic *inside* a primitive (summation
   order of a convolution, sequential float32 cumsum, SAME-padding split) -- SURVEY.md A.1.  ``make_reference_model_goldens.py``

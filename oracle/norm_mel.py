@@ -5,7 +5,7 @@ is estimated per frame from the log-mel, smoothed by overlap-adding (squared) Ha
 divided by the smoothed frame RMS before the generator and the generated signal is multiplied by the sample-rate RMS
 afterwards.  NumPy float32, op by op like the TensorFlow code.  Unpinned against a TensorFlow run (TensorFlow absent); pinned
 on the reference's own source executed over NumPy stand-ins for the TensorFlow primitives
-(tests/golden/make_reference_norm_goldens.py -> tests/test_reference_pulse.py) and anchored on closed forms in tests/test_norm_mel.py.
+(tests/golden/make_reference_norm_goldens.py -> tests/test_reference_source.py) and anchored on closed forms in tests/test_norm_mel.py.
 """
 from __future__ import annotations
 

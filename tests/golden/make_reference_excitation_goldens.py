@@ -27,7 +27,7 @@ residual / skip split order and the last layer's skip-only case, `end` applied t
 synthesis.  What it cannot pin is TensorFlow's arithmetic inside a primitive (summation order of a convolution): float outputs
 are compared with a tolerance.
 
-Output: tests/golden/reference_excitation.npz (committed); tests/test_reference_pulse.py checks the oracle against it,
+Output: tests/golden/reference_excitation.npz (committed); tests/test_reference_source.py checks the oracle against it,
 tests/test_gpu_parity.py the CUDA path.
 """
 import ast

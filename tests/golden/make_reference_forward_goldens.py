@@ -19,7 +19,7 @@ overlap-add), ``tf.signal.inverse_stft_window_fn`` (forward window / sum of its 
 ``tf.signal.rfft``, ``tf.complex`` / ``exp`` / ``real`` / ``imag`` / ``tanh``, ``tf.round`` (half to even), ``tf.pad`` with modes.
 The lifter bank and the F0 smoothing kernel (numpy inside MBExWN.__init__, :404-450) come from mbexwn_vocoder_b200.dsp_init.
 
-Output: tests/golden/reference_forward.npz (committed); tests/test_reference_pulse.py checks the oracle against it,
+Output: tests/golden/reference_forward.npz (committed); tests/test_reference_source.py checks the oracle against it,
 tests/test_gpu_parity.py the CUDA path.
 """
 import os

@@ -11,7 +11,7 @@ reference's own keyword arguments).  Stand-ins: the TensorFlow primitives (NumPy
 ``Layer`` (name, lazy build, add_weight), Keras' PReLU, and the constructor of the two weight-normalised conv classes, which fetches
 ``v`` / ``g`` / ``bias`` by layer name instead of creating variables (their ``call`` is the reference's).
 
-Output: tests/golden/reference_model.npz (committed); tests/test_reference_pulse.py checks the oracle against it.
+Output: tests/golden/reference_model.npz (committed); tests/test_reference_source.py checks the oracle against it.
 """
 import os
 import sys

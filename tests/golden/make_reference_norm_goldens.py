@@ -9,7 +9,7 @@ TensorFlow).  librosa is absent: ``librosa_mel_frequencies`` / ``get_mel_filter`
 Slaney mel scale restated from its published definition) -- the band centres and the mel basis are therefore NOT pinned here, the
 normaliser's algorithm (frame padding, Hann^2 overlap-add offsets, gain normalisation, smoothing iterations, re-scaling) is.
 
-Output: tests/golden/reference_norm.npz (committed); tests/test_reference_pulse.py checks oracle/norm_mel.py against it.
+Output: tests/golden/reference_norm.npz (committed); tests/test_reference_source.py checks oracle/norm_mel.py against it.
 """
 import os
 import sys

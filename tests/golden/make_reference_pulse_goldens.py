@@ -19,7 +19,7 @@ is TensorFlow's own arithmetic inside a primitive; the stand-ins state the assum
 
 The wavetable bank fed to the methods is the one ``reference_init_dsp.npz`` already pins to the reference's own construction code.
 
-Output: tests/golden/reference_pulse.npz (committed); tests/test_reference_pulse.py checks the oracle against it on any machine,
+Output: tests/golden/reference_pulse.npz (committed); tests/test_reference_source.py checks the oracle against it on any machine,
 tests/test_gpu_parity.py the CUDA kernels (index and phase bit-exact).
 """
 import ast

@@ -145,7 +145,7 @@ def test_cuda_excitation_branch_matches_the_reference_source(tag):
     (tests/golden/make_reference_excitation_goldens.py), no oracle in between: table index exact, WaveNet output, sub-band
     signals and excitation within 1e-4 of their peak, for the fp32 and both fp32-accurate tensor-core paths."""
     from mbexwn_vocoder_b200.engine import Engine
-    from test_reference_pulse import EXC, excitation_case
+    from test_reference_source import EXC, excitation_case
     hp, plan, w = excitation_case(tag)
     eng = Engine(plan, w, device=0)
     mels, noise, f0 = list(EXC[f"{tag}_mel"]), list(EXC[f"{tag}_noise"]), list(EXC[f"{tag}_f0"])
@@ -170,7 +170,7 @@ def test_cuda_forward_matches_the_reference_source(tag):
     tags are variants of the path (per-band gain instead of the STFT filter, force_causal, PQMF analysis of the pulse train with a
     sub-harmonic channel)."""
     from mbexwn_vocoder_b200.engine import Engine
-    from test_reference_pulse import FWD, FWD_CASES, forward_case
+    from test_reference_source import FWD, FWD_CASES, forward_case
     hp, plan, w = forward_case(tag)
     eng = Engine(plan, w, device=0)
     mels, noise, f0 = list(FWD[f"{tag}_mel"]), list(FWD[f"{tag}_noise"]), list(FWD[f"{tag}_F0"])
@@ -205,7 +205,7 @@ def test_cuda_matches_the_reference_model_object(tag):
     from mbexwn_vocoder_b200.config import read_config
     from mbexwn_vocoder_b200.engine import Engine
     from mbexwn_vocoder_b200.plan import build_plan
-    from test_reference_pulse import MODEL_CASES, MODEL_GOLD
+    from test_reference_source import MODEL_CASES, MODEL_GOLD
     hp = read_config(get_config_file("SPEECH"))
     hp["mbexwn_config"].update(MODEL_CASES[tag])
     plan = build_plan(hp)

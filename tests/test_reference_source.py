@@ -1,7 +1,8 @@
-"""The pulse generator of the oracle against goldens produced by the REAL reference source: tests/golden/reference_pulse.npz holds
-what ``PulseWaveTable.call`` / ``stable_cumsum_and_wrap`` / ``_linear_lookup`` (tf_wavetable.py:429-638), executed unmodified from
-/root/reference over NumPy stand-ins for the TensorFlow primitives (tests/golden/make_reference_pulse_goldens.py), return for
-constant, swept and random-walk F0 contours.  Wrapped phase and table index must match bit for bit, the float outputs to 1e-6."""
+"""The oracle and the host logic against goldens produced by the REAL reference source.  tests/golden/reference_*.npz hold what the
+reference's own code -- compiled unmodified from /root/reference by tests/golden/make_reference_*_goldens.py and executed over NumPy
+stand-ins for the TensorFlow primitives -- returns for the pulse generator, the excitation branch, the whole inference branch, the
+model object built by its own constructors, NormMelComponents and MELInverter.scale_mel.  Integer indices and the wrapped phase must
+match bit for bit, float outputs to float32 rounding.  The CUDA path is held to the same files in tests/test_gpu_parity.py."""
 import os
 
 import numpy as np
@@ -202,3 +203,26 @@ def test_oracle_matches_the_reference_model_object(tag):
     if plan.env_order_scale:                                                    # the lifter bank of the reference's constructor
         assert np.array_equal(plan.lifters, MODEL_GOLD[f"{tag}_lifters"])
         assert np.array_equal(plan.lifter_log10f0, MODEL_GOLD[f"{tag}_lifter_grid"])
+
+
+# ---- MELInverter.scale_mel (host side of the boundary) ----------------------------------------------------------------------
+def test_scale_mel_matches_the_real_reference():
+    """tests/golden/reference_scale_mel.npz = the reference's own MELInverter.scale_mel (mel_inverter.py:48-148, plain NumPy)
+    called from /root/reference on the same inputs (tests/golden/make_reference_scale_mel_goldens.py): bit-identical."""
+    import importlib.util
+    from mbexwn_vocoder_b200.mel_inverter import MELInverter
+    spec = importlib.util.spec_from_file_location(
+        "make_scale_mel", os.path.join(os.path.dirname(__file__), "golden", "make_reference_scale_mel_goldens.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_scale_mel.npz"))
+    for tag, (cfg, model_extra) in gen.cases().items():
+        inv = MELInverter(None)
+        m = dict(gen.MODEL, **model_extra)
+        inv.hop_size, inv._srate, inv.fft_size, inv.fmin, inv.fmax, inv.mel_channels = (
+            m["hop_size"], m["srate"], m["fft_size"], m["fmin"], m["fmax"], m["mel_channels"])
+        inv.lin_amp_scale, inv.lin_amp_off, inv.mel_amp_scale, inv.use_max_limit = (
+            m["lin_amp_scale"], m["lin_amp_off"], m["mel_amp_scale"], m["use_max_limit"])
+        got = inv.scale_mel({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in cfg.items()})
+        assert got.dtype == np.float32 and got.shape == gold[tag].shape, tag
+        assert np.array_equal(got, gold[tag]), tag
