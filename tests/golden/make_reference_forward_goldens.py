@@ -85,6 +85,7 @@ def extend_tf(tf, weights):
     class PReLU(X.Layer):                                      # tf.keras.layers.PReLU(shared_axes=[1]): one slope per channel
         def __init__(self, alpha_initializer=None, shared_axes=None, name=None, **kw):
             assert list(shared_axes) == [1]
+            self.weight_key = name
             self.alpha = np.asarray(weights[f"{name}/alpha"], F32)
 
         def call(self, x):
@@ -160,6 +161,7 @@ def load_forward(state, weights):
                 self.pretrain_activations, self.activation = False, None
                 if f"{name}/v" not in weights:                 # a sub-layer of a WaveNetAE built by the reference's constructor
                     name = f"{SCOPE[0]}/{name}"
+                self.weight_key = name
                 self.v, self.g = np.asarray(weights[f"{name}/v"], F32), np.asarray(weights[f"{name}/g"], F32)
                 assert self.v.shape[0] == kernel_size and self.v.shape[2] == filters * (factor if up_sample else 1), name
                 self.conv1d_layer = X.KerasConv1D(weights[f"{name}/bias"], padding, kw.get("dilation_rate", 1))

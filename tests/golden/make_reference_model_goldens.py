@@ -98,6 +98,20 @@ def main():
             wn = blk.wavenet
             assert (wn.n_channels, wn.cond_conv_upsampling, wn.cond_lin_upsampling) == (spec.c, spec.cond_conv_up, spec.cond_lin_up)
             assert [l.conv1d_layer.dilation for l in wn.conv_layers] == spec.dilations
+        # attribute tree of the reference object = the object-graph paths of a Keras checkpoint of it (tf_checkpoint.py writes /
+        # reads those paths): position, kind and name of every member of the two sub-net layer lists
+        table = []
+        for attr in ("pp_subnet_layers", "ps_subnet_layers"):
+            for i, layer in enumerate(getattr(model, attr)):
+                kind = "conv" if hasattr(layer, "v") else "prelu" if hasattr(layer, "alpha") else type(layer).__name__
+                key = getattr(layer, "weight_key", None) or getattr(layer, "name", "")
+                table.append(f"{attr}/{i}|{kind}|{key}")
+        for ib, blk in enumerate(model.pp_waveNetBlocks):
+            for attr in ("start", "end", "cond_layer", "conv_layers", "res_skip_layers"):
+                assert hasattr(blk.wavenet, attr), attr
+            table.append(f"pp_waveNetBlocks/{ib}|block|{'up_down_sample' if blk.up_down_sample is not None else ''}")
+        assert len(model.wn_post_net) == 1
+        out[f"{tag}_layer_table"] = np.array(table)
         shell = types.SimpleNamespace(segment_length=0, spect_hop_size=plan.hop, norm_mel_components=None, block=model)
         mel = np.stack([synthetic_mel(T, 80 + i) for i in range(2)]).astype(F32)
         noise = np.stack([synthetic_noise(T * plan.steps_per_frame, 80 + i) for i in range(2)]).astype(F32)

@@ -226,3 +226,42 @@ def test_scale_mel_matches_the_real_reference():
         got = inv.scale_mel({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in cfg.items()})
         assert got.dtype == np.float32 and got.shape == gold[tag].shape, tag
         assert np.array_equal(got, gold[tag]), tag
+
+
+@pytest.mark.parametrize("tag", sorted(MODEL_CASES))
+def test_checkpoint_paths_follow_the_reference_object_tree(tag, tmp_path):
+    """A Keras checkpoint names a variable by the attribute path that leads to it.  reference_model.npz holds, for the reference's
+    MBExWN object built by its own constructor, the position / kind / layer name of every member of pp_subnet_layers and
+    ps_subnet_layers (pad, conv, PReLU and interpolation layers interleave) and the up_down_sample attribute of the WaveNet blocks.
+    The checkpoint tf_checkpoint.export_weights writes must put each conv / PReLU variable at exactly that path, so that the
+    unmodified reference can load_weights() it -- and import_weights must read a reference checkpoint the same way."""
+    from mbexwn_vocoder_b200 import tf_checkpoint as T
+    hp = read_config(get_config_file("SPEECH"))
+    hp["mbexwn_config"].update(MODEL_CASES[tag])
+    plan = build_plan(hp, finalize=False)
+    w = W.init_synthetic(plan, seed=int(MODEL_GOLD[f"{tag}_seed"]))
+    prefix = str(tmp_path / "weights.tf")
+    T.export_weights(prefix, hp, w)
+    rd = T.BundleReader(prefix)
+    keys = set(rd.keys())
+    suffix = "/.ATTRIBUTES/VARIABLE_VALUE"
+    n_conv = n_act = 0
+    for row in MODEL_GOLD[f"{tag}_layer_table"]:
+        path, kind, name = str(row).split("|")
+        if kind == "conv":
+            for part, leaf in (("v", "v"), ("g", "g"), ("bias", "conv1d_layer/bias")):
+                key = f"block/{path}/{leaf}{suffix}"
+                assert key in keys, key
+                assert np.array_equal(np.asarray(rd.get(key)).reshape(w[f"{name}/{part}"].shape), w[f"{name}/{part}"]), key
+            n_conv += 1
+        elif kind == "prelu":
+            key = f"block/{path}/alpha{suffix}"
+            assert key in keys, key
+            assert np.array_equal(np.asarray(rd.get(key)).reshape(-1), w[f"{name}/alpha"]), key
+            n_act += 1
+        elif kind == "block":
+            has_up = f"block/{path}/up_down_sample/v{suffix}" in keys
+            assert has_up == (name == "up_down_sample"), path
+            assert f"block/{path}/wavenet/cond_layer/v{suffix}" in keys and f"block/{path}/wavenet/res_skip_layers/0/g{suffix}" in keys
+    assert n_conv == sum(op.kind == "conv" for ops in (plan.pp_ops, plan.ps_ops) for op in ops) and n_act > 0
+    assert f"block/wn_post_net/0/v{suffix}" in keys
