@@ -157,8 +157,6 @@ static Workspace carve(const mbexwn_handle_s& hd, int64_t F, int64_t n_chunks, i
             // input with the row pitch of wn_out
             if (hd.blocks[ib].up > 1)
                 need("blk_in", (size_t)brows * hd.blocks[ib].up * (ib + 1 < hd.blocks.size() ? c.wn_cout : out_pad) * f4);
-            else if (ib + 1 < hd.blocks.size())
-                need("blk_in", (size_t)brows * c.wn_cout * f4);
         }
         for (auto& e : wn) w.add(e.first, e.second);
     }
@@ -388,7 +386,7 @@ static mbexwn_op_t simple_conv(int k, int cin, int cout, int dil, int pad_l) {
     return op;
 }
 
-static int wavenet_fp32(Ctx& cx, const mbexwn_config_t& c, const float* wn_in) {
+static int wavenet_fp32(Ctx& cx, const mbexwn_config_t& c, const float* wn_in, int ld_in) {
     mbexwn_handle_t h = cx.h;
     const long long rows = (long long)cx.g.n_frames * c.steps_per_frame;
     const std::string n = c.wn_name;
@@ -400,7 +398,9 @@ static int wavenet_fp32(Ctx& cx, const mbexwn_config_t& c, const float* wn_in) {
         const float* w = tensor(h, n + "/start/W", (size_t)c.wn_cin * c.wn_c * 4, &rc); if (!w) return rc;
         const float* b = tensor(h, n + "/start/b", (size_t)c.wn_c * 4, &rc); if (!b) return rc;
         mbexwn_op_t op = simple_conv(1, c.wn_cin, c.wn_c, 1, 0);
-        MBX_CUDA_CHECK(launch_conv1d(conv_args(c, op, c.steps_per_frame, rows, wn_in, w, b, nullptr, hbuf), cx.g, cx.s));
+        ConvArgs sa = conv_args(c, op, c.steps_per_frame, rows, wn_in, w, b, nullptr, hbuf);
+        sa.ld_x = ld_in;
+        MBX_CUDA_CHECK(launch_conv1d(sa, cx.g, cx.s));
         h->launches++;
     }
     for (int i = 0; i < c.wn_layers; ++i) {
@@ -536,10 +536,14 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
         const mbexwn_config_t& bc = blk.cfg;
         const bool last_block = ib + 1 == h->blocks.size();
         const long long brows = (long long)b->n_frames * bc.steps_per_frame;
-        const float* wn_in = ib == 0 ? cx.p<float>("wn_in") : cx.p<float>("blk_in");
+        // block 0 reads the excitation head's rows; a later block reads what the previous one left: its up-sampling conv's output
+        // (blk_in, wn_cout floats per row) or, without up-sampling, the previous WaveNet output in place (row pitch out_pad)
+        const bool prev_up = ib > 0 && h->blocks[ib - 1].up > 1;
+        const float* wn_in = ib == 0 ? cx.p<float>("wn_in") : (prev_up ? cx.p<float>("blk_in") : cx.p<float>("wn_out"));
+        const int ld_in = ib == 0 ? bc.wn_cin : (prev_up ? bc.wn_cin : out_pad);
         if (ib > 0 && (rc = run_cond(bc))) return rc;         // every block has its own conditioning conv
         if (precision == MBEXWN_PREC_FP32_SIMT) {
-            rc = wavenet_fp32(cx, bc, wn_in);
+            rc = wavenet_fp32(cx, bc, wn_in, ld_in);
             if (rc) return rc;
             // `end` 1x1 over the skip sum (custom_AE_layers.py:340); the tensor-core path folds it into the res_skip matrices
             const std::string n = std::string(bc.wn_name) + "/end";
@@ -553,7 +557,7 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
             MBX_CUDA_CHECK(launch_conv1d(a, cx.g, s));
             h->launches++;
         } else {
-            rc = wn_tc_forward(h->tc, bc, cx.g, precision, wn_in, cx.p<float>("cond"), cx.p<float>("wn_out"),
+            rc = wn_tc_forward(h->tc, bc, cx.g, precision, wn_in, ld_in, cx.p<float>("cond"), cx.p<float>("wn_out"),
                                [&](const char* nm) { return (void*)cx.p<char>(nm); },
                                [&](const std::string& nm, size_t bytes) { int r = 0; return (const void*)tensor(h, nm, bytes, &r); },
                                s, &h->launches, &h->error);
@@ -575,10 +579,6 @@ static int forward_impl(mbexwn_handle_t h, const mbexwn_batch_t* b, int precisio
             MBX_CUDA_CHECK(launch_conv1d(a, cx.g, s));
             h->launches++;
             if (last_block) post_in = cx.p<float>("blk_in");
-        } else if (!last_block) {
-            // the next block reads rows of wn_cout contiguous channels
-            MBX_CUDA_CHECK(cudaMemcpy2DAsync(cx.p<float>("blk_in"), (size_t)bc.wn_cout * 4, cx.p<float>("wn_out"), (size_t)out_pad * 4,
-                                             (size_t)bc.wn_cout * 4, (size_t)brows, cudaMemcpyDeviceToDevice, s));
         }
     }
     mark();

@@ -1359,7 +1359,7 @@ constexpr int START_WIDE_CIN = 40;                     // START_ROWS x cin float
 constexpr int START_LANES = 8;                          // rows in flight per block pass
 template <int CIN_MAX>
 __global__ void __launch_bounds__(START_LANES * 48, (CIN_MAX > 0 && CIN_MAX <= 8) ? 2 : 1)
-start_pack_kernel(const float* __restrict__ x, int cin, const float* __restrict__ w, const float* __restrict__ b,
+start_pack_kernel(const float* __restrict__ x, int ld_x, int cin, const float* __restrict__ w, const float* __restrict__ b,
                   __nv_bfloat16* __restrict__ out, long long rows, int c, int cpad, int rate, FrameGrid g,
                   int f16f8, float lo_scale) {
     extern __shared__ float sx[];                       // [START_ROWS][cin] inputs, zero for guard rows
@@ -1385,7 +1385,7 @@ start_pack_kernel(const float* __restrict__ x, int cin, const float* __restrict_
     __syncthreads();
     for (int i = threadIdx.x; i < START_ROWS * cin; i += blockDim.x) {
         const int rl = i / cin;
-        sx[i] = svalid[rl] ? x[(r0 + rl) * cin + (i - rl * cin)] : 0.f;
+        sx[i] = svalid[rl] ? x[(r0 + rl) * ld_x + (i - rl * cin)] : 0.f;
     }
     __syncthreads();
     if (!active) return;
@@ -1600,7 +1600,7 @@ void wn_tc_carve(const mbexwn_config_t& c, long long rows, int precision, const 
 
 int wn_tc_out_pad(const mbexwn_config_t& c) { return round_up(c.wn_cout, 32); }
 
-int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, int precision, const float* wn_in,
+int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, int precision, const float* wn_in, int ld_in,
                   const float* cond, float* wn_out, const std::function<void*(const char*)>& slot,
                   const std::function<const void*(const std::string&, size_t)>& tensor, cudaStream_t s, int* launches,
                   std::string* error) {
@@ -1633,13 +1633,13 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         const size_t smem = (size_t)START_ROWS * c.wn_cin * sizeof(float);
         const unsigned nblk = (unsigned)((rows + START_ROWS - 1) / START_ROWS), nthr = (unsigned)(START_LANES * (cpad >> 3));
         if (c.wn_cin <= 8)
-            start_pack_kernel<8><<<nblk, nthr, smem, s>>>(wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g,
+            start_pack_kernel<8><<<nblk, nthr, smem, s>>>(wn_in, ld_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g,
                                                           f8 ? 1 : 0, h_lo);
         else if (c.wn_cin <= START_MAX_CIN)
-            start_pack_kernel<16><<<nblk, nthr, smem, s>>>(wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g,
+            start_pack_kernel<16><<<nblk, nthr, smem, s>>>(wn_in, ld_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g,
                                                            f8 ? 1 : 0, h_lo);
         else
-            start_pack_kernel<0><<<nblk, nthr, smem, s>>>(wn_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g,
+            start_pack_kernel<0><<<nblk, nthr, smem, s>>>(wn_in, ld_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g,
                                                           f8 ? 1 : 0, h_lo);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(std::string("start conv: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);

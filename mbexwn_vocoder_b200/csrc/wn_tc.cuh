@@ -33,7 +33,9 @@ int wn_tc_out_pad(const mbexwn_config_t& c);
 
 // Runs start conv + all WaveNet layers; leaves end(skip sum) = the WaveNet output (rows, wn_tc_out_pad) fp32 in
 // `wn_out` (the linear `end` 1x1 is folded into the skip half of every res_skip matrix at pack time).
-int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, int precision, const float* wn_in,
+// `wn_in` rows hold wn_cin channels with a pitch of `ld_in` floats (a later block of a stack reads the previous block's
+// output in place, whose pitch is wn_tc_out_pad).
+int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, int precision, const float* wn_in, int ld_in,
                   const float* cond, float* wn_out, const std::function<void*(const char*)>& slot,
                   const std::function<const void*(const std::string&, size_t)>& tensor, cudaStream_t s, int* launches,
                   std::string* error);

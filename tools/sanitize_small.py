@@ -16,10 +16,14 @@ def multi_block_variants():
     import tempfile
     import yaml
     from mbexwn_vocoder_b200 import get_config_file
-    for name, ups, fac in (("blocks_2x1", [2, 1], [0.5, 0.25]), ("blocks_1x2", [1, 2], [0.25, 0.5])):
+    variants = {"blocks_2x1": {"pulse_channels": 10, "pp_mod_subnet_upsampling_factors": [2, 1],
+                               "pp_mod_subnet_channel_factors": [0.5, 0.25]},
+                "blocks_1x2": {"pulse_channels": 10, "pp_mod_subnet_upsampling_factors": [1, 2],
+                               "pp_mod_subnet_channel_factors": [0.25, 0.5]},
+                "lifter_causal": {"ps_env_order_scale": 1.5, "force_causal": True}}       # F0-dependent cepstral lifter
+    for name, extra in variants.items():
         cfg = yaml.safe_load(open(get_config_file("SPEECH")))
-        cfg["mbexwn_config"].update({"pulse_channels": 10, "pp_mod_subnet_upsampling_factors": ups,
-                                     "pp_mod_subnet_channel_factors": fac})
+        cfg["mbexwn_config"].update(extra)
         d = tempfile.mkdtemp(prefix=name)
         yaml.safe_dump(cfg, open(os.path.join(d, "config.yaml"), "w"))
         mb = MELInverter(d, device=0, precision="f16f8")
