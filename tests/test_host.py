@@ -85,7 +85,6 @@ def test_subnet_grammar_matches_reference_layer_list():
 
 
 def test_plan_config_errors(speech_setup):
-    import copy
     hp, _, _ = speech_setup
     bad = copy.deepcopy(hp)
     bad["mbexwn_config"]["pulse_channels"] = 4              # 8000/4*15 != 24000 (custom_pulsed_generator.py:344)
@@ -312,3 +311,34 @@ def test_long_form_context_covers_the_receptive_field(speech_setup):
     assert ctx * wn.steps_per_frame >= sum(d * (wn.k - 1) // 2 for d in wn.dilations) + plan.pqmf_q
     assert ctx >= subnet_reach_frames(plan.ps_ops) and ctx * plan.hop >= plan.stft_win
     assert subnet_reach_frames(plan.pp_ops) >= 2
+
+
+def test_create_validates_the_wavenet_block_table():
+    """mbexwn_create checks a multi-block description before it touches CUDA: block count, per-block fields, the rate chain
+    steps_per_frame x prod(up) = hop / subbands and block rate = cond_conv_up x cond_lin_up (custom_pulsed_generator.py:344, :469)."""
+    from mbexwn_vocoder_b200 import get_config_file
+    from mbexwn_vocoder_b200.config import read_config
+    from mbexwn_vocoder_b200.engine import make_config
+    from mbexwn_vocoder_b200.plan import build_plan
+    hp = read_config(get_config_file("SPEECH"))
+    hp["mbexwn_config"].update({"pulse_channels": 10, "pp_mod_subnet_upsampling_factors": [2, 1],
+                                "pp_mod_subnet_channel_factors": [0.5, 0.25]})
+    plan = build_plan(hp)
+    lib = _cabi.load()
+
+    def create(mutate):
+        cfg = make_config(plan)
+        mutate(cfg)
+        h = ctypes.c_void_p()
+        rc = lib.mbexwn_create(ctypes.byref(cfg), ctypes.byref(h))
+        if rc == _cabi.OK:
+            lib.mbexwn_destroy(h)
+        return rc
+
+    assert create(lambda c: None) in (_cabi.OK, _cabi.ERR_CUDA)            # valid: OK on a GPU box, ERR_CUDA without a device
+    assert create(lambda c: setattr(c, "wn_n_blocks", _cabi.MAX_BLOCKS + 1)) == _cabi.ERR_INVALID
+    assert create(lambda c: setattr(c.wn_blocks[0], "up", 3)) == _cabi.ERR_INVALID           # 10 x 3 x 15 != 300
+    assert create(lambda c: setattr(c.wn_blocks[1], "cond_conv_up", 1)) == _cabi.ERR_INVALID  # 20 rows per frame != 1 x 10
+    assert create(lambda c: setattr(c.wn_blocks[0], "c", 0)) == _cabi.ERR_INVALID
+    assert create(lambda c: setattr(c.wn_blocks[0], "up_name", b"")) == _cabi.ERR_INVALID    # up = 2 needs its conv
+    assert create(lambda c: setattr(c, "abi_version", _cabi.ABI_VERSION - 1)) == _cabi.ERR_INVALID
