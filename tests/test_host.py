@@ -85,6 +85,7 @@ def test_subnet_grammar_matches_reference_layer_list():
 
 
 def test_plan_config_errors(speech_setup):
+    import copy
     hp, _, _ = speech_setup
     bad = copy.deepcopy(hp)
     bad["mbexwn_config"]["pulse_channels"] = 4              # 8000/4*15 != 24000 (custom_pulsed_generator.py:344)
