@@ -89,8 +89,6 @@ struct KBlock {
     int a_col;      // first A column (elements) of the hi plane for this K block
     int a_shift;    // row shift of the A tile (dilated tap)
     int b_col;      // first B column (elements) of the hi plane
-    int k16;        // 16-channel groups of the block that hold real channels (1 .. 4): the zero padding of the last block of a
-                    // channel count that is no multiple of 64 (C = 340 -> 384) is not multiplied
 };
 
 struct alignas(64) GemmParams {
@@ -1152,13 +1150,12 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
             uint32_t ia = 0, ib = 0, tile_it = 0;
             const uint32_t a_base = smem_u32(ring_a) >> 4, b_base = smem_u32(ring_b) >> 4;
             // first: 0 = accumulate, 1 = the first MMA overwrites the accumulator, 2 = the first MMA rescales it by 2^-15
-            auto mma4 = [&](uint32_t tacc, uint32_t sa, uint32_t sb, uint32_t idesc, int first, int nk) {
+            auto mma4 = [&](uint32_t tacc, uint32_t sa, uint32_t sb, uint32_t idesc, int first) {
                 if (p.debug & 4) return;
                 const uint64_t da = DESC_HI | (uint64_t)(a_base + sa * (A_BYTES >> 4));
                 const uint64_t db = DESC_HI | (uint64_t)(b_base + sb * (B_BYTES >> 4));
 #pragma unroll
                 for (int k = 0; k < TILE_K / UMMA_K; ++k) {
-                    if (k >= nk) break;
                     // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16-byte units
                     if (k == 0 && first == 2) {
                         if (CG == 1) tc_mma_f16_sd(tacc, da, db, idesc);
@@ -1168,14 +1165,12 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                 }
             };
             // e4m3 products of one K block: [lo8 | hi8] (A) x [hi8 | lo8] (B) = 128 bytes along K = 4 instructions of K = 32
-            auto mma8 = [&](uint32_t tacc, uint32_t sa, uint32_t sb, uint32_t idesc, bool first, int nk) {
+            auto mma8 = [&](uint32_t tacc, uint32_t sa, uint32_t sb, uint32_t idesc, bool first) {
                 if (p.debug & 4) return;
                 const uint64_t da = DESC_HI | (uint64_t)(a_base + sa * (A_BYTES >> 4));
                 const uint64_t db = DESC_HI | (uint64_t)(b_base + sb * (B_BYTES >> 4));
-                const int nk8 = (nk + 1) >> 1;                  // K = 32 instructions per e4m3 plane that hold real channels
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if ((k & 1) >= nk8) continue;               // k = 0, 1: lo8 x hi8 plane pair; k = 2, 3: hi8 x lo8
                     if (CG == 1) tc_mma_f8(tacc, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
                     else tc_mma_f8_2sm(tacc, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
                 }
@@ -1199,7 +1194,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                         mbar_wait(&full_b[sb], pb);
                         tc_fence_after();
                         if (elect_one()) {
-                            mma8(tacc, sa, sb, idesc, kb == 0, p.kb[kb].k16);
+                            mma8(tacc, sa, sb, idesc, kb == 0);
                             commit(&empty_a[sa]);
                             commit(&empty_b[sb]);
                         }
@@ -1217,12 +1212,12 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                     if (p.n_terms == 3) {
                         const uint32_t sa_lo = (ia + 1) % NA, pa_lo = ((ia + 1) / NA) & 1;
                         const uint32_t sb_lo = (ib + 1) % NB, pb_lo = ((ib + 1) / NB) & 1;
-                        if (elect_one()) mma4(tacc, sa_hi, sb_hi, idesc, kb == 0 ? 1 : 0, p.kb[kb].k16);     // hi * hi
+                        if (elect_one()) mma4(tacc, sa_hi, sb_hi, idesc, kb == 0 ? 1 : 0);     // hi * hi
                         __syncwarp();
                         mbar_wait(&full_a[sa_lo], pa_lo);
                         tc_fence_after();
                         if (elect_one()) {
-                            mma4(tacc, sa_lo, sb_hi, idesc, 0, p.kb[kb].k16);                        // lo * hi
+                            mma4(tacc, sa_lo, sb_hi, idesc, 0);                        // lo * hi
                             commit(&empty_a[sa_lo]);
                             commit(&empty_b[sb_hi]);
                         }
@@ -1230,7 +1225,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                         mbar_wait(&full_b[sb_lo], pb_lo);
                         tc_fence_after();
                         if (elect_one()) {
-                            mma4(tacc, sa_hi, sb_lo, idesc, 0, p.kb[kb].k16);                        // hi * lo
+                            mma4(tacc, sa_hi, sb_lo, idesc, 0);                        // hi * lo
                             commit(&empty_a[sa_hi]);
                             commit(&empty_b[sb_lo]);
                             if (kb == p.n_kb - 1) commit(&tmem_full[as]);              // accumulator complete
@@ -1240,7 +1235,7 @@ wn_gemm_kernel(const __grid_constant__ GemmParams p) {
                         ib += 2;
                     } else {
                         if (elect_one()) {
-                            mma4(tacc, sa_hi, sb_hi, idesc, kb == 0 ? (p.n_terms == 2 ? 2 : 1) : 0, p.kb[kb].k16);
+                            mma4(tacc, sa_hi, sb_hi, idesc, kb == 0 ? (p.n_terms == 2 ? 2 : 1) : 0);
                             commit(&empty_a[sa_hi]);
                             commit(&empty_b[sb_hi]);
                             if (kb == p.n_kb - 1) commit(&tmem_full[as]);              // both CTAs of a pair are told
@@ -1576,15 +1571,12 @@ cudaError_t launch_gemm(Impl* im, GemmParams& p, cudaStream_t s) {
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // K-block program of a launch: one entry per (tap, 64-channel block); the lo planes are addressed by fixed offsets.
-int build_kblocks(KBlock* kb, int n_taps, const int* shifts, int cpad, int c_valid) {
+int build_kblocks(KBlock* kb, int n_taps, const int* shifts, int cpad) {
     int n = 0;
     for (int tap = 0; tap < n_taps; ++tap)
         for (int cb = 0; cb < cpad / TILE_K; ++cb) {
             if (n >= MAX_KB) return -1;
-            int left = c_valid - cb * TILE_K;
-            left = left > TILE_K ? TILE_K : left;
-            const int k16 = left <= 0 ? 1 : (left + UMMA_K - 1) / UMMA_K;
-            kb[n++] = KBlock{cb * TILE_K, shifts[tap], tap * cpad + cb * TILE_K, k16};
+            kb[n++] = KBlock{cb * TILE_K, shifts[tap], tap * cpad + cb * TILE_K};
         }
     return n;
 }
@@ -1690,7 +1682,7 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         if ((rc = make_map(im, &p1.tm_b, w1, n1, k1, TILE_N, error))) return rc;
         int shifts[16];
         for (int t = 0; t < c.wn_k; ++t) shifts[t] = (t - (c.wn_causal ? c.wn_k - 1 : (c.wn_k - 1) / 2)) * d;
-        p1.n_kb = build_kblocks(p1.kb, c.wn_k, shifts, cpad, c.wn_c);
+        p1.n_kb = build_kblocks(p1.kb, c.wn_k, shifts, cpad);
         p1.n_terms = n_terms; p1.a_lo_off = cpad; p1.b_lo_off = c.wn_k * cpad;
         if (f8) { p1.f16 = 1; p1.out_f16f8 = 1; p1.out_lo_scale = a_lo; }
         p1.rows = rows; p1.n_cols = n1; p1.bias = b1; p1.cond = cond; p1.act = a2; p1.ld_act = 2 * cpad;
@@ -1707,7 +1699,7 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         p2.tm_out = tm_h;
         if ((rc = make_map(im, &p2.tm_b, w2, n2, k2, TILE_N, error))) return rc;
         int zero = 0;
-        p2.n_kb = build_kblocks(p2.kb, 1, &zero, cpad, c.wn_c);
+        p2.n_kb = build_kblocks(p2.kb, 1, &zero, cpad);
         p2.n_terms = n_terms; p2.a_lo_off = cpad; p2.b_lo_off = cpad;
         if (f8) { p2.f16 = 1; p2.out_f16f8 = 1; p2.out_lo_scale = h_lo; p2.in_lo_inv = 1.f / h_lo; }
         p2.rows = rows; p2.n_cols = n2; p2.bias = b2; p2.h = h2; p2.ld_h = 2 * cpad;
@@ -1758,7 +1750,7 @@ int wn_tc_conv(WnTcState& st, const TcConvArgs& a, const FrameGrid& g, cudaStrea
     if ((rc = make_map(im, &p.tm_b, a.w, a.cout, 2 * a.k * a.cin_pad, TILE_N, error))) return rc;
     int shifts[16];
     for (int t = 0; t < a.k; ++t) shifts[t] = t * a.dilation - a.pad_l;
-    p.n_kb = build_kblocks(p.kb, a.k, shifts, a.cin_pad, a.cin_pad);
+    p.n_kb = build_kblocks(p.kb, a.k, shifts, a.cin_pad);
     p.n_terms = 3; p.a_lo_off = a.cin_pad; p.b_lo_off = a.k * a.cin_pad;
     p.rows = a.rows; p.n_cols = a.cout; p.bias = a.bias;
     p.out_f32 = a.out_f32; p.ld_out = a.ld_out;
@@ -1783,7 +1775,7 @@ int wn_tc_gemm_test(WnTcState& st, const void* a_bf16, long long rows, int a_col
     p.n_terms = 1;
     if ((rc = make_map(im, &p.tm_a, a_bf16, rows, a_cols, TILE_M, error))) return rc;
     if ((rc = make_map(im, &p.tm_b, b_bf16, n, b_cols, TILE_N, error))) return rc;
-    for (int i = 0; i < n_kb; ++i) p.kb[i] = KBlock{kblocks[3 * i], kblocks[3 * i + 1], kblocks[3 * i + 2], TILE_K / UMMA_K};
+    for (int i = 0; i < n_kb; ++i) p.kb[i] = KBlock{kblocks[3 * i], kblocks[3 * i + 1], kblocks[3 * i + 2]};
     p.n_kb = n_kb; p.rows = rows; p.n_cols = n; p.out_f32 = out; p.bias = nullptr;
     cudaError_t e = launch_gemm<EPI_PLAIN>(im, p, s);
     if (e != cudaSuccess) { if (error) *error = cudaGetErrorString(e); return MBEXWN_ERR_CUDA; }
@@ -1805,7 +1797,7 @@ int wn_tc_gemm_test_f16f8(WnTcState& st, const void* a, long long rows, int a_cp
     if ((rc = make_map(im, &p.tm_a, a, rows, 2 * a_cpad, TILE_M, error))) return rc;
     if ((rc = make_map(im, &p.tm_b, b, n, 2 * b_k, TILE_N, error))) return rc;
     p.a_lo_off = a_cpad; p.b_lo_off = b_k;
-    for (int i = 0; i < n_kb; ++i) p.kb[i] = KBlock{kblocks[3 * i], kblocks[3 * i + 1], kblocks[3 * i + 2], TILE_K / UMMA_K};
+    for (int i = 0; i < n_kb; ++i) p.kb[i] = KBlock{kblocks[3 * i], kblocks[3 * i + 1], kblocks[3 * i + 2]};
     p.n_kb = n_kb; p.rows = rows; p.n_cols = n; p.out_f32 = out; p.bias = nullptr;
     cudaError_t e = launch_gemm<EPI_PLAIN>(im, p, s);
     if (e != cudaSuccess) { if (error) *error = cudaGetErrorString(e); return MBEXWN_ERR_CUDA; }
