@@ -239,7 +239,8 @@ MBEXWN_API int mbexwn_stage_ms(mbexwn_handle_t h, float* ms);
 
 /* Device time of the WaveNet tap-GEMM launches of the last forward (needs "stage_timing" and a tensor-core precision):
  * sum over the layers of the gate launches (dilated conv + gate epilogue) and of the res/skip launches, from CUDA events
- * recorded on the caller's stream around every launch.  Synchronises on the last event. */
+ * recorded on the caller's stream around every launch.  Synchronises on the last event.  A stack of several WaveNet blocks
+ * (wn_n_blocks > 1) reports the launches of its last block; mbexwn_stage_ms covers all blocks in the "wavenet" stage. */
 MBEXWN_API int mbexwn_wavenet_launch_ms(mbexwn_handle_t h, float* gate_ms, float* resskip_ms, int32_t* n_layers);
 
 /* ---- single kernels on caller-provided buffers (stage-level parity tests; same kernels the forward uses) ---- */
