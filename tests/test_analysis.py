@@ -112,3 +112,18 @@ def test_no_cpu_fallback_for_analysis(pc):
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         PA.MelAnalyzer(pc)
+
+
+def test_oracle_analysis_matches_the_reference_functions():
+    """`mell_*` of reference_analysis.npz = the reference's compute_mel_spectrogram_internal + scale_mel_spectrogram
+    (preprocess.py:81-113, :417-572), AST-extracted and run unmodified with this package's mel basis standing in for librosa's:
+    the oracle's framing, projection and log / scale post-processing must be bit-identical."""
+    from mbexwn_vocoder_b200 import get_config_file
+    from mbexwn_vocoder_b200.config import read_config
+    from oracle.analysis import compute_mel_spectrogram
+    g = np.load(GOLD)
+    pc = read_config(get_config_file("SPEECH"))["preprocess_config"]
+    assert np.array_equal(compute_mel_spectrogram(g["audio"], pc), g["mell_post"])
+    assert np.array_equal(compute_mel_spectrogram(g["audio"], pc, do_post=False), g["mell_nopost"])
+    pc2 = dict(pc, lin_amp_scale=0.5, lin_amp_off=1e-3, mel_amp_scale=0.25, use_max_limit=True)
+    assert np.array_equal(compute_mel_spectrogram(g["audio"], pc2), g["mell_post_scaled"])
