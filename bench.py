@@ -214,6 +214,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tc-debug", type=int, default=0, help="kernel timing experiments (invalid results): see GemmParams::debug")
     ap.add_argument("--cta-group", type=int, default=2, choices=[1, 2], help="tcgen05 tiles per CTA (1) or per CTA pair (2)")
+    ap.add_argument("--fused", type=int, default=2, choices=[0, 1, 2],
+                    help="WaveNet layer as one persistent kernel: 0 never (gate + res/skip launches), 1 always, 2 auto (default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.precision is None:
@@ -241,6 +243,7 @@ def main():
     eng.set_option("debug_taps", 0)
     eng.set_option("stage_timing", 0)
     eng.set_option("tc_cta_group", args.cta_group)
+    eng.set_option("tc_fused", args.fused)
     if args.tc_debug:
         eng.set_option("tc_debug", args.tc_debug)
     mels, noise = synthetic_batch(batch, frames, plan.steps_per_frame, seed0=rank * batch)
@@ -340,7 +343,14 @@ def main():
     peak = pk["bf16_tflops_sustained"]
     # dominant kernel: the gate tap-GEMM (dilated conv, K = k C, N = 2 C), one launch per layer
     gate_flops = 2.0 * wn.k * wn.c * 2 * wn.c * rows                     # algorithmic, un-padded, per launch
-    if args.precision != "fp32" and wn_launch["gate"] > 0:
+    fused_layer = args.precision != "fp32" and wn_launch["gate"] > 0 and wn_launch["resskip"] == 0.0
+    if fused_layer:
+        # one persistent kernel per layer: dilated conv + gate + res/skip 1x1 + residual update (k_wavenet_layer.cu)
+        gate_flops = wn_flops / L                                        # algorithmic FLOPs of an average layer launch
+        gate_ms = wn_launch["gate"] / L
+        achieved = gate_flops / (gate_ms / 1e3) / 1e12
+        kernel = "wn_layer_kernel (tcgen05: dilated-conv tap-GEMM + gate + res/skip 1x1 + residual update, one launch per layer)"
+    elif args.precision != "fp32" and wn_launch["gate"] > 0:
         gate_ms = wn_launch["gate"] / L
         achieved = gate_flops / (gate_ms / 1e3) / 1e12
         kernel = "wn_gemm_kernel<EPI_GATE> (tcgen05 tap-GEMM of the dilated conv + tanh*sigmoid gate epilogue)"
@@ -380,7 +390,7 @@ def main():
                   "fp32": "f32"}[args.precision],
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "per_gpu_batch": batch, "frames": frames,
-                   "precision": args.precision, "tc_cta_group": args.cta_group, "parallelism": f"dp{world} (independent utterances, no collective)",
+                   "precision": args.precision, "tc_cta_group": args.cta_group, "fused_layer_kernel": bool(fused_layer), "parallelism": f"dp{world} (independent utterances, no collective)",
                    "l2": (f"per-step working set {pb.ws_bytes / 1e6:.0f} MB of activations "
                           + (">> 126 MB L2; no flush needed" if pb.ws_bytes > 4 * 126e6 else "(comparable to the 126 MB L2: not flushed, "
                              "treat as an L2-warm figure)"))},

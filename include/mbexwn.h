@@ -229,7 +229,12 @@ MBEXWN_API int mbexwn_last_launch_count(mbexwn_handle_t h);
  * "tc_cond_stage" (default 1): the gate epilogue reads its conditioning rows from a shared-memory stage (0: global);
  * "fuse_tail" (default 1): the LinInterp -> 1x1 -> LinInterp end of the F0 sub-net runs as one kernel;
  * "stop_after_f0" (default 0): return after the F0 sub-net (tap "F0"), for the F0 pass of chunked long-form synthesis;
- * "tc8_h_lo" / "tc8_a_lo": log2 scale of the e4m3 lo8 planes of the residual stream / gated activations (F16F8). */
+ * "tc8_h_lo" / "tc8_a_lo": log2 scale of the e4m3 lo8 planes of the residual stream / gated activations (F16F8);
+ * "tc_fused" (default 2): one persistent kernel per WaveNet layer (dilated conv, gate, res/skip 1x1 and the residual update in one
+ *   launch; the gated activations stay in L2) -- 0: never (a gate and a res/skip launch per layer), 1: whenever the geometry allows,
+ *   2: when every CTA pair gets at least two 256-row tiles (short batches keep the two-launch schedule that spreads one M tile
+ *   over several CTAs);
+ * "tc_trace" (default 0): k > 0 records per-tile cycle stamps of the fused kernel of layer k - 1 (mbexwn_tc_trace_read). */
 MBEXWN_API int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value);
 
 /* Device time of each stage of the last forward (needs "stage_timing"); ms[MBEXWN_N_STAGES] in the order
@@ -242,6 +247,11 @@ MBEXWN_API int mbexwn_stage_ms(mbexwn_handle_t h, float* ms);
  * recorded on the caller's stream around every launch.  Synchronises on the last event.  A stack of several WaveNet blocks
  * (wn_n_blocks > 1) reports the launches of its last block; mbexwn_stage_ms covers all blocks in the "wavenet" stage. */
 MBEXWN_API int mbexwn_wavenet_launch_ms(mbexwn_handle_t h, float* gate_ms, float* resskip_ms, int32_t* n_layers);
+/* With "tc_fused" in effect a layer is ONE launch: gate_ms then holds the sum of the fused launches and resskip_ms is 0. */
+
+/* Profiling aid ("tc_trace"): copies the cycle stamps of the traced fused-layer launch to `out` (host, n_words uint32);
+ * layout [cta][role: 0 producer, 1 MMA issuer, 2 epilogue warp][384 tiles][4 words].  Returns the words written or < 0. */
+MBEXWN_API int64_t mbexwn_tc_trace_read(mbexwn_handle_t h, uint32_t* out, int64_t n_words);
 
 /* ---- single kernels on caller-provided buffers (stage-level parity tests; same kernels the forward uses) ---- */
 MBEXWN_API int mbexwn_k_conv1d(mbexwn_handle_t h, const mbexwn_batch_t* grid, const mbexwn_op_t* op, int32_t rate,

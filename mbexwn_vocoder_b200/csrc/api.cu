@@ -862,6 +862,8 @@ int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value) {
     if (!strcmp(name, "tc_cond_stage")) { h->tc.cond_stage = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "stop_after_f0")) { h->stop_after_f0 = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "tc_debug")) { h->tc.debug = value; return MBEXWN_OK; }
+    if (!strcmp(name, "tc_fused")) { h->tc.fused = value < 0 ? 0 : (value > 2 ? 2 : value); return MBEXWN_OK; }
+    if (!strcmp(name, "tc_trace")) { h->tc.trace_on = value; return MBEXWN_OK; }
     if (!strcmp(name, "tc8_h_lo")) { h->tc.sh_h_lo = value; return MBEXWN_OK; }
     if (!strcmp(name, "tc8_a_lo")) { h->tc.sh_a_lo = value; return MBEXWN_OK; }
     return mbx::fail(h, MBEXWN_ERR_INVALID, std::string("unknown option: ") + name);
@@ -882,6 +884,11 @@ int mbexwn_wavenet_launch_ms(mbexwn_handle_t h, float* gate_ms, float* resskip_m
     if (rc) return mbx::fail(h, rc, "no WaveNet launch timing recorded (set option stage_timing, tensor-core precision)");
     *n_layers = n;
     return MBEXWN_OK;
+}
+
+int64_t mbexwn_tc_trace_read(mbexwn_handle_t h, uint32_t* out, int64_t n_words) {
+    if (!h || !out || n_words <= 0) return -1;
+    return mbx::wn_tc_read_trace(h->tc, out, n_words);
 }
 
 int mbexwn_k_conv1d(mbexwn_handle_t h, const mbexwn_batch_t* b, const mbexwn_op_t* op, int32_t rate, const float* x,

@@ -45,6 +45,7 @@
 
 #include "kernels.cuh"
 #include "wn_tc.cuh"
+#include "tc_common.cuh"
 
 namespace mbx {
 
@@ -141,244 +142,9 @@ struct alignas(64) GemmParams {
                             // 8 = epilogues skip their global stores, 16 = no gate math, 32 = res/skip does not read h
 };
 
-// ---- PTX wrappers ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(0x989680u)      // suspend-time hint: sleep in hardware instead of spinning
-        : "memory");                                   // (a spinning warp costs issue slots and power the tensor pipe needs)
-    return done;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    if (mbar_try_wait(addr, parity)) return;
-    // slow path: try_wait suspends the thread for a hardware time slice per attempt; a protocol bug must trap, not
-    // hang the device (the counter is only touched when the barrier was not ready)
-    uint32_t spins = 0;
-    while (!mbar_try_wait(addr, parity))
-        if (++spins > (1u << 26)) __trap();
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-template <int THREADS>
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"((uint64_t)tm), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    // default semantics (.release at CTA scope): the accumulator reads were already ordered by tcgen05.wait::ld +
-    // tcgen05.fence::before_thread_sync; a .release.cluster arrive costs MEMBAR.ALL.GPU + ERRBAR per tile and warp
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// 2-CTA TMA load: data lands in this CTA's smem, the transaction bytes are reported to the pair leader's mbarrier
-__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* tm, uint32_t leader_bar, void* dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(leader_bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// e4m3 x e4m3 -> fp32 (kind::f8f6f4, K = 32 per instruction: twice the MACs of a kind::f16 instruction in the same time)
-__device__ __forceinline__ void tc_mma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_mma_f8_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// D = A * B + D * 2^-15 (scale-input-d): folds the 2^15 scale of the e4m3 correction products already sitting in the
-// accumulator into the first fp16 product of a tile
-constexpr int CORR_SHIFT = 15;
-__device__ __forceinline__ void tc_mma_f16_sd(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, 1, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, %4;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(CORR_SHIFT)
-        : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16_sd_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, 1, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p, %4;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(CORR_SHIFT)
-        : "memory");
-}
-// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-// 32 lanes x 16 columns
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M x N
-__device__ __forceinline__ constexpr uint32_t make_idesc(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-// the same with format code 0 for A and B: fp16 under kind::f16, e4m3 under kind::f8f6f4
-__device__ __forceinline__ constexpr uint32_t make_idesc_fmt0(int m, int n) {
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
-    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
-
-// MBEXWN_PREC_F16F8 operand planes of 8 consecutive channels: fp16(x), e4m3((x - fp16(x)) * lo_scale), e4m3(x).
-// The scales are powers of two chosen so that the planes sit in e4m3's normal range and the two correction products of a
-// GEMM share the factor 2^15 that scale-input-d removes (see wn_tc_forward).
-__device__ __forceinline__ void split_f16f8(const float (&a)[8], float lo_scale, uint4& h16, uint2& lo8, uint2& hi8) {
-    uint32_t hw[4], l[4], h[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const __half2 hh = __floats2half2_rn(a[2 * e], a[2 * e + 1]);
-        const float2 hf = __half22float2(hh);
-        hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
-        l[e] = __nv_cvt_float2_to_fp8x2(make_float2((a[2 * e] - hf.x) * lo_scale, (a[2 * e + 1] - hf.y) * lo_scale), __NV_SATFINITE, __NV_E4M3);
-        h[e] = __nv_cvt_float2_to_fp8x2(make_float2(a[2 * e], a[2 * e + 1]), __NV_SATFINITE, __NV_E4M3);
-    }
-    h16 = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    lo8 = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
-    hi8 = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
-}
-
-// byte offset of the e4m3 lo8 group of channel ch (a multiple of 8) inside a row of 4 * cpad bytes; hi8 sits 64 bytes further
-__device__ __forceinline__ int f8_off(int cpad, int ch) { return 2 * cpad + ((ch >> 6) << 7) + (ch & 63); }
-
-// the value a (fp16, e4m3 lo8) pair stands for: 8 channels
-__device__ __forceinline__ void join_f16f8(const uint4& h16, const uint2& lo8, float lo_inv, float (&x)[8]) {
-    const uint32_t hw[4] = {h16.x, h16.y, h16.z, h16.w};
-    const uint32_t lw[2] = {lo8.x, lo8.y};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
-        const __half2_raw lr = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(lw[e >> 1] >> (16 * (e & 1))), __NV_E4M3);
-        const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lr));
-        x[2 * e] = fmaf(lf.x, lo_inv, hf.x);
-        x[2 * e + 1] = fmaf(lf.y, lo_inv, hf.y);
-    }
-}
+using namespace tcx;
 
 // ---- epilogues: one thread = one accumulator row -----------------------------------------------------------------
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// tanh / sigmoid from one ex2 + one rcp each (relative error ~1e-6, saturates cleanly at +-inf)
-__device__ __forceinline__ float fast_tanh(float x) { return 1.f - 2.f * rcp_approx(1.f + ex2_approx(x * 2.885390081777927f)); }
-__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.f + ex2_approx(x * -1.4426950408889634f)); }
 
 // `part` (0 .. nparts-1) selects which 32-column chunks of the tile this warp handles (part, part + nparts, ...);
 // `width` = valid tile columns.
@@ -1539,6 +1305,35 @@ int ensure_impl(WnTcState& st, std::string* err) {
     return MBEXWN_OK;
 }
 
+}  // namespace
+
+int wn_tc_encode_map(WnTcState& st, void* tensor_map, const void* base, long long rows, long long cols, int box_rows,
+                     std::string* error) {
+    int rc = ensure_impl(st, error);
+    if (rc) return rc;
+    Impl* im = reinterpret_cast<Impl*>(st.impl);
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TILE_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = im->encode(reinterpret_cast<CUtensorMap*>(tensor_map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                            dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (error) *error = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
+        return MBEXWN_ERR_CUDA;
+    }
+    return MBEXWN_OK;
+}
+
+int wn_tc_sm_count(WnTcState& st) {
+    std::string e;
+    if (ensure_impl(st, &e)) return 0;
+    return reinterpret_cast<Impl*>(st.impl)->sm_count;
+}
+
+namespace {
+
 template <int EPI>
 cudaError_t launch_gemm(Impl* im, GemmParams& p, cudaStream_t s) {
     p.tiles_m = (int)((p.rows + TILE_M - 1) / TILE_M);
@@ -1586,8 +1381,18 @@ int build_kblocks(KBlock* kb, int n_taps, const int* shifts, int cpad) {
 void wn_tc_carve(const mbexwn_config_t& c, long long rows, int precision, const std::function<void(const char*, size_t)>& add) {
     (void)precision;
     const int cpad = round_up(c.wn_c, TILE_K);
+    // two-launch path: h2 = residual stream (in place), a2 = gated activations; fused layer kernel: h2 / a2 = residual stream
+    // ping-pong, act_scr = per-pair scratch of the gated activations (L2 resident)
     add("h2", (size_t)rows * 2 * cpad * sizeof(__nv_bfloat16));
     add("a2", (size_t)rows * 2 * cpad * sizeof(__nv_bfloat16));
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            sm_count = 0;
+        if (sm_count <= 0) sm_count = 148;
+    }
+    add("act_scr", wn_layer_scratch_bytes(cpad, sm_count));
 }
 
 int wn_tc_out_pad(const mbexwn_config_t& c) { return round_up(c.wn_cout, 32); }
@@ -1663,6 +1468,49 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         }
         ev = reinterpret_cast<cudaEvent_t*>(st.events);
         cudaEventRecord(ev[st.n_timed++], s);
+    }
+    // fused per-layer kernel (k_wavenet_layer.cu) when the problem is large enough to keep every CTA pair busy
+    const int tiles_mg_l = (int)((rows + 2 * TILE_M - 1) / (2 * TILE_M));
+    const bool fused = st.fused && im->cta_group == 2 && wn_layer_supported(c, cpad, n_terms, cond_rows) &&
+                       (st.fused == 1 || tiles_mg_l >= 2 * (im->sm_count / 2));
+    st.last_fused = fused ? 1 : 0;
+    if (fused) {
+        __nv_bfloat16* hbuf[2] = {h2, a2};
+        void* scr = slot("act_scr");
+        for (int i = 0; i < c.wn_layers; ++i) {
+            const std::string li = std::to_string(i);
+            const bool last = i == c.wn_layers - 1;
+            const int d = c.wn_dilations[i];
+            WnLayerArgs a{};
+            a.n1 = 2 * cpad; a.k1 = 2 * c.wn_k * cpad;
+            a.n2 = (last ? 0 : cpad) + out_pad; a.k2 = 2 * cpad;
+            a.w1 = tensor(n + tc + "W1_" + li, (size_t)a.n1 * a.k1 * 2);
+            a.bias1 = (const float*)tensor(n + "/tc/b1_" + li, (size_t)a.n1 * 4);
+            a.w2 = tensor(n + tc + "R_" + li, (size_t)a.n2 * a.k2 * 2);
+            a.bias2 = (const float*)tensor(n + "/tc/rb_" + li, (size_t)a.n2 * 4);
+            if (!a.w1 || !a.bias1 || !a.w2 || !a.bias2) return fail("packed tensor-core weights missing for layer " + li, MBEXWN_ERR_MISSING);
+            a.h_in = hbuf[i & 1];
+            a.h_out = last ? nullptr : hbuf[(i + 1) & 1];
+            a.scratch = scr;
+            a.rows = rows; a.c = c.wn_c; a.cpad = cpad; a.n_terms = n_terms; a.n_taps = c.wn_k;
+            for (int t = 0; t < c.wn_k; ++t) a.shifts[t] = (t - (c.wn_causal ? c.wn_k - 1 : (c.wn_k - 1) / 2)) * d;
+            a.cond = cond; a.cond_total = rows / c.wn_cond_lin_up; a.cond_rows = cond_rows; a.lin_up = c.wn_cond_lin_up;
+            a.gate = c.wn_gate; a.steps_per_frame = c.steps_per_frame;
+            for (int u = 0; u < c.wn_cond_lin_up; ++u) { a.lin_w0[u] = lw0[u]; a.lin_w1[u] = lw1[u]; }
+            a.act_lo_scale = a_lo; a.h_lo_scale = h_lo;
+            a.skip = wn_out; a.skip_ld = out_pad; a.skip_c = out_pad; a.res_cols = last ? 0 : cpad; a.first = i == 0;
+            a.grid = g; a.sm_count = im->sm_count;
+            a.trace = nullptr;
+            if (st.trace_on == i + 1) {
+                if (!st.trace && cudaMalloc(&st.trace, wn_layer_trace_bytes(im->sm_count)) != cudaSuccess) return fail("trace buffer", MBEXWN_ERR_CUDA);
+                cudaMemsetAsync(st.trace, 0, wn_layer_trace_bytes(im->sm_count), s);
+                a.trace = st.trace;
+            }
+            if ((rc = wn_layer_forward(st, a, s, error))) return rc;
+            if (ev) cudaEventRecord(ev[st.n_timed++], s);
+            *launches += 1;
+        }
+        return MBEXWN_OK;
     }
     for (int i = 0; i < c.wn_layers; ++i) {
         const std::string li = std::to_string(i);
@@ -1805,22 +1653,32 @@ int wn_tc_gemm_test_f16f8(WnTcState& st, const void* a, long long rows, int a_cp
 }
 
 int wn_tc_launch_ms(WnTcState& st, float* gate_ms, float* resskip_ms, int* n_layers) {
-    if (!st.events || st.n_timed < 3) return MBEXWN_ERR_INVALID;
+    if (!st.events || st.n_timed < 2) return MBEXWN_ERR_INVALID;
     cudaEvent_t* ev = reinterpret_cast<cudaEvent_t*>(st.events);
     if (cudaEventSynchronize(ev[st.n_timed - 1]) != cudaSuccess) return MBEXWN_ERR_CUDA;
     float g = 0.f, r = 0.f;
     for (int i = 0; i + 1 < st.n_timed; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) != cudaSuccess) return MBEXWN_ERR_CUDA;
-        (i & 1 ? r : g) += ms;
+        (!st.last_fused && (i & 1) ? r : g) += ms;
     }
-    *gate_ms = g; *resskip_ms = r; *n_layers = (st.n_timed - 1) / 2;
+    *gate_ms = g; *resskip_ms = r; *n_layers = st.last_fused ? st.n_timed - 1 : (st.n_timed - 1) / 2;
     return MBEXWN_OK;
 }
 
 void wn_tc_invalidate(WnTcState&) {}
 
+long long wn_tc_read_trace(WnTcState& st, uint32_t* out, long long n_words) {
+    if (!st.trace || !st.impl) return -1;
+    const long long have = (long long)(wn_layer_trace_bytes(reinterpret_cast<Impl*>(st.impl)->sm_count) / 4);
+    const long long n = n_words < have ? n_words : have;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpy(out, st.trace, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return n;
+}
+
 void wn_tc_destroy(WnTcState& st) {
+    if (st.trace) { cudaFree(st.trace); st.trace = nullptr; }
     if (st.events) {
         cudaEvent_t* e = reinterpret_cast<cudaEvent_t*>(st.events);
         for (int i = 0; i < 2 * MBEXWN_MAX_LAYERS + 1; ++i) cudaEventDestroy(e[i]);

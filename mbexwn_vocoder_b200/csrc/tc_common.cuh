@@ -1,0 +1,256 @@
+// PTX wrappers and operand-plane helpers shared by the tensor-core kernels (k_wavenet_tc.cu: tap-GEMM with separate
+// gate / res-skip launches, sub-net convs; k_wavenet_layer.cu: the fused per-layer kernel).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <stdint.h>
+
+namespace mbx {
+namespace tcx {
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(0x989680u)      // suspend-time hint: sleep in hardware instead of spinning
+        : "memory");                                   // (a spinning warp costs issue slots and power the tensor pipe needs)
+    return done;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    if (mbar_try_wait(addr, parity)) return;
+    // slow path: try_wait suspends the thread for a hardware time slice per attempt; a protocol bug must trap, not
+    // hang the device: four seconds of wall clock on one barrier are far beyond any launch of this library
+    const uint64_t t0 = global_timer_ns();
+    while (!mbar_try_wait(addr, parity))
+        if (global_timer_ns() - t0 > 4000000000ull) __trap();
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+template <int THREADS>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"((uint64_t)tm), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default semantics (.release at CTA scope): the accumulator reads were already ordered by tcgen05.wait::ld +
+    // tcgen05.fence::before_thread_sync; a .release.cluster arrive costs MEMBAR.ALL.GPU + ERRBAR per tile and warp
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-CTA TMA load: data lands in this CTA's smem, the transaction bytes are reported to the pair leader's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* tm, uint32_t leader_bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// e4m3 x e4m3 -> fp32 (kind::f8f6f4, K = 32 per instruction: twice the MACs of a kind::f16 instruction in the same time)
+__device__ __forceinline__ void tc_mma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_f8_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// D = A * B + D * 2^-15 (scale-input-d): folds the 2^15 scale of the e4m3 correction products already sitting in the
+// accumulator into the first fp16 product of a tile
+constexpr int CORR_SHIFT = 15;
+__device__ __forceinline__ void tc_mma_f16_sd(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, %4;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(CORR_SHIFT)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_sd_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p, %4;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(CORR_SHIFT)
+        : "memory");
+}
+// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M x N
+__device__ __forceinline__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// the same with format code 0 for A and B: fp16 under kind::f16, e4m3 under kind::f8f6f4
+__device__ __forceinline__ constexpr uint32_t make_idesc_fmt0(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// MBEXWN_PREC_F16F8 operand planes of 8 consecutive channels: fp16(x), e4m3((x - fp16(x)) * lo_scale), e4m3(x).
+// The scales are powers of two chosen so that the planes sit in e4m3's normal range and the two correction products of a
+// GEMM share the factor 2^15 that scale-input-d removes (see wn_tc_forward).
+__device__ __forceinline__ void split_f16f8(const float (&a)[8], float lo_scale, uint4& h16, uint2& lo8, uint2& hi8) {
+    uint32_t hw[4], l[4], h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __half2 hh = __floats2half2_rn(a[2 * e], a[2 * e + 1]);
+        const float2 hf = __half22float2(hh);
+        hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[e] = __nv_cvt_float2_to_fp8x2(make_float2((a[2 * e] - hf.x) * lo_scale, (a[2 * e + 1] - hf.y) * lo_scale), __NV_SATFINITE, __NV_E4M3);
+        h[e] = __nv_cvt_float2_to_fp8x2(make_float2(a[2 * e], a[2 * e + 1]), __NV_SATFINITE, __NV_E4M3);
+    }
+    h16 = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    lo8 = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
+    hi8 = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+}
+
+// byte offset of the e4m3 lo8 group of channel ch (a multiple of 8) inside a row of 4 * cpad bytes; hi8 sits 64 bytes further
+__device__ __forceinline__ int f8_off(int cpad, int ch) { return 2 * cpad + ((ch >> 6) << 7) + (ch & 63); }
+
+// the value a (fp16, e4m3 lo8) pair stands for: 8 channels
+__device__ __forceinline__ void join_f16f8(const uint4& h16, const uint2& lo8, float lo_inv, float (&x)[8]) {
+    const uint32_t hw[4] = {h16.x, h16.y, h16.z, h16.w};
+    const uint32_t lw[2] = {lo8.x, lo8.y};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+        const __half2_raw lr = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(lw[e >> 1] >> (16 * (e & 1))), __NV_E4M3);
+        const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lr));
+        x[2 * e] = fmaf(lf.x, lo_inv, hf.x);
+        x[2 * e + 1] = fmaf(lf.y, lo_inv, hf.y);
+    }
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// tanh / sigmoid from one ex2 + one rcp each (relative error ~1e-6, saturates cleanly at +-inf)
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - 2.f * rcp_approx(1.f + ex2_approx(x * 2.885390081777927f)); }
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_approx(1.f + ex2_approx(x * -1.4426950408889634f)); }
+
+}  // namespace tcx
+}  // namespace mbx

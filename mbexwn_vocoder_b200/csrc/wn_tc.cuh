@@ -21,8 +21,49 @@ struct WnTcState {
     int n_timed = 0;            // events recorded by the last forward (n launches + 1)
     void* events = nullptr;     // cudaEvent_t[2 * MBEXWN_MAX_LAYERS + 1]
     int debug = 0;              // option "tc_debug": timing experiments (results are wrong), see GemmParams::debug
+    // option "tc_fused": one persistent kernel per WaveNet layer (k_wavenet_layer.cu) instead of a gate and a res/skip launch:
+    // 0 = never, 1 = whenever the geometry allows, 2 (default) = when every CTA pair gets at least two 256-row M tiles
+    int fused = 2;
+    int last_fused = 0;         // the last forward ran the fused kernel
+    void* trace = nullptr;      // option "tc_trace": device buffer of per-tile cycle stamps of the last fused launch
+    int trace_on = 0;
     void* impl = nullptr;
 };
+
+// ---- fused per-layer kernel (k_wavenet_layer.cu) ----------------------------------------------------------------
+struct WnLayerArgs {
+    const void* h_in;           // (rows, 2 cpad) operand planes of the layer input
+    void* h_out;                // same geometry, or nullptr for the last layer (no residual output)
+    void* scratch;              // wn_layer_scratch_bytes: per-pair double-buffered gated activations
+    const void* w1;             // (n1, k1) packed dilated-conv weights
+    const void* w2;             // (n2, k2) packed res / skip weights
+    int n1, k1, n2, k2;
+    long long rows;
+    int c, cpad, n_terms, n_taps;
+    int shifts[16];
+    const float* bias1;
+    const float* cond;
+    long long cond_total;
+    int cond_rows, lin_up, gate, steps_per_frame;
+    float lin_w0[32], lin_w1[32];
+    float act_lo_scale, h_lo_scale;
+    const float* bias2;
+    float* skip;
+    int skip_ld, skip_c, res_cols, first;
+    FrameGrid grid;
+    int sm_count;
+    void* trace;                // nullptr, or wn_layer_trace_bytes of device memory
+};
+size_t wn_layer_scratch_bytes(int cpad, int sm_count);
+size_t wn_layer_trace_bytes(int sm_count);
+bool wn_layer_supported(const mbexwn_config_t& c, int cpad, int n_terms, int cond_rows);
+int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::string* error);
+// cuTensorMapEncodeTiled of a row-major 16-bit matrix (rows, cols) with a 64-column x box_rows box, SWIZZLE_128B
+int wn_tc_encode_map(WnTcState& st, void* tensor_map, const void* base, long long rows, long long cols, int box_rows,
+                     std::string* error);
+int wn_tc_sm_count(WnTcState& st);
+// copies the trace of the last fused launch to the host (n_words uint32); returns the number of words written or < 0
+long long wn_tc_read_trace(WnTcState& st, uint32_t* out, long long n_words);
 
 // workspace slots the tensor-core path needs (called from the workspace carver)
 void wn_tc_carve(const mbexwn_config_t& c, long long rows, int precision,

@@ -115,8 +115,16 @@ def _snr_db(ref, test):
     return 10 * np.log10(np.sum(ref ** 2) / max(np.sum(err ** 2), 1e-300))
 
 
+@pytest.fixture(params=[0, 1], ids=["two_launch", "fused_layer"])
+def fused(request, engine):
+    """tc_fused = 1 forces the one-kernel-per-layer path (k_wavenet_layer.cu) also for batches this short (CTA pairs only)."""
+    engine.set_option("tc_fused", request.param)
+    yield request.param
+    engine.set_option("tc_fused", 2)
+
+
 @pytest.mark.parametrize("precision,tol,snr", [("bf16x3", 1e-4, 60.0), ("f16f8", 1e-4, 60.0), ("bf16", 5e-2, 35.0)])
-def test_wavenet_tc_parity(engine, cg, speech_setup, precision, tol, snr):
+def test_wavenet_tc_parity(engine, cg, fused, speech_setup, precision, tol, snr):
     hp, plan, w = speech_setup
     oracle = OracleMBExWN(hp, w, torch.float32)
     lengths = [23, 57, 10]
@@ -136,6 +144,30 @@ def test_wavenet_tc_parity(engine, cg, speech_setup, precision, tol, snr):
         e = np.abs(out[u] - ref["waveform"][0]).max() / np.abs(ref["waveform"][0]).max()
         print(f"{precision} utt {u} waveform: max|err|/peak {e:.3e}  SNR {s:.1f} dB")
         assert s >= snr and e <= tol
+
+
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3", "bf16"])
+def test_fused_layer_kernel_equals_two_launch_path(engine, speech_setup, precision):
+    """One persistent kernel per layer (gate tiles of M tile m, res tiles of M tile m - 1, activations through the L2 scratch,
+    residual stream ping-pong) against the gate + res/skip launches on a batch that gives every CTA pair several M tiles
+    and a ragged tail: the same products, summed in a different K order -- fp32 rounding apart (1e-5 of peak), every buffer agrees."""
+    hp, plan, w = speech_setup
+    lengths = [400, 380, 17, 400, 211, 400, 1, 400, 399, 400, 2, 400, 400, 333]
+    mels = [synthetic_mel(t, 40 + i) for i, t in enumerate(lengths)]
+    noise = [synthetic_noise(t * plan.steps_per_frame, 40 + i) for i, t in enumerate(lengths)]
+    engine.set_option("tc_cta_group", 2)
+    res = []
+    for mode in (0, 1):
+        engine.set_option("tc_fused", mode)
+        out, tp = engine.forward(mels, noise=noise, precision=precision, taps=["wn_out", "excitation"])
+        res.append((out, tp))
+    engine.set_option("tc_fused", 2)
+    engine.set_option("tc_cta_group", 1)
+    for u in range(len(lengths)):
+        assert np.all(np.isfinite(res[1][0][u]))
+        tol = 2e-3 if precision == "bf16" else 1e-5          # bf16 re-rounds the activations of every layer
+        for a, b, what in ((res[0][1]["wn_out"][u], res[1][1]["wn_out"][u], "wn_out"), (res[0][0][u], res[1][0][u], "waveform")):
+            assert np.abs(a - b).max() <= tol * max(np.abs(a).max(), 1e-30), f"{what} of utterance {u}"
 
 
 @pytest.mark.parametrize("lengths", [[40], [23, 57, 10, 1, 2]])
@@ -178,7 +210,10 @@ def test_wavenet_tc_parity_c340():
         n = t * plan.pulse_per_frame
         x = np.linspace(0, 1, n)
         f0.append((45.0 * (1400.0 / 45.0) ** x * (1 + 0.03 * np.sin(2 * np.pi * 5.5 * np.arange(n) / 8000.0))).astype(np.float32))
-    for precision, tol, snr in (("bf16x3", 1e-4, 60.0), ("f16f8", 1e-4, 60.0), ("fp32", 1e-4, 60.0)):
+    eng.set_option("tc_cta_group", 2)
+    for precision, tol, snr, fused in (("bf16x3", 1e-4, 60.0, 0), ("f16f8", 1e-4, 60.0, 0), ("f16f8", 1e-4, 60.0, 1),
+                                       ("bf16x3", 1e-4, 60.0, 1), ("fp32", 1e-4, 60.0, 0)):
+        eng.set_option("tc_fused", fused)
         out, tp = eng.forward(mels, noise=noise, f0=f0, precision=precision, taps=["index", "phase", "pulse", "wn_out"])
         for u in range(len(lengths)):
             ref = oracle.forward(mels[u][None], noise[u][None], f0_override=f0[u][None])
