@@ -234,6 +234,8 @@ MBEXWN_API int mbexwn_last_launch_count(mbexwn_handle_t h);
  *   launch; the gated activations stay in L2) -- 0: never (a gate and a res/skip launch per layer), 1: whenever the geometry allows,
  *   2: when every CTA pair gets at least two 256-row tiles (short batches keep the two-launch schedule that spreads one M tile
  *   over several CTAs);
+ * "tc_slab" (default 1): the dilated taps of the fused kernel share one A slab per 64-channel block (row-shifted MMA operand
+ *   views of one shared-memory tile); 0: one TMA tile per tap (bit-identical results, more L2 -> SM traffic);
  * "tc_trace" (default 0): k > 0 records per-tile cycle stamps of the fused kernel of layer k - 1 (mbexwn_tc_trace_read). */
 MBEXWN_API int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value);
 

@@ -863,6 +863,8 @@ int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value) {
     if (!strcmp(name, "stop_after_f0")) { h->stop_after_f0 = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "tc_debug")) { h->tc.debug = value; return MBEXWN_OK; }
     if (!strcmp(name, "tc_fused")) { h->tc.fused = value < 0 ? 0 : (value > 2 ? 2 : value); return MBEXWN_OK; }
+    if (!strcmp(name, "tc_slab")) { h->tc.slab = value ? 1 : 0; return MBEXWN_OK; }
+    if (!strcmp(name, "tc_ring_a")) { h->tc.n_a = value; return MBEXWN_OK; }
     if (!strcmp(name, "tc_trace")) { h->tc.trace_on = value; return MBEXWN_OK; }
     if (!strcmp(name, "tc8_h_lo")) { h->tc.sh_h_lo = value; return MBEXWN_OK; }
     if (!strcmp(name, "tc8_a_lo")) { h->tc.sh_a_lo = value; return MBEXWN_OK; }

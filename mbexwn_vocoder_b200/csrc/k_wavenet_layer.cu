@@ -18,10 +18,21 @@
 // * the residual stream ping-pongs between two buffers (the dilated taps of the neighbouring M tiles must keep reading
 //   the layer's *input*): old block TMA-loaded from h_in into a staging tile, updated in place by the epilogue warps,
 //   TMA-stored to h_out.  Guard rows pass through as the zeros they are.
-// * one operand ring of 4 stages, a stage = A tile (128 rows x 64 K) + B tile (this CTA's half of the N rows x 64 K) behind
-//   ONE full / empty mbarrier pair: the producer and MMA warps of the two-launch kernel spend ~70 % of their time in
-//   the serial latencies of two waits + two arrivals per K block (ncu source page, profiles/r01k), which is what kept
-//   its tensor pipe at 70 %.
+// * operand feed.  The trace of the first version of this kernel (profiles/r02a_trace.txt, "tc_trace") showed the MMA warp
+//   waiting for operands 65 % of the time with the producer waiting for free stages 78 % of the time: the L2 -> SM path
+//   delivers ~52 bytes per clock and SM (7.7 KB / clock for the chip, also with the MMAs switched off), and a 128 x 256 x 64
+//   block per CTA wants 32 KB per 512 cycles = 62.5.  So the bytes per MMA cycle are what had to shrink:
+//     - the three dilated taps of a 64-channel block read ONE slab of pad_l + 128 + pad_r rows (18 KB instead of 3 x 16 KB);
+//       tap t is the MMA descriptor view that starts (pad_l + shift_t) rows into the slab -- SWIZZLE_128B keeps its
+//       phase through the descriptor's base-offset field ((start >> 7) & 7);
+//     - N tiles are cut evenly in 16-channel chunks (C = 320: 224 + 224 + 192 gate columns, 176 + 176 res columns, instead of
+//       256 + 256 + 128 and 256 + 96) and every B tile is loaded with a box of exactly its rows: a 128-wide tile cost the
+//       tensor pipe as many cycles as a 256-wide one (its smem operand reads bound it) and its box moved 16 KB for 8;
+//   W1 rows are packed [16 tanh channels | their 16 sigmoid partners] per chunk (tc_pack.py), so any split in whole chunks
+//   keeps the gate local to a tile and a chunk is 32 adjacent accumulator columns.
+// * two operand rings: A slabs (3 x 20 KB) and B tiles (4 x 16 KB), each slot with a full / empty mbarrier pair.
+// * the epilogue warps pull ALL their accumulator columns of a tile into registers first and hand the TMEM buffer back
+//   before any math (tmem_empty right after tcgen05.wait::ld): the tensor pipe never waits for gate / residual math.
 // * staging tiles (2 x 32 KB) are handed around with mbarriers only -- no CTA-wide named barrier in the epilogue: the
 //   16 epilogue warps arrive on `stg_ready`, one manager thread (warp 2) issues every TMA store, recycles the buffer
 //   (`stg_avail`: plain arrive for a gate block, expect_tx + TMA load of the old residual block for a res block) one block
@@ -46,43 +57,67 @@ namespace {
 
 using namespace tcx;
 
-constexpr int TILE_M = 128, TILE_N = 256, TILE_K = 64;
-constexpr int NST = 4;                                   // operand ring stages
-constexpr int A_BYTES = TILE_M * TILE_K * 2;             // 16 KB
-constexpr int B_BYTES = (TILE_N / 2) * TILE_K * 2;       // 16 KB: a CTA of the pair loads half of the B rows
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int TILE_M = 128, TILE_K = 64, ACC_COLS = 256;
+constexpr int NA = 3;                                    // A slab ring: slots of (pad_l + 128 + pad_r rows) x 128 bytes
+constexpr int SLAB_ROWS_MAX = 160;
+constexpr int MAX_NB = 8;                                // B tile ring: as many slots of (widest tile / 2 rows) x 128 bytes as fit
 constexpr int NSTG = 2;                                  // staging blocks: [16-bit plane tile 16 KB | lo plane tile 16 KB]
 constexpr int STG_BYTES = 2 * TILE_M * 128;
-constexpr int COND_ROWS = 16, COND_LD = TILE_N + 4;
-constexpr int COND_BYTES = COND_ROWS * COND_LD * 4;
-constexpr int OFF_STG = NST * STAGE_BYTES;               // 128 KB
-constexpr int OFF_COND = OFF_STG + NSTG * STG_BYTES;     // 192 KB
-constexpr int OFF_BAR = OFF_COND + 2 * COND_BYTES;
-constexpr int L_SMEM_BYTES = 1024 + OFF_BAR + 512;
-static_assert(L_SMEM_BYTES <= 232448, "dynamic shared memory budget (227 KB)");
-static_assert(OFF_STG % 1024 == 0 && STG_BYTES % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+constexpr int COND_ROWS = 15;                            // conditioning rows a 128-row tile can touch at lin_up = 10
+// dynamic shared memory: [barriers 512 B | K tables 1.5 KB | A ring | B ring | staging | 2 conditioning stages], offsets in LayerParams
+constexpr int OFF_A = 3072;
+constexpr int SMEM_LIMIT = 232448;
 constexpr int EW = 16, L_THREADS = 128 + 32 * EW;
-constexpr int MAX_KB1 = 64, MAX_KB2 = 24, MAX_BLK = 24, MAX_LIN = 32;
+constexpr int MAX_TILES = 4, MAX_BLK = 24, MAX_LIN = 32, MAX_PHASE = 3;
 constexpr int TRACE_SLOTS = 384;                          // tile records per role and CTA
+// barrier slots (uint64) at the start of the dynamic shared memory
+constexpr int BAR_FULL_A = 0, BAR_EMPTY_A = BAR_FULL_A + NA, BAR_FULL_B = BAR_EMPTY_A + NA, BAR_EMPTY_B = BAR_FULL_B + MAX_NB;
+constexpr int BAR_TMEM_FULL = BAR_EMPTY_B + MAX_NB, BAR_TMEM_EMPTY = BAR_TMEM_FULL + 2, BAR_STG_AVAIL = BAR_TMEM_EMPTY + 2;
+constexpr int BAR_STG_READY = BAR_STG_AVAIL + NSTG, BAR_COND_FULL = BAR_STG_READY + NSTG, BAR_COND_EMPTY = BAR_COND_FULL + 2;
+constexpr int BAR_ACT_READY = BAR_COND_EMPTY + 2, BAR_END = BAR_ACT_READY + 2;
+static_assert(BAR_END * 8 + 16 <= 512, "barrier block");
 
-struct LKB { int a_col, a_shift, b_col; };
+enum : int { KF_NEW_SLAB = 1, KF_LAST_OF_SLAB = 2, KF_F8 = 4, KF_SCALE_D = 8, KF_OVERWRITE = 16 };
+
+// One B tile (64 K) of an accumulator tile's K loop and the A slab view it multiplies.  The tables are built on the host and
+// copied to shared memory at kernel start: the producer and MMA warps walk them once per tile, and indexed reads of the
+// kernel parameters cost them hundreds of cycles per entry (trace of the first attempt, profiles/README.md).
+struct KEnt {
+    int a_col;      // KF_NEW_SLAB: first column of the slab in the A tensor
+    short a_row;    // KF_NEW_SLAB: first row of the slab relative to the tile's first row (-pad_l, or the tap shift)
+    short a_view;   // rows between the slab's first row and the MMA operand's first row (pad_l + shift, or 0)
+    int b_col;      // first column (K) of the B tile
+    int flags;
+};
+constexpr int MAX_K1 = 64, MAX_K2 = 24;
+constexpr int OFF_KTAB = 512;                            // K tables behind the 512-byte barrier block, in front of the A ring
+static_assert(sizeof(KEnt) == 16 && OFF_KTAB + (MAX_K1 + MAX_K2) * 16 + (MAX_K1 + MAX_K2 + 2) * 8 <= 3072, "K tables");
+
+struct TileDesc {
+    int n0, w;      // first packed column and width (MMA N) of the tile
+    int bmap;       // which of the two B tensor maps has a box of w / 2 rows
+    int c0, nch;    // first chunk and number of chunks (gate: 16 channels = 32 columns; res: 16 columns)
+};
 
 struct alignas(64) LayerParams {
-    CUtensorMap tm_h;        // layer input (rows, 2 cpad), box 64 x 128: gate A operand and the old residual blocks
-    CUtensorMap tm_w1;       // (n1, k1) dilated-conv weights, box 64 x 128
-    CUtensorMap tm_w2;       // (n2, k2) res / skip weights, box 64 x 128
+    CUtensorMap tm_hs;       // layer input (rows, 2 cpad), box 64 x slab rows: gate A operand
+    CUtensorMap tm_h;        // the same tensor, box 64 x 128: old residual blocks
     CUtensorMap tm_scr;      // act scratch (n_groups * 512, 2 cpad), box 64 x 128: gate stores, res A operand
     CUtensorMap tm_hout;     // layer output (rows, 2 cpad), box 64 x 128
-    LKB kb1[MAX_KB1];        // K blocks of a gate tile: first n8_1 e4m3 blocks (K = 128 bytes), then n16_1 16-bit blocks
-    LKB kb2[MAX_KB2];        // K blocks of a res tile (a_shift unused)
-    int n8_1, n16_1, n8_2, n16_2;
+    CUtensorMap tm_w1[2];    // (n1, k1) dilated-conv weights, boxes 64 x (w / 2) for the two tile widths
+    CUtensorMap tm_w2[2];    // (n2, k2) res / skip weights
+    KEnt k1[MAX_K1];         // K loop of a gate tile
+    KEnt k2[MAX_K2];         // K loop of a res tile
+    int n_k1, n_k2, n8_1, n8_2;   // entries of a gate / res tile; the first n8 are e4m3 blocks
+    TileDesc t1[MAX_TILES], t2[MAX_TILES];
+    int n_t1, n_t2;
+    int slab_bytes;          // bytes one gate slab load brings (slab rows x 128)
+    // shared memory carve-up (bytes from the 1024-aligned base)
+    int slab_slot, n_a, off_b, n_b, b_slot, off_stg, off_cond, cond_ld;
     int f16;                 // 16-bit operands are fp16 (MBEXWN_PREC_F16F8), else bf16
-    int n1, n2, tiles_n1, tiles_n2;
     long long rows;
     int tiles_mg;            // 256-row M tiles
-    // staged blocks of one step in epilogue order: kind 0 = gate output (to the scratch), 1 = residual read-modify-write
-    int n_blk;
-    int blk_kind[MAX_BLK], blk_col[MAX_BLK], blk_last_gate[MAX_BLK];
+    int n_gate_blk, n_res_blk;   // staged 64-channel blocks of a step: gate outputs, then residual read-modify-writes
     // gate epilogue
     const float* bias1;
     const float* cond;
@@ -107,9 +142,10 @@ __device__ __forceinline__ uint32_t clk32() {
     return c;
 }
 
-// conditioning rows (+ bias) of a gate tile -> smem stage, by the 32 lanes of warp 3 (see k_wavenet_tc.cu:gate_stage_fill)
-__device__ __forceinline__ void cond_stage_fill(const LayerParams& p, float* buf, int m0, int n0, int width, int lane) {
-    const int w4 = width >> 2, hw = width >> 1;
+// conditioning rows (+ bias) of a gate tile -> smem stage, by the 32 lanes of warp 3.  Stage column j is packed column
+// n0 + j: chunk j / 32, [16 tanh | 16 sigmoid] channels inside a chunk.
+__device__ __forceinline__ void cond_stage_fill(const LayerParams& p, float* buf, int m0, const TileDesc& td, int lane) {
+    const int w4 = td.w >> 2;
     const int rc0 = m0 / p.lin_up;
     const int total = p.cond_rows * w4;
     for (int f0 = lane; f0 < total; f0 += 32 * 4) {
@@ -118,12 +154,13 @@ __device__ __forceinline__ void cond_stage_fill(const LayerParams& p, float* buf
         for (int i = 0; i < 4; ++i) {
             const int f = f0 + 32 * i;
             const int r = f / w4, j = (f - r * w4) * 4;
-            const int ch = (n0 >> 1) + (j < hw ? j : j - hw);
-            const int src_col = (j < hw ? 0 : p.c) + ch;
+            const int within = j & 31;
+            const int ch = 16 * (td.c0 + (j >> 5)) + (within & 15);
+            const int src_col = (within >= 16 ? p.c : 0) + ch;
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (f < total && ch < p.c && rc0 + r < p.cond_total) {
-                b[i] = __ldg(reinterpret_cast<const float4*>(p.bias1 + n0 + j));
+            if (f < total && ch < p.c && rc0 + r < p.cond_total) {           // channel padding: C is a multiple of 4
+                b[i] = __ldg(reinterpret_cast<const float4*>(p.bias1 + td.n0 + j));
                 v[i] = __ldg(reinterpret_cast<const float4*>(p.cond + (long long)(rc0 + r) * 2 * p.c + src_col));
             }
         }
@@ -132,217 +169,163 @@ __device__ __forceinline__ void cond_stage_fill(const LayerParams& p, float* buf
             const int f = f0 + 32 * i;
             const int r = f / w4, j = (f - r * w4) * 4;
             if (f < total)
-                *reinterpret_cast<float4*>(buf + r * COND_LD + j) =
+                *reinterpret_cast<float4*>(buf + r * p.cond_ld + j) =
                     make_float4(v[i].x + b[i].x, v[i].y + b[i].y, v[i].z + b[i].z, v[i].w + b[i].w);
         }
     }
 }
 
+// tanh(t) * sigmoid(s) with three MUFU operations: u = e^-2t, v = e^-s, (1 - u) / ((1 + u) (1 + v)).  u and v are capped so
+// that the denominator stays finite (tanh is +-1 to fp32 precision long before).
+__device__ __forceinline__ float gate_gtu(float t, float s) {
+    const float u = fminf(ex2_approx(t * -2.885390081777927f), 1e18f);
+    const float v = fminf(ex2_approx(s * -1.4426950408889634f), 1e18f);
+    return (1.f - u) * rcp_approx((1.f + u) * (1.f + v));
+}
+
 struct EpiState {
-    uint8_t* stg;
-    uint64_t* stg_avail;
-    uint64_t* stg_ready;
+    uint8_t* smem;           // 1024-byte aligned base of the dynamic shared memory: barriers at its start
+    uint8_t* stg;            // staging tiles
     uint32_t blk;            // staged blocks of this CTA so far
     uint32_t wait_cyc;       // TRACE: cycles spent waiting for staging tiles
 };
+__device__ __forceinline__ uint64_t* epi_bar(const EpiState& es, int idx) { return reinterpret_cast<uint64_t*>(es.smem) + idx; }
 
-// Gate tile: accumulator columns [0, hw) are the tanh pre-activations of channels n0/2 .., columns [hw, 2 hw) their sigmoid
-// partners.  One thread = one row; warp part `part` owns the 16-channel chunk `part` of every 64-channel block.
-template <bool TRACE>
-__device__ __forceinline__ void epi_gate_tile(const LayerParams& p, EpiState& es, const float* cbuf, uint32_t tacc, int row, int m0,
-                                              int n0, int width, int part, int lane) {
-    const int hw = width >> 1;
-    const bool in_range = row < (int)p.rows && !(TRACE && (p.debug & 8));
-    bool valid = false;
-    int rl0 = 0, rl1 = 0;
-    float w0 = 1.f, w1 = 0.f;
-    if (in_range) {
-        const int f = row / p.steps_per_frame;
-        const int u = p.grid.frame_utt[f];
-        if (u >= 0) {
-            valid = true;
-            const int hic = p.grid.utt_end[u] * p.steps_per_frame / p.lin_up;
-            const int rc0 = m0 / p.lin_up, rc = row / p.lin_up;
-            const int un = row - rc * p.lin_up;
-            const int rn = rc + 1 < hic ? rc + 1 : hic - 1;
-            rl0 = rc - rc0;
-            rl1 = rn - rc0;
-            w0 = p.lin_w0[un];
-            w1 = p.lin_w1[un];
+// Eight gate outputs of one row: zt / zs = tanh / sigmoid pre-activations of channels 8 half .. + 7 of a 16-channel chunk,
+// cs0 / cs1 = the two conditioning rows (+ bias) of this row in the smem stage at the chunk's first column
+// ([16 tanh | 16 sigmoid]).  Result: 16 bytes of the fp16 / bf16 plane and the matching bytes of the lo plane in the staging tile.
+__device__ __forceinline__ void gate_half(const LayerParams& p, const float (&zt)[8], const float (&zs)[8], const float* cs0, const float* cs1,
+                                          float w0, float w1, bool valid, uint8_t* t_hi, int sw, int part, int half) {
+    float a[8];
+    if (valid) {
+#pragma unroll
+        for (int v4 = 0; v4 < 2; ++v4) {
+            const int col = 8 * half + 4 * v4;
+            const float4 x0 = *reinterpret_cast<const float4*>(cs0 + col);
+            const float4 x1 = *reinterpret_cast<const float4*>(cs1 + col);
+            const float4 y0 = *reinterpret_cast<const float4*>(cs0 + 16 + col);
+            const float4 y1 = *reinterpret_cast<const float4*>(cs1 + 16 + col);
+            const float xa[4] = {x0.x, x0.y, x0.z, x0.w}, xb[4] = {x1.x, x1.y, x1.z, x1.w};
+            const float ya[4] = {y0.x, y0.y, y0.z, y0.w}, yb[4] = {y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float t = fmaf(xb[e], w1, fmaf(xa[e], w0, zt[4 * v4 + e]));
+                const float sg = fmaf(yb[e], w1, fmaf(ya[e], w0, zs[4 * v4 + e]));
+                if (p.gate == GATE_GTU) {
+                    a[4 * v4 + e] = gate_gtu(t, sg);
+                } else {
+                    if (p.gate == GATE_GFU) t = t * rcp_approx(1.f + fabsf(t));
+                    else if (p.gate == GATE_GSU) t = t * rcp_approx(1.f + sqrtf(fabsf(t)));
+                    a[4 * v4 + e] = t * fast_sigmoid(sg);
+                }
+            }
         }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] = 0.f;                  // guard rows stay zero
     }
-    const float* s0 = cbuf + rl0 * COND_LD;
-    const float* s1 = cbuf + rl1 * COND_LD;
-    const int r = row - m0, sw = r & 7;
-    float zt[16], zs[16];
-#pragma unroll 1
-    for (int k = 0; k < hw / 64; ++k) {
-        const int c0 = 64 * k + 16 * part;                         // tile column of this warp's chunk (tanh half)
-        tmem_ld16(tacc + c0, zt);
-        tmem_ld16(tacc + hw + c0, zs);
-        const uint32_t buf = es.blk % NSTG;
-        {
-            const uint32_t t0 = TRACE ? clk32() : 0u;
-            mbar_wait(&es.stg_avail[buf], (es.blk / NSTG) & 1);
-            if (TRACE) es.wait_cyc += clk32() - t0;
+    // staging tiles, SWIZZLE_128B: 16-byte chunk c of row r sits at r * 128 + ((c ^ (r & 7)) << 4)
+    uint8_t* t_lo = t_hi + TILE_M * 128;
+    if (p.out_f16f8) {
+        uint4 h16;
+        uint2 l8, h8;
+        split_f16f8(a, p.act_lo_scale, h16, l8, h8);
+        *reinterpret_cast<uint4*>(t_hi + (((2 * part + half) ^ sw) << 4)) = h16;
+        *reinterpret_cast<uint2*>(t_lo + ((part ^ sw) << 4) + 8 * half) = l8;                 // lo8: bytes 0 .. 63 of the row
+        *reinterpret_cast<uint2*>(t_lo + (((4 + part) ^ sw) << 4) + 8 * half) = h8;           // hi8: bytes 64 .. 127
+    } else {
+        uint32_t hw4[4], lw4[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(a[e], h0, l0);
+            split_bf16(a[e + 1], h1, l1);
+            hw4[e / 2] = pack2(h0, h1);
+            lw4[e / 2] = pack2(l0, l1);
         }
-        tmem_ld_wait();
+        *reinterpret_cast<uint4*>(t_hi + (((2 * part + half) ^ sw) << 4)) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
+        if (p.write_lo) *reinterpret_cast<uint4*>(t_lo + (((2 * part + half) ^ sw) << 4)) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
+    }
+}
+
+// One residual chunk: v = 16 accumulator values of one row, residual channels n .. n + 15; the old values sit in the staging
+// tile the manager loaded (updated in place, guard rows untouched).
+template <bool TRACE>
+__device__ __forceinline__ void res_chunk(const LayerParams& p, EpiState& es, const float (&v)[16], int n, bool valid, int r, int part,
+                                          int lane) {
+    const uint32_t buf = es.blk % NSTG;
+    {
+        const uint32_t t0 = TRACE ? clk32() : 0u;
+        mbar_wait(epi_bar(es, BAR_STG_AVAIL + buf), (es.blk / NSTG) & 1);
+        if (TRACE) es.wait_cyc += clk32() - t0;
+    }
+    if (valid) {
+        const int sw = r & 7;
         uint8_t* t_hi = es.stg + buf * STG_BYTES + r * 128;
         uint8_t* t_lo = t_hi + TILE_M * 128;
 #pragma unroll
         for (int i = 0; i < 16; i += 8) {
-            if (!in_range) break;
-            float a[8];
-            if (valid) {
-#pragma unroll
-                for (int v4 = 0; v4 < 2; ++v4) {
-                    const int col = c0 + i + 4 * v4;
-                    const float4 x0 = *reinterpret_cast<const float4*>(s0 + col);
-                    const float4 x1 = *reinterpret_cast<const float4*>(s1 + col);
-                    const float4 y0 = *reinterpret_cast<const float4*>(s0 + hw + col);
-                    const float4 y1 = *reinterpret_cast<const float4*>(s1 + hw + col);
-                    const float xa[4] = {x0.x, x0.y, x0.z, x0.w}, xb[4] = {x1.x, x1.y, x1.z, x1.w};
-                    const float ya[4] = {y0.x, y0.y, y0.z, y0.w}, yb[4] = {y1.x, y1.y, y1.z, y1.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float t = fmaf(xb[e], w1, fmaf(xa[e], w0, zt[i + 4 * v4 + e]));
-                        const float sg = fmaf(yb[e], w1, fmaf(ya[e], w0, zs[i + 4 * v4 + e]));
-                        switch (p.gate) {
-                            case GATE_GTU: t = fast_tanh(t); break;
-                            case GATE_GFU: t = t * rcp_approx(1.f + fabsf(t)); break;
-                            case GATE_GSU: t = t * rcp_approx(1.f + sqrtf(fabsf(t))); break;
-                            default: break;
-                        }
-                        a[4 * v4 + e] = t * fast_sigmoid(sg);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) a[e] = 0.f;              // guard rows stay zero
-            }
-            // staging tiles, SWIZZLE_128B: 16-byte chunk c of row r sits at r * 128 + ((c ^ (r & 7)) << 4)
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias2 + n + i)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias2 + n + i) + 1);
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint4* ph16 = reinterpret_cast<uint4*>(t_hi + (((2 * part + (i >> 3)) ^ sw) << 4));
+            float prev[8], o[8];
             if (p.out_f16f8) {
+                uint2* pl8 = reinterpret_cast<uint2*>(t_lo + ((part ^ sw) << 4) + i);
+                join_f16f8(*ph16, *pl8, p.h_lo_inv, prev);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = (n + i + e < p.c) ? prev[e] + (v[i + e] + bv[e]) : 0.f;
                 uint4 h16;
                 uint2 l8, h8;
-                split_f16f8(a, p.act_lo_scale, h16, l8, h8);
-                *reinterpret_cast<uint4*>(t_hi + (((2 * part + (i >> 3)) ^ sw) << 4)) = h16;
-                *reinterpret_cast<uint2*>(t_lo + ((part ^ sw) << 4) + i) = l8;                 // lo8: bytes 0 .. 63 of the row
-                *reinterpret_cast<uint2*>(t_lo + (((4 + part) ^ sw) << 4) + i) = h8;           // hi8: bytes 64 .. 127
+                split_f16f8(o, p.h_lo_scale, h16, l8, h8);
+                *ph16 = h16;
+                *pl8 = l8;
+                *reinterpret_cast<uint2*>(t_lo + (((4 + part) ^ sw) << 4) + i) = h8;
             } else {
-                uint32_t hw4[4], lw4[4];
+                uint4* plo = reinterpret_cast<uint4*>(t_lo + (((2 * part + (i >> 3)) ^ sw) << 4));
+                const uint4 oh = *ph16, ol = *plo;
+                const uint32_t hw[4] = {oh.x, oh.y, oh.z, oh.w}, lw[4] = {ol.x, ol.y, ol.z, ol.w};
+                uint32_t nh[4], nl[4];
 #pragma unroll
-                for (int e = 0; e < 8; e += 2) {
+                for (int w = 0; w < 4; ++w) {
+                    float x[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int idx = 2 * w + e;
+                        const float pv = __bfloat162float(__ushort_as_bfloat16((unsigned short)(hw[w] >> (16 * e)))) +
+                                         __bfloat162float(__ushort_as_bfloat16((unsigned short)(lw[w] >> (16 * e))));
+                        x[e] = (n + i + idx < p.c) ? pv + (v[i + idx] + bv[idx]) : 0.f;
+                    }
                     __nv_bfloat16 h0, l0, h1, l1;
-                    split_bf16(a[e], h0, l0);
-                    split_bf16(a[e + 1], h1, l1);
-                    hw4[e / 2] = pack2(h0, h1);
-                    lw4[e / 2] = pack2(l0, l1);
+                    split_bf16(x[0], h0, l0);
+                    split_bf16(x[1], h1, l1);
+                    nh[w] = pack2(h0, h1);
+                    nl[w] = pack2(l0, l1);
                 }
-                *reinterpret_cast<uint4*>(t_hi + (((2 * part + (i >> 3)) ^ sw) << 4)) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
-                if (p.write_lo)
-                    *reinterpret_cast<uint4*>(t_lo + (((2 * part + (i >> 3)) ^ sw) << 4)) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
+                *ph16 = make_uint4(nh[0], nh[1], nh[2], nh[3]);
+                *plo = make_uint4(nl[0], nl[1], nl[2], nl[3]);
             }
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&es.stg_ready[buf]);
-        ++es.blk;
     }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(epi_bar(es, BAR_STG_READY + buf));
+    ++es.blk;
 }
 
-// Res tile: columns n < res_cols are residual channels (64-column blocks updated inside the staging tile the manager
-// filled with the old values), the c_out columns behind them are accumulated into the WaveNet output in global memory.
-template <bool TRACE>
-__device__ __forceinline__ void epi_res_tile(const LayerParams& p, EpiState& es, uint32_t tacc, int row, int m0, int n0, int width,
-                                             int part, int lane) {
-    const bool in_range = row < (int)p.rows;
-    bool valid = false;
-    if (in_range && !(TRACE && (p.debug & 8))) valid = p.grid.frame_utt[row / p.steps_per_frame] >= 0;
-    const int r = row - m0, sw = r & 7;
-    float v[16];
-#pragma unroll 1
-    for (int g = 0; g * 64 < width; ++g) {
-        const int ct = 64 * g + 16 * part;                          // tile column of this warp's chunk
-        const int n = n0 + ct;
-        const bool rmw = n0 + 64 * g < p.res_cols;
-        if (!rmw && ct >= width) continue;                          // beyond the tile: nothing in TMEM
-        tmem_ld16(tacc + ct, v);
-        if (rmw) {
-            const uint32_t buf = es.blk % NSTG;
-            {
-                const uint32_t t0 = TRACE ? clk32() : 0u;
-                mbar_wait(&es.stg_avail[buf], (es.blk / NSTG) & 1);
-                if (TRACE) es.wait_cyc += clk32() - t0;
-            }
-            tmem_ld_wait();
-            if (valid) {
-                uint8_t* t_hi = es.stg + buf * STG_BYTES + r * 128;
-                uint8_t* t_lo = t_hi + TILE_M * 128;
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias2 + n)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias2 + n) + 1);
-                const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.bias2 + n) + 2), b3 = __ldg(reinterpret_cast<const float4*>(p.bias2 + n) + 3);
-                const float bv[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+// 16 WaveNet-output columns of one row: accumulated in global memory (fp32)
+__device__ __forceinline__ void skip_chunk(const LayerParams& p, const float (&v)[16], int n, long long row, bool valid) {
+    const int sc = n - p.res_cols;
+    if (!valid || sc >= p.skip_c) return;
+    float* dst = p.skip + row * p.skip_ld + sc;
 #pragma unroll
-                for (int i = 0; i < 16; i += 8) {
-                    uint4* ph16 = reinterpret_cast<uint4*>(t_hi + (((2 * part + (i >> 3)) ^ sw) << 4));
-                    float prev[8], o[8];
-                    if (p.out_f16f8) {
-                        uint2* pl8 = reinterpret_cast<uint2*>(t_lo + ((part ^ sw) << 4) + i);
-                        join_f16f8(*ph16, *pl8, p.h_lo_inv, prev);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) o[e] = (n + i + e < p.c) ? prev[e] + (v[i + e] + bv[i + e]) : 0.f;
-                        uint4 h16;
-                        uint2 l8, h8;
-                        split_f16f8(o, p.h_lo_scale, h16, l8, h8);
-                        *ph16 = h16;
-                        *pl8 = l8;
-                        *reinterpret_cast<uint2*>(t_lo + (((4 + part) ^ sw) << 4) + i) = h8;
-                    } else {
-                        uint4* plo = reinterpret_cast<uint4*>(t_lo + (((2 * part + (i >> 3)) ^ sw) << 4));
-                        const uint4 oh = *ph16, ol = *plo;
-                        const uint32_t hw[4] = {oh.x, oh.y, oh.z, oh.w}, lw[4] = {ol.x, ol.y, ol.z, ol.w};
-                        uint32_t nh[4], nl[4];
-#pragma unroll
-                        for (int w = 0; w < 4; ++w) {
-                            float x[2];
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const int idx = 2 * w + e;
-                                const float pv = __bfloat162float(__ushort_as_bfloat16((unsigned short)(hw[w] >> (16 * e)))) +
-                                                 __bfloat162float(__ushort_as_bfloat16((unsigned short)(lw[w] >> (16 * e))));
-                                x[e] = (n + i + idx < p.c) ? pv + (v[i + idx] + bv[i + idx]) : 0.f;
-                            }
-                            __nv_bfloat16 h0, l0, h1, l1;
-                            split_bf16(x[0], h0, l0);
-                            split_bf16(x[1], h1, l1);
-                            nh[w] = pack2(h0, h1);
-                            nl[w] = pack2(l0, l1);
-                        }
-                        *ph16 = make_uint4(nh[0], nh[1], nh[2], nh[3]);
-                        *plo = make_uint4(nl[0], nl[1], nl[2], nl[3]);
-                    }
-                }
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&es.stg_ready[buf]);
-            ++es.blk;
-        } else {
-            tmem_ld_wait();
-            const int sc = n - p.res_cols;                          // 16 consecutive WaveNet-output channels of this row
-            if (valid && sc < p.skip_c) {
-                float* dst = p.skip + (long long)row * p.skip_ld + sc;
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias2 + n + i));
-                    float4 nv = make_float4(v[i] + b4.x, v[i + 1] + b4.y, v[i + 2] + b4.z, v[i + 3] + b4.w);
-                    if (!p.first) {
-                        const float4 ov = *reinterpret_cast<const float4*>(dst + i);
-                        nv.x += ov.x; nv.y += ov.y; nv.z += ov.z; nv.w += ov.w;
-                    }
-                    *reinterpret_cast<float4*>(dst + i) = nv;
-                }
-            }
+    for (int i = 0; i < 16; i += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias2 + n + i));
+        float4 nv = make_float4(v[i] + b4.x, v[i + 1] + b4.y, v[i + 2] + b4.z, v[i + 3] + b4.w);
+        if (!p.first) {
+            const float4 ov = *reinterpret_cast<const float4*>(dst + i);
+            nv.x += ov.x; nv.y += ov.y; nv.z += ov.z; nv.w += ov.w;
         }
+        *reinterpret_cast<float4*>(dst + i) = nv;
     }
 }
 
@@ -352,19 +335,38 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
     constexpr uint64_t DESC_HI = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* ring = smem;                                           // stage s: A at s * STAGE_BYTES, B behind it
-    uint8_t* stg = smem + OFF_STG;
-    float* cond_stage = reinterpret_cast<float*>(smem + OFF_COND);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t* empty = full + NST;
-    uint64_t* tmem_full = empty + NST;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint64_t* stg_avail = tmem_empty + 2;
-    uint64_t* stg_ready = stg_avail + NSTG;
-    uint64_t* cond_full = stg_ready + NSTG;
-    uint64_t* cond_empty = cond_full + 2;
-    uint64_t* act_ready = cond_empty + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(act_ready + 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* full_a = bars + BAR_FULL_A;
+    uint64_t* empty_a = bars + BAR_EMPTY_A;
+    uint64_t* full_b = bars + BAR_FULL_B;
+    uint64_t* empty_b = bars + BAR_EMPTY_B;
+    uint64_t* tmem_full = bars + BAR_TMEM_FULL;
+    uint64_t* tmem_empty = bars + BAR_TMEM_EMPTY;
+    uint64_t* stg_avail = bars + BAR_STG_AVAIL;
+    uint64_t* stg_ready = bars + BAR_STG_READY;
+    uint64_t* cond_full = bars + BAR_COND_FULL;
+    uint64_t* cond_empty = bars + BAR_COND_EMPTY;
+    uint64_t* act_ready = bars + BAR_ACT_READY;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + BAR_END);
+    uint8_t* ring_a = smem + OFF_A;
+    uint8_t* ring_b = smem + p.off_b;
+    uint8_t* stg = smem + p.off_stg;
+    float* cond_stage = reinterpret_cast<float*>(smem + p.off_cond);
+    const int cond_buf = COND_ROWS * p.cond_ld;                    // floats per conditioning stage
+    KEnt* k1 = reinterpret_cast<KEnt*>(smem + OFF_KTAB);
+    KEnt* k2 = k1 + MAX_K1;
+    // the MMA warp's view of the same loops: {A view offset in 16-byte units, flags} (one spare entry behind each table)
+    int2* km1 = reinterpret_cast<int2*>(smem + OFF_KTAB + (MAX_K1 + MAX_K2) * 16);
+    int2* km2 = km1 + MAX_K1 + 1;
+    for (int i = threadIdx.x; i < MAX_K1 + MAX_K2; i += L_THREADS) {
+        const KEnt& e = i < MAX_K1 ? p.k1[i] : p.k2[i - MAX_K1];
+        (i < MAX_K1 ? km1[i] : km2[i - MAX_K1]) = make_int2((int)e.a_view * 8, e.flags);
+    }
+    for (int i = threadIdx.x; i < (MAX_K1 + MAX_K2) * 4; i += L_THREADS) {
+        const int e = i >> 2, w = i & 3;
+        const int* src = e < MAX_K1 ? reinterpret_cast<const int*>(&p.k1[e]) : reinterpret_cast<const int*>(&p.k2[e - MAX_K1]);
+        reinterpret_cast<int*>(k1)[i] = src[w];
+    }
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -375,18 +377,20 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
     // rows of this CTA in M tile j of the pair / in the act scratch
     auto m0_of = [&](int j) { return ((group + n_groups * j) * 2 + rank) * TILE_M; };
     auto scr_of = [&](int j) { return ((group * 2 + (j & 1)) * 2 + rank) * TILE_M; };
-    auto gate_width = [&](int t) { const int w = p.n1 - t * TILE_N; return w > TILE_N ? TILE_N : w; };
-    auto res_width = [&](int t) { const int w = p.n2 - t * TILE_N; return w > TILE_N ? TILE_N : ((w + 15) & ~15); };
 
     if (warp == 0 && elect_one()) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_hs) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_h) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_w1) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_w2) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_w1[0]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_w1[1]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_w2[0]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_w2[1]) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_scr) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&p.tm_hout) : "memory");
     }
     if (warp == 1 && elect_one()) {
-        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < p.n_b; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], 2 * EW);
@@ -407,132 +411,165 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     uint32_t* trc = TRACE ? p.trace + (size_t)blockIdx.x * 3 * TRACE_SLOTS * 4 : nullptr;
+    const int dbg = TRACE ? p.debug : 0;
 
     if (warp == 0) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        // ===== TMA producer =====
-        uint32_t it = 0, tile_it = 0;
-        const uint32_t lfull0 = map_to_cta(smem_u32(&full[0]), 0);
-        auto load_tile = [&](const CUtensorMap* tma, const CUtensorMap* tmb, const LKB* kb, int nkb, int a_row, int b_row) {
-            uint32_t wait_cyc = 0;
-            for (int i = 0; i < nkb; ++i, ++it) {
-                const uint32_t s = it % NST, ph = (it / NST) & 1;
-                const int a_col = kb[i].a_col, a_r = a_row + kb[i].a_shift, b_col = kb[i].b_col;
-                {
-                    const uint32_t t0 = TRACE ? clk32() : 0u;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    if (TRACE) wait_cyc += clk32() - t0;
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        // ===== TMA producer: the whole warp walks the K loops, one elected lane issues =====
+        uint32_t sa = 0, pha = 0, sb = 0, phb = 0, tile_it = 0;     // ring slots and phase parities
+        const uint32_t lfa0 = map_to_cta(smem_u32(&full_a[0]), 0), lfb0 = map_to_cta(smem_u32(&full_b[0]), 0);
+        uint32_t wait_cyc = 0;
+        auto load_a = [&](const CUtensorMap* tma, uint32_t a_bytes, int col, int row) {
+            const uint32_t t0 = TRACE ? clk32() : 0u;
+            mbar_wait(&empty_a[sa], pha ^ 1);
+            if (TRACE) wait_cyc += clk32() - t0;
+            if (elect_one()) {
+                if (dbg & 2) {
+                    if (leader) mbar_arrive(&full_a[sa]);
+                } else {
+                    if (leader) mbar_expect_tx(&full_a[sa], 2 * a_bytes);
+                    tma_load_2d_2sm(tma, lfa0 + sa * 8, ring_a + sa * p.slab_slot, col, row);
                 }
-                if (elect_one()) {
-                    const int dbg = TRACE ? p.debug : 0;
-                    const uint32_t bytes = ((dbg & 1) ? 0 : B_BYTES) + ((dbg & 2) ? 0 : A_BYTES);
-                    if (leader) {
-                        if (bytes) mbar_expect_tx(&full[s], 2 * bytes);
-                        else mbar_arrive(&full[s]);
-                    }
-                    const uint32_t lbar = lfull0 + s * 8;
-                    if (!(dbg & 2)) tma_load_2d_2sm(tma, lbar, ring + s * STAGE_BYTES, a_col, a_r);
-                    if (!(dbg & 1)) tma_load_2d_2sm(tmb, lbar, ring + s * STAGE_BYTES + A_BYTES, b_col, b_row);
+            }
+            __syncwarp();
+            if (++sa == (uint32_t)p.n_a) { sa = 0; pha ^= 1; }
+        };
+        auto load_b = [&](const CUtensorMap* tmb, uint32_t b_bytes, int col, int row) {
+            const uint32_t t0 = TRACE ? clk32() : 0u;
+            mbar_wait(&empty_b[sb], phb ^ 1);
+            if (TRACE) wait_cyc += clk32() - t0;
+            if (elect_one()) {
+                if (dbg & 1) {
+                    if (leader) mbar_arrive(&full_b[sb]);
+                } else {
+                    if (leader) mbar_expect_tx(&full_b[sb], 2 * b_bytes);
+                    tma_load_2d_2sm(tmb, lfb0 + sb * 8, ring_b + sb * p.b_slot, col, row);
                 }
-                __syncwarp();
+            }
+            __syncwarp();
+            if (++sb == (uint32_t)p.n_b) { sb = 0; phb ^= 1; }
+        };
+        auto load_tile = [&](const CUtensorMap* tma, uint32_t a_bytes, const CUtensorMap* tmb, uint32_t b_bytes, const KEnt* ke, int n,
+                             int a_row0, int b_row) {
+            wait_cyc = 0;
+            int4 e = *reinterpret_cast<const int4*>(ke);            // {a_col, a_row | a_view << 16, b_col, flags}
+            for (int i = 0; i < n; ++i) {
+                const int4 cur = e;
+                if (i + 1 < n) e = *reinterpret_cast<const int4*>(ke + i + 1);
+                if (cur.w & KF_NEW_SLAB) load_a(tma, a_bytes, cur.x, a_row0 + (int)(short)(cur.y & 0xffff));
+                load_b(tmb, b_bytes, cur.z, b_row);
             }
             if (TRACE && lane == 0 && tile_it < TRACE_SLOTS) {
                 uint32_t* t = trc + (0 * TRACE_SLOTS + tile_it) * 4;
-                t[0] = clk32(); t[1] = wait_cyc; t[2] = (uint32_t)nkb; t[3] = 0;
+                t[0] = clk32(); t[1] = wait_cyc; t[2] = (uint32_t)n; t[3] = 0;
             }
             ++tile_it;
         };
         for (int j = 0; j <= n_j; ++j) {
             if (j < n_j)
-                for (int t = 0; t < p.tiles_n1; ++t)
-                    load_tile(&p.tm_h, &p.tm_w1, p.kb1, p.n8_1 + p.n16_1, m0_of(j), t * TILE_N + rank * (gate_width(t) >> 1));
+                for (int t = 0; t < p.n_t1; ++t)
+                    load_tile(&p.tm_hs, (uint32_t)p.slab_bytes, &p.tm_w1[p.t1[t].bmap], (uint32_t)(p.t1[t].w >> 1) * 128u, k1, p.n_k1, m0_of(j),
+                              p.t1[t].n0 + rank * (p.t1[t].w >> 1));
             if (j > 0) {
                 // the act of M tile j - 1 must have landed in the scratch (writes of the async proxy, completed by the manager)
                 mbar_wait(&act_ready[(j - 1) & 1], ((j - 1) >> 1) & 1);
                 asm volatile("fence.proxy.async;" ::: "memory");
-                for (int t = 0; t < p.tiles_n2; ++t)
-                    load_tile(&p.tm_scr, &p.tm_w2, p.kb2, p.n8_2 + p.n16_2, scr_of(j - 1), t * TILE_N + rank * (res_width(t) >> 1));
+                for (int t = 0; t < p.n_t2; ++t)
+                    load_tile(&p.tm_scr, (uint32_t)(TILE_M * 128), &p.tm_w2[p.t2[t].bmap], (uint32_t)(p.t2[t].w >> 1) * 128u, k2, p.n_k2, scr_of(j - 1),
+                              p.t2[t].n0 + rank * (p.t2[t].w >> 1));
             }
         }
     } else if (warp == 1) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        // ===== MMA issuer (leader CTA) =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        // ===== MMA issuer (leader CTA): the whole warp walks the K loops, one elected lane issues =====
         if (leader) {
-            uint32_t it = 0, tile_it = 0;
-            const uint32_t ring_base = smem_u32(ring) >> 4;
-            auto mma_tile = [&](int width, int n8, int n16) {
+            uint32_t sa = 0, pha = 0, sb = 0, phb = 0, tile_it = 0;
+            const uint32_t a_base = smem_u32(ring_a), b_base = smem_u32(ring_b);
+            // running descriptor words of the current ring slots (bits 0..13 = shared address >> 4; the upper descriptor word is constant)
+            const uint32_t a_slot16 = (uint32_t)p.slab_slot >> 4, b_slot16 = (uint32_t)p.b_slot >> 4;
+            const uint32_t a_desc0 = a_base >> 4, b_desc0 = b_base >> 4;
+            uint32_t a_desc = a_desc0, b_desc = b_desc0;            // descriptor word of slot sa / sb
+            uint32_t cur_a_desc = a_desc0, cur_a = 0;
+            // one K block: 4 MMAs on (A view, B slot sb), then the slot(s) go back to the producer
+            auto block = [&](const uint32_t tacc, const uint32_t idesc, const int2 e, const int mode, const bool last) {
+                // e.x = A view offset in 16-byte units, e.y = flags; mode 0: e4m3, 1: 16-bit
+                const int flags = e.y;
+                if (flags & KF_NEW_SLAB) {
+                    mbar_wait(&full_a[sa], pha);
+                    cur_a = sa;
+                    cur_a_desc = a_desc;
+                    a_desc += a_slot16;
+                    if (++sa == (uint32_t)p.n_a) { sa = 0; pha ^= 1; a_desc = a_desc0; }
+                }
+                mbar_wait(&full_b[sb], phb);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t da = DESC_HI | (uint64_t)(cur_a_desc + (uint32_t)e.x);
+                    const uint64_t db = DESC_HI | (uint64_t)b_desc;
+                    if (!(dbg & 4)) {
+                        if (mode == 0) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) tc_mma_f8_2sm(tacc, da + 2 * k, db + 2 * k, idesc, !((flags & KF_OVERWRITE) && k == 0));
+                        } else {
+                            if (flags & KF_SCALE_D) tc_mma_f16_sd_2sm(tacc, da, db, idesc);      // rescales the e4m3 products by 2^-15
+                            else tc_mma_bf16_2sm(tacc, da, db, idesc, (flags & KF_OVERWRITE) ? 0u : 1u);
+#pragma unroll
+                            for (int k = 1; k < 4; ++k) tc_mma_bf16_2sm(tacc, da + 2 * k, db + 2 * k, idesc, 1u);
+                        }
+                    }
+                    tc_commit_2sm(&empty_b[sb]);
+                    if (flags & KF_LAST_OF_SLAB) tc_commit_2sm(&empty_a[cur_a]);
+                    if (last) tc_commit_2sm(&tmem_full[(tile_it & 1)]);
+                }
+                __syncwarp();
+                b_desc += b_slot16;
+                if (++sb == (uint32_t)p.n_b) { sb = 0; phb ^= 1; b_desc = b_desc0; }
+            };
+            auto mma_tile = [&](int width, const int2* km, int n8, int n) {
                 const uint32_t idesc = p.f16 ? make_idesc_fmt0(2 * TILE_M, width) : make_idesc(2 * TILE_M, width);
                 const uint32_t as = tile_it & 1, aph = (tile_it >> 1) & 1;
                 const uint32_t t0 = TRACE ? clk32() : 0u;
                 mbar_wait(&tmem_empty[as], aph ^ 1);
                 tc_fence_after();
                 const uint32_t t1 = TRACE ? clk32() : 0u;
-                uint32_t wait_cyc = 0;
-                const uint32_t tacc = tmem_base + as * TILE_N;
-                for (int i = 0; i < n8; ++i, ++it) {
-                    const uint32_t s = it % NST, ph = (it / NST) & 1;
-                    {
-                        const uint32_t w0 = TRACE ? clk32() : 0u;
-                        mbar_wait(&full[s], ph);
-                        if (TRACE) wait_cyc += clk32() - w0;
-                    }
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t da = DESC_HI | (uint64_t)(ring_base + s * (STAGE_BYTES >> 4));
-                        const uint64_t db = da + (A_BYTES >> 4);
-                        if (!(TRACE && (p.debug & 4))) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) tc_mma_f8_2sm(tacc, da + 2 * k, db + 2 * k, idesc, !(i == 0 && k == 0));
-                        }
-                        tc_commit_2sm(&empty[s]);
-                    }
-                    __syncwarp();
+                const uint32_t tacc = tmem_base + as * ACC_COLS;
+                int2 e = km[0];
+                int i = 0;
+                for (; i < n8; ++i) {                               // e4m3 correction blocks
+                    const int2 cur = e;
+                    e = km[i + 1];                                  // the table has one spare entry behind the last
+                    block(tacc, idesc, cur, 0, false);
                 }
-                for (int i = 0; i < n16; ++i, ++it) {
-                    const uint32_t s = it % NST, ph = (it / NST) & 1;
-                    {
-                        const uint32_t w0 = TRACE ? clk32() : 0u;
-                        mbar_wait(&full[s], ph);
-                        if (TRACE) wait_cyc += clk32() - w0;
-                    }
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t da = DESC_HI | (uint64_t)(ring_base + s * (STAGE_BYTES >> 4));
-                        const uint64_t db = da + (A_BYTES >> 4);
-                        if (!(TRACE && (p.debug & 4))) {
-                            if (i == 0 && n8 > 0) tc_mma_f16_sd_2sm(tacc, da, db, idesc);          // rescales the e4m3 products by 2^-15
-                            else tc_mma_bf16_2sm(tacc, da, db, idesc, i != 0);
-#pragma unroll
-                            for (int k = 1; k < 4; ++k) tc_mma_bf16_2sm(tacc, da + 2 * k, db + 2 * k, idesc, 1u);
-                        }
-                        tc_commit_2sm(&empty[s]);
-                        if (i == n16 - 1) tc_commit_2sm(&tmem_full[as]);
-                    }
-                    __syncwarp();
+                for (; i < n - 1; ++i) {                            // 16-bit blocks
+                    const int2 cur = e;
+                    e = km[i + 1];
+                    block(tacc, idesc, cur, 1, false);
                 }
+                block(tacc, idesc, e, 1, true);
                 if (TRACE && lane == 0 && tile_it < TRACE_SLOTS) {
                     uint32_t* t = trc + (1 * TRACE_SLOTS + tile_it) * 4;
-                    t[0] = t0; t[1] = t1; t[2] = clk32(); t[3] = wait_cyc;
+                    t[0] = t0; t[1] = t1; t[2] = clk32(); t[3] = 0;
                 }
                 ++tile_it;
             };
             for (int j = 0; j <= n_j; ++j) {
                 if (j < n_j)
-                    for (int t = 0; t < p.tiles_n1; ++t) mma_tile(gate_width(t), p.n8_1, p.n16_1);
+                    for (int t = 0; t < p.n_t1; ++t) mma_tile(p.t1[t].w, km1, p.n8_1, p.n_k1);
                 if (j > 0)
-                    for (int t = 0; t < p.tiles_n2; ++t) mma_tile(res_width(t), p.n8_2, p.n16_2);
+                    for (int t = 0; t < p.n_t2; ++t) mma_tile(p.t2[t].w, km2, p.n8_2, p.n_k2);
             }
         }
     } else if (warp == 2) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        // ===== staging manager: one thread recycles the staging tiles one block ahead of the epilogue and issues every store =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        // ===== staging manager: one thread recycles the staging tiles ahead of the epilogue and issues every store =====
         if (lane == 0) {
+            const int n_blk = p.n_gate_blk + p.n_res_blk;
             int pj = 0, pe = -1, sj = 0, se = -1;                   // prepare / store cursors over (step, block-of-step)
             auto advance = [&](int& j, int& e) {
                 for (;;) {
-                    if (++e >= p.n_blk) { e = 0; ++j; }
+                    if (++e >= n_blk) { e = 0; ++j; }
                     if (j > n_j) return false;
-                    if (p.blk_kind[e] == 0 ? j < n_j : j > 0) return true;
+                    if (e < p.n_gate_blk ? j < n_j : j > 0) return true;
                 }
             };
             uint32_t pb = 0, sb = 0;                                // blocks prepared / stored
@@ -544,10 +581,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                 while (more_p && pb < sb + NSTG) {
                     tma_store_wait_read();
                     const uint32_t buf = pb % NSTG;
-                    if (p.blk_kind[pe] == 0) {
+                    if (pe < p.n_gate_blk) {
                         mbar_arrive(&stg_avail[buf]);
                     } else {
-                        const int col = p.blk_col[pe], row0 = m0_of(pj - 1);
+                        const int col = 64 * (pe - p.n_gate_blk), row0 = m0_of(pj - 1);
                         mbar_expect_tx(&stg_avail[buf], STG_BYTES);
                         tma_load_2d(&p.tm_h, &stg_avail[buf], stg + buf * STG_BYTES, col, row0);
                         tma_load_2d(&p.tm_h, &stg_avail[buf], stg + buf * STG_BYTES + TILE_M * 128, p.cpad + col, row0);
@@ -565,14 +602,13 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                 const uint32_t buf = sb % NSTG;
                 mbar_wait(&stg_ready[buf], (sb / NSTG) & 1);
                 const uint8_t* t_hi = stg + buf * STG_BYTES;
-                const int col = p.blk_col[se];
-                if (p.blk_kind[se] == 0) {
-                    const int row0 = scr_of(sj);
+                if (se < p.n_gate_blk) {
+                    const int col = 64 * se, row0 = scr_of(sj);
                     tma_store_2d(&p.tm_scr, t_hi, col, row0);
                     if (p.out_f16f8 || p.write_lo) tma_store_2d(&p.tm_scr, t_hi + TILE_M * 128, p.cpad + col, row0);
-                    if (p.blk_last_gate[se]) pending_act = sj;
+                    if (se == p.n_gate_blk - 1) pending_act = sj;
                 } else {
-                    const int row0 = m0_of(sj - 1);
+                    const int col = 64 * (se - p.n_gate_blk), row0 = m0_of(sj - 1);
                     tma_store_2d(&p.tm_hout, t_hi, col, row0);
                     tma_store_2d(&p.tm_hout, t_hi + TILE_M * 128, p.cpad + col, row0);
                 }
@@ -587,32 +623,35 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
             }
         }
     } else if (warp == 3) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ===== conditioning stager: one gate tile ahead of the epilogue warps =====
         uint32_t gt = 0;
         for (int j = 0; j < n_j; ++j)
-            for (int t = 0; t < p.tiles_n1; ++t, ++gt) {
+            for (int t = 0; t < p.n_t1; ++t, ++gt) {
                 const uint32_t b = gt & 1;
                 mbar_wait(&cond_empty[b], ((gt >> 1) & 1) ^ 1);
-                cond_stage_fill(p, cond_stage + b * (COND_ROWS * COND_LD), m0_of(j), t * TILE_N, gate_width(t), lane);
+                cond_stage_fill(p, cond_stage + b * cond_buf, m0_of(j), p.t1[t], lane);
                 mbar_arrive(&cond_full[b]);                         // every lane: its own writes are released
             }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ===== epilogue warps =====
         const int q4 = warp & 3, part = (warp - 4) >> 2;
-        EpiState es{stg, stg_avail, stg_ready, 0u, 0u};
+        EpiState es{smem, stg, 0u, 0u};
         uint32_t tile_it = 0, gt = 0;
         const uint32_t lempty0 = map_to_cta(smem_u32(&tmem_empty[0]), 0);
-        auto begin_tile = [&](uint32_t& t0, uint32_t& t1) -> uint32_t {
+        const int rl = q4 * 32 + lane;                              // row of this thread inside the CTA's 128 rows
+        auto wait_tile = [&](uint32_t& t0, uint32_t& t1) -> uint32_t {
             const uint32_t as = tile_it & 1, aph = (tile_it >> 1) & 1;
             t0 = TRACE ? clk32() : 0u;
             mbar_wait(&tmem_full[as], aph);
             tc_fence_after();
             t1 = TRACE ? clk32() : 0u;
-            return tmem_base + ((uint32_t)(q4 * 32) << 16) + as * TILE_N;
+            return tmem_base + ((uint32_t)(q4 * 32) << 16) + as * ACC_COLS;
         };
-        auto end_tile = [&](uint32_t t0, uint32_t t1, int kind) {
+        // the accumulator values of this warp are in registers: hand the TMEM buffer back to the MMA warp
+        auto release_tile = [&]() {
+            tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -620,6 +659,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                 if (leader) mbar_arrive(&tmem_empty[as]);
                 else mbar_arrive_cluster(lempty0 + as * 8);
             }
+        };
+        auto end_tile = [&](uint32_t t0, uint32_t t1, int kind) {
             if (TRACE && warp == 4 && lane == 0 && tile_it < TRACE_SLOTS) {
                 uint32_t* t = trc + (2 * TRACE_SLOTS + tile_it) * 4;
                 t[0] = t0; t[1] = t1; t[2] = clk32(); t[3] = es.wait_cyc | ((uint32_t)kind << 31);
@@ -630,12 +671,62 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
         for (int j = 0; j <= n_j; ++j) {
             if (j < n_j) {
                 const int m0 = m0_of(j);
-                for (int t = 0; t < p.tiles_n1; ++t, ++gt) {
+                const int row = m0 + rl;
+                const bool in_range = row < (int)p.rows && !(dbg & 8);
+                bool valid = false;
+                int rl0 = 0, rl1 = 0;
+                float w0 = 1.f, w1 = 0.f;
+                if (in_range) {
+                    const int u = p.grid.frame_utt[row / p.steps_per_frame];
+                    if (u >= 0) {
+                        valid = true;
+                        const int hic = p.grid.utt_end[u] * p.steps_per_frame / p.lin_up;
+                        const int rc0 = m0 / p.lin_up, rc = row / p.lin_up;
+                        const int un = row - rc * p.lin_up;
+                        const int rn = rc + 1 < hic ? rc + 1 : hic - 1;
+                        rl0 = rc - rc0;
+                        rl1 = rn - rc0;
+                        w0 = p.lin_w0[un];
+                        w1 = p.lin_w1[un];
+                    }
+                }
+                for (int t = 0; t < p.n_t1; ++t, ++gt) {
                     uint32_t t0, t1;
+                    const TileDesc td = p.t1[t];
+                    const uint32_t tacc = wait_tile(t0, t1);
+                    // chunks c0 + k of this tile with (c0 + k) % 4 == part: at most two (a tile has at most eight); eight channels
+                    // (8 tanh + 8 sigmoid accumulators) at a time.  The TMEM buffer goes back to the MMA warp when the last eight
+                    // are in registers.
+                    const int k0 = (part - td.c0) & 3;
+                    const int nmy = k0 < td.nch ? (k0 + 4 < td.nch ? 2 : 1) : 0;
+                    if (nmy == 0) release_tile();
                     mbar_wait(&cond_full[gt & 1], (gt >> 1) & 1);
-                    const uint32_t tacc = begin_tile(t0, t1);
-                    epi_gate_tile<TRACE>(p, es, cond_stage + (gt & 1) * (COND_ROWS * COND_LD), tacc, m0 + q4 * 32 + lane, m0, t * TILE_N,
-                                         gate_width(t), part, lane);
+                    const float* cbuf = cond_stage + (gt & 1) * cond_buf;
+#pragma unroll 1
+                    for (int k = 0; k < nmy; ++k) {
+                        const int cl = 32 * (k0 + 4 * k);
+                        const uint32_t buf = es.blk % NSTG;
+                        float zt[8], zs[8];
+                        tmem_ld8(tacc + cl, zt);
+                        tmem_ld8(tacc + cl + 16, zs);
+                        {
+                            const uint32_t w0c = TRACE ? clk32() : 0u;
+                            mbar_wait(epi_bar(es, BAR_STG_AVAIL + buf), (es.blk / NSTG) & 1);
+                            if (TRACE) es.wait_cyc += clk32() - w0c;
+                        }
+                        uint8_t* t_hi = stg + buf * STG_BYTES + rl * 128;
+                        tmem_ld_wait();
+                        if (in_range) gate_half(p, zt, zs, cbuf + rl0 * p.cond_ld + cl, cbuf + rl1 * p.cond_ld + cl, w0, w1, valid, t_hi, rl & 7, part, 0);
+                        tmem_ld8(tacc + cl + 8, zt);
+                        tmem_ld8(tacc + cl + 24, zs);
+                        if (k == nmy - 1) release_tile();
+                        else tmem_ld_wait();
+                        if (in_range) gate_half(p, zt, zs, cbuf + rl0 * p.cond_ld + cl, cbuf + rl1 * p.cond_ld + cl, w0, w1, valid, t_hi, rl & 7, part, 1);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(epi_bar(es, BAR_STG_READY + buf));
+                        ++es.blk;
+                    }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&cond_empty[gt & 1]);
                     end_tile(t0, t1, 0);
@@ -643,10 +734,27 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
             }
             if (j > 0) {
                 const int m0 = m0_of(j - 1);
-                for (int t = 0; t < p.tiles_n2; ++t) {
+                const int row = m0 + rl;
+                bool valid = false;
+                if (row < (int)p.rows && !(dbg & 8)) valid = p.grid.frame_utt[row / p.steps_per_frame] >= 0;
+                for (int t = 0; t < p.n_t2; ++t) {
                     uint32_t t0, t1;
-                    const uint32_t tacc = begin_tile(t0, t1);
-                    epi_res_tile<TRACE>(p, es, tacc, m0 + q4 * 32 + lane, m0, t * TILE_N, res_width(t), part, lane);
+                    const TileDesc td = p.t2[t];
+                    const uint32_t tacc = wait_tile(t0, t1);
+                    // 16-column chunks c0 + k with (c0 + k) % 4 == part: at most four (a tile has at most sixteen)
+                    const int k0 = (part - td.c0) & 3;
+                    float v[4][16];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k0 + 4 * k < td.nch) tmem_ld16(tacc + 16 * (k0 + 4 * k), v[k]);
+                    release_tile();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k0 + 4 * k < td.nch) {
+                            const int n = 16 * (td.c0 + k0 + 4 * k);               // first packed column of the chunk
+                            if (n < p.res_cols) res_chunk<TRACE>(p, es, v[k], n, valid, rl, part, lane);
+                            else skip_chunk(p, v[k], n, (long long)row, valid);
+                        }
                     end_tile(t0, t1, 1);
                 }
             }
@@ -662,6 +770,17 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
     }
 }
 
+// N tiles of (almost) equal width: `chunks` chunks of `cw` columns in ceil(chunks * cw / 256) tiles
+int split_tiles(TileDesc* td, int chunks, int cw) {
+    const int nt = (chunks * cw + ACC_COLS - 1) / ACC_COLS;
+    int c0 = 0;
+    for (int t = 0; t < nt; ++t) {
+        const int nch = chunks / nt + (t < chunks % nt ? 1 : 0);
+        td[t] = TileDesc{c0 * cw, nch * cw, 0, c0, nch};
+        c0 += nch;
+    }
+    return nt;
+}
 
 }  // namespace
 
@@ -672,9 +791,10 @@ size_t wn_layer_trace_bytes(int sm_count) { return (size_t)sm_count * 3 * TRACE_
 bool wn_layer_supported(const mbexwn_config_t& c, int cpad, int n_terms, int cond_rows) {
     const int nkb = c.wn_k * (cpad / TILE_K);
     const int per = n_terms == 3 ? 3 : (n_terms == 2 ? 2 : 1);
-    if (nkb * per > MAX_KB1 || (cpad / TILE_K) * per > MAX_KB2) return false;
-    if (cond_rows <= 0 || cond_rows > COND_ROWS - 1) return false;      // the gate epilogue reads its conditioning from the smem stage
+    if (nkb * per > MAX_K1 || (cpad / TILE_K) * per > MAX_K2) return false;
+    if (cond_rows <= 0 || cond_rows > COND_ROWS) return false;      // the gate epilogue reads its conditioning from the smem stage
     if (2 * (cpad / 64) > MAX_BLK) return false;
+    if ((2 * cpad + ACC_COLS - 1) / ACC_COLS > MAX_TILES || (cpad + 32 + ACC_COLS - 1) / ACC_COLS > MAX_TILES) return false;
     return true;
 }
 
@@ -684,77 +804,149 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
     int dev = 0;
     cudaGetDevice(&dev);
     if (!((attr_set >> (dev & 63)) & 1ull)) {
-        cudaError_t e = cudaFuncSetAttribute(wn_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(wn_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(wn_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(wn_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) return fail(std::string("cudaFuncSetAttribute(layer kernel): ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
         attr_set |= 1ull << (dev & 63);
     }
     const int cpad = a.cpad;
     LayerParams p{};
     int rc;
+    // A operand of the gate tiles: one slab of pad_l + 128 + pad_r rows per 64-channel block serves every tap (pad_l a multiple
+    // of 8 rows keeps the slab's first row on the 1024-byte swizzle pattern); dilations too wide for a slab slot load per tap
+    int smin = 0, smax = 0;
+    for (int t = 0; t < a.n_taps; ++t) { if (a.shifts[t] < smin) smin = a.shifts[t]; if (a.shifts[t] > smax) smax = a.shifts[t]; }
+    const int pad_l = (-smin + 7) / 8 * 8, pad_r = smax;
+    const bool slab = st.slab && pad_l + TILE_M + pad_r <= SLAB_ROWS_MAX;
+    const int slab_rows = slab ? pad_l + TILE_M + pad_r : TILE_M;
+    p.slab_bytes = slab_rows * 128;
+    if ((rc = wn_tc_encode_map(st, &p.tm_hs, a.h_in, a.rows, 2 * cpad, slab_rows, error))) return rc;
     if ((rc = wn_tc_encode_map(st, &p.tm_h, a.h_in, a.rows, 2 * cpad, TILE_M, error))) return rc;
     if ((rc = wn_tc_encode_map(st, &p.tm_hout, a.h_out ? a.h_out : a.h_in, a.rows, 2 * cpad, TILE_M, error))) return rc;
-    if ((rc = wn_tc_encode_map(st, &p.tm_w1, a.w1, a.n1, a.k1, TILE_N / 2, error))) return rc;
-    if ((rc = wn_tc_encode_map(st, &p.tm_w2, a.w2, a.n2, a.k2, TILE_N / 2, error))) return rc;
     const int groups_max = a.sm_count / 2;
     if ((rc = wn_tc_encode_map(st, &p.tm_scr, a.scratch, (long long)groups_max * 4 * TILE_M, 2 * cpad, TILE_M, error))) return rc;
 
-    // K-block programs: e4m3 correction blocks first (their products are rescaled by the first 16-bit MMA of a tile)
-    const int ncb = cpad / TILE_K;
-    int n = 0;
-    auto add1 = [&](int a_off, int b_off) {
-        for (int tap = 0; tap < a.n_taps; ++tap)
-            for (int cb = 0; cb < ncb; ++cb) p.kb1[n++] = LKB{cb * TILE_K + a_off, a.shifts[tap], tap * cpad + cb * TILE_K + b_off};
-    };
-    const int b1_lo = a.n_taps * cpad;
-    if (a.n_terms == 2) { add1(cpad, b1_lo); p.n8_1 = n; add1(0, 0); p.n16_1 = n - p.n8_1; }
-    else if (a.n_terms == 3) {
-        // hi * hi, lo * hi, hi * lo per (tap, channel block): the summation order of the two-launch kernel
-        for (int tap = 0; tap < a.n_taps; ++tap)
-            for (int cb = 0; cb < ncb; ++cb) {
-                const int ac = cb * TILE_K, bc = tap * cpad + cb * TILE_K;
-                p.kb1[n++] = LKB{ac, a.shifts[tap], bc};
-                p.kb1[n++] = LKB{ac + cpad, a.shifts[tap], bc};
-                p.kb1[n++] = LKB{ac, a.shifts[tap], bc + b1_lo};
-            }
-        p.n8_1 = 0; p.n16_1 = n;
-    }
-    else { add1(0, 0); p.n8_1 = 0; p.n16_1 = n; }
-    n = 0;
-    auto add2 = [&](int a_off, int b_off) {
-        for (int cb = 0; cb < ncb; ++cb) p.kb2[n++] = LKB{cb * TILE_K + a_off, 0, cb * TILE_K + b_off};
-    };
-    if (a.n_terms == 2) { add2(cpad, cpad); p.n8_2 = n; add2(0, 0); p.n16_2 = n - p.n8_2; }
-    else if (a.n_terms == 3) {
-        for (int cb = 0; cb < ncb; ++cb) {
-            p.kb2[n++] = LKB{cb * TILE_K, 0, cb * TILE_K};
-            p.kb2[n++] = LKB{cb * TILE_K + cpad, 0, cb * TILE_K};
-            p.kb2[n++] = LKB{cb * TILE_K, 0, cb * TILE_K + cpad};
+    // N tiles and their B boxes (at most two distinct widths per GEMM)
+    p.n_t1 = split_tiles(p.t1, cpad / 16, 32);
+    p.n_t2 = split_tiles(p.t2, a.n2 / 16, 16);
+    auto make_b_maps = [&](CUtensorMap* tm, TileDesc* td, int nt, const void* w, int n, int k) -> int {
+        int widths[2] = {td[0].w, 0};
+        for (int t = 0; t < nt; ++t) {
+            if (td[t].w == widths[0]) td[t].bmap = 0;
+            else if (widths[1] == 0 || td[t].w == widths[1]) { widths[1] = td[t].w; td[t].bmap = 1; }
+            else return MBEXWN_ERR_UNSUPPORTED;
         }
-        p.n8_2 = 0; p.n16_2 = n;
+        for (int i = 0; i < 2; ++i) {
+            const int w_i = widths[i] ? widths[i] : widths[0];
+            int r = wn_tc_encode_map(st, &tm[i], w, n, k, w_i / 2, error);
+            if (r) return r;
+        }
+        return (int)MBEXWN_OK;
+    };
+    if (a.n2 % 16) return fail("layer kernel: res / skip columns must be a multiple of 16", MBEXWN_ERR_UNSUPPORTED);
+    if ((rc = make_b_maps(p.tm_w1, p.t1, p.n_t1, a.w1, a.n1, a.k1))) return rc;
+    if ((rc = make_b_maps(p.tm_w2, p.t2, p.n_t2, a.w2, a.n2, a.k2))) return rc;
+
+    // K loops.  Gate: per A plane and 64-channel block one slab, then one B tile per tap (and per B plane); the e4m3
+    // correction blocks come first (their products are rescaled by the first 16-bit MMA of the tile).
+    const int ncb = cpad / TILE_K;
+    const int b1_lo = a.n_taps * cpad;
+    int n = 0;
+    auto gate_group = [&](int a_off, const int* b_offs, int nb, int kflags) {
+        for (int cb = 0; cb < ncb; ++cb) {
+            bool first = true;
+            for (int tap = 0; tap < a.n_taps; ++tap)
+                for (int ib = 0; ib < nb; ++ib) {
+                    KEnt e{};
+                    e.a_col = cb * TILE_K + a_off;
+                    e.b_col = tap * cpad + cb * TILE_K + b_offs[ib];
+                    e.flags = kflags;
+                    if (slab) {
+                        e.a_row = (short)-pad_l;
+                        e.a_view = (short)(pad_l + a.shifts[tap]);
+                        if (first) e.flags |= KF_NEW_SLAB;
+                        if (tap == a.n_taps - 1 && ib == nb - 1) e.flags |= KF_LAST_OF_SLAB;
+                    } else {
+                        e.a_row = (short)a.shifts[tap];
+                        e.a_view = 0;
+                        if (ib == 0) e.flags |= KF_NEW_SLAB;
+                        if (ib == nb - 1) e.flags |= KF_LAST_OF_SLAB;
+                    }
+                    first = false;
+                    p.k1[n++] = e;
+                }
+        }
+    };
+    const int zero = 0;
+    if (a.n_terms == 2) {
+        gate_group(cpad, &b1_lo, 1, KF_F8);
+        const int n8 = n;
+        p.n8_1 = n8;
+        gate_group(0, &zero, 1, 0);
+        p.k1[0].flags |= KF_OVERWRITE;
+        p.k1[n8].flags |= KF_SCALE_D;
+    } else if (a.n_terms == 3) {
+        const int both[2] = {0, b1_lo};
+        gate_group(0, both, 2, 0);                                  // A_hi x (B_hi, B_lo) over the taps of every 64-channel block
+        gate_group(cpad, &zero, 1, 0);                              // then A_lo x B_hi
+        p.k1[0].flags |= KF_OVERWRITE;
+    } else {
+        gate_group(0, &zero, 1, 0);
+        p.k1[0].flags |= KF_OVERWRITE;
     }
-    else { add2(0, 0); p.n8_2 = 0; p.n16_2 = n; }
+    p.n_k1 = n;
+    n = 0;
+    auto res_group = [&](int a_off, const int* b_offs, int nb, int kflags) {
+        for (int cb = 0; cb < ncb; ++cb)
+            for (int ib = 0; ib < nb; ++ib) {
+                KEnt e{};
+                e.a_col = cb * TILE_K + a_off;
+                e.b_col = cb * TILE_K + b_offs[ib];
+                e.flags = kflags | (ib == 0 ? KF_NEW_SLAB : 0) | (ib == nb - 1 ? KF_LAST_OF_SLAB : 0);
+                p.k2[n++] = e;
+            }
+    };
+    if (a.n_terms == 2) {
+        res_group(cpad, &cpad, 1, KF_F8);
+        const int n8 = n;
+        p.n8_2 = n8;
+        res_group(0, &zero, 1, 0);
+        p.k2[0].flags |= KF_OVERWRITE;
+        p.k2[n8].flags |= KF_SCALE_D;
+    } else if (a.n_terms == 3) {
+        const int both[2] = {0, cpad};
+        res_group(0, both, 2, 0);
+        res_group(cpad, &zero, 1, 0);
+        p.k2[0].flags |= KF_OVERWRITE;
+    } else {
+        res_group(0, &zero, 1, 0);
+        p.k2[0].flags |= KF_OVERWRITE;
+    }
+    p.n_k2 = n;
+
+    // shared memory carve-up: barriers, A slab ring, B tile ring (as deep as the rest allows), staging blocks, conditioning stages
+    int wmax = 0, w1max = 0;
+    for (int t = 0; t < p.n_t1; ++t) { if (p.t1[t].w > wmax) wmax = p.t1[t].w; if (p.t1[t].w > w1max) w1max = p.t1[t].w; }
+    for (int t = 0; t < p.n_t2; ++t) if (p.t2[t].w > wmax) wmax = p.t2[t].w;
+    p.slab_slot = (slab_rows * 128 + 1023) / 1024 * 1024;
+    p.b_slot = ((wmax / 2) * 128 + 1023) / 1024 * 1024;
+    p.cond_ld = w1max + 4;
+    const int cond_bytes = (COND_ROWS * p.cond_ld * 4 + 15) / 16 * 16;
+    p.n_a = st.n_a >= 2 && st.n_a <= NA ? st.n_a : NA;
+    const int fixed = 1024 /* alignment slack */ + OFF_A + p.n_a * p.slab_slot + NSTG * STG_BYTES + 2 * cond_bytes;
+    p.n_b = (SMEM_LIMIT - fixed) / p.b_slot;
+    if (p.n_b > MAX_NB) p.n_b = MAX_NB;
+    if (p.n_b < 3) return fail("layer kernel: shared memory too small for the operand rings", MBEXWN_ERR_UNSUPPORTED);
+    p.off_b = OFF_A + p.n_a * p.slab_slot;
+    p.off_stg = p.off_b + p.n_b * p.b_slot;
+    p.off_cond = p.off_stg + NSTG * STG_BYTES;
+    const int smem_bytes = 1024 + p.off_cond + 2 * cond_bytes;
     p.f16 = a.n_terms == 2;
-    p.n1 = a.n1; p.n2 = a.n2;
-    p.tiles_n1 = (a.n1 + TILE_N - 1) / TILE_N;
-    p.tiles_n2 = (a.n2 + TILE_N - 1) / TILE_N;
     p.rows = a.rows;
     const int tiles_m = (int)((a.rows + TILE_M - 1) / TILE_M);
     p.tiles_mg = (tiles_m + 1) / 2;
-    // staged blocks of a step in the order the epilogue warps meet them
-    int nb = 0;
-    for (int t = 0; t < p.tiles_n1; ++t) {
-        const int w = a.n1 - t * TILE_N > TILE_N ? TILE_N : a.n1 - t * TILE_N;
-        for (int k = 0; k < (w / 2) / 64; ++k) { p.blk_kind[nb] = 0; p.blk_col[nb] = t * (TILE_N / 2) + 64 * k; p.blk_last_gate[nb] = 0; ++nb; }
-    }
-    if (nb == 0) return fail("layer kernel: no gate blocks", MBEXWN_ERR_UNSUPPORTED);
-    p.blk_last_gate[nb - 1] = 1;
-    for (int t = 0; t < p.tiles_n2; ++t)
-        for (int g = 0; g < 4; ++g) {
-            const int col = t * TILE_N + 64 * g;
-            if (col < a.res_cols) { p.blk_kind[nb] = 1; p.blk_col[nb] = col; p.blk_last_gate[nb] = 0; ++nb; }
-        }
-    p.n_blk = nb;
+    p.n_gate_blk = cpad / 64;
+    p.n_res_blk = a.res_cols / 64;
     p.bias1 = a.bias1; p.cond = a.cond; p.cond_total = a.cond_total; p.cond_rows = a.cond_rows;
     p.c = a.c; p.cpad = cpad; p.lin_up = a.lin_up; p.gate = a.gate; p.write_lo = a.n_terms == 3; p.steps_per_frame = a.steps_per_frame;
     p.out_f16f8 = a.n_terms == 2;
@@ -770,7 +962,7 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(groups * 2);
     cfg.blockDim = dim3(L_THREADS);
-    cfg.dynamicSmemBytes = L_SMEM_BYTES;
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

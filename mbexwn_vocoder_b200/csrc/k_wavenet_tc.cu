@@ -1484,8 +1484,9 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
             WnLayerArgs a{};
             a.n1 = 2 * cpad; a.k1 = 2 * c.wn_k * cpad;
             a.n2 = (last ? 0 : cpad) + out_pad; a.k2 = 2 * cpad;
-            a.w1 = tensor(n + tc + "W1_" + li, (size_t)a.n1 * a.k1 * 2);
-            a.bias1 = (const float*)tensor(n + "/tc/b1_" + li, (size_t)a.n1 * 4);
+            // W1 rows in the chunk order of the fused kernel: [16 tanh channels | their 16 sigmoid partners] (tc_pack.py)
+            a.w1 = tensor(n + (f8 ? "/tcf8/" : "/tcf/") + "W1_" + li, (size_t)a.n1 * a.k1 * 2);
+            a.bias1 = (const float*)tensor(n + "/tcf/b1_" + li, (size_t)a.n1 * 4);
             a.w2 = tensor(n + tc + "R_" + li, (size_t)a.n2 * a.k2 * 2);
             a.bias2 = (const float*)tensor(n + "/tc/rb_" + li, (size_t)a.n2 * 4);
             if (!a.w1 || !a.bias1 || !a.w2 || !a.bias2) return fail("packed tensor-core weights missing for layer " + li, MBEXWN_ERR_MISSING);

@@ -74,12 +74,12 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));       // not volatile: rematerialised where needed instead of spilled
     return r;
 }
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
     uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
@@ -180,6 +180,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// 32 lanes x 8 columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
         : "r"(taddr)
         : "memory");
 }

@@ -24,6 +24,9 @@ struct WnTcState {
     // option "tc_fused": one persistent kernel per WaveNet layer (k_wavenet_layer.cu) instead of a gate and a res/skip launch:
     // 0 = never, 1 = whenever the geometry allows, 2 (default) = when every CTA pair gets at least two 256-row M tiles
     int fused = 2;
+    int n_a = 3;                // option "tc_ring_a": A slab ring slots of the fused kernel (2 or 3); the B ring takes the rest
+    int slab = 1;               // option "tc_slab": the dilated taps of the fused kernel share one A slab per 64-channel block (0: one
+                                // A tile per tap)
     int last_fused = 0;         // the last forward ran the fused kernel
     void* trace = nullptr;      // option "tc_trace": device buffer of per-tile cycle stamps of the last fused launch
     int trace_on = 0;

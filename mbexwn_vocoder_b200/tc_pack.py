@@ -43,6 +43,20 @@ def gate_permutation(c: int, cpad: int):
     return np.where(is_sig, c + ch, ch), ch < c
 
 
+GATE_CHUNK = 16
+
+
+def gate_permutation_chunked(c: int, cpad: int):
+    """Row order of W1 for the fused layer kernel (csrc/k_wavenet_layer.cu): per 16-channel chunk [16 tanh rows | the 16 matching
+    sigmoid rows], so that any N tile made of whole chunks holds both halves of the gate and a chunk is 32 adjacent
+    accumulator columns.  Returns (source column in the reference's [tanh(C) | sigmoid(C)] order, valid mask)."""
+    n = np.arange(2 * cpad)
+    within = n % (2 * GATE_CHUNK)
+    is_sig = within >= GATE_CHUNK
+    ch = GATE_CHUNK * (n // (2 * GATE_CHUNK)) + within % GATE_CHUNK
+    return np.where(is_sig, c + ch, ch), ch < c
+
+
 def pack_tc_weights(plan: ModelPlan, weights: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
     """bf16 [hi | lo] planes of the packed matrices, fp32 biases."""
     out: Dict[str, torch.Tensor] = {}
@@ -65,6 +79,7 @@ def _tc_block_matrices(wn, weights: Dict[str, np.ndarray]) -> Dict[str, np.ndarr
     cpad = -(-C // TILE_K) * TILE_K
     name = wn.name + "_WNBlock_WN"
     col1, ok1 = gate_permutation(C, cpad)
+    col1f, ok1f = gate_permutation_chunked(C, cpad)
     out: Dict[str, np.ndarray] = {}
     we, be = W.folded(weights, f"{name}/end")                         # (1, C, c_out), (c_out,)
     we64 = we[0].astype(np.float64)
@@ -80,6 +95,12 @@ def _tc_block_matrices(wn, weights: Dict[str, np.ndarray]) -> Dict[str, np.ndarr
         b1[ok1] = b[col1[ok1]]
         out[f"{name}/tc/W1_{i}"] = w1.reshape(2 * cpad, k * cpad)
         out[f"{name}/tc/b1_{i}"] = b1
+        w1f = np.zeros((2 * cpad, k, cpad), dtype=np.float32)
+        w1f[ok1f, :, :C] = np.transpose(w[:, :, col1f[ok1f]], (2, 0, 1))
+        b1f = np.zeros(2 * cpad, dtype=np.float32)
+        b1f[ok1f] = b[col1f[ok1f]]
+        out[f"{name}/tcf/W1_{i}"] = w1f.reshape(2 * cpad, k * cpad)
+        out[f"{name}/tcf/b1_{i}"] = b1f
         r, rb = W.folded(weights, f"{name}/res_skip_{i}")             # (1, C, 2C) or (1, C, C) for the last layer
         last = i == wn.n_layers - 1
         r64 = r[0].astype(np.float64)
@@ -147,7 +168,7 @@ def pack_tc8_weights(plan: ModelPlan, weights: Dict[str, np.ndarray]):
     out: Dict[str, torch.Tensor] = {}
     for key, m in mats.items():
         if "/W1_" in key:
-            out[key.replace("/tc/", "/tc8/")] = f16f8_planes(m, CORR_SHIFT - sh["tc8_h_lo"], CORR_SHIFT)
+            out[key.replace("/tcf/", "/tcf8/").replace("/tc/", "/tc8/")] = f16f8_planes(m, CORR_SHIFT - sh["tc8_h_lo"], CORR_SHIFT)
         elif "/R_" in key:
             out[key.replace("/tc/", "/tc8/")] = f16f8_planes(m, CORR_SHIFT - sh["tc8_a_lo"], CORR_SHIFT)
     return out, sh

@@ -161,6 +161,9 @@ def test_fused_layer_kernel_equals_two_launch_path(engine, speech_setup, precisi
         engine.set_option("tc_fused", mode)
         out, tp = engine.forward(mels, noise=noise, precision=precision, taps=["wn_out", "excitation"])
         res.append((out, tp))
+        res[-1] += (int(engine.lib.mbexwn_last_launch_count(engine._handle)),)
+    # one launch per layer against two: the fused kernel must really have run
+    assert res[0][2] - res[1][2] == plan.wavenet.n_layers, (res[0][2], res[1][2])
     engine.set_option("tc_fused", 2)
     engine.set_option("tc_cta_group", 1)
     for u in range(len(lengths)):
@@ -168,6 +171,30 @@ def test_fused_layer_kernel_equals_two_launch_path(engine, speech_setup, precisi
         tol = 2e-3 if precision == "bf16" else 1e-5          # bf16 re-rounds the activations of every layer
         for a, b, what in ((res[0][1]["wn_out"][u], res[1][1]["wn_out"][u], "wn_out"), (res[0][0][u], res[1][0][u], "waveform")):
             assert np.abs(a - b).max() <= tol * max(np.abs(a).max(), 1e-30), f"{what} of utterance {u}"
+
+
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
+def test_fused_layer_slab_views_equal_per_tap_loads(engine, speech_setup, precision):
+    """The dilated taps of the fused kernel read ONE slab per 64-channel block through row-shifted MMA descriptor views
+    (SWIZZLE_128B with the descriptor's base offset); with "tc_slab" = 0 every tap gets its own TMA tile.  Same products in
+    the same order: the outputs must be bit-identical -- for every dilation of the stack (shifts of 1, 2, 4 and 8 rows)."""
+    hp, plan, w = speech_setup
+    lengths = [400, 150, 1, 400, 37, 400, 400, 260]
+    mels = [synthetic_mel(t, 60 + i) for i, t in enumerate(lengths)]
+    noise = [synthetic_noise(t * plan.steps_per_frame, 60 + i) for i, t in enumerate(lengths)]
+    engine.set_option("tc_cta_group", 2)
+    engine.set_option("tc_fused", 1)
+    res = []
+    for slab in (0, 1):
+        engine.set_option("tc_slab", slab)
+        out, tp = engine.forward(mels, noise=noise, precision=precision, taps=["wn_out"])
+        res.append((out, tp))
+    engine.set_option("tc_fused", 2)
+    engine.set_option("tc_cta_group", 1)
+    for u in range(len(lengths)):
+        assert np.all(np.isfinite(res[1][0][u]))
+        assert np.array_equal(res[0][1]["wn_out"][u], res[1][1]["wn_out"][u]), f"wn_out of utterance {u}"
+        assert np.array_equal(res[0][0][u], res[1][0][u]), f"waveform of utterance {u}"
 
 
 @pytest.mark.parametrize("lengths", [[40], [23, 57, 10, 1, 2]])

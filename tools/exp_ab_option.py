@@ -13,6 +13,7 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 inv = MELInverter("SPEECH", device=0, precision="f16f8")
 eng, plan = inv.model, inv.plan
 eng.set_option("debug_taps", 0)
+eng.set_option("tc_fused", 1)
 mels, noise = bench.synthetic_batch(64, 400, plan.steps_per_frame)
 pb = eng.prepare([400] * 64, precision="f16f8", with_noise=True)
 pb.load(mels, noise)
