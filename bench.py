@@ -10,9 +10,12 @@ same size (independent utterances, no data-path collective; weak scaling); time 
 
 JSON keys beyond the base contract:
   value     whole-job audio-s/s with inputs already resident in HBM (device events around K steps)
-  e2e       the same metric through the host-buffer C-ABI calls (H2D of mel+noise and D2H of audio of every step inside the
-            timing): pipelined form (two buffer sets, copies under the neighbouring step's kernels); e2e.serial = one
-            blocking mbexwn_forward_host per step
+  e2e       the same metric through the product's Python API, NumPy in -> NumPy out: MELInverter.synth_stream over the
+            step's batches (layout scatter into pinned memory, H2D, forward, D2H, per-utterance copies out; two buffer sets,
+            the host work of step i +- 1 under the kernels of step i); e2e.cabi = the C-ABI calls alone on pre-filled pinned
+            buffers (mbexwn_forward_host_begin/_wait), e2e.serial = one blocking mbexwn_forward_host per step
+  config4   (sub-record) BASELINE.json configs[3]: 8192 utterances of 1-30 s, LPT-sharded over the ranks, host prep and the
+            final host gather inside the timing (strong scaling; multi_gpu.run_shard)
   roofline  the dominant kernel (wn_gemm_kernel<EPI_GATE>: dilated-conv tap-GEMM + gate epilogue, one launch per WaveNet
             layer): its algorithmic TFLOP/s over its average launch duration, from CUDA events recorded inside the library
             on the launch stream around every launch (a separate pass after the headline timing)
@@ -32,9 +35,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one wn_gemm_kernel<EPI_GATE> launch from the `ncu --set full` capture
-# committed under profiles/ (bytes per launch; None where no capture exists for the configuration)
-NCU_TRAFFIC = {("config2", "f16f8"): 805.3e6 + 626.1e6}     # profiles/r01k_wn_gemm_full_raw.csv
+def ncu_traffic(workload, precision, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the newest `ncu --set full`
+    capture committed under profiles/ (profiles/ncu_traffic.json, written by tools/ncu_traffic.py); None without one."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        table = json.load(open(path))
+    except Exception:
+        return None
+    hit = table.get(f"{workload}/{precision}/{kernel}")
+    return None if hit is None else float(hit["dram_bytes_per_launch"])
 
 WORKLOADS = {
     # name: (model id, batch, frames, description)
@@ -42,6 +54,18 @@ WORKLOADS = {
     "config3": ("VOICE", 256, 800, "MW-VO-FD batch 256 x 10 s synthetic mels"),
     "config1": ("SPEECH", 1, 400, "MW-SP-FD batch 1 x 5 s synthetic mel"),
 }
+CONFIG4 = {"model": "SING", "utts": 8192, "min_frames": 80, "max_frames": 2400, "seed": 1,
+           "desc": "MW-SI-FD 8192 synthetic utterances of mixed length 1-30 s"}
+
+
+def config_dict(args, world, batch, frames, desc, extra=None):
+    """`config` of the JSON line: identical for the own arm and the reference arm (the driver compares them)."""
+    c = {"workload": f"{args.workload}: {desc}", "per_gpu_batch": batch, "frames": frames, "precision": args.precision,
+         "parallelism": f"dp{world} (independent utterances, no collective)"}
+    if extra:
+        c.update(extra)
+    return c
+
 
 
 def peaks():
@@ -189,17 +213,91 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     audio_s = sample * frames * plan.hop / plan.sample_rate
     value = audio_s * args.steps / dt
-    sample_desc = f"{sample} of {batch} utterances x {frames} frames per step"
+    sample_desc = (f"{sample} of {batch} utterances x {frames} frames per step (linear in the utterances), restated reference "
+                   f"forward (torch-CPU fp32, {threads} threads), not TensorFlow")
     line = {
         "impl": "reference", "metric": "audio-sec generated/sec (24 kHz)", "value": value, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "note": "restated reference forward (torch-CPU), not TensorFlow"},
+        "config": config_dict(args, max(1, args.gpus), batch, frames, desc),
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample_desc},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+def run_config4(args, rank, world, local, dist):
+    """BASELINE.json configs[3]: MW-SI-FD, 8192 synthetic utterances of 1-30 s (T ~ U{80..2400} frames, seed 1), LPT-sharded
+    over the ranks.  Strong scaling: the set is fixed, rank r computes shard r (multi_gpu.run_shard: batches under a frame
+    budget, two pinned buffer sets, host scatter / gather overlapped with the kernels); the timing covers host preparation,
+    copies, kernels and the gather of every waveform into one host buffer per rank plus the ranks' result tables on rank 0."""
+    import torch
+    from mbexwn_vocoder_b200 import sched
+    from mbexwn_vocoder_b200.mel_inverter import MELInverter
+    from mbexwn_vocoder_b200.multi_gpu import imbalance, run_shard
+    inv = MELInverter(CONFIG4["model"], device=local, precision=args.precision, allow_synthetic_weights=True)
+    eng, plan = inv.model, inv.plan
+    eng.set_option("debug_taps", 0)
+    eng.set_option("tc_cta_group", args.cta_group)
+    eng.set_option("tc_fused", args.fused)
+    rng = np.random.default_rng(CONFIG4["seed"])
+    lengths = rng.integers(CONFIG4["min_frames"], CONFIG4["max_frames"] + 1, size=args.config4_utts)
+    shards = sched.lpt_shards(lengths, world)
+    mine = shards[rank]
+    # utterance u = a window of a periodically extended base mel (35 h of distinct mels would be 3 GB of host memory)
+    base = synthetic_batch(1, CONFIG4["max_frames"], plan.steps_per_frame)[0][0]
+    base2 = np.concatenate([base, base])
+    get_mel = lambda u: base2[(-int(u)) % CONFIG4["max_frames"]:(-int(u)) % CONFIG4["max_frames"] + int(lengths[u])]
+    # the gathered result: one pre-faulted host buffer per rank, a waveform = a slice of it
+    offs = np.concatenate(([0], np.cumsum([int(lengths[u]) * plan.hop for u in mine]))).astype(np.int64)
+    result = np.zeros(int(offs[-1]), dtype=np.float32)
+    where = {int(u): k for k, u in enumerate(mine)}
+
+    def sink(u, w):                             # the host gather: the pinned grid's slice lands in the result buffer
+        k = where[int(u)]
+        result[offs[k]:offs[k + 1]] = w
+    # warm-up: a few batches of this rank's shard (allocates the two buffer sets and the workspace)
+    warm = mine[:min(len(mine), 8)]
+    run_shard(inv, get_mel, lengths, warm, {}, args.max_batch_frames, seed=7, keep=False)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    st = run_shard(inv, get_mel, lengths, mine, sink, args.max_batch_frames, seed=7)
+    table = np.array([[u, offs[k], offs[k + 1] - offs[k], float(np.abs(result[offs[k]:offs[k + 1]:997]).sum())]
+                      for k, u in enumerate(mine)], dtype=np.float64)
+    local_s = time.perf_counter() - t0
+    tables = [table]
+    if dist is not None:
+        tables = [None] * world
+        dist.all_gather_object(tables, table)   # the ranks' result tables (id, offset, samples, checksum): the final host gather
+        torch.cuda.synchronize()
+    wall_s = time.perf_counter() - t0
+    stats = [st.wall_s, st.host_prep_s, st.host_gather_s, st.wait_s, local_s, wall_s, float(st.frames), float(st.range_reruns)]
+    if dist is not None:
+        t = torch.tensor(stats, dtype=torch.float64, device="cuda")
+        allst = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allst, t)
+        allst = [x.cpu().numpy() for x in allst]
+    else:
+        allst = [np.array(stats)]
+    wall = max(float(x[5]) for x in allst)
+    n_done = sum(len(tb) for tb in tables)
+    audio_s = float(sum(lengths)) * plan.hop / plan.sample_rate
+    inv.model.close()
+    del inv
+    torch.cuda.empty_cache()
+    return {"workload": f"config4: {CONFIG4['desc']}, LPT over {world} rank(s), batches <= {args.max_batch_frames} frames",
+            "scaling": "strong", "utterances": int(n_done), "audio_s": audio_s, "wall_s": wall, "value": audio_s / wall,
+            "unit": "audio-s/s", "precision": args.precision,
+            "lpt_imbalance": imbalance(lengths, shards),
+            "shard_audio_s": [float(sum(int(lengths[u]) for u in sh)) * plan.hop / plan.sample_rate for sh in shards],
+            "per_rank": [{"wall_s": float(x[0]), "host_scatter_s": float(x[1]), "host_gather_s": float(x[2]),
+                          "host_waiting_for_gpu_s": float(x[3]), "range_reruns": int(x[7])} for x in allst],
+            "gathered": "every waveform in one host buffer per rank (node-local), result tables (id, offset, samples, checksum) "
+                        "of all ranks on every rank",
+            "checksum": float(sum(tb[:, 3].sum() for tb in tables))}
 
 
 def main():
@@ -212,10 +310,13 @@ def main():
                     help="default: f16f8 (fp32-accurate) for config1/2, bf16 for config3 (BASELINE.json configs)")
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the config-4 sub-record (8192 mixed-length utterances, LPT-sharded)")
+    ap.add_argument("--config4-utts", type=int, default=CONFIG4["utts"])
+    ap.add_argument("--max-batch-frames", type=int, default=32768)
     ap.add_argument("--tc-debug", type=int, default=0, help="kernel timing experiments (invalid results): see GemmParams::debug")
     ap.add_argument("--cta-group", type=int, default=2, choices=[1, 2], help="tcgen05 tiles per CTA (1) or per CTA pair (2)")
-    ap.add_argument("--fused", type=int, default=2, choices=[0, 1, 2],
-                    help="WaveNet layer as one persistent kernel: 0 never (gate + res/skip launches), 1 always, 2 auto (default)")
+    ap.add_argument("--fused", type=int, default=1, choices=[0, 1, 2],
+                    help="WaveNet layer as one persistent kernel: 0 never (gate + res/skip launches), 1 whenever supported (default), 2 large batches only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.precision is None:
@@ -238,7 +339,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     model_id, batch, frames, desc = WORKLOADS[args.workload]
-    inv = MELInverter(model_id, device=local, precision=args.precision)
+    inv = MELInverter(model_id, device=local, precision=args.precision, allow_synthetic_weights=True)
     eng, plan = inv.model, inv.plan
     eng.set_option("debug_taps", 0)
     eng.set_option("stage_timing", 0)
@@ -272,6 +373,7 @@ def main():
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = pb.launches() * args.steps
+    ws_bytes = pb.ws_bytes
     # per-stage / per-launch device times over a few more steps (outside the headline timing): CUDA events recorded
     # inside the library on the launch stream at the stage boundaries and around every WaveNet tap-GEMM launch
     eng.set_option("stage_timing", 1)
@@ -288,8 +390,8 @@ def main():
     eng.set_option("stage_timing", 0)
     torch.cuda.synchronize()
 
-    # ---- end to end through the host-buffer C-ABI call -------------------------------------------------
-    # serial form: H2D, forward, D2H and a stream synchronisation inside every call
+    # ---- end to end ----------------------------------------------------------------------------------------
+    # (a) C-ABI, serial: H2D, forward, D2H and a stream synchronisation inside every mbexwn_forward_host call
     for _ in range(2):
         pb.run_host()
     barrier()
@@ -299,8 +401,8 @@ def main():
     torch.cuda.synchronize()
     e2e_serial_s = time.perf_counter() - t0
     barrier()
-    # pipelined form (the serving call, MELInverter.synth_stream): two buffer sets alternate, the copies of step i +- 1
-    # run under the kernels of step i; every step still moves its own inputs and its own waveform
+    # (b) C-ABI, pipelined (mbexwn_forward_host_begin/_wait): two pre-filled pinned buffer sets alternate, the copies of step
+    #     i +- 1 run under the kernels of step i; every step still moves its own inputs and its own waveform
     pb2 = eng.prepare([frames] * batch, precision=args.precision, with_noise=True)
     pb2.load(mels, noise)
     slots = (pb, pb2)
@@ -317,15 +419,39 @@ def main():
     slots[0].wait_host(0)
     slots[1].wait_host(1)
     torch.cuda.synchronize()
+    e2e_cabi_s = time.perf_counter() - t0
+    barrier()
+    del pb2
+    # (c) the product API, NumPy in -> NumPy out: MELInverter.synth_stream over the steps' batches -- layout scatter into
+    #     pinned memory, H2D, forward (noise channel drawn in-kernel like the reference draws it inside the graph), D2H and the
+    #     copies of the waveforms out of the pinned grid are all inside the timing
+    def api_steps(n):
+        got = 0
+        for waves in inv.synth_stream(mels for _ in range(n)):
+            got += sum(w.size for w in waves)
+        return got
+    api_steps(3)
+    barrier()
+    t0 = time.perf_counter()
+    n_samples = api_steps(args.steps)
+    torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    assert n_samples == args.steps * batch * frames * plan.hop
+    api_h2d = (batch * frames + eng.halo * (batch + 1)) * plan.mel_channels * 4
+    api_d2h = (batch * frames + eng.halo * (batch + 1)) * plan.hop * 4
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s, e2e_serial_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, e2e_s, e2e_serial_s, e2e_cabi_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, e2e_serial_s = float(t[0]), float(t[1]), float(t[2])
+        dev_ms, e2e_s, e2e_serial_s, e2e_cabi_s = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+
+    # ---- BASELINE.json configs[3]: the mixed-length set, LPT-sharded over the ranks (strong scaling) ------------------
+    config4 = None
+    if not args.no_config4 and args.workload == "config2":
+        config4 = run_config4(args, rank, world, local, dist if world > 1 else None)
 
     audio_s_step = batch * frames * plan.hop / plan.sample_rate          # per rank
     value = world * audio_s_step * args.steps / (dev_ms / 1e3)
@@ -358,14 +484,14 @@ def main():
         gate_ms = wn_ms / L
         achieved = wn_flops / L / (gate_ms / 1e3) / 1e12
         kernel = "fp32 SIMT WaveNet layer (conv1d + gate + res/skip kernels)"
-    ncu_traffic = NCU_TRAFFIC.get((args.workload, args.precision))
+    traffic = ncu_traffic(args.workload, args.precision, "wn_layer_kernel" if fused_layer else "wn_gemm_kernel<EPI_GATE>")
     roofline = {
         "bound": "tensor", "kernel": kernel,
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "peak_source": f"{pk['source']} bf16 dense sustained (MEASURED_PEAKS.json; kernel timed inside a long step)",
         "executed_flop_factor": factor, "frac_executed": achieved * factor / peak,
         "launches_per_step": L, "avg_launch_ms": gate_ms, "algorithmic_flops_per_launch": gate_flops,
-        "traffic": ncu_traffic,
+        "traffic": traffic,
         "wavenet_stage": {"ms": wn_ms, "gate_ms": wn_launch["gate"], "resskip_ms": wn_launch["resskip"],
                           "algorithmic_tflops": wn_flops / (wn_ms / 1e3) / 1e12,
                           "frac_executed": wn_flops * factor / (wn_ms / 1e3) / 1e12 / peak},
@@ -389,18 +515,23 @@ def main():
                   "bf16x3": "bf16x3 (bf16 hi/lo split, fp32 accumulate; fp32-accurate)", "bf16": "bf16",
                   "fp32": "f32"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "per_gpu_batch": batch, "frames": frames,
-                   "precision": args.precision, "tc_cta_group": args.cta_group, "fused_layer_kernel": bool(fused_layer), "parallelism": f"dp{world} (independent utterances, no collective)",
-                   "l2": (f"per-step working set {pb.ws_bytes / 1e6:.0f} MB of activations "
-                          + (">> 126 MB L2; no flush needed" if pb.ws_bytes > 4 * 126e6 else "(comparable to the 126 MB L2: not flushed, "
-                             "treat as an L2-warm figure)"))},
-        "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": pb.h2d_bytes, "d2h_bytes_per_step": pb.d2h_bytes,
+        "config": config_dict(args, world, batch, frames, desc),
+        "kernel_options": {"tc_cta_group": args.cta_group, "fused_layer_kernel": bool(fused_layer),
+                           "l2": (f"per-step working set {ws_bytes / 1e6:.0f} MB of activations "
+                                  + (">> 126 MB L2; no flush needed" if ws_bytes > 4 * 126e6 else "(comparable to the 126 MB L2: not "
+                                     "flushed, treat as an L2-warm figure)"))},
+        "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": api_h2d, "d2h_bytes_per_step": api_d2h,
                 "ms_per_step": 1e3 * e2e_s / args.steps,
-                "call": "mbexwn_forward_host_begin/_wait (pipelined over two buffer sets; copies of every step inside the timing)",
+                "call": "MELInverter.synth_stream: list of NumPy mels in, list of NumPy waveforms out (scatter into pinned memory, "
+                        "H2D, forward, D2H and the copies out inside the timing; two buffer sets)",
+                "cabi": {"value": world * audio_s_step * args.steps / e2e_cabi_s, "ms_per_step": 1e3 * e2e_cabi_s / args.steps,
+                         "call": "mbexwn_forward_host_begin/_wait on pre-filled pinned buffers (explicit noise input)"},
                 "serial": {"value": world * audio_s_step * args.steps / e2e_serial_s, "ms_per_step": 1e3 * e2e_serial_s / args.steps,
                            "call": "mbexwn_forward_host (H2D, forward, D2H, synchronise per call)"}},
         "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "stages": stages,
     }
+    if config4 is not None:
+        line["config4"] = config4
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -414,7 +545,7 @@ def main():
                 sweep[str(n)] = cpu_oracle_throughput(model_id, frames, 1, 1, n)[0]
         line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
                                 "sample": f"{sample} of {batch} utterances x {frames} frames, median of 2 runs "
-                                          f"({med:.1f} s each), restated reference forward (torch-CPU fp32)",
+                                          f"({med:.1f} s each), restated reference forward (torch-CPU fp32), not TensorFlow",
                                 "by_threads": sweep}
     if rank == 0:
         print(json.dumps(line))

@@ -42,12 +42,13 @@ def _write(outfile, audio, rate, fmt):
 
 
 def main(model_id, input_mell_files, output_dir, use_gpu=True, format=None, verbose=False, seed=42, num_threads=2,
-         quiet=False, precision="f16f8", device=0):
+         quiet=False, precision="f16f8", device=0, devices=None, max_batch_frames=32768, synthetic_weights=False):
     format = format or default_format()
     if seed >= 0:
         np.random.seed(seed)
     MelInv = mel_inverter.MELInverter(model_id_or_path=model_id, device=device, precision=precision,
-                                      seed=seed if seed >= 0 else 42, verbose=verbose)
+                                      seed=seed if seed >= 0 else 42, verbose=verbose, devices=devices,
+                                      allow_synthetic_weights=True if synthetic_weights else None)
     if output_dir and not os.path.exists(output_dir):
         os.makedirs(output_dir)
 
@@ -61,7 +62,9 @@ def main(model_id, input_mell_files, output_dir, use_gpu=True, format=None, verb
         outfiles.append(outfile)
 
     start_time = time.time()
-    audios = MelInv.synth_batch(mels)
+    # the reference loops over the files one by one (bin/resynth_mel.py:72-104); here the set is LPT-sharded over the devices
+    # and cut into batches under a frame budget, so memory does not grow with the number of files
+    audios = MelInv.synth_many(mels, max_batch_frames=max_batch_frames)
     end_time = time.time()
     total = sum(a.size for a in audios)
     if verbose:
@@ -102,6 +105,12 @@ def build_parser():
     parser.add_argument("--precision", default="f16f8", choices=["f16f8", "bf16x3", "bf16", "fp32"],
                         help="arithmetic of the WaveNet contractions (Def: %(default)s, fp32-accurate)")
     parser.add_argument("--device", default=0, type=int, help="CUDA device index (Def: %(default)s)")
+    parser.add_argument("--devices", default=None, type=int, nargs="+",
+                        help="several CUDA devices: the files are sharded over them by length (longest-processing-time first)")
+    parser.add_argument("--max_batch_frames", default=32768, type=int,
+                        help="mel frames (incl. guard frames) per forward call and GPU (Def: %(default)s, about 7 minutes of audio)")
+    parser.add_argument("--synthetic_weights", action="store_true",
+                        help="accept a model directory without weights and run on random-initialised ones (tests only)")
     return parser
 
 

@@ -230,10 +230,10 @@ MBEXWN_API int mbexwn_last_launch_count(mbexwn_handle_t h);
  * "fuse_tail" (default 1): the LinInterp -> 1x1 -> LinInterp end of the F0 sub-net runs as one kernel;
  * "stop_after_f0" (default 0): return after the F0 sub-net (tap "F0"), for the F0 pass of chunked long-form synthesis;
  * "tc8_h_lo" / "tc8_a_lo": log2 scale of the e4m3 lo8 planes of the residual stream / gated activations (F16F8);
- * "tc_fused" (default 2): one persistent kernel per WaveNet layer (dilated conv, gate, res/skip 1x1 and the residual update in one
- *   launch; the gated activations stay in L2) -- 0: never (a gate and a res/skip launch per layer), 1: whenever the geometry allows,
- *   2: when every CTA pair gets at least two 256-row tiles (short batches keep the two-launch schedule that spreads one M tile
- *   over several CTAs);
+ * "tc_fused" (default 1): one persistent kernel per WaveNet layer (dilated conv, gate, res/skip 1x1 and the residual update in one
+ *   launch; the gated activations stay in L2) -- 0: never (a gate and a res/skip launch per layer), 1: whenever the geometry allows
+ *   (CTA pairs, conditioning rows fit the shared-memory stage), 2: only when every CTA pair gets at least two 256-row tiles.  The two
+ *   paths agree to ~1e-5 of peak (different K order), so the default never switches with the batch size;
  * "tc_slab" (default 1): the dilated taps of the fused kernel share one A slab per 64-channel block (row-shifted MMA operand
  *   views of one shared-memory tile); 0: one TMA tile per tap (bit-identical results, more L2 -> SM traffic);
  * "tc_trace" (default 0): k > 0 records per-tile cycle stamps of the fused kernel of layer k - 1 (mbexwn_tc_trace_read). */
@@ -250,6 +250,14 @@ MBEXWN_API int mbexwn_stage_ms(mbexwn_handle_t h, float* ms);
  * (wn_n_blocks > 1) reports the launches of its last block; mbexwn_stage_ms covers all blocks in the "wavenet" stage. */
 MBEXWN_API int mbexwn_wavenet_launch_ms(mbexwn_handle_t h, float* gate_ms, float* resskip_ms, int32_t* n_layers);
 /* With "tc_fused" in effect a layer is ONE launch: gate_ms then holds the sum of the fused launches and resskip_ms is 0. */
+
+/* Range guard of MBEXWN_PREC_F16F8.  The main operand plane of that path is fp16 and the hi8 correction plane is e4m3(x),
+ * unscaled and saturating at 448: a model whose residual stream leaves that range would silently drop to plain-fp16 accuracy
+ * (no non-finite sample marks it).  The kernels that write the residual stream (start conv, res/skip epilogue) therefore OR
+ * their findings into a sticky word: bit 0 = |x| > 448 seen, bit 1 = |x| > 60000 seen.  Valid once the forward's stream
+ * has been synchronised (mbexwn_forward_host, mbexwn_forward_host_wait); `reset` != 0 clears it.  The Python MELInverter
+ * re-runs a flagged batch on MBEXWN_PREC_BF16X3 (same accuracy class, fp32 exponent range) with a note on stderr. */
+MBEXWN_API int mbexwn_range_status(mbexwn_handle_t h, int32_t* flags, int32_t reset);
 
 /* Profiling aid ("tc_trace"): copies the cycle stamps of the traced fused-layer launch to `out` (host, n_words uint32);
  * layout [cta][role: 0 producer, 1 MMA issuer, 2 epilogue warp][384 tiles][4 words].  Returns the words written or < 0. */

@@ -41,6 +41,7 @@ struct mbexwn_handle_s {
     cudaEvent_t ev_h2d[2] = {}, ev_done[2] = {}, ev_d2h[2] = {};
     bool pipe_ready = false;
     bool slot_busy[2] = {false, false};
+    int* range_flag = nullptr;   // host-mapped word the f16f8 kernels OR their range findings into (mbexwn_range_status)
 };
 
 namespace mbx {
@@ -734,6 +735,13 @@ int mbexwn_create(const mbexwn_config_t* cfg, mbexwn_handle_t* out) {
             rate *= bl.up;
         }
     }
+    // sticky range-guard word of the f16f8 path in mapped host memory: the kernels write it, the host reads it after a
+    // synchronisation without any copy
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h->range_flag), 64, cudaHostAllocMapped) == cudaSuccess && h->range_flag) {
+        *h->range_flag = 0;
+        int* dptr = nullptr;
+        if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), h->range_flag, 0) == cudaSuccess) h->tc.range_flag = dptr;
+    }
     *out = h;
     return MBEXWN_OK;
 }
@@ -747,6 +755,7 @@ void mbexwn_destroy(mbexwn_handle_t h) {
         cudaStreamDestroy(h->copy_out);
     }
     mbx::wn_tc_destroy(h->tc);
+    if (h->range_flag) cudaFreeHost(h->range_flag);
     delete h;
 }
 
@@ -885,6 +894,13 @@ int mbexwn_wavenet_launch_ms(mbexwn_handle_t h, float* gate_ms, float* resskip_m
     int rc = mbx::wn_tc_launch_ms(h->tc, gate_ms, resskip_ms, &n);
     if (rc) return mbx::fail(h, rc, "no WaveNet launch timing recorded (set option stage_timing, tensor-core precision)");
     *n_layers = n;
+    return MBEXWN_OK;
+}
+
+int mbexwn_range_status(mbexwn_handle_t h, int32_t* flags, int32_t reset) {
+    if (!h || !flags) return MBEXWN_ERR_INVALID;
+    *flags = h->range_flag ? *reinterpret_cast<volatile int*>(h->range_flag) : 0;
+    if (reset && h->range_flag) *reinterpret_cast<volatile int*>(h->range_flag) = 0;
     return MBEXWN_OK;
 }
 

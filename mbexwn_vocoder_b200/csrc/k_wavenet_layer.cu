@@ -131,6 +131,7 @@ struct alignas(64) LayerParams {
     float* skip;
     int skip_ld, skip_c, res_cols, first;
     FrameGrid grid;
+    int* range_flag;         // f16f8 range guard (tc_common.cuh: range_check8), or nullptr
     uint32_t* trace;         // TRACE builds: [cta][role 0..2][TRACE_SLOTS][4]
     int debug;               // TRACE builds only, timing experiments (results are wrong): 1 = no B loads, 2 = no A loads,
                              // 4 = no MMAs are issued, 8 = the epilogue skips its math
@@ -274,6 +275,7 @@ __device__ __forceinline__ void res_chunk(const LayerParams& p, EpiState& es, co
                 join_f16f8(*ph16, *pl8, p.h_lo_inv, prev);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] = (n + i + e < p.c) ? prev[e] + (v[i + e] + bv[e]) : 0.f;
+                range_check8(o, p.range_flag);
                 uint4 h16;
                 uint2 l8, h8;
                 split_f16f8(o, p.h_lo_scale, h16, l8, h8);
@@ -954,6 +956,7 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
     for (int u = 0; u < a.lin_up && u < MAX_LIN; ++u) { p.lin_w0[u] = a.lin_w0[u]; p.lin_w1[u] = a.lin_w1[u]; }
     p.bias2 = a.bias2; p.skip = a.skip; p.skip_ld = a.skip_ld; p.skip_c = a.skip_c; p.res_cols = a.res_cols; p.first = a.first;
     p.grid = a.grid;
+    p.range_flag = a.range_flag;
     p.trace = reinterpret_cast<uint32_t*>(a.trace);
     p.debug = a.trace ? st.debug : 0;
 

@@ -137,6 +137,7 @@ struct alignas(64) GemmParams {
     int res_cols;           // cpad, or 0 for the last layer (skip only)
     int first;              // skip = instead of +=
     FrameGrid grid;
+    int* range_flag;        // f16f8 range guard (tc_common.cuh: range_check8), or nullptr
     int debug;              // timing experiments only (option "tc_debug"): 1 = epilogues skip their math and stores,
                             // 2 = every tile loads the operands of tile 0 (L2-resident feed), 4 = no MMAs are issued,
                             // 8 = epilogues skip their global stores, 16 = no gate math, 32 = res/skip does not read h
@@ -521,6 +522,7 @@ __device__ __forceinline__ void resskip_store(const GemmParams& p, const ResSkip
                 join_f16f8(old[ps], make_uint2(old[4 + ps].x, old[4 + ps].y), p.in_lo_inv, prev);
 #pragma unroll
                 for (int idx = 0; idx < 8; ++idx) o[idx] = (ch0 + idx < p.c) ? prev[idx] + (xv[idx] + bv[idx]) : 0.f;
+                range_check8(o, p.range_flag);
                 uint4 h16;
                 uint2 l8, h8;
                 split_f16f8(o, p.out_lo_scale, h16, l8, h8);
@@ -649,6 +651,7 @@ __device__ __forceinline__ void epi_resskip_tma(const GemmParams& p, RsPipe& rp,
                         join_f16f8(*ph16, *pl8, p.in_lo_inv, prev);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) o[e] = (n + i + e < p.c) ? prev[e] + (v[i + e] + bv[i + e]) : 0.f;
+                        range_check8(o, p.range_flag);
                         uint4 h16;
                         uint2 l8, h8;
                         split_f16f8(o, p.out_lo_scale, h16, l8, h8);
@@ -1122,7 +1125,7 @@ template <int CIN_MAX>
 __global__ void __launch_bounds__(START_LANES * 48, (CIN_MAX > 0 && CIN_MAX <= 8) ? 2 : 1)
 start_pack_kernel(const float* __restrict__ x, int ld_x, int cin, const float* __restrict__ w, const float* __restrict__ b,
                   __nv_bfloat16* __restrict__ out, long long rows, int c, int cpad, int rate, FrameGrid g,
-                  int f16f8, float lo_scale) {
+                  int f16f8, float lo_scale, int* range_flag) {
     extern __shared__ float sx[];                       // [START_ROWS][cin] inputs, zero for guard rows
     __shared__ int svalid[START_ROWS];
     const int groups = cpad >> 3;                       // <= 48 (cpad <= 384)
@@ -1178,6 +1181,7 @@ start_pack_kernel(const float* __restrict__ x, int ld_x, int cin, const float* _
         if (f16f8) {
             uint4 h16;
             uint2 l8, h8;
+            range_check8(v, range_flag);
             split_f16f8(v, lo_scale, h16, l8, h8);
             uint8_t* p8 = reinterpret_cast<uint8_t*>(out + r * 2 * cpad) + f8_off(cpad, ch0);
             *reinterpret_cast<uint4*>(out + r * 2 * cpad + ch0) = h16;
@@ -1431,13 +1435,13 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         const unsigned nblk = (unsigned)((rows + START_ROWS - 1) / START_ROWS), nthr = (unsigned)(START_LANES * (cpad >> 3));
         if (c.wn_cin <= 8)
             start_pack_kernel<8><<<nblk, nthr, smem, s>>>(wn_in, ld_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g,
-                                                          f8 ? 1 : 0, h_lo);
+                                                          f8 ? 1 : 0, h_lo, f8 ? st.range_flag : nullptr);
         else if (c.wn_cin <= START_MAX_CIN)
             start_pack_kernel<16><<<nblk, nthr, smem, s>>>(wn_in, ld_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g,
-                                                           f8 ? 1 : 0, h_lo);
+                                                           f8 ? 1 : 0, h_lo, f8 ? st.range_flag : nullptr);
         else
             start_pack_kernel<0><<<nblk, nthr, smem, s>>>(wn_in, ld_in, c.wn_cin, w, b, h2, rows, c.wn_c, cpad, c.steps_per_frame, g,
-                                                          f8 ? 1 : 0, h_lo);
+                                                          f8 ? 1 : 0, h_lo, f8 ? st.range_flag : nullptr);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(std::string("start conv: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
         *launches += 1;
@@ -1501,6 +1505,7 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
             a.act_lo_scale = a_lo; a.h_lo_scale = h_lo;
             a.skip = wn_out; a.skip_ld = out_pad; a.skip_c = out_pad; a.res_cols = last ? 0 : cpad; a.first = i == 0;
             a.grid = g; a.sm_count = im->sm_count;
+            a.range_flag = f8 ? st.range_flag : nullptr;
             a.trace = nullptr;
             if (st.trace_on == i + 1) {
                 if (!st.trace && cudaMalloc(&st.trace, wn_layer_trace_bytes(im->sm_count)) != cudaSuccess) return fail("trace buffer", MBEXWN_ERR_CUDA);
@@ -1555,6 +1560,7 @@ int wn_tc_forward(WnTcState& st, const mbexwn_config_t& c, const FrameGrid& g, i
         p2.skip = wn_out; p2.skip_ld = out_pad; p2.skip_c = out_pad;
         p2.c = c.wn_c; p2.cpad = cpad; p2.res_cols = last ? 0 : cpad; p2.first = i == 0;
         p2.steps_per_frame = c.steps_per_frame; p2.grid = g; p2.debug = st.debug;
+        p2.range_flag = f8 ? st.range_flag : nullptr;
         e = launch_gemm<EPI_RESSKIP>(im, p2, s);
         if (e != cudaSuccess) return fail(std::string("res/skip GEMM: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
         if (ev) cudaEventRecord(ev[st.n_timed++], s);

@@ -230,6 +230,13 @@ __device__ __forceinline__ void split_f16f8(const float (&a)[8], float lo_scale,
     hi8 = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
 }
 
+// Range guard of the f16f8 operand planes: the hi8 plane is e4m3(x), unscaled and saturating at 448; the main plane is fp16.
+__device__ __forceinline__ void range_check8(const float (&a)[8], int* flag) {
+    const float m = fmaxf(fmaxf(fmaxf(fabsf(a[0]), fabsf(a[1])), fmaxf(fabsf(a[2]), fabsf(a[3]))),
+                          fmaxf(fmaxf(fabsf(a[4]), fabsf(a[5])), fmaxf(fabsf(a[6]), fabsf(a[7]))));
+    if (m > 448.f && flag) atomicOr(flag, m > 60000.f ? 3 : 1);
+}
+
 // byte offset of the e4m3 lo8 group of channel ch (a multiple of 8) inside a row of 4 * cpad bytes; hi8 sits 64 bytes further
 __device__ __forceinline__ int f8_off(int cpad, int ch) { return 2 * cpad + ((ch >> 6) << 7) + (ch & 63); }
 

@@ -22,8 +22,13 @@ struct WnTcState {
     void* events = nullptr;     // cudaEvent_t[2 * MBEXWN_MAX_LAYERS + 1]
     int debug = 0;              // option "tc_debug": timing experiments (results are wrong), see GemmParams::debug
     // option "tc_fused": one persistent kernel per WaveNet layer (k_wavenet_layer.cu) instead of a gate and a res/skip launch:
-    // 0 = never, 1 = whenever the geometry allows, 2 (default) = when every CTA pair gets at least two 256-row M tiles
-    int fused = 2;
+    // 0 = never, 1 (default) = whenever the geometry allows, 2 = only when every CTA pair gets at least two 256-row M tiles.
+    // The two paths sum the same products in a different K order (agreement ~1e-5 of peak), so a batch-size dependent
+    // choice would make an utterance's samples depend on the batch it travels in: the default does not switch.
+    int fused = 1;
+    // MBEXWN_PREC_F16F8 range guard: kernels set bit 0 of this (host-mapped) word when a residual-stream value leaves the range of
+    // the unscaled e4m3 hi8 plane (|x| > 448: the correction product would silently lose its meaning), bit 1 beyond 60000 (fp16)
+    int* range_flag = nullptr;
     int n_a = 3;                // option "tc_ring_a": A slab ring slots of the fused kernel (2 or 3); the B ring takes the rest
     int slab = 1;               // option "tc_slab": the dilated taps of the fused kernel share one A slab per 64-channel block (0: one
                                 // A tile per tap)
@@ -55,6 +60,7 @@ struct WnLayerArgs {
     int skip_ld, skip_c, res_cols, first;
     FrameGrid grid;
     int sm_count;
+    int* range_flag;            // WnTcState::range_flag
     void* trace;                // nullptr, or wn_layer_trace_bytes of device memory
 };
 size_t wn_layer_scratch_bytes(int cpad, int sm_count);

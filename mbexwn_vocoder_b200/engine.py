@@ -219,6 +219,14 @@ class Engine:
         _cabi.check(self.lib, self._handle, rc, "mbexwn_k_tc_gemm_f16f8")
         return out
 
+    def range_status(self, reset: bool = True) -> int:
+        """Sticky range-guard word of the f16f8 path (include/mbexwn.h: mbexwn_range_status): bit 0 = a residual-stream value
+        left the range of the e4m3 hi8 plane (|x| > 448), bit 1 = beyond 60000 (fp16).  Call after the forward's stream has
+        been synchronised (forward / run_host / wait_host do that)."""
+        flags = C.c_int32(0)
+        _cabi.check(self.lib, self._handle, self.lib.mbexwn_range_status(self._handle, C.byref(flags), 1 if reset else 0), "range_status")
+        return int(flags.value)
+
     def set_option(self, name: str, value: int):
         _cabi.check(self.lib, self._handle, self.lib.mbexwn_set_option(self._handle, name.encode(), value), "set_option")
 

@@ -22,10 +22,19 @@ from .plan import build_plan
 log_to_db = 20 * np.log10(np.exp(1))            # vocoder/model/preprocess.py:78
 
 
-def resolve_weights(model_dir: str, plan, hparams: Dict, verbose: bool = False) -> Dict[str, np.ndarray]:
+SYNTHETIC_WEIGHTS_ENV = "MBEXWN_SYNTHETIC_WEIGHTS"
+
+
+def resolve_weights(model_dir: str, plan, hparams: Dict, verbose: bool = False,
+                    allow_synthetic_weights: Optional[bool] = None) -> Dict[str, np.ndarray]:
     """Weights of a model directory, in this order: ``weights.npz`` (this package's container), ``weights.tf``
-    (the reference's TensorFlow checkpoint, mel_inverter.py:203-208, read without TensorFlow by tf_checkpoint.py),
-    else Keras-like random initialisation from the seed in the config (no released weights ship offline)."""
+    (the reference's TensorFlow checkpoint, mel_inverter.py:203-208, read without TensorFlow by tf_checkpoint.py).
+
+    Without either the reference fails hard in ``load_weights`` (mel_inverter.py:203-210) and so does this function
+    (FileNotFoundError) -- audio from random weights is noise, and the model directories that ship with this package hold
+    synthetic configurations under the reference's model names.  Tests, benchmarks and parity runs opt in explicitly with
+    ``allow_synthetic_weights=True`` (or the environment variable MBEXWN_SYNTHETIC_WEIGHTS=1): Keras-like random
+    initialisation from the seed in the config, announced on stderr."""
     npz = os.path.join(model_dir, "weights.npz")
     tf_prefix = os.path.join(model_dir, "weights.tf")
     if os.path.exists(npz):
@@ -39,15 +48,28 @@ def resolve_weights(model_dir: str, plan, hparams: Dict, verbose: bool = False) 
         if verbose:
             print(f"restore from {tf_prefix}", file=sys.stderr)
         return import_weights(tf_prefix, plan)
+    if allow_synthetic_weights is None:
+        allow_synthetic_weights = os.environ.get(SYNTHETIC_WEIGHTS_ENV, "") not in ("", "0")
+    if not allow_synthetic_weights:
+        raise FileNotFoundError(f"no weights.npz / weights.tf in {model_dir}: install the released models "
+                                f"(tools/install_models.py) or pass allow_synthetic_weights=True / set {SYNTHETIC_WEIGHTS_ENV}=1 "
+                                f"for random-initialised weights (tests and benchmarks only)")
     seed = int(hparams.get("synthetic_weights", {}).get("seed", 0))
-    if verbose:
-        print(f"no weights in {model_dir}: random-initialised weights, seed {seed}", file=sys.stderr)
+    print(f"MELInverter::warning::no weights in {model_dir}: RANDOM-INITIALISED weights (seed {seed}); the output is not speech",
+          file=sys.stderr)
     return W.init_synthetic(plan, seed=seed)
 
 
 class MELInverter(object):
     def __init__(self, model_id_or_path: Union[str, None] = None, verbose: bool = False,
-                 device: Union[int, str] = 0, precision: str = "fp32", seed: int = 42):
+                 device: Union[int, str] = 0, precision: str = "f16f8", seed: int = 42,
+                 allow_synthetic_weights: Optional[bool] = None, devices: Optional[Sequence[int]] = None):
+        """Reference signature ``MELInverter(model_id_or_path=None, verbose=False)`` (mel_inverter.py:21-41) plus:
+
+        precision   "f16f8" (default: the fp32-accurate tensor-core path the benchmarks measure), "bf16x3", "bf16", "fp32"
+        device      CUDA device of ``synth_from_mel`` / ``synth_batch``
+        devices     several CUDA devices for ``synth_many`` (one engine per GPU, LPT sharding, host gather)
+        allow_synthetic_weights   see ``resolve_weights``"""
         self.model = None
         self.model_id_or_path = model_id_or_path
         self.config_file = None
@@ -65,7 +87,10 @@ class MELInverter(object):
         self.mel_amp_scale = 1
         self.use_max_limit = False
 
-        self.device = device
+        self.devices = [int(d) for d in devices] if devices else None
+        self.device = self.devices[0] if self.devices else device
+        self.allow_synthetic_weights = allow_synthetic_weights
+        self._pool = None
         self.precision = precision
         self.seed = seed                        # bin/resynth_mel.py:65-67 seeds everything with 42
         self.plan = None
@@ -156,9 +181,15 @@ class MELInverter(object):
         A strided probe of the output detects that and the batch is re-run on the equally accurate bf16x3 path (bf16 planes
         have the fp32 exponent range), with a note on stderr -- never a silent change of accuracy class."""
         out, tp = self.model.forward(mels, noise=noise, f0=f0, precision=self.precision, seed=seed, taps=taps)
-        # one hop in four is probed (every frame overlaps four hops, so a non-finite frame cannot hide), at least 64 probes
-        if self.precision == "f16f8" and not all(np.isfinite(w[::max(1, min(self.hop_size * 4 - 1, w.size // 64))]).all() for w in out):
-            print("MELInverter::warning::non-finite samples on the f16f8 path (fp16 operand range exceeded); "
+        if self.precision != "f16f8":
+            return out, tp
+        # (1) the kernels that write the residual stream flag values beyond the e4m3 hi8 plane's range (|x| > 448: the
+        #     correction products would silently lose their meaning, no non-finite value marks it) -- mbexwn_range_status;
+        # (2) a strided probe of the output for non-finite samples (one hop in four: every frame overlaps four hops)
+        flags = self.model.range_status(reset=True)
+        bad = flags != 0 or not all(np.isfinite(w[::max(1, min(self.hop_size * 4 - 1, w.size // 64))]).all() for w in out)
+        if bad:
+            print(f"MELInverter::warning::operand range of the f16f8 path exceeded (range flags {flags}); "
                   "re-running this batch with precision bf16x3", file=sys.stderr)
             out, tp = self.model.forward(mels, noise=noise, f0=f0, precision="bf16x3", seed=seed, taps=taps)
         return out, tp
@@ -170,6 +201,26 @@ class MELInverter(object):
                                 seed=self.seed if seed is None else seed, taps=taps)
         return (out, tp) if taps else out
 
+    def synth_many(self, mels: Sequence[np.ndarray], max_batch_frames: int = 32768, seed: Optional[int] = None,
+                   return_stats: bool = False):
+        """Any number of (T_u, n_mel) mels -> list of (T_u * hop,) waveforms in input order: the caller loop of the reference
+        (bin/resynth_mel.py:72-104) as one call.  The set is LPT-sharded over ``devices`` (one engine and one host thread per
+        GPU, no collective), cut into batches of at most ``max_batch_frames`` padded frames and pipelined over two pinned buffer
+        sets per GPU; the result is gathered on the host (multi_gpu.py).  A waveform does not depend on the sharding."""
+        from .multi_gpu import DevicePool
+        if self._pool is None:
+            invs = [self]
+            for d in (self.devices or [self.device])[1:]:
+                other = MELInverter.__new__(MELInverter)
+                other.__dict__.update(self.__dict__)
+                from .engine import Engine
+                other.device = d
+                other.model = Engine(self.plan, self.weights, device=d)
+                other._pool = None
+                invs.append(other)
+            self._pool = DevicePool(invs)
+        return self._pool.synth_many(mels, max_batch_frames, self.seed if seed is None else seed, self.precision, return_stats)
+
     def synth_stream(self, batches, noise=None, seed: Optional[int] = None):
         """Throughput serving: iterate over batches (each a list of (T_u, n_mel) mels) and yield, per batch, the list of
         waveforms.  Consecutive batches alternate between two device buffer sets, so the host->device copy of the next
@@ -177,29 +228,45 @@ class MELInverter(object):
         (mbexwn_forward_host_begin / _wait).  ``noise``: optional iterable of per-batch noise lists (parity runs)."""
         eng = self.model
         seed = self.seed if seed is None else seed
-        pending = []                                         # (slot, PreparedBatch)
+        pending = []                                         # (slot, PreparedBatch, mels, noise, precision)
         noise_it = iter(noise) if noise is not None else None
+        # f16f8 range guard (mbexwn_range_status): the word is sticky and shared by the two batches in flight, so once it is
+        # raised every f16f8 batch still in flight is re-run on bf16x3 and the rest of the stream is submitted as bf16x3
+        state = {"prec": self.precision, "warned": False}
         for i, mels in enumerate(batches):
             slot = i & 1
             if len(pending) == 2:                            # the slot about to be reused must be drained first
-                s0, pb0 = pending.pop(0)
-                pb0.wait_host(s0)
-                yield [w.copy() for w in pb0.waveforms()]
+                yield self._drain_stream(pending.pop(0), seed, state)
             nz = next(noise_it) if noise_it is not None else None
             mels = [np.asarray(m, dtype=np.float32) for m in mels]
-            pb = eng.prepare_cached([m.shape[0] for m in mels], self.precision, nz is not None, slot=slot)
+            pb = eng.prepare_cached([m.shape[0] for m in mels], state["prec"], nz is not None, slot=slot)
             pb.load(mels, nz)
             pb.begin_host(slot, seed)
-            pending.append((slot, pb))
-        for s0, pb0 in pending:
-            pb0.wait_host(s0)
-            yield [w.copy() for w in pb0.waveforms()]
+            pending.append((slot, pb, mels, nz, state["prec"]))
+        for item in pending:
+            yield self._drain_stream(item, seed, state)
+        if self.precision == "f16f8":
+            eng.range_status(reset=True)
+
+    def _drain_stream(self, item, seed, state):
+        slot, pb, mels, nz, prec = item
+        pb.wait_host(slot)
+        if prec == "f16f8" and self.model.range_status(reset=False) != 0:
+            if not state["warned"]:
+                print("MELInverter::warning::operand range of the f16f8 path exceeded; this stream continues with precision bf16x3",
+                      file=sys.stderr)
+                state["warned"] = True
+            state["prec"] = "bf16x3"
+            return self.model.forward(mels, noise=nz, precision="bf16x3", seed=seed)[0]
+        return [w.copy() for w in pb.waveforms()]
 
     def synth_long_from_mel(self, scaled_mell, noise=None, chunk_frames: int = 400, max_batch_frames: int = 32768,
                             seed: Optional[int] = None, return_info: bool = False):
         """One long (T, n_mel) or (1, T, n_mel) mel -> flat waveform, synthesised in windows of `chunk_frames` frames with
-        receptive-field overlap and a carried pulse phase (long_form.py).  Equal to synth_from_mel on the same input, with
-        device memory bounded by `max_batch_frames` instead of T."""
+        receptive-field overlap and a carried pulse phase (long_form.py), device memory bounded by `max_batch_frames` instead
+        of T.  With the same explicit `noise` (T * steps values) it equals synth_from_mel / synth_batch on the same input bit
+        for bit; with noise=None the draw comes from NumPy's default_rng(seed) on the host, whereas synth_from_mel uses the
+        in-kernel Philox stream -- the two then differ in their noise channel (same distribution, different numbers)."""
         from .long_form import synth_long
         mel = np.asarray(scaled_mell, dtype=np.float32)
         if mel.ndim == 3:
@@ -247,7 +314,7 @@ class MELInverter(object):
         self.preprocess_config = hparams["preprocess_config"]
         self.plan = build_plan(hparams)
 
-        weights = resolve_weights(model_dir, self.plan, hparams, verbose=verbose)
+        weights = resolve_weights(model_dir, self.plan, hparams, verbose=verbose, allow_synthetic_weights=self.allow_synthetic_weights)
         self.weights = weights
         self.model = Engine(self.plan, weights, device=self.device)
 

@@ -386,8 +386,8 @@ class BundleReader:
                 ln, pos = _get_varint(raw, pos)
                 lengths.append(ln)
             crc = 0
-            for ln in lengths:                       # the checksum runs over the lengths as uint64, not the varints
-                crc = crc32c(struct.pack("<Q", ln), crc)
+            for ln in lengths:                       # the checksum runs over the fixed-width lengths, not the varints
+                crc = crc32c(_length_bytes(ln), crc)
             if self.verify and struct.unpack_from("<I", raw, pos)[0] != mask_crc(crc):
                 raise ValueError("checkpoint string tensor: length checksum mismatch")
             crc = crc32c(raw[pos:pos + 4], crc)
@@ -408,9 +408,16 @@ class BundleReader:
         return arr.reshape(e.shape).copy()
 
 
+def _length_bytes(ln: int) -> bytes:
+    """How a string length enters the length checksum of a DT_STRING tensor: TensorFlow's tensor_bundle
+    (WriteStringTensor / ReadStringTensor) extends the CRC with the length as a 4-byte uint32 whenever it fits
+    (<= UINT32_MAX) and as a uint64 only above that.  Every real weights.tf stores _CHECKPOINTABLE_OBJECT_GRAPH this way."""
+    return struct.pack("<I", ln) if ln <= 0xFFFFFFFF else struct.pack("<Q", ln)
+
+
 def _string_tensor_bytes(value: bytes) -> Tuple[bytes, int]:
-    """Scalar DT_STRING payload and its CRC (lengths as uint64, the length checksum, then the bytes)."""
-    crc = crc32c(struct.pack("<Q", len(value)))
+    """Scalar DT_STRING payload and its CRC (varint length, the checksum over the fixed-width length, then the bytes)."""
+    crc = crc32c(_length_bytes(len(value)))
     cks = struct.pack("<I", mask_crc(crc))
     crc = crc32c(cks, crc)
     crc = crc32c(value, crc)

@@ -8,6 +8,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# the model directories of this package hold synthetic configurations without weights: tests run on random-initialised
+# weights (MELInverter refuses that unless asked to, like the reference's load_weights would)
+os.environ.setdefault("MBEXWN_SYNTHETIC_WEIGHTS", "1")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
 

@@ -338,3 +338,33 @@ def test_f16f8_range_guard_falls_back_to_bf16x3(tmp_path, capsys):
     assert "bf16x3" in capsys.readouterr().err
     ref, _ = inv.model.forward(list(mel), precision="bf16x3", seed=1)
     assert np.array_equal(y, ref[0])
+
+
+def test_f16f8_hi8_saturation_is_flagged_and_falls_back(tmp_path, capsys):
+    """the hi8 correction plane of the f16f8 path is e4m3(x), unscaled and saturating at 448.  A residual stream
+    between 448 and the fp16 limit yields finite but silently less accurate output -- no non-finite sample marks it.  The
+    kernels that write the residual stream flag it (mbexwn_range_status bit 0) and the inverter re-runs the batch on bf16x3."""
+    from mbexwn_vocoder_b200 import get_config_file, weights as W
+    from mbexwn_vocoder_b200.config import read_config
+    from mbexwn_vocoder_b200.mel_inverter import MELInverter
+    from mbexwn_vocoder_b200.plan import build_plan
+    import shutil
+    cfg = get_config_file("SPEECH")
+    hp = read_config(cfg)
+    plan = build_plan(hp, finalize=False)
+    w = W.init_synthetic(plan, seed=12)
+    name = "PP_waveNetBlock_ups1_0_WNBlock_WN/start"
+    w[f"{name}/g"] = w[f"{name}/g"] * 2e3                          # residual stream ~1e3: inside fp16, beyond e4m3
+    shutil.copy(cfg, tmp_path / "config.yaml")
+    W.save(str(tmp_path / "weights.npz"), w)
+    inv = MELInverter(str(tmp_path), device=0, precision="f16f8")
+    mel = synthetic_mel(12, 0)[None]
+    inv.model.range_status(reset=True)
+    raw, _ = inv.model.forward(list(mel), precision="f16f8", seed=1)
+    assert np.isfinite(raw[0]).all()                               # nothing visible in the samples ...
+    assert inv.model.range_status(reset=True) & 1                  # ... but the guard word is raised
+    y = inv.synth_from_mel(mel, seed=1)
+    assert "bf16x3" in capsys.readouterr().err
+    ref, _ = inv.model.forward(list(mel), precision="bf16x3", seed=1)
+    assert np.array_equal(y, ref[0])
+    assert inv.model.range_status(reset=True) == 0

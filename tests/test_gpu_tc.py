@@ -120,7 +120,7 @@ def fused(request, engine):
     """tc_fused = 1 forces the one-kernel-per-layer path (k_wavenet_layer.cu) also for batches this short (CTA pairs only)."""
     engine.set_option("tc_fused", request.param)
     yield request.param
-    engine.set_option("tc_fused", 2)
+    engine.set_option("tc_fused", 1)
 
 
 @pytest.mark.parametrize("precision,tol,snr", [("bf16x3", 1e-4, 60.0), ("f16f8", 1e-4, 60.0), ("bf16", 5e-2, 35.0)])
@@ -150,7 +150,7 @@ def test_wavenet_tc_parity(engine, cg, fused, speech_setup, precision, tol, snr)
 def test_fused_layer_kernel_equals_two_launch_path(engine, speech_setup, precision):
     """One persistent kernel per layer (gate tiles of M tile m, res tiles of M tile m - 1, activations through the L2 scratch,
     residual stream ping-pong) against the gate + res/skip launches on a batch that gives every CTA pair several M tiles
-    and a ragged tail: the same products, summed in a different K order -- fp32 rounding apart (1e-5 of peak), every buffer agrees."""
+    and a ragged tail: the same products, summed in a different K order -- fp32 rounding apart (5e-5 of peak), every buffer agrees."""
     hp, plan, w = speech_setup
     lengths = [400, 380, 17, 400, 211, 400, 1, 400, 399, 400, 2, 400, 400, 333]
     mels = [synthetic_mel(t, 40 + i) for i, t in enumerate(lengths)]
@@ -164,11 +164,11 @@ def test_fused_layer_kernel_equals_two_launch_path(engine, speech_setup, precisi
         res[-1] += (int(engine.lib.mbexwn_last_launch_count(engine._handle)),)
     # one launch per layer against two: the fused kernel must really have run
     assert res[0][2] - res[1][2] == plan.wavenet.n_layers, (res[0][2], res[1][2])
-    engine.set_option("tc_fused", 2)
+    engine.set_option("tc_fused", 1)
     engine.set_option("tc_cta_group", 1)
     for u in range(len(lengths)):
         assert np.all(np.isfinite(res[1][0][u]))
-        tol = 2e-3 if precision == "bf16" else 1e-5          # bf16 re-rounds the activations of every layer
+        tol = 2e-3 if precision == "bf16" else 5e-5          # bf16 re-rounds the activations of every layer
         for a, b, what in ((res[0][1]["wn_out"][u], res[1][1]["wn_out"][u], "wn_out"), (res[0][0][u], res[1][0][u], "waveform")):
             assert np.abs(a - b).max() <= tol * max(np.abs(a).max(), 1e-30), f"{what} of utterance {u}"
 
@@ -189,7 +189,7 @@ def test_fused_layer_slab_views_equal_per_tap_loads(engine, speech_setup, precis
         engine.set_option("tc_slab", slab)
         out, tp = engine.forward(mels, noise=noise, precision=precision, taps=["wn_out"])
         res.append((out, tp))
-    engine.set_option("tc_fused", 2)
+    engine.set_option("tc_fused", 1)
     engine.set_option("tc_cta_group", 1)
     for u in range(len(lengths)):
         assert np.all(np.isfinite(res[1][0][u]))

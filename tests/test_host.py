@@ -198,6 +198,24 @@ def test_no_cpu_fallback_without_gpu(speech_setup):
     assert lib.mbexwn_create(ctypes.byref(make_config(plan)), ctypes.byref(h)) == _cabi.ERR_CUDA
 
 
+def test_missing_weights_fail_hard_unless_asked_for_synthetic_ones(monkeypatch, speech_setup):
+    """The reference fails in load_weights when a model directory has no checkpoint (mel_inverter.py:203-210); so does
+    resolve_weights -- random weights need an explicit opt-in (argument or MBEXWN_SYNTHETIC_WEIGHTS=1) and announce themselves."""
+    from mbexwn_vocoder_b200 import get_config_file
+    from mbexwn_vocoder_b200.mel_inverter import resolve_weights
+    hp, plan, w = speech_setup
+    model_dir = os.path.dirname(get_config_file("SPEECH"))
+    monkeypatch.delenv("MBEXWN_SYNTHETIC_WEIGHTS", raising=False)
+    with pytest.raises(FileNotFoundError, match="allow_synthetic_weights"):
+        resolve_weights(model_dir, plan, hp)
+    got = resolve_weights(model_dir, plan, hp, allow_synthetic_weights=True)
+    assert set(got) == set(w)
+    monkeypatch.setenv("MBEXWN_SYNTHETIC_WEIGHTS", "1")
+    assert set(resolve_weights(model_dir, plan, hp)) == set(w)
+    with pytest.raises(FileNotFoundError):
+        resolve_weights(model_dir, plan, hp, allow_synthetic_weights=False)
+
+
 def test_product_never_imports_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "mbexwn_vocoder_b200")):
         for f in files:

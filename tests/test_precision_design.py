@@ -50,7 +50,7 @@ def test_packed_tc8_weights_match_bf16_packing_geometry(speech_setup):
     b, shifts = tc_pack.pack_tc8_weights(plan, w)
     assert shifts == tc_pack.choose_tc8_shifts(0.0, 0.0) or set(shifts) == set(tc_pack.TC8_DEFAULT_SHIFTS)
     for key, t in b.items():
-        ref = a[key.replace("/tc8/", "/tc/")]
+        ref = a[key.replace("/tcf8/", "/tcf/").replace("/tc8/", "/tc/")]
         assert t.shape[0] == ref.shape[0] and t.shape[1] == 2 * ref.shape[1]       # same rows, same bytes per row
         k = ref.shape[1] // 2
         h16, _, _ = _decode_planes(t, k)
@@ -85,3 +85,15 @@ def test_emulated_f16f8_wavenet_meets_the_fp32_tolerance():
     out16, _ = sp.wavenet(orc, sp.Scheme("bf16"), x, cond)
     e16 = out16 - ref
     assert 10 * np.log10(float((ref ** 2).sum() / (e16 ** 2).sum())) >= 35.0
+
+
+def test_chunked_gate_permutation_of_the_fused_layer_kernel():
+    """W1 rows for csrc/k_wavenet_layer.cu: per 16-channel chunk [16 tanh rows | their 16 sigmoid partners] -- a permutation of the
+    reference's [tanh(C) | sigmoid(C)] columns (custom_AE_layers.py:309-321) with the padding rows masked."""
+    for c, cpad in ((320, 320), (340, 384)):
+        col, ok = tc_pack.gate_permutation_chunked(c, cpad)
+        assert col.shape == (2 * cpad,) and sorted(col[ok]) == list(range(2 * c))
+        n = np.arange(2 * cpad)
+        chunk, within = n // 32, n % 32
+        assert np.array_equal(col[ok] % c, (16 * chunk + within % 16)[ok])          # tanh row and sigmoid row: same channel
+        assert np.array_equal(col[ok] >= c, (within >= 16)[ok])                      # sigmoid half = second 16 rows of a chunk

@@ -139,12 +139,42 @@ def test_bundle_round_trip(tmp_path):
 
 
 def test_string_tensor_layout():
+    """DT_STRING payload as TensorFlow's tensor_bundle writes it (WriteStringTensor): varint64 lengths, then the masked CRC-32C
+    over the lengths -- each one extended as a 4-byte uint32 when it fits, as a uint64 only above UINT32_MAX --, then the
+    bytes; the tensor CRC continues over the 4 checksum bytes and the string bytes.  Bytes below are assembled by hand from
+    that description (not through the module's writer)."""
     raw, crc = T._string_tensor_bytes(b"hello")
-    # [varint length][masked crc of the uint64 length][bytes]
     assert raw[0] == 5 and raw[5:] == b"hello" and len(raw) == 10
-    lencrc = T.crc32c(struct.pack("<Q", 5))
+    lencrc = T.crc32c(bytes([5, 0, 0, 0]))                     # uint32 little endian, NOT eight bytes
+    assert lencrc != T.crc32c(bytes([5, 0, 0, 0, 0, 0, 0, 0]))
     assert struct.unpack("<I", raw[1:5])[0] == T.mask_crc(lencrc)
     assert crc == T.crc32c(b"hello", T.crc32c(raw[1:5], lencrc))
+    assert T._length_bytes(0xFFFFFFFF) == b"\xff\xff\xff\xff"
+    assert T._length_bytes(0x100000000) == struct.pack("<Q", 0x100000000)
+
+
+def test_reader_accepts_a_hand_assembled_string_tensor(tmp_path):
+    """A bundle whose string entry was laid out by hand (uint32 length checksum) reads back with verification on, and a
+    payload with the old uint64 length checksum is rejected."""
+    value = b"object graph stand-in"
+    good = T._put_varint(len(value))
+    lcrc = T.crc32c(struct.pack("<I", len(value)))
+    cks = struct.pack("<I", T.mask_crc(lcrc))
+    good += cks + value
+    crc_good = T.crc32c(value, T.crc32c(cks, lcrc))
+    raw, crc = T._string_tensor_bytes(value)
+    assert raw == good and crc == crc_good
+    prefix = str(tmp_path / "w")
+    T.write_bundle(prefix, {"_CHECKPOINTABLE_OBJECT_GRAPH": value, "x": np.arange(3, dtype=np.float32)})
+    r = T.BundleReader(prefix)
+    assert r.get("_CHECKPOINTABLE_OBJECT_GRAPH") == value
+    # same payload with the length checksummed as uint64: the reader must refuse it
+    data = open(prefix + ".data-00000-of-00001", "rb").read()
+    bad_cks = struct.pack("<I", T.mask_crc(T.crc32c(struct.pack("<Q", len(value)))))
+    assert cks in data
+    open(prefix + ".data-00000-of-00001", "wb").write(data.replace(cks, bad_cks))
+    with pytest.raises(ValueError):
+        T.BundleReader(prefix).get("_CHECKPOINTABLE_OBJECT_GRAPH")
 
 
 def test_object_graph_round_trip():

@@ -10,7 +10,7 @@ from mbexwn_vocoder_b200.mel_inverter import MELInverter
 opt = sys.argv[1]
 VALUES = tuple(int(x) for x in sys.argv[3].split(",")) if len(sys.argv) > 3 else (0, 1)
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-inv = MELInverter("SPEECH", device=0, precision="f16f8")
+inv = MELInverter("SPEECH", device=0, precision="f16f8", allow_synthetic_weights=True)
 eng, plan = inv.model, inv.plan
 eng.set_option("debug_taps", 0)
 eng.set_option("tc_fused", 1)

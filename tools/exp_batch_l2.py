@@ -9,7 +9,7 @@ import bench
 from mbexwn_vocoder_b200.mel_inverter import MELInverter
 
 sizes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [64, 32, 16, 10, 8, 6, 5, 4, 3, 64]
-inv = MELInverter("SPEECH", device=0, precision="f16f8")
+inv = MELInverter("SPEECH", device=0, precision="f16f8", allow_synthetic_weights=True)
 eng, plan = inv.model, inv.plan
 eng.set_option("debug_taps", 0)
 for B in sizes:

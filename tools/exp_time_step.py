@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from mbexwn_vocoder_b200.mel_inverter import MELInverter
 
-inv = MELInverter("SPEECH", device=0, precision="f16f8")
+inv = MELInverter("SPEECH", device=0, precision="f16f8", allow_synthetic_weights=True)
 eng, plan = inv.model, inv.plan
 eng.set_option("debug_taps", 0)
 mels, noise = bench.synthetic_batch(64, 400, plan.steps_per_frame)

@@ -25,7 +25,7 @@ debug = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 SLOTS = 384
 
 model_id, batch, frames, _ = bench.WORKLOADS[workload]
-inv = MELInverter(model_id, device=0, precision=precision)
+inv = MELInverter(model_id, device=0, precision=precision, allow_synthetic_weights=True)
 eng, plan = inv.model, inv.plan
 eng.set_option("debug_taps", 0)
 eng.set_option("tc_cta_group", 2)

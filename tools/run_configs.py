@@ -53,7 +53,7 @@ def main():
 
     if args.config == "config3":
         prec = args.precision or "bf16"
-        inv = MELInverter("VOICE", device=local, precision=prec)
+        inv = MELInverter("VOICE", device=local, precision=prec, allow_synthetic_weights=True)
         eng, plan = inv.model, inv.plan
         eng.set_option("debug_taps", 0)
         B, T = 256, 800
@@ -76,7 +76,7 @@ def main():
                 "finite": bool(np.isfinite(pb.out_dev[:100000].cpu().numpy()).all())}
     elif args.config == "config4":
         prec = args.precision or "f16f8"
-        inv = MELInverter("SING", device=local, precision=prec)
+        inv = MELInverter("SING", device=local, precision=prec, allow_synthetic_weights=True)
         eng, plan = inv.model, inv.plan
         eng.set_option("debug_taps", 0)
         rng = np.random.default_rng(1)
@@ -143,7 +143,7 @@ def main():
                 "checksum": float(tot[1])}
     else:
         prec = args.precision or "f16f8"
-        inv = MELInverter("SPEECH", device=local, precision=prec)
+        inv = MELInverter("SPEECH", device=local, precision=prec, allow_synthetic_weights=True)
         plan = inv.plan
         inv.model.set_option("debug_taps", 0)
         T = int(args.minutes * 60 * plan.sample_rate / plan.hop)

@@ -26,7 +26,7 @@ def multi_block_variants():
         cfg["mbexwn_config"].update(extra)
         d = tempfile.mkdtemp(prefix=name)
         yaml.safe_dump(cfg, open(os.path.join(d, "config.yaml"), "w"))
-        mb = MELInverter(d, device=0, precision="f16f8")
+        mb = MELInverter(d, device=0, precision="f16f8", allow_synthetic_weights=True)
         for prec in ("f16f8", "bf16", "fp32"):
             mb.precision = prec
             out = mb.synth_batch(mels)
@@ -37,7 +37,7 @@ def multi_block_variants():
 if len(sys.argv) > 1 and sys.argv[1] == "blocks":
     multi_block_variants()
     sys.exit(0)
-inv = MELInverter("SPEECH", device=0, precision="f16f8")
+inv = MELInverter("SPEECH", device=0, precision="f16f8", allow_synthetic_weights=True)
 for prec in ("f16f8", "bf16x3", "bf16", "fp32"):
     inv.precision = prec
     out = inv.synth_batch(mels)
