@@ -256,15 +256,16 @@ def run_config4(args, rank, world, local, dist):
 
     def sink(u, w):                             # the host gather: the pinned grid's slice lands in the result buffer
         k = where[int(u)]
-        result[offs[k]:offs[k + 1]] = w
+        return result[offs[k]:offs[k + 1]]
     # warm-up: a few batches of this rank's shard (allocates the two buffer sets and the workspace)
     warm = mine[:min(len(mine), 8)]
-    run_shard(inv, get_mel, lengths, warm, {}, args.max_batch_frames, seed=7, keep=False)
+    host_threads = max(1, min(4, (os.cpu_count() or 4) // max(1, world)))
+    run_shard(inv, get_mel, lengths, warm, {}, args.max_batch_frames, seed=7, keep=False, host_threads=host_threads)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    st = run_shard(inv, get_mel, lengths, mine, sink, args.max_batch_frames, seed=7)
+    st = run_shard(inv, get_mel, lengths, mine, sink, args.max_batch_frames, seed=7, host_threads=host_threads)
     table = np.array([[u, offs[k], offs[k + 1] - offs[k], float(np.abs(result[offs[k]:offs[k + 1]:997]).sum())]
                       for k, u in enumerate(mine)], dtype=np.float64)
     local_s = time.perf_counter() - t0
@@ -291,7 +292,7 @@ def run_config4(args, rank, world, local, dist):
     return {"workload": f"config4: {CONFIG4['desc']}, LPT over {world} rank(s), batches <= {args.max_batch_frames} frames",
             "scaling": "strong", "utterances": int(n_done), "audio_s": audio_s, "wall_s": wall, "value": audio_s / wall,
             "unit": "audio-s/s", "precision": args.precision,
-            "lpt_imbalance": imbalance(lengths, shards),
+            "lpt_imbalance": imbalance(lengths, shards), "host_threads_per_rank": host_threads,
             "shard_audio_s": [float(sum(int(lengths[u]) for u in sh)) * plan.hop / plan.sample_rate for sh in shards],
             "per_rank": [{"wall_s": float(x[0]), "host_scatter_s": float(x[1]), "host_gather_s": float(x[2]),
                           "host_waiting_for_gpu_s": float(x[3]), "range_reruns": int(x[7])} for x in allst],

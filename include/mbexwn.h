@@ -251,6 +251,19 @@ MBEXWN_API int mbexwn_stage_ms(mbexwn_handle_t h, float* ms);
 MBEXWN_API int mbexwn_wavenet_launch_ms(mbexwn_handle_t h, float* gate_ms, float* resskip_ms, int32_t* n_layers);
 /* With "tc_fused" in effect a layer is ONE launch: gate_ms then holds the sum of the fused launches and resskip_ms is 0. */
 
+/* ---- chunked long-form synthesis (BASELINE.json configs[4]; long_form.py) without the host in the loop ----
+ * mbexwn_phase_carry: f0_dev = F0 of ONE whole signal at the pulse rate (n_samples, device); run_out_dev[c] (device,
+ * ceil(n_samples / cumsum_chunk) floats) = the unwrapped float32 running sum of the wrapped chunk totals of chunks 0 .. c - 1,
+ * i.e. mbexwn_batch_t.phase_carry of a window that starts at chunk c.  Same association order as the forward's own phase
+ * kernels (PulseWaveTable.stable_cumsum_and_wrap, tf_wavetable.py:429-492).
+ * mbexwn_gather_rows: for every segment s: dst[dst_row + r, :] = src[src_row + r, :], r < n_rows, rows of row_elems floats
+ * (float4 copies when row_elems % 4 == 0); seg_dev = n_seg x {src_row, dst_row, n_rows} int64 on the device (n_seg <= 65535),
+ * max_rows = the longest segment.  Cuts the
+ * windows of a long signal out of device-resident mel / noise / F0 buffers into a batch grid and the cores back out of it. */
+MBEXWN_API int mbexwn_phase_carry(mbexwn_handle_t h, const float* f0_dev, int64_t n_samples, float* run_out_dev, void* cuda_stream);
+MBEXWN_API int mbexwn_gather_rows(mbexwn_handle_t h, const float* src_dev, float* dst_dev, int32_t row_elems, const int64_t* seg_dev,
+                                  int32_t n_seg, int32_t max_rows, void* cuda_stream);
+
 /* Range guard of MBEXWN_PREC_F16F8.  The main operand plane of that path is fp16 and the hi8 correction plane is e4m3(x),
  * unscaled and saturating at 448: a model whose residual stream leaves that range would silently drop to plain-fp16 accuracy
  * (no non-finite sample marks it).  The kernels that write the residual stream (start conv, res/skip epilogue) therefore OR

@@ -111,6 +111,8 @@ SYMBOLS = {
     "mbexwn_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
     "mbexwn_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mbexwn_wavenet_launch_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "mbexwn_phase_carry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "mbexwn_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "mbexwn_range_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32]),
     "mbexwn_tc_trace_read": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "mbexwn_k_conv1d": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Op), C.c_int32, C.c_void_p, C.c_void_p,

@@ -897,6 +897,21 @@ int mbexwn_wavenet_launch_ms(mbexwn_handle_t h, float* gate_ms, float* resskip_m
     return MBEXWN_OK;
 }
 
+int mbexwn_phase_carry(mbexwn_handle_t h, const float* f0_dev, int64_t n_samples, float* run_out_dev, void* cuda_stream) {
+    if (!h || !f0_dev || !run_out_dev || n_samples < 1) return MBEXWN_ERR_INVALID;
+    MBX_CUDA_CHECK(mbx::launch_phase_carry(f0_dev, n_samples, h->cfg.pulse_rate, h->cfg.cumsum_chunk, run_out_dev,
+                                           reinterpret_cast<cudaStream_t>(cuda_stream)));
+    return MBEXWN_OK;
+}
+
+int mbexwn_gather_rows(mbexwn_handle_t h, const float* src_dev, float* dst_dev, int32_t row_elems, const int64_t* seg_dev,
+                       int32_t n_seg, int32_t max_rows, void* cuda_stream) {
+    if (!h || !src_dev || !dst_dev || !seg_dev) return MBEXWN_ERR_INVALID;
+    MBX_CUDA_CHECK(mbx::launch_gather_rows(src_dev, dst_dev, row_elems, reinterpret_cast<const long long*>(seg_dev), n_seg, max_rows,
+                                           reinterpret_cast<cudaStream_t>(cuda_stream)));
+    return MBEXWN_OK;
+}
+
 int mbexwn_range_status(mbexwn_handle_t h, int32_t* flags, int32_t reset) {
     if (!h || !flags) return MBEXWN_ERR_INVALID;
     *flags = h->range_flag ? *reinterpret_cast<volatile int*>(h->range_flag) : 0;

@@ -278,7 +278,79 @@ __global__ void pulse_kernel(ExcitationArgs a, FrameGrid g) {
     if (a.pulse_out) a.pulse_out[n] = acc;
 }
 
+// ---- long-form helpers (chunked synthesis of one long signal, long_form.py) ------------------------------------------
+// Wrapped total of every 1000-sample chunk of ONE signal, in the association order of phase_chunk_kernel: the velocities
+// f0 / rate are summed sequentially in float32 inside the chunk.  One warp per chunk; lane 0 runs the chain.
+__global__ void __launch_bounds__(CHUNK_WARPS * 32)
+chunk_total_kernel(const float* __restrict__ f0, long long n, float pulse_rate, int chunk, float* __restrict__ tot, int n_chunks) {
+    __shared__ __align__(16) float buf[CHUNK_WARPS][MAX_CHUNK];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * CHUNK_WARPS + warp;
+    if (c >= n_chunks) return;
+    const long long s0 = (long long)c * chunk;
+    const int m = (int)min((long long)chunk, n - s0);
+    const int m8 = (m + 7) & ~7;
+    float* si = buf[warp];
+    for (int i = lane; i < m8; i += 32) si[i] = i < m ? __fdiv_rn(__ldg(f0 + s0 + i), pulse_rate) : 0.f;
+    __syncwarp();
+    if (lane == 0) {
+        float acc = 0.f;
+        for (int i = 0; i < m8; ++i) acc = __fadd_rn(acc, si[i]);      // x + 0 is exact: the padding does not change the sum
+        tot[c] = wrap1(acc);
+    }
+}
+
+// run[c] = unwrapped float32 running sum of the wrapped totals of chunks 0 .. c - 1 (tf.cumsum over the chunk axis,
+// tf_wavetable.py:470-486; the same sequential order as chunk_offset_kernel): the phase carry a window starting at chunk c
+// continues from.  In place; one thread (a few thousand dependent adds for a ten-minute signal).
+__global__ void chunk_run_kernel(float* __restrict__ tot_run, int n_chunks) {
+    if (blockIdx.x || threadIdx.x) return;
+    float run = 0.f;
+    for (int c = 0; c < n_chunks; ++c) {
+        const float t = tot_run[c];
+        tot_run[c] = run;
+        run = __fadd_rn(run, t);
+    }
+}
+
+// dst[dst_row[s] + r, :] = src[src_row[s] + r, :] for r < n_rows[s]; rows of row_vec elements of type V (float4 when the
+// row length allows it, else float)
+template <typename V>
+__global__ void gather_rows_kernel(const V* __restrict__ src, V* __restrict__ dst, int row_vec, const long long* __restrict__ seg, int n_seg) {
+    const int s = blockIdx.y;
+    if (s >= n_seg) return;
+    const long long src_row = seg[3 * s], dst_row = seg[3 * s + 1], n_rows = seg[3 * s + 2];
+    const long long total = n_rows * row_vec;
+    const V* ps = src + src_row * row_vec;
+    V* pd = dst + dst_row * row_vec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) pd[i] = ps[i];
+}
+
 }  // namespace
+
+cudaError_t launch_phase_carry(const float* f0, long long n_samples, float pulse_rate, int chunk, float* run_out, cudaStream_t s) {
+    if (chunk > MAX_CHUNK || chunk < 1 || n_samples < 1) return cudaErrorInvalidValue;
+    const int n_chunks = (int)((n_samples + chunk - 1) / chunk);
+    chunk_total_kernel<<<(n_chunks + CHUNK_WARPS - 1) / CHUNK_WARPS, CHUNK_WARPS * 32, 0, s>>>(f0, n_samples, pulse_rate, chunk, run_out, n_chunks);
+    chunk_run_kernel<<<1, 32, 0, s>>>(run_out, n_chunks);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_rows(const float* src, float* dst, int row_elems, const long long* seg, int n_seg, int max_rows, cudaStream_t s) {
+    if (row_elems < 1 || n_seg < 1 || n_seg > 65535) return cudaErrorInvalidValue;
+    const bool vec = (row_elems & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    const int row_vec = vec ? row_elems / 4 : row_elems;
+    const long long per = (long long)max_rows * row_vec;
+    int bx = (int)((per + 255) / 256);
+    if (bx > 64) bx = 64;
+    if (bx < 1) bx = 1;
+    if (vec)
+        gather_rows_kernel<float4><<<dim3((unsigned)bx, (unsigned)n_seg), 256, 0, s>>>(reinterpret_cast<const float4*>(src),
+                                                                                 reinterpret_cast<float4*>(dst), row_vec, seg, n_seg);
+    else
+        gather_rows_kernel<float><<<dim3((unsigned)bx, (unsigned)n_seg), 256, 0, s>>>(src, dst, row_vec, seg, n_seg);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_excitation(const ExcitationArgs& a, const FrameGrid& g, int n_chunks_total, cudaStream_t s) {
     if (a.chunk > MAX_CHUNK) return cudaErrorInvalidValue;

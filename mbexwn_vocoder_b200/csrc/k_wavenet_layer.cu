@@ -178,9 +178,14 @@ __device__ __forceinline__ void cond_stage_fill(const LayerParams& p, float* buf
 
 // tanh(t) * sigmoid(s) with three MUFU operations: u = e^-2t, v = e^-s, (1 - u) / ((1 + u) (1 + v)).  u and v are capped so
 // that the denominator stays finite (tanh is +-1 to fp32 precision long before).
+__device__ __forceinline__ float min_nan(float a, float b) {     // NaN-propagating minimum (fminf would swallow a NaN accumulator)
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
 __device__ __forceinline__ float gate_gtu(float t, float s) {
-    const float u = fminf(ex2_approx(t * -2.885390081777927f), 1e18f);
-    const float v = fminf(ex2_approx(s * -1.4426950408889634f), 1e18f);
+    const float u = min_nan(ex2_approx(t * -2.885390081777927f), 1e18f);
+    const float v = min_nan(ex2_approx(s * -1.4426950408889634f), 1e18f);
     return (1.f - u) * rcp_approx((1.f + u) * (1.f + v));
 }
 

@@ -107,6 +107,10 @@ struct ExcitationArgs {
 };
 cudaError_t launch_excitation(const ExcitationArgs& a, const FrameGrid& g, int n_chunks_total, cudaStream_t s);
 
+// long-form helpers: phase carry before every cumsum chunk of one signal; row-segment gather between device buffers
+cudaError_t launch_phase_carry(const float* f0, long long n_samples, float pulse_rate, int chunk, float* run_out, cudaStream_t s);
+cudaError_t launch_gather_rows(const float* src, float* dst, int row_elems, const long long* seg, int n_seg, int max_rows, cudaStream_t s);
+
 // ---- k_synth.cu ----------------------------------------------------------------------------------
 struct PqmfArgs {
     const float* sub;       // (frames * steps, S)

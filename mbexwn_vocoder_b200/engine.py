@@ -7,6 +7,7 @@ fallback: constructing an Engine without a CUDA device or without the built libr
 from __future__ import annotations
 
 import ctypes as C
+import sys
 from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Union
 
@@ -135,6 +136,7 @@ class Engine:
         self._upload(weights)
         self.last_layout: Optional[FrameGridLayout] = None
         self._last = None
+        self.use_graphs = True
 
     # ---- weights / constants ----------------------------------------------------------------------
     def _register(self, name: str, array: np.ndarray):
@@ -268,6 +270,10 @@ class Engine:
         pb.batch.utt_ids = None
         return pb
 
+    # batches of at most this many padded frames replay a CUDA graph of their forward (captured per cached batch geometry):
+    # the launch-bound case of BASELINE.json configs[0] (one 5 s utterance: ~25 kernel launches of a few microseconds each)
+    GRAPH_MAX_FRAMES = 1024
+
     def forward(self, mels: Sequence[np.ndarray], noise: Optional[Sequence[np.ndarray]] = None,
                 f0: Optional[Sequence[np.ndarray]] = None, precision: str = "fp32", seed: int = 0,
                 taps: Sequence[str] = (), utt_ids: Optional[Sequence[int]] = None):
@@ -278,7 +284,10 @@ class Engine:
         pb.load(mels, noise, f0)
         if utt_ids is not None:
             pb.set_utt_ids(utt_ids)
-        pb.run_host(seed)
+        if self.use_graphs and not taps and utt_ids is None and pb.layout.n_frames <= self.GRAPH_MAX_FRAMES:
+            pb.run_graph(seed)
+        else:
+            pb.run_host(seed)
         out = [w.copy() for w in pb.waveforms()]
         return out, {t: pb.tap(t) for t in taps}
 
@@ -329,6 +338,7 @@ class PreparedBatch:
         self.ws_bytes = int(eng.lib.mbexwn_workspace_bytes(eng._handle, F, self.cap_chunks, self.prec))
         self.workspace = eng._ensure_workspace(self.ws_bytes)
         self.utt_ids = None
+        self._graphs = {}                                     # seed -> CUDA graph of [H2D, forward, D2H] (run_graph)
         self.batch = _cabi.Batch()
         b = self.batch
         b.frame_utt, b.utt_begin, b.utt_end = self.frame_utt.data_ptr(), self.utt_begin.data_ptr(), self.utt_end.data_ptr()
@@ -360,9 +370,20 @@ class PreparedBatch:
         if L.n_frames > self.cap_frames or L.n_utt > self.cap_utts or L.n_chunks > self.cap_chunks:
             raise RuntimeError(f"batch of {L.n_frames} padded frames / {L.n_utt} utterances exceeds the prepared capacity "
                                f"({self.cap_frames} / {self.cap_utts})")
-        self.mel_host[:L.n_frames].zero_()
-        if self.noise_host is not None:
-            self.noise_host[:L.n_frames * plan.steps_per_frame].zero_()
+        # only the guard rows need clearing: every utterance row is overwritten by the next load (clearing the whole grid cost
+        # more host time than scattering the mels into it -- 10 MB per 32k-frame batch)
+        mh = self.mel_host.numpy()
+        nh = self.noise_host.numpy() if self.noise_host is not None else None
+        spf = plan.steps_per_frame
+        prev = 0
+        for u in range(L.n_utt + 1):
+            nxt = int(L.utt_begin[u]) if u < L.n_utt else L.n_frames
+            if nxt > prev:
+                mh[prev:nxt] = 0.0
+                if nh is not None:
+                    nh[prev * spf:nxt * spf] = 0.0
+            if u < L.n_utt:
+                prev = int(L.utt_end[u])
         self._bind(L)
         self.batch.utt_ids = None
         return self
@@ -428,6 +449,44 @@ class PreparedBatch:
     def wait_host(self, slot: int):
         _cabi.check(self.eng.lib, self.eng._handle, self.eng.lib.mbexwn_forward_host_wait(self.eng._handle, slot),
                     "mbexwn_forward_host_wait")
+
+    def run_graph(self, seed: int = 0):
+        """Host mel in -> host waveform out through a CUDA graph of [H2D, forward, D2H] captured once per (geometry, seed): one
+        graph launch instead of ~25 kernel launches and as many cuTensorMapEncode calls.  Falls back to run_host if the capture
+        fails (and stays there for this batch geometry)."""
+        eng = self.eng
+        key = int(seed)
+        g = self._graphs.get(key) if self._graphs is not None else None
+        if g is None and self._graphs is not None:
+            try:
+                n = self.layout.n_frames * eng.plan.hop
+                with torch.cuda.device(eng.device):
+                    side = torch.cuda.Stream(eng.device)
+                    side.wait_stream(torch.cuda.current_stream(eng.device))
+                    with torch.cuda.stream(side):               # warm-up outside the capture: one-time initialisations
+                        self.upload()
+                        self.run_device(seed)
+                    torch.cuda.current_stream(eng.device).wait_stream(side)
+                    torch.cuda.synchronize(eng.device)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        self.upload()
+                        self.run_device(seed)
+                        self.out_host[:n].copy_(self.out_dev[:n], non_blocking=True)
+                if len(self._graphs) >= 4:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key] = g
+            except Exception as e:                              # capture is an optimisation, never a requirement
+                print(f"mbexwn_vocoder_b200::note::CUDA graph capture failed ({type(e).__name__}: {e}); using plain launches",
+                      file=sys.stderr)
+                torch.cuda.synchronize(eng.device)
+                self._graphs = None
+                g = None
+        if g is None:
+            return self.run_host(seed)
+        with torch.cuda.device(eng.device):
+            g.replay()
+            torch.cuda.current_stream(eng.device).synchronize()
 
     def upload(self):
         F, spf = self.layout.n_frames, self.eng.plan.steps_per_frame

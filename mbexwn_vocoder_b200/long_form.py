@@ -7,13 +7,17 @@ window is kept.  With a context that covers the receptive field of every stage t
 un-chunked result, because every kernel works per row with a fixed summation order (tests/test_gpu_long_form.py).
 
 Three passes:
-  1. F0 pass  -- the F0 sub-net over windows with its own (small) context -> exact F0 track of the whole signal;
-  2. phase carry -- the unwrapped running sum of the wrapped 1000-sample chunk totals (host, float32, the reference's
-                    sequential association order), one value per cumsum chunk;
+  1. F0 pass  -- the F0 sub-net over the whole signal (one utterance of one forward that stops behind the sub-net; rows are
+                 independent, so this equals any chunked evaluation bit for bit) -> exact F0 track, left on the device;
+  2. phase carry -- the unwrapped running sum of the wrapped 1000-sample chunk totals (float32, the reference's sequential
+                    association order), one value per cumsum chunk: mbexwn_phase_carry on the device;
   3. main pass -- windows whose start is a multiple of the cumsum chunk (10 frames) with f0_override = exact F0 slice and
-                  phase_carry = the running sum before the window's first chunk.
+                  phase_carry = the running sum before the window's first chunk.  The windows are cut out of the
+                  device-resident mel / noise / F0 buffers by mbexwn_gather_rows and their cores are gathered into one
+                  device buffer the same way: after the upload of the mel the host only enqueues.
 Windows are batched up to `max_batch_frames` per call, so throughput comes from the same batched kernels as configs 2-4;
-the first window alone gives the first-chunk latency.
+the first window alone gives the first-chunk latency.  `host_loop=True` keeps the round-1 form (F0 track and phase carry
+through the host), used by the tests as a second opinion.
 """
 from __future__ import annotations
 
@@ -109,10 +113,12 @@ def _batches(windows: Sequence[Window], max_batch_frames: int) -> List[List[int]
 
 
 def synth_long(engine, mel: np.ndarray, noise: np.ndarray, chunk_frames: int = 400, precision: str = "f16f8",
-               max_batch_frames: int = 32768, first_alone: bool = True) -> Tuple[np.ndarray, Dict[str, float]]:
+               max_batch_frames: int = 32768, first_alone: bool = True, host_loop: bool = False) -> Tuple[np.ndarray, Dict[str, float]]:
     """mel (T, n_mel), noise (T * steps_per_frame,) standard normal -> waveform (T * hop,), timing info.
 
     `first_alone`: the first window is synthesised in a call of its own (first-chunk latency of a streaming client)."""
+    if not host_loop:
+        return _synth_long_device(engine, mel, noise, chunk_frames, precision, max_batch_frames, first_alone)
     plan: ModelPlan = engine.plan
     if plan.norm is not None:
         raise NotImplementedError("chunked synthesis with normalize_rms_from_mell is not built (the smoothed RMS spans "
@@ -201,5 +207,140 @@ def synth_long(engine, mel: np.ndarray, noise: np.ndarray, chunk_frames: int = 4
     info["total_s"] = time.perf_counter() - t0
     info["audio_s"] = T * hop / plan.sample_rate
     info["n_windows"] = len(main_wins)
+    info["context_frames"] = ctx
+    return out, info
+
+
+def _synth_long_device(engine, mel: np.ndarray, noise: np.ndarray, chunk_frames: int, precision: str, max_batch_frames: int,
+                       first_alone: bool) -> Tuple[np.ndarray, Dict[str, float]]:
+    """Chunked synthesis with the whole signal resident on the device (module docstring)."""
+    import ctypes as C
+
+    import torch
+
+    from . import _cabi
+    plan: ModelPlan = engine.plan
+    if plan.norm is not None:
+        raise NotImplementedError("chunked synthesis with normalize_rms_from_mell is not built (the smoothed RMS spans "
+                                  "window borders)")
+    mel = np.ascontiguousarray(mel, dtype=np.float32)
+    T = mel.shape[0]
+    ppf, spf, hop = plan.pulse_per_frame, plan.steps_per_frame, plan.hop
+    noise = np.asarray(noise, dtype=np.float32).reshape(-1)
+    if noise.size != T * spf:
+        raise RuntimeError(f"noise must hold {T * spf} draws, got {noise.size}")
+    chunk = int(engine.cfg.cumsum_chunk)
+    if chunk % ppf:
+        raise NotImplementedError("cumsum chunk is not a whole number of frames")
+    align = chunk // ppf
+    dev = engine.device
+    lib, handle = engine.lib, engine._handle
+    info: Dict[str, float] = {}
+    t0 = time.perf_counter()
+    ctx = main_context_frames(plan)
+    wins = plan_windows(T, chunk_frames, ctx, align)
+    out = np.empty(T * hop, dtype=np.float32)
+
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+
+        # ---- first window on its own (host buffers, cached geometry): it needs the F0 of its own frames only and a zero carry
+        first_done = False
+        if first_alone and len(wins) > 1:
+            w0 = wins[0]
+            f0_ctx = subnet_reach_frames(plan.pp_ops)
+            b = min(T, w0.stop + f0_ctx)
+            engine.set_option("stop_after_f0", 1)
+            try:
+                pbf = engine.prepare_cached([b], precision, with_noise=False)
+                pbf.load([mel[:b]])
+                pbf.upload()
+                pbf.run_device()
+                f0_first = pbf.tap_grid("F0")[engine.halo * ppf:(engine.halo + w0.stop) * ppf].clone()
+            finally:
+                engine.set_option("stop_after_f0", 0)
+            pb0 = engine.prepare_cached([w0.stop - w0.start], precision, with_noise=True, with_f0=True, with_carry=True)
+            pb0.load([mel[w0.start:w0.stop]], noise=[noise[w0.start * spf:w0.stop * spf]], carry=[0.0])
+            pb0.f0_dev[engine.halo * ppf:(engine.halo + w0.stop - w0.start) * ppf].copy_(f0_first[w0.start * ppf:])
+            pb0.run_host()
+            y = pb0.waveforms()[0]
+            out[w0.core0 * hop:w0.core1 * hop] = y[(w0.core0 - w0.start) * hop:(w0.core1 - w0.start) * hop]
+            info["first_chunk_latency_s"] = time.perf_counter() - t0
+            first_done = True
+
+        # ---- whole signal to the device; pass 1: F0 of the whole signal as one utterance (stays on the device) -----------
+        t_f0 = time.perf_counter()
+        pbF = engine.prepare_cached([T], precision, with_noise=False)
+        pbF.load([mel])
+        pbF.upload()
+        engine.set_option("stop_after_f0", 1)
+        try:
+            pbF.run_device()
+        finally:
+            engine.set_option("stop_after_f0", 0)
+        halo = engine.halo
+        f0_full = pbF.tap_grid("F0")[halo * ppf:(halo + T) * ppf]          # view into the workspace: copied before the next forward
+        key = ("long_form", T)
+        bufs = getattr(engine, "_long_bufs", {}).get(key)
+        if bufs is None:
+            n_chunks = -(-T * ppf // chunk)
+            bufs = {"f0": torch.empty(T * ppf, dtype=torch.float32, device=dev),
+                    "noise": torch.empty(T * spf, dtype=torch.float32, device=dev),
+                    "noise_pin": torch.empty(T * spf, dtype=torch.float32).pin_memory(),
+                    "run": torch.empty(n_chunks, dtype=torch.float32, device=dev),
+                    "out": torch.empty(T * hop, dtype=torch.float32, device=dev),
+                    "out_pin": torch.empty(T * hop, dtype=torch.float32).pin_memory()}
+            engine._long_bufs = {key: bufs}
+        bufs["f0"].copy_(f0_full)
+        mel_full = pbF.mel_dev[halo:halo + T]                              # the whole mel is already on the device
+        bufs["noise_pin"].numpy()[:] = noise
+        bufs["noise"].copy_(bufs["noise_pin"], non_blocking=True)
+        # ---- pass 2: phase carry before every cumsum chunk ----------------------------------------------------------
+        _cabi.check(lib, handle, lib.mbexwn_phase_carry(handle, bufs["f0"].data_ptr(), T * ppf, bufs["run"].data_ptr(), stream),
+                    "mbexwn_phase_carry")
+        info["f0_pass_s"] = time.perf_counter() - t_f0
+
+        # ---- pass 3: the windows, batched; cut out and gathered back on the device -----------------------------------
+        t1 = time.perf_counter()
+        rest = list(range(1 if first_done else 0, len(wins)))
+        groups = [[rest[j] for j in g] for g in _batches([wins[i] for i in rest], max_batch_frames)] if rest else []
+
+        def gather(src, dst, row_elems, seg_dev, n_seg, max_rows):
+            _cabi.check(lib, handle, lib.mbexwn_gather_rows(handle, src.data_ptr(), dst.data_ptr(), row_elems, seg_dev.data_ptr(),
+                                                           n_seg, max_rows, stream), "mbexwn_gather_rows")
+        for gi, grp in enumerate(groups):
+            lens = [wins[i].stop - wins[i].start for i in grp]
+            pb = engine.prepare_cached(lens, precision, with_noise=True, with_f0=True, with_carry=True, slot=gi & 1)
+            L = pb.layout
+            seg_in = np.stack([np.array([wins[i].start for i in grp], dtype=np.int64), L.utt_begin.astype(np.int64),
+                               np.array(lens, dtype=np.int64)], axis=1)
+            seg_out = np.stack([L.utt_begin.astype(np.int64) + np.array([wins[i].core0 - wins[i].start for i in grp], dtype=np.int64),
+                                np.array([wins[i].core0 for i in grp], dtype=np.int64),
+                                np.array([wins[i].core1 - wins[i].core0 for i in grp], dtype=np.int64)], axis=1)
+            seg = torch.from_numpy(np.concatenate([seg_in, seg_out]).reshape(-1)).to(dev, non_blocking=True)
+            n = len(grp)
+            seg_i, seg_o = seg[:3 * n], seg[3 * n:]
+            gather(mel_full, pb.mel_dev, plan.mel_channels, seg_i, n, max(lens))
+            gather(bufs["noise"], pb.noise_dev, spf, seg_i, n, max(lens))
+            gather(bufs["f0"], pb.f0_dev, ppf, seg_i, n, max(lens))
+            idx = torch.from_numpy(np.array([wins[i].start // align for i in grp], dtype=np.int64)).to(dev, non_blocking=True)
+            pb.carry_dev[:n].copy_(bufs["run"].index_select(0, idx))
+            pb.run_device()
+            gather(pb.out_dev, bufs["out"], hop, seg_o, n, max(w.core1 - w.core0 for w in (wins[i] for i in grp)))
+            if gi == 0 and not first_done:
+                # first audio of a call without a separate first window: the first group's cores
+                c0, c1 = wins[grp[0]].core0 * hop, wins[grp[0]].core1 * hop
+                bufs["out_pin"][c0:c1].copy_(bufs["out"][c0:c1], non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+                info["first_chunk_latency_s"] = time.perf_counter() - t0
+        if rest:
+            c0, c1 = wins[rest[0]].core0 * hop, wins[rest[-1]].core1 * hop
+            bufs["out_pin"][c0:c1].copy_(bufs["out"][c0:c1], non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            out[c0:c1] = bufs["out_pin"].numpy()[c0:c1]
+        info["main_pass_s"] = time.perf_counter() - t1
+    info["total_s"] = time.perf_counter() - t0
+    info["audio_s"] = T * hop / plan.sample_rate
+    info["n_windows"] = len(wins)
     info["context_frames"] = ctx
     return out, info

@@ -59,14 +59,31 @@ class ShardStats:
     extra: Dict[str, float] = field(default_factory=dict)
 
 
+def _copy_all(pool, jobs):
+    """jobs: list of (dst_view, src) -- NumPy copies release the GIL, so a few host threads move the utterances in parallel."""
+    if pool is None or len(jobs) < 8:
+        for dst, src in jobs:
+            dst[...] = src
+        return
+    n = pool._max_workers
+
+    def part(k):
+        for dst, src in jobs[k::n]:
+            dst[...] = src
+    list(pool.map(part, range(n)))
+
+
 def run_shard(inv, get_mel: Callable[[int], np.ndarray], lengths: Sequence[int], ids: Sequence[int], out,
-              max_batch_frames: int = 32768, seed: int = 0, precision: Optional[str] = None, keep: bool = True) -> ShardStats:
+              max_batch_frames: int = 32768, seed: int = 0, precision: Optional[str] = None, keep: bool = True,
+              host_threads: int = 4) -> ShardStats:
     """Synthesize the utterances `ids` on `inv`'s GPU: pipelined batches, waveforms gathered on the host.
 
     get_mel(i) returns the (T_i, n_mel) float32 mel of utterance i (a view is fine: it is copied into the pinned grid).
-    out: a dict (out[id] = a fresh copy of the waveform) or a callable out(id, view) that receives a view of the pinned grid
-    and must copy what it keeps (a caller that owns one big result buffer copies straight into its slice).
-    keep = False drops the waveforms after touching them (warm-up)."""
+    out: a dict (out[id] = a fresh copy of the waveform) or a callable out(id, view) that returns the destination array the
+    view of the pinned grid is to be copied into (a caller that owns one big result buffer returns its slice), or None after
+    consuming the view itself.
+    keep = False drops the waveforms after touching them (warm-up).
+    host_threads: threads that scatter the mels into / gather the waveforms out of the pinned grids (memcpy bound)."""
     import torch
     eng, plan = inv.model, inv.plan
     precision = precision or inv.precision
@@ -86,6 +103,9 @@ def run_shard(inv, get_mel: Callable[[int], np.ndarray], lengths: Sequence[int],
                      for _ in range(2)]
         eng._shard_slots = {key: slots}             # one geometry is kept: a serving loop calls with the same budget
     in_flight: List[Optional[List[int]]] = [None, None]
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=host_threads) if host_threads > 1 else None
+    hop = plan.hop
 
     def drain(s: int):
         grp = in_flight[s]
@@ -105,11 +125,14 @@ def run_shard(inv, get_mel: Callable[[int], np.ndarray], lengths: Sequence[int],
         else:
             waves = slots[s].waveforms()
         if keep and callable(out):
-            for i, w in zip(grp, waves):
-                out(i, w)
+            jobs = [out(i, w) for i, w in zip(grp, waves)]        # a callable returns the destination view (or copies itself)
+            jobs = [(d, w) for d, w in zip(jobs, waves) if d is not None]
+            _copy_all(pool, jobs)
         elif keep:
-            for i, w in zip(grp, waves):
-                out[i] = np.array(w, dtype=np.float32, copy=True)
+            dsts = [np.empty(int(lengths[i]) * hop, dtype=np.float32) for i in grp]
+            _copy_all(pool, list(zip(dsts, waves)))
+            for i, d in zip(grp, dsts):
+                out[i] = d
         else:
             for i, w in zip(grp, waves):
                 _ = float(w[0])                     # touch only
@@ -123,7 +146,8 @@ def run_shard(inv, get_mel: Callable[[int], np.ndarray], lengths: Sequence[int],
             t0 = time.perf_counter()
             pb = slots[s].rebind([int(lengths[i]) for i in grp])
             pb.set_utt_ids(grp)
-            pb.load([get_mel(i) for i in grp])
+            L, mh = pb.layout, pb.mel_host.numpy()
+            _copy_all(pool, [(mh[L.utt_begin[k]:L.utt_end[k]], get_mel(i)) for k, i in enumerate(grp)])
             st.host_prep_s += time.perf_counter() - t0
             pb.begin_host(s, seed=seed)
             in_flight[s] = grp
@@ -134,6 +158,8 @@ def run_shard(inv, get_mel: Callable[[int], np.ndarray], lengths: Sequence[int],
         drain(last)
         if precision == "f16f8":
             eng.range_status(reset=True)
+    if pool is not None:
+        pool.shutdown()
     st.n_utts, st.batches = len(ids), len(batches)
     st.wall_s = time.perf_counter() - t_start
     return st

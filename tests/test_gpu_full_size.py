@@ -29,6 +29,8 @@ def _run(model_id, precision, batch, frames, picks, snr_bar, index_exact=True):
     pb.run_host()
     full = [w.copy() for w in pb.waveforms()]
     index = pb.tap("index")
+    stage_names = ("pulse", "wn_out", "subbands", "excitation")
+    stages = {k: [np.array(v[u], copy=True) for u in picks] for k, v in ((k, pb.tap(k)) for k in stage_names)}
     assert all(np.isfinite(w).all() and w.shape == (frames * plan.hop,) for w in full)
     pb.run_host()                                            # determinism over the whole batch
     again = pb.waveforms()
@@ -45,7 +47,19 @@ def _run(model_id, precision, batch, frames, picks, snr_bar, index_exact=True):
             assert np.array_equal(ref["index"][0].reshape(-1), index[u].reshape(-1)), f"utterance {u}: wavetable index"
         f0_ref = oracle.generate_f0(torch.as_tensor(mels[u][None])).numpy()
         assert np.abs(f0 - f0_ref).max() <= (1e-4 if precision != "bf16" else 5e-2) * np.abs(f0_ref).max()
+        # per-stage bar of north_star at FULL size: the taps of this utterance out of the full batch against the oracle
+        # (fp32-accurate path: 1e-4 of the stage peak; bf16: the stages are reported, the bar is the waveform SNR)
+        for k in stage_names:
+            got = stages[k][picks.index(u)].reshape(-1)
+            r = np.asarray(ref[k][0], dtype=np.float64).reshape(-1)
+            e = float(np.abs(got - r).max() / np.abs(r).max())
+            print(f"{model_id} {precision} full batch, utterance {u}, stage {k}: max|err|/peak {e:.3e}")
+            if precision != "bf16":
+                assert e <= 1e-4, (u, k, e)
         assert _snr(ref["waveform"][0], full[u]) >= snr_bar, (u, _snr(ref["waveform"][0], full[u]))
+        e = float(np.abs(full[u] - ref["waveform"][0]).max() / np.abs(ref["waveform"][0]).max())
+        if precision != "bf16":
+            assert e <= 1e-4, (u, "waveform", e)
     del pb
     inv.model.close()
     torch.cuda.empty_cache()

@@ -168,7 +168,7 @@ def test_fused_layer_kernel_equals_two_launch_path(engine, speech_setup, precisi
     engine.set_option("tc_cta_group", 1)
     for u in range(len(lengths)):
         assert np.all(np.isfinite(res[1][0][u]))
-        tol = 2e-3 if precision == "bf16" else 5e-5          # bf16 re-rounds the activations of every layer
+        tol = 3e-2 if precision == "bf16" else 5e-5          # bf16 re-rounds the activations of every layer
         for a, b, what in ((res[0][1]["wn_out"][u], res[1][1]["wn_out"][u], "wn_out"), (res[0][0][u], res[1][0][u], "waveform")):
             assert np.abs(a - b).max() <= tol * max(np.abs(a).max(), 1e-30), f"{what} of utterance {u}"
 
