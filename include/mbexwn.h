@@ -236,8 +236,16 @@ MBEXWN_API int mbexwn_last_launch_count(mbexwn_handle_t h);
  *   paths agree to ~1e-5 of peak (different K order), so the default never switches with the batch size;
  * "tc_slab" (default 1): the dilated taps of the fused kernel share one A slab per 64-channel block (row-shifted MMA operand
  *   views of one shared-memory tile); 0: one TMA tile per tap (bit-identical results, more L2 -> SM traffic);
+ * "tc_cluster" (default 4): CTAs per cluster of the fused kernel.  4: two CTA pairs walk the same weight-tile sequence and
+ *   share every weight (B) tile load by TMA multicast, which halves the dominant L2 -> SM stream (bit-identical results);
+ *   used when every pair has at least two 256-row tiles and the device keeps >= 128 SMs busy with clusters of 4
+ *   (cudaOccupancyMaxActiveClusters), else 2;
  * "tc_trace" (default 0): k > 0 records per-tile cycle stamps of the fused kernel of layer k - 1 (mbexwn_tc_trace_read). */
 MBEXWN_API int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value);
+
+/* What the last forward did: "tc_last_fused" (1: fused layer kernel), "tc_last_cluster" (CTAs per cluster of the fused
+ * kernel, 2 or 4), "tc_max_quads" (clusters of 4 the device holds at once; 0: not asked yet, -1: the query failed). */
+MBEXWN_API int mbexwn_get_info(mbexwn_handle_t h, const char* name, int32_t* value);
 
 /* Device time of each stage of the last forward (needs "stage_timing"); ms[MBEXWN_N_STAGES] in the order
  * f0_net, excitation, cond_conv, wavenet, post_pqmf, vtf_net, stft_ola.  Synchronises on the last event. */

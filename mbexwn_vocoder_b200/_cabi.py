@@ -109,6 +109,7 @@ SYMBOLS = {
                              C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mbexwn_last_launch_count": (C.c_int, [C.c_void_p]),
     "mbexwn_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
+    "mbexwn_get_info": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32)]),
     "mbexwn_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mbexwn_wavenet_launch_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "mbexwn_phase_carry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

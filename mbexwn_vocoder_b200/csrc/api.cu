@@ -861,6 +861,15 @@ int mbexwn_tap(mbexwn_handle_t h, const char* name, int32_t n_frames, int32_t n_
 
 int mbexwn_last_launch_count(mbexwn_handle_t h) { return h ? h->launches : 0; }
 
+int mbexwn_get_info(mbexwn_handle_t h, const char* name, int32_t* value) {
+    if (!h || !name || !value) return MBEXWN_ERR_INVALID;
+    if (!strcmp(name, "tc_last_fused")) { *value = h->tc.last_fused; return MBEXWN_OK; }
+    if (!strcmp(name, "tc_last_cluster")) { *value = h->tc.last_cluster; return MBEXWN_OK; }
+    if (!strcmp(name, "tc_max_quads")) { *value = h->tc.last_quads; return MBEXWN_OK; }
+    h->error = std::string("unknown info: ") + name;
+    return MBEXWN_ERR_INVALID;
+}
+
 int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value) {
     if (!h || !name) return MBEXWN_ERR_INVALID;
     if (!strcmp(name, "debug_taps")) { h->debug_taps = value ? 1 : 0; return MBEXWN_OK; }
@@ -874,6 +883,8 @@ int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value) {
     if (!strcmp(name, "tc_fused")) { h->tc.fused = value < 0 ? 0 : (value > 2 ? 2 : value); return MBEXWN_OK; }
     if (!strcmp(name, "tc_slab")) { h->tc.slab = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "tc_ring_a")) { h->tc.n_a = value; return MBEXWN_OK; }
+    if (!strcmp(name, "tc_l2_hints")) { h->tc.l2_hints = value; return MBEXWN_OK; }
+    if (!strcmp(name, "tc_cluster")) { h->tc.cluster = value == 4 ? 4 : 2; return MBEXWN_OK; }
     if (!strcmp(name, "tc_trace")) { h->tc.trace_on = value; return MBEXWN_OK; }
     if (!strcmp(name, "tc8_h_lo")) { h->tc.sh_h_lo = value; return MBEXWN_OK; }
     if (!strcmp(name, "tc8_a_lo")) { h->tc.sh_a_lo = value; return MBEXWN_OK; }

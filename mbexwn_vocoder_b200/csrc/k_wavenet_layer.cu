@@ -114,6 +114,11 @@ struct alignas(64) LayerParams {
     int slab_bytes;          // bytes one gate slab load brings (slab rows x 128)
     // shared memory carve-up (bytes from the 1024-aligned base)
     int slab_slot, n_a, off_b, n_b, b_slot, off_stg, off_cond, cond_ld;
+    // L2 eviction policies of the TMA traffic (tc_common.cuh: L2_EVICT_*): the layer streams 0.64 GB in and 0.64 GB out through
+    // a 126 MB L2 that also has to hold, for one step, the pairs' activation scratch and the residual rows their next res
+    // tiles read back
+    unsigned long long pol_w, pol_h, pol_rmw, pol_scr_st, pol_scr_ld, pol_out;
+    int cluster;             // CTAs per cluster: 2 (one pair) or 4 (two pairs sharing the B tiles by multicast)
     int f16;                 // 16-bit operands are fp16 (MBEXWN_PREC_F16F8), else bf16
     long long rows;
     int tiles_mg;            // 256-row M tiles
@@ -134,7 +139,8 @@ struct alignas(64) LayerParams {
     int* range_flag;         // f16f8 range guard (tc_common.cuh: range_check8), or nullptr
     uint32_t* trace;         // TRACE builds: [cta][role 0..2][TRACE_SLOTS][4]
     int debug;               // TRACE builds only, timing experiments (results are wrong): 1 = no B loads, 2 = no A loads,
-                             // 4 = no MMAs are issued, 8 = the epilogue skips its math
+                             // 4 = no MMAs are issued, 8 = the epilogue skips its math, 64 = no loads of the old residual blocks,
+                             // 128 = no stores (scratch, layer output)
 };
 
 __device__ __forceinline__ uint32_t clk32() {
@@ -377,10 +383,20 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    const int rank = (int)cluster_ctarank();
+    // Cluster of 2 (one CTA pair) or 4 (two pairs that walk the same B tile sequence and share every B load by multicast:
+    // the weights are re-streamed from the L2 for every M tile, and at one pair per cluster the L2 -> SM traffic of the 148
+    // CTAs, ~39 B/clk/SM, is what bounds the kernel -- the L2 delivers ~42 B/clk/SM).
+    const int crank = (int)cluster_ctarank();
+    const int rank = crank & 1;                                     // rank inside the CTA pair
+    const int pair_in_cluster = crank >> 1;
+    const uint32_t lead_rank = (uint32_t)(crank & ~1);              // cluster rank of this pair's leader CTA
     const bool leader = rank == 0;
+    const bool quad = p.cluster == 4;
     const int group = blockIdx.x >> 1, n_groups = gridDim.x >> 1;
-    const int n_j = group < p.tiles_mg ? (p.tiles_mg - group + n_groups - 1) / n_groups : 0;    // M tiles of this pair
+    // M tiles of this pair; the pairs of a cluster run the same number of steps (the second one may end on a tile past the
+    // last row: loads are zero-filled, stores clipped, the epilogue's row checks fail)
+    const int group0 = quad ? (group & ~1) : group;
+    const int n_j = group0 < p.tiles_mg ? (p.tiles_mg - group0 + n_groups - 1) / n_groups : 0;
     // rows of this CTA in M tile j of the pair / in the act scratch
     auto m0_of = [&](int j) { return ((group + n_groups * j) * 2 + rank) * TILE_M; };
     auto scr_of = [&](int j) { return ((group * 2 + (j & 1)) * 2 + rank) * TILE_M; };
@@ -397,7 +413,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
     }
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < NA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
-        for (int s = 0; s < p.n_b; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+        for (int s = 0; s < p.n_b; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], quad ? 2 : 1); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], 2 * EW);
@@ -423,10 +439,16 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
     if (warp == 0) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ===== TMA producer: the whole warp walks the K loops, one elected lane issues =====
-        uint32_t sa = 0, pha = 0, sb = 0, phb = 0, tile_it = 0;     // ring slots and phase parities
-        const uint32_t lfa0 = map_to_cta(smem_u32(&full_a[0]), 0), lfb0 = map_to_cta(smem_u32(&full_b[0]), 0);
+        // In a cluster of 4 the two pairs take turns with the B tiles: the CTAs of pair (entry & 1) load their half of the
+        // tile and multicast it to the CTA of the same rank in the other pair.  A slot is free when BOTH pairs have consumed
+        // it (empty_b counts two commits, each multicast to the four CTAs); every leader arms its own full barrier, whoever
+        // loads -- the bytes of the other pair's load may be counted before that (the tx count goes negative meanwhile).
+        uint32_t sa = 0, pha = 0, sb = 0, phb = 0, tile_it = 0, ent = 0;     // ring slots and phase parities, B tiles so far
+        const uint32_t lfa0 = map_to_cta(smem_u32(&full_a[0]), lead_rank), lfb0 = map_to_cta(smem_u32(&full_b[0]), lead_rank);
+        const uint32_t fb0_mc = smem_u32(&full_b[0]) & 0xFEFFFFFFu;  // multicast form: this offset in the even CTA of each destination's pair
+        const uint16_t mc_mask = (uint16_t)(0x5u << rank);
         uint32_t wait_cyc = 0;
-        auto load_a = [&](const CUtensorMap* tma, uint32_t a_bytes, int col, int row) {
+        auto load_a = [&](const CUtensorMap* tma, uint32_t a_bytes, int col, int row, uint64_t pol) {
             const uint32_t t0 = TRACE ? clk32() : 0u;
             mbar_wait(&empty_a[sa], pha ^ 1);
             if (TRACE) wait_cyc += clk32() - t0;
@@ -435,35 +457,40 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                     if (leader) mbar_arrive(&full_a[sa]);
                 } else {
                     if (leader) mbar_expect_tx(&full_a[sa], 2 * a_bytes);
-                    tma_load_2d_2sm(tma, lfa0 + sa * 8, ring_a + sa * p.slab_slot, col, row);
+                    tma_load_2d_2sm_hint(tma, lfa0 + sa * 8, ring_a + sa * p.slab_slot, col, row, pol);
                 }
             }
             __syncwarp();
             if (++sa == (uint32_t)p.n_a) { sa = 0; pha ^= 1; }
         };
         auto load_b = [&](const CUtensorMap* tmb, uint32_t b_bytes, int col, int row) {
-            const uint32_t t0 = TRACE ? clk32() : 0u;
-            mbar_wait(&empty_b[sb], phb ^ 1);
-            if (TRACE) wait_cyc += clk32() - t0;
-            if (elect_one()) {
-                if (dbg & 1) {
-                    if (leader) mbar_arrive(&full_b[sb]);
-                } else {
-                    if (leader) mbar_expect_tx(&full_b[sb], 2 * b_bytes);
-                    tma_load_2d_2sm(tmb, lfb0 + sb * 8, ring_b + sb * p.b_slot, col, row);
+            const bool mine = !quad || (int)(ent & 1u) == pair_in_cluster;
+            ++ent;
+            if (mine || leader) {
+                const uint32_t t0 = TRACE ? clk32() : 0u;
+                mbar_wait(&empty_b[sb], phb ^ 1);
+                if (TRACE) wait_cyc += clk32() - t0;
+                if (elect_one()) {
+                    if (dbg & 1) {
+                        if (leader) mbar_arrive(&full_b[sb]);
+                    } else {
+                        if (leader) mbar_expect_tx(&full_b[sb], 2 * b_bytes);
+                        if (!quad) tma_load_2d_2sm_hint(tmb, lfb0 + sb * 8, ring_b + sb * p.b_slot, col, row, p.pol_w);
+                        else if (mine) tma_load_2d_2sm_mc(tmb, fb0_mc + sb * 8, ring_b + sb * p.b_slot, col, row, mc_mask, p.pol_w);
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
             if (++sb == (uint32_t)p.n_b) { sb = 0; phb ^= 1; }
         };
         auto load_tile = [&](const CUtensorMap* tma, uint32_t a_bytes, const CUtensorMap* tmb, uint32_t b_bytes, const KEnt* ke, int n,
-                             int a_row0, int b_row) {
+                             int a_row0, int b_row, uint64_t pol_a) {
             wait_cyc = 0;
             int4 e = *reinterpret_cast<const int4*>(ke);            // {a_col, a_row | a_view << 16, b_col, flags}
             for (int i = 0; i < n; ++i) {
                 const int4 cur = e;
                 if (i + 1 < n) e = *reinterpret_cast<const int4*>(ke + i + 1);
-                if (cur.w & KF_NEW_SLAB) load_a(tma, a_bytes, cur.x, a_row0 + (int)(short)(cur.y & 0xffff));
+                if (cur.w & KF_NEW_SLAB) load_a(tma, a_bytes, cur.x, a_row0 + (int)(short)(cur.y & 0xffff), pol_a);
                 load_b(tmb, b_bytes, cur.z, b_row);
             }
             if (TRACE && lane == 0 && tile_it < TRACE_SLOTS) {
@@ -476,14 +503,14 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
             if (j < n_j)
                 for (int t = 0; t < p.n_t1; ++t)
                     load_tile(&p.tm_hs, (uint32_t)p.slab_bytes, &p.tm_w1[p.t1[t].bmap], (uint32_t)(p.t1[t].w >> 1) * 128u, k1, p.n_k1, m0_of(j),
-                              p.t1[t].n0 + rank * (p.t1[t].w >> 1));
+                              p.t1[t].n0 + rank * (p.t1[t].w >> 1), p.pol_h);
             if (j > 0) {
                 // the act of M tile j - 1 must have landed in the scratch (writes of the async proxy, completed by the manager)
                 mbar_wait(&act_ready[(j - 1) & 1], ((j - 1) >> 1) & 1);
                 asm volatile("fence.proxy.async;" ::: "memory");
                 for (int t = 0; t < p.n_t2; ++t)
                     load_tile(&p.tm_scr, (uint32_t)(TILE_M * 128), &p.tm_w2[p.t2[t].bmap], (uint32_t)(p.t2[t].w >> 1) * 128u, k2, p.n_k2, scr_of(j - 1),
-                              p.t2[t].n0 + rank * (p.t2[t].w >> 1));
+                              p.t2[t].n0 + rank * (p.t2[t].w >> 1), p.pol_scr_ld);
             }
         }
     } else if (warp == 1) {
@@ -497,6 +524,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
             const uint32_t a_desc0 = a_base >> 4, b_desc0 = b_base >> 4;
             uint32_t a_desc = a_desc0, b_desc = b_desc0;            // descriptor word of slot sa / sb
             uint32_t cur_a_desc = a_desc0, cur_a = 0;
+            const uint16_t mask_pair = (uint16_t)(3u << lead_rank), mask_b = quad ? (uint16_t)0xF : mask_pair;
             // one K block: 4 MMAs on (A view, B slot sb), then the slot(s) go back to the producer
             auto block = [&](const uint32_t tacc, const uint32_t idesc, const int2 e, const int mode, const bool last) {
                 // e.x = A view offset in 16-byte units, e.y = flags; mode 0: e4m3, 1: 16-bit
@@ -524,9 +552,9 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                             for (int k = 1; k < 4; ++k) tc_mma_bf16_2sm(tacc, da + 2 * k, db + 2 * k, idesc, 1u);
                         }
                     }
-                    tc_commit_2sm(&empty_b[sb]);
-                    if (flags & KF_LAST_OF_SLAB) tc_commit_2sm(&empty_a[cur_a]);
-                    if (last) tc_commit_2sm(&tmem_full[(tile_it & 1)]);
+                    tc_commit_mc(&empty_b[sb], mask_b);
+                    if (flags & KF_LAST_OF_SLAB) tc_commit_mc(&empty_a[cur_a], mask_pair);
+                    if (last) tc_commit_mc(&tmem_full[(tile_it & 1)], mask_pair);
                 }
                 __syncwarp();
                 b_desc += b_slot16;
@@ -592,9 +620,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                         mbar_arrive(&stg_avail[buf]);
                     } else {
                         const int col = 64 * (pe - p.n_gate_blk), row0 = m0_of(pj - 1);
+                        if (dbg & 64) { mbar_arrive(&stg_avail[buf]); ++pb; more_p = advance(pj, pe); continue; }
                         mbar_expect_tx(&stg_avail[buf], STG_BYTES);
-                        tma_load_2d(&p.tm_h, &stg_avail[buf], stg + buf * STG_BYTES, col, row0);
-                        tma_load_2d(&p.tm_h, &stg_avail[buf], stg + buf * STG_BYTES + TILE_M * 128, p.cpad + col, row0);
+                        tma_load_2d_hint(&p.tm_h, &stg_avail[buf], stg + buf * STG_BYTES, col, row0, p.pol_rmw);
+                        tma_load_2d_hint(&p.tm_h, &stg_avail[buf], stg + buf * STG_BYTES + TILE_M * 128, p.cpad + col, row0, p.pol_rmw);
                     }
                     ++pb;
                     more_p = advance(pj, pe);
@@ -609,15 +638,17 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                 const uint32_t buf = sb % NSTG;
                 mbar_wait(&stg_ready[buf], (sb / NSTG) & 1);
                 const uint8_t* t_hi = stg + buf * STG_BYTES;
-                if (se < p.n_gate_blk) {
+                if (dbg & 128) {
+                    if (se == p.n_gate_blk - 1) pending_act = sj;
+                } else if (se < p.n_gate_blk) {
                     const int col = 64 * se, row0 = scr_of(sj);
-                    tma_store_2d(&p.tm_scr, t_hi, col, row0);
-                    if (p.out_f16f8 || p.write_lo) tma_store_2d(&p.tm_scr, t_hi + TILE_M * 128, p.cpad + col, row0);
+                    tma_store_2d_hint(&p.tm_scr, t_hi, col, row0, p.pol_scr_st);
+                    if (p.out_f16f8 || p.write_lo) tma_store_2d_hint(&p.tm_scr, t_hi + TILE_M * 128, p.cpad + col, row0, p.pol_scr_st);
                     if (se == p.n_gate_blk - 1) pending_act = sj;
                 } else {
                     const int col = 64 * (se - p.n_gate_blk), row0 = m0_of(sj - 1);
-                    tma_store_2d(&p.tm_hout, t_hi, col, row0);
-                    tma_store_2d(&p.tm_hout, t_hi + TILE_M * 128, p.cpad + col, row0);
+                    tma_store_2d_hint(&p.tm_hout, t_hi, col, row0, p.pol_out);
+                    tma_store_2d_hint(&p.tm_hout, t_hi + TILE_M * 128, p.cpad + col, row0, p.pol_out);
                 }
                 tma_store_commit();
                 ++sb;
@@ -646,7 +677,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
         const int q4 = warp & 3, part = (warp - 4) >> 2;
         EpiState es{smem, stg, 0u, 0u};
         uint32_t tile_it = 0, gt = 0;
-        const uint32_t lempty0 = map_to_cta(smem_u32(&tmem_empty[0]), 0);
+        const uint32_t lempty0 = map_to_cta(smem_u32(&tmem_empty[0]), lead_rank);
         const int rl = q4 * 32 + lane;                              // row of this thread inside the CTA's 128 rows
         auto wait_tile = [&](uint32_t& t0, uint32_t& t1) -> uint32_t {
             const uint32_t as = tile_it & 1, aph = (tile_it >> 1) & 1;
@@ -770,7 +801,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
 
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                                             // nobody leaves while the pair still uses its smem / TMEM
+    cluster_sync_all();                                             // nobody leaves while the cluster still uses its smem / TMEM
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -962,13 +993,20 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
     p.bias2 = a.bias2; p.skip = a.skip; p.skip_ld = a.skip_ld; p.skip_c = a.skip_c; p.res_cols = a.res_cols; p.first = a.first;
     p.grid = a.grid;
     p.range_flag = a.range_flag;
+    if (st.l2_hints) {
+        p.pol_w = L2_EVICT_LAST; p.pol_h = L2_EVICT_NORMAL; p.pol_rmw = L2_EVICT_FIRST;
+        p.pol_scr_st = L2_EVICT_LAST; p.pol_scr_ld = L2_EVICT_LAST; p.pol_out = L2_EVICT_FIRST;
+        if (st.l2_hints >= 2) p.pol_h = L2_EVICT_LAST;
+        if (st.l2_hints >= 3) p.pol_scr_ld = L2_EVICT_FIRST;       // the scratch rows are dead once the res tiles have read them
+    } else {
+        p.pol_w = p.pol_h = p.pol_rmw = p.pol_scr_st = p.pol_scr_ld = p.pol_out = L2_EVICT_NORMAL;
+    }
     p.trace = reinterpret_cast<uint32_t*>(a.trace);
     p.debug = a.trace ? st.debug : 0;
 
     int groups = groups_max;
     if (p.tiles_mg < groups) groups = p.tiles_mg;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(groups * 2);
     cfg.blockDim = dim3(L_THREADS);
     cfg.dynamicSmemBytes = (size_t)smem_bytes;
     cfg.stream = s;
@@ -979,6 +1017,29 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    // Clusters of 4 when every pair has work for several steps.  How many of them the device holds at once depends on the
+    // GPC sizes (a cluster lives inside one GPC), so ask: the persistent schedule needs all of them resident.
+    p.cluster = 2;
+    if (st.cluster == 4 && p.tiles_mg >= 2 * groups_max) {
+        static int max_quads[64] = {0};
+        int& mq = max_quads[dev & 63];
+        if (mq == 0) {
+            cfg.gridDim = dim3(a.sm_count / 4 * 4);
+            attr[0].val.clusterDim.x = 4;
+            int n = 0;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&n, wn_layer_kernel<false>, &cfg);
+            mq = (e == cudaSuccess && n > 0) ? n : -1;
+            cudaGetLastError();
+        }
+        if (mq > 0 && 4 * mq >= st.cluster_min_sms) {
+            p.cluster = 4;
+            groups = 2 * (mq < a.sm_count / 4 ? mq : a.sm_count / 4);
+        }
+        st.last_quads = mq;
+    }
+    cfg.gridDim = dim3(groups * 2);
+    attr[0].val.clusterDim.x = p.cluster;
+    st.last_cluster = p.cluster;
     cudaError_t e = a.trace ? cudaLaunchKernelEx(&cfg, wn_layer_kernel<true>, p) : cudaLaunchKernelEx(&cfg, wn_layer_kernel<false>, p);
     if (e != cudaSuccess) return fail(std::string("fused layer kernel: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
     return MBEXWN_OK;

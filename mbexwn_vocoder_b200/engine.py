@@ -137,6 +137,7 @@ class Engine:
         self.last_layout: Optional[FrameGridLayout] = None
         self._last = None
         self.use_graphs = True
+        self._aux_stream = None
 
     # ---- weights / constants ----------------------------------------------------------------------
     def _register(self, name: str, array: np.ndarray):
@@ -221,6 +222,12 @@ class Engine:
         _cabi.check(self.lib, self._handle, rc, "mbexwn_k_tc_gemm_f16f8")
         return out
 
+    def aux_stream(self):
+        """Side stream for small asynchronous uploads (batch geometry) that must not queue behind a running forward."""
+        if self._aux_stream is None:
+            self._aux_stream = torch.cuda.Stream(self.device)
+        return self._aux_stream
+
     def range_status(self, reset: bool = True) -> int:
         """Sticky range-guard word of the f16f8 path (include/mbexwn.h: mbexwn_range_status): bit 0 = a residual-stream value
         left the range of the e4m3 hi8 plane (|x| > 448), bit 1 = beyond 60000 (fp16).  Call after the forward's stream has
@@ -231,6 +238,13 @@ class Engine:
 
     def set_option(self, name: str, value: int):
         _cabi.check(self.lib, self._handle, self.lib.mbexwn_set_option(self._handle, name.encode(), value), "set_option")
+
+    def get_info(self, name: str) -> int:
+        """mbexwn_get_info: what the last forward did ("tc_last_fused", "tc_last_cluster", "tc_max_quads")."""
+        import ctypes
+        v = ctypes.c_int32(0)
+        _cabi.check(self.lib, self._handle, self.lib.mbexwn_get_info(self._handle, name.encode(), ctypes.byref(v)), "get_info")
+        return int(v.value)
 
     # ---- forward ----------------------------------------------------------------------------------
     def _ensure_workspace(self, nbytes: int) -> torch.Tensor:
@@ -321,10 +335,20 @@ class PreparedBatch:
         self.cap_frames, self.cap_utts = F, U
         # worst case of ceil(T_u * pulse_per_frame / chunk) summed over the utterances
         self.cap_chunks = max(L.n_chunks, -(-F * plan.pulse_per_frame // eng.cfg.cumsum_chunk) + U)
-        self.frame_utt = torch.full((F,), -1, dtype=torch.int32, device=dev)
-        self.utt_begin = torch.zeros(U, dtype=torch.int32, device=dev)
-        self.utt_end = torch.zeros(U, dtype=torch.int32, device=dev)
-        self.chunk_first = torch.zeros(U + 1, dtype=torch.int32, device=dev)
+        # batch geometry (frame -> utterance map, utterance bounds, chunk table, global utterance ids): ONE device buffer fed
+        # from ONE pinned staging buffer by an asynchronous copy on the engine's auxiliary stream.  A pageable copy on the
+        # compute stream would queue behind the forward of the other buffer set and stall the host for a whole batch
+        # (this serialised host preparation and GPU work in the many-utterance path).
+        n_meta = F + 4 * U + 8
+        self.meta_host = torch.zeros(n_meta, dtype=torch.int32).pin_memory()
+        self.meta_dev = torch.zeros(n_meta, dtype=torch.int32, device=dev)
+        self.frame_utt = self.meta_dev[:F]
+        self.utt_begin = self.meta_dev[F:F + U]
+        self.utt_end = self.meta_dev[F + U:F + 2 * U]
+        self.chunk_first = self.meta_dev[F + 2 * U:F + 3 * U + 1]
+        self._utt_ids_dev = self.meta_dev[F + 3 * U + 4:F + 4 * U + 4]
+        self._meta_dirty = False
+        self._meta_event = None
         self.mel_host = torch.zeros(F, plan.mel_channels, dtype=torch.float32).pin_memory()
         self.out_host = torch.zeros(F * plan.hop, dtype=torch.float32).pin_memory()
         self.mel_dev = torch.zeros(F, plan.mel_channels, dtype=torch.float32, device=dev)
@@ -355,10 +379,13 @@ class PreparedBatch:
 
     def _bind(self, L: FrameGridLayout):
         self.layout = L
-        self.frame_utt[:L.n_frames].copy_(torch.from_numpy(L.frame_utt))
-        self.utt_begin[:L.n_utt].copy_(torch.from_numpy(L.utt_begin))
-        self.utt_end[:L.n_utt].copy_(torch.from_numpy(L.utt_end))
-        self.chunk_first[:L.n_utt + 1].copy_(torch.from_numpy(L.chunk_first))
+        F, U = self.cap_frames, self.cap_utts
+        mh = self.meta_host.numpy()
+        mh[:L.n_frames] = L.frame_utt
+        mh[F:F + L.n_utt] = L.utt_begin
+        mh[F + U:F + U + L.n_utt] = L.utt_end
+        mh[F + 2 * U:F + 2 * U + L.n_utt + 1] = L.chunk_first
+        self._meta_dirty = True
         b = self.batch
         b.n_utt, b.n_frames, b.n_chunks = L.n_utt, L.n_frames, L.n_chunks
 
@@ -391,10 +418,28 @@ class PreparedBatch:
     def set_utt_ids(self, utt_ids: Sequence[int]):
         ids = np.asarray(utt_ids, dtype=np.int32)
         assert ids.shape == (self.layout.n_utt,)
-        if self.utt_ids is None or self.utt_ids.numel() < self.cap_utts:
-            self.utt_ids = torch.zeros(self.cap_utts, dtype=torch.int32, device=self.eng.device)
-        self.utt_ids[:ids.size].copy_(torch.from_numpy(ids))
-        self.batch.utt_ids = self.utt_ids.data_ptr()
+        F, U = self.cap_frames, self.cap_utts
+        self.meta_host.numpy()[F + 3 * U + 4:F + 3 * U + 4 + ids.size] = ids
+        self.utt_ids = self._utt_ids_dev
+        self.batch.utt_ids = self._utt_ids_dev.data_ptr()
+        self._meta_dirty = True
+
+    def _flush_meta(self):
+        """Upload the batch geometry if it changed: asynchronous copy on the auxiliary stream, the compute stream waits on the
+        device (the host never blocks).  The previous user of these device arrays was this buffer set's own previous forward,
+        which the caller has drained (wait_host / run_host) before re-binding."""
+        if not self._meta_dirty:
+            return
+        eng = self.eng
+        with torch.cuda.device(eng.device):
+            aux = eng.aux_stream()
+            with torch.cuda.stream(aux):
+                self.meta_dev.copy_(self.meta_host, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(aux)
+            torch.cuda.current_stream(eng.device).wait_event(ev)
+            self._meta_event = ev
+        self._meta_dirty = False
 
     # bytes moved per run_host call
     @property
@@ -427,6 +472,7 @@ class PreparedBatch:
         """Host mel in -> host waveform out through mbexwn_forward_host (copies inside the call)."""
         eng = self.eng
         self.batch.seed = seed
+        self._flush_meta()
         with torch.cuda.device(eng.device):
             rc = eng.lib.mbexwn_forward_host(
                 eng._handle, C.byref(self.batch), self.prec, self.mel_host.data_ptr(),
@@ -439,6 +485,7 @@ class PreparedBatch:
         objects of one engine alternately as slot 0 / 1 and call wait_host(slot) before touching out_host / mel_host."""
         eng = self.eng
         self.batch.seed = seed
+        self._flush_meta()
         with torch.cuda.device(eng.device):
             rc = eng.lib.mbexwn_forward_host_begin(
                 eng._handle, slot, C.byref(self.batch), self.prec, self.mel_host.data_ptr(),
@@ -498,6 +545,7 @@ class PreparedBatch:
         """Device-resident inputs -> device output (asynchronous on the current stream)."""
         eng = self.eng
         self.batch.seed = seed
+        self._flush_meta()
         with torch.cuda.device(eng.device):
             rc = eng.lib.mbexwn_forward(eng._handle, C.byref(self.batch), self.prec, self.workspace.data_ptr(),
                                         self.workspace.numel(), self._stream())

@@ -197,6 +197,36 @@ def test_fused_layer_slab_views_equal_per_tap_loads(engine, speech_setup, precis
         assert np.array_equal(res[0][0][u], res[1][0][u]), f"waveform of utterance {u}"
 
 
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
+def test_fused_layer_clusters_of_four_equal_pairs(engine, speech_setup, precision):
+    """"tc_cluster" = 4: two CTA pairs of a cluster take turns loading the weight tiles and multicast them to each other
+    (the second pair of the last cluster may run one step past the last row).  Same products in the same order as with one
+    pair per cluster: bit-identical outputs, for a batch large enough that every pair gets several 256-row tiles."""
+    hp, plan, w = speech_setup
+    lengths = [400] * 14 + [150, 1, 37, 260, 333]
+    mels = [synthetic_mel(t, 80 + i) for i, t in enumerate(lengths)]
+    noise = [synthetic_noise(t * plan.steps_per_frame, 80 + i) for i, t in enumerate(lengths)]
+    engine.set_option("tc_cta_group", 2)
+    engine.set_option("tc_fused", 1)
+    res, used = [], []
+    for cluster in (2, 4):
+        engine.set_option("tc_cluster", cluster)
+        out, tp = engine.forward(mels, noise=noise, precision=precision, taps=["wn_out"])
+        res.append((out, tp))
+        used.append(engine.get_info("tc_last_cluster"))
+    quads = engine.get_info("tc_max_quads")
+    engine.set_option("tc_cluster", 2)
+    engine.set_option("tc_cta_group", 1)
+    print(f"clusters of 4 resident at once: {quads}; cluster sizes used: {used}")
+    assert used[0] == 2
+    if quads * 4 >= 128:
+        assert used[1] == 4, "the batch is large enough for clusters of 4"
+    for u in range(len(lengths)):
+        assert np.all(np.isfinite(res[1][0][u]))
+        assert np.array_equal(res[0][1]["wn_out"][u], res[1][1]["wn_out"][u]), f"wn_out of utterance {u}"
+        assert np.array_equal(res[0][0][u], res[1][0][u]), f"waveform of utterance {u}"
+
+
 @pytest.mark.parametrize("lengths", [[40], [23, 57, 10, 1, 2]])
 def test_subnets_tc_parity(engine, cg, speech_setup, lengths):
     """F0 net, VTF net and conditioning conv as 3-product bf16 tap-GEMMs (mirrored pad rows, sub-pixel unfold, PReLU
