@@ -341,7 +341,12 @@ class PreparedBatch:
         # (this serialised host preparation and GPU work in the many-utterance path).
         n_meta = F + 4 * U + 8
         self.meta_host = torch.zeros(n_meta, dtype=torch.int32).pin_memory()
-        self.meta_dev = torch.zeros(n_meta, dtype=torch.int32, device=dev)
+        # torch.empty, not zeros: a fill kernel on the compute stream could run AFTER the first upload on the auxiliary stream and
+        # wipe the geometry (every frame a guard frame: an all-zero waveform).  The block may also have had earlier users whose
+        # work is still queued on the compute stream: the first upload waits for the event recorded here.
+        self.meta_dev = torch.empty(n_meta, dtype=torch.int32, device=dev)
+        self._alloc_event = torch.cuda.Event()
+        self._alloc_event.record(torch.cuda.current_stream(dev))
         self.frame_utt = self.meta_dev[:F]
         self.utt_begin = self.meta_dev[F:F + U]
         self.utt_end = self.meta_dev[F + U:F + 2 * U]
@@ -376,6 +381,10 @@ class PreparedBatch:
             self.carry_dev = torch.zeros(U, dtype=torch.float32, device=dev)
             b.phase_carry = self.carry_dev.data_ptr()
         self._bind(L)
+        # The buffers above were zero-filled by kernels queued on the compute stream, possibly behind a forward that is still
+        # running; the pipelined host path copies into them from its own copy streams, which do not wait for the compute
+        # stream.  Creating a buffer set is rare (prepare_cached) and slow anyway (pinned allocations): finish the fills here.
+        torch.cuda.current_stream(dev).synchronize()
 
     def _bind(self, L: FrameGridLayout):
         self.layout = L
@@ -433,6 +442,9 @@ class PreparedBatch:
         eng = self.eng
         with torch.cuda.device(eng.device):
             aux = eng.aux_stream()
+            if self._alloc_event is not None:
+                aux.wait_event(self._alloc_event)
+                self._alloc_event = None
             with torch.cuda.stream(aux):
                 self.meta_dev.copy_(self.meta_host, non_blocking=True)
                 ev = torch.cuda.Event()

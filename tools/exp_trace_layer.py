@@ -63,11 +63,13 @@ for cta in ((0, 74) if debug else (0, 2, 74, 146)):
     nt = int(np.count_nonzero(mma[:, 2]))
     if nt == 0:
         continue
-    t0, t1, t2, wf = mma[:nt, 0], mma[:nt, 1], mma[:nt, 2], mma[:nt, 3]
+    t0, t1, t2 = mma[:nt, 0], mma[:nt, 1], mma[:nt, 2]
+    wfa, wfb = (mma[:nt, 3] >> 16) * 8, (mma[:nt, 3] & 0xFFFF) * 8      # cycles the MMA warp waited for A slabs / B tiles
+    wf = wfa + wfb
     total = d(t2[-1], t0[0])
     w_empty = d(t1, t0).sum()
     print(f"cta {cta}: {nt} tiles, MMA warp span {total} cyc; waiting tmem_empty {100 * w_empty / total:.1f} %, "
-          f"waiting operands {100 * wf.sum() / total:.1f} %, issuing {100 * (total - w_empty - wf.sum()) / total:.1f} %")
+          f"waiting operands {100 * wf.sum() / total:.1f} % (A {100 * wfa.sum() / total:.1f}, B {100 * wfb.sum() / total:.1f}), issuing {100 * (total - w_empty - wf.sum()) / total:.1f} %")
     ne = int(np.count_nonzero(epi[:, 2]))
     e0, e1, e2, ws = epi[:ne, 0], epi[:ne, 1], epi[:ne, 2], epi[:ne, 3] & 0x7FFFFFFF
     kind = epi[:ne, 3] >> 31
