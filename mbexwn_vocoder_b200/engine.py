@@ -222,6 +222,13 @@ class Engine:
         _cabi.check(self.lib, self._handle, rc, "mbexwn_k_tc_gemm_f16f8")
         return out
 
+    def copy_stream(self):
+        """Side stream for large device->host result copies (kept apart from aux_stream, whose small geometry uploads gate the
+        next forward)."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        return self._copy_stream
+
     def aux_stream(self):
         """Side stream for small asynchronous uploads (batch geometry) that must not queue behind a running forward."""
         if self._aux_stream is None:
