@@ -128,6 +128,7 @@ struct alignas(64) LayerParams {
     // blocks) lets the res tiles follow the gated activations and the residual rows they read back after ONE tile instead
     // of a whole step, while those are still in the L2.
     int g_first, nb0;
+    int spin;                // the producer and MMA warps poll their barriers instead of suspending (option "tc_spin")
     // gate epilogue
     const float* bias1;
     const float* cond;
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
         uint32_t wait_cyc = 0;
         auto load_a = [&](const CUtensorMap* tma, uint32_t a_bytes, int col, int row, uint64_t pol) {
             const uint32_t t0 = TRACE ? clk32() : 0u;
-            mbar_wait(&empty_a[sa], pha ^ 1);
+            if (p.spin) mbar_wait_spin(&empty_a[sa], pha ^ 1); else mbar_wait(&empty_a[sa], pha ^ 1);
             if (TRACE) wait_cyc += clk32() - t0;
             if (elect_one()) {
                 if (dbg & 2) {
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
             ++ent;
             if (mine || leader) {
                 const uint32_t t0 = TRACE ? clk32() : 0u;
-                mbar_wait(&empty_b[sb], phb ^ 1);
+                if (p.spin) mbar_wait_spin(&empty_b[sb], phb ^ 1); else mbar_wait(&empty_b[sb], phb ^ 1);
                 if (TRACE) wait_cyc += clk32() - t0;
                 if (elect_one()) {
                     if (dbg & 1) {
@@ -539,7 +540,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                 const int flags = e.y;
                 if (flags & KF_NEW_SLAB) {
                     const uint32_t w0 = TRACE ? clk32() : 0u;
-                    mbar_wait(&full_a[sa], pha);
+                    if (p.spin) mbar_wait_spin(&full_a[sa], pha); else mbar_wait(&full_a[sa], pha);
                     if (TRACE) wait_a += clk32() - w0;
                     cur_a = sa;
                     cur_a_desc = a_desc;
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                     if (++sa == (uint32_t)p.n_a) { sa = 0; pha ^= 1; a_desc = a_desc0; }
                 }
                 const uint32_t w1 = TRACE ? clk32() : 0u;
-                mbar_wait(&full_b[sb], phb);
+                if (p.spin) mbar_wait_spin(&full_b[sb], phb); else mbar_wait(&full_b[sb], phb);
                 if (TRACE) wait_b += clk32() - w1;
                 tc_fence_after();
                 if (elect_one()) {
@@ -1032,6 +1033,7 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
     p.bias2 = a.bias2; p.skip = a.skip; p.skip_ld = a.skip_ld; p.skip_c = a.skip_c; p.res_cols = a.res_cols; p.first = a.first;
     p.grid = a.grid;
     p.range_flag = a.range_flag;
+    p.spin = st.spin;
     if (st.l2_hints) {
         p.pol_w = L2_EVICT_LAST; p.pol_h = L2_EVICT_NORMAL; p.pol_rmw = L2_EVICT_FIRST;
         p.pol_scr_st = L2_EVICT_LAST; p.pol_scr_ld = L2_EVICT_LAST; p.pol_out = L2_EVICT_FIRST;

@@ -47,6 +47,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(addr, parity))
         if (global_timer_ns() - t0 > 4000000000ull) __trap();
 }
+// Polling wait (mbarrier.test_wait, no hardware suspend) for the two single-purpose warps whose reaction time is part of a ring
+// slot's turn-around; traps like mbar_wait.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0, n = 0;
+    uint64_t t0 = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if ((++n & 0xffffu) == 0) {
+            const uint64_t t = global_timer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ull) __trap();
+        }
+    }
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(

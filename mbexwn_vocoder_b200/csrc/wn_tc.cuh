@@ -37,6 +37,7 @@ struct WnTcState {
     int trace_on = 0;
     int interleave = 0;         // option "tc_interleave": the res tiles of M tile j - 1 run behind the FIRST gate tile of M tile j (0: behind the
                                 // last): 0.5 GB less DRAM traffic per layer at config 2, same speed within noise, one B ring slot fewer
+    int spin = 0;               // option "tc_spin": producer / MMA warps of the fused kernel poll their barriers (test_wait) instead of try_wait
     int l2_hints = 1;           // option "tc_l2_hints": L2 eviction policies on the fused kernel's TMA traffic (0: none)
     int cluster = 2;            // option "tc_cluster": CTAs per cluster of the fused kernel, 2 (one pair) or 4 (two pairs share the B tiles by TMA multicast)
     int cluster_min_sms = 128;  // clusters of 4 only when the device keeps at least this many SMs busy with them

@@ -309,7 +309,7 @@ class Engine:
             pb.run_graph(seed)
         else:
             pb.run_host(seed)
-        out = [w.copy() for w in pb.waveforms()]
+        out = pb.waveforms_copy()
         return out, {t: pb.tap(t) for t in taps}
 
     def close(self):
@@ -587,6 +587,29 @@ class PreparedBatch:
 
     def launches(self) -> int:
         return int(self.eng.lib.mbexwn_last_launch_count(self.eng._handle))
+
+    def waveforms_copy(self, threads: int = 4) -> List[np.ndarray]:
+        """Fresh copies of the waveforms in the pinned output grid.  Small batches: one copy per utterance; from a few MB on the
+        utterances are copied into ONE new array by a few threads (NumPy copies release the GIL: a 245 MB batch takes 30 ms on one
+        host thread) and returned as views of it."""
+        views = self.waveforms()
+        total = sum(v.size for v in views)
+        if total < (1 << 20) or threads <= 1:
+            return [v.copy() for v in views]
+        flat = np.empty(total, dtype=np.float32)
+        offs = np.concatenate(([0], np.cumsum([v.size for v in views])))
+        outs = [flat[offs[i]:offs[i + 1]] for i in range(len(views))]
+        import threading
+
+        def part(k):
+            for d, v in zip(outs[k::threads], views[k::threads]):
+                d[...] = v
+        ts = [threading.Thread(target=part, args=(k,)) for k in range(threads)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return outs
 
     def waveforms(self, from_device: bool = False) -> List[np.ndarray]:
         n = self.layout.n_frames * self.eng.plan.hop

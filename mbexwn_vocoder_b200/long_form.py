@@ -245,27 +245,18 @@ def _synth_long_device(engine, mel: np.ndarray, noise: np.ndarray, chunk_frames:
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
 
-        # ---- first window on its own (host buffers, cached geometry): it needs the F0 of its own frames only and a zero carry
+        # ---- first window on its own (host buffers, cached geometry): ONE plain forward over its frames plus the reach of the
+        # F0 sub-net to the right, so that the F0 it computes itself is exact on every frame the core can see (frames behind
+        # w0.stop are outside the core's context); zero phase carry = a plain forward
         first_done = False
         if first_alone and len(wins) > 1:
             w0 = wins[0]
-            f0_ctx = subnet_reach_frames(plan.pp_ops)
-            b = min(T, w0.stop + f0_ctx)
-            engine.set_option("stop_after_f0", 1)
-            try:
-                pbf = engine.prepare_cached([b], precision, with_noise=False)
-                pbf.load([mel[:b]])
-                pbf.upload()
-                pbf.run_device()
-                f0_first = pbf.tap_grid("F0")[engine.halo * ppf:(engine.halo + w0.stop) * ppf].clone()
-            finally:
-                engine.set_option("stop_after_f0", 0)
-            pb0 = engine.prepare_cached([w0.stop - w0.start], precision, with_noise=True, with_f0=True, with_carry=True)
-            pb0.load([mel[w0.start:w0.stop]], noise=[noise[w0.start * spf:w0.stop * spf]], carry=[0.0])
-            pb0.f0_dev[engine.halo * ppf:(engine.halo + w0.stop - w0.start) * ppf].copy_(f0_first[w0.start * ppf:])
+            b = min(T, w0.stop + subnet_reach_frames(plan.pp_ops))
+            pb0 = engine.prepare_cached([b], precision, with_noise=True)
+            pb0.load([mel[:b]], noise=[noise[:b * spf]])
             pb0.run_host()
             y = pb0.waveforms()[0]
-            out[w0.core0 * hop:w0.core1 * hop] = y[(w0.core0 - w0.start) * hop:(w0.core1 - w0.start) * hop]
+            out[w0.core0 * hop:w0.core1 * hop] = y[w0.core0 * hop:w0.core1 * hop]
             info["first_chunk_latency_s"] = time.perf_counter() - t0
             first_done = True
 

@@ -258,7 +258,7 @@ class MELInverter(object):
                 state["warned"] = True
             state["prec"] = "bf16x3"
             return self.model.forward(mels, noise=nz, precision="bf16x3", seed=seed)[0]
-        return [w.copy() for w in pb.waveforms()]
+        return pb.waveforms_copy()
 
     def synth_long_from_mel(self, scaled_mell, noise=None, chunk_frames: int = 400, max_batch_frames: int = 32768,
                             seed: Optional[int] = None, return_info: bool = False):

@@ -176,6 +176,8 @@ class DevicePool:
         lengths = [int(np.asarray(m).shape[0]) for m in mels]
         n = len(self.inverters)
         shards = sched.lpt_shards(lengths, n)
+        import os
+        host_threads = max(1, min(4, (os.cpu_count() or 4) // n))     # copy threads per GPU: the host cores are shared
         out: Dict[int, np.ndarray] = {}
         stats: List[Optional[ShardStats]] = [None] * n
         errors: List[BaseException] = []
@@ -183,7 +185,7 @@ class DevicePool:
         def work(k: int):
             try:
                 stats[k] = run_shard(self.inverters[k], lambda i: np.asarray(mels[i], dtype=np.float32), lengths, shards[k], out,
-                                     max_batch_frames, seed, precision)
+                                     max_batch_frames, seed, precision, host_threads=host_threads)
             except BaseException as e:          # surfaced in the caller's thread
                 errors.append(e)
 
