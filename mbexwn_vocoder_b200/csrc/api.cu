@@ -884,8 +884,7 @@ int mbexwn_set_option(mbexwn_handle_t h, const char* name, int32_t value) {
     if (!strcmp(name, "tc_slab")) { h->tc.slab = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "tc_ring_a")) { h->tc.n_a = value; return MBEXWN_OK; }
     if (!strcmp(name, "tc_interleave")) { h->tc.interleave = value ? 1 : 0; return MBEXWN_OK; }
-    if (!strcmp(name, "tc_spin")) { h->tc.spin = value ? 1 : 0; return MBEXWN_OK; }
-    if (!strcmp(name, "tc_l2_hints")) { h->tc.l2_hints = value; return MBEXWN_OK; }
+    if (!strcmp(name, "tc_discard")) { h->tc.discard = value ? 1 : 0; return MBEXWN_OK; }
     if (!strcmp(name, "tc_cluster")) { h->tc.cluster = value == 4 ? 4 : 2; return MBEXWN_OK; }
     if (!strcmp(name, "tc_trace")) { h->tc.trace_on = value; return MBEXWN_OK; }
     if (!strcmp(name, "tc8_h_lo")) { h->tc.sh_h_lo = value; return MBEXWN_OK; }

@@ -114,10 +114,6 @@ struct alignas(64) LayerParams {
     int slab_bytes;          // bytes one gate slab load brings (slab rows x 128)
     // shared memory carve-up (bytes from the 1024-aligned base)
     int slab_slot, n_a, off_b, n_b, b_slot, off_stg, off_cond, cond_ld;
-    // L2 eviction policies of the TMA traffic (tc_common.cuh: L2_EVICT_*): the layer streams 0.64 GB in and 0.64 GB out through
-    // a 126 MB L2 that also has to hold, for one step, the pairs' activation scratch and the residual rows their next res
-    // tiles read back
-    unsigned long long pol_w, pol_h, pol_rmw, pol_scr_st, pol_scr_ld, pol_out;
     int cluster;             // CTAs per cluster: 2 (one pair) or 4 (two pairs sharing the B tiles by multicast)
     int f16;                 // 16-bit operands are fp16 (MBEXWN_PREC_F16F8), else bf16
     long long rows;
@@ -128,7 +124,8 @@ struct alignas(64) LayerParams {
     // blocks) lets the res tiles follow the gated activations and the residual rows they read back after ONE tile instead
     // of a whole step, while those are still in the L2.
     int g_first, nb0;
-    int spin;                // the producer and MMA warps poll their barriers instead of suspending (option "tc_spin")
+    int n_seq, seq[2 * MAX_TILES];   // the tiles of a step in issue order: t = gate tile t, 16 + t = res tile t
+    uint8_t* scr_discard;    // the activation scratch when its dead rows are to be discarded from the L2 (option "tc_discard"), else nullptr
     // gate epilogue
     const float* bias1;
     const float* cond;
@@ -212,6 +209,9 @@ __device__ __forceinline__ uint64_t* epi_bar(const EpiState& es, int idx) { retu
 // Eight gate outputs of one row: zt / zs = tanh / sigmoid pre-activations of channels 8 half .. + 7 of a 16-channel chunk,
 // cs0 / cs1 = the two conditioning rows (+ bias) of this row in the smem stage at the chunk's first column
 // ([16 tanh | 16 sigmoid]).  Result: 16 bytes of the fp16 / bf16 plane and the matching bytes of the lo plane in the staging tile.
+// MODE: 0 = F16F8 planes (fp16 + e4m3 lo8 / hi8), 1 = bf16 (hi plane only), 2 = bf16x3 (hi + lo planes); GTU: the gate is
+// tanh * sigmoid (compile-time: the other gate types keep the run-time switch)
+template <int MODE, bool GTU>
 __device__ __forceinline__ void gate_half(const LayerParams& p, const float (&zt)[8], const float (&zs)[8], const float* cs0, const float* cs1,
                                           float w0, float w1, bool valid, uint8_t* t_hi, int sw, int part, int half) {
     float a[8];
@@ -229,7 +229,7 @@ __device__ __forceinline__ void gate_half(const LayerParams& p, const float (&zt
             for (int e = 0; e < 4; ++e) {
                 float t = fmaf(xb[e], w1, fmaf(xa[e], w0, zt[4 * v4 + e]));
                 const float sg = fmaf(yb[e], w1, fmaf(ya[e], w0, zs[4 * v4 + e]));
-                if (p.gate == GATE_GTU) {
+                if (GTU) {
                     a[4 * v4 + e] = gate_gtu(t, sg);
                 } else {
                     if (p.gate == GATE_GFU) t = t * rcp_approx(1.f + fabsf(t));
@@ -244,7 +244,7 @@ __device__ __forceinline__ void gate_half(const LayerParams& p, const float (&zt
     }
     // staging tiles, SWIZZLE_128B: 16-byte chunk c of row r sits at r * 128 + ((c ^ (r & 7)) << 4)
     uint8_t* t_lo = t_hi + TILE_M * 128;
-    if (p.out_f16f8) {
+    if (MODE == 0) {
         uint4 h16;
         uint2 l8, h8;
         split_f16f8(a, p.act_lo_scale, h16, l8, h8);
@@ -262,13 +262,13 @@ __device__ __forceinline__ void gate_half(const LayerParams& p, const float (&zt
             lw4[e / 2] = pack2(l0, l1);
         }
         *reinterpret_cast<uint4*>(t_hi + (((2 * part + half) ^ sw) << 4)) = make_uint4(hw4[0], hw4[1], hw4[2], hw4[3]);
-        if (p.write_lo) *reinterpret_cast<uint4*>(t_lo + (((2 * part + half) ^ sw) << 4)) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
+        if (MODE == 2) *reinterpret_cast<uint4*>(t_lo + (((2 * part + half) ^ sw) << 4)) = make_uint4(lw4[0], lw4[1], lw4[2], lw4[3]);
     }
 }
 
 // One residual chunk: v = 16 accumulator values of one row, residual channels n .. n + 15; the old values sit in the staging
 // tile the manager loaded (updated in place, guard rows untouched).
-template <bool TRACE>
+template <bool TRACE, int MODE>
 __device__ __forceinline__ void res_chunk(const LayerParams& p, EpiState& es, const float (&v)[16], int n, bool valid, int r, int part,
                                           int lane) {
     const uint32_t buf = es.blk % NSTG;
@@ -287,7 +287,7 @@ __device__ __forceinline__ void res_chunk(const LayerParams& p, EpiState& es, co
             const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             uint4* ph16 = reinterpret_cast<uint4*>(t_hi + (((2 * part + (i >> 3)) ^ sw) << 4));
             float prev[8], o[8];
-            if (p.out_f16f8) {
+            if (MODE == 0) {
                 uint2* pl8 = reinterpret_cast<uint2*>(t_lo + ((part ^ sw) << 4) + i);
                 join_f16f8(*ph16, *pl8, p.h_lo_inv, prev);
 #pragma unroll
@@ -348,7 +348,7 @@ __device__ __forceinline__ void skip_chunk(const LayerParams& p, const float (&v
     }
 }
 
-template <bool TRACE>
+template <bool TRACE, bool QUAD, int MODE, bool GTU>
 __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_constant__ LayerParams p) {
     // K-major SWIZZLE_128B smem matrix descriptor without the address field (see k_wavenet_tc.cu)
     constexpr uint64_t DESC_HI = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
     const int pair_in_cluster = crank >> 1;
     const uint32_t lead_rank = (uint32_t)(crank & ~1);              // cluster rank of this pair's leader CTA
     const bool leader = rank == 0;
-    const bool quad = p.cluster == 4;
+    constexpr bool quad = QUAD;                                     // clusters of 4 are a separate instantiation: none of it in the pair kernel
     const int group = blockIdx.x >> 1, n_groups = gridDim.x >> 1;
     // M tiles of this pair; the pairs of a cluster run the same number of steps (the second one may end on a tile past the
     // last row: loads are zero-filled, stores clipped, the epilogue's row checks fail)
@@ -454,16 +454,16 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
         const uint32_t fb0_mc = smem_u32(&full_b[0]) & 0xFEFFFFFFu;  // multicast form: this offset in the even CTA of each destination's pair
         const uint16_t mc_mask = (uint16_t)(0x5u << rank);
         uint32_t wait_cyc = 0;
-        auto load_a = [&](const CUtensorMap* tma, uint32_t a_bytes, int col, int row, uint64_t pol) {
+        auto load_a = [&](const CUtensorMap* tma, uint32_t a_bytes, int col, int row) {
             const uint32_t t0 = TRACE ? clk32() : 0u;
-            if (p.spin) mbar_wait_spin(&empty_a[sa], pha ^ 1); else mbar_wait(&empty_a[sa], pha ^ 1);
+            mbar_wait(&empty_a[sa], pha ^ 1);
             if (TRACE) wait_cyc += clk32() - t0;
             if (elect_one()) {
                 if (dbg & 2) {
                     if (leader) mbar_arrive(&full_a[sa]);
                 } else {
                     if (leader) mbar_expect_tx(&full_a[sa], 2 * a_bytes);
-                    tma_load_2d_2sm_hint(tma, lfa0 + sa * 8, ring_a + sa * p.slab_slot, col, row, pol);
+                    tma_load_2d_2sm(tma, lfa0 + sa * 8, ring_a + sa * p.slab_slot, col, row);
                 }
             }
             __syncwarp();
@@ -474,15 +474,15 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
             ++ent;
             if (mine || leader) {
                 const uint32_t t0 = TRACE ? clk32() : 0u;
-                if (p.spin) mbar_wait_spin(&empty_b[sb], phb ^ 1); else mbar_wait(&empty_b[sb], phb ^ 1);
+                mbar_wait(&empty_b[sb], phb ^ 1);
                 if (TRACE) wait_cyc += clk32() - t0;
                 if (elect_one()) {
                     if (dbg & 1) {
                         if (leader) mbar_arrive(&full_b[sb]);
                     } else {
                         if (leader) mbar_expect_tx(&full_b[sb], 2 * b_bytes);
-                        if (!quad) tma_load_2d_2sm_hint(tmb, lfb0 + sb * 8, ring_b + sb * p.b_slot, col, row, p.pol_w);
-                        else if (mine) tma_load_2d_2sm_mc(tmb, fb0_mc + sb * 8, ring_b + sb * p.b_slot, col, row, mc_mask, p.pol_w);
+                        if (!quad) tma_load_2d_2sm(tmb, lfb0 + sb * 8, ring_b + sb * p.b_slot, col, row);
+                        else if (mine) tma_load_2d_2sm_mc(tmb, fb0_mc + sb * 8, ring_b + sb * p.b_slot, col, row, mc_mask, L2_EVICT_NORMAL);
                     }
                 }
                 __syncwarp();
@@ -490,13 +490,13 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
             if (++sb == (uint32_t)p.n_b) { sb = 0; phb ^= 1; }
         };
         auto load_tile = [&](const CUtensorMap* tma, uint32_t a_bytes, const CUtensorMap* tmb, uint32_t b_bytes, const KEnt* ke, int n,
-                             int a_row0, int b_row, uint64_t pol_a) {
+                             int a_row0, int b_row) {
             wait_cyc = 0;
             int4 e = *reinterpret_cast<const int4*>(ke);            // {a_col, a_row | a_view << 16, b_col, flags}
             for (int i = 0; i < n; ++i) {
                 const int4 cur = e;
                 if (i + 1 < n) e = *reinterpret_cast<const int4*>(ke + i + 1);
-                if (cur.w & KF_NEW_SLAB) load_a(tma, a_bytes, cur.x, a_row0 + (int)(short)(cur.y & 0xffff), pol_a);
+                if (cur.w & KF_NEW_SLAB) load_a(tma, a_bytes, cur.x, a_row0 + (int)(short)(cur.y & 0xffff));
                 load_b(tmb, b_bytes, cur.z, b_row);
             }
             if (TRACE && lane == 0 && tile_it < TRACE_SLOTS) {
@@ -505,22 +505,25 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
             }
             ++tile_it;
         };
-        auto gate_tiles = [&](int j, int t_begin, int t_end) {
-            for (int t = t_begin; t < t_end; ++t)
-                load_tile(&p.tm_hs, (uint32_t)p.slab_bytes, &p.tm_w1[p.t1[t].bmap], (uint32_t)(p.t1[t].w >> 1) * 128u, k1, p.n_k1, m0_of(j),
-                          p.t1[t].n0 + rank * (p.t1[t].w >> 1), p.pol_h);
-        };
         for (int j = 0; j <= n_j; ++j) {
-            if (j < n_j) gate_tiles(j, 0, p.g_first);
-            if (j > 0) {
-                // the act of M tile j - 1 must have landed in the scratch (writes of the async proxy, completed by the manager)
-                mbar_wait(&act_ready[(j - 1) & 1], ((j - 1) >> 1) & 1);
-                asm volatile("fence.proxy.async;" ::: "memory");
-                for (int t = 0; t < p.n_t2; ++t)
+            bool act_seen = false;
+            for (int e = 0; e < p.n_seq; ++e) {
+                const int code = p.seq[e], t = code & 15;
+                if (code < 16) {
+                    if (j < n_j)
+                        load_tile(&p.tm_hs, (uint32_t)p.slab_bytes, &p.tm_w1[p.t1[t].bmap], (uint32_t)(p.t1[t].w >> 1) * 128u, k1, p.n_k1, m0_of(j),
+                                  p.t1[t].n0 + rank * (p.t1[t].w >> 1));
+                } else if (j > 0) {
+                    if (!act_seen) {
+                        // the act of M tile j - 1 must have landed in the scratch (writes of the async proxy, completed by the manager)
+                        mbar_wait(&act_ready[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        act_seen = true;
+                    }
                     load_tile(&p.tm_scr, (uint32_t)(TILE_M * 128), &p.tm_w2[p.t2[t].bmap], (uint32_t)(p.t2[t].w >> 1) * 128u, k2, p.n_k2, scr_of(j - 1),
-                              p.t2[t].n0 + rank * (p.t2[t].w >> 1), p.pol_scr_ld);
+                              p.t2[t].n0 + rank * (p.t2[t].w >> 1));
+                }
             }
-            if (j < n_j) gate_tiles(j, p.g_first, p.n_t1);
         }
     } else if (warp == 1) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -540,7 +543,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                 const int flags = e.y;
                 if (flags & KF_NEW_SLAB) {
                     const uint32_t w0 = TRACE ? clk32() : 0u;
-                    if (p.spin) mbar_wait_spin(&full_a[sa], pha); else mbar_wait(&full_a[sa], pha);
+                    mbar_wait(&full_a[sa], pha);
                     if (TRACE) wait_a += clk32() - w0;
                     cur_a = sa;
                     cur_a_desc = a_desc;
@@ -548,7 +551,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                     if (++sa == (uint32_t)p.n_a) { sa = 0; pha ^= 1; a_desc = a_desc0; }
                 }
                 const uint32_t w1 = TRACE ? clk32() : 0u;
-                if (p.spin) mbar_wait_spin(&full_b[sb], phb); else mbar_wait(&full_b[sb], phb);
+                mbar_wait(&full_b[sb], phb);
                 if (TRACE) wait_b += clk32() - w1;
                 tc_fence_after();
                 if (elect_one()) {
@@ -565,16 +568,22 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                             for (int k = 1; k < 4; ++k) tc_mma_bf16_2sm(tacc, da + 2 * k, db + 2 * k, idesc, 1u);
                         }
                     }
-                    tc_commit_mc(&empty_b[sb], mask_b);
-                    if (flags & KF_LAST_OF_SLAB) tc_commit_mc(&empty_a[cur_a], mask_pair);
-                    if (last) tc_commit_mc(&tmem_full[(tile_it & 1)], mask_pair);
+                    if (quad) {
+                        tc_commit_mc(&empty_b[sb], mask_b);
+                        if (flags & KF_LAST_OF_SLAB) tc_commit_mc(&empty_a[cur_a], mask_pair);
+                        if (last) tc_commit_mc(&tmem_full[(tile_it & 1)], mask_pair);
+                    } else {
+                        tc_commit_2sm(&empty_b[sb]);
+                        if (flags & KF_LAST_OF_SLAB) tc_commit_2sm(&empty_a[cur_a]);
+                        if (last) tc_commit_2sm(&tmem_full[(tile_it & 1)]);
+                    }
                 }
                 __syncwarp();
                 b_desc += b_slot16;
                 if (++sb == (uint32_t)p.n_b) { sb = 0; phb ^= 1; b_desc = b_desc0; }
             };
             auto mma_tile = [&](int width, const int2* km, int n8, int n) {
-                const uint32_t idesc = p.f16 ? make_idesc_fmt0(2 * TILE_M, width) : make_idesc(2 * TILE_M, width);
+                const uint32_t idesc = MODE == 0 ? make_idesc_fmt0(2 * TILE_M, width) : make_idesc(2 * TILE_M, width);
                 const uint32_t as = tile_it & 1, aph = (tile_it >> 1) & 1;
                 const uint32_t t0 = TRACE ? clk32() : 0u;
                 mbar_wait(&tmem_empty[as], aph ^ 1);
@@ -601,14 +610,12 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                 wait_a = wait_b = 0;
                 ++tile_it;
             };
-            for (int j = 0; j <= n_j; ++j) {
-                if (j < n_j)
-                    for (int t = 0; t < p.g_first; ++t) mma_tile(p.t1[t].w, km1, p.n8_1, p.n_k1);
-                if (j > 0)
-                    for (int t = 0; t < p.n_t2; ++t) mma_tile(p.t2[t].w, km2, p.n8_2, p.n_k2);
-                if (j < n_j)
-                    for (int t = p.g_first; t < p.n_t1; ++t) mma_tile(p.t1[t].w, km1, p.n8_1, p.n_k1);
-            }
+            for (int j = 0; j <= n_j; ++j)
+                for (int e = 0; e < p.n_seq; ++e) {
+                    const int code = p.seq[e], t = code & 15;
+                    const bool gate = code < 16;
+                    if (gate ? j < n_j : j > 0) mma_tile(gate ? p.t1[t].w : p.t2[t].w, gate ? km1 : km2, gate ? p.n8_1 : p.n8_2, gate ? p.n_k1 : p.n_k2);
+                }
         }
     } else if (warp == 2) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -641,8 +648,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                         const int col = 64 * (pe - p.nb0), row0 = m0_of(pj - 1);
                         if (dbg & 64) { mbar_arrive(&stg_avail[buf]); ++pb; more_p = advance(pj, pe); continue; }
                         mbar_expect_tx(&stg_avail[buf], STG_BYTES);
-                        tma_load_2d_hint(&p.tm_h, &stg_avail[buf], stg + buf * STG_BYTES, col, row0, p.pol_rmw);
-                        tma_load_2d_hint(&p.tm_h, &stg_avail[buf], stg + buf * STG_BYTES + TILE_M * 128, p.cpad + col, row0, p.pol_rmw);
+                        tma_load_2d(&p.tm_h, &stg_avail[buf], stg + buf * STG_BYTES, col, row0);
+                        tma_load_2d(&p.tm_h, &stg_avail[buf], stg + buf * STG_BYTES + TILE_M * 128, p.cpad + col, row0);
                     }
                     ++pb;
                     more_p = advance(pj, pe);
@@ -662,13 +669,13 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                     if (last_gate) pending_act = sj;
                 } else if (is_gate(se)) {
                     const int col = 64 * gate_idx(se), row0 = scr_of(sj);
-                    tma_store_2d_hint(&p.tm_scr, t_hi, col, row0, p.pol_scr_st);
-                    if (p.out_f16f8 || p.write_lo) tma_store_2d_hint(&p.tm_scr, t_hi + TILE_M * 128, p.cpad + col, row0, p.pol_scr_st);
+                    tma_store_2d(&p.tm_scr, t_hi, col, row0);
+                    if (MODE != 1) tma_store_2d(&p.tm_scr, t_hi + TILE_M * 128, p.cpad + col, row0);
                     if (last_gate) pending_act = sj;
                 } else {
                     const int col = 64 * (se - p.nb0), row0 = m0_of(sj - 1);
-                    tma_store_2d_hint(&p.tm_hout, t_hi, col, row0, p.pol_out);
-                    tma_store_2d_hint(&p.tm_hout, t_hi + TILE_M * 128, p.cpad + col, row0, p.pol_out);
+                    tma_store_2d(&p.tm_hout, t_hi, col, row0);
+                    tma_store_2d(&p.tm_hout, t_hi + TILE_M * 128, p.cpad + col, row0);
                 }
                 tma_store_commit();
                 ++sb;
@@ -726,101 +733,127 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
             }
             ++tile_it;
         };
-        auto gate_tiles = [&](int j, int t_begin, int t_end) {
-            if (t_begin >= t_end) return;
-            const int m0 = m0_of(j);
-            const int row = m0 + rl;
-            const bool in_range = row < (int)p.rows && !(dbg & 8);
-            bool valid = false;
-            int rl0 = 0, rl1 = 0;
-            float w0 = 1.f, w1 = 0.f;
-            if (in_range) {
-                const int u = p.grid.frame_utt[row / p.steps_per_frame];
-                if (u >= 0) {
-                    valid = true;
-                    const int hic = p.grid.utt_end[u] * p.steps_per_frame / p.lin_up;
-                    const int rc0 = m0 / p.lin_up, rc = row / p.lin_up;
-                    const int un = row - rc * p.lin_up;
-                    const int rn = rc + 1 < hic ? rc + 1 : hic - 1;
-                    rl0 = rc - rc0;
-                    rl1 = rn - rc0;
-                    w0 = p.lin_w0[un];
-                    w1 = p.lin_w1[un];
-                }
-            }
-            for (int t = t_begin; t < t_end; ++t, ++gt) {
-                uint32_t t0, t1;
-                const TileDesc td = p.t1[t];
-                const uint32_t tacc = wait_tile(t0, t1);
-                // chunks c0 + k of this tile with (c0 + k) % 4 == part: at most two (a tile has at most eight); eight channels
-                // (8 tanh + 8 sigmoid accumulators) at a time.  The TMEM buffer goes back to the MMA warp when the last eight
-                // are in registers.
-                const int k0 = (part - td.c0) & 3;
-                const int nmy = k0 < td.nch ? (k0 + 4 < td.nch ? 2 : 1) : 0;
-                if (nmy == 0) release_tile();
-                mbar_wait(&cond_full[gt & 1], (gt >> 1) & 1);
-                const float* cbuf = cond_stage + (gt & 1) * cond_buf;
-#pragma unroll 1
-                for (int k = 0; k < nmy; ++k) {
-                    const int cl = 32 * (k0 + 4 * k);
-                    const uint32_t buf = es.blk % NSTG;
-                    float zt[8], zs[8];
-                    tmem_ld8(tacc + cl, zt);
-                    tmem_ld8(tacc + cl + 16, zs);
-                    {
-                        const uint32_t w0c = TRACE ? clk32() : 0u;
-                        mbar_wait(epi_bar(es, BAR_STG_AVAIL + buf), (es.blk / NSTG) & 1);
-                        if (TRACE) es.wait_cyc += clk32() - w0c;
-                    }
-                    uint8_t* t_hi = stg + buf * STG_BYTES + rl * 128;
-                    tmem_ld_wait();
-                    if (in_range) gate_half(p, zt, zs, cbuf + rl0 * p.cond_ld + cl, cbuf + rl1 * p.cond_ld + cl, w0, w1, valid, t_hi, rl & 7, part, 0);
-                    tmem_ld8(tacc + cl + 8, zt);
-                    tmem_ld8(tacc + cl + 24, zs);
-                    if (k == nmy - 1) release_tile();
-                    else tmem_ld_wait();
-                    if (in_range) gate_half(p, zt, zs, cbuf + rl0 * p.cond_ld + cl, cbuf + rl1 * p.cond_ld + cl, w0, w1, valid, t_hi, rl & 7, part, 1);
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(epi_bar(es, BAR_STG_READY + buf));
-                    ++es.blk;
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&cond_empty[gt & 1]);
-                end_tile(t0, t1, 0);
-            }
-
-        };
-        for (int j = 0; j <= n_j; ++j) {
-            if (j < n_j) gate_tiles(j, 0, p.g_first);
-            if (j > 0) {
-                const int m0 = m0_of(j - 1);
+        // per-step row state of the gate tiles (recomputed when the step changes) ...
+        int g_step = -1;
+        bool in_range = false, valid = false;
+        int rl0 = 0, rl1 = 0;
+        float w0 = 1.f, w1 = 0.f;
+        auto gate_tile = [&](int j, int t) {
+            if (g_step != j) {
+                g_step = j;
+                const int m0 = m0_of(j);
                 const int row = m0 + rl;
-                bool valid = false;
-                if (row < (int)p.rows && !(dbg & 8)) valid = p.grid.frame_utt[row / p.steps_per_frame] >= 0;
-                for (int t = 0; t < p.n_t2; ++t) {
-                    uint32_t t0, t1;
-                    const TileDesc td = p.t2[t];
-                    const uint32_t tacc = wait_tile(t0, t1);
-                    // 16-column chunks c0 + k with (c0 + k) % 4 == part: at most four (a tile has at most sixteen)
-                    const int k0 = (part - td.c0) & 3;
-                    float v[4][16];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (k0 + 4 * k < td.nch) tmem_ld16(tacc + 16 * (k0 + 4 * k), v[k]);
-                    release_tile();
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (k0 + 4 * k < td.nch) {
-                            const int n = 16 * (td.c0 + k0 + 4 * k);               // first packed column of the chunk
-                            if (n < p.res_cols) res_chunk<TRACE>(p, es, v[k], n, valid, rl, part, lane);
-                            else skip_chunk(p, v[k], n, (long long)row, valid);
-                        }
-                    end_tile(t0, t1, 1);
+                in_range = row < (int)p.rows && !(dbg & 8);
+                valid = false;
+                rl0 = rl1 = 0;
+                w0 = 1.f; w1 = 0.f;
+                if (in_range) {
+                    const int u = p.grid.frame_utt[row / p.steps_per_frame];
+                    if (u >= 0) {
+                        valid = true;
+                        const int hic = p.grid.utt_end[u] * p.steps_per_frame / p.lin_up;
+                        const int rc0 = m0 / p.lin_up, rc = row / p.lin_up;
+                        const int un = row - rc * p.lin_up;
+                        const int rn = rc + 1 < hic ? rc + 1 : hic - 1;
+                        rl0 = rc - rc0;
+                        rl1 = rn - rc0;
+                        w0 = p.lin_w0[un];
+                        w1 = p.lin_w1[un];
+                    }
                 }
             }
-            if (j < n_j) gate_tiles(j, p.g_first, p.n_t1);
-        }
+            uint32_t t0, t1;
+            const TileDesc td = p.t1[t];
+            const uint32_t tacc = wait_tile(t0, t1);
+            // chunks c0 + k of this tile with (c0 + k) % 4 == part: at most two (a tile has at most eight); eight channels
+            // (8 tanh + 8 sigmoid accumulators) at a time.  The TMEM buffer goes back to the MMA warp when the last eight
+            // are in registers.
+            const int k0 = (part - td.c0) & 3;
+            const int nmy = k0 < td.nch ? (k0 + 4 < td.nch ? 2 : 1) : 0;
+            if (nmy == 0) release_tile();
+            mbar_wait(&cond_full[gt & 1], (gt >> 1) & 1);
+            const float* cbuf = cond_stage + (gt & 1) * cond_buf;
+#pragma unroll 1
+            for (int k = 0; k < nmy; ++k) {
+                const int cl = 32 * (k0 + 4 * k);
+                const uint32_t buf = es.blk % NSTG;
+                float zt[8], zs[8];
+                tmem_ld8(tacc + cl, zt);
+                tmem_ld8(tacc + cl + 16, zs);
+                {
+                    const uint32_t w0c = TRACE ? clk32() : 0u;
+                    mbar_wait(epi_bar(es, BAR_STG_AVAIL + buf), (es.blk / NSTG) & 1);
+                    if (TRACE) es.wait_cyc += clk32() - w0c;
+                }
+                uint8_t* t_hi = stg + buf * STG_BYTES + rl * 128;
+                tmem_ld_wait();
+                if (in_range) gate_half<MODE, GTU>(p, zt, zs, cbuf + rl0 * p.cond_ld + cl, cbuf + rl1 * p.cond_ld + cl, w0, w1, valid, t_hi, rl & 7, part, 0);
+                tmem_ld8(tacc + cl + 8, zt);
+                tmem_ld8(tacc + cl + 24, zs);
+                if (k == nmy - 1) release_tile();
+                else tmem_ld_wait();
+                if (in_range) gate_half<MODE, GTU>(p, zt, zs, cbuf + rl0 * p.cond_ld + cl, cbuf + rl1 * p.cond_ld + cl, w0, w1, valid, t_hi, rl & 7, part, 1);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(epi_bar(es, BAR_STG_READY + buf));
+                ++es.blk;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cond_empty[gt & 1]);
+            end_tile(t0, t1, 0);
+            ++gt;
+        };
+        // ... and of the res tiles
+        int r_step = -1, r_row = 0;
+        bool r_valid = false;
+        auto res_tile = [&](int j, int t) {
+            if (r_step != j) {
+                r_step = j;
+                r_row = m0_of(j - 1) + rl;
+                r_valid = false;
+                if (r_row < (int)p.rows && !(dbg & 8)) r_valid = p.grid.frame_utt[r_row / p.steps_per_frame] >= 0;
+            }
+            const int row = r_row;
+            const bool valid = r_valid;
+            uint32_t t0, t1;
+            const TileDesc td = p.t2[t];
+            const uint32_t tacc = wait_tile(t0, t1);
+            if (t == p.n_t2 - 1 && p.scr_discard) {
+                // The accumulator of the LAST res tile is complete: every activation tile of M tile j - 1 has been read
+                // out of the scratch.  Its rows are dead until the gate stores of step j + 1 re-write them in full: drop
+                // the lines from the L2 instead of letting it write them back (0.64 GB per layer at 64 x 5 s).  Four
+                // threads share a row (128-byte lines `part`, part + 4, ...); the proxy fence orders the discards
+                // before the TMA stores that will re-use the rows (issued after this thread's next staging arrive).
+                uint8_t* srow = p.scr_discard + (size_t)(scr_of(j - 1) + rl) * ((size_t)4 * p.cpad);
+                for (int l = part; l * 128 < 4 * p.cpad; l += 4)
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(srow + l * 128) : "memory");
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
+            // 16-column chunks c0 + k with (c0 + k) % 4 == part: at most four (a tile has at most sixteen)
+            const int k0 = (part - td.c0) & 3;
+            float v[4][16];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k0 + 4 * k < td.nch) tmem_ld16(tacc + 16 * (k0 + 4 * k), v[k]);
+            release_tile();
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k0 + 4 * k < td.nch) {
+                    const int n = 16 * (td.c0 + k0 + 4 * k);               // first packed column of the chunk
+                    if (n < p.res_cols) res_chunk<TRACE, MODE>(p, es, v[k], n, valid, rl, part, lane);
+                    else skip_chunk(p, v[k], n, (long long)row, valid);
+                }
+            end_tile(t0, t1, 1);
+        };
+        for (int j = 0; j <= n_j; ++j)
+            for (int e = 0; e < p.n_seq; ++e) {
+                const int code = p.seq[e], t = code & 15;
+                if (code < 16) {
+                    if (j < n_j) gate_tile(j, t);
+                } else if (j > 0) {
+                    res_tile(j, t);
+                }
+            }
     }
 
     tc_fence_before();
@@ -862,13 +895,30 @@ bool wn_layer_supported(const mbexwn_config_t& c, int cpad, int n_terms, int con
 
 int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::string* error) {
     auto fail = [&](const std::string& m, int code) { if (error) *error = m; return code; };
+    const int mode = a.n_terms == 2 ? 0 : (a.n_terms == 3 ? 2 : 1);
+    const bool gtu = a.gate == GATE_GTU;
+    // instantiations: (trace, pair) | (no trace, pair) | (no trace, clusters of 4), each for the three operand modes and gtu / other gates
+    using Kern = void (*)(LayerParams);
+    static const Kern kerns[3][3][2] = {
+        {{wn_layer_kernel<false, false, 0, false>, wn_layer_kernel<false, false, 0, true>},
+         {wn_layer_kernel<false, false, 1, false>, wn_layer_kernel<false, false, 1, true>},
+         {wn_layer_kernel<false, false, 2, false>, wn_layer_kernel<false, false, 2, true>}},
+        {{wn_layer_kernel<false, true, 0, false>, wn_layer_kernel<false, true, 0, true>},
+         {wn_layer_kernel<false, true, 1, false>, wn_layer_kernel<false, true, 1, true>},
+         {wn_layer_kernel<false, true, 2, false>, wn_layer_kernel<false, true, 2, true>}},
+        {{wn_layer_kernel<true, false, 0, false>, wn_layer_kernel<true, false, 0, true>},
+         {wn_layer_kernel<true, false, 1, false>, wn_layer_kernel<true, false, 1, true>},
+         {wn_layer_kernel<true, false, 2, false>, wn_layer_kernel<true, false, 2, true>}}};
     static unsigned long long attr_set = 0;                    // bit per device: the attribute belongs to the device's function
     int dev = 0;
     cudaGetDevice(&dev);
     if (!((attr_set >> (dev & 63)) & 1ull)) {
-        cudaError_t e = cudaFuncSetAttribute(wn_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(wn_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e != cudaSuccess) return fail(std::string("cudaFuncSetAttribute(layer kernel): ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
+        for (int v = 0; v < 3; ++v)
+            for (int m = 0; m < 3; ++m)
+                for (int g = 0; g < 2; ++g) {
+                    cudaError_t e = cudaFuncSetAttribute(kerns[v][m][g], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+                    if (e != cudaSuccess) return fail(std::string("cudaFuncSetAttribute(layer kernel): ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
+                }
         attr_set |= 1ull << (dev & 63);
     }
     const int cpad = a.cpad;
@@ -922,6 +972,10 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
         return (int)MBEXWN_OK;
     };
     if (a.n2 % 16) return fail("layer kernel: res / skip columns must be a multiple of 16", MBEXWN_ERR_UNSUPPORTED);
+    p.n_seq = 0;
+    for (int t = 0; t < p.g_first; ++t) p.seq[p.n_seq++] = t;
+    for (int t = 0; t < p.n_t2; ++t) p.seq[p.n_seq++] = 16 + t;
+    for (int t = p.g_first; t < p.n_t1; ++t) p.seq[p.n_seq++] = t;
     if ((rc = make_b_maps(p.tm_w1, p.t1, p.n_t1, a.w1, a.n1, a.k1))) return rc;
     if ((rc = make_b_maps(p.tm_w2, p.t2, p.n_t2, a.w2, a.n2, a.k2))) return rc;
 
@@ -1033,15 +1087,7 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
     p.bias2 = a.bias2; p.skip = a.skip; p.skip_ld = a.skip_ld; p.skip_c = a.skip_c; p.res_cols = a.res_cols; p.first = a.first;
     p.grid = a.grid;
     p.range_flag = a.range_flag;
-    p.spin = st.spin;
-    if (st.l2_hints) {
-        p.pol_w = L2_EVICT_LAST; p.pol_h = L2_EVICT_NORMAL; p.pol_rmw = L2_EVICT_FIRST;
-        p.pol_scr_st = L2_EVICT_LAST; p.pol_scr_ld = L2_EVICT_LAST; p.pol_out = L2_EVICT_FIRST;
-        if (st.l2_hints >= 2) p.pol_h = L2_EVICT_LAST;
-        if (st.l2_hints >= 3) p.pol_scr_ld = L2_EVICT_FIRST;       // the scratch rows are dead once the res tiles have read them
-    } else {
-        p.pol_w = p.pol_h = p.pol_rmw = p.pol_scr_st = p.pol_scr_ld = p.pol_out = L2_EVICT_NORMAL;
-    }
+    p.scr_discard = st.discard && (4 * cpad) % 128 == 0 ? reinterpret_cast<uint8_t*>(a.scratch) : nullptr;
     p.trace = reinterpret_cast<uint32_t*>(a.trace);
     p.debug = a.trace ? st.debug : 0;
 
@@ -1068,7 +1114,7 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
             cfg.gridDim = dim3(a.sm_count / 4 * 4);
             attr[0].val.clusterDim.x = 4;
             int n = 0;
-            cudaError_t e = cudaOccupancyMaxActiveClusters(&n, wn_layer_kernel<false>, &cfg);
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kerns[1][mode][gtu ? 1 : 0], &cfg);
             mq = (e == cudaSuccess && n > 0) ? n : -1;
             cudaGetLastError();
         }
@@ -1081,7 +1127,9 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
     cfg.gridDim = dim3(groups * 2);
     attr[0].val.clusterDim.x = p.cluster;
     st.last_cluster = p.cluster;
-    cudaError_t e = a.trace ? cudaLaunchKernelEx(&cfg, wn_layer_kernel<true>, p) : cudaLaunchKernelEx(&cfg, wn_layer_kernel<false>, p);
+    // a trace run of a cluster-of-4 launch uses the untraced kernel (the trace build exists for pairs only)
+    const int variant = p.cluster == 4 ? 1 : (a.trace ? 2 : 0);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kerns[variant][mode][gtu ? 1 : 0], p);
     if (e != cudaSuccess) return fail(std::string("fused layer kernel: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
     return MBEXWN_OK;
 }

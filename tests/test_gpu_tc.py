@@ -229,9 +229,10 @@ def test_fused_layer_clusters_of_four_equal_pairs(engine, speech_setup, precisio
 
 @pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
 def test_fused_layer_interleaved_tile_order_is_bit_identical(engine, speech_setup, precision):
-    """"tc_interleave" = 1 runs the res tiles of M tile j - 1 behind the first gate tile of M tile j (cut at a 64-channel
-    block: 256 + 192 + 192 columns instead of 224 + 224 + 192) so that they find their operands in the L2.  Every output
-    element sums the same products in the same order."""
+    """"tc_interleave" = 1 (default) runs the res tiles of M tile j - 1 behind the first gate tile of M tile j (cut at a
+    64-channel block: 256 + 192 + 192 columns instead of 224 + 224 + 192) so that they find their operands in the L2, and
+    "tc_discard" drops the scratch rows from the L2 once they have been read.  Every output element sums the same products in
+    the same order: all four combinations agree bit for bit."""
     hp, plan, w = speech_setup
     lengths = [400, 150, 1, 400, 37, 400, 400, 260]
     mels = [synthetic_mel(t, 90 + i) for i, t in enumerate(lengths)]
@@ -239,15 +240,18 @@ def test_fused_layer_interleaved_tile_order_is_bit_identical(engine, speech_setu
     engine.set_option("tc_cta_group", 2)
     engine.set_option("tc_fused", 1)
     res = []
-    for il in (0, 1):
+    for il, discard in ((0, 0), (1, 1), (0, 1), (1, 0)):
         engine.set_option("tc_interleave", il)
+        engine.set_option("tc_discard", discard)                   # dead scratch rows dropped from the L2: must not change a bit
         res.append(engine.forward(mels, noise=noise, precision=precision, taps=["wn_out"]))
-    engine.set_option("tc_interleave", 0)
+    engine.set_option("tc_interleave", 1)
+    engine.set_option("tc_discard", 1)
     engine.set_option("tc_cta_group", 1)
     for u in range(len(lengths)):
         assert np.all(np.isfinite(res[1][0][u]))
-        assert np.array_equal(res[0][1]["wn_out"][u], res[1][1]["wn_out"][u]), f"wn_out of utterance {u}"
-        assert np.array_equal(res[0][0][u], res[1][0][u]), f"waveform of utterance {u}"
+        for k in (1, 2, 3):
+            assert np.array_equal(res[0][1]["wn_out"][u], res[k][1]["wn_out"][u]), f"wn_out of utterance {u}, variant {k}"
+            assert np.array_equal(res[0][0][u], res[k][0][u]), f"waveform of utterance {u}, variant {k}"
 
 
 @pytest.mark.parametrize("lengths", [[40], [23, 57, 10, 1, 2]])

@@ -10,6 +10,12 @@ from mbexwn_vocoder_b200.mel_inverter import MELInverter
 inv = MELInverter("SPEECH", device=0, precision="f16f8", allow_synthetic_weights=True)
 eng, plan = inv.model, inv.plan
 eng.set_option("debug_taps", 0)
+for a in sys.argv[2:]:                      # opt=value ... (options a library build does not know are skipped)
+    k, v = a.split("=")
+    try:
+        eng.set_option(k, int(v))
+    except Exception:
+        pass
 mels, noise = bench.synthetic_batch(64, 400, plan.steps_per_frame)
 pb = eng.prepare([400] * 64, precision="f16f8", with_noise=True)
 pb.load(mels, noise)
