@@ -6,15 +6,20 @@
 //   h' = h + rs[:, :C];  wn_out (+)= rs[:, C:]
 //
 // The two-launch version (k_wavenet_tc.cu) writes `act` (4 bytes per element) to HBM and reads it back, and reads the
-// residual stream twice: 3.5 GB per layer at 64 x 5 s against ~1.45 GB that have to move.  Here a CTA pair (cluster of 2,
-// cta_group::2, 256 rows) runs the res tiles of M tile m - 1 right after the gate tiles of M tile m:
+// residual stream twice: 3.5 GB per layer at 64 x 5 s against ~1.5 GB that have to move.  Here a CTA pair (cluster of 2,
+// cta_group::2, 256 rows) runs the res tiles of M tile m - 1 between the gate tiles of M tile m:
 //
-//   accumulator tiles of step j:   G0(m_j) G1(m_j) G2(m_j) | R0(m_j-1) R1(m_j-1)          (C = 320: 256 + 256 + 128 | 256 + 96)
+//   accumulator tiles of step j:   G0(m_j) | R0(m_j-1) R1(m_j-1) | G1(m_j) G2(m_j)      (C = 320: 256 | 176 + 176 | 192 + 192)
 //
+//   ("tc_interleave", default; 0 = G0 G1 G2 | R0 R1 with 224 + 224 + 192).  The tile sequence of a step is a small table
+//   (LayerParams::seq) that every role walks; G0 ends on a 64-channel block so that the staging blocks complete in order.
 // * `act` of an M tile goes through a per-pair, double-buffered scratch in global memory (2 x 256 rows x 4 cpad bytes per
-//   pair, 48 MB for 74 pairs) that is re-written every step and therefore lives in the 126 MB L2: TMA store from the
-//   gate epilogue's staging tiles, TMA load as the A operand of the res tiles one step later.  The skew by one M tile
-//   takes the store -> load round trip and the last gate epilogue off the tensor pipe's critical path.
+//   pair, 48 MB for 74 pairs): TMA store from the gate epilogue's staging tiles, TMA load as the A operand of the res
+//   tiles.  The skew by one M tile takes the store -> load round trip and the last gate epilogue off the tensor pipe's
+//   critical path; with the res tiles right behind G0 of the next M tile the activations (and the residual rows the res
+//   epilogue reads back) are still in the L2 when they are needed -- one whole step of all 74 pairs later they are not
+//   (profiles/README.md, round 2).  Once the res tiles have read them the scratch rows are dropped from the L2 with
+//   discard.global.L2 instead of being written back ("tc_discard").
 // * the residual stream ping-pongs between two buffers (the dilated taps of the neighbouring M tiles must keep reading
 //   the layer's *input*): old block TMA-loaded from h_in into a staging tile, updated in place by the epilogue warps,
 //   TMA-stored to h_out.  Guard rows pass through as the zeros they are.
@@ -30,7 +35,11 @@
 //       tensor pipe as many cycles as a 256-wide one (its smem operand reads bound it) and its box moved 16 KB for 8;
 //   W1 rows are packed [16 tanh channels | their 16 sigmoid partners] per chunk (tc_pack.py), so any split in whole chunks
 //   keeps the gate local to a tile and a chunk is 32 adjacent accumulator columns.
-// * two operand rings: A slabs (3 x 20 KB) and B tiles (4 x 16 KB), each slot with a full / empty mbarrier pair.
+// * two operand rings: A slabs (3 x 20 KB) and B tiles (4 x 16 KB; 5 x 14 KB without the interleaving), each slot with a full /
+//   empty mbarrier pair.  The kernel's speed is the operand bytes in flight over the ~3000-cycle turn-around of a ring slot.
+// * the loops of the control warps are the most sensitive code of the kernel: run-time options inside them (polling waits, L2
+//   cache-hint forms of the TMA instructions, cluster-of-4 bookkeeping) cost 3 - 5 % each and are compiled out (template
+//   parameters QUAD, MODE, GTU) or gone; the epilogue's code size matters too (one copy of the gate / res tile code).
 // * the epilogue warps pull ALL their accumulator columns of a tile into registers first and hand the TMEM buffer back
 //   before any math (tmem_empty right after tcgen05.wait::ld): the tensor pipe never waits for gate / residual math.
 // * staging tiles (2 x 32 KB) are handed around with mbarriers only -- no CTA-wide named barrier in the epilogue: the
