@@ -35,7 +35,7 @@
 //       tensor pipe as many cycles as a 256-wide one (its smem operand reads bound it) and its box moved 16 KB for 8;
 //   W1 rows are packed [16 tanh channels | their 16 sigmoid partners] per chunk (tc_pack.py), so any split in whole chunks
 //   keeps the gate local to a tile and a chunk is 32 adjacent accumulator columns.
-// * two operand rings: A slabs (3 x 20 KB) and B tiles (4 x 16 KB; 5 x 14 KB without the interleaving), each slot with a full /
+// * two operand rings: A slabs (3 x 18 KB) and B tiles (5 x 16 KB; 6 x 14 KB without the interleaving), each slot with a full /
 //   empty mbarrier pair.  The kernel's speed is the operand bytes in flight over the ~3000-cycle turn-around of a ring slot.
 // * the loops of the control warps are the most sensitive code of the kernel: run-time options inside them (polling waits, L2
 //   cache-hint forms of the TMA instructions, cluster-of-4 bookkeeping) cost 3 - 5 % each and are compiled out (template
@@ -77,7 +77,7 @@ constexpr int COND_ROWS = 15;                            // conditioning rows a 
 constexpr int OFF_A = 3072;
 constexpr int SMEM_LIMIT = 232448;
 constexpr int EW = 16, L_THREADS = 128 + 32 * EW;
-constexpr int MAX_TILES = 4, MAX_BLK = 24, MAX_LIN = 32, MAX_PHASE = 3;
+constexpr int MAX_TILES = 4, MAX_BLK = 24, MAX_LIN = 32;
 constexpr int TRACE_SLOTS = 384;                          // tile records per role and CTA
 // barrier slots (uint64) at the start of the dynamic shared memory
 constexpr int BAR_FULL_A = 0, BAR_EMPTY_A = BAR_FULL_A + NA, BAR_FULL_B = BAR_EMPTY_A + NA, BAR_EMPTY_B = BAR_FULL_B + MAX_NB;
@@ -161,10 +161,15 @@ __device__ __forceinline__ uint32_t clk32() {
     return c;
 }
 
-// conditioning rows (+ bias) of a gate tile -> smem stage, by the 32 lanes of warp 3.  Stage column j is packed column
-// n0 + j: chunk j / 32, [16 tanh | 16 sigmoid] channels inside a chunk.
-__device__ __forceinline__ void cond_stage_fill(const LayerParams& p, float* buf, int m0, const TileDesc& td, int lane) {
-    const int w4 = td.w >> 2;
+// conditioning rows (+ bias) of HALF a gate tile (columns 128 half .. + 127: the chunks the epilogue warps work on at the same
+// time) -> smem stage, by the 32 lanes of warp 3.  Stage column j is packed column n0 + 128 half + j: chunk j / 32,
+// [16 tanh | 16 sigmoid] channels inside a chunk.
+constexpr int COND_COLS = 128, COND_LD = COND_COLS + 4;
+__device__ __forceinline__ void cond_stage_fill(const LayerParams& p, float* buf, int m0, const TileDesc& td, int lane, int half) {
+    const int col0 = COND_COLS * half;
+    const int w = td.w - col0 < COND_COLS ? td.w - col0 : COND_COLS;     // columns of this half (<= 0: the tile ends before it)
+    if (w <= 0) return;
+    const int w4 = w >> 2;
     const int rc0 = m0 / p.lin_up;
     const int total = p.cond_rows * w4;
     for (int f0 = lane; f0 < total; f0 += 32 * 4) {
@@ -173,13 +178,14 @@ __device__ __forceinline__ void cond_stage_fill(const LayerParams& p, float* buf
         for (int i = 0; i < 4; ++i) {
             const int f = f0 + 32 * i;
             const int r = f / w4, j = (f - r * w4) * 4;
-            const int within = j & 31;
-            const int ch = 16 * (td.c0 + (j >> 5)) + (within & 15);
+            const int jt = col0 + j;                                     // column inside the tile
+            const int within = jt & 31;
+            const int ch = 16 * (td.c0 + (jt >> 5)) + (within & 15);
             const int src_col = (within >= 16 ? p.c : 0) + ch;
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (f < total && ch < p.c && rc0 + r < p.cond_total) {           // channel padding: C is a multiple of 4
-                b[i] = __ldg(reinterpret_cast<const float4*>(p.bias1 + td.n0 + j));
+                b[i] = __ldg(reinterpret_cast<const float4*>(p.bias1 + td.n0 + jt));
                 v[i] = __ldg(reinterpret_cast<const float4*>(p.cond + (long long)(rc0 + r) * 2 * p.c + src_col));
             }
         }
@@ -188,7 +194,7 @@ __device__ __forceinline__ void cond_stage_fill(const LayerParams& p, float* buf
             const int f = f0 + 32 * i;
             const int r = f / w4, j = (f - r * w4) * 4;
             if (f < total)
-                *reinterpret_cast<float4*>(buf + r * p.cond_ld + j) =
+                *reinterpret_cast<float4*>(buf + r * COND_LD + j) =
                     make_float4(v[i].x + b[i].x, v[i].y + b[i].y, v[i].z + b[i].z, v[i].w + b[i].w);
         }
     }
@@ -380,7 +386,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
     uint8_t* ring_b = smem + p.off_b;
     uint8_t* stg = smem + p.off_stg;
     float* cond_stage = reinterpret_cast<float*>(smem + p.off_cond);
-    const int cond_buf = COND_ROWS * p.cond_ld;                    // floats per conditioning stage
+    constexpr int cond_buf = COND_ROWS * COND_LD;                  // floats per conditioning stage (half a gate tile)
     KEnt* k1 = reinterpret_cast<KEnt*>(smem + OFF_KTAB);
     KEnt* k2 = k1 + MAX_K1;
     // the MMA warp's view of the same loops: {A view offset in 16-byte units, flags} (one spare entry behind each table)
@@ -698,15 +704,17 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
         }
     } else if (warp == 3) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        // ===== conditioning stager: one gate tile ahead of the epilogue warps =====
-        uint32_t gt = 0;
+        // ===== conditioning stager: half a gate tile (the chunks the epilogue warps work on at the same time) ahead of them;
+        // two half-tile stages instead of two tile stages give the B ring one more tile =====
+        uint32_t hs = 0;
         for (int j = 0; j < n_j; ++j)
-            for (int t = 0; t < p.n_t1; ++t, ++gt) {
-                const uint32_t b = gt & 1;
-                mbar_wait(&cond_empty[b], ((gt >> 1) & 1) ^ 1);
-                cond_stage_fill(p, cond_stage + b * cond_buf, m0_of(j), p.t1[t], lane);
-                mbar_arrive(&cond_full[b]);                         // every lane: its own writes are released
-            }
+            for (int t = 0; t < p.n_t1; ++t)
+                for (int half = 0; half < 2; ++half, ++hs) {
+                    const uint32_t b = hs & 1;
+                    mbar_wait(&cond_empty[b], ((hs >> 1) & 1) ^ 1);
+                    cond_stage_fill(p, cond_stage + b * cond_buf, m0_of(j), p.t1[t], lane, half);
+                    mbar_arrive(&cond_full[b]);                     // every lane: its own writes are released
+                }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ===== epilogue warps =====
@@ -780,10 +788,18 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
             const int k0 = (part - td.c0) & 3;
             const int nmy = k0 < td.nch ? (k0 + 4 < td.nch ? 2 : 1) : 0;
             if (nmy == 0) release_tile();
-            mbar_wait(&cond_full[gt & 1], (gt >> 1) & 1);
-            const float* cbuf = cond_stage + (gt & 1) * cond_buf;
 #pragma unroll 1
-            for (int k = 0; k < nmy; ++k) {
+            for (int k = 0; k < 2; ++k) {
+                // half-tile stage 2 gt + k: every warp waits for it and hands it back, with or without a chunk in this half
+                // (a warp that ran ahead could otherwise arrive twice in one phase of `cond_empty`)
+                const uint32_t hs = 2 * gt + k;
+                mbar_wait(&cond_full[hs & 1], (hs >> 1) & 1);
+                if (k >= nmy) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&cond_empty[hs & 1]);
+                    continue;
+                }
+                const float* cbuf = cond_stage + (hs & 1) * cond_buf - COND_COLS * k;     // indexed by the column inside the tile
                 const int cl = 32 * (k0 + 4 * k);
                 const uint32_t buf = es.blk % NSTG;
                 float zt[8], zs[8];
@@ -796,19 +812,20 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                 }
                 uint8_t* t_hi = stg + buf * STG_BYTES + rl * 128;
                 tmem_ld_wait();
-                if (in_range) gate_half<MODE, GTU>(p, zt, zs, cbuf + rl0 * p.cond_ld + cl, cbuf + rl1 * p.cond_ld + cl, w0, w1, valid, t_hi, rl & 7, part, 0);
+                if (in_range) gate_half<MODE, GTU>(p, zt, zs, cbuf + rl0 * COND_LD + cl, cbuf + rl1 * COND_LD + cl, w0, w1, valid, t_hi, rl & 7, part, 0);
                 tmem_ld8(tacc + cl + 8, zt);
                 tmem_ld8(tacc + cl + 24, zs);
                 if (k == nmy - 1) release_tile();
                 else tmem_ld_wait();
-                if (in_range) gate_half<MODE, GTU>(p, zt, zs, cbuf + rl0 * p.cond_ld + cl, cbuf + rl1 * p.cond_ld + cl, w0, w1, valid, t_hi, rl & 7, part, 1);
+                if (in_range) gate_half<MODE, GTU>(p, zt, zs, cbuf + rl0 * COND_LD + cl, cbuf + rl1 * COND_LD + cl, w0, w1, valid, t_hi, rl & 7, part, 1);
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(epi_bar(es, BAR_STG_READY + buf));
+                if (lane == 0) {
+                    mbar_arrive(epi_bar(es, BAR_STG_READY + buf));
+                    mbar_arrive(&cond_empty[hs & 1]);
+                }
                 ++es.blk;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&cond_empty[gt & 1]);
             end_tile(t0, t1, 0);
             ++gt;
         };
@@ -1071,8 +1088,8 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
     for (int t = 0; t < p.n_t2; ++t) if (p.t2[t].w > wmax) wmax = p.t2[t].w;
     p.slab_slot = (slab_rows * 128 + 1023) / 1024 * 1024;
     p.b_slot = ((wmax / 2) * 128 + 1023) / 1024 * 1024;
-    p.cond_ld = w1max + 4;
-    const int cond_bytes = (COND_ROWS * p.cond_ld * 4 + 15) / 16 * 16;
+    p.cond_ld = COND_LD;
+    const int cond_bytes = (COND_ROWS * COND_LD * 4 + 15) / 16 * 16;            // one half-tile stage
     p.n_a = st.n_a >= 2 && st.n_a <= NA ? st.n_a : NA;
     const int fixed = 1024 /* alignment slack */ + OFF_A + p.n_a * p.slab_slot + NSTG * STG_BYTES + 2 * cond_bytes;
     p.n_b = (SMEM_LIMIT - fixed) / p.b_slot;
