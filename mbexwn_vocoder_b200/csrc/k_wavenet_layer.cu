@@ -47,8 +47,10 @@
 //   (`stg_avail`: plain arrive for a gate block, expect_tx + TMA load of the old residual block for a res block) one block
 //   ahead of the epilogue, and signals `act_ready` to the producer once the scratch writes of a step have completed.
 //
-// Warp roles (640 threads): 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator + staging manager, 3 conditioning
-// stager, 4-19 epilogue (TMEM lane quarter = warp % 4, 16-column chunk of every 64-column block = (warp - 4) / 4).
+// Warp roles (640 threads): 0 TMA producer of the B tiles, 1 MMA issuer in the leader CTA / TMA producer of BOTH CTAs' A slabs
+// in the other one (it has no MMAs to issue; the leader's slab goes into the leader's shared memory as a multicast to that one
+// CTA), 2 TMEM allocator + staging manager, 3 conditioning stager, 4-19 epilogue (TMEM lane quarter = warp % 4, 16-column chunk
+// of every 64-column block = (warp - 4) / 4).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -100,7 +102,7 @@ struct KEnt {
 };
 constexpr int MAX_K1 = 64, MAX_K2 = 24;
 constexpr int OFF_KTAB = 512;                            // K tables behind the 512-byte barrier block, in front of the A ring
-static_assert(sizeof(KEnt) == 16 && OFF_KTAB + (MAX_K1 + MAX_K2) * 16 + (MAX_K1 + MAX_K2 + 2) * 8 <= 3072, "K tables");
+static_assert(sizeof(KEnt) == 16 && OFF_KTAB + (MAX_K1 + MAX_K2) * 16 + (MAX_K1 + MAX_K2 + 2) * 8 + MAX_K1 <= 3072, "K tables");
 
 struct TileDesc {
     int n0, w;      // first packed column and width (MMA N) of the tile
@@ -118,6 +120,7 @@ struct alignas(64) LayerParams {
     KEnt k1[MAX_K1];         // K loop of a gate tile
     KEnt k2[MAX_K2];         // K loop of a res tile
     int n_k1, n_k2, n8_1, n8_2;   // entries of a gate / res tile; the first n8 are e4m3 blocks
+    int n_slab1, n_slab2;         // A slabs one gate / res tile starts (KEnt::flags >> 8 numbers them)
     TileDesc t1[MAX_TILES], t2[MAX_TILES];
     int n_t1, n_t2;
     int slab_bytes;          // bytes one gate slab load brings (slab rows x 128)
@@ -392,9 +395,13 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
     // the MMA warp's view of the same loops: {A view offset in 16-byte units, flags} (one spare entry behind each table)
     int2* km1 = reinterpret_cast<int2*>(smem + OFF_KTAB + (MAX_K1 + MAX_K2) * 16);
     int2* km2 = km1 + MAX_K1 + 1;
+    // slab_ent[k] = entry of a gate tile that starts its A slab k; slab_ent[MAX_K1 / 2 + k] the same for a res tile
+    uint8_t* slab_ent = reinterpret_cast<uint8_t*>(km2 + MAX_K2 + 1);
     for (int i = threadIdx.x; i < MAX_K1 + MAX_K2; i += L_THREADS) {
         const KEnt& e = i < MAX_K1 ? p.k1[i] : p.k2[i - MAX_K1];
-        (i < MAX_K1 ? km1[i] : km2[i - MAX_K1]) = make_int2((int)e.a_view * 8, e.flags);
+        (i < MAX_K1 ? km1[i] : km2[i - MAX_K1]) = make_int2((int)e.a_view * 8, e.flags & 0xff);
+        const bool live = i < MAX_K1 ? i < p.n_k1 : i - MAX_K1 < p.n_k2;
+        if (live && (e.flags & KF_NEW_SLAB)) slab_ent[(i < MAX_K1 ? 0 : MAX_K1 / 2) + (e.flags >> 8)] = (uint8_t)(i < MAX_K1 ? i : i - MAX_K1);
     }
     for (int i = threadIdx.x; i < (MAX_K1 + MAX_K2) * 4; i += L_THREADS) {
         const int e = i >> 2, w = i & 3;
@@ -440,7 +447,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
             mbar_init(&tmem_empty[s], 2 * EW);
             mbar_init(&cond_full[s], 32);
             mbar_init(&cond_empty[s], EW);
-            mbar_init(&act_ready[s], 1);
+            mbar_init(&act_ready[s], 2);                        // both CTAs' managers (the A producer of the pair runs in the non-leader CTA)
         }
         for (int s = 0; s < NSTG; ++s) { mbar_init(&stg_avail[s], 1); mbar_init(&stg_ready[s], EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -459,31 +466,19 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
 
     if (warp == 0) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        // ===== TMA producer: the whole warp walks the K loops, one elected lane issues =====
+        // ===== TMA producer of the B tiles (weights): the whole warp walks the K loops, one elected lane issues.  One
+        // cp.async.bulk.tensor costs its issuing thread ~270 cycles whatever the box size; a K block of a res tile (352 MMA cycles)
+        // needs an A tile and a B tile, so the A operand has a producer of its own: warp 1 of the NON-leader CTA, which has no
+        // MMAs to issue, loads the A slabs / tiles of both CTAs of the pair =====
         // In a cluster of 4 the two pairs take turns with the B tiles: the CTAs of pair (entry & 1) load their half of the
         // tile and multicast it to the CTA of the same rank in the other pair.  A slot is free when BOTH pairs have consumed
         // it (empty_b counts two commits, each multicast to the four CTAs); every leader arms its own full barrier, whoever
         // loads -- the bytes of the other pair's load may be counted before that (the tx count goes negative meanwhile).
-        uint32_t sa = 0, pha = 0, sb = 0, phb = 0, tile_it = 0, ent = 0;     // ring slots and phase parities, B tiles so far
-        const uint32_t lfa0 = map_to_cta(smem_u32(&full_a[0]), lead_rank), lfb0 = map_to_cta(smem_u32(&full_b[0]), lead_rank);
+        uint32_t sb = 0, phb = 0, tile_it = 0, ent = 0;            // B ring slot and phase parity, B tiles so far
+        const uint32_t lfb0 = map_to_cta(smem_u32(&full_b[0]), lead_rank);
         const uint32_t fb0_mc = smem_u32(&full_b[0]) & 0xFEFFFFFFu;  // multicast form: this offset in the even CTA of each destination's pair
         const uint16_t mc_mask = (uint16_t)(0x5u << rank);
         uint32_t wait_cyc = 0;
-        auto load_a = [&](const CUtensorMap* tma, uint32_t a_bytes, int col, int row) {
-            const uint32_t t0 = TRACE ? clk32() : 0u;
-            mbar_wait(&empty_a[sa], pha ^ 1);
-            if (TRACE) wait_cyc += clk32() - t0;
-            if (elect_one()) {
-                if (dbg & 2) {
-                    if (leader) mbar_arrive(&full_a[sa]);
-                } else {
-                    if (leader) mbar_expect_tx(&full_a[sa], 2 * a_bytes);
-                    tma_load_2d_2sm(tma, lfa0 + sa * 8, ring_a + sa * p.slab_slot, col, row);
-                }
-            }
-            __syncwarp();
-            if (++sa == (uint32_t)p.n_a) { sa = 0; pha ^= 1; }
-        };
         auto load_b = [&](const CUtensorMap* tmb, uint32_t b_bytes, int col, int row) {
             const bool mine = !quad || (int)(ent & 1u) == pair_in_cluster;
             ++ent;
@@ -504,15 +499,13 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
             }
             if (++sb == (uint32_t)p.n_b) { sb = 0; phb ^= 1; }
         };
-        auto load_tile = [&](const CUtensorMap* tma, uint32_t a_bytes, const CUtensorMap* tmb, uint32_t b_bytes, const KEnt* ke, int n,
-                             int a_row0, int b_row) {
+        auto load_tile = [&](const CUtensorMap* tmb, uint32_t b_bytes, const KEnt* ke, int n, int b_row) {
             wait_cyc = 0;
-            int4 e = *reinterpret_cast<const int4*>(ke);            // {a_col, a_row | a_view << 16, b_col, flags}
+            int b_col = ke[0].b_col;
             for (int i = 0; i < n; ++i) {
-                const int4 cur = e;
-                if (i + 1 < n) e = *reinterpret_cast<const int4*>(ke + i + 1);
-                if (cur.w & KF_NEW_SLAB) load_a(tma, a_bytes, cur.x, a_row0 + (int)(short)(cur.y & 0xffff));
-                load_b(tmb, b_bytes, cur.z, b_row);
+                const int col = b_col;
+                if (i + 1 < n) b_col = ke[i + 1].b_col;
+                load_b(tmb, b_bytes, col, b_row);
             }
             if (TRACE && lane == 0 && tile_it < TRACE_SLOTS) {
                 uint32_t* t = trc + (0 * TRACE_SLOTS + tile_it) * 4;
@@ -520,26 +513,15 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
             }
             ++tile_it;
         };
-        for (int j = 0; j <= n_j; ++j) {
-            bool act_seen = false;
+        for (int j = 0; j <= n_j; ++j)
             for (int e = 0; e < p.n_seq; ++e) {
                 const int code = p.seq[e], t = code & 15;
                 if (code < 16) {
-                    if (j < n_j)
-                        load_tile(&p.tm_hs, (uint32_t)p.slab_bytes, &p.tm_w1[p.t1[t].bmap], (uint32_t)(p.t1[t].w >> 1) * 128u, k1, p.n_k1, m0_of(j),
-                                  p.t1[t].n0 + rank * (p.t1[t].w >> 1));
+                    if (j < n_j) load_tile(&p.tm_w1[p.t1[t].bmap], (uint32_t)(p.t1[t].w >> 1) * 128u, k1, p.n_k1, p.t1[t].n0 + rank * (p.t1[t].w >> 1));
                 } else if (j > 0) {
-                    if (!act_seen) {
-                        // the act of M tile j - 1 must have landed in the scratch (writes of the async proxy, completed by the manager)
-                        mbar_wait(&act_ready[(j - 1) & 1], ((j - 1) >> 1) & 1);
-                        asm volatile("fence.proxy.async;" ::: "memory");
-                        act_seen = true;
-                    }
-                    load_tile(&p.tm_scr, (uint32_t)(TILE_M * 128), &p.tm_w2[p.t2[t].bmap], (uint32_t)(p.t2[t].w >> 1) * 128u, k2, p.n_k2, scr_of(j - 1),
-                              p.t2[t].n0 + rank * (p.t2[t].w >> 1));
+                    load_tile(&p.tm_w2[p.t2[t].bmap], (uint32_t)(p.t2[t].w >> 1) * 128u, k2, p.n_k2, p.t2[t].n0 + rank * (p.t2[t].w >> 1));
                 }
             }
-        }
     } else if (warp == 1) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ===== MMA issuer (leader CTA): the whole warp walks the K loops, one elected lane issues =====
@@ -631,12 +613,63 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                     const bool gate = code < 16;
                     if (gate ? j < n_j : j > 0) mma_tile(gate ? p.t1[t].w : p.t2[t].w, gate ? km1 : km2, gate ? p.n8_1 : p.n8_2, gate ? p.n_k1 : p.n_k2);
                 }
+        } else {
+            // ===== A producer of the pair (non-leader CTA): lane 0 loads this CTA's slab, lane 1 the leader's -- into the leader's
+            // shared memory, as a multicast to that one CTA -- both reporting to the leader's full barrier.  This CTA's empty
+            // barriers see the leader's commits (multicast to the pair), so one wait covers both slots. =====
+            uint32_t sa = 0, pha = 0;
+            const uint32_t lfa0 = map_to_cta(smem_u32(&full_a[0]), lead_rank);
+            const uint32_t fa0_mc = smem_u32(&full_a[0]) & 0xFEFFFFFFu;
+            const uint16_t lead_mask = (uint16_t)(1u << lead_rank);
+            auto load_slabs = [&](const CUtensorMap* tma, uint32_t a_bytes, const KEnt* ke, const uint8_t* first, int n_slabs, int a_row0) {
+                for (int k = 0; k < n_slabs; ++k) {
+                    const int4 ent = *reinterpret_cast<const int4*>(ke + first[k]);   // {a_col, a_row | a_view << 16, b_col, flags}
+                    const int row = a_row0 + (int)(short)(ent.y & 0xffff);
+                    mbar_wait(&empty_a[sa], pha ^ 1);
+                    uint8_t* dst = ring_a + sa * p.slab_slot;
+                    if (dbg & 2) {
+                        if (lane == 0) { mbar_expect_tx_cluster(lfa0 + sa * 8, 0); }
+                    } else if (lane == 0) {
+                        mbar_expect_tx_cluster(lfa0 + sa * 8, 2 * a_bytes);
+                        tma_load_2d_2sm(tma, lfa0 + sa * 8, dst, ent.x, row);
+                    } else if (lane == 1) {
+                        tma_load_2d_2sm_mc(tma, fa0_mc + sa * 8, dst, ent.x, row - TILE_M, lead_mask, L2_EVICT_NORMAL);
+                    }
+                    __syncwarp();
+                    if (++sa == (uint32_t)p.n_a) { sa = 0; pha ^= 1; }
+                }
+            };
+            for (int j = 0; j <= n_j; ++j) {
+                bool act_seen = false;
+                for (int e = 0; e < p.n_seq; ++e) {
+                    const int code = p.seq[e];
+                    if (code < 16) {
+                        if (j < n_j) load_slabs(&p.tm_hs, (uint32_t)p.slab_bytes, k1, slab_ent, p.n_slab1, m0_of(j));
+                    } else if (j > 0) {
+                        if (!act_seen) {
+                            // the act of M tile j - 1 must have landed in the scratch: both CTAs' managers have completed their
+                            // TMA stores and arrived here
+                            mbar_wait(&act_ready[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                            asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                            asm volatile("fence.proxy.async;" ::: "memory");
+                            act_seen = true;
+                        }
+                        load_slabs(&p.tm_scr, (uint32_t)(TILE_M * 128), k2, slab_ent + MAX_K1 / 2, p.n_slab2, scr_of(j - 1));
+                    }
+                }
+            }
         }
     } else if (warp == 2) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ===== staging manager: one thread recycles the staging tiles ahead of the epilogue and issues every store =====
         if (lane == 0) {
             const int n_blk = p.n_gate_blk + p.n_res_blk;
+            // `act_ready` lives in the non-leader CTA (the pair's A producer): the leader's manager arrives there remotely
+            const uint32_t act_remote = map_to_cta(smem_u32(&act_ready[0]), lead_rank + 1);
+            auto act_arrive = [&](int b) {
+                if (leader) mbar_arrive_cluster_release(act_remote + b * 8);
+                else mbar_arrive(&act_ready[b]);
+            };
             int pj = 0, pe = -1, sj = 0, se = -1;                   // prepare / store cursors over (step, block-of-step)
             // position e of a step: gate blocks 0 .. nb0 - 1, the res blocks, the other gate blocks
             auto is_gate = [&](int e) { return e < p.nb0 || e >= p.nb0 + p.n_res_blk; };
@@ -673,7 +706,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                     // scratch writes of a finished step: complete them (not just the smem reads) and tell the producer
                     tma_store_wait_all();
                     asm volatile("fence.proxy.async;" ::: "memory");
-                    mbar_arrive(&act_ready[pending_act & 1]);
+                    act_arrive(pending_act & 1);
                     pending_act = -1;
                 }
                 const uint32_t buf = sb % NSTG;
@@ -699,7 +732,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
             tma_store_wait_all();                                   // staging tiles and global writes outlive the loop
             if (pending_act >= 0) {
                 asm volatile("fence.proxy.async;" ::: "memory");
-                mbar_arrive(&act_ready[pending_act & 1]);
+                act_arrive(pending_act & 1);
             }
         }
     } else if (warp == 3) {
@@ -923,18 +956,15 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
     auto fail = [&](const std::string& m, int code) { if (error) *error = m; return code; };
     const int mode = a.n_terms == 2 ? 0 : (a.n_terms == 3 ? 2 : 1);
     const bool gtu = a.gate == GATE_GTU;
-    // instantiations: (trace, pair) | (no trace, pair) | (no trace, clusters of 4), each for the three operand modes and gtu / other gates
+    // instantiations: pairs for the three operand modes and gtu / other gates; clusters of 4 and the trace build for the gtu gate only
+    // (another gate type runs the plain pair kernel)
     using Kern = void (*)(LayerParams);
     static const Kern kerns[3][3][2] = {
         {{wn_layer_kernel<false, false, 0, false>, wn_layer_kernel<false, false, 0, true>},
          {wn_layer_kernel<false, false, 1, false>, wn_layer_kernel<false, false, 1, true>},
          {wn_layer_kernel<false, false, 2, false>, wn_layer_kernel<false, false, 2, true>}},
-        {{wn_layer_kernel<false, true, 0, false>, wn_layer_kernel<false, true, 0, true>},
-         {wn_layer_kernel<false, true, 1, false>, wn_layer_kernel<false, true, 1, true>},
-         {wn_layer_kernel<false, true, 2, false>, wn_layer_kernel<false, true, 2, true>}},
-        {{wn_layer_kernel<true, false, 0, false>, wn_layer_kernel<true, false, 0, true>},
-         {wn_layer_kernel<true, false, 1, false>, wn_layer_kernel<true, false, 1, true>},
-         {wn_layer_kernel<true, false, 2, false>, wn_layer_kernel<true, false, 2, true>}}};
+        {{nullptr, wn_layer_kernel<false, true, 0, true>}, {nullptr, wn_layer_kernel<false, true, 1, true>}, {nullptr, wn_layer_kernel<false, true, 2, true>}},
+        {{nullptr, wn_layer_kernel<true, false, 0, true>}, {nullptr, wn_layer_kernel<true, false, 1, true>}, {nullptr, wn_layer_kernel<true, false, 2, true>}}};
     static unsigned long long attr_set = 0;                    // bit per device: the attribute belongs to the device's function
     int dev = 0;
     cudaGetDevice(&dev);
@@ -942,6 +972,7 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
         for (int v = 0; v < 3; ++v)
             for (int m = 0; m < 3; ++m)
                 for (int g = 0; g < 2; ++g) {
+                    if (!kerns[v][m][g]) continue;
                     cudaError_t e = cudaFuncSetAttribute(kerns[v][m][g], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
                     if (e != cudaSuccess) return fail(std::string("cudaFuncSetAttribute(layer kernel): ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
                 }
@@ -1053,6 +1084,9 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
         p.k1[0].flags |= KF_OVERWRITE;
     }
     p.n_k1 = n;
+    p.n_slab1 = 0;
+    for (int i = 0; i < p.n_k1; ++i)
+        if (p.k1[i].flags & KF_NEW_SLAB) p.k1[i].flags |= (p.n_slab1++) << 8;
     n = 0;
     auto res_group = [&](int a_off, const int* b_offs, int nb, int kflags) {
         for (int cb = 0; cb < ncb; ++cb)
@@ -1081,6 +1115,9 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
         p.k2[0].flags |= KF_OVERWRITE;
     }
     p.n_k2 = n;
+    p.n_slab2 = 0;
+    for (int i = 0; i < p.n_k2; ++i)
+        if (p.k2[i].flags & KF_NEW_SLAB) p.k2[i].flags |= (p.n_slab2++) << 8;
 
     // shared memory carve-up: barriers, A slab ring, B tile ring (as deep as the rest allows), staging blocks, conditioning stages
     int wmax = 0, w1max = 0;
@@ -1133,7 +1170,7 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
     // Clusters of 4 when every pair has work for several steps.  How many of them the device holds at once depends on the
     // GPC sizes (a cluster lives inside one GPC), so ask: the persistent schedule needs all of them resident.
     p.cluster = 2;
-    if (st.cluster == 4 && p.tiles_mg >= 2 * groups_max) {
+    if (st.cluster == 4 && gtu && p.tiles_mg >= 2 * groups_max) {
         static int max_quads[64] = {0};
         int& mq = max_quads[dev & 63];
         if (mq == 0) {
@@ -1154,7 +1191,7 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
     attr[0].val.clusterDim.x = p.cluster;
     st.last_cluster = p.cluster;
     // a trace run of a cluster-of-4 launch uses the untraced kernel (the trace build exists for pairs only)
-    const int variant = p.cluster == 4 ? 1 : (a.trace ? 2 : 0);
+    const int variant = p.cluster == 4 ? 1 : (a.trace && gtu ? 2 : 0);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kerns[variant][mode][gtu ? 1 : 0], p);
     if (e != cudaSuccess) return fail(std::string("fused layer kernel: ") + cudaGetErrorString(e), MBEXWN_ERR_CUDA);
     return MBEXWN_OK;

@@ -119,6 +119,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     // tcgen05.fence::before_thread_sync; a .release.cluster arrive costs MEMBAR.ALL.GPU + ERRBAR per tile and warp
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// arrive.expect_tx on a barrier of another CTA of the cluster (cluster address from map_to_cta)
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+// arrive on a barrier of another CTA, ordering this thread's earlier writes for the waiter (cluster scope)
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
