@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-T=r03k
+T=r03n
 timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -8 > gpurun_out/${T}_pytest_gpu.log
 cat gpurun_out/${T}_pytest_gpu.log | tail -4
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
@@ -16,7 +16,7 @@ python - <<'PY'
 import json
 for f in ('bench','bench_unfused','bench_config3','bench_config1','bench_ref'):
     try:
-        d=json.load(open(f'gpurun_out/r03k_{f}.json'))
+        d=json.load(open(f'gpurun_out/r03n_{f}.json'))
         print(f, 'ms/step', d.get('ms_per_step'), 'value', d['value'], 'e2e', d['e2e']['value'], 'frac', d.get('roofline',{}).get('frac'), 'traffic', d.get('roofline',{}).get('traffic'), d.get('clocks'))
         c=d.get('config4'); 
         if c: print('  config4', c.get('value'), c.get('wall_s'), c.get('per_rank'))
