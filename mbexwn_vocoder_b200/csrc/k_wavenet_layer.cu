@@ -168,6 +168,7 @@ __device__ __forceinline__ uint32_t clk32() {
 // time) -> smem stage, by the 32 lanes of warp 3.  Stage column j is packed column n0 + 128 half + j: chunk j / 32,
 // [16 tanh | 16 sigmoid] channels inside a chunk.
 constexpr int COND_COLS = 128, COND_LD = COND_COLS + 4;
+constexpr int NCOND = 2;                                 // half-tile conditioning stages (1 would give the B ring 8 KB more, but the stager can then not run ahead: measured slower)
 __device__ __forceinline__ void cond_stage_fill(const LayerParams& p, float* buf, int m0, const TileDesc& td, int lane, int half) {
     const int col0 = COND_COLS * half;
     const int w = td.w - col0 < COND_COLS ? td.w - col0 : COND_COLS;     // columns of this half (<= 0: the tile ends before it)
@@ -743,8 +744,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
         for (int j = 0; j < n_j; ++j)
             for (int t = 0; t < p.n_t1; ++t)
                 for (int half = 0; half < 2; ++half, ++hs) {
-                    const uint32_t b = hs & 1;
-                    mbar_wait(&cond_empty[b], ((hs >> 1) & 1) ^ 1);
+                    const uint32_t b = hs % NCOND;
+                    mbar_wait(&cond_empty[b], ((hs / NCOND) & 1) ^ 1);
                     cond_stage_fill(p, cond_stage + b * cond_buf, m0_of(j), p.t1[t], lane, half);
                     mbar_arrive(&cond_full[b]);                     // every lane: its own writes are released
                 }
@@ -826,13 +827,13 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                 // half-tile stage 2 gt + k: every warp waits for it and hands it back, with or without a chunk in this half
                 // (a warp that ran ahead could otherwise arrive twice in one phase of `cond_empty`)
                 const uint32_t hs = 2 * gt + k;
-                mbar_wait(&cond_full[hs & 1], (hs >> 1) & 1);
+                mbar_wait(&cond_full[hs % NCOND], (hs / NCOND) & 1);
                 if (k >= nmy) {
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&cond_empty[hs & 1]);
+                    if (lane == 0) mbar_arrive(&cond_empty[hs % NCOND]);
                     continue;
                 }
-                const float* cbuf = cond_stage + (hs & 1) * cond_buf - COND_COLS * k;     // indexed by the column inside the tile
+                const float* cbuf = cond_stage + (hs % NCOND) * cond_buf - COND_COLS * k;     // indexed by the column inside the tile
                 const int cl = 32 * (k0 + 4 * k);
                 const uint32_t buf = es.blk % NSTG;
                 float zt[8], zs[8];
@@ -855,7 +856,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(epi_bar(es, BAR_STG_READY + buf));
-                    mbar_arrive(&cond_empty[hs & 1]);
+                    mbar_arrive(&cond_empty[hs % NCOND]);
                 }
                 ++es.blk;
             }
@@ -1128,14 +1129,14 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
     p.cond_ld = COND_LD;
     const int cond_bytes = (COND_ROWS * COND_LD * 4 + 15) / 16 * 16;            // one half-tile stage
     p.n_a = st.n_a >= 2 && st.n_a <= NA ? st.n_a : NA;
-    const int fixed = 1024 /* alignment slack */ + OFF_A + p.n_a * p.slab_slot + NSTG * STG_BYTES + 2 * cond_bytes;
+    const int fixed = 1024 /* alignment slack */ + OFF_A + p.n_a * p.slab_slot + NSTG * STG_BYTES + NCOND * cond_bytes;
     p.n_b = (SMEM_LIMIT - fixed) / p.b_slot;
     if (p.n_b > MAX_NB) p.n_b = MAX_NB;
     if (p.n_b < 3) return fail("layer kernel: shared memory too small for the operand rings", MBEXWN_ERR_UNSUPPORTED);
     p.off_b = OFF_A + p.n_a * p.slab_slot;
     p.off_stg = p.off_b + p.n_b * p.b_slot;
     p.off_cond = p.off_stg + NSTG * STG_BYTES;
-    const int smem_bytes = 1024 + p.off_cond + 2 * cond_bytes;
+    const int smem_bytes = 1024 + p.off_cond + NCOND * cond_bytes;
     p.f16 = a.n_terms == 2;
     p.rows = a.rows;
     const int tiles_m = (int)((a.rows + TILE_M - 1) / TILE_M);
