@@ -73,9 +73,15 @@ def _copy_all(pool, jobs):
     list(pool.map(part, range(n)))
 
 
+def shard_capacity(lengths: Sequence[int], ids: Sequence[int], halo: int, max_batch_frames: int):
+    """(padded frames, utterances) of the largest batch plan_batches cuts out of `ids`: the capacity of the two buffer sets."""
+    batches = plan_batches(lengths, list(ids), halo, max_batch_frames)
+    return (max(sum(int(lengths[i]) + halo for i in b) + halo for b in batches), max(len(b) for b in batches))
+
+
 def run_shard(inv, get_mel: Callable[[int], np.ndarray], lengths: Sequence[int], ids: Sequence[int], out,
               max_batch_frames: int = 32768, seed: int = 0, precision: Optional[str] = None, keep: bool = True,
-              host_threads: int = 4) -> ShardStats:
+              host_threads: int = 4, capacity=None) -> ShardStats:
     """Synthesize the utterances `ids` on `inv`'s GPU: pipelined batches, waveforms gathered on the host.
 
     get_mel(i) returns the (T_i, n_mel) float32 mel of utterance i (a view is fine: it is copied into the pinned grid).
@@ -83,7 +89,8 @@ def run_shard(inv, get_mel: Callable[[int], np.ndarray], lengths: Sequence[int],
     view of the pinned grid is to be copied into (a caller that owns one big result buffer returns its slice), or None after
     consuming the view itself.
     keep = False drops the waveforms after touching them (warm-up).
-    host_threads: threads that scatter the mels into / gather the waveforms out of the pinned grids (memcpy bound)."""
+    host_threads: threads that scatter the mels into / gather the waveforms out of the pinned grids (memcpy bound).
+    capacity: (padded frames, utterances) to size the two buffer sets for, if larger than this call needs (shard_capacity)."""
     import torch
     eng, plan = inv.model, inv.plan
     precision = precision or inv.precision
@@ -95,6 +102,8 @@ def run_shard(inv, get_mel: Callable[[int], np.ndarray], lengths: Sequence[int],
     batches = plan_batches(lengths, ids, eng.halo, max_batch_frames)
     cap_frames = max(sum(int(lengths[i]) + eng.halo for i in b) + eng.halo for b in batches)
     cap_utts = max(len(b) for b in batches)
+    if capacity is not None:                        # buffer sets sized for a larger set (a warm-up that allocates for the real run)
+        cap_frames, cap_utts = max(cap_frames, int(capacity[0])), max(cap_utts, int(capacity[1]))
     key = ("multi_gpu", precision, cap_frames, cap_utts)
     slots = getattr(eng, "_shard_slots", {}).get(key)
     if slots is None:
