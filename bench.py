@@ -60,8 +60,12 @@ CONFIG4 = {"model": "SING", "utts": 8192, "min_frames": 80, "max_frames": 2400, 
 
 def config_dict(args, world, batch, frames, desc, extra=None):
     """`config` of the JSON line: identical for the own arm and the reference arm (the driver compares them)."""
+    # residual stream of one WaveNet layer: 20 rows per frame x 4 * 320 bytes -- what every layer reads and re-writes
+    stream_mb = batch * frames * 20 * 1280 / 1e6
     c = {"workload": f"{args.workload}: {desc}", "per_gpu_batch": batch, "frames": frames, "precision": args.precision,
-         "parallelism": f"dp{world} (independent utterances, no collective)"}
+         "parallelism": f"dp{world} (independent utterances, no collective)",
+         "l2": (f"no flush between steps: each WaveNet layer streams {stream_mb:.0f} MB in and out, "
+                + ("several times the 126 MB L2" if stream_mb > 2 * 126 else "which fits the 126 MB L2 -- an L2-warm figure"))}
     if extra:
         c.update(extra)
     return c
