@@ -30,6 +30,18 @@ VARIANTS = {"causal": {"force_causal": True},
                            "pp_mod_subnet_channel_factors": [0.25, 0.5]}}
 
 
+def _wavenet_with(**kw):
+    sub = dict(yaml.safe_load(open(get_config_file("SPEECH")))["mbexwn_config"]["pp_mod_subnet"])
+    sub.update(kw)
+    return {"pp_mod_subnet": sub}
+
+
+# the other gated units of WaveNetAE (custom_AE_layers.py:273-304): the fused layer kernel compiles tanh * sigmoid in and keeps
+# a run-time switch for these
+VARIANTS.update({"gate_gfu": _wavenet_with(activation="gfu"), "gate_gsu": _wavenet_with(activation="gsu"),
+                 "gate_glu": _wavenet_with(activation="glu")})
+
+
 def _hp(extra):
     hp = read_config(get_config_file("SPEECH"))
     hp["mbexwn_config"].update(extra)
