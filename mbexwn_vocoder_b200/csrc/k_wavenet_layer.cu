@@ -835,6 +835,9 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                 }
                 const float* cbuf = cond_stage + (hs % NCOND) * cond_buf - COND_COLS * k;     // indexed by the column inside the tile
                 const int cl = 32 * (k0 + 4 * k);
+                // chunks behind the tile's MMA width are channel padding that is not computed at all (C = 340: 22 of the 24 chunks
+                // of cpad = 384): their warps write the zeros the staging block needs and nothing else
+                const bool live = valid && cl < td.w;
                 const uint32_t buf = es.blk % NSTG;
                 float zt[8], zs[8];
                 tmem_ld8(tacc + cl, zt);
@@ -846,12 +849,12 @@ __global__ void __launch_bounds__(L_THREADS, 1) wn_layer_kernel(const __grid_con
                 }
                 uint8_t* t_hi = stg + buf * STG_BYTES + rl * 128;
                 tmem_ld_wait();
-                if (in_range) gate_half<MODE, GTU>(p, zt, zs, cbuf + rl0 * COND_LD + cl, cbuf + rl1 * COND_LD + cl, w0, w1, valid, t_hi, rl & 7, part, 0);
+                if (in_range) gate_half<MODE, GTU>(p, zt, zs, cbuf + rl0 * COND_LD + cl, cbuf + rl1 * COND_LD + cl, w0, w1, live, t_hi, rl & 7, part, 0);
                 tmem_ld8(tacc + cl + 8, zt);
                 tmem_ld8(tacc + cl + 24, zs);
                 if (k == nmy - 1) release_tile();
                 else tmem_ld_wait();
-                if (in_range) gate_half<MODE, GTU>(p, zt, zs, cbuf + rl0 * COND_LD + cl, cbuf + rl1 * COND_LD + cl, w0, w1, valid, t_hi, rl & 7, part, 1);
+                if (in_range) gate_half<MODE, GTU>(p, zt, zs, cbuf + rl0 * COND_LD + cl, cbuf + rl1 * COND_LD + cl, w0, w1, live, t_hi, rl & 7, part, 1);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
@@ -1030,6 +1033,13 @@ int wn_layer_forward(WnTcState& st, const WnLayerArgs& a, cudaStream_t s, std::s
         return (int)MBEXWN_OK;
     };
     if (a.n2 % 16) return fail("layer kernel: res / skip columns must be a multiple of 16", MBEXWN_ERR_UNSUPPORTED);
+    // channel padding beyond the last 16-channel chunk that holds a real channel is not computed: the last gate tile's MMA / B box
+    // is that much narrower (C = 340: 704 instead of 768 gate columns), its epilogue still covers the chunks of the whole staging block
+    {
+        const int phantom = cpad / 16 - (a.c + 15) / 16;
+        TileDesc& last = p.t1[p.n_t1 - 1];
+        if (phantom > 0 && phantom < last.nch) last.w -= 32 * phantom;
+    }
     p.n_seq = 0;
     for (int t = 0; t < p.g_first; ++t) p.seq[p.n_seq++] = t;
     for (int t = 0; t < p.n_t2; ++t) p.seq[p.n_seq++] = 16 + t;
